@@ -1,0 +1,197 @@
+/* riqn_b200.h -- C-ABI of the B200-native Rainbow-IQN Ape-X learner hot path.
+ *
+ * The reference (valeoai/rainbow-iqn-apex) is pure Python/PyTorch and has no FFI or operator registry:
+ * its boundary for this path is the Python class surface Agent / Learner / DQN / NoisyLinear /
+ * ReplayRedisMemory.  This header is the boundary a native replacement exports
+ * underneath that surface; rainbow_iqn_apex_b200/*.py binds it with ctypes and
+ * re-creates the reference classes on top.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a cudaError_t value; nothing is allocated inside, all
+ *     buffers are caller-owned DEVICE pointers unless stated; work is enqueued on `stream`
+ *     (a cudaStream_t passed as void*) and is stream-ordered, re-entrant per stream;
+ *   - fp32 tensors row-major; head rows are quantile-major, r = q * batch + b
+ *     (reference rainbowiqn/model.py:149, compute_loss_iqn.py:238-310);
+ *   - `long long*` index buffers are int64 like the reference's torch.int64 / numpy int64.
+ *
+ * Each entry point cites the reference code it replaces (paths relative to /root/reference).
+ */
+#ifndef RIQN_B200_H
+#define RIQN_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RIQN_B200_ABI_VERSION 1
+
+/* Library / build identification.  Returns RIQN_B200_ABI_VERSION. */
+int riqn_version(void);
+/* 1 if the running device is compute capability 10.x (sm_100a cubins only), else 0; <0 on CUDA error. */
+int riqn_device_ok(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Conv trunk                                     replaces nn.Conv2d x3 + ReLU, rainbowiqn/model.py:65-67,115-118
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct riqn_conv_geom {
+  int B, Cin, H, W;          /* input  (B, Cin, H, W), NCHW                                     */
+  int Cout, KH, KW;          /* weight (Cout, Cin, KH, KW)                                       */
+  int stride, pad;
+  int OH, OW;                /* output (B, Cout, OH, OW), NCHW (flattens C-major, model.py:118)  */
+  long in_bstride;           /* elements between consecutive samples of the input (>= Cin*H*W):
+                                lets conv1 read states / next_states as strided views of the
+                                (B, history+n, 84, 84) replay window                             */
+} riqn_conv_geom;
+
+/* out = relu(conv(in) + bias).  `in` is uint8 frames (x/255 applied on the fly, reproducing
+ * redis_memory.py:527-536) when in_is_u8 != 0, else fp32.  `col` (B*OH*OW, Cin*KH*KW) is workspace
+ * that riqn_conv_bwd re-uses. */
+int riqn_conv_fwd(const riqn_conv_geom* g, const void* in, int in_is_u8, const float* w, const float* bias,
+                  float* col, float* out, void* stream);
+/* Backward of the above: dout is dL/d(out) (post-ReLU), `out` the forward output (ReLU mask).
+ * dw/dbias are ACCUMULATED into (zero them first, like zero_grad -- learner.py:22); din (may be NULL
+ * for the first layer) is overwritten with dL/d(in).  dY (B*OH*OW, Cout) and dcol (like col) are
+ * workspaces. */
+int riqn_conv_bwd(const riqn_conv_geom* g, const float* dout, const float* out, const float* col, const float* w,
+                  float* dY, float* dcol, float* dw, float* dbias, float* din, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Randomness                       replaces torch normal_/uniform_ draws, model.py:32-37 and :131-134
+ * ---------------------------------------------------------------------------------------------- */
+/* out[i] ~ U(0,1): the quantile fractions tau.  Philox4x32-10 keyed by (seed, stream_id). */
+int riqn_fill_uniform(long n, unsigned long long seed, unsigned long long stream_id, float* out, void* stream);
+/* out[i] = sign(x) sqrt|x|, x ~ N(0,1): NoisyLinear._scale_noise (model.py:32-37). */
+int riqn_noisy_sample(long n, unsigned long long seed, unsigned long long stream_id, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * NoisyLinear                                             replaces rainbowiqn/model.py:9-53
+ * ---------------------------------------------------------------------------------------------- */
+/* reset_noise + effective weights in one pass.  If eps_in/eps_out are non-NULL, weight_epsilon :=
+ * eps_out (x) eps_in and bias_epsilon := eps_out are (re)written (model.py:39-43); otherwise the
+ * stored epsilons are used.  w_eff = mu + sigma*eps, b_eff likewise (training != 0, model.py:46-51)
+ * or the mu's alone (eval, model.py:52-53). */
+int riqn_noisy_compose(int out_features, int in_features, const float* weight_mu, const float* weight_sigma,
+                       float* weight_epsilon, const float* eps_in, const float* eps_out, const float* bias_mu,
+                       const float* bias_sigma, float* bias_epsilon, float* w_eff, float* b_eff, int training,
+                       void* stream);
+/* h = relu(x w_eff^T + b_eff)   (the hidden layers fcnoisy_h_v | fcnoisy_h_a concatenated along out_features,
+ * model.py:153-154 with the F.relu folded in). */
+int riqn_noisy_linear_fwd(long rows, int in_features, int out_features, const float* x, const float* w_eff,
+                          const float* b_eff, float* h, void* stream);
+/* dx = dh w_eff   (dh already masked by the ReLU). */
+int riqn_noisy_linear_dgrad(long rows, int in_features, int out_features, const float* dh, const float* w_eff,
+                            float* dx, void* stream);
+/* grad_weight_mu += dh^T x ; grad_weight_sigma += (dh^T x) * weight_epsilon ; bias grads likewise.
+ * db_scratch: out_features floats. */
+int riqn_noisy_linear_wgrad(long rows, int in_features, int out_features, const float* dh, const float* x,
+                            const float* weight_epsilon, const float* bias_epsilon, float* db_scratch,
+                            float* grad_weight_mu, float* grad_weight_sigma, float* grad_bias_mu,
+                            float* grad_bias_sigma, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Quantile embedding                                      replaces rainbowiqn/model.py:136-151
+ * ---------------------------------------------------------------------------------------------- */
+/* cosv[r,i] = cos(fl(fl(i+1)*fl(pi)) * tau[r]);  x[r,:] = feat[r % batch,:] * relu(cosv[r,:] iqn_w^T + iqn_b).
+ * tau (rows), feat (batch, feat_dim), iqn_w (feat_dim, embed_dim); cosv (rows, embed_dim) and
+ * x (rows, feat_dim) are outputs, rows = batch * num_quantiles. */
+int riqn_quantile_embed_fwd(int batch, int num_quantiles, int embed_dim, int feat_dim, const float* tau,
+                            const float* feat, const float* iqn_w, const float* iqn_b, float* cosv, float* x,
+                            void* stream);
+/* Given dL/dx in dx_inout (overwritten with dL/d(pre-activation of iqn_fc)): dfeat (batch, feat_dim) is
+ * overwritten; grad_iqn_w / grad_iqn_b are accumulated into. */
+int riqn_quantile_embed_bwd(int batch, int num_quantiles, int embed_dim, int feat_dim, const float* x,
+                            const float* feat, const float* cosv, float* dx_inout, float* dfeat, float* grad_iqn_w,
+                            float* grad_iqn_b, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * z-layers + dueling aggregation                          replaces rainbowiqn/model.py:153-156
+ * ---------------------------------------------------------------------------------------------- */
+/* h (rows, 2*hidden) = [value-stream hidden | advantage-stream hidden]; wz (1+A, hidden) = effective
+ * weights of fcnoisy_z_v (row 0) and fcnoisy_z_a; bz (1+A).  q (rows, A) = v + a - mean_a a. */
+int riqn_dueling_fwd(long rows, int hidden, int action_space, const float* h, const float* wz, const float* bz,
+                     float* q, void* stream);
+/* Backward for the gathered action: dq[r, actions[b]] = dtheta[r] * gscale[b].  Writes dh (rows, 2*hidden),
+ * already masked by h > 0, and dz (rows, 32) = [dv, da_0.., 0..] for riqn_z_wgrad. */
+int riqn_dueling_bwd(long rows, int batch, int hidden, int action_space, const float* h, const float* wz,
+                     const float* dtheta, const float* gscale, const long long* actions, float* dh, float* dz,
+                     void* stream);
+/* Parameter gradients of the two z-layers (accumulated): dwz_scratch 32*2*hidden floats, dbz_scratch 32. */
+int riqn_z_wgrad(long rows, int hidden, int action_space, const float* dz, const float* h, float* dwz_scratch,
+                 float* dbz_scratch, const float* eps_w_zv, const float* eps_b_zv, const float* eps_w_za,
+                 const float* eps_b_za, float* g_mu_zv, float* g_sig_zv, float* g_bmu_zv, float* g_bsig_zv,
+                 float* g_mu_za, float* g_sig_za, float* g_bmu_za, float* g_bsig_za, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * IQN loss                                     replaces rainbowiqn/compute_loss_iqn.py:216-358
+ * ---------------------------------------------------------------------------------------------- */
+/* a_star[b] = argmax_a mean_k q[k*batch+b, a]            (compute_loss_iqn.py:238-245) */
+int riqn_argmax_mean(int batch, int num_quantiles, int action_space, const float* q, long long* a_star, void* stream);
+/* Fused n-step target + pairwise quantile-Huber loss and its gradient (compute_loss_iqn.py:262-357):
+ *   target[b,j] = returns[b] + gamma_n*nonterminals[b]*q_target[j*batch+b, a_star[b]]
+ *   theta[b,i]  = q_online[i*batch+b, actions[b]]
+ *   loss[b]     = mean_j sum_i |tau[i*batch+b] - 1{d<0}| huber_kappa(d)/kappa ,  d = target_j - theta_i
+ *   dtheta[i*batch+b] = d loss[b] / d theta[b,i]
+ * theta_out (batch, n_tau) / target_out (batch, n_tau_prime) are optional debug outputs (may be NULL). */
+int riqn_iqn_loss_fwd_bwd(int batch, int n_tau, int n_tau_prime, int action_space, const float* q_online,
+                          const float* q_target, const float* tau, const long long* actions, const long long* a_star,
+                          const float* returns, const float* nonterminals, float gamma_n, float kappa, float* loss,
+                          float* dtheta, float* theta_out, float* target_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Optimiser                              replaces torch.optim.Adam.step, agent.py:43 / learner.py:24
+ * ---------------------------------------------------------------------------------------------- */
+/* One Adam step over a flat arena of n fp32 parameters; `step` is the 1-based step count; grads are
+ * multiplied by grad_scale first (1/world_size after a gradient all-reduce). */
+int riqn_adam_step(long n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int step, float lr,
+                   float beta1, float beta2, float eps, float grad_scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Prioritized replay: sum-tree          replaces RedisSegmentTree / ReplayRedisMemory, redis_memory.py
+ * tree: 2*capacity-1 float64 nodes in HBM, leaf of data index d at d + capacity - 1.
+ * ---------------------------------------------------------------------------------------------- */
+/* Stratified sample values, one per segment of total/n, shuffled (redis_memory.py:276-287). n <= 12000. */
+int riqn_sumtree_stratified(int n, unsigned long long seed, unsigned long long stream_id, const double* tree,
+                            double* values, void* stream);
+/* Descent (_retrieve_multiple_values :205-229) + transform_to_valid_tree_indexes (:242-264) + priority
+ * read (:315-321).  index_actor: per-actor write heads (int64).  Bit-exact with the reference. */
+int riqn_sumtree_sample(int n, long capacity, int actor_capacity, const double* tree, const double* values,
+                        const long long* index_actor, int history, int n_step, long long* tree_idx,
+                        long long* data_idx, double* priorities, void* stream);
+/* Importance-sampling weights (sample_byte :465-475); n_nonpositive (device int, may be NULL) counts the
+ * priorities <= 0 that were replaced by 1/capacity (:446-456). */
+int riqn_sumtree_is_weights(int n, const double* tree, const double* priorities, double current_capacity,
+                            double priority_weight, double* w64, float* w32, int* n_nonpositive, void* stream);
+/* update_priorities / update_multiple_value / _propagate_multiple_values (:557-573,139-151,94-105).
+ * apply_pow != 0: new = np.power(loss, float32(priority_exponent)) first.  new_priorities (n floats) and
+ * diff_scratch (n doubles) are outputs/workspace; *max_priority (device double) is raised if needed.
+ * n <= 5000.  Bit-exact with the reference including duplicated indices. */
+int riqn_sumtree_update(int n, long capacity, double* tree, const long long* tree_idx, const float* loss,
+                        float priority_exponent, int apply_pow, float* new_priorities, double* diff_scratch,
+                        double* max_priority, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Prioritized replay: frame store            replaces the Redis hashes "transitions<i>" (:184-193)
+ * ---------------------------------------------------------------------------------------------- */
+/* Frame half of append_actor_buffer (:159-199): n consecutive transitions of one actor into its ring. */
+int riqn_replay_append(int n, int actor_capacity, int id_actor, int start, const unsigned char* frames,
+                       const int* timestep, const int* action, const float* reward, const unsigned char* nonterminal,
+                       unsigned char* s_frames, int* s_timestep, int* s_action, float* s_reward,
+                       unsigned char* s_nonterminal, void* stream);
+/* Transition assembly (:347-369, :479-541): window (batch, history+n_step, 84, 84) uint8 with blank frames
+ * across episode boundaries; states = window[:, :history], next_states = window[:, n_step:].
+ * gamma_pow: n_step doubles, discount**k. */
+int riqn_frame_gather(int batch, int actor_capacity, int history, int n_step, const long long* data_idx,
+                      const unsigned char* s_frames, const int* s_timestep, const int* s_action, const float* s_reward,
+                      const unsigned char* s_nonterminal, const double* gamma_pow, unsigned char* window,
+                      long long* actions, float* returns, float* nonterminals, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Test hook: plain strided fp32 product C[m,n] = sum_k A[m*sAm + k*sAk] * B[n*sBn + k*sBk].
+ * ---------------------------------------------------------------------------------------------- */
+int riqn_gemm_f32(int M, int N, int K, const float* A, long sAm, long sAk, const float* B, long sBn, long sBk,
+                  float* C, long ldc, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RIQN_B200_H */

@@ -306,7 +306,8 @@ def golden_sumtree(name, actor_capacity, nb_actor, batch, rounds, seed):
             if ci == 0:
                 ts[0] = 0
             ts[n // 2] = 0  # an episode start in the middle
-            frames = rs.randint(0, 256, (n, 84, 84)).astype(np.uint8)
+            frame_seed = seed * 1000 + a * 10 + ci
+            frames = np.random.RandomState(frame_seed).randint(0, 256, (n, 84, 84)).astype(np.uint8)
             actions = rs.randint(0, 18, n)
             rewards = rs.randint(-1, 2, n).astype(np.float64)
             dones = rs.uniform(size=n) < 0.05
@@ -322,7 +323,7 @@ def golden_sumtree(name, actor_capacity, nb_actor, batch, rounds, seed):
             rec[f"append_act_{a}_{ci}"] = actions
             rec[f"append_rew_{a}_{ci}"] = rewards
             rec[f"append_done_{a}_{ci}"] = dones
-            rec[f"append_frame_seed_{a}_{ci}"] = 0  # frames regenerate from the same RandomState stream
+            rec[f"append_frame_seed_{a}_{ci}"] = frame_seed
             start = (start + n) % actor_capacity
             if ci == 1:
                 fr.set("is_full_actor:" + str(a), 1)

@@ -1,0 +1,71 @@
+"""Actor -- mirror of the reference ``rainbowiqn/actor.py:11-124`` (act, act_e_greedy,
+load_weight_from_redis, compute_priorities), computed by the CUDA path."""
+import io
+import math
+import random
+
+import numpy as np
+import torch
+
+from .agent import Agent
+from .learner import MODEL_WEIGHT_STR
+
+
+class Actor(Agent):
+    def act(self, state_buffer):
+        """actor.py:15-25: greedy action from the mean over K sampled quantiles (IQN) or the expected
+        value of the categorical distribution (C51).  Frames go to the device as uint8; the /255 of the
+        reference happens inside the conv kernel."""
+        state = torch.from_numpy(np.stack(state_buffer).astype(np.uint8)).to(self.online_net._flat.device)
+        with torch.no_grad():
+            if self.rainbow_only:
+                p = self.online_net(state.unsqueeze(0))
+                return (p * self.support).sum(2).argmax(1).item()
+            quantile_values, _ = self.online_net(state.unsqueeze(0), self.num_quantile_samples)
+            return quantile_values.mean(0).argmax(0).item()
+
+    def act_batch(self, states_u8):
+        """Batched greedy actions for many environments at once: states (E, history, 84, 84) uint8 -> (E,)."""
+        with torch.no_grad():
+            if self.rainbow_only:
+                return (self.online_net(states_u8) * self.support).sum(2).argmax(1)
+            E = states_u8.shape[0]
+            q, _ = self.online_net(states_u8, self.num_quantile_samples)
+            return q.view(self.num_quantile_samples, E, self.action_space).mean(0).argmax(1)
+
+    def act_e_greedy(self, state_buffer, epsilon=0.001):
+        """actor.py:27-34"""
+        return random.randrange(self.action_space) if random.random() < epsilon else self.act(state_buffer)
+
+    def load_weight_from_redis(self):
+        """actor.py:36-39"""
+        load_bytesIO = io.BytesIO(self.redis_servor.get(MODEL_WEIGHT_STR))
+        self.online_net.load_state_dict(torch.load(load_bytesIO, map_location="cpu"))
+        self.online_net.compose_weights()
+
+    def compute_priorities(self, tab_state, tab_action, tab_reward, tab_nonterminal, priority_exponent):
+        """actor.py:41-124: initial priorities = loss ** exponent for a buffer of consecutive steps."""
+        len_buffer = len(tab_action)
+        assert len(tab_action) == len(tab_reward) == len(tab_nonterminal) == len(tab_state) - self.history + 1
+        tab_nonterminal = np.float32(tab_nonterminal[self.n:])
+        for indice in np.where(tab_nonterminal == 0)[0]:                       # actor.py:67-69
+            tab_nonterminal[indice + 1:(indice + self.n + 1)] = 0
+        dev = self.online_net._flat.device
+        actions = torch.tensor(tab_action[: len_buffer - self.n], dtype=torch.int64, device=dev)
+        tab_returns = [sum(self.discount ** n * tab_reward[n + indice] for n in range(self.n))
+                       for indice in range(0, len_buffer - self.n)]
+        returns = torch.tensor(tab_returns, dtype=torch.float32, device=dev)
+        nonterminals = torch.tensor(tab_nonterminal, dtype=torch.float32, device=dev)
+        frames = torch.from_numpy(np.stack(tab_state).astype(np.uint8)).to(dev)  # (len+history-1, 84, 84)
+        tab_priorities = []
+        with torch.no_grad():
+            for indice in range(math.ceil(len(actions) / self.batch_size)):
+                lo = indice * self.batch_size
+                hi = min((indice + 1) * self.batch_size, len(actions))
+                idx = torch.arange(lo, hi, device=dev)[:, None] + torch.arange(self.history, device=dev)[None, :]
+                states = frames[idx]                        # (b, history, 84, 84)
+                next_states = frames[idx + self.n]
+                loss = self.compute_loss_actor_or_learner(states, actions[lo:hi], returns[lo:hi], next_states,
+                                                          nonterminals[lo:hi])
+                tab_priorities.append(loss.detach().cpu().numpy())
+        return np.power(np.concatenate(tab_priorities), priority_exponent)

@@ -1,0 +1,15 @@
+// Library identification entry points of the C-ABI (include/riqn_b200.h).
+#include "common.cuh"
+#include "../../include/riqn_b200.h"
+
+RIQN_API int riqn_version(void) { return RIQN_B200_ABI_VERSION; }
+
+RIQN_API int riqn_device_ok(void) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return -(int)e;
+  int major = 0;
+  e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (e != cudaSuccess) return -(int)e;
+  return major == 10 ? 1 : 0;
+}

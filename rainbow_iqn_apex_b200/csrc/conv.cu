@@ -1,0 +1,146 @@
+// Conv trunk of the DQN (reference rainbowiqn/model.py:65-67,115-118) as im2col + GEMM.
+//
+//   conv1 8x8 s4 p1 (4->32)   conv2 4x4 s2 (32->64)   conv3 3x3 s1 (64->64), ReLU after each,
+//   activations NCHW so that conv3's output flattens C-major into the 3136 features the
+//   quantile embedding and the NoisyLinear head expect (model.py:118).
+//
+// The uint8 frame stack (B,4,84,84) is read directly: x = float(u8) / 255.0f reproduces the
+// reference's `.to(float32).div_(255)` (redis_memory.py:527-536) bit for bit, without ever
+// materialising the fp32 frames in HBM.
+#include "common.cuh"
+#include "gemm.h"
+#include "../../include/riqn_b200.h"
+
+namespace riqn {
+
+template <typename T>
+__device__ __forceinline__ float load_px(const T* p);
+template <>
+__device__ __forceinline__ float load_px<uint8_t>(const uint8_t* p) { return (float)(*p) / 255.0f; }
+template <>
+__device__ __forceinline__ float load_px<float>(const float* p) { return *p; }
+
+// col[m, k] , m = (b, oh, ow), k = (cin, kh, kw)  -- k order == the (Cout, Cin*KH*KW) weight layout
+template <typename T>
+__global__ void im2col_kernel(riqn_conv_geom g, const T* __restrict__ in, float* __restrict__ col) {
+  const int K = g.Cin * g.KH * g.KW;
+  const long total = (long)g.B * g.OH * g.OW * K;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int k = (int)(idx % K);
+    const long m = idx / K;
+    const int kw = k % g.KW, kh = (k / g.KW) % g.KH, c = k / (g.KW * g.KH);
+    const int ow = (int)(m % g.OW), oh = (int)((m / g.OW) % g.OH), b = (int)(m / ((long)g.OW * g.OH));
+    const int ih = oh * g.stride + kh - g.pad, iw = ow * g.stride + kw - g.pad;
+    float v = 0.f;
+    if (ih >= 0 && ih < g.H && iw >= 0 && iw < g.W) v = load_px<T>(&in[(((long)b * g.Cin + c) * g.H + ih) * g.W + iw]);
+    col[idx] = v;
+  }
+}
+
+// dY[m, c] = dout[b, c, p] * (out[b, c, p] > 0)      (ReLU backward + NCHW -> (M, Cout))
+__global__ void conv_dy_kernel(int B, int Cout, int ohw, const float* __restrict__ dout,
+                               const float* __restrict__ out, float* __restrict__ dY) {
+  const long total = (long)B * Cout * ohw;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int p = (int)(idx % ohw);
+    const int c = (int)((idx / ohw) % Cout);
+    const long b = idx / ((long)ohw * Cout);
+    const float v = out[idx] > 0.f ? dout[idx] : 0.f;
+    dY[(b * ohw + p) * Cout + c] = v;
+  }
+}
+
+// din[b, c, ih, iw] = sum_{kh,kw} dcol[(b,oh,ow), (c,kh,kw)]
+__global__ void col2im_kernel(riqn_conv_geom g, const float* __restrict__ dcol, float* __restrict__ din) {
+  const int K = g.Cin * g.KH * g.KW;
+  const long total = (long)g.B * g.Cin * g.H * g.W;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int iw = (int)(idx % g.W), ih = (int)((idx / g.W) % g.H);
+    const int c = (int)((idx / ((long)g.W * g.H)) % g.Cin);
+    const long b = idx / ((long)g.W * g.H * g.Cin);
+    float acc = 0.f;
+    for (int kh = 0; kh < g.KH; ++kh) {
+      const int t = ih + g.pad - kh;
+      if (t < 0 || t % g.stride) continue;
+      const int oh = t / g.stride;
+      if (oh >= g.OH) continue;
+      for (int kw = 0; kw < g.KW; ++kw) {
+        const int u = iw + g.pad - kw;
+        if (u < 0 || u % g.stride) continue;
+        const int ow = u / g.stride;
+        if (ow >= g.OW) continue;
+        acc += dcol[((b * g.OH + oh) * g.OW + ow) * K + (c * g.KH + kh) * g.KW + kw];
+      }
+    }
+    din[idx] = acc;
+  }
+}
+
+// out[n] += sum_m X[m, n]
+__global__ void colsum_atomic_kernel(long M, int N, const float* __restrict__ X, float* __restrict__ out, int rows_per_block) {
+  const int n = blockIdx.x * 128 + (threadIdx.x & 127);
+  const int half = threadIdx.x >> 7;
+  if (n >= N) return;
+  const long r0 = (long)blockIdx.y * rows_per_block;
+  const long r1 = min(M, r0 + rows_per_block);
+  float acc = 0.f;
+  for (long r = r0 + half; r < r1; r += 2) acc += X[r * N + n];
+  atomicAdd(&out[n], acc);
+}
+
+int colsum_atomic(long M, int N, const float* X, float* out, cudaStream_t s) {
+  int rows_per_block = 256;
+  dim3 grid((N + 127) / 128, (unsigned)((M + rows_per_block - 1) / rows_per_block));
+  colsum_atomic_kernel<<<grid, 256, 0, s>>>(M, N, X, out, rows_per_block);
+  return (int)cudaGetLastError();
+}
+
+static inline int grid_for(long total) {
+  long b = (total + 255) / 256;
+  return (int)(b > 148L * 32 ? 148L * 32 : (b < 1 ? 1 : b));
+}
+
+}  // namespace riqn
+
+using namespace riqn;
+
+RIQN_API int riqn_conv_fwd(const riqn_conv_geom* g, const void* in, int in_is_u8, const float* w, const float* bias,
+                           float* col, float* out, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  const long M = (long)g->B * g->OH * g->OW;
+  const int K = g->Cin * g->KH * g->KW;
+  if (in_is_u8) im2col_kernel<uint8_t><<<grid_for(M * K), 256, 0, s>>>(*g, (const uint8_t*)in, col);
+  else im2col_kernel<float><<<grid_for(M * K), 256, 0, s>>>(*g, (const float*)in, col);
+  RIQN_LAUNCH_CHECK();
+  EpiArgs e;
+  e.bias = bias;
+  e.ohw = g->OH * g->OW;
+  return gemm_f32((int)M, g->Cout, K, col, K, 1, w, K, 1, out, g->Cout, EPI_BIAS_RELU_NCHW, e, 1, s);
+}
+
+RIQN_API int riqn_conv_bwd(const riqn_conv_geom* g, const float* dout, const float* out, const float* col,
+                           const float* w, float* dY, float* dcol, float* dw, float* dbias, float* din, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  const long M = (long)g->B * g->OH * g->OW;
+  const int K = g->Cin * g->KH * g->KW;
+  const int ohw = g->OH * g->OW;
+  conv_dy_kernel<<<grid_for(M * g->Cout), 256, 0, s>>>(g->B, g->Cout, ohw, dout, out, dY);
+  RIQN_LAUNCH_CHECK();
+  int rc = colsum_atomic(M, g->Cout, dY, dbias, s);
+  if (rc) return rc;
+  // dW[c, k] += sum_m dY[m, c] * col[m, k]
+  EpiArgs e;
+  const int tiles = ((g->Cout + 127) / 128) * ((K + 127) / 128);
+  int split = (2 * 148 + tiles - 1) / tiles;
+  if ((long)split * 64 > M) split = (int)((M + 63) / 64);
+  rc = gemm_f32(g->Cout, K, (int)M, dY, 1, g->Cout, col, 1, K, dw, K, EPI_ATOMIC, e, split, s);
+  if (rc) return rc;
+  if (din) {
+    // dcol[m, k] = sum_c dY[m, c] * W[c, k]
+    rc = gemm_f32((int)M, K, g->Cout, dY, g->Cout, 1, w, 1, K, dcol, K, EPI_STORE, e, 1, s);
+    if (rc) return rc;
+    col2im_kernel<<<grid_for((long)g->B * g->Cin * g->H * g->W), 256, 0, s>>>(*g, dcol, din);
+    RIQN_LAUNCH_CHECK();
+  }
+  return 0;
+}

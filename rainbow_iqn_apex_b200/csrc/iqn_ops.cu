@@ -1,0 +1,486 @@
+// IQN head of the DQN and the quantile-Huber loss (reference rainbowiqn/model.py:9-53,130-157 and
+// rainbowiqn/compute_loss_iqn.py:216-358) as CUDA ops behind the C-ABI in include/riqn_b200.h.
+//
+// Row convention everywhere: r = q * B + b  (quantile-major, model.py:149; compute_loss_iqn.py:238-310).
+#include "common.cuh"
+#include "gemm.h"
+#include "../../include/riqn_b200.h"
+
+namespace riqn {
+int colsum_atomic(long M, int N, const float* X, float* out, cudaStream_t s);
+
+// ------------------------------------------------------------------------------------------------
+// RNG fills
+// ------------------------------------------------------------------------------------------------
+__global__ void fill_uniform_kernel(long n, uint64_t seed, uint64_t stream, float* __restrict__ out) {
+  const long i4 = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i4 * 4 >= n) return;
+  const uint4 r = Philox::draw(seed, stream, (uint64_t)i4);
+  const float v[4] = {Philox::u01(r.x), Philox::u01(r.y), Philox::u01(r.z), Philox::u01(r.w)};
+  for (int j = 0; j < 4; ++j)
+    if (i4 * 4 + j < n) out[i4 * 4 + j] = v[j];
+}
+
+// f(x) = sign(x) sqrt|x| of x ~ N(0,1)            (NoisyLinear._scale_noise, model.py:32-37)
+__global__ void fill_scaled_normal_kernel(long n, uint64_t seed, uint64_t stream, float* __restrict__ out) {
+  const long i4 = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i4 * 4 >= n) return;
+  const uint4 r = Philox::draw(seed, stream, (uint64_t)i4);
+  const float u0 = Philox::u01(r.x), u1 = Philox::u01(r.y), u2 = Philox::u01(r.z), u3 = Philox::u01(r.w);
+  const float ra = sqrtf(-2.f * logf(u0)), rb = sqrtf(-2.f * logf(u2));
+  float s0, c0, s1, c1;
+  sincospif(2.f * u1, &s0, &c0);
+  sincospif(2.f * u3, &s1, &c1);
+  const float z[4] = {ra * c0, ra * s0, rb * c1, rb * s1};
+  for (int j = 0; j < 4; ++j)
+    if (i4 * 4 + j < n) out[i4 * 4 + j] = copysignf(sqrtf(fabsf(z[j])), z[j]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Quantile embedding input: cos(fl(fl(i) * fl(pi)) * tau), i = 1..E          (model.py:136-144)
+// ------------------------------------------------------------------------------------------------
+__global__ void cos_embed_kernel(long R, int E, const float* __restrict__ tau, float* __restrict__ cosv) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= R * E) return;
+  const int i = (int)(idx % E) + 1;
+  const float ipi = __fmul_rn((float)i, 3.14159274101257324f);
+  cosv[idx] = cosf(__fmul_rn(ipi, tau[idx / E]));
+}
+
+// ------------------------------------------------------------------------------------------------
+// NoisyLinear: (optional) eps_w = eps_out (x) eps_in, then W_eff = mu + sigma*eps_w, b_eff likewise
+// (model.py:39-53).  training == 0 gives the eval-mode weights (mu only).
+// ------------------------------------------------------------------------------------------------
+__global__ void noisy_compose_kernel(int out_f, int in_f, const float* __restrict__ mu, const float* __restrict__ sigma,
+                                     float* __restrict__ eps_w, const float* __restrict__ eps_in,
+                                     const float* __restrict__ eps_out, const float* __restrict__ bmu,
+                                     const float* __restrict__ bsigma, float* __restrict__ beps,
+                                     float* __restrict__ w_eff, float* __restrict__ b_eff, int training) {
+  const long total = (long)out_f * in_f;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int o = (int)(idx / in_f), i = (int)(idx % in_f);
+    float e;
+    if (eps_in) {
+      e = __fmul_rn(eps_out[o], eps_in[i]);
+      eps_w[idx] = e;
+    } else {
+      e = eps_w[idx];
+    }
+    w_eff[idx] = training ? __fadd_rn(mu[idx], __fmul_rn(sigma[idx], e)) : mu[idx];
+    if (i == 0) {
+      float eb;
+      if (eps_in) {
+        eb = eps_out[o];
+        beps[o] = eb;
+      } else {
+        eb = beps[o];
+      }
+      b_eff[o] = training ? __fadd_rn(bmu[o], __fmul_rn(bsigma[o], eb)) : bmu[o];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// z-layers + dueling: q[r,a] = v + a_a - mean_a(a)                           (model.py:153-156)
+//   H (R, 2*hid): [:, :hid] value stream hidden, [:, hid:] advantage stream hidden (post-ReLU)
+//   Wz (1+A, hid): row 0 = z_v effective weight, rows 1.. = z_a ; bz (1+A)
+// One warp per row.
+// ------------------------------------------------------------------------------------------------
+template <int HID>
+__global__ void z_dueling_fwd_kernel(long R, int A, const float* __restrict__ H, const float* __restrict__ Wz,
+                                     const float* __restrict__ bz, float* __restrict__ q) {
+  extern __shared__ float sW[];  // (1+A) * HID
+  for (int i = threadIdx.x; i < (1 + A) * HID; i += blockDim.x) sW[i] = Wz[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  constexpr int T = HID / 32;
+  for (long r = (long)blockIdx.x * wpb + warp; r < R; r += (long)gridDim.x * wpb) {
+    const float* h = H + r * (2 * HID);
+    float hv[T], ha[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      hv[t] = h[lane + 32 * t];
+      ha[t] = h[HID + lane + 32 * t];
+    }
+    float v = 0.f;
+#pragma unroll
+    for (int t = 0; t < T; ++t) v = fmaf(hv[t], sW[lane + 32 * t], v);
+    v = warp_sum(v) + bz[0];
+    float mine = 0.f, asum = 0.f;
+    for (int k = 0; k < A; ++k) {
+      float a = 0.f;
+      const float* wk = sW + (1 + k) * HID;
+#pragma unroll
+      for (int t = 0; t < T; ++t) a = fmaf(ha[t], wk[lane + 32 * t], a);
+      a = warp_sum(a) + bz[1 + k];
+      asum += a;
+      if (lane == k) mine = a;
+    }
+    if (lane < A) q[r * A + lane] = v + mine - asum / (float)A;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Double-DQN action: a*[b] = argmax_a mean_k q[k*B+b, a]               (compute_loss_iqn.py:238-245)
+// ------------------------------------------------------------------------------------------------
+__global__ void argmax_mean_kernel(int B, int K, int A, const float* __restrict__ q, int64_t* __restrict__ a_star) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float best = 0.f;
+  int arg = 0;
+  for (int a = 0; a < A; ++a) {
+    float s = 0.f;
+    for (int k = 0; k < K; ++k) s += q[((long)k * B + b) * A + a];
+    s /= (float)K;
+    if (a == 0 || s > best) { best = s; arg = a; }
+  }
+  a_star[b] = arg;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused IQN quantile-Huber loss, forward + dloss/dtheta            (compute_loss_iqn.py:262-357)
+//   T[b,j]   = R[b] + fl(gamma^n)*nt[b] * q_tgt[(j*B+b), a*[b]]
+//   th[b,i]  = q_on[(i*B+b), act[b]]
+//   loss[b]  = (1/N') sum_j sum_i |tau_i - 1{d<0}| * huber_k(d) / k ,  d = T_j - th_i
+//   dth[i*B+b] = dloss[b]/dth_i  (indicator detached, :344-346)
+// One CTA per transition; thread i owns th_i and walks the N' targets staged in shared memory.
+// ------------------------------------------------------------------------------------------------
+__global__ void iqn_loss_kernel(int B, int N, int Np, int A, const float* __restrict__ q_on,
+                                const float* __restrict__ q_tgt, const float* __restrict__ tau,
+                                const int64_t* __restrict__ actions, const int64_t* __restrict__ a_star,
+                                const float* __restrict__ returns, const float* __restrict__ nonterminals,
+                                float gamma_n, float kappa, float* __restrict__ loss, float* __restrict__ dtheta,
+                                float* __restrict__ theta_out, float* __restrict__ target_out) {
+  extern __shared__ float sT[];  // Np targets + 32 reduction slots
+  float* red = sT + Np;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int as = (int)a_star[b], ac = (int)actions[b];
+  const float g = __fmul_rn(gamma_n, nonterminals[b]);
+  for (int j = tid; j < Np; j += blockDim.x) {
+    const float t = __fadd_rn(returns[b], __fmul_rn(g, q_tgt[((long)j * B + b) * A + as]));
+    sT[j] = t;
+    if (target_out) target_out[(long)b * Np + j] = t;
+  }
+  __syncthreads();
+  float part = 0.f;
+  for (int i = tid; i < N; i += blockDim.x) {
+    const float th = q_on[((long)i * B + b) * A + ac];
+    const float ta = tau[(long)i * B + b];
+    float acc = 0.f, gacc = 0.f;
+    for (int j = 0; j < Np; ++j) {
+      const float d = sT[j] - th;
+      const float ad = fabsf(d);
+      const float hub = ad <= kappa ? 0.5f * d * d : kappa * (ad - 0.5f * kappa);
+      const float dh = ad <= kappa ? d : copysignf(kappa, d);
+      const float w = fabsf(ta - (d < 0.f ? 1.f : 0.f));
+      acc += w * hub / kappa;
+      gacc -= w * dh / kappa;
+    }
+    part += acc;
+    dtheta[(long)i * B + b] = gacc / (float)Np;
+    if (theta_out) theta_out[(long)b * N + i] = th;
+  }
+  part = warp_sum(part);
+  if ((tid & 31) == 0) red[tid >> 5] = part;
+  __syncthreads();
+  if (tid < 32) {
+    float v = tid < (blockDim.x >> 5) ? red[tid] : 0.f;
+    v = warp_sum(v);
+    if (tid == 0) loss[b] = v / (float)Np;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Backward of dueling + z-layers + hidden ReLU, one warp per row.
+//   g = dtheta[r] * gscale[b];  dq[a] = g*1{a==act}  =>  dv = g ,  da_k = g*(1{k==act} - 1/A)
+//   dH_v = dv * w_zv ; dH_a = g*(W_za[act] - colmean(W_za)) ; masked by H > 0
+//   dz (R, 32): [g, da_0..da_{A-1}, 0...] feeds the z-layer weight-gradient reduction.
+// ------------------------------------------------------------------------------------------------
+template <int HID>
+__global__ void z_dueling_bwd_kernel(long R, int B, int A, const float* __restrict__ H, const float* __restrict__ Wz,
+                                     const float* __restrict__ dtheta, const float* __restrict__ gscale,
+                                     const int64_t* __restrict__ actions, float* __restrict__ dH,
+                                     float* __restrict__ dz) {
+  extern __shared__ float sW[];  // (1+A)*HID weights + HID colmean
+  float* wbar = sW + (1 + A) * HID;
+  for (int i = threadIdx.x; i < (1 + A) * HID; i += blockDim.x) sW[i] = Wz[i];
+  __syncthreads();
+  for (int j = threadIdx.x; j < HID; j += blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < A; ++k) s += sW[(1 + k) * HID + j];
+    wbar[j] = s / (float)A;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  for (long r = (long)blockIdx.x * wpb + warp; r < R; r += (long)gridDim.x * wpb) {
+    const int b = (int)(r % B);
+    const float g = dtheta[r] * gscale[b];
+    const int act = (int)actions[b];
+    const float* h = H + r * (2 * HID);
+    float* o = dH + r * (2 * HID);
+    const float* wa = sW + (1 + act) * HID;
+    for (int j = lane; j < HID; j += 32) {
+      o[j] = h[j] > 0.f ? g * sW[j] : 0.f;
+      o[HID + j] = h[HID + j] > 0.f ? g * (wa[j] - wbar[j]) : 0.f;
+    }
+    float z = 0.f;
+    if (lane == 0) z = g;
+    else if (lane <= A) z = g * ((lane - 1 == act ? 1.f : 0.f) - 1.f / (float)A);
+    dz[r * 32 + lane] = z;
+  }
+}
+
+// dWz (32, 2*HID) from dz^T * H  ->  parameter gradients of the two noisy z-layers.
+//   z_v: weight (1,HID) = dWz[0, :HID] ; z_a: weight (A,HID) = dWz[1+k, HID:]
+//   dmu += g ; dsigma += g * eps          (model.py:45-53)
+__global__ void z_wgrad_finish_kernel(int A, int HID, const float* __restrict__ dWz, const float* __restrict__ dbz,
+                                      const float* __restrict__ eps_w_zv, const float* __restrict__ eps_b_zv,
+                                      const float* __restrict__ eps_w_za, const float* __restrict__ eps_b_za,
+                                      float* g_mu_zv, float* g_sig_zv, float* g_bmu_zv, float* g_bsig_zv,
+                                      float* g_mu_za, float* g_sig_za, float* g_bmu_za, float* g_bsig_za) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < HID) {
+    const float g = dWz[idx];
+    g_mu_zv[idx] += g;
+    g_sig_zv[idx] += g * eps_w_zv[idx];
+  }
+  if (idx < A * HID) {
+    const int k = idx / HID, j = idx % HID;
+    const float g = dWz[(long)(1 + k) * (2 * HID) + HID + j];
+    g_mu_za[idx] += g;
+    g_sig_za[idx] += g * eps_w_za[idx];
+  }
+  if (idx == 0) {
+    g_bmu_zv[0] += dbz[0];
+    g_bsig_zv[0] += dbz[0] * eps_b_zv[0];
+  }
+  if (idx < A) {
+    g_bmu_za[idx] += dbz[1 + idx];
+    g_bsig_za[idx] += dbz[1 + idx] * eps_b_za[idx];
+  }
+}
+
+// dmu_b += db ; dsigma_b += db * eps_b
+__global__ void noisy_bias_grad_kernel(int n, const float* __restrict__ db, const float* __restrict__ eps_b,
+                                       float* g_bmu, float* g_bsig) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  g_bmu[i] += db[i];
+  g_bsig[i] += db[i] * eps_b[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Backward through x = feat[b] (.) phi[r]  (model.py:149-151) given dX (in place -> dpre):
+//   dpre[r,f]  = dX * feat[b,f] * 1{phi>0}          (grad wrt iqn_fc pre-activation)
+//   dfeat[b,f] = sum_q dX[q*B+b,f] * phi[q*B+b,f]   with phi = X/feat where feat > 0
+// (feat == 0 means conv3's ReLU is closed, so dfeat there is masked anyway.)
+// ------------------------------------------------------------------------------------------------
+__global__ void embed_bwd_elem_kernel(int B, int Nq, int F, const float* __restrict__ X, const float* __restrict__ feat,
+                                      float* __restrict__ dX, float* __restrict__ dfeat) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)B * F) return;
+  const float ft = feat[idx];
+  float acc = 0.f;
+  for (int q = 0; q < Nq; ++q) {
+    const long o = (long)q * B * F + idx;
+    const float x = X[o], dx = dX[o];
+    acc = fmaf(dx, x, acc);
+    dX[o] = x > 0.f ? dx * ft : 0.f;
+  }
+  dfeat[idx] = ft > 0.f ? acc / ft : 0.f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Adam over a flat fp32 arena (torch.optim.Adam semantics; agent.py:43, learner.py:24)
+// ------------------------------------------------------------------------------------------------
+__global__ void adam_kernel(long n, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, float lr_over_bc1, float inv_sqrt_bc2, float eps, float b1, float b2,
+                            float grad_scale) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * grad_scale;
+    const float mi = m[i] + (gi - m[i]) * (1.f - b1);           // lerp_, as torch
+    const float vi = v[i] * b2 + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
+    p[i] -= lr_over_bc1 * (mi / denom);
+  }
+}
+
+static inline int grid_for(long total, int per = 256) {
+  long b = (total + per - 1) / per;
+  return (int)(b > 148L * 64 ? 148L * 64 : (b < 1 ? 1 : b));
+}
+
+}  // namespace riqn
+
+using namespace riqn;
+
+RIQN_API int riqn_fill_uniform(long n, unsigned long long seed, unsigned long long stream_id, float* out, void* stream) {
+  if (n <= 0) return 0;
+  fill_uniform_kernel<<<riqn_cdiv((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(n, seed, stream_id, out);
+  return (int)cudaGetLastError();
+}
+
+RIQN_API int riqn_noisy_sample(long n, unsigned long long seed, unsigned long long stream_id, float* out, void* stream) {
+  if (n <= 0) return 0;
+  fill_scaled_normal_kernel<<<riqn_cdiv((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(n, seed, stream_id, out);
+  return (int)cudaGetLastError();
+}
+
+RIQN_API int riqn_noisy_compose(int out_features, int in_features, const float* weight_mu, const float* weight_sigma,
+                                float* weight_epsilon, const float* eps_in, const float* eps_out, const float* bias_mu,
+                                const float* bias_sigma, float* bias_epsilon, float* w_eff, float* b_eff, int training,
+                                void* stream) {
+  noisy_compose_kernel<<<grid_for((long)out_features * in_features), 256, 0, (cudaStream_t)stream>>>(
+      out_features, in_features, weight_mu, weight_sigma, weight_epsilon, eps_in, eps_out, bias_mu, bias_sigma,
+      bias_epsilon, w_eff, b_eff, training);
+  return (int)cudaGetLastError();
+}
+
+RIQN_API int riqn_quantile_embed_fwd(int batch, int num_quantiles, int embed_dim, int feat_dim, const float* tau,
+                                     const float* feat, const float* iqn_w, const float* iqn_b, float* cosv, float* x,
+                                     void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  const long R = (long)batch * num_quantiles;
+  cos_embed_kernel<<<riqn_cdiv(R * embed_dim, 256), 256, 0, s>>>(R, embed_dim, tau, cosv);
+  RIQN_LAUNCH_CHECK();
+  EpiArgs e;
+  e.bias = iqn_b;
+  e.feat = feat;
+  e.batch = batch;
+  return gemm_f32((int)R, feat_dim, embed_dim, cosv, embed_dim, 1, iqn_w, embed_dim, 1, x, feat_dim, EPI_EMBED, e, 1, s);
+}
+
+RIQN_API int riqn_quantile_embed_bwd(int batch, int num_quantiles, int embed_dim, int feat_dim, const float* x,
+                                     const float* feat, const float* cosv, float* dx_inout, float* dfeat,
+                                     float* grad_iqn_w, float* grad_iqn_b, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  const long R = (long)batch * num_quantiles;
+  embed_bwd_elem_kernel<<<riqn_cdiv((long)batch * feat_dim, 256), 256, 0, s>>>(batch, num_quantiles, feat_dim, x, feat,
+                                                                             dx_inout, dfeat);
+  RIQN_LAUNCH_CHECK();
+  int rc = colsum_atomic(R, feat_dim, dx_inout, grad_iqn_b, s);
+  if (rc) return rc;
+  EpiArgs e;
+  const int tiles = (feat_dim + 127) / 128;
+  int split = (3 * 148 + tiles - 1) / tiles;
+  if ((long)split * 64 > R) split = (int)((R + 63) / 64);
+  // dWe[f, i] += sum_r dpre[r, f] * cos[r, i]
+  return gemm_f32(feat_dim, embed_dim, (int)R, dx_inout, 1, feat_dim, cosv, 1, embed_dim, grad_iqn_w, embed_dim,
+                  EPI_ATOMIC, e, split, s);
+}
+
+RIQN_API int riqn_noisy_linear_fwd(long rows, int in_features, int out_features, const float* x, const float* w_eff,
+                                   const float* b_eff, float* h, void* stream) {
+  EpiArgs e;
+  e.bias = b_eff;
+  return gemm_f32((int)rows, out_features, in_features, x, in_features, 1, w_eff, in_features, 1, h, out_features,
+                  EPI_BIAS_RELU, e, 1, (cudaStream_t)stream);
+}
+
+RIQN_API int riqn_noisy_linear_dgrad(long rows, int in_features, int out_features, const float* dh, const float* w_eff,
+                                     float* dx, void* stream) {
+  EpiArgs e;
+  return gemm_f32((int)rows, in_features, out_features, dh, out_features, 1, w_eff, 1, in_features, dx, in_features,
+                  EPI_STORE, e, 1, (cudaStream_t)stream);
+}
+
+RIQN_API int riqn_noisy_linear_wgrad(long rows, int in_features, int out_features, const float* dh, const float* x,
+                                     const float* weight_epsilon, const float* bias_epsilon, float* db_scratch,
+                                     float* grad_weight_mu, float* grad_weight_sigma, float* grad_bias_mu,
+                                     float* grad_bias_sigma, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  EpiArgs e;
+  e.out2 = grad_weight_sigma;
+  e.eps = weight_epsilon;
+  int rc = gemm_f32(out_features, in_features, (int)rows, dh, 1, out_features, x, 1, in_features, grad_weight_mu,
+                    in_features, EPI_NOISY_WGRAD, e, 1, s);
+  if (rc) return rc;
+  RIQN_CUDA(cudaMemsetAsync(db_scratch, 0, sizeof(float) * out_features, s));
+  rc = colsum_atomic(rows, out_features, dh, db_scratch, s);
+  if (rc) return rc;
+  noisy_bias_grad_kernel<<<riqn_cdiv(out_features, 256), 256, 0, s>>>(out_features, db_scratch, bias_epsilon,
+                                                                    grad_bias_mu, grad_bias_sigma);
+  return (int)cudaGetLastError();
+}
+
+RIQN_API int riqn_dueling_fwd(long rows, int hidden, int action_space, const float* h, const float* wz, const float* bz,
+                              float* q, void* stream) {
+  if (hidden != 512 || action_space > 31) return (int)cudaErrorInvalidValue;
+  const size_t smem = sizeof(float) * (1 + action_space) * hidden;
+  static bool attr = false;
+  if (!attr) {
+    RIQN_CUDA(cudaFuncSetAttribute(z_dueling_fwd_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    attr = true;
+  }
+  z_dueling_fwd_kernel<512><<<148 * 4, 256, smem, (cudaStream_t)stream>>>(rows, action_space, h, wz, bz, q);
+  return (int)cudaGetLastError();
+}
+
+RIQN_API int riqn_dueling_bwd(long rows, int batch, int hidden, int action_space, const float* h, const float* wz,
+                              const float* dtheta, const float* gscale, const long long* actions, float* dh, float* dz,
+                              void* stream) {
+  if (hidden != 512 || action_space > 31) return (int)cudaErrorInvalidValue;
+  const size_t smem = sizeof(float) * ((1 + action_space) * hidden + hidden);
+  static bool attr = false;
+  if (!attr) {
+    RIQN_CUDA(cudaFuncSetAttribute(z_dueling_bwd_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    attr = true;
+  }
+  z_dueling_bwd_kernel<512><<<148 * 4, 256, smem, (cudaStream_t)stream>>>(rows, batch, action_space, h, wz, dtheta, gscale,
+                                                                       (const int64_t*)actions, dh, dz);
+  return (int)cudaGetLastError();
+}
+
+RIQN_API int riqn_z_wgrad(long rows, int hidden, int action_space, const float* dz, const float* h, float* dwz_scratch,
+                          float* dbz_scratch, const float* eps_w_zv, const float* eps_b_zv, const float* eps_w_za,
+                          const float* eps_b_za, float* g_mu_zv, float* g_sig_zv, float* g_bmu_zv, float* g_bsig_zv,
+                          float* g_mu_za, float* g_sig_za, float* g_bmu_za, float* g_bsig_za, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  const int W = 2 * hidden;
+  RIQN_CUDA(cudaMemsetAsync(dwz_scratch, 0, sizeof(float) * 32 * W, s));
+  RIQN_CUDA(cudaMemsetAsync(dbz_scratch, 0, sizeof(float) * 32, s));
+  EpiArgs e;
+  int split = 32;
+  if ((long)split * 64 > rows) split = (int)((rows + 63) / 64);
+  int rc = gemm_f32(32, W, (int)rows, dz, 1, 32, h, 1, W, dwz_scratch, W, EPI_ATOMIC, e, split, s);
+  if (rc) return rc;
+  rc = colsum_atomic(rows, 32, dz, dbz_scratch, s);
+  if (rc) return rc;
+  z_wgrad_finish_kernel<<<riqn_cdiv((long)action_space * hidden, 256), 256, 0, s>>>(
+      action_space, hidden, dwz_scratch, dbz_scratch, eps_w_zv, eps_b_zv, eps_w_za, eps_b_za, g_mu_zv, g_sig_zv, g_bmu_zv,
+      g_bsig_zv, g_mu_za, g_sig_za, g_bmu_za, g_bsig_za);
+  return (int)cudaGetLastError();
+}
+
+RIQN_API int riqn_argmax_mean(int batch, int num_quantiles, int action_space, const float* q, long long* a_star,
+                              void* stream) {
+  argmax_mean_kernel<<<riqn_cdiv(batch, 128), 128, 0, (cudaStream_t)stream>>>(batch, num_quantiles, action_space, q,
+                                                                            (int64_t*)a_star);
+  return (int)cudaGetLastError();
+}
+
+RIQN_API int riqn_iqn_loss_fwd_bwd(int batch, int n_tau, int n_tau_prime, int action_space, const float* q_online,
+                                   const float* q_target, const float* tau, const long long* actions,
+                                   const long long* a_star, const float* returns, const float* nonterminals,
+                                   float gamma_n, float kappa, float* loss, float* dtheta, float* theta_out,
+                                   float* target_out, void* stream) {
+  int threads = ((n_tau > n_tau_prime ? n_tau : n_tau_prime) + 31) / 32 * 32;
+  if (threads > 1024) threads = 1024;
+  if (threads < 32) threads = 32;
+  const size_t smem = sizeof(float) * (n_tau_prime + 32);
+  iqn_loss_kernel<<<batch, threads, smem, (cudaStream_t)stream>>>(
+      batch, n_tau, n_tau_prime, action_space, q_online, q_target, tau, (const int64_t*)actions, (const int64_t*)a_star,
+      returns, nonterminals, gamma_n, kappa, loss, dtheta, theta_out, target_out);
+  return (int)cudaGetLastError();
+}
+
+RIQN_API int riqn_adam_step(long n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int step,
+                            float lr, float beta1, float beta2, float eps, float grad_scale, void* stream) {
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  adam_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(n, params, grads, exp_avg, exp_avg_sq, (float)(lr / bc1),
+                                                            (float)(1.0 / sqrt(bc2)), eps, beta1, beta2, grad_scale);
+  return (int)cudaGetLastError();
+}

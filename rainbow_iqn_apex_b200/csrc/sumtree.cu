@@ -1,0 +1,376 @@
+// Device-resident prioritized-replay sum-tree and frame store (reference rainbowiqn/redis_memory.py).
+//
+// The reference keeps the tree as Redis string keys "priorities:<i>" (decimal strings parsed to
+// float64) and spends one network round trip per tree level; here the 2C-1 float64 nodes live in HBM
+// (implicit heap, leaf of data index d at d + C - 1) and every operation is one or two launches.
+// All arithmetic is float64 in the reference's exact order, so indices and node values are bit-exact:
+//   * descent:  `if value <= left: go left else value -= left; go right`, non-power-of-two guard
+//               (redis_memory.py:205-229)
+//   * update:   old leaves read first (duplicates see the same old), diff = new - old; every ancestor
+//               gets `+= diff` sequentially in batch order; index 0 skipped on the way up and the root
+//               finally receives numpy's pairwise np.sum(diffs) (redis_memory.py:94-105,139-151)
+//   * valid-index shift away from actor write heads (redis_memory.py:242-264)
+#include "common.cuh"
+#include "../../include/riqn_b200.h"
+
+namespace riqn {
+
+// ------------------------------------------------------------------------------------------------
+// Sampling
+// ------------------------------------------------------------------------------------------------
+// samples[i] = a + (b - a) * u_i, a = i*seg, b = (i+1)*seg (CPython random.uniform), then shuffled
+// (redis_memory.py:276-287).  Single CTA; thread 0 runs the Fisher-Yates shuffle in shared memory.
+__global__ void stratified_kernel(int n, uint64_t seed, uint64_t stream, const double* __restrict__ tree,
+                                  double* __restrict__ values) {
+  extern __shared__ int perm[];
+  const double seg = tree[0] / (double)n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) perm[i] = i;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = n - 1; i > 0; --i) {
+      const uint4 r = Philox::draw(seed, stream ^ 0x5bd1e995ull, (uint64_t)i);
+      const int j = (int)(((uint64_t)r.x * (uint64_t)(i + 1)) >> 32);
+      const int t = perm[i]; perm[i] = perm[j]; perm[j] = t;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int s = perm[i];
+    const uint4 r = Philox::draw(seed, stream, (uint64_t)s);
+    const double a = (double)s * seg, b = (double)(s + 1) * seg;
+    values[i] = a + (b - a) * Philox::u01d(r.x, r.y);
+  }
+}
+
+// One warp per query.  The warp prefetches the whole 5-level subtree under the current node (62 nodes,
+// two coalesced 8-byte loads per lane), then walks it with shuffles: 5 levels per dependent memory
+// round trip instead of 1, using exactly the reference's stored node values and comparison order.
+__global__ void sumtree_sample_kernel(int n, long C, int actor_cap, const double* __restrict__ tree,
+                                      const double* __restrict__ values, const int64_t* __restrict__ index_actor,
+                                      int history, int n_step, int64_t* __restrict__ tree_idx,
+                                      int64_t* __restrict__ data_idx, double* __restrict__ priorities) {
+  const int lane = threadIdx.x & 31;
+  const long q = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (q >= n) return;
+  const long n_nodes = 2 * C - 1;
+  long idx = 0;
+  double value = values[q];
+  while (2 * idx + 1 < n_nodes) {
+    // relative level l (1..5) under idx holds nodes (idx+1)*2^l - 1 + [0, 2^l)
+    // lane j loads: slot j  -> levels 1..4 packed (30 nodes: offsets 0..29), slot 32+j -> level 5
+    double lo = 0.0, hi = 0.0;
+    {
+      // packed index p in [0,30): level l = floor(log2(p+2)), pos = p + 2 - 2^l
+      const int p = lane;
+      if (p < 30) {
+        const int l = 31 - __clz(p + 2);
+        const long node = ((idx + 1) << l) - 1 + (p + 2 - (1 << l));
+        if (node < n_nodes) lo = tree[node];
+      }
+      const long node5 = ((idx + 1) << 5) - 1 + lane;
+      if (node5 < n_nodes) hi = tree[node5];
+    }
+    int pos = 0;  // position within the current relative level
+#pragma unroll
+    for (int l = 1; l <= 5; ++l) {
+      const long left = 2 * idx + 1;
+      if (left >= n_nodes) break;  // warp-uniform
+      const int lpos = 2 * pos;    // left child position in level l
+      double left_sum;
+      if (l < 5) left_sum = __shfl_sync(0xffffffffu, lo, (1 << l) - 2 + lpos);
+      else left_sum = __shfl_sync(0xffffffffu, hi, lpos);
+      if (value <= left_sum) { idx = left; pos = lpos; }
+      else { idx = left + 1; value = value - left_sum; pos = lpos + 1; }
+    }
+  }
+  if (lane == 0) {
+    // transform_to_valid_tree_indexes                                  redis_memory.py:242-264
+    long d = idx - C + 1;
+    const long actor = d / actor_cap;
+    const long dist = (d % actor_cap) - index_actor[actor];
+    if (dist >= 0 && dist <= history) {
+      long t = (d + history - dist + 1) % actor_cap;
+      d = t + actor * actor_cap;
+    } else if (dist < 0 && dist >= -n_step) {
+      long t = (d - n_step - dist - 1) % actor_cap;
+      if (t < 0) t += actor_cap;  // python modulo
+      d = t + actor * actor_cap;
+    }
+    const long ti = d + C - 1;
+    tree_idx[q] = ti;
+    data_idx[q] = d;
+    priorities[q] = tree[ti];
+  }
+}
+
+// w = (capacity * p / p_total)^-beta / max(w)                           redis_memory.py:465-475
+// Non-positive priorities fall back to the uniform 1/capacity (redis_memory.py:446-456); their count
+// is reported so the host can apply the reference's resample-first policy if it wants to.
+__global__ void is_weights_kernel(int n, const double* __restrict__ tree, const double* __restrict__ priorities,
+                                  double capacity, double beta, double* __restrict__ w64, float* __restrict__ w32,
+                                  int* __restrict__ n_nonpositive) {
+  __shared__ double red[32];
+  __shared__ int cnt;
+  if (threadIdx.x == 0) cnt = 0;
+  __syncthreads();
+  const double p_total = tree[0];
+  double mx = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    double p = priorities[i];
+    if (p <= 0.0) { p = 1.0 / capacity; atomicAdd(&cnt, 1); }
+    const double w = pow(capacity * (p / p_total), -beta);
+    w64[i] = w;
+    mx = fmax(mx, w);
+  }
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    mx = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (threadIdx.x == 0) red[0] = mx;
+  }
+  __syncthreads();
+  mx = red[0];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double w = w64[i] / mx;
+    w64[i] = w;
+    w32[i] = (float)w;
+  }
+  if (threadIdx.x == 0 && n_nonpositive) *n_nonpositive = cnt;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Update
+// ------------------------------------------------------------------------------------------------
+// priorities = np.power(loss_f32, float32(omega))  (redis_memory.py:560) evaluated as a correctly
+// rounded float: double pow then one rounding.  exponent < 0 sentinel => priorities passed through.
+__global__ void update_prepare_kernel(int n, const double* __restrict__ tree, const int64_t* __restrict__ idx,
+                                      const float* __restrict__ loss, float exponent, int apply_pow,
+                                      float* __restrict__ new_pri, double* __restrict__ diff,
+                                      double* __restrict__ max_priority) {
+  __shared__ float red[32];
+  float mx = -INFINITY;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    float p = loss[j];
+    if (apply_pow) p = (float)pow((double)p, (double)exponent);
+    new_pri[j] = p;
+    diff[j] = (double)p - tree[idx[j]];
+    mx = fmaxf(mx, p);
+  }
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    mx = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : -INFINITY;
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (threadIdx.x == 0 && (double)mx > *max_priority) *max_priority = (double)mx;   // :150-151
+  }
+}
+
+// numpy pairwise summation (np.sum of a contiguous float64 vector == 0 + pairwise(a, n)).
+__device__ double np_pairwise_sum(const double* a, int n) {
+  if (n < 8) {
+    double r = 0.0;
+    for (int i = 0; i < n; ++i) r += a[i];
+    return r;
+  }
+  if (n <= 128) {
+    double r[8];
+    for (int k = 0; k < 8; ++k) r[k] = a[k];
+    int i = 8;
+    for (; i < n - (n % 8); i += 8)
+      for (int k = 0; k < 8; ++k) r[k] += a[i + k];
+    double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < n; ++i) res += a[i];
+    return res;
+  }
+  int n2 = n / 2;
+  n2 -= n2 % 8;
+  return np_pairwise_sum(a, n2) + np_pairwise_sum(a + n2, n - n2);
+}
+
+// One CTA per tree level (blockIdx.x = number of parent steps from the leaf); the last CTA does the
+// root.  Within a level, the first batch entry that touches a node applies all of that node's diffs in
+// batch order (sequential float64 adds, like the reference's per-entry INCRBYFLOAT stream).
+__global__ void update_propagate_kernel(int n, int n_levels, double* __restrict__ tree,
+                                        const int64_t* __restrict__ idx, const double* __restrict__ diff) {
+  extern __shared__ unsigned char smem_raw[];
+  int64_t* node = reinterpret_cast<int64_t*>(smem_raw);
+  double* sd = reinterpret_cast<double*>(node + n);
+  const int level = blockIdx.x;
+  if (level == n_levels) {  // root: tree[0] += np.sum(diffs)
+    for (int j = threadIdx.x; j < n; j += blockDim.x) sd[j] = diff[j];
+    __syncthreads();
+    if (threadIdx.x == 0) tree[0] = tree[0] + (0.0 + np_pairwise_sum(sd, n));
+    return;
+  }
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    int64_t i = idx[j];
+    for (int l = 0; l < level; ++l) i = (i - 1) >> 1;  // floor division; 0 -> -1 -> -1 ...
+    node[j] = i;
+    sd[j] = diff[j];
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    const int64_t me = node[j];
+    if (me <= 0) continue;  // root handled separately; negatives hit the reference's junk key
+    bool leader = true;
+    for (int k = 0; k < j; ++k)
+      if (node[k] == me) { leader = false; break; }
+    if (!leader) continue;
+    double acc = tree[me];
+    for (int k = j; k < n; ++k)
+      if (node[k] == me) acc += sd[k];
+    tree[me] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Frame store
+// ------------------------------------------------------------------------------------------------
+constexpr int FRAME_BYTES = 84 * 84;  // 7056 = 441 * 16
+
+// append_actor_buffer, frame half: slots (start + i) % actor_cap + actor*actor_cap   (:159-165,174-199)
+__global__ void replay_append_kernel(int n, int actor_cap, int id_actor, int start, const uint8_t* __restrict__ frames,
+                                     const int32_t* __restrict__ timestep, const int32_t* __restrict__ action,
+                                     const float* __restrict__ reward, const uint8_t* __restrict__ nonterminal,
+                                     uint8_t* __restrict__ s_frames, int32_t* __restrict__ s_timestep,
+                                     int32_t* __restrict__ s_action, float* __restrict__ s_reward,
+                                     uint8_t* __restrict__ s_nonterminal) {
+  const int i = blockIdx.x;
+  const long slot = (long)((start + i) % actor_cap) + (long)id_actor * actor_cap;
+  const uint4* src = reinterpret_cast<const uint4*>(frames + (long)i * FRAME_BYTES);
+  uint4* dst = reinterpret_cast<uint4*>(s_frames + slot * FRAME_BYTES);
+  for (int t = threadIdx.x; t < FRAME_BYTES / 16; t += blockDim.x) dst[t] = src[t];
+  if (threadIdx.x == 0) {
+    s_timestep[slot] = timestep[i];
+    s_action[slot] = action[i];
+    s_reward[slot] = reward[i];
+    s_nonterminal[slot] = nonterminal[i];
+  }
+}
+
+// Transition assembly (redis_memory.py:347-369,479-541): 7-frame window idx-3..idx+3 inside the actor's
+// ring, blank frames across episode boundaries, n-step return in float64, output the uint8 window
+// (B, history+n, 84, 84): states = window[:, :history], next_states = window[:, n:n+history].
+__global__ void frame_gather_kernel(int B, int actor_cap, int history, int n_step, const int64_t* __restrict__ data_idx,
+                                    const uint8_t* __restrict__ s_frames, const int32_t* __restrict__ s_timestep,
+                                    const int32_t* __restrict__ s_action, const float* __restrict__ s_reward,
+                                    const uint8_t* __restrict__ s_nonterminal, const double* __restrict__ gamma_pow,
+                                    uint8_t* __restrict__ window, int64_t* __restrict__ actions,
+                                    float* __restrict__ returns, float* __restrict__ nonterminals) {
+  const int b = blockIdx.x;
+  const int L = history + n_step;
+  __shared__ long slots[16];
+  __shared__ int blank[16];
+  if (threadIdx.x == 0) {
+    const long d = data_idx[b];
+    const long actor = d / actor_cap;
+    int ts[16], nt[16];
+    for (int k = 0; k < L; ++k) {
+      long pos = (k + d - history + 1) % actor_cap;
+      if (pos < 0) pos += actor_cap;
+      slots[k] = pos + actor * actor_cap;
+      ts[k] = s_timestep[slots[k]];
+      nt[k] = s_nonterminal[slots[k]];
+      blank[k] = 0;
+    }
+    for (int t = history - 2; t >= 0; --t)
+      if (ts[t + 1] == 0) { blank[t] = 1; ts[t] = 0; nt[t] = 0; }
+    for (int t = history; t < L; ++t)
+      if (!nt[t - 1]) { blank[t] = 1; ts[t] = 0; nt[t] = 0; }
+    double ret = 0.0;
+    for (int k = 0; k < n_step; ++k) {
+      const int t = history + k - 1;
+      const double r = blank[t] ? 0.0 : (double)s_reward[slots[t]];
+      ret = ret + gamma_pow[k] * r;
+    }
+    returns[b] = (float)ret;
+    actions[b] = s_action[slots[history - 1]];
+    nonterminals[b] = nt[L - 1] ? 1.f : 0.f;
+  }
+  __syncthreads();
+  constexpr int V = FRAME_BYTES / 16;
+  for (int t = threadIdx.x; t < L * V; t += blockDim.x) {
+    const int k = t / V, o = t % V;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (!blank[k]) v = reinterpret_cast<const uint4*>(s_frames + slots[k] * FRAME_BYTES)[o];
+    reinterpret_cast<uint4*>(window + ((long)b * L + k) * FRAME_BYTES)[o] = v;
+  }
+}
+
+}  // namespace riqn
+
+using namespace riqn;
+
+RIQN_API int riqn_sumtree_stratified(int n, unsigned long long seed, unsigned long long stream_id, const double* tree,
+                                     double* values, void* stream) {
+  if (n <= 0 || n > 12000) return (int)cudaErrorInvalidValue;
+  stratified_kernel<<<1, 1024, sizeof(int) * n, (cudaStream_t)stream>>>(n, seed, stream_id, tree, values);
+  return (int)cudaGetLastError();
+}
+
+RIQN_API int riqn_sumtree_sample(int n, long capacity, int actor_capacity, const double* tree, const double* values,
+                                 const long long* index_actor, int history, int n_step, long long* tree_idx,
+                                 long long* data_idx, double* priorities, void* stream) {
+  if (n <= 0) return 0;
+  const int warps_per_block = 4;
+  sumtree_sample_kernel<<<riqn_cdiv(n, warps_per_block), warps_per_block * 32, 0, (cudaStream_t)stream>>>(
+      n, capacity, actor_capacity, tree, values, (const int64_t*)index_actor, history, n_step, (int64_t*)tree_idx,
+      (int64_t*)data_idx, priorities);
+  return (int)cudaGetLastError();
+}
+
+RIQN_API int riqn_sumtree_is_weights(int n, const double* tree, const double* priorities, double current_capacity,
+                                     double priority_weight, double* w64, float* w32, int* n_nonpositive, void* stream) {
+  is_weights_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(n, tree, priorities, current_capacity, priority_weight, w64,
+                                                          w32, n_nonpositive);
+  return (int)cudaGetLastError();
+}
+
+RIQN_API int riqn_sumtree_update(int n, long capacity, double* tree, const long long* tree_idx, const float* loss,
+                                 float priority_exponent, int apply_pow, float* new_priorities, double* diff_scratch,
+                                 double* max_priority, void* stream) {
+  if (n <= 0) return 0;
+  if (n > 5000) return (int)cudaErrorInvalidValue;  // shared-memory bound of the propagate kernel
+  cudaStream_t s = (cudaStream_t)stream;
+  update_prepare_kernel<<<1, 1024, 0, s>>>(n, tree, (const int64_t*)tree_idx, loss, priority_exponent, apply_pow,
+                                           new_priorities, diff_scratch, max_priority);
+  RIQN_LAUNCH_CHECK();
+  int n_levels = 0;  // parent steps needed to bring the deepest leaf (index 2C-2) to the root
+  for (long i = 2 * capacity - 2; i > 0; i = (i - 1) / 2) ++n_levels;
+  const size_t smem = (size_t)n * 16;
+  static bool attr = false;
+  if (!attr) {
+    RIQN_CUDA(cudaFuncSetAttribute(update_propagate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    attr = true;
+  }
+  update_propagate_kernel<<<n_levels + 1, 512, smem, s>>>(n, n_levels, tree, (const int64_t*)tree_idx, diff_scratch);
+  return (int)cudaGetLastError();
+}
+
+RIQN_API int riqn_replay_append(int n, int actor_capacity, int id_actor, int start, const unsigned char* frames,
+                                const int* timestep, const int* action, const float* reward,
+                                const unsigned char* nonterminal, unsigned char* s_frames, int* s_timestep, int* s_action,
+                                float* s_reward, unsigned char* s_nonterminal, void* stream) {
+  if (n <= 0) return 0;
+  replay_append_kernel<<<n, 128, 0, (cudaStream_t)stream>>>(n, actor_capacity, id_actor, start, frames, timestep, action,
+                                                            reward, nonterminal, s_frames, s_timestep, s_action, s_reward,
+                                                            s_nonterminal);
+  return (int)cudaGetLastError();
+}
+
+RIQN_API int riqn_frame_gather(int batch, int actor_capacity, int history, int n_step, const long long* data_idx,
+                               const unsigned char* s_frames, const int* s_timestep, const int* s_action,
+                               const float* s_reward, const unsigned char* s_nonterminal, const double* gamma_pow,
+                               unsigned char* window, long long* actions, float* returns, float* nonterminals,
+                               void* stream) {
+  if (batch <= 0) return 0;
+  if (history + n_step > 16) return (int)cudaErrorInvalidValue;
+  frame_gather_kernel<<<batch, 256, 0, (cudaStream_t)stream>>>(batch, actor_capacity, history, n_step,
+                                                               (const int64_t*)data_idx, s_frames, s_timestep, s_action,
+                                                               s_reward, s_nonterminal, gamma_pow, window,
+                                                               (int64_t*)actions, returns, nonterminals);
+  return (int)cudaGetLastError();
+}

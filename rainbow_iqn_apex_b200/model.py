@@ -1,0 +1,375 @@
+"""DQN / NoisyLinear with the reference's API and state_dict keys, computed by libriqn_b200.so.
+
+Mirrors ``rainbowiqn/model.py`` of the reference (NoisyLinear :9-53, DQN :56-162):
+same constructor arguments, same parameter / buffer names and shapes
+(``conv{1,2,3}.{weight,bias}``, ``iqn_fc.{weight,bias}``,
+``fcnoisy_{h_v,h_a,z_v,z_a}.{weight_mu,weight_sigma,bias_mu,bias_sigma,weight_epsilon,bias_epsilon}``),
+same ``forward(x, num_quantiles)`` -> ``(q (Nq*B, A), quantiles (Nq*B, 1))`` row convention
+(row = quantile * B + sample) and same ``reset_noise()`` semantics.
+
+B200-native layout: all trainable parameters live in ONE flat fp32 arena in HBM (gradients and the
+Adam moments in matching arenas), ordered so that fcnoisy_h_v|fcnoisy_h_a form a single
+(2*hidden, 3136) operand and fcnoisy_z_v|fcnoisy_z_a a single (1+A, hidden) operand.  The nn.Parameters
+are views of the arena, so torch's state_dict / load_state_dict / checkpoints keep working while the
+optimiser and the gradient all-reduce touch one contiguous buffer.
+
+There is no PyTorch fallback: every tensor operation below is a C-ABI call (include/riqn_b200.h).
+"""
+import math
+from types import SimpleNamespace
+
+import torch
+from torch import nn
+
+from . import _lib
+from ._lib import ConvGeom, call, ptr
+
+FEAT = 3136
+_ALIGN = 64  # floats; arena groups start on 256-byte boundaries
+
+
+class NoisyLinear(nn.Module):
+    """Factorised-noise linear layer (reference model.py:9-53)."""
+
+    def __init__(self, in_features, out_features, std_init, disable_cuda=False):
+        super().__init__()
+        self.disable_cuda = disable_cuda
+        self.in_features = in_features
+        self.out_features = out_features
+        self.std_init = std_init
+        self.weight_mu = nn.Parameter(torch.empty(out_features, in_features))
+        self.weight_sigma = nn.Parameter(torch.empty(out_features, in_features))
+        self.register_buffer("weight_epsilon", torch.zeros(out_features, in_features))
+        self.bias_mu = nn.Parameter(torch.empty(out_features))
+        self.bias_sigma = nn.Parameter(torch.empty(out_features))
+        self.register_buffer("bias_epsilon", torch.zeros(out_features))
+        # scratch for the factor vectors f(eps_in), f(eps_out) and the composed weights (set by DQN)
+        self._eps_in = None
+        self._eps_out = None
+        self._w_eff = None
+        self._b_eff = None
+        self._noise_calls = 0
+        self._layer_id = 0  # distinct Philox streams per layer (set by DQN)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        """model.py:25-30"""
+        mu_range = 1 / math.sqrt(self.in_features)
+        self.weight_mu.data.uniform_(-mu_range, mu_range)
+        self.weight_sigma.data.fill_(self.std_init / math.sqrt(self.in_features))
+        self.bias_mu.data.uniform_(-mu_range, mu_range)
+        self.bias_sigma.data.fill_(self.std_init / math.sqrt(self.out_features))
+
+    def _ensure_scratch(self):
+        dev = self.weight_mu.device
+        if self._eps_in is None or self._eps_in.device != dev:
+            self._eps_in = torch.empty(self.in_features, device=dev)
+            self._eps_out = torch.empty(self.out_features, device=dev)
+        if self._w_eff is None or self._w_eff.device != dev:
+            self._w_eff = torch.empty(self.out_features, self.in_features, device=dev)
+            self._b_eff = torch.empty(self.out_features, device=dev)
+
+    def reset_noise(self, eps_in=None, eps_out=None, seed=None):
+        """model.py:39-43.  ``eps_in``/``eps_out`` inject already-scaled factor vectors (parity runs);
+        otherwise they are drawn on the device (Philox) as f(N(0,1)), f(x)=sign(x)sqrt|x| (model.py:32-37)."""
+        self._ensure_scratch()
+        if eps_in is None:
+            if seed is None:
+                seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+            base = (self._layer_id << 40) + 2 * self._noise_calls
+            call("riqn_noisy_sample", self.in_features, seed, base, ptr(self._eps_in))
+            call("riqn_noisy_sample", self.out_features, seed, base + 1, ptr(self._eps_out))
+            self._noise_calls += 1
+        else:
+            self._eps_in.copy_(eps_in)
+            self._eps_out.copy_(eps_out)
+        self._compose(resample=True)
+
+    def _compose(self, resample=False):
+        self._ensure_scratch()
+        call("riqn_noisy_compose", self.out_features, self.in_features, ptr(self.weight_mu), ptr(self.weight_sigma),
+             ptr(self.weight_epsilon), ptr(self._eps_in) if resample else None,
+             ptr(self._eps_out) if resample else None, ptr(self.bias_mu), ptr(self.bias_sigma),
+             ptr(self.bias_epsilon), ptr(self._w_eff), ptr(self._b_eff), 1 if self.training else 0)
+
+    def forward(self, input):
+        """model.py:45-53 (inference helper; the learner path goes through DQN's fused ops)."""
+        self._compose()
+        x = input.contiguous().float()
+        out = torch.empty(x.shape[0], self.out_features, device=x.device)
+        call("riqn_gemm_f32", x.shape[0], self.out_features, self.in_features, ptr(x), self.in_features, 1,
+             ptr(self._w_eff), self.in_features, 1, ptr(out), self.out_features)
+        return out + self._b_eff
+
+
+def _geom(batch, cin, h, cout, k, stride, pad, in_bstride=None):
+    oh = (h + 2 * pad - k) // stride + 1
+    return ConvGeom(batch, cin, h, h, cout, k, k, stride, pad, oh, oh, in_bstride if in_bstride else cin * h * h)
+
+
+class DQN(nn.Module):
+    """Reference model.py:56-162 (IQN branch; the C51 branch lives in c51.py)."""
+
+    def __init__(self, args, action_space):
+        super().__init__()
+        self.rainbow_only = args.rainbow_only
+        self.action_space = action_space
+        self.device = args.device
+        self.disable_cuda = args.disable_cuda
+        self.history = args.history_length
+        self.hidden = args.hidden_size
+        if self.hidden != 512:
+            raise ValueError("the sm_100a kernels are specialised for hidden_size == 512")
+        self.conv1 = nn.Conv2d(args.history_length, 32, 8, stride=4, padding=1)
+        self.conv2 = nn.Conv2d(32, 64, 4, stride=2)
+        self.conv3 = nn.Conv2d(64, 64, 3)
+        if self.rainbow_only:
+            self.atoms = args.atoms
+            zv, za = self.atoms, action_space * self.atoms
+        else:
+            self.quantile_embedding_dim = args.quantile_embedding_dim
+            self.iqn_fc = nn.Linear(self.quantile_embedding_dim, FEAT)
+            zv, za = 1, action_space
+        kw = dict(std_init=args.noisy_std, disable_cuda=args.disable_cuda)
+        # "fcnoisy" in the name marks the noisy layers (model.py:159-162)
+        self.fcnoisy_h_v = NoisyLinear(FEAT, args.hidden_size, **kw)
+        self.fcnoisy_h_a = NoisyLinear(FEAT, args.hidden_size, **kw)
+        self.fcnoisy_z_v = NoisyLinear(args.hidden_size, zv, **kw)
+        self.fcnoisy_z_a = NoisyLinear(args.hidden_size, za, **kw)
+        for i, m in enumerate((self.fcnoisy_h_v, self.fcnoisy_h_a, self.fcnoisy_z_v, self.fcnoisy_z_a)):
+            m._layer_id = i + 1
+        self._tau_calls = 0
+        self._rng_seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        self._flatten()
+        if self._flat.is_cuda:
+            self.reset_noise()
+
+    # ------------------------------------------------------------------ arenas
+    def _param_groups_in_arena_order(self):
+        g = [[self.conv1.weight], [self.conv1.bias], [self.conv2.weight], [self.conv2.bias],
+             [self.conv3.weight], [self.conv3.bias]]
+        if not self.rainbow_only:
+            g += [[self.iqn_fc.weight], [self.iqn_fc.bias]]
+        hv, ha, zv, za = self.fcnoisy_h_v, self.fcnoisy_h_a, self.fcnoisy_z_v, self.fcnoisy_z_a
+        g += [[hv.weight_mu, ha.weight_mu], [hv.weight_sigma, ha.weight_sigma],
+              [hv.bias_mu, ha.bias_mu], [hv.bias_sigma, ha.bias_sigma],
+              [zv.weight_mu, za.weight_mu], [zv.weight_sigma, za.weight_sigma],
+              [zv.bias_mu, za.bias_mu], [zv.bias_sigma, za.bias_sigma]]
+        return g
+
+    def _flatten(self):
+        """(Re)build the flat parameter / gradient / epsilon arenas on the parameters' current device."""
+        groups = self._param_groups_in_arena_order()
+        dev = groups[0][0].device
+        total = 0
+        offsets = []
+        for grp in groups:
+            total = (total + _ALIGN - 1) // _ALIGN * _ALIGN
+            for p in grp:
+                offsets.append(total)
+                total += p.numel()
+        total = (total + _ALIGN - 1) // _ALIGN * _ALIGN
+        flat = torch.zeros(total, device=dev, dtype=torch.float32)
+        flat_grad = torch.zeros(total, device=dev, dtype=torch.float32)
+        i = 0
+        self._offsets = {}
+        for grp in groups:
+            for p in grp:
+                off, n = offsets[i], p.numel()
+                flat[off:off + n].copy_(p.data.reshape(-1).float())
+                p.data = flat[off:off + n].view(p.shape)
+                p.grad = flat_grad[off:off + n].view(p.shape)
+                self._offsets[id(p)] = off
+                i += 1
+        self._flat, self._flat_grad = flat, flat_grad
+        # epsilon arena: [h_v.weight_epsilon | h_a.weight_epsilon], h bias eps, [z_v | z_a] weight eps, z bias eps
+        hv, ha, zv, za = self.fcnoisy_h_v, self.fcnoisy_h_a, self.fcnoisy_z_v, self.fcnoisy_z_a
+        eg = [[(hv, "weight_epsilon"), (ha, "weight_epsilon")], [(hv, "bias_epsilon"), (ha, "bias_epsilon")],
+              [(zv, "weight_epsilon"), (za, "weight_epsilon")], [(zv, "bias_epsilon"), (za, "bias_epsilon")]]
+        etotal, eoffs = 0, []
+        for grp in eg:
+            etotal = (etotal + _ALIGN - 1) // _ALIGN * _ALIGN
+            for m, name in grp:
+                eoffs.append(etotal)
+                etotal += m._buffers[name].numel()
+        eflat = torch.zeros(etotal + _ALIGN, device=dev, dtype=torch.float32)
+        i = 0
+        for grp in eg:
+            for m, name in grp:
+                old = m._buffers[name]
+                n = old.numel()
+                eflat[eoffs[i]:eoffs[i] + n].copy_(old.reshape(-1).float())
+                m._buffers[name] = eflat[eoffs[i]:eoffs[i] + n].view(old.shape)
+                i += 1
+        self._eps_flat = eflat
+        # composed (effective) weights, concatenated like the arenas
+        hid = self.hidden
+        nz = zv.out_features + za.out_features
+        self._w_eff_h = torch.empty(2 * hid, FEAT, device=dev)
+        self._b_eff_h = torch.empty(2 * hid, device=dev)
+        self._w_eff_z = torch.empty(nz, hid, device=dev)
+        self._b_eff_z = torch.empty(nz, device=dev)
+        hv._w_eff, ha._w_eff = self._w_eff_h[:hid], self._w_eff_h[hid:]
+        hv._b_eff, ha._b_eff = self._b_eff_h[:hid], self._b_eff_h[hid:]
+        zv._w_eff, za._w_eff = self._w_eff_z[:zv.out_features], self._w_eff_z[zv.out_features:]
+        zv._b_eff, za._b_eff = self._b_eff_z[:zv.out_features], self._b_eff_z[zv.out_features:]
+        for m in (hv, ha, zv, za):
+            m._eps_in = torch.empty(m.in_features, device=dev)
+            m._eps_out = torch.empty(m.out_features, device=dev)
+
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        self._flatten()
+        if self._flat.is_cuda:
+            self.reset_noise()  # NoisyLinear.__init__ resets noise in the reference (model.py:23)
+        return out
+
+    def zero_grad(self, set_to_none=False):
+        """One memset over the gradient arena; the .grad views stay bound (learner.py:22)."""
+        self._flat_grad.zero_()
+        for grp in self._param_groups_in_arena_order():
+            for p in grp:
+                if p.grad is None or p.grad.data_ptr() != self._flat_grad.data_ptr() + 4 * self._offsets[id(p)]:
+                    off = self._offsets[id(p)]
+                    p.grad = self._flat_grad[off:off + p.numel()].view(p.shape)
+
+    def grad_view(self, p):
+        off = self._offsets[id(p)]
+        return self._flat_grad[off:off + p.numel()].view(p.shape)
+
+    def noisy_layers(self):
+        return [(n, m) for n, m in self.named_children() if "fcnoisy" in n]
+
+    # ------------------------------------------------------------------ noise
+    def reset_noise(self, noise=None):
+        """model.py:159-162.  ``noise``: optional {layer_name: (f(eps_in), f(eps_out))} injection."""
+        for name, module in self.noisy_layers():
+            if noise is not None:
+                e_in, e_out = noise[name]
+                module.reset_noise(e_in.to(self._flat.device), e_out.to(self._flat.device))
+            else:
+                module.reset_noise(seed=self._rng_seed)
+
+    def compose_weights(self):
+        """Recompute the effective weights from the stored epsilons (after load_state_dict / optimiser steps)."""
+        for _, module in self.noisy_layers():
+            module._compose()
+
+    def draw_quantiles(self, n):
+        tau = torch.empty(n, 1, device=self._flat.device)
+        call("riqn_fill_uniform", n, self._rng_seed ^ 0x7A75, self._tau_calls, ptr(tau))
+        self._tau_calls += 1
+        return tau
+
+    # ------------------------------------------------------------------ forward pieces
+    def trunk(self, x, keep=None):
+        """conv1-3 + ReLU -> (B, 3136).  x: (B, history, 84, 84) uint8 (scaled by 1/255 on the fly) or
+        fp32; may be a view with a larger batch stride (the replay window).  model.py:115-118"""
+        _lib.require_device()
+        B = x.shape[0]
+        if x.dtype not in (torch.uint8, torch.float32):
+            x = x.float()
+        if x.stride()[1:] != (84 * 84, 84, 1):
+            x = x.contiguous()
+        is_u8 = 1 if x.dtype == torch.uint8 else 0
+        dev = x.device
+        g1 = _geom(B, self.history, 84, 32, 8, 4, 1, in_bstride=x.stride(0))
+        g2 = _geom(B, 32, 20, 64, 4, 2, 0)
+        g3 = _geom(B, 64, 9, 64, 3, 1, 0)
+        col1 = torch.empty(B * 400, self.history * 64, device=dev)
+        out1 = torch.empty(B, 32, 20, 20, device=dev)
+        call("riqn_conv_fwd", g1, ptr(x), is_u8, ptr(self.conv1.weight), ptr(self.conv1.bias), ptr(col1), ptr(out1))
+        col2 = torch.empty(B * 81, 512, device=dev)
+        out2 = torch.empty(B, 64, 9, 9, device=dev)
+        call("riqn_conv_fwd", g2, ptr(out1), 0, ptr(self.conv2.weight), ptr(self.conv2.bias), ptr(col2), ptr(out2))
+        col3 = torch.empty(B * 49, 576, device=dev)
+        out3 = torch.empty(B, 64, 7, 7, device=dev)
+        call("riqn_conv_fwd", g3, ptr(out2), 0, ptr(self.conv3.weight), ptr(self.conv3.bias), ptr(col3), ptr(out3))
+        if keep is not None:
+            keep.update(x=x, g=(g1, g2, g3), col=(col1, col2, col3), out=(out1, out2, out3))
+        return out3.view(B, FEAT)
+
+    def iqn_head(self, feat, num_quantiles, tau, keep=None):
+        """Quantile embedding, Hadamard, noisy hidden layers, z-layers, dueling.  model.py:131-157"""
+        B = feat.shape[0]
+        R = B * num_quantiles
+        dev = feat.device
+        E, hid, A = self.quantile_embedding_dim, self.hidden, self.action_space
+        cosv = torch.empty(R, E, device=dev)
+        xt = torch.empty(R, FEAT, device=dev)
+        call("riqn_quantile_embed_fwd", B, num_quantiles, E, FEAT, ptr(tau), ptr(feat), ptr(self.iqn_fc.weight),
+             ptr(self.iqn_fc.bias), ptr(cosv), ptr(xt))
+        h = torch.empty(R, 2 * hid, device=dev)
+        call("riqn_noisy_linear_fwd", R, FEAT, 2 * hid, ptr(xt), ptr(self._w_eff_h), ptr(self._b_eff_h), ptr(h))
+        q = torch.empty(R, A, device=dev)
+        call("riqn_dueling_fwd", R, hid, A, ptr(h), ptr(self._w_eff_z), ptr(self._b_eff_z), ptr(q))
+        if keep is not None:
+            keep.update(feat=feat, cos=cosv, xt=xt, h=h, q=q, tau=tau, num_quantiles=num_quantiles)
+        return q
+
+    def forward(self, x, num_quantiles=None, log=False, tau=None, keep=None, fresh_weights=False):
+        """model.py:112-157.  Returns (q, quantiles) in IQN mode."""
+        if self.rainbow_only:
+            from . import c51
+            return c51.forward(self, x, log=log, keep=keep, fresh_weights=fresh_weights)
+        if not fresh_weights:
+            self.compose_weights()
+        feat = self.trunk(x, keep)
+        if tau is None:
+            tau = self.draw_quantiles(num_quantiles * x.shape[0])
+        else:
+            tau = tau.to(feat.device, torch.float32).reshape(-1, 1).contiguous()
+        q = self.iqn_head(feat, num_quantiles, tau, keep)
+        return q, tau
+
+    # ------------------------------------------------------------------ backward of forward()
+    def backward_iqn(self, keep, dtheta, gscale, actions):
+        """Accumulate dL/dparams into the gradient arena for the forward recorded in ``keep``, where
+        dL/dq[r, actions[b]] = dtheta[r] * gscale[b]  (r = quantile*B + b)."""
+        B = keep["feat"].shape[0]
+        Nq = keep["num_quantiles"]
+        R = B * Nq
+        dev = keep["feat"].device
+        hid, A, E = self.hidden, self.action_space, self.quantile_embedding_dim
+        hv, ha, zv, za = self.fcnoisy_h_v, self.fcnoisy_h_a, self.fcnoisy_z_v, self.fcnoisy_z_a
+        gv = self.grad_view
+        dh = torch.empty(R, 2 * hid, device=dev)
+        dz = torch.empty(R, 32, device=dev)
+        call("riqn_dueling_bwd", R, B, hid, A, ptr(keep["h"]), ptr(self._w_eff_z), ptr(dtheta), ptr(gscale),
+             ptr(actions), ptr(dh), ptr(dz))
+        dwz = torch.empty(32, 2 * hid, device=dev)
+        dbz = torch.empty(32, device=dev)
+        call("riqn_z_wgrad", R, hid, A, ptr(dz), ptr(keep["h"]), ptr(dwz), ptr(dbz),
+             ptr(zv.weight_epsilon), ptr(zv.bias_epsilon), ptr(za.weight_epsilon), ptr(za.bias_epsilon),
+             ptr(gv(zv.weight_mu)), ptr(gv(zv.weight_sigma)), ptr(gv(zv.bias_mu)), ptr(gv(zv.bias_sigma)),
+             ptr(gv(za.weight_mu)), ptr(gv(za.weight_sigma)), ptr(gv(za.bias_mu)), ptr(gv(za.bias_sigma)))
+        dbs = torch.empty(2 * hid, device=dev)
+        # [h_v | h_a] are adjacent in every arena, so one (2*hid, 3136) product serves both layers
+        call("riqn_noisy_linear_wgrad", R, FEAT, 2 * hid, ptr(dh), ptr(keep["xt"]), ptr(hv.weight_epsilon),
+             ptr(hv.bias_epsilon), ptr(dbs), ptr(gv(hv.weight_mu)), ptr(gv(hv.weight_sigma)), ptr(gv(hv.bias_mu)),
+             ptr(gv(hv.bias_sigma)))
+        dx = torch.empty(R, FEAT, device=dev)
+        call("riqn_noisy_linear_dgrad", R, FEAT, 2 * hid, ptr(dh), ptr(self._w_eff_h), ptr(dx))
+        dfeat = torch.empty(B, FEAT, device=dev)
+        call("riqn_quantile_embed_bwd", B, Nq, E, FEAT, ptr(keep["xt"]), ptr(keep["feat"]), ptr(keep["cos"]), ptr(dx),
+             ptr(dfeat), ptr(gv(self.iqn_fc.weight)), ptr(gv(self.iqn_fc.bias)))
+        self.backward_trunk(keep, dfeat)
+
+    def backward_trunk(self, keep, dfeat):
+        (g1, g2, g3), (col1, col2, col3), (out1, out2, out3) = keep["g"], keep["col"], keep["out"]
+        dev = dfeat.device
+        gv = self.grad_view
+        B = out1.shape[0]
+        d_out2 = torch.empty_like(out2)
+        dY3 = torch.empty(B * 49, 64, device=dev)
+        dcol3 = torch.empty_like(col3)
+        call("riqn_conv_bwd", g3, ptr(dfeat), ptr(out3), ptr(col3), ptr(self.conv3.weight), ptr(dY3), ptr(dcol3),
+             ptr(gv(self.conv3.weight)), ptr(gv(self.conv3.bias)), ptr(d_out2))
+        d_out1 = torch.empty_like(out1)
+        dY2 = torch.empty(B * 81, 64, device=dev)
+        dcol2 = torch.empty_like(col2)
+        call("riqn_conv_bwd", g2, ptr(d_out2), ptr(out2), ptr(col2), ptr(self.conv2.weight), ptr(dY2), ptr(dcol2),
+             ptr(gv(self.conv2.weight)), ptr(gv(self.conv2.bias)), ptr(d_out1))
+        dY1 = torch.empty(B * 400, 32, device=dev)
+        call("riqn_conv_bwd", g1, ptr(d_out1), ptr(out1), ptr(col1), ptr(self.conv1.weight), ptr(dY1), None,
+             ptr(gv(self.conv1.weight)), ptr(gv(self.conv1.bias)), None)

@@ -1,0 +1,169 @@
+"""GPU: per-op parity of the CUDA kernels (through the C-ABI) against the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import load_params, make_args, rel_err
+from oracle import cases, losses, network as net
+
+pytestmark = pytest.mark.gpu
+
+
+def _call():
+    from rainbow_iqn_apex_b200._lib import call, ptr
+    return call, ptr
+
+
+@pytest.mark.parametrize("M,N,K,ta,tb", [(130, 70, 33, False, False), (257, 129, 64, True, False),
+                                         (64, 300, 1000, False, True), (19, 1024, 777, True, True)])
+def test_gemm_f32_strided(cuda_dev, M, N, K, ta, tb):
+    call, ptr = _call()
+    rs = np.random.RandomState(0)
+    A = rs.standard_normal((M, K)).astype(np.float32)
+    B = rs.standard_normal((N, K)).astype(np.float32)
+    ref = A.astype(np.float64) @ B.astype(np.float64).T
+    a = torch.from_numpy(A.T.copy() if ta else A).to(cuda_dev)
+    b = torch.from_numpy(B.T.copy() if tb else B).to(cuda_dev)
+    c = torch.empty(M, N, device=cuda_dev)
+    sa = (1, M) if ta else (K, 1)
+    sb = (1, N) if tb else (K, 1)
+    call("riqn_gemm_f32", M, N, K, ptr(a), sa[0], sa[1], ptr(b), sb[0], sb[1], ptr(c), N)
+    assert rel_err(c.cpu().numpy(), ref) < 1e-5
+
+
+@pytest.fixture(scope="module")
+def nets(cuda_dev):
+    from rainbow_iqn_apex_b200.model import DQN
+    params = net.make_params(7)
+    d = DQN(make_args(cuda_dev), 18).to(cuda_dev)
+    load_params(d, params)
+    return d, params
+
+
+def test_trunk_u8_and_f32(cuda_dev, nets):
+    d, params = nets
+    b = cases.make_batch(3, 6)
+    p = net.to_torch(params)
+    ref = net.conv_trunk(p, torch.from_numpy(b["states"]).float().div_(255)).numpy()
+    got_u8 = d.trunk(torch.from_numpy(b["states"]).to(cuda_dev)).cpu().numpy()
+    got_f32 = d.trunk(torch.from_numpy(b["states"]).float().div_(255).to(cuda_dev)).cpu().numpy()
+    assert rel_err(got_u8, ref) < 1e-5
+    assert np.array_equal(got_u8, got_f32)          # u8 ingest == fp32/255 ingest, bit for bit
+    # strided window view (B, 7, 84, 84)[:, 3:7]
+    win = torch.from_numpy(np.concatenate([b["states"][:, :3], b["next_states"]], axis=1)).to(cuda_dev)
+    got_view = d.trunk(win[:, 3:7]).cpu().numpy()
+    ref2 = net.conv_trunk(p, torch.from_numpy(b["next_states"]).float().div_(255)).numpy()
+    assert rel_err(got_view, ref2) < 1e-5
+
+
+def test_forward_injected(cuda_dev, nets):
+    d, params = nets
+    B, Nq = 5, 8
+    b = cases.make_batch(4, B)
+    noise = net.make_noise(11)
+    tau = torch.from_numpy(np.random.RandomState(5).uniform(0, 1, (Nq * B, 1)).astype(np.float32))
+    p = net.apply_noise(net.to_torch(params), noise)
+    keep = {}
+    ref = net.dqn_forward_iqn(p, torch.from_numpy(b["states"]).float().div_(255), Nq, tau, keep=keep)
+    d.train()
+    d.reset_noise(noise)
+    k2 = {}
+    q, tau_out = d.forward(torch.from_numpy(b["states"]).to(cuda_dev), Nq, tau=tau, keep=k2, fresh_weights=True)
+    assert torch.equal(tau_out.cpu(), tau)
+    assert rel_err(k2["cos"].cpu().numpy(), keep["cos"].numpy()) < 2e-6
+    assert rel_err(k2["xt"].cpu().numpy(), keep["x"].numpy()) < 1e-5
+    assert rel_err(k2["h"][:, :512].cpu().numpy(), keep["h_v"].numpy()) < 1e-5
+    assert rel_err(k2["h"][:, 512:].cpu().numpy(), keep["h_a"].numpy()) < 1e-5
+    assert rel_err(q.cpu().numpy(), ref.numpy()) < 1e-5
+    # stored epsilons == outer product of the injected factors (model.py:39-43), bit for bit
+    assert torch.equal(d.fcnoisy_h_a.weight_epsilon.cpu(), torch.outer(noise["fcnoisy_h_a"][1], noise["fcnoisy_h_a"][0]))
+    # eval mode uses mu only (model.py:52-53)
+    d.eval()
+    q_eval, _ = d.forward(torch.from_numpy(b["states"]).to(cuda_dev), Nq, tau=tau)
+    ref_eval = net.dqn_forward_iqn(p, torch.from_numpy(b["states"]).float().div_(255), Nq, tau, training=False)
+    assert rel_err(q_eval.cpu().numpy(), ref_eval.numpy()) < 1e-5
+    d.train()
+
+
+@pytest.mark.parametrize("B,N,Np,kappa", [(7, 8, 8, 1.0), (33, 64, 64, 1.0), (4, 16, 40, 0.5), (3, 100, 9, 2.0)])
+def test_iqn_loss_kernel(cuda_dev, B, N, Np, kappa):
+    call, ptr = _call()
+    rs = np.random.RandomState(B)
+    A = 18
+    q_on = torch.from_numpy(rs.standard_normal((N * B, A)).astype(np.float32)).requires_grad_(True)
+    q_tg = torch.from_numpy(rs.standard_normal((Np * B, A)).astype(np.float32))
+    tau = torch.from_numpy(rs.uniform(0, 1, (N * B, 1)).astype(np.float32))
+    actions = torch.from_numpy(rs.randint(0, A, B).astype(np.int64))
+    a_star = torch.from_numpy(rs.randint(0, A, B).astype(np.int64))
+    returns = torch.from_numpy(rs.standard_normal(B).astype(np.float32))
+    nt = torch.from_numpy((rs.uniform(size=B) < 0.8).astype(np.float32))
+    g = 0.99 ** 3
+    target = (returns[:, None].repeat(Np, 1) + (g * nt[:, None]).repeat(Np, 1)
+              * q_tg.gather(1, a_star[:, None].repeat(Np, 1))).reshape(Np, B).t()
+    theta = q_on.gather(1, actions[:, None].repeat(N, 1)).reshape(N, B).t()
+    ref = losses.iqn_pairwise_loss(theta, target, tau.reshape(N, B).t(), kappa)
+    w = torch.from_numpy(rs.uniform(0.1, 1, B).astype(np.float32))
+    (w * ref).sum().backward()
+    dev = cuda_dev
+    loss = torch.empty(B, device=dev)
+    dth = torch.empty(N * B, device=dev)
+    th_o = torch.empty(B, N, device=dev)
+    tg_o = torch.empty(B, Np, device=dev)
+    call("riqn_iqn_loss_fwd_bwd", B, N, Np, A, ptr(q_on.detach().to(dev)), ptr(q_tg.to(dev)), ptr(tau.to(dev)),
+         ptr(actions.to(dev)), ptr(a_star.to(dev)), ptr(returns.to(dev)), ptr(nt.to(dev)), float(g), float(kappa),
+         ptr(loss), ptr(dth), ptr(th_o), ptr(tg_o))
+    assert np.array_equal(tg_o.cpu().numpy(), target.numpy())       # same fp32 op order as the reference
+    assert np.array_equal(th_o.cpu().numpy(), theta.detach().numpy())
+    assert rel_err(loss.cpu().numpy(), ref.detach().numpy()) < 1e-5   # loss kernel alone <= 1e-5
+    # dtheta[i*B+b] * w[b] == dL/dq_on[i*B+b, actions[b]]
+    gref = q_on.grad.gather(1, actions[:, None].repeat(N, 1)).reshape(N, B)
+    got = dth.cpu().reshape(N, B) * w[None, :]
+    assert rel_err(got.numpy(), gref.numpy()) < 1e-5
+
+
+def test_argmax_mean(cuda_dev):
+    call, ptr = _call()
+    rs = np.random.RandomState(1)
+    B, K, A = 37, 32, 18
+    q = torch.from_numpy(rs.standard_normal((K * B, A)).astype(np.float32))
+    ref = q.reshape(K, B, A).mean(0).argmax(1)
+    out = torch.empty(B, dtype=torch.int64, device=cuda_dev)
+    call("riqn_argmax_mean", B, K, A, ptr(q.to(cuda_dev)), ptr(out))
+    assert torch.equal(out.cpu(), ref)
+
+
+def test_adam_matches_torch(cuda_dev):
+    call, ptr = _call()
+    rs = np.random.RandomState(2)
+    n = 10007
+    p0 = rs.standard_normal(n).astype(np.float32)
+    p_ref = torch.nn.Parameter(torch.from_numpy(p0.copy()))
+    opt = torch.optim.Adam([p_ref], lr=5e-5, eps=3.125e-4)
+    p = torch.from_numpy(p0.copy()).to(cuda_dev)
+    m = torch.zeros(n, device=cuda_dev)
+    v = torch.zeros(n, device=cuda_dev)
+    for step in range(1, 4):
+        g = (rs.standard_normal(n) * 10.0 ** rs.randint(-6, 1, n)).astype(np.float32)
+        p_ref.grad = torch.from_numpy(g.copy())
+        opt.step()
+        call("riqn_adam_step", n, ptr(p), ptr(torch.from_numpy(g).to(cuda_dev)), ptr(m), ptr(v), step, 5e-5, 0.9,
+             0.999, 3.125e-4, 1.0)
+        assert np.allclose(p.cpu().numpy(), p_ref.detach().numpy(), rtol=0, atol=2e-9)
+    assert rel_err(m.cpu().numpy(), opt.state[p_ref]["exp_avg"].numpy()) < 1e-6
+
+
+def test_device_rng_statistics(cuda_dev):
+    call, ptr = _call()
+    n = 1 << 20
+    u = torch.empty(n, device=cuda_dev)
+    call("riqn_fill_uniform", n, 1234, 0, ptr(u))
+    u2 = torch.empty(n, device=cuda_dev)
+    call("riqn_fill_uniform", n, 1234, 1, ptr(u2))
+    a = u.cpu().numpy().astype(np.float64)
+    assert 0 < a.min() and a.max() < 1 and abs(a.mean() - 0.5) < 2e-3 and abs(a.var() - 1 / 12) < 1e-3
+    assert abs(np.corrcoef(a, u2.cpu().numpy())[0, 1]) < 5e-3
+    z = torch.empty(n, device=cuda_dev)
+    call("riqn_noisy_sample", n, 99, 0, ptr(z))
+    f = z.cpu().numpy().astype(np.float64)
+    x = np.sign(f) * f * f                      # invert f(x) = sign(x) sqrt|x|  -> N(0,1)
+    assert abs(x.mean()) < 5e-3 and abs(x.var() - 1) < 1e-2 and abs((x ** 4).mean() - 3) < 0.1

@@ -1,0 +1,191 @@
+"""GPU: device-resident sum-tree / frame store against the reference goldens and the numpy oracle.
+Bit-exact (float64 tree nodes, int64 indices, uint8 frames); IS weights to 1e-12 (CUDA pow is not
+correctly rounded, numpy's is)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import make_args
+from oracle import replay as oreplay, sumtree as osum
+
+pytestmark = pytest.mark.gpu
+
+
+def _mem(dev, cap, nb, batch=32):
+    from rainbow_iqn_apex_b200 import ReplayMemory
+    return ReplayMemory(make_args(dev, batch, nb_actor=nb, actor_capacity=cap), None)
+
+
+@pytest.mark.parametrize("name", ["tree_pow2", "tree_npow2"])
+def test_replay_matches_reference_golden(cuda_dev, golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    cap, nb, batch, rounds = (int(g[k]) for k in ("actor_capacity", "nb_actor", "batch", "rounds"))
+    mem = _mem(cuda_dev, cap, nb, batch)
+    tr = mem.transitions
+    store = oreplay.ReplayStore(cap, nb)
+    for a in range(nb):
+        for ci in range(3):
+            start, n = (int(v) for v in g[f"append_{a}_{ci}"])
+            frames = np.random.RandomState(int(g[f"append_frame_seed_{a}_{ci}"])).randint(0, 256, (n, 84, 84)).astype(np.uint8)
+            buf = [[int(g[f"append_ts_{a}_{ci}"][i]), frames[i], int(g[f"append_act_{a}_{ci}"][i]),
+                    float(g[f"append_rew_{a}_{ci}"][i]), bool(g[f"append_done_{a}_{ci}"][i])] for i in range(n)]
+            tr.append_actor_buffer(buf, start, a, g[f"append_pri_{a}_{ci}"], 0)
+            store.write(a, start, g[f"append_ts_{a}_{ci}"], frames, g[f"append_act_{a}_{ci}"],
+                        g[f"append_rew_{a}_{ci}"], g[f"append_done_{a}_{ci}"])
+    assert np.array_equal(tr.tree.cpu().numpy(), g["tree_after_append"])
+    assert np.array_equal(tr.index_actor.cpu().numpy(), g["heads"])
+    assert tr.get_current_capacity() == cap * nb
+    for r in range(rounds):
+        tree_idx, data_idx, pri, w64, w32 = mem.sample_indices(batch, samples=g[f"samples_{r}"])
+        assert np.array_equal(tree_idx.cpu().numpy(), g[f"tree_idx_{r}"])
+        assert np.array_equal(pri.cpu().numpy(), g[f"pri_{r}"])
+        assert tr.total() == float(g[f"p_total_{r}"])
+        assert np.allclose(w64.cpu().numpy(), g[f"weights_{r}"], rtol=1e-12, atol=0)
+        assert np.allclose(w32.cpu().numpy(), g[f"weights_{r}"].astype(np.float32), rtol=1e-6, atol=0)
+        st, ac, rt, nx, nt = mem.assemble(data_idx)
+        ost, oac, ort, onx, ont = store.assemble(data_idx.cpu().numpy())
+        assert np.array_equal(st.cpu().numpy(), ost) and np.array_equal(nx.cpu().numpy(), onx)
+        assert np.array_equal(ac.cpu().numpy(), g[f"asm_actions_{r}"])
+        assert np.array_equal(rt.cpu().numpy(), g[f"asm_returns_{r}"])
+        assert np.array_equal(nt.cpu().numpy(), g[f"asm_nonterminals_{r}"])
+        mem.update_priorities(g[f"upd_idx_{r}"], g[f"upd_loss_{r}"])
+        assert np.array_equal(tr.tree.cpu().numpy(), g[f"tree_after_update_{r}"])
+        assert float(tr.max_priority.item()) == float(g[f"max_priority_{r}"])
+
+
+@pytest.mark.parametrize("cap,nb,batch", [(1 << 14, 1, 512), (5000, 3, 640), (1000, 7, 2560), (37, 1, 5)])
+def test_tree_random_vs_oracle(cuda_dev, cap, nb, batch):
+    """Random append / sample / update rounds, pow2 and non-pow2 capacities, duplicates, write-head shifts."""
+    rs = np.random.RandomState(cap + nb)
+    mem = _mem(cuda_dev, cap, nb, batch)
+    tr = mem.transitions
+    ot = osum.SumTree(cap, nb)
+    C = cap * nb
+    for a in range(nb):
+        n = cap if cap <= 5000 else 4096
+        for lo in range(0, cap, n):
+            m = min(n, cap - lo)
+            pri = (rs.uniform(1e-3, 1, m) ** 0.2).astype(np.float32)
+            idx = (np.arange(lo, lo + m) % cap) + a * cap + C - 1
+            tr.update_multiple_value(torch.from_numpy(idx).to(cuda_dev), torch.from_numpy(pri).to(cuda_dev))
+            ot.update_multiple_value(idx, pri)
+        head = int(rs.randint(0, cap))
+        tr.index_actor[a] = head
+        tr.index_actor_host[a] = head
+        tr.is_full_actor[a] = 1
+        ot.index_actor[a] = head
+        ot.is_full_actor[a] = 1
+    assert np.array_equal(tr.tree.cpu().numpy(), ot.tree)
+    for r in range(4):
+        samples = osum.stratified_samples(ot.total(), batch, rs.uniform(size=batch), rs.permutation(batch))
+        if r == 1:  # make some samples land next to the write heads and at the extremes
+            samples[0], samples[1] = 0.0, ot.total()
+        tree_idx, data_idx, pri, w64, _ = mem.sample_indices(batch, samples=samples)
+        o_pri, o_data, o_idx, o_tot = ot.find(samples, 4, 3)
+        assert np.array_equal(tree_idx.cpu().numpy(), o_idx)
+        assert np.array_equal(data_idx.cpu().numpy(), o_data)
+        assert np.array_equal(pri.cpu().numpy(), o_pri)
+        assert np.allclose(w64.cpu().numpy(), osum.importance_weights(o_pri, o_tot, ot.get_current_capacity(), 0.4),
+                           rtol=1e-12, atol=0)
+        loss = rs.uniform(0, 3, batch).astype(np.float32)
+        upd = o_idx.copy()
+        if batch >= 4:
+            upd[3] = upd[2] = upd[0]          # triple duplicate
+        new_pri = mem.update_priorities(upd, loss)
+        assert np.array_equal(new_pri.cpu().numpy(), np.power(loss, 0.2))     # float32 power, bit for bit
+        ot.update_priorities(upd, loss, 0.2)
+        assert np.array_equal(tr.tree.cpu().numpy(), ot.tree)
+        assert float(tr.max_priority.item()) == ot.max_priority
+    assert tr.check_sumtree_correct() < 1e-9
+
+
+def test_valid_index_shift_near_write_heads(cuda_dev):
+    """transform_to_valid_tree_indexes (redis_memory.py:242-264): every distance -n..history from a head."""
+    cap, nb = 64, 2
+    mem = _mem(cuda_dev, cap, nb, 16)
+    tr = mem.transitions
+    ot = osum.SumTree(cap, nb)
+    C = cap * nb
+    pri = np.ones(C, np.float32)
+    idx = np.arange(C) + C - 1
+    tr.update_multiple_value(torch.from_numpy(idx).to(cuda_dev), torch.from_numpy(pri).to(cuda_dev))
+    ot.update_multiple_value(idx, pri)
+    for heads in ([0, 63], [2, 30], [61, 1]):
+        for a, h in enumerate(heads):
+            tr.index_actor[a] = h
+            ot.index_actor[a] = h
+        samples = np.arange(C, dtype=np.float64) + 0.5       # one sample per leaf
+        tree_idx, data_idx, _, _, _ = mem.sample_indices(C, samples=samples)
+        _, o_data, o_idx, _ = ot.find(samples, 4, 3)
+        assert np.array_equal(tree_idx.cpu().numpy(), o_idx)
+        assert (np.abs(o_data - (np.arange(C))) > 0).any()
+
+
+def test_device_stratified_sampler(cuda_dev):
+    """Native sampling: one value per stratum (a permutation of the strata), inside the stratum bounds."""
+    mem = _mem(cuda_dev, 4096, 1, 512)
+    tr = mem.transitions
+    rs = np.random.RandomState(0)
+    pri = rs.uniform(0.1, 1, 4096).astype(np.float32)
+    tr.update_multiple_value(torch.arange(4096, device=cuda_dev) + 4095, torch.from_numpy(pri).to(cuda_dev))
+    from rainbow_iqn_apex_b200._lib import call, ptr
+    n = 2560
+    vals = torch.empty(n, dtype=torch.float64, device=cuda_dev)
+    call("riqn_sumtree_stratified", n, 42, 0, ptr(tr.tree), ptr(vals))
+    v = vals.cpu().numpy()
+    seg = tr.total() / n
+    strata = np.floor(v / seg).astype(np.int64)
+    assert sorted(strata.tolist()) == list(range(n))
+    assert not np.array_equal(strata, np.arange(n))          # shuffled
+    vals2 = torch.empty(n, dtype=torch.float64, device=cuda_dev)
+    call("riqn_sumtree_stratified", n, 42, 1, ptr(tr.tree), ptr(vals2))
+    assert not np.array_equal(v, vals2.cpu().numpy())
+    out = mem.sample(512)
+    assert out[1].shape == (512, 4, 84, 84) and out[1].dtype == torch.uint8 and out[6].max().item() == 1.0
+
+
+def test_full_size_tree_properties(cuda_dev):
+    """BASELINE config 4 shard size (2^19 leaves) and a non-power-of-two 500 000: invariants that do not need
+    the O(n) python oracle -- parent == left + right after many batched updates, root == sum(leaves),
+    sampled leaf contains its sample value (prefix-sum property), sortedness of stratified picks."""
+    for cap in (1 << 19, 500000):
+        mem = _mem(cuda_dev, cap, 1, 512)
+        tr = mem.transitions
+        tr.store_frames = False
+        rs = np.random.RandomState(1)
+        g = torch.Generator(device="cpu").manual_seed(0)
+        for lo in range(0, cap, 4096):
+            m = min(4096, cap - lo)
+            pri = torch.rand(m, generator=g).add_(0.01).to(cuda_dev)
+            tr.update_multiple_value(torch.arange(lo, lo + m, device=cuda_dev) + cap - 1, pri)
+        assert tr.check_sumtree_correct() < 1e-7
+        leaves = tr.tree[cap - 1:]
+        assert abs(tr.total() - float(leaves.sum().item())) < 1e-6 * tr.total()
+        tr.index_actor[0] = 0
+        samples = np.sort(rs.uniform(0, tr.total(), 2048))
+        tree_idx, data_idx, pri, _, _ = mem.sample_indices(2048, samples=samples)
+        di = data_idx.cpu().numpy()
+        inner = (di > 8) & (di < cap - 8)
+        # leaves are visited in heap order, which for a complete tree == left-to-right order of the
+        # deepest level then the shallower level; check the prefix-sum containment on the heap order
+        order = torch.argsort(_heap_leaf_rank(cap, cuda_dev))
+        csum = torch.cumsum(leaves[order].double(), 0).cpu().numpy()
+        rank = _heap_leaf_rank(cap, cuda_dev).cpu().numpy()
+        rk = rank[di[inner]]
+        hi = csum[rk]
+        lo_ = np.where(rk > 0, csum[np.maximum(rk - 1, 0)], 0.0)
+        s = samples[inner]
+        assert np.all(s <= hi + 1e-6) and np.all(s >= lo_ - 1e-6)
+
+
+def _heap_leaf_rank(cap, dev):
+    """Left-to-right rank of each data index's leaf in the implicit heap (deeper level first half)."""
+    n_nodes = 2 * cap - 1
+    idx = torch.arange(cap, device=dev) + cap - 1
+    depth = torch.floor(torch.log2((idx + 1).double())).long()
+    maxd = int(depth.max().item())
+    # position of the leaf when every leaf is projected to the deepest level
+    pos = ((idx + 1) << (maxd - depth)) - (1 << maxd)
+    return torch.argsort(torch.argsort(pos))
