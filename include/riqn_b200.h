@@ -164,7 +164,9 @@ int riqn_sumtree_is_weights(int n, const double* tree, const double* priorities,
 /* update_priorities / update_multiple_value / _propagate_multiple_values (:557-573,139-151,94-105).
  * apply_pow != 0: new = np.power(loss, float32(priority_exponent)) first.  new_priorities (n floats) and
  * diff_scratch (n doubles) are outputs/workspace; *max_priority (device double) is raised if needed.
- * n <= 5000.  Bit-exact with the reference including duplicated indices. */
+ * n <= 4096.  The tree arithmetic is bit-exact with the reference (including duplicated indices) given the
+ * float32 priorities; the power itself is the correctly rounded float32 value, which numpy/libm powf only
+ * approximates (<= 1 ulp apart, platform dependent). */
 int riqn_sumtree_update(int n, long capacity, double* tree, const long long* tree_idx, const float* loss,
                         float priority_exponent, int apply_pow, float* new_priorities, double* diff_scratch,
                         double* max_priority, void* stream);

@@ -371,6 +371,7 @@ def golden_sumtree(name, actor_capacity, nb_actor, batch, rounds, seed):
         rec[f"p_total_{r}"] = p_total
         rec[f"upd_idx_{r}"] = upd_idx
         rec[f"upd_loss_{r}"] = new_loss
+        rec[f"upd_pri_{r}"] = np.power(new_loss, 0.2)   # what redis_memory.py:560 produced on this host
         rec[f"tree_after_update_{r}"] = tree.tree.copy()
         rec[f"max_priority_{r}"] = tree.max_priority
         rec[f"asm_actions_{r}"] = oac

@@ -146,12 +146,14 @@ def noisy_linear(p, name, x, training=True):
     return F.linear(x, p[name + ".weight_mu"], p[name + ".bias_mu"])
 
 
-def conv_trunk(p, x):
+def conv_trunk(p, x, keep=None):
     """conv1(8x8,s4,p1) conv2(4x4,s2) conv3(3x3) + ReLU, flatten C-major   model.py:65-67,115-118"""
-    x = F.relu(F.conv2d(x, p["conv1.weight"], p["conv1.bias"], stride=4, padding=1))
-    x = F.relu(F.conv2d(x, p["conv2.weight"], p["conv2.bias"], stride=2))
-    x = F.relu(F.conv2d(x, p["conv3.weight"], p["conv3.bias"]))
-    return x.reshape(-1, FEAT)
+    o1 = F.relu(F.conv2d(x, p["conv1.weight"], p["conv1.bias"], stride=4, padding=1))
+    o2 = F.relu(F.conv2d(o1, p["conv2.weight"], p["conv2.bias"], stride=2))
+    o3 = F.relu(F.conv2d(o2, p["conv3.weight"], p["conv3.bias"]))
+    if keep is not None:
+        keep.update(o1=o1, o2=o2, o3=o3)
+    return o3.reshape(-1, FEAT)
 
 
 def cos_embedding(tau, embed):
@@ -167,7 +169,7 @@ def dqn_forward_iqn(p, x, num_quantiles, tau, training=True, keep=None):
     Returns q (num_quantiles*B, A).  ``keep`` (a dict) receives intermediates.
     """
     batch = x.shape[0]
-    feat = conv_trunk(p, x)
+    feat = conv_trunk(p, x, keep)
     embed = p["iqn_fc.weight"].shape[1]
     cosv = cos_embedding(tau, embed)
     phi = F.relu(F.linear(cosv, p["iqn_fc.weight"], p["iqn_fc.bias"]))

@@ -57,7 +57,8 @@ def loss_core(agent, states, actions, returns, next_states, nonterminals, keep_g
          ptr(returns), ptr(nonterminals), float(agent.discount ** agent.n), float(agent.kappa), ptr(loss),
          ptr(dtheta), ptr(theta_out), ptr(target_out))                              # :262-357
     if debug is not None:
-        debug.update(a_star=a_star, theta=theta_out, target=target_out, q_sel=q_sel, q_tgt=q_tgt, q_on=q_on, tau=tau)
+        debug.update(a_star=a_star, theta=theta_out, target=target_out, q_sel=q_sel, q_tgt=q_tgt, q_on=q_on, tau=tau,
+                     keep=keep)
     return loss, dtheta, keep, actions
 
 

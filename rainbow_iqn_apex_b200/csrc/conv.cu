@@ -32,7 +32,7 @@ __global__ void im2col_kernel(riqn_conv_geom g, const T* __restrict__ in, float*
     const int ow = (int)(m % g.OW), oh = (int)((m / g.OW) % g.OH), b = (int)(m / ((long)g.OW * g.OH));
     const int ih = oh * g.stride + kh - g.pad, iw = ow * g.stride + kw - g.pad;
     float v = 0.f;
-    if (ih >= 0 && ih < g.H && iw >= 0 && iw < g.W) v = load_px<T>(&in[(((long)b * g.Cin + c) * g.H + ih) * g.W + iw]);
+    if (ih >= 0 && ih < g.H && iw >= 0 && iw < g.W) v = load_px<T>(&in[(long)b * g.in_bstride + ((long)c * g.H + ih) * g.W + iw]);
     col[idx] = v;
   }
 }

@@ -294,7 +294,7 @@ __global__ void embed_bwd_elem_kernel(int B, int Nq, int F, const float* __restr
 // Adam over a flat fp32 arena (torch.optim.Adam semantics; agent.py:43, learner.py:24)
 // ------------------------------------------------------------------------------------------------
 __global__ void adam_kernel(long n, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                            float* __restrict__ v, float lr_over_bc1, float inv_sqrt_bc2, float eps, float b1, float b2,
+                            float* __restrict__ v, float neg_step_size, float sqrt_bc2, float eps, float b1, float b2,
                             float grad_scale) {
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     const float gi = g[i] * grad_scale;
@@ -302,8 +302,8 @@ __global__ void adam_kernel(long n, float* __restrict__ p, const float* __restri
     const float vi = v[i] * b2 + (1.f - b2) * gi * gi;
     m[i] = mi;
     v[i] = vi;
-    const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
-    p[i] -= lr_over_bc1 * (mi / denom);
+    const float denom = __fadd_rn(__fdiv_rn(sqrtf(vi), sqrt_bc2), eps);   // (v.sqrt() / sqrt(bc2)).add_(eps)
+    p[i] = __fadd_rn(p[i], __fdiv_rn(__fmul_rn(neg_step_size, mi), denom)); // addcdiv_(m, denom, value=-step_size)
   }
 }
 
@@ -480,7 +480,7 @@ RIQN_API int riqn_adam_step(long n, float* params, const float* grads, float* ex
                             float lr, float beta1, float beta2, float eps, float grad_scale, void* stream) {
   const double bc1 = 1.0 - pow((double)beta1, (double)step);
   const double bc2 = 1.0 - pow((double)beta2, (double)step);
-  adam_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(n, params, grads, exp_avg, exp_avg_sq, (float)(lr / bc1),
-                                                            (float)(1.0 / sqrt(bc2)), eps, beta1, beta2, grad_scale);
+  adam_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(n, params, grads, exp_avg, exp_avg_sq, (float)(-(lr / bc1)),
+                                                            (float)sqrt(bc2), eps, beta1, beta2, grad_scale);
   return (int)cudaGetLastError();
 }

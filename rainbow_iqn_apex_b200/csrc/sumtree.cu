@@ -38,7 +38,7 @@ __global__ void stratified_kernel(int n, uint64_t seed, uint64_t stream, const d
     const int s = perm[i];
     const uint4 r = Philox::draw(seed, stream, (uint64_t)s);
     const double a = (double)s * seg, b = (double)(s + 1) * seg;
-    values[i] = a + (b - a) * Philox::u01d(r.x, r.y);
+    values[i] = __dadd_rn(a, __dmul_rn(b - a, Philox::u01d(r.x, r.y)));   // a + (b-a)*u, no FMA contraction
   }
 }
 
@@ -168,60 +168,108 @@ __global__ void update_prepare_kernel(int n, const double* __restrict__ tree, co
   }
 }
 
-// numpy pairwise summation (np.sum of a contiguous float64 vector == 0 + pairwise(a, n)).
-__device__ double np_pairwise_sum(const double* a, int n) {
+// numpy pairwise summation (np.sum of a contiguous float64 vector == 0 + pairwise(a, n)): blocks of <= 128
+// elements are summed with 8 interleaved accumulators, larger ranges split at n/2 rounded down to a multiple
+// of 8 and the two halves added.  Iterative post-order walk of that recursion (no device stack needed).
+__device__ __forceinline__ double np_block_sum(const double* a, int n) {
   if (n < 8) {
     double r = 0.0;
     for (int i = 0; i < n; ++i) r += a[i];
     return r;
   }
-  if (n <= 128) {
-    double r[8];
-    for (int k = 0; k < 8; ++k) r[k] = a[k];
-    int i = 8;
-    for (; i < n - (n % 8); i += 8)
-      for (int k = 0; k < 8; ++k) r[k] += a[i + k];
-    double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
-    for (; i < n; ++i) res += a[i];
-    return res;
+  double r[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) r[k] = a[k];
+  int i = 8;
+  for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r[k] += a[i + k];
   }
-  int n2 = n / 2;
-  n2 -= n2 % 8;
-  return np_pairwise_sum(a, n2) + np_pairwise_sum(a + n2, n - n2);
+  double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+  for (; i < n; ++i) res += a[i];
+  return res;
 }
 
-// One CTA per tree level (blockIdx.x = number of parent steps from the leaf); the last CTA does the
-// root.  Within a level, the first batch entry that touches a node applies all of that node's diffs in
-// batch order (sequential float64 adds, like the reference's per-entry INCRBYFLOAT stream).
-__global__ void update_propagate_kernel(int n, int n_levels, double* __restrict__ tree,
+__device__ double np_pairwise_sum(const double* a, int n) {
+  int off[24], len[24], stage[24];
+  double left[24];
+  int sp = 0;
+  off[0] = 0; len[0] = n; stage[0] = 0; sp = 1;
+  double ret = 0.0;
+  while (sp > 0) {
+    const int t = sp - 1;
+    if (len[t] <= 128) {
+      ret = np_block_sum(a + off[t], len[t]);
+      --sp;
+      // hand the value to the ancestors that are waiting for it
+      while (sp > 0) {
+        const int p = sp - 1;
+        if (stage[p] == 1) {  // left half done -> start the right half
+          left[p] = ret;
+          stage[p] = 2;
+          int n2 = len[p] / 2;
+          n2 -= n2 % 8;
+          off[sp] = off[p] + n2; len[sp] = len[p] - n2; stage[sp] = 0;
+          ++sp;
+          break;
+        }
+        ret = left[p] + ret;  // stage 2: both halves done
+        --sp;
+      }
+    } else {
+      int n2 = len[t] / 2;
+      n2 -= n2 % 8;
+      stage[t] = 1;
+      off[sp] = off[t]; len[sp] = n2; stage[sp] = 0;
+      ++sp;
+    }
+  }
+  return ret;
+}
+
+// One CTA per tree depth d >= 1 (blockIdx.x = d - 1); the last CTA does the root.  For a node X at depth d
+// the reference applies, level by level, first the diffs of batch entries whose leaf is fewer parent steps
+// away (the shallower leaves of a non-power-of-two tree), then the deeper ones, each group in batch order
+// (redis_memory.py:94-105).  The first batch entry that touches X replays exactly that sequence of float64
+// adds, so every node is written by one thread only.
+__global__ void update_propagate_kernel(int n, int max_depth, double* __restrict__ tree,
                                         const int64_t* __restrict__ idx, const double* __restrict__ diff) {
   extern __shared__ unsigned char smem_raw[];
   int64_t* node = reinterpret_cast<int64_t*>(smem_raw);
   double* sd = reinterpret_cast<double*>(node + n);
-  const int level = blockIdx.x;
-  if (level == n_levels) {  // root: tree[0] += np.sum(diffs)
+  int* steps = reinterpret_cast<int*>(sd + n);
+  if ((int)blockIdx.x == max_depth) {  // root: tree[0] += np.sum(diffs)
     for (int j = threadIdx.x; j < n; j += blockDim.x) sd[j] = diff[j];
     __syncthreads();
     if (threadIdx.x == 0) tree[0] = tree[0] + (0.0 + np_pairwise_sum(sd, n));
     return;
   }
+  const int d = blockIdx.x + 1;
   for (int j = threadIdx.x; j < n; j += blockDim.x) {
-    int64_t i = idx[j];
-    for (int l = 0; l < level; ++l) i = (i - 1) >> 1;  // floor division; 0 -> -1 -> -1 ...
-    node[j] = i;
+    const int64_t leaf = idx[j];
+    const int depth = 63 - __clzll((unsigned long long)(leaf + 1));  // floor(log2(leaf + 1))
+    const int st = depth - d;                                        // parent steps from the leaf to depth d
+    node[j] = st >= 0 ? ((leaf + 1) >> st) - 1 : -1;
+    steps[j] = st;
     sd[j] = diff[j];
   }
   __syncthreads();
   for (int j = threadIdx.x; j < n; j += blockDim.x) {
     const int64_t me = node[j];
-    if (me <= 0) continue;  // root handled separately; negatives hit the reference's junk key
+    if (me <= 0) continue;
     bool leader = true;
-    for (int k = 0; k < j; ++k)
-      if (node[k] == me) { leader = false; break; }
+    int smin = steps[j], smax = steps[j];
+    for (int k = 0; k < n; ++k) {
+      if (node[k] != me) continue;
+      if (k < j) { leader = false; break; }
+      smin = min(smin, steps[k]);
+      smax = max(smax, steps[k]);
+    }
     if (!leader) continue;
     double acc = tree[me];
-    for (int k = j; k < n; ++k)
-      if (node[k] == me) acc += sd[k];
+    for (int s = smin; s <= smax; ++s)
+      for (int k = j; k < n; ++k)
+        if (node[k] == me && steps[k] == s) acc += sd[k];
     tree[me] = acc;
   }
 }
@@ -284,7 +332,7 @@ __global__ void frame_gather_kernel(int B, int actor_cap, int history, int n_ste
     for (int k = 0; k < n_step; ++k) {
       const int t = history + k - 1;
       const double r = blank[t] ? 0.0 : (double)s_reward[slots[t]];
-      ret = ret + gamma_pow[k] * r;
+      ret = __dadd_rn(ret, __dmul_rn(gamma_pow[k], r));   // python: sum(discount**k * reward), no FMA
     }
     returns[b] = (float)ret;
     actions[b] = s_action[slots[history - 1]];
@@ -333,20 +381,20 @@ RIQN_API int riqn_sumtree_update(int n, long capacity, double* tree, const long 
                                  float priority_exponent, int apply_pow, float* new_priorities, double* diff_scratch,
                                  double* max_priority, void* stream) {
   if (n <= 0) return 0;
-  if (n > 5000) return (int)cudaErrorInvalidValue;  // shared-memory bound of the propagate kernel
+  if (n > 4096) return (int)cudaErrorInvalidValue;  // shared-memory bound of the propagate kernel
   cudaStream_t s = (cudaStream_t)stream;
   update_prepare_kernel<<<1, 1024, 0, s>>>(n, tree, (const int64_t*)tree_idx, loss, priority_exponent, apply_pow,
                                            new_priorities, diff_scratch, max_priority);
   RIQN_LAUNCH_CHECK();
-  int n_levels = 0;  // parent steps needed to bring the deepest leaf (index 2C-2) to the root
-  for (long i = 2 * capacity - 2; i > 0; i = (i - 1) / 2) ++n_levels;
-  const size_t smem = (size_t)n * 16;
+  int max_depth = 0;  // depth of the deepest leaf (index 2C-2)
+  for (long i = 2 * capacity - 2; i > 0; i = (i - 1) / 2) ++max_depth;
+  const size_t smem = (size_t)n * 20;
   static bool attr = false;
   if (!attr) {
     RIQN_CUDA(cudaFuncSetAttribute(update_propagate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     attr = true;
   }
-  update_propagate_kernel<<<n_levels + 1, 512, smem, s>>>(n, n_levels, tree, (const int64_t*)tree_idx, diff_scratch);
+  update_propagate_kernel<<<max_depth + 1, 512, smem, s>>>(n, max_depth, tree, (const int64_t*)tree_idx, diff_scratch);
   return (int)cudaGetLastError();
 }
 

@@ -16,7 +16,7 @@ optimiser and the gradient all-reduce touch one contiguous buffer.
 There is no PyTorch fallback: every tensor operation below is a C-ABI call (include/riqn_b200.h).
 """
 import math
-from types import SimpleNamespace
+import weakref
 
 import torch
 from torch import nn
@@ -180,6 +180,8 @@ class DQN(nn.Module):
                 p.data = flat[off:off + n].view(p.shape)
                 p.grad = flat_grad[off:off + n].view(p.shape)
                 self._offsets[id(p)] = off
+                p._riqn_owner = weakref.ref(self)
+                p._riqn_offset = off
                 i += 1
         self._flat, self._flat_grad = flat, flat_grad
         # epsilon arena: [h_v.weight_epsilon | h_a.weight_epsilon], h bias eps, [z_v | z_a] weight eps, z bias eps

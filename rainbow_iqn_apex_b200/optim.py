@@ -20,17 +20,18 @@ class Adam(torch.optim.Optimizer):
 
     def _bind(self):
         ps = [p for g in self.param_groups for p in g["params"]]
-        base = ps[0].data._base
-        if base is None or any(p.data._base is not base for p in ps):
+        owner = getattr(ps[0], "_riqn_owner", None)
+        owner = owner() if owner is not None else None
+        if owner is None or any(getattr(p, "_riqn_owner", lambda: None)() is not owner for p in ps):
             raise ValueError("Adam expects the parameters of a rainbow_iqn_apex_b200 DQN (views of one flat arena)")
-        self._flat = base
-        self._exp_avg = torch.zeros_like(base)
-        self._exp_avg_sq = torch.zeros_like(base)
+        self._net = owner
+        self._flat = owner._flat
+        self._exp_avg = torch.zeros_like(self._flat)
+        self._exp_avg_sq = torch.zeros_like(self._flat)
         self._params = ps
 
     def _views(self, p):
-        off = (p.data_ptr() - self._flat.data_ptr()) // 4
-        n = p.numel()
+        off, n = p._riqn_offset, p.numel()
         return self._exp_avg[off:off + n].view(p.shape), self._exp_avg_sq[off:off + n].view(p.shape)
 
     def _publish_state(self):
@@ -40,12 +41,16 @@ class Adam(torch.optim.Optimizer):
 
     @torch.no_grad()
     def step(self, closure=None):
-        if self._flat.data_ptr() != self._params[0].data._base.data_ptr():
+        if self._flat is not self._net._flat:       # the module was moved / re-flattened after construction
             self._rebind_after_move()
-        grad_flat = self._params[0].grad._base if self._params[0].grad is not None else None
-        if grad_flat is None or any(p.grad is None or p.grad._base is not grad_flat for p in self._params):
-            raise RuntimeError("gradients are not bound to the DQN gradient arena; call online_net.zero_grad() "
-                               "(not set_to_none) before backward")
+        grad_flat = self._net._flat_grad
+        base = grad_flat.data_ptr()
+        for p in self._params:
+            if p.grad is None:
+                raise RuntimeError("a parameter has no gradient; call online_net.zero_grad() (arena memset) "
+                                   "instead of setting grads to None")
+            if p.grad.data_ptr() != base + 4 * p._riqn_offset:   # foreign gradient tensor: stage it into the arena
+                self._net.grad_view(p).copy_(p.grad)
         self._step += 1
         g = self.param_groups[0]
         call("riqn_adam_step", self._flat.numel(), ptr(self._flat), ptr(grad_flat), ptr(self._exp_avg),

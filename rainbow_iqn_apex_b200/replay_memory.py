@@ -82,9 +82,9 @@ class SegmentTree:
         for lo in range(0, n, 4096):  # the reference issues one update per batch; huge batches are chunked
             hi = min(n, lo + 4096)
             diff = torch.empty(hi - lo, dtype=torch.float64, device=self.device)
-            call("riqn_sumtree_update", hi - lo, self.full_capacity, ptr(self.tree), ptr(tree_idx[lo:hi]),
-                 ptr(values[lo:hi]), float(exponent), 1 if apply_pow else 0, ptr(new_pri[lo:hi]), ptr(diff),
-                 ptr(self.max_priority))
+            idx_c, val_c, out_c = tree_idx[lo:hi], values[lo:hi], new_pri[lo:hi]
+            call("riqn_sumtree_update", hi - lo, self.full_capacity, ptr(self.tree), ptr(idx_c), ptr(val_c),
+                 float(exponent), 1 if apply_pow else 0, ptr(out_c), ptr(diff), ptr(self.max_priority))
         return new_pri
 
     def append_arrays(self, id_actor, start, timesteps, frames, actions, rewards, dones, priorities, T_actor=0):
@@ -103,10 +103,12 @@ class SegmentTree:
 
         fr = frames if torch.is_tensor(frames) else torch.from_numpy(np.ascontiguousarray(frames))
         fr = fr.to(dev, torch.uint8).reshape(n, FRAME).contiguous()
+        # device staging buffers are bound to names so they outlive the (asynchronous) kernel launch
         nonterminal = dv(~np.asarray(dones, np.bool_), torch.uint8)
-        call("riqn_replay_append", n, cap, id_actor, int(start), ptr(fr), ptr(dv(timesteps, torch.int32)),
-             ptr(dv(actions, torch.int32)), ptr(dv(rewards, torch.float32)), ptr(nonterminal), ptr(self.frames),
-             ptr(self.timestep), ptr(self.action), ptr(self.reward), ptr(self.nonterminal))
+        ts_d, ac_d, rw_d = dv(timesteps, torch.int32), dv(actions, torch.int32), dv(rewards, torch.float32)
+        call("riqn_replay_append", n, cap, id_actor, int(start), ptr(fr), ptr(ts_d), ptr(ac_d), ptr(rw_d),
+             ptr(nonterminal), ptr(self.frames), ptr(self.timestep), ptr(self.action), ptr(self.reward),
+             ptr(self.nonterminal))
         if start + n >= cap:
             self.is_full_actor[id_actor] = 1                 # launch_actor.py:117-121
         self.index_actor_host[id_actor] = (start + n) % cap  # redis_memory.py:197

