@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""Learner hot-path benchmark (BASELINE.json metric: learner grad-steps/sec at batch=512, N=N'=64).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host CPU cores
+
+One "step" = one full `Learner.learn` of BASELINE config 2 on every rank: prioritized sample from the
+device-resident replay shard (sum-tree descent + IS weights + 7-frame window gather), three network passes,
+fused IQN loss, backward, (gradient all-reduce when N > 1), Adam, priority update of the sampled leaves.
+N > 1 is the data-parallel learner of config 5 (512 transitions per GPU, weak scaling).
+
+Timing: W untimed warm-up steps, then K steps bracketed by barrier + torch.cuda.synchronize(), CUDA events on
+the launching stream, max over ranks.  Inputs are larger than L2: every step draws a fresh prioritized
+minibatch from a multi-GB replay shard and streams > 2 GB of activations.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from types import SimpleNamespace
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+METRIC = "learner grad-steps/sec (batch=512, N=N'=64)"
+B, N_TAU, N_TAU_P, K_Q, ACTIONS = 512, 64, 64, 32, 18
+FEAT, HID = 3136, 512
+
+
+def make_args(device, capacity):
+    return SimpleNamespace(
+        multi_step=3, history_length=4, discount=0.99, device=device, batch_size=B, length_actor_buffer=1000,
+        model=None, lr=5e-5, adam_eps=3.125e-4, rainbow_only=0, atoms=51, V_min=-10.0, V_max=10.0, kappa=1.0,
+        num_tau_samples=N_TAU, num_tau_prime_samples=N_TAU_P, num_quantile_samples=K_Q, quantile_embedding_dim=64,
+        hidden_size=HID, noisy_std=0.1, disable_cuda=False, nb_actor=1, actor_capacity=capacity, priority_weight=0.4,
+        priority_exponent=0.2)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v == "Active":
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def fill_replay(mem, capacity, device, seed):
+    """Synthetic 84x84 uint8 frames + metadata written straight into the shard (setup, not timed)."""
+    tr = mem.transitions
+    g = torch.Generator(device=device).manual_seed(seed)
+    chunk = 1 << 16
+    for lo in range(0, capacity, chunk):
+        hi = min(capacity, lo + chunk)
+        tr.frames[lo:hi] = torch.randint(0, 256, (hi - lo, 7056), dtype=torch.uint8, device=device, generator=g)
+    pos = torch.arange(capacity, device=device)
+    tr.timestep.copy_((pos % 1000).to(torch.int32))
+    tr.nonterminal.copy_(((pos % 1000) != 999).to(torch.uint8))
+    tr.action.copy_(torch.randint(0, ACTIONS, (capacity,), device=device, generator=g).to(torch.int32))
+    tr.reward.copy_((torch.randint(0, 3, (capacity,), device=device, generator=g) - 1).float())
+    for lo in range(0, capacity, 4096):                     # priorities U(0,1)^0.2 through the update kernel
+        hi = min(capacity, lo + 4096)
+        pri = torch.rand(hi - lo, device=device, generator=g).clamp_(min=1e-3).pow_(0.2)
+        tr.update_multiple_value(torch.arange(lo, hi, device=device) + capacity - 1, pri)
+    head = int(torch.randint(0, capacity, (1,), generator=torch.Generator().manual_seed(seed)).item())
+    tr.index_actor[0] = head
+    tr.index_actor_host[0] = head
+    tr.is_full_actor[0] = 1
+
+
+def run_ours(args):
+    from rainbow_iqn_apex_b200 import Learner, ReplayMemory, _lib, parallel
+    rank, world, local = parallel.init_from_env()
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    _lib.require_device()
+    torch.manual_seed(123 + rank)
+    a = make_args(dev, args.replay_capacity)
+    learner = Learner(a, ACTIONS, None)
+    learner.train()
+    parallel.make_data_parallel(learner)
+    mem = ReplayMemory(a, None)
+    fill_replay(mem, args.replay_capacity, dev, 1000 + rank)
+
+    def step():
+        idxs, loss = learner.learn(mem, None)
+        mem.update_priorities(idxs, loss)
+        return loss
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    timed_names = ("riqn_noisy_linear_fwd", "riqn_iqn_loss_fwd_bwd", "riqn_noisy_linear_wgrad", "riqn_noisy_linear_dgrad",
+                   "riqn_quantile_embed_fwd", "riqn_conv_fwd")
+    clocks = ClockSampler(local)
+    clocks.start()
+    launches0 = _lib.launch_count()
+    timers = _lib.time_entry_points(timed_names)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        loss = step()
+    e1.record()
+    barrier()
+    _lib.time_entry_points(None)
+    launches = _lib.launch_count() - launches0
+    clk = clocks.stop()
+    ms = parallel.allreduce_max(e0.elapsed_time(e1), dev)
+    ms_per_step = ms / args.steps
+    value = world * 1000.0 / ms_per_step
+    assert torch.isfinite(loss).all()
+
+    # per-entry-point device time from the CUDA events recorded on the launching stream
+    per = {}
+    for name, evs in timers.items():
+        tot = sum(a_.elapsed_time(b_) for a_, b_, _ in evs)
+        rows = sum(int(r) for _, _, r in evs if isinstance(r, int))
+        per[name] = dict(ms_total=tot, calls=len(evs), rows=rows)
+    pk = peaks()
+    head = per["riqn_noisy_linear_fwd"]
+    head_flops = 2.0 * head["rows"] * FEAT * (2 * HID)              # algorithmic: 2*rows*3136*1024 per launch
+    head_tf = head_flops / (head["ms_total"] * 1e-3) / 1e12 if head["ms_total"] > 0 else 0.0
+    roof = {"kernel": "riqn_noisy_linear_fwd (hidden NoisyLinear GEMM, 3 launches/step)", "bound": "tensor",
+            "achieved": head_tf, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": head_tf / pk["tf_sust"],
+            "traffic": None, "peak_source": pk["src"] + " bf16 sustained",
+            "share_of_step": head["ms_total"] / ms}
+    lk = per["riqn_iqn_loss_fwd_bwd"]
+    loss_bytes = 4 * B * (N_TAU + N_TAU_P + N_TAU) + 4 * B * N_TAU + B * (4 + 4 + 8 + 8 + 4)   # SURVEY 8d gathered form
+    loss_us = lk["ms_total"] * 1e3 / max(lk["calls"], 1)
+    roof_loss = {"kernel": "riqn_iqn_loss_fwd_bwd", "bound": "hbm", "achieved": loss_bytes / (loss_us * 1e-6) / 1e9,
+                 "peak": pk["hbm"], "unit": "GB/s", "frac": loss_bytes / (loss_us * 1e-6) / 1e9 / pk["hbm"],
+                 "traffic": None, "us_per_launch": loss_us, "algorithmic_bytes": loss_bytes,
+                 "note": "0.54 MB per launch: latency-bound at B=512 (SURVEY 8d note)"}
+
+    # ---- end-to-end through the reference-facing API with HOST buffers (pinned), H2D/D2H inside the timed region
+    pool = []
+    for _ in range(4):
+        idxs, st, ac, rt, nx, nt, w = mem.sample(B)
+        pool.append(tuple(t.contiguous().cpu().pin_memory() for t in (idxs, st, ac, rt, nx, nt, w)))
+    h2d = sum(t.numel() * t.element_size() for t in pool[0])
+    d2h = B * 4
+
+    def e2e_step(i):
+        host = pool[i % len(pool)]
+        idxs, st, ac, rt, nx, nt, w = (t.to(dev, non_blocking=True) for t in host)
+        loss = learner.learn_on_batch(st, ac, rt, nx, nt, w)
+        loss_host = loss.cpu()                                   # D2H + sync: the result the caller consumes
+        mem.update_priorities(idxs, loss)
+        return loss_host
+
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for i in range(args.steps):
+        e2e_step(i)
+    e1.record()
+    barrier()
+    e2e_ms = parallel.allreduce_max(e0.elapsed_time(e1), dev) / args.steps
+    e2e = {"value": world * 1000.0 / e2e_ms, "unit": "grad-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "ms_per_step": e2e_ms}
+
+    out = {
+        "metric": METRIC, "value": value, "unit": "grad-steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "impl": "ours",
+        "config": {"workload": "configs[1]: 1xB200 learner, synthetic 84x84x4 replay, batch=512/GPU, N=N'=64, K=32, n-step=3",
+                   "batch_per_gpu": B, "global_batch": B * world, "n_tau": N_TAU, "n_tau_prime": N_TAU_P,
+                   "n_quantile": K_Q, "replay_capacity_per_gpu": args.replay_capacity,
+                   "parallelism": f"dp{world}" if world > 1 else "single",
+                   "l2": "inputs larger than L2 (fresh prioritized minibatch from a %.1f GB replay shard each step; "
+                         ">2 GB of activations streamed per step)" % (args.replay_capacity * 7056 / 1e9)},
+        "frames_per_s": value * B * 4, "transitions_per_s": value * B,
+        "clocks": clk, "e2e": e2e, "gpu_launches": launches,
+        "roofline": roof, "roofline_iqn_loss": roof_loss,
+        "kernel_ms_per_step": {k: v["ms_total"] / args.steps for k, v in per.items()},
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(max_seconds=25.0)
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------ CPU arms
+def oracle_learner(batch):
+    """The oracle port of Learner.learn (oracle/losses.py) on the host CPU cores."""
+    from oracle import cases, losses, network as net
+    torch.set_num_threads(os.cpu_count())
+    params = net.make_params(123)
+    p_on, p_tg = net.to_torch(params, requires_grad=True), net.to_torch(params)
+    adam = losses.Adam([k for k in p_on if net.is_trainable(k)], lr=5e-5, eps=3.125e-4)
+    cfg = cases.iqn_cfg(N_TAU, N_TAU_P, K_Q)
+    b = cases.make_batch(7, batch)
+    tb = cases.batch_to_torch(b)
+    w = torch.from_numpy(b["weights"])
+    noise_shapes = cases.make_noises(0)
+
+    def step(i):
+        noises = tuple({k: (net.scale_noise(torch.randn_like(v[0])), net.scale_noise(torch.randn_like(v[1])))
+                        for k, v in n.items()} for n in noise_shapes)
+        taus = tuple(torch.rand(nq * batch, 1) for nq in (K_Q, N_TAU_P, N_TAU))
+        losses.learn_step(p_on, p_tg, adam, tb, w, noises, taus, cfg)
+
+    return step
+
+
+def cpu_baseline(max_seconds=25.0):
+    step = oracle_learner(B)
+    t0 = time.perf_counter()
+    step(0)                                     # warm-up (also sizes the sample)
+    t1 = time.perf_counter() - t0
+    n = int(max(2, min(5, max_seconds // max(t1, 1e-3) - 1)))
+    t0 = time.perf_counter()
+    for i in range(n):
+        step(i)
+    dt = (time.perf_counter() - t0) / n
+    return {"value": 1.0 / dt, "unit": "grad-steps/s", "cores": os.cpu_count(), "threads": torch.get_num_threads(),
+            "kind": "port", "sample": f"{n} full learner steps at batch=512, N=N'=64, K=32 (oracle port, torch CPU fp32)",
+            "ms_per_step": dt * 1e3}
+
+
+def run_reference(args):
+    """Reference arm: the reference's own algorithm (pure Python/PyTorch, cannot travel to the GPU box) restated in
+    oracle/ and timed on the host cores with every thread torch can use.  Rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    world = args.gpus
+    # bound the run: each step is a sample of `bs` of the 512 transitions, scaled linearly to a full step
+    probe = oracle_learner(64)
+    t0 = time.perf_counter()
+    probe(0)
+    t64 = time.perf_counter() - t0
+    budget = 150.0
+    total_steps = args.steps + max(args.warmup, 1)
+    bs = B
+    while bs > 32 and (t64 * bs / 64) * total_steps > budget:
+        bs //= 2
+    step = oracle_learner(bs)
+    for i in range(max(args.warmup, 1)):
+        step(i)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step(i)
+    dt = (time.perf_counter() - t0) / args.steps
+    full = dt * (B / bs)                                    # time of one full 512-transition learner step
+    value = 1.0 / full
+    out = {"metric": METRIC, "value": value, "unit": "grad-steps/s", "n_gpus": world, "steps": args.steps,
+           "warmup": max(args.warmup, 1), "ms_per_step": full * 1e3, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "impl": "reference",
+           "config": {"workload": "configs[1]: learner step, batch=512, N=N'=64, K=32, n-step=3 (host CPU cores)",
+                      "sample_batch": bs},
+           "cpu_baseline": {"value": value, "unit": "grad-steps/s", "cores": os.cpu_count(),
+                            "threads": torch.get_num_threads(), "kind": "port",
+                            "sample": f"each step = {bs} of the 512 transitions of one learner step, time scaled x{B // bs}"},
+           "e2e": {"value": value, "unit": "grad-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--replay-capacity", type=int, default=1 << 19)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -27,6 +27,8 @@ extern "C" {
 
 /* Library / build identification.  Returns RIQN_B200_ABI_VERSION. */
 int riqn_version(void);
+/* Number of CUDA kernels this library has launched in this process (bench.py's gpu_launches). */
+long long riqn_launch_count(void);
 /* 1 if the running device is compute capability 10.x (sm_100a cubins only), else 0; <0 on CUDA error. */
 int riqn_device_ok(void);
 

@@ -24,6 +24,7 @@ class ConvGeom(C.Structure):
 SIGNATURES = {
     "riqn_version": [],
     "riqn_device_ok": [],
+    "riqn_launch_count": [],
     "riqn_conv_fwd": [C.POINTER(ConvGeom), _P, C.c_int, _P, _P, _P, _P, _P],
     "riqn_conv_bwd": [C.POINTER(ConvGeom), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "riqn_fill_uniform": [C.c_long, C.c_ulonglong, C.c_ulonglong, _P, _P],
@@ -69,7 +70,7 @@ def load():
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.argtypes = argtypes
-        fn.restype = C.c_int
+        fn.restype = C.c_longlong if name == "riqn_launch_count" else C.c_int
     if lib.riqn_version() != 1:
         raise RiqnError("ABI version mismatch between _lib.py and libriqn_b200.so")
     _lib = lib
@@ -87,12 +88,33 @@ def ptr(t):
     return t.data_ptr()
 
 
+_timers = None  # {entry point name: [(start_event, end_event), ...]} while bench.py profiles a region
+
+
+def time_entry_points(names):
+    """Record CUDA events (on the launching stream) around every call of the named entry points."""
+    global _timers
+    _timers = {n: [] for n in names} if names else None
+    return _timers
+
+
 def call(name, *args):
     """Invoke a C-ABI entry point on torch's current stream; raise on a non-zero return."""
     lib = load()
-    rc = getattr(lib, name)(*args, stream())
+    if _timers is not None and name in _timers:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*args, stream())
+        e1.record()
+        _timers[name].append((e0, e1, args[0] if args else None))
+    else:
+        rc = getattr(lib, name)(*args, stream())
     if rc != 0:
         raise RiqnError(f"{name} failed with cudaError {rc}")
+
+
+def launch_count():
+    return int(load().riqn_launch_count())
 
 
 def require_device():

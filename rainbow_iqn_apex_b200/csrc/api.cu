@@ -13,3 +13,11 @@ RIQN_API int riqn_device_ok(void) {
   if (e != cudaSuccess) return -(int)e;
   return major == 10 ? 1 : 0;
 }
+
+#include <atomic>
+namespace riqn {
+static std::atomic<long long> g_launches{0};
+void note_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+}  // namespace riqn
+
+RIQN_API long long riqn_launch_count(void) { return riqn::g_launches.load(std::memory_order_relaxed); }

@@ -18,6 +18,8 @@
     if (_e != cudaSuccess) return (int)_e;                    \
   } while (0)
 
+namespace riqn { void note_launches(int n); }   // bookkeeping for riqn_launch_count()
+
 static inline int riqn_cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 
 // ----------------------------------------------------------------------------------------------

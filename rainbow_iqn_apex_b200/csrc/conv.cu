@@ -106,6 +106,7 @@ using namespace riqn;
 
 RIQN_API int riqn_conv_fwd(const riqn_conv_geom* g, const void* in, int in_is_u8, const float* w, const float* bias,
                            float* col, float* out, void* stream) {
+  riqn::note_launches(2);
   cudaStream_t s = (cudaStream_t)stream;
   const long M = (long)g->B * g->OH * g->OW;
   const int K = g->Cin * g->KH * g->KW;
@@ -120,6 +121,7 @@ RIQN_API int riqn_conv_fwd(const riqn_conv_geom* g, const void* in, int in_is_u8
 
 RIQN_API int riqn_conv_bwd(const riqn_conv_geom* g, const float* dout, const float* out, const float* col,
                            const float* w, float* dY, float* dcol, float* dw, float* dbias, float* din, void* stream) {
+  riqn::note_launches(din ? 5 : 3);
   cudaStream_t s = (cudaStream_t)stream;
   const long M = (long)g->B * g->OH * g->OW;
   const int K = g->Cin * g->KH * g->KW;

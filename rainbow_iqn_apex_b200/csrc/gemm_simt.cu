@@ -183,6 +183,7 @@ int gemm_f32(int M, int N, int K, const float* A, long sAm, long sAk, const floa
 // Test hook (C-ABI): plain strided fp32 product, C = A * B^T in the (m,k)/(n,k) stride convention.
 RIQN_API int riqn_gemm_f32(int M, int N, int K, const float* A, long sAm, long sAk, const float* B, long sBn,
                            long sBk, float* C, long ldc, void* stream) {
+  riqn::note_launches(1);
   riqn::EpiArgs e;
   return riqn::gemm_f32(M, N, K, A, sAm, sAk, B, sBn, sBk, C, ldc, riqn::EPI_STORE, e, 1, (cudaStream_t)stream);
 }

@@ -317,12 +317,14 @@ static inline int grid_for(long total, int per = 256) {
 using namespace riqn;
 
 RIQN_API int riqn_fill_uniform(long n, unsigned long long seed, unsigned long long stream_id, float* out, void* stream) {
+  riqn::note_launches(1);
   if (n <= 0) return 0;
   fill_uniform_kernel<<<riqn_cdiv((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(n, seed, stream_id, out);
   return (int)cudaGetLastError();
 }
 
 RIQN_API int riqn_noisy_sample(long n, unsigned long long seed, unsigned long long stream_id, float* out, void* stream) {
+  riqn::note_launches(1);
   if (n <= 0) return 0;
   fill_scaled_normal_kernel<<<riqn_cdiv((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(n, seed, stream_id, out);
   return (int)cudaGetLastError();
@@ -332,6 +334,7 @@ RIQN_API int riqn_noisy_compose(int out_features, int in_features, const float* 
                                 float* weight_epsilon, const float* eps_in, const float* eps_out, const float* bias_mu,
                                 const float* bias_sigma, float* bias_epsilon, float* w_eff, float* b_eff, int training,
                                 void* stream) {
+  riqn::note_launches(1);
   noisy_compose_kernel<<<grid_for((long)out_features * in_features), 256, 0, (cudaStream_t)stream>>>(
       out_features, in_features, weight_mu, weight_sigma, weight_epsilon, eps_in, eps_out, bias_mu, bias_sigma,
       bias_epsilon, w_eff, b_eff, training);
@@ -341,6 +344,7 @@ RIQN_API int riqn_noisy_compose(int out_features, int in_features, const float* 
 RIQN_API int riqn_quantile_embed_fwd(int batch, int num_quantiles, int embed_dim, int feat_dim, const float* tau,
                                      const float* feat, const float* iqn_w, const float* iqn_b, float* cosv, float* x,
                                      void* stream) {
+  riqn::note_launches(2);
   cudaStream_t s = (cudaStream_t)stream;
   const long R = (long)batch * num_quantiles;
   cos_embed_kernel<<<riqn_cdiv(R * embed_dim, 256), 256, 0, s>>>(R, embed_dim, tau, cosv);
@@ -355,6 +359,7 @@ RIQN_API int riqn_quantile_embed_fwd(int batch, int num_quantiles, int embed_dim
 RIQN_API int riqn_quantile_embed_bwd(int batch, int num_quantiles, int embed_dim, int feat_dim, const float* x,
                                      const float* feat, const float* cosv, float* dx_inout, float* dfeat,
                                      float* grad_iqn_w, float* grad_iqn_b, void* stream) {
+  riqn::note_launches(3);
   cudaStream_t s = (cudaStream_t)stream;
   const long R = (long)batch * num_quantiles;
   embed_bwd_elem_kernel<<<riqn_cdiv((long)batch * feat_dim, 256), 256, 0, s>>>(batch, num_quantiles, feat_dim, x, feat,
@@ -373,6 +378,7 @@ RIQN_API int riqn_quantile_embed_bwd(int batch, int num_quantiles, int embed_dim
 
 RIQN_API int riqn_noisy_linear_fwd(long rows, int in_features, int out_features, const float* x, const float* w_eff,
                                    const float* b_eff, float* h, void* stream) {
+  riqn::note_launches(1);
   EpiArgs e;
   e.bias = b_eff;
   return gemm_f32((int)rows, out_features, in_features, x, in_features, 1, w_eff, in_features, 1, h, out_features,
@@ -381,6 +387,7 @@ RIQN_API int riqn_noisy_linear_fwd(long rows, int in_features, int out_features,
 
 RIQN_API int riqn_noisy_linear_dgrad(long rows, int in_features, int out_features, const float* dh, const float* w_eff,
                                      float* dx, void* stream) {
+  riqn::note_launches(1);
   EpiArgs e;
   return gemm_f32((int)rows, in_features, out_features, dh, out_features, 1, w_eff, 1, in_features, dx, in_features,
                   EPI_STORE, e, 1, (cudaStream_t)stream);
@@ -390,6 +397,7 @@ RIQN_API int riqn_noisy_linear_wgrad(long rows, int in_features, int out_feature
                                      const float* weight_epsilon, const float* bias_epsilon, float* db_scratch,
                                      float* grad_weight_mu, float* grad_weight_sigma, float* grad_bias_mu,
                                      float* grad_bias_sigma, void* stream) {
+  riqn::note_launches(3);
   cudaStream_t s = (cudaStream_t)stream;
   EpiArgs e;
   e.out2 = grad_weight_sigma;
@@ -407,6 +415,7 @@ RIQN_API int riqn_noisy_linear_wgrad(long rows, int in_features, int out_feature
 
 RIQN_API int riqn_dueling_fwd(long rows, int hidden, int action_space, const float* h, const float* wz, const float* bz,
                               float* q, void* stream) {
+  riqn::note_launches(1);
   if (hidden != 512 || action_space > 31) return (int)cudaErrorInvalidValue;
   const size_t smem = sizeof(float) * (1 + action_space) * hidden;
   static bool attr = false;
@@ -421,6 +430,7 @@ RIQN_API int riqn_dueling_fwd(long rows, int hidden, int action_space, const flo
 RIQN_API int riqn_dueling_bwd(long rows, int batch, int hidden, int action_space, const float* h, const float* wz,
                               const float* dtheta, const float* gscale, const long long* actions, float* dh, float* dz,
                               void* stream) {
+  riqn::note_launches(1);
   if (hidden != 512 || action_space > 31) return (int)cudaErrorInvalidValue;
   const size_t smem = sizeof(float) * ((1 + action_space) * hidden + hidden);
   static bool attr = false;
@@ -437,6 +447,7 @@ RIQN_API int riqn_z_wgrad(long rows, int hidden, int action_space, const float* 
                           float* dbz_scratch, const float* eps_w_zv, const float* eps_b_zv, const float* eps_w_za,
                           const float* eps_b_za, float* g_mu_zv, float* g_sig_zv, float* g_bmu_zv, float* g_bsig_zv,
                           float* g_mu_za, float* g_sig_za, float* g_bmu_za, float* g_bsig_za, void* stream) {
+  riqn::note_launches(3);
   cudaStream_t s = (cudaStream_t)stream;
   const int W = 2 * hidden;
   RIQN_CUDA(cudaMemsetAsync(dwz_scratch, 0, sizeof(float) * 32 * W, s));
@@ -456,6 +467,7 @@ RIQN_API int riqn_z_wgrad(long rows, int hidden, int action_space, const float* 
 
 RIQN_API int riqn_argmax_mean(int batch, int num_quantiles, int action_space, const float* q, long long* a_star,
                               void* stream) {
+  riqn::note_launches(1);
   argmax_mean_kernel<<<riqn_cdiv(batch, 128), 128, 0, (cudaStream_t)stream>>>(batch, num_quantiles, action_space, q,
                                                                             (int64_t*)a_star);
   return (int)cudaGetLastError();
@@ -466,6 +478,7 @@ RIQN_API int riqn_iqn_loss_fwd_bwd(int batch, int n_tau, int n_tau_prime, int ac
                                    const long long* a_star, const float* returns, const float* nonterminals,
                                    float gamma_n, float kappa, float* loss, float* dtheta, float* theta_out,
                                    float* target_out, void* stream) {
+  riqn::note_launches(1);
   int threads = ((n_tau > n_tau_prime ? n_tau : n_tau_prime) + 31) / 32 * 32;
   if (threads > 1024) threads = 1024;
   if (threads < 32) threads = 32;
@@ -478,6 +491,7 @@ RIQN_API int riqn_iqn_loss_fwd_bwd(int batch, int n_tau, int n_tau_prime, int ac
 
 RIQN_API int riqn_adam_step(long n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int step,
                             float lr, float beta1, float beta2, float eps, float grad_scale, void* stream) {
+  riqn::note_launches(1);
   const double bc1 = 1.0 - pow((double)beta1, (double)step);
   const double bc2 = 1.0 - pow((double)beta2, (double)step);
   adam_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(n, params, grads, exp_avg, exp_avg_sq, (float)(-(lr / bc1)),

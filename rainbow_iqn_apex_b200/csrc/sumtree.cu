@@ -354,6 +354,7 @@ using namespace riqn;
 
 RIQN_API int riqn_sumtree_stratified(int n, unsigned long long seed, unsigned long long stream_id, const double* tree,
                                      double* values, void* stream) {
+  riqn::note_launches(1);
   if (n <= 0 || n > 12000) return (int)cudaErrorInvalidValue;
   stratified_kernel<<<1, 1024, sizeof(int) * n, (cudaStream_t)stream>>>(n, seed, stream_id, tree, values);
   return (int)cudaGetLastError();
@@ -362,6 +363,7 @@ RIQN_API int riqn_sumtree_stratified(int n, unsigned long long seed, unsigned lo
 RIQN_API int riqn_sumtree_sample(int n, long capacity, int actor_capacity, const double* tree, const double* values,
                                  const long long* index_actor, int history, int n_step, long long* tree_idx,
                                  long long* data_idx, double* priorities, void* stream) {
+  riqn::note_launches(1);
   if (n <= 0) return 0;
   const int warps_per_block = 4;
   sumtree_sample_kernel<<<riqn_cdiv(n, warps_per_block), warps_per_block * 32, 0, (cudaStream_t)stream>>>(
@@ -372,6 +374,7 @@ RIQN_API int riqn_sumtree_sample(int n, long capacity, int actor_capacity, const
 
 RIQN_API int riqn_sumtree_is_weights(int n, const double* tree, const double* priorities, double current_capacity,
                                      double priority_weight, double* w64, float* w32, int* n_nonpositive, void* stream) {
+  riqn::note_launches(1);
   is_weights_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(n, tree, priorities, current_capacity, priority_weight, w64,
                                                           w32, n_nonpositive);
   return (int)cudaGetLastError();
@@ -380,6 +383,7 @@ RIQN_API int riqn_sumtree_is_weights(int n, const double* tree, const double* pr
 RIQN_API int riqn_sumtree_update(int n, long capacity, double* tree, const long long* tree_idx, const float* loss,
                                  float priority_exponent, int apply_pow, float* new_priorities, double* diff_scratch,
                                  double* max_priority, void* stream) {
+  riqn::note_launches(2);
   if (n <= 0) return 0;
   if (n > 4096) return (int)cudaErrorInvalidValue;  // shared-memory bound of the propagate kernel
   cudaStream_t s = (cudaStream_t)stream;
@@ -402,6 +406,7 @@ RIQN_API int riqn_replay_append(int n, int actor_capacity, int id_actor, int sta
                                 const int* timestep, const int* action, const float* reward,
                                 const unsigned char* nonterminal, unsigned char* s_frames, int* s_timestep, int* s_action,
                                 float* s_reward, unsigned char* s_nonterminal, void* stream) {
+  riqn::note_launches(1);
   if (n <= 0) return 0;
   replay_append_kernel<<<n, 128, 0, (cudaStream_t)stream>>>(n, actor_capacity, id_actor, start, frames, timestep, action,
                                                             reward, nonterminal, s_frames, s_timestep, s_action, s_reward,
@@ -414,6 +419,7 @@ RIQN_API int riqn_frame_gather(int batch, int actor_capacity, int history, int n
                                const float* s_reward, const unsigned char* s_nonterminal, const double* gamma_pow,
                                unsigned char* window, long long* actions, float* returns, float* nonterminals,
                                void* stream) {
+  riqn::note_launches(1);
   if (batch <= 0) return 0;
   if (history + n_step > 16) return (int)cudaErrorInvalidValue;
   frame_gather_kernel<<<batch, 256, 0, (cudaStream_t)stream>>>(batch, actor_capacity, history, n_step,

@@ -139,6 +139,7 @@ class DQN(nn.Module):
         for i, m in enumerate((self.fcnoisy_h_v, self.fcnoisy_h_a, self.fcnoisy_z_v, self.fcnoisy_z_a)):
             m._layer_id = i + 1
         self._tau_calls = 0
+        self._tau_stream_offset = 0   # rank-private quantile stream under data parallelism
         self._rng_seed = int(torch.randint(0, 2 ** 62, (1,)).item())
         self._flatten()
         if self._flat.is_cuda:
@@ -259,7 +260,7 @@ class DQN(nn.Module):
 
     def draw_quantiles(self, n):
         tau = torch.empty(n, 1, device=self._flat.device)
-        call("riqn_fill_uniform", n, self._rng_seed ^ 0x7A75, self._tau_calls, ptr(tau))
+        call("riqn_fill_uniform", n, self._rng_seed ^ 0x7A75, self._tau_stream_offset + self._tau_calls, ptr(tau))
         self._tau_calls += 1
         return tau
 
