@@ -90,6 +90,10 @@ int riqn_noisy_linear_wgrad(long rows, int in_features, int out_features, const 
                             float* grad_weight_mu, float* grad_weight_sigma, float* grad_bias_mu,
                             float* grad_bias_sigma, void* stream);
 
+/* Bias half of the above alone (used when the weight half runs on the tensor cores). */
+int riqn_noisy_bias_grad(long rows, int out_features, const float* dh, const float* bias_epsilon, float* db_scratch,
+                         float* grad_bias_mu, float* grad_bias_sigma, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Quantile embedding                                      replaces rainbowiqn/model.py:136-151
  * ---------------------------------------------------------------------------------------------- */
@@ -188,6 +192,19 @@ int riqn_frame_gather(int batch, int actor_capacity, int history, int n_step, co
                       const unsigned char* s_frames, const int* s_timestep, const int* s_action, const float* s_reward,
                       const unsigned char* s_nonterminal, const double* gamma_pow, unsigned char* window,
                       long long* actions, float* returns, float* nonterminals, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Tensor-core building blocks of the NoisyLinear products (tcgen05.mma + TMA; csrc/gemm_tc.cu).
+ * ---------------------------------------------------------------------------------------------- */
+/* fp32 (rows, cols) -> bf16 hi and lo = bf16(x - hi) (either may be NULL); hi_t / lo_t (may be NULL) receive the
+ * transposed (cols, rows) copies the weight-gradient product consumes. */
+int riqn_split_bf16(long rows, int cols, const float* src, void* hi, void* lo, void* hi_t, void* lo_t, void* stream);
+/* C (+)= A B^T with A (M,K), B (N,K) row-major bf16, K % 8 == 0, fp32 accumulation in TMEM.  a_lo/b_lo non-NULL
+ * selects the split-bf16 x3 (fp32-faithful) product.  epilogue: 0 store, 1 relu(acc+bias[n]), 2 atomicAdd into C,
+ * 3 atomicAdd into C and acc*eps[m,n] into out2 (NoisyLinear dmu / dsigma).  split_k > 1 needs 2 or 3. */
+int riqn_gemm_bf16_tc(int M, int N, int K, const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo,
+                      float* c, long ldc, int epilogue, const float* bias, float* out2, const float* eps, int split_k,
+                      void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Test hook: plain strided fp32 product C[m,n] = sum_k A[m*sAm + k*sAk] * B[n*sBn + k*sBk].

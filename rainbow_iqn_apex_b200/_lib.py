@@ -33,6 +33,7 @@ SIGNATURES = {
     "riqn_noisy_linear_fwd": [C.c_long, C.c_int, C.c_int, _P, _P, _P, _P, _P],
     "riqn_noisy_linear_dgrad": [C.c_long, C.c_int, C.c_int, _P, _P, _P, _P],
     "riqn_noisy_linear_wgrad": [C.c_long, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "riqn_noisy_bias_grad": [C.c_long, C.c_int, _P, _P, _P, _P, _P, _P],
     "riqn_quantile_embed_fwd": [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P],
     "riqn_quantile_embed_bwd": [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P],
     "riqn_dueling_fwd": [C.c_long, C.c_int, C.c_int, _P, _P, _P, _P, _P],
@@ -48,6 +49,8 @@ SIGNATURES = {
     "riqn_sumtree_update": [C.c_int, C.c_long, _P, _P, _P, C.c_float, C.c_int, _P, _P, _P, _P],
     "riqn_replay_append": [C.c_int, C.c_int, C.c_int, C.c_int] + [_P] * 11,
     "riqn_frame_gather": [C.c_int, C.c_int, C.c_int, C.c_int] + [_P] * 12,
+    "riqn_split_bf16": [C.c_long, C.c_int, _P, _P, _P, _P, _P, _P],
+    "riqn_gemm_bf16_tc": [C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, C.c_long, C.c_int, _P, _P, _P, C.c_int, _P],
     "riqn_gemm_f32": [C.c_int, C.c_int, C.c_int, _P, C.c_long, C.c_long, _P, C.c_long, C.c_long, _P, C.c_long, _P],
 }
 
@@ -106,7 +109,7 @@ def call(name, *args):
         e0.record()
         rc = getattr(lib, name)(*args, stream())
         e1.record()
-        _timers[name].append((e0, e1, args[0] if args else None))
+        _timers[name].append((e0, e1, args))
     else:
         rc = getattr(lib, name)(*args, stream())
     if rc != 0:

@@ -1,0 +1,439 @@
+// tcgen05 / TMA GEMM for the NoisyLinear hidden layers of the IQN head (the >90% of the learner step's FLOPs:
+// reference model.py:153-154 forward, and its dgrad / wgrad), sm_100a only.
+//
+//   C[m,n] = sum_k A[m,k] * B[n,k]        A (M,K) and B (N,K) both K-major bf16 in HBM, fp32 accumulate in TMEM
+//
+// * operands arrive by TMA (cp.async.bulk.tensor.2d, 128-byte swizzle) into a multi-stage shared-memory ring,
+// * one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (UMMA 128x256x16) on shared-memory descriptors,
+// * accumulators live in TMEM, double buffered (2 x 256 columns = all 512) so the epilogue of tile i overlaps the
+//   MMAs of tile i+1; 4 epilogue warps read them back with tcgen05.ld and apply the fused epilogue,
+// * persistent CTAs (one per SM) walk (m-tile, n-tile, k-split) work units round-robin.
+//
+// Precision: NSPLIT == 1 multiplies bf16(A) * bf16(B).  NSPLIT == 3 takes each operand as hi + lo bf16 pairs
+// (a = a_hi + a_lo exactly to ~2^-17) and accumulates a_hi*b_hi + a_hi*b_lo + a_lo*b_hi into the same TMEM
+// accumulator: an fp32-faithful product (rel. error ~1e-5 per term) at 3 MMAs per k-step, which keeps the IQN
+// loss within 1e-6 of the fp32 reference instead of bf16's 1e-4.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include "common.cuh"
+#include "gemm.h"
+#include "../../include/riqn_b200.h"
+
+namespace riqn {
+
+using bf16 = __nv_bfloat16;
+
+constexpr int TBM = 128, TBN = 256, TBK = 64, UMMA_K = 16;
+constexpr int TC_THREADS = 192;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr uint32_t TMEM_COLS = 512;
+
+template <int NSPLIT>
+struct TcCfg {
+  static constexpr int kOps = NSPLIT == 1 ? 1 : 2;                                   // hi (+ lo) per operand
+  static constexpr int kStages = NSPLIT == 1 ? 4 : 2;
+  static constexpr uint32_t kABytes = TBM * TBK * 2, kBBytes = TBN * TBK * 2;
+  static constexpr uint32_t kStageBytes = kOps * (kABytes + kBBytes);                // 48 KB or 96 KB
+  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+// ---------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
+      "%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128-byte-swizzled operand tile: rows of 64 bf16 (128 B), 8-row swizzle atoms 1024 B apart.
+// Descriptor fields (cute/arch/mma_sm100_desc.hpp): start>>4 [0,14), LBO>>4 [16,30) (=1, unused for swizzled
+// K-major), SBO>>4 [32,46) (=1024>>4), version=1 [46,48), layout SWIZZLE_128B=2 [61,64).
+__device__ __forceinline__ uint64_t umma_desc_k128(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+// kind::f16 instruction descriptor: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, K-major both, N>>3 [17,23), M>>4 [24,29)
+__device__ __forceinline__ uint32_t umma_idesc_bf16(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+enum TcEpi { TC_STORE = 0, TC_BIAS_RELU = 1, TC_ATOMIC = 2, TC_NOISY_WGRAD = 3 };
+
+struct TcArgs {
+  int M, N, K;
+  int m_tiles, n_tiles, k_splits, kb_per_split, kb_total;
+  float* C;
+  long ldc;
+  const float* bias;     // TC_BIAS_RELU
+  float* out2;           // TC_NOISY_WGRAD: grad_sigma
+  const float* eps;      // TC_NOISY_WGRAD: weight_epsilon (same layout as C)
+};
+
+template <int NSPLIT, int EPI>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
+               const __grid_constant__ CUtensorMap mapB_hi, const __grid_constant__ CUtensorMap mapB_lo, TcArgs p) {
+  using Cfg = TcCfg<NSPLIT>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full = bars;                       // [kStages]  TMA -> MMA
+  uint64_t* empty = bars + Cfg::kStages;       // [kStages]  MMA -> TMA
+  uint64_t* tfull = bars + 2 * Cfg::kStages;   // [2]        MMA -> epilogue
+  uint64_t* tempty = tfull + 2;                // [2]        epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_units = p.m_tiles * p.n_tiles * p.k_splits;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+        const int ks = u % p.k_splits, t = u / p.k_splits;
+        const int mt = t % p.m_tiles, nt = t / p.m_tiles;
+        const int kb0 = ks * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* s = smem + stage * Cfg::kStageBytes;
+          mbar_expect_tx(&full[stage], Cfg::kStageBytes);
+          tma_load_2d(s, &mapA_hi, kb * TBK, mt * TBM, &full[stage]);
+          tma_load_2d(s + Cfg::kOps * Cfg::kABytes, &mapB_hi, kb * TBK, nt * TBN, &full[stage]);
+          if (NSPLIT == 3) {
+            tma_load_2d(s + Cfg::kABytes, &mapA_lo, kb * TBK, mt * TBM, &full[stage]);
+            tma_load_2d(s + 2 * Cfg::kABytes + Cfg::kBBytes, &mapB_lo, kb * TBK, nt * TBN, &full[stage]);
+          }
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (one thread)
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(TBM, TBN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++local) {
+        const int ks = u % p.k_splits;
+        const int kb0 = ks * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        const int as = local & 1;
+        const uint32_t aphase = (local >> 1) & 1;
+        mbar_wait(&tempty[as], aphase ^ 1);     // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * TBN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t sb = sa + Cfg::kOps * Cfg::kABytes;
+#pragma unroll
+          for (int k = 0; k < TBK / UMMA_K; ++k) {
+            const uint32_t koff = k * UMMA_K * 2;   // bytes along K inside the 128 B swizzle row
+            const uint64_t a_hi = umma_desc_k128(sa + koff), b_hi = umma_desc_k128(sb + koff);
+            umma_bf16(tmem_d, a_hi, b_hi, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (NSPLIT == 3) {
+              const uint64_t a_lo = umma_desc_k128(sa + Cfg::kABytes + koff);
+              const uint64_t b_lo = umma_desc_k128(sb + Cfg::kBBytes + koff);
+              umma_bf16(tmem_d, a_hi, b_lo, idesc, 1u);
+              umma_bf16(tmem_d, a_lo, b_hi, idesc, 1u);
+            }
+          }
+          umma_commit(&empty[stage]);             // smem slot free once these MMAs retire
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull[as]);                  // accumulator complete
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps (TMEM -> registers -> HBM)
+    const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32) are the ones this warp may read
+    int local = 0;
+    for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++local) {
+      const int t = u / p.k_splits;
+      const int mt = t % p.m_tiles, nt = t / p.m_tiles;
+      const int as = local & 1;
+      const uint32_t aphase = (local >> 1) & 1;
+      mbar_wait(&tfull[as], aphase);
+      tc_fence_after();
+      const int m = mt * TBM + quarter * 32 + lane;
+      const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * TBN;
+#pragma unroll 1
+      for (int c = 0; c < TBN; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(trow + c, v);
+        const int n0 = nt * TBN + c;
+        if (m < p.M && n0 < p.N) {
+          float* crow = p.C + (long)m * p.ldc + n0;
+          if (EPI == TC_STORE || EPI == TC_BIAS_RELU) {
+            if (n0 + 32 <= p.N) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                       __uint_as_float(v[j + 3]));
+                if (EPI == TC_BIAS_RELU) {
+                  const float4 b = *reinterpret_cast<const float4*>(p.bias + n0 + j);
+                  o.x = fmaxf(o.x + b.x, 0.f); o.y = fmaxf(o.y + b.y, 0.f);
+                  o.z = fmaxf(o.z + b.z, 0.f); o.w = fmaxf(o.w + b.w, 0.f);
+                }
+                *reinterpret_cast<float4*>(crow + j) = o;
+              }
+            } else {
+              for (int j = 0; j < 32 && n0 + j < p.N; ++j) {
+                float o = __uint_as_float(v[j]);
+                if (EPI == TC_BIAS_RELU) o = fmaxf(o + p.bias[n0 + j], 0.f);
+                crow[j] = o;
+              }
+            }
+          } else {
+            for (int j = 0; j < 32 && n0 + j < p.N; ++j) {
+              const float o = __uint_as_float(v[j]);
+              atomicAdd(crow + j, o);
+              if (EPI == TC_NOISY_WGRAD)
+                atomicAdd(p.out2 + (long)m * p.ldc + n0 + j, o * p.eps[(long)m * p.ldc + n0 + j]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  });
+  return fn;
+}
+
+// (rows, K) row-major bf16 matrix, box = box_rows x 64 elements, 128-byte swizzle.  Out-of-bounds -> zeros.
+static int make_map(CUtensorMap* map, const bf16* base, long rows, long K, int box_rows) {
+  auto enc = get_encode();
+  if (!enc) return (int)cudaErrorNotSupported;
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)(K * sizeof(bf16))};
+  cuuint32_t box[2] = {(cuuint32_t)TBK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
+}
+
+template <int NSPLIT, int EPI>
+static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
+                     const TcArgs& p, cudaStream_t s) {
+  using Cfg = TcCfg<NSPLIT>;
+  static bool attr = false;
+  if (!attr) {
+    RIQN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<NSPLIT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)Cfg::kSmemBytes));
+    attr = true;
+  }
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    RIQN_CUDA(cudaGetDevice(&dev));
+    RIQN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int units = p.m_tiles * p.n_tiles * p.k_splits;
+  const int grid = units < sms ? units : sms;
+  gemm_tc_kernel<NSPLIT, EPI><<<grid, TC_THREADS, Cfg::kSmemBytes, s>>>(a_hi, a_lo, b_hi, b_lo, p);
+  return (int)cudaGetLastError();
+}
+
+// C (+)= A * B^T on the tensor cores.  A (M,K), B (N,K) bf16 row-major (K % 8 == 0); *_lo may be null (NSPLIT 1).
+int gemm_bf16_tc(int M, int N, int K, const bf16* A_hi, const bf16* A_lo, const bf16* B_hi, const bf16* B_lo, float* C,
+                 long ldc, int epi, const float* bias, float* out2, const float* eps, int split_k, cudaStream_t s) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if (K % 8) return (int)cudaErrorInvalidValue;
+  const bool split3 = A_lo != nullptr && B_lo != nullptr;
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  int rc = make_map(&ma_hi, A_hi, M, K, TBM);
+  if (rc) return rc;
+  rc = make_map(&mb_hi, B_hi, N, K, TBN);
+  if (rc) return rc;
+  if (split3) {
+    rc = make_map(&ma_lo, A_lo, M, K, TBM);
+    if (rc) return rc;
+    rc = make_map(&mb_lo, B_lo, N, K, TBN);
+    if (rc) return rc;
+  } else {
+    ma_lo = ma_hi;
+    mb_lo = mb_hi;
+  }
+  TcArgs p;
+  p.M = M; p.N = N; p.K = K;
+  p.m_tiles = (M + TBM - 1) / TBM;
+  p.n_tiles = (N + TBN - 1) / TBN;
+  p.kb_total = (K + TBK - 1) / TBK;
+  if (split_k < 1) split_k = 1;
+  if (split_k > p.kb_total) split_k = p.kb_total;
+  p.kb_per_split = (p.kb_total + split_k - 1) / split_k;
+  p.k_splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+  if (p.k_splits > 1 && epi != TC_ATOMIC && epi != TC_NOISY_WGRAD) return (int)cudaErrorInvalidValue;
+  p.C = C; p.ldc = ldc; p.bias = bias; p.out2 = out2; p.eps = eps;
+#define RIQN_TC_GO(NS, EP) return launch_tc<NS, EP>(ma_hi, ma_lo, mb_hi, mb_lo, p, s)
+  if (split3) {
+    switch (epi) {
+      case TC_STORE: RIQN_TC_GO(3, TC_STORE);
+      case TC_BIAS_RELU: RIQN_TC_GO(3, TC_BIAS_RELU);
+      case TC_ATOMIC: RIQN_TC_GO(3, TC_ATOMIC);
+      case TC_NOISY_WGRAD: RIQN_TC_GO(3, TC_NOISY_WGRAD);
+    }
+  } else {
+    switch (epi) {
+      case TC_STORE: RIQN_TC_GO(1, TC_STORE);
+      case TC_BIAS_RELU: RIQN_TC_GO(1, TC_BIAS_RELU);
+      case TC_ATOMIC: RIQN_TC_GO(1, TC_ATOMIC);
+      case TC_NOISY_WGRAD: RIQN_TC_GO(1, TC_NOISY_WGRAD);
+    }
+  }
+#undef RIQN_TC_GO
+  return (int)cudaErrorInvalidValue;
+}
+
+// ---------------------------------------------------------------------------------------------- operand producers
+// fp32 (rows, cols) -> bf16 hi (+ lo = bf16(x - hi)), optionally also transposed copies (cols, rows).
+__global__ void split_bf16_kernel(long rows, int cols, const float* __restrict__ src, bf16* __restrict__ hi,
+                                  bf16* __restrict__ lo, bf16* __restrict__ hiT, bf16* __restrict__ loT) {
+  __shared__ float tile[32][33];
+  const long r0 = (long)blockIdx.y * 32;
+  const int c0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const long r = r0 + i;
+    const int c = c0 + tx;
+    float x = 0.f;
+    if (r < rows && c < cols) {
+      x = src[r * cols + c];
+      const bf16 h = __float2bfloat16_rn(x);
+      if (hi) hi[r * cols + c] = h;
+      if (lo) lo[r * cols + c] = __float2bfloat16_rn(x - __bfloat162float(h));
+    }
+    tile[i][tx] = x;
+  }
+  if (!hiT) return;
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i;
+    const long r = r0 + tx;
+    if (r < rows && c < cols) {
+      const float x = tile[tx][i];
+      const bf16 h = __float2bfloat16_rn(x);
+      hiT[(long)c * rows + r] = h;
+      if (loT) loT[(long)c * rows + r] = __float2bfloat16_rn(x - __bfloat162float(h));
+    }
+  }
+}
+
+int split_bf16(long rows, int cols, const float* src, bf16* hi, bf16* lo, bf16* hiT, bf16* loT, cudaStream_t s) {
+  dim3 grid((cols + 31) / 32, (unsigned)((rows + 31) / 32));
+  split_bf16_kernel<<<grid, 256, 0, s>>>(rows, cols, src, hi, lo, hiT, loT);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace riqn
+
+using namespace riqn;
+
+RIQN_API int riqn_split_bf16(long rows, int cols, const float* src, void* hi, void* lo, void* hi_t, void* lo_t,
+                             void* stream) {
+  riqn::note_launches(1);
+  return split_bf16(rows, cols, src, (bf16*)hi, (bf16*)lo, (bf16*)hi_t, (bf16*)lo_t, (cudaStream_t)stream);
+}
+
+RIQN_API int riqn_gemm_bf16_tc(int M, int N, int K, const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo,
+                               float* c, long ldc, int epilogue, const float* bias, float* out2, const float* eps,
+                               int split_k, void* stream) {
+  riqn::note_launches(1);
+  return gemm_bf16_tc(M, N, K, (const bf16*)a_hi, (const bf16*)a_lo, (const bf16*)b_hi, (const bf16*)b_lo, c, ldc, epilogue,
+                      bias, out2, eps, split_k, (cudaStream_t)stream);
+}

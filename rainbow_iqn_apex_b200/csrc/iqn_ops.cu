@@ -413,6 +413,18 @@ RIQN_API int riqn_noisy_linear_wgrad(long rows, int in_features, int out_feature
   return (int)cudaGetLastError();
 }
 
+RIQN_API int riqn_noisy_bias_grad(long rows, int out_features, const float* dh, const float* bias_epsilon,
+                                  float* db_scratch, float* grad_bias_mu, float* grad_bias_sigma, void* stream) {
+  riqn::note_launches(2);
+  cudaStream_t s = (cudaStream_t)stream;
+  RIQN_CUDA(cudaMemsetAsync(db_scratch, 0, sizeof(float) * out_features, s));
+  int rc = colsum_atomic(rows, out_features, dh, db_scratch, s);
+  if (rc) return rc;
+  noisy_bias_grad_kernel<<<riqn_cdiv(out_features, 256), 256, 0, s>>>(out_features, db_scratch, bias_epsilon,
+                                                                    grad_bias_mu, grad_bias_sigma);
+  return (int)cudaGetLastError();
+}
+
 RIQN_API int riqn_dueling_fwd(long rows, int hidden, int action_space, const float* h, const float* wz, const float* bz,
                               float* q, void* stream) {
   riqn::note_launches(1);

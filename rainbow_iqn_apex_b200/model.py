@@ -16,6 +16,7 @@ optimiser and the gradient all-reduce touch one contiguous buffer.
 There is no PyTorch fallback: every tensor operation below is a C-ABI call (include/riqn_b200.h).
 """
 import math
+import os
 import weakref
 
 import torch
@@ -26,6 +27,21 @@ from ._lib import ConvGeom, call, ptr
 
 FEAT = 3136
 _ALIGN = 64  # floats; arena groups start on 256-byte boundaries
+
+# Arithmetic of the hidden NoisyLinear products (x W^T, dh W, dh^T x -- 91% of the step's FLOPs):
+#   "bf16x3": tcgen05 tensor cores, every operand split into bf16 hi + lo, 3 MMAs per k-step (fp32-faithful)
+#   "bf16"  : tcgen05 tensor cores, operands rounded to bf16 once, fp32 accumulation in TMEM
+#   "fp32"  : CUDA-core fp32 GEMM (gemm_simt.cu), the cross-check path
+PRECISION = {"fwd": os.environ.get("RIQN_FWD_PRECISION", "bf16x3"), "bwd": os.environ.get("RIQN_BWD_PRECISION", "bf16")}
+WGRAD_SPLIT_K = int(os.environ.get("RIQN_WGRAD_SPLIT_K", "6"))
+
+
+def set_precision(fwd=None, bwd=None):
+    for k, v in (("fwd", fwd), ("bwd", bwd)):
+        if v is not None:
+            if v not in ("bf16x3", "bf16", "fp32"):
+                raise ValueError(v)
+            PRECISION[k] = v
 
 
 class NoisyLinear(nn.Module):
@@ -252,11 +268,27 @@ class DQN(nn.Module):
                 module.reset_noise(e_in.to(self._flat.device), e_out.to(self._flat.device))
             else:
                 module.reset_noise(seed=self._rng_seed)
+        self._refresh_tc_operands()
 
     def compose_weights(self):
         """Recompute the effective weights from the stored epsilons (after load_state_dict / optimiser steps)."""
         for _, module in self.noisy_layers():
             module._compose()
+        self._refresh_tc_operands()
+
+    def _refresh_tc_operands(self):
+        """bf16 (hi, lo) images of the composed hidden-layer weights for the tcgen05 path: (2*hid, 3136) K-major for
+        the forward product and the transposed (3136, 2*hid) copy the data-gradient product consumes."""
+        if self.rainbow_only or (PRECISION["fwd"] == "fp32" and PRECISION["bwd"] == "fp32") or not self._flat.is_cuda:
+            return
+        dev = self._flat.device
+        if getattr(self, "_w_hi", None) is None or self._w_hi.device != dev:
+            n = 2 * self.hidden
+            mk = lambda *sh: torch.empty(*sh, dtype=torch.bfloat16, device=dev)
+            self._w_hi, self._w_lo = mk(n, FEAT), mk(n, FEAT)
+            self._w_hiT, self._w_loT = mk(FEAT, n), mk(FEAT, n)
+        call("riqn_split_bf16", 2 * self.hidden, FEAT, ptr(self._w_eff_h), ptr(self._w_hi), ptr(self._w_lo),
+             ptr(self._w_hiT), ptr(self._w_loT))
 
     def draw_quantiles(self, n):
         tau = torch.empty(n, 1, device=self._flat.device)
@@ -303,11 +335,25 @@ class DQN(nn.Module):
         call("riqn_quantile_embed_fwd", B, num_quantiles, E, FEAT, ptr(tau), ptr(feat), ptr(self.iqn_fc.weight),
              ptr(self.iqn_fc.bias), ptr(cosv), ptr(xt))
         h = torch.empty(R, 2 * hid, device=dev)
-        call("riqn_noisy_linear_fwd", R, FEAT, 2 * hid, ptr(xt), ptr(self._w_eff_h), ptr(self._b_eff_h), ptr(h))
+        fwd = PRECISION["fwd"]
+        want_t = keep is not None and PRECISION["bwd"] != "fp32" and R % 8 == 0
+        tc = None
+        if fwd != "fp32" or want_t:
+            bf = lambda *sh: torch.empty(*sh, dtype=torch.bfloat16, device=dev)
+            x3 = fwd == "bf16x3"
+            t3 = want_t and PRECISION["bwd"] == "bf16x3"
+            tc = dict(x_hi=bf(R, FEAT) if fwd != "fp32" else None, x_lo=bf(R, FEAT) if x3 else None,
+                      x_hiT=bf(FEAT, R) if want_t else None, x_loT=bf(FEAT, R) if t3 else None)
+            call("riqn_split_bf16", R, FEAT, ptr(xt), ptr(tc["x_hi"]), ptr(tc["x_lo"]), ptr(tc["x_hiT"]), ptr(tc["x_loT"]))
+        if fwd == "fp32":
+            call("riqn_noisy_linear_fwd", R, FEAT, 2 * hid, ptr(xt), ptr(self._w_eff_h), ptr(self._b_eff_h), ptr(h))
+        else:
+            call("riqn_gemm_bf16_tc", R, 2 * hid, FEAT, ptr(tc["x_hi"]), ptr(tc["x_lo"]), ptr(self._w_hi),
+                 ptr(self._w_lo) if fwd == "bf16x3" else None, ptr(h), 2 * hid, 1, ptr(self._b_eff_h), None, None, 1)
         q = torch.empty(R, A, device=dev)
         call("riqn_dueling_fwd", R, hid, A, ptr(h), ptr(self._w_eff_z), ptr(self._b_eff_z), ptr(q))
         if keep is not None:
-            keep.update(feat=feat, cos=cosv, xt=xt, h=h, q=q, tau=tau, num_quantiles=num_quantiles)
+            keep.update(feat=feat, cos=cosv, xt=xt, h=h, q=q, tau=tau, num_quantiles=num_quantiles, tc=tc)
         return q
 
     def forward(self, x, num_quantiles=None, log=False, tau=None, keep=None, fresh_weights=False):
@@ -347,12 +393,30 @@ class DQN(nn.Module):
              ptr(gv(zv.weight_mu)), ptr(gv(zv.weight_sigma)), ptr(gv(zv.bias_mu)), ptr(gv(zv.bias_sigma)),
              ptr(gv(za.weight_mu)), ptr(gv(za.weight_sigma)), ptr(gv(za.bias_mu)), ptr(gv(za.bias_sigma)))
         dbs = torch.empty(2 * hid, device=dev)
-        # [h_v | h_a] are adjacent in every arena, so one (2*hid, 3136) product serves both layers
-        call("riqn_noisy_linear_wgrad", R, FEAT, 2 * hid, ptr(dh), ptr(keep["xt"]), ptr(hv.weight_epsilon),
-             ptr(hv.bias_epsilon), ptr(dbs), ptr(gv(hv.weight_mu)), ptr(gv(hv.weight_sigma)), ptr(gv(hv.bias_mu)),
-             ptr(gv(hv.bias_sigma)))
         dx = torch.empty(R, FEAT, device=dev)
-        call("riqn_noisy_linear_dgrad", R, FEAT, 2 * hid, ptr(dh), ptr(self._w_eff_h), ptr(dx))
+        bwd = PRECISION["bwd"]
+        tc = keep.get("tc")
+        # [h_v | h_a] are adjacent in every arena, so one (2*hid, 3136) product serves both layers
+        if bwd == "fp32" or tc is None or tc["x_hiT"] is None:
+            call("riqn_noisy_linear_wgrad", R, FEAT, 2 * hid, ptr(dh), ptr(keep["xt"]), ptr(hv.weight_epsilon),
+                 ptr(hv.bias_epsilon), ptr(dbs), ptr(gv(hv.weight_mu)), ptr(gv(hv.weight_sigma)), ptr(gv(hv.bias_mu)),
+                 ptr(gv(hv.bias_sigma)))
+            call("riqn_noisy_linear_dgrad", R, FEAT, 2 * hid, ptr(dh), ptr(self._w_eff_h), ptr(dx))
+        else:
+            bf = lambda *sh: torch.empty(*sh, dtype=torch.bfloat16, device=dev)
+            b3 = bwd == "bf16x3"
+            dh_hi, dh_hiT = bf(R, 2 * hid), bf(2 * hid, R)
+            dh_lo, dh_loT = (bf(R, 2 * hid), bf(2 * hid, R)) if b3 else (None, None)
+            call("riqn_split_bf16", R, 2 * hid, ptr(dh), ptr(dh_hi), ptr(dh_lo), ptr(dh_hiT), ptr(dh_loT))
+            # dW[o, i] = sum_r dh[r, o] x[r, i]  -> dmu += dW, dsigma += dW * eps   (split-K, atomics)
+            call("riqn_gemm_bf16_tc", 2 * hid, FEAT, R, ptr(dh_hiT), ptr(dh_loT), ptr(tc["x_hiT"]),
+                 ptr(tc["x_loT"]) if b3 else None, ptr(gv(hv.weight_mu)), FEAT, 3, None, ptr(gv(hv.weight_sigma)),
+                 ptr(hv.weight_epsilon), WGRAD_SPLIT_K)
+            call("riqn_noisy_bias_grad", R, 2 * hid, ptr(dh), ptr(hv.bias_epsilon), ptr(dbs), ptr(gv(hv.bias_mu)),
+                 ptr(gv(hv.bias_sigma)))
+            # dx[r, i] = sum_o dh[r, o] W_eff[o, i]
+            call("riqn_gemm_bf16_tc", R, FEAT, 2 * hid, ptr(dh_hi), ptr(dh_lo), ptr(self._w_hiT),
+                 ptr(self._w_loT) if b3 else None, ptr(dx), FEAT, 0, None, None, None, 1)
         dfeat = torch.empty(B, FEAT, device=dev)
         call("riqn_quantile_embed_bwd", B, Nq, E, FEAT, ptr(keep["xt"]), ptr(keep["feat"]), ptr(keep["cos"]), ptr(dx),
              ptr(dfeat), ptr(gv(self.iqn_fc.weight)), ptr(gv(self.iqn_fc.bias)))

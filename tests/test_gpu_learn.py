@@ -13,7 +13,21 @@ from helpers import digest, load_params, make_args, rel_err
 from oracle import cases, losses, network as net
 
 pytestmark = pytest.mark.gpu
-LOSS_TOL = 2e-4
+LOSS_TOL = 2e-4      # fp32 / split-bf16x3 forward products; the north_star bound is 1e-3
+
+
+def _grad_tol():
+    """Norm-relative gradient tolerance of the current backward arithmetic (model.PRECISION)."""
+    from rainbow_iqn_apex_b200 import model
+    return 1e-3 if model.PRECISION["bwd"] in ("fp32", "bf16x3") else 1e-2
+
+
+@pytest.fixture
+def precision():
+    from rainbow_iqn_apex_b200 import model
+    old = dict(model.PRECISION)
+    yield model.set_precision
+    model.PRECISION.update(old)
 
 
 def _cfg(g):
@@ -68,7 +82,7 @@ def test_learn_matches_reference_golden(cuda_dev, golden_dir, name):
             # CPU and the GPU moves the conv1/conv2 gradients by percents (iqn_small step 1 has exactly one such
             # element in conv2's output; everything downstream of it stays at 1e-7).  Trunk tolerances allow
             # for one flip; every other parameter is held to 1e-3.
-            gtol = 5e-2 if k.startswith(("conv1", "conv2")) else 1e-3
+            gtol = 5e-2 if k.startswith(("conv1", "conv2")) else _grad_tol()
             assert abs(gd[2] - ref[2]) <= gtol * ref[2] + 1e-9, (k, gd[:3], ref[:3])       # l2 norm
             assert np.allclose(gd[3:], ref[3:], rtol=2 * gtol, atol=2 * gtol * ref[2] / np.sqrt(p.numel()) + 1e-9), k
             pd, pref = digest(p), g[f"param_{s}_{k}"]
@@ -91,11 +105,15 @@ def _tie_mask(keep_oracle, a_star_gpu, tol=1e-5):
     return diff
 
 
+@pytest.mark.parametrize("mode", [("fp32", "fp32"), ("bf16x3", "bf16x3"), ("bf16x3", "bf16"), ("bf16", "bf16")])
 @pytest.mark.parametrize("batch,cfg", [(16, cases.iqn_cfg(64, 64, 32)), (5, cases.iqn_cfg(16, 24, 8, kappa=0.5))])
-def test_loss_api_and_autograd_vs_oracle(cuda_dev, batch, cfg):
+def test_loss_api_and_autograd_vs_oracle(cuda_dev, precision, batch, cfg, mode):
     """Agent.compute_loss_actor_or_learner + (weights*loss).mean().backward() + optimiser.step(), the exact
     call sequence of learner.py:18-24, against the oracle (autograd on CPU)."""
     from rainbow_iqn_apex_b200 import Agent
+    precision(*mode)
+    loss_tol = 1e-3 if mode[0] == "bf16" else LOSS_TOL      # bf16 operands: the north_star bound itself
+    act_tol = 2e-3 if mode[0] == "bf16" else 1e-4
     seed = 900 + batch
     params = net.make_params(seed)
     ag = Agent(make_args(cuda_dev, batch, cfg), 18, None)
@@ -120,12 +138,12 @@ def test_loss_api_and_autograd_vs_oracle(cuda_dev, batch, cfg):
     keep = {}
     o_loss, o_grads = losses.learn_step(p_on, p_tg, adam, cases.batch_to_torch(b), torch.from_numpy(b["weights"]),
                                         noises, taus, cfg, keep=keep)
-    ties = _tie_mask(keep, dbg["a_star"].cpu().numpy())
+    ties = _tie_mask(keep, dbg["a_star"].cpu().numpy(), tol=1e-3 if mode[0] == "bf16" else 1e-5)
     ok = ~ties
     lg, lo = loss.detach().cpu().numpy(), o_loss.numpy()
-    assert np.max(np.abs(lg[ok] - lo[ok]) / np.abs(lo[ok])) < LOSS_TOL
-    assert rel_err(dbg["theta"].cpu().numpy(), keep["theta"].detach().numpy()) < 1e-4
-    assert rel_err(dbg["target"].cpu().numpy()[ok], keep["target"].numpy()[ok]) < 1e-4
+    assert np.max(np.abs(lg[ok] - lo[ok]) / np.abs(lo[ok])) < loss_tol
+    assert rel_err(dbg["theta"].cpu().numpy(), keep["theta"].detach().numpy()) < act_tol
+    assert rel_err(dbg["target"].cpu().numpy()[ok], keep["target"].numpy()[ok]) < act_tol
     # ReLU-kink flips between the CPU and GPU activations (see the golden test) relax the gradient check
     gk = dbg["keep"]
     flips = sum(int(((a.cpu() > 0) != (b_ > 0)).sum()) for a, b_ in
@@ -137,9 +155,9 @@ def test_loss_api_and_autograd_vs_oracle(cuda_dev, batch, cfg):
             cos = float((gg * g_ref).sum() / (gg.norm() * g_ref.norm() + 1e-30))
             rel = float((gg - g_ref).norm() / (g_ref.norm() + 1e-30))
             if flips == 0:
-                assert cos > 0.999 and rel < 1e-3, (k, cos, rel)
+                assert cos > 0.999 and rel < (3e-2 if mode[0] == "bf16" else _grad_tol()), (k, cos, rel)   # SURVEY 8d gate: cos
                 assert np.allclose(dict(ag.online_net.named_parameters())[k].detach().cpu().numpy(),
-                                   p_on[k].detach().numpy(), rtol=0, atol=2e-7), k
+                                   p_on[k].detach().numpy(), rtol=0, atol=1e-6 if _grad_tol() < 5e-3 else 5e-6), k
             else:
                 assert cos > 0.99 and rel < 0.1, (k, cos, rel, flips)
 

@@ -72,16 +72,16 @@ def test_forward_injected(cuda_dev, nets):
     assert torch.equal(tau_out.cpu(), tau)
     assert rel_err(k2["cos"].cpu().numpy(), keep["cos"].numpy()) < 2e-6
     assert rel_err(k2["xt"].cpu().numpy(), keep["x"].numpy()) < 1e-5
-    assert rel_err(k2["h"][:, :512].cpu().numpy(), keep["h_v"].numpy()) < 1e-5
-    assert rel_err(k2["h"][:, 512:].cpu().numpy(), keep["h_a"].numpy()) < 1e-5
-    assert rel_err(q.cpu().numpy(), ref.numpy()) < 1e-5
+    assert rel_err(k2["h"][:, :512].cpu().numpy(), keep["h_v"].numpy()) < 5e-5   # split-bf16x3 tensor-core product
+    assert rel_err(k2["h"][:, 512:].cpu().numpy(), keep["h_a"].numpy()) < 5e-5
+    assert rel_err(q.cpu().numpy(), ref.numpy()) < 5e-5
     # stored epsilons == outer product of the injected factors (model.py:39-43), bit for bit
     assert torch.equal(d.fcnoisy_h_a.weight_epsilon.cpu(), torch.outer(noise["fcnoisy_h_a"][1], noise["fcnoisy_h_a"][0]))
     # eval mode uses mu only (model.py:52-53)
     d.eval()
     q_eval, _ = d.forward(torch.from_numpy(b["states"]).to(cuda_dev), Nq, tau=tau)
     ref_eval = net.dqn_forward_iqn(p, torch.from_numpy(b["states"]).float().div_(255), Nq, tau, training=False)
-    assert rel_err(q_eval.cpu().numpy(), ref_eval.numpy()) < 1e-5
+    assert rel_err(q_eval.cpu().numpy(), ref_eval.numpy()) < 5e-5
     d.train()
 
 
