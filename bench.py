@@ -151,7 +151,7 @@ def run_ours(args):
         step()
     barrier()
     timed_names = ("riqn_gemm_bf16_tc", "riqn_noisy_linear_fwd", "riqn_iqn_loss_fwd_bwd", "riqn_split_bf16",
-                   "riqn_quantile_embed_fwd", "riqn_quantile_embed_bwd", "riqn_conv_fwd", "riqn_conv_bwd",
+                   "riqn_quantile_embed_fwd_tc", "riqn_quantile_embed_bwd_tc", "riqn_conv_fwd_tc", "riqn_conv_bwd_tc",
                    "riqn_dueling_fwd", "riqn_dueling_bwd", "riqn_z_wgrad", "riqn_adam_step", "riqn_frame_gather",
                    "riqn_sumtree_sample", "riqn_sumtree_update", "riqn_noisy_compose")
     clocks = ClockSampler(local)

@@ -57,6 +57,20 @@ int riqn_conv_fwd(const riqn_conv_geom* g, const void* in, int in_is_u8, const f
 int riqn_conv_bwd(const riqn_conv_geom* g, const float* dout, const float* out, const float* col, const float* w,
                   float* dY, float* dcol, float* dw, float* dbias, float* din, void* stream);
 
+/* fp32 im2col alone: col (B*OH*OW, Cin*KH*KW), the workspace riqn_conv_bwd expects. */
+int riqn_im2col_f32(const riqn_conv_geom* g, const void* in, int in_is_u8, float* col, void* stream);
+
+/* Tensor-core variants (tcgen05 GEMM on bf16 im2col operands written straight from the uint8 / fp32 input).
+ * w_hi / w_lo: bf16 images of the (Cout, Cin*KH*KW) weight (riqn_split_bf16); col_lo == NULL selects the
+ * single-bf16 product, otherwise split-bf16 x3 (fp32-faithful).  col_hi/col_lo (M, K) bf16 workspaces; colT_hi
+ * (K, M), if non-NULL, is also written for riqn_conv_bwd_tc (needs B*OH*OW % 8 == 0). */
+int riqn_conv_fwd_tc(const riqn_conv_geom* g, const void* in, int in_is_u8, const void* w_hi, const void* w_lo,
+                     const float* bias, void* col_hi, void* col_lo, void* colT_hi, float* out, void* stream);
+/* Backward on the tensor cores (bf16 operands, fp32 accumulate): wT_hi (K, Cout) bf16; dY_hi (M, Cout) and dYT_hi
+ * (Cout, M) bf16 workspaces; dcol fp32 (M, K) workspace; dw/dbias accumulated; din may be NULL. */
+int riqn_conv_bwd_tc(const riqn_conv_geom* g, const float* dout, const float* out, const void* colT_hi, const void* wT_hi,
+                     void* dY_hi, void* dYT_hi, float* dcol, float* dw, float* dbias, float* din, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Randomness                       replaces torch normal_/uniform_ draws, model.py:32-37 and :131-134
  * ---------------------------------------------------------------------------------------------- */
@@ -108,6 +122,21 @@ int riqn_quantile_embed_fwd(int batch, int num_quantiles, int embed_dim, int fea
 int riqn_quantile_embed_bwd(int batch, int num_quantiles, int embed_dim, int feat_dim, const float* x,
                             const float* feat, const float* cosv, float* dx_inout, float* dfeat, float* grad_iqn_w,
                             float* grad_iqn_b, void* stream);
+
+/* Tensor-core variants.  Forward: the tcgen05 GEMM's epilogue applies relu / bias / the Hadamard with feat and writes
+ * the bf16 operand images of x directly: x_hi, x_lo (rows, feat_dim) for the NoisyLinear product, x_hi_t / x_lo_t
+ * (feat_dim, rows) for its weight gradient (each may be NULL); x32 (may be NULL) is the fp32 matrix.  cos_hi / cos_lo
+ * (rows, embed_dim) and cos_t_hi (embed_dim, rows; may be NULL) are outputs too.  cos_lo == NULL selects the
+ * single-bf16 product.  iqn_w_hi / iqn_w_lo: bf16 images of iqn_fc.weight (riqn_split_bf16). */
+int riqn_quantile_embed_fwd_tc(int batch, int num_quantiles, int embed_dim, int feat_dim, const float* tau,
+                               const float* feat, const void* iqn_w_hi, const void* iqn_w_lo, const float* iqn_b,
+                               void* cos_hi, void* cos_lo, void* cos_t_hi, float* x32, void* x_hi, void* x_lo, void* x_hi_t,
+                               void* x_lo_t, void* stream);
+/* Backward on bf16 operands (rows % 8 == 0): dx fp32 (rows, feat_dim) from the head dgrad; dpre_t (feat_dim, rows)
+ * bf16 workspace; dfeat overwritten; grad_iqn_w / grad_iqn_b accumulated. */
+int riqn_quantile_embed_bwd_tc(int batch, int num_quantiles, int embed_dim, int feat_dim, const void* x_hi, const void* x_lo,
+                               const float* feat, const void* cos_t_hi, const float* dx, void* dpre_t, float* dfeat,
+                               float* grad_iqn_w, float* grad_iqn_b, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * z-layers + dueling aggregation                          replaces rainbowiqn/model.py:153-156

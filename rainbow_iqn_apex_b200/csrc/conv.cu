@@ -95,6 +95,116 @@ int colsum_atomic(long M, int N, const float* X, float* out, cudaStream_t s) {
   return (int)cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Tensor-core path: im2col straight into bf16 (hi, lo) operands for gemm_tc.cu
+// ---------------------------------------------------------------------------------------------------------------
+using bf16 = __nv_bfloat16;
+
+template <typename T>
+__device__ __forceinline__ float im2col_at(const riqn_conv_geom& g, const T* __restrict__ in, long m, int k) {
+  const int kw = k % g.KW, kh = (k / g.KW) % g.KH, c = k / (g.KW * g.KH);
+  const int ow = (int)(m % g.OW), oh = (int)((m / g.OW) % g.OH);
+  const long b = m / ((long)g.OW * g.OH);
+  const int ih = oh * g.stride + kh - g.pad, iw = ow * g.stride + kw - g.pad;
+  if (ih < 0 || ih >= g.H || iw < 0 || iw >= g.W) return 0.f;
+  return load_px<T>(&in[b * g.in_bstride + ((long)c * g.H + ih) * g.W + iw]);
+}
+
+__device__ __forceinline__ void pack8(const float (&x)[8], uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int t = 0; t < 8; t += 2) {
+    const bf16 h0 = __float2bfloat16_rn(x[t]), h1 = __float2bfloat16_rn(x[t + 1]);
+    const bf16 l0 = __float2bfloat16_rn(x[t] - __bfloat162float(h0)), l1 = __float2bfloat16_rn(x[t + 1] - __bfloat162float(h1));
+    h[t / 2] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    l[t / 2] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// col (M, K): one thread = 8 consecutive k of one row m -> one 16-byte store per image.  (c, kh, kw) of the first
+// k is decoded once and then stepped without divisions.
+template <typename T>
+__global__ void im2col_bf16_kernel(riqn_conv_geom g, const T* __restrict__ in, bf16* __restrict__ hi, bf16* __restrict__ lo) {
+  const int K = g.Cin * g.KH * g.KW, K8 = K / 8;
+  const long total = (long)g.B * g.OH * g.OW * K8;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int k0 = (int)(idx % K8) * 8;
+    const long m = idx / K8;
+    const int ow = (int)(m % g.OW), oh = (int)((m / g.OW) % g.OH);
+    const long b = m / ((long)g.OW * g.OH);
+    int kw = k0 % g.KW, kh = (k0 / g.KW) % g.KH, c = k0 / (g.KW * g.KH);
+    const T* base = in + b * g.in_bstride;
+    const int ih0 = oh * g.stride - g.pad, iw0 = ow * g.stride - g.pad;
+    float x[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int ih = ih0 + kh, iw = iw0 + kw;
+      x[t] = (ih >= 0 && ih < g.H && iw >= 0 && iw < g.W) ? load_px<T>(&base[((long)c * g.H + ih) * g.W + iw]) : 0.f;
+      if (++kw == g.KW) { kw = 0; if (++kh == g.KH) { kh = 0; ++c; } }
+    }
+    uint4 h, l;
+    pack8(x, h, l);
+    *reinterpret_cast<uint4*>(hi + m * K + k0) = h;
+    if (lo) *reinterpret_cast<uint4*>(lo + m * K + k0) = l;
+  }
+}
+
+// colT (K, M): one thread = 8 consecutive m of one k  (M % 8 == 0)
+template <typename T>
+__global__ void im2col_bf16_t_kernel(riqn_conv_geom g, const T* __restrict__ in, bf16* __restrict__ hiT) {
+  const int K = g.Cin * g.KH * g.KW;
+  const long M = (long)g.B * g.OH * g.OW, M8 = M / 8;
+  const long total = M8 * K;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const long m0 = (idx % M8) * 8;
+    const int k = (int)(idx / M8);
+    const int kw = k % g.KW, kh = (k / g.KW) % g.KH, c = k / (g.KW * g.KH);
+    int ow = (int)(m0 % g.OW), oh = (int)((m0 / g.OW) % g.OH);
+    long b = m0 / ((long)g.OW * g.OH);
+    float x[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int ih = oh * g.stride + kh - g.pad, iw = ow * g.stride + kw - g.pad;
+      x[t] = (ih >= 0 && ih < g.H && iw >= 0 && iw < g.W)
+                 ? load_px<T>(&in[b * g.in_bstride + ((long)c * g.H + ih) * g.W + iw]) : 0.f;
+      if (++ow == g.OW) { ow = 0; if (++oh == g.OH) { oh = 0; ++b; } }
+    }
+    uint4 h, l;
+    pack8(x, h, l);
+    *reinterpret_cast<uint4*>(hiT + (long)k * M + m0) = h;
+  }
+}
+
+// dY = dout * (out > 0) from NCHW into the two bf16 operand layouts: dY (M, Cout) and dYT (Cout, M); the bias
+// gradient (sum over b, p) is reduced per channel on the way.
+__global__ void conv_dy_bf16_kernel(int B, int Cout, int ohw, const float* __restrict__ dout, const float* __restrict__ out,
+                                    bf16* __restrict__ dY, bf16* __restrict__ dYT, float* __restrict__ dbias) {
+  const int c = blockIdx.y;
+  const long M = (long)B * ohw;
+  float acc = 0.f;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (long)gridDim.x * blockDim.x) {
+    const long b = i / ohw;
+    const int p = (int)(i - b * ohw);
+    const long src = (b * Cout + c) * ohw + p;
+    const float v = out[src] > 0.f ? dout[src] : 0.f;
+    acc += v;
+    const bf16 h = __float2bfloat16_rn(v);
+    if (dY) dY[i * Cout + c] = h;
+    dYT[(long)c * M + i] = h;
+  }
+  acc = warp_sum(acc);
+  __shared__ float red[32];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) atomicAdd(&dbias[c], v);
+  }
+}
+
 static inline int grid_for(long total) {
   long b = (total + 255) / 256;
   return (int)(b > 148L * 32 ? 148L * 32 : (b < 1 ? 1 : b));
@@ -119,6 +229,16 @@ RIQN_API int riqn_conv_fwd(const riqn_conv_geom* g, const void* in, int in_is_u8
   return gemm_f32((int)M, g->Cout, K, col, K, 1, w, K, 1, out, g->Cout, EPI_BIAS_RELU_NCHW, e, 1, s);
 }
 
+RIQN_API int riqn_im2col_f32(const riqn_conv_geom* g, const void* in, int in_is_u8, float* col, void* stream) {
+  riqn::note_launches(1);
+  cudaStream_t s = (cudaStream_t)stream;
+  const long M = (long)g->B * g->OH * g->OW;
+  const int K = g->Cin * g->KH * g->KW;
+  if (in_is_u8) im2col_kernel<uint8_t><<<grid_for(M * K), 256, 0, s>>>(*g, (const uint8_t*)in, col);
+  else im2col_kernel<float><<<grid_for(M * K), 256, 0, s>>>(*g, (const float*)in, col);
+  return (int)cudaGetLastError();
+}
+
 RIQN_API int riqn_conv_bwd(const riqn_conv_geom* g, const float* dout, const float* out, const float* col,
                            const float* w, float* dY, float* dcol, float* dw, float* dbias, float* din, void* stream) {
   riqn::note_launches(din ? 5 : 3);
@@ -140,6 +260,60 @@ RIQN_API int riqn_conv_bwd(const riqn_conv_geom* g, const float* dout, const flo
   if (din) {
     // dcol[m, k] = sum_c dY[m, c] * W[c, k]
     rc = gemm_f32((int)M, K, g->Cout, dY, g->Cout, 1, w, 1, K, dcol, K, EPI_STORE, e, 1, s);
+    if (rc) return rc;
+    col2im_kernel<<<grid_for((long)g->B * g->Cin * g->H * g->W), 256, 0, s>>>(*g, dcol, din);
+    RIQN_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Tensor-core conv entry points (tcgen05 GEMM on bf16 hi/lo im2col operands)
+// ---------------------------------------------------------------------------------------------------------------
+RIQN_API int riqn_conv_fwd_tc(const riqn_conv_geom* g, const void* in, int in_is_u8, const void* w_hi, const void* w_lo,
+                              const float* bias, void* col_hi, void* col_lo, void* colT_hi, float* out, void* stream) {
+  riqn::note_launches(colT_hi ? 3 : 2);
+  cudaStream_t s = (cudaStream_t)stream;
+  const long M = (long)g->B * g->OH * g->OW;
+  const int K = g->Cin * g->KH * g->KW;
+  if (K % 8 || (colT_hi && M % 8)) return (int)cudaErrorInvalidValue;
+  if (in_is_u8) im2col_bf16_kernel<uint8_t><<<grid_for(M * K / 8), 256, 0, s>>>(*g, (const uint8_t*)in, (bf16*)col_hi, (bf16*)col_lo);
+  else im2col_bf16_kernel<float><<<grid_for(M * K / 8), 256, 0, s>>>(*g, (const float*)in, (bf16*)col_hi, (bf16*)col_lo);
+  RIQN_LAUNCH_CHECK();
+  if (colT_hi) {
+    if (in_is_u8) im2col_bf16_t_kernel<uint8_t><<<grid_for(M * K / 8), 256, 0, s>>>(*g, (const uint8_t*)in, (bf16*)colT_hi);
+    else im2col_bf16_t_kernel<float><<<grid_for(M * K / 8), 256, 0, s>>>(*g, (const float*)in, (bf16*)colT_hi);
+    RIQN_LAUNCH_CHECK();
+  }
+  TcExtra ex;
+  ex.ohw = g->OH * g->OW;
+  return gemm_bf16_tc((int)M, g->Cout, K, (const bf16*)col_hi, (const bf16*)col_lo, (const bf16*)w_hi,
+                      col_lo ? (const bf16*)w_lo : nullptr, out, g->Cout, TC_BIAS_RELU_NCHW, bias, nullptr, nullptr, 1, s, &ex);
+}
+
+RIQN_API int riqn_conv_bwd_tc(const riqn_conv_geom* g, const float* dout, const float* out, const void* colT_hi,
+                              const void* wT_hi, void* dY_hi, void* dYT_hi, float* dcol, float* dw, float* dbias, float* din,
+                              void* stream) {
+  riqn::note_launches(din ? 4 : 2);
+  cudaStream_t s = (cudaStream_t)stream;
+  const long M = (long)g->B * g->OH * g->OW;
+  const int K = g->Cin * g->KH * g->KW;
+  const int ohw = g->OH * g->OW;
+  if (M % 8 || g->Cout % 8) return (int)cudaErrorInvalidValue;
+  dim3 grid((unsigned)((M + 256 * 8 - 1) / (256 * 8)), g->Cout);
+  conv_dy_bf16_kernel<<<grid, 256, 0, s>>>(g->B, g->Cout, ohw, dout, out, din ? (bf16*)dY_hi : nullptr, (bf16*)dYT_hi, dbias);
+  RIQN_LAUNCH_CHECK();
+  // dW[c, k] += sum_m dY[m, c] * col[m, k]      (K' = M is long: split it over every SM)
+  const int n_tiles = (K + 255) / 256;
+  int split = (148 + n_tiles - 1) / n_tiles;
+  int rc = gemm_bf16_tc(g->Cout, K, (int)M, (const bf16*)dYT_hi, nullptr, (const bf16*)colT_hi, nullptr, dw, K, TC_ATOMIC,
+                        nullptr, nullptr, nullptr, split, s, nullptr);
+  if (rc) return rc;
+  if (din) {
+    // dcol[m, k] = sum_c dY[m, c] * W[c, k]
+    rc = gemm_bf16_tc((int)M, K, g->Cout, (const bf16*)dY_hi, nullptr, (const bf16*)wT_hi, nullptr, dcol, K, TC_STORE, nullptr,
+                      nullptr, nullptr, 1, s, nullptr);
     if (rc) return rc;
     col2im_kernel<<<grid_for((long)g->B * g->Cin * g->H * g->W), 256, 0, s>>>(*g, dcol, din);
     RIQN_LAUNCH_CHECK();

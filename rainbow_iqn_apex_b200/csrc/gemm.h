@@ -1,5 +1,6 @@
 // Internal GEMM interface shared by the op implementations (not part of the C-ABI).
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
 namespace riqn {
@@ -28,5 +29,22 @@ struct EpiArgs {
 // fp32 CUDA-core GEMM with arbitrary operand strides.  Returns a cudaError_t as int.
 int gemm_f32(int M, int N, int K, const float* A, long sAm, long sAk, const float* B, long sBn, long sBk,
              float* C, long ldc, int epi, const EpiArgs& e, int split_k, cudaStream_t stream);
+
+// ---- tcgen05 / TMA path (gemm_tc.cu) ---------------------------------------------------------------------------
+enum TcEpi { TC_STORE = 0, TC_BIAS_RELU = 1, TC_ATOMIC = 2, TC_NOISY_WGRAD = 3, TC_BIAS_RELU_NCHW = 4, TC_EMBED = 5 };
+
+struct TcExtra {
+  int ohw = 1;
+  const float* feat = nullptr;
+  int batch = 1;
+  __nv_bfloat16 *o_hi = nullptr, *o_lo = nullptr, *o_hiT = nullptr, *o_loT = nullptr;
+};
+
+// C (+)= A B^T, A (M,K) / B (N,K) row-major bf16 (K % 8 == 0); *_lo non-null selects the split-bf16 x3 product.
+int gemm_bf16_tc(int M, int N, int K, const __nv_bfloat16* A_hi, const __nv_bfloat16* A_lo, const __nv_bfloat16* B_hi,
+                 const __nv_bfloat16* B_lo, float* C, long ldc, int epi, const float* bias, float* out2, const float* eps,
+                 int split_k, cudaStream_t s, const TcExtra* ex);
+int split_bf16(long rows, int cols, const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, __nv_bfloat16* hiT,
+               __nv_bfloat16* loT, cudaStream_t s);
 
 }  // namespace riqn

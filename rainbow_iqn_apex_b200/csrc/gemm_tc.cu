@@ -31,6 +31,7 @@ constexpr int TBM = 128, TBN = 256, TBK = 64, UMMA_K = 16;
 constexpr int TC_THREADS = 192;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
 constexpr uint32_t TMEM_COLS = 512;
 
+
 template <int NSPLIT>
 struct TcCfg {
   static constexpr int kOps = NSPLIT == 1 ? 1 : 2;                                   // hi (+ lo) per operand
@@ -112,16 +113,19 @@ __device__ __forceinline__ uint32_t umma_idesc_bf16(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-enum TcEpi { TC_STORE = 0, TC_BIAS_RELU = 1, TC_ATOMIC = 2, TC_NOISY_WGRAD = 3 };
-
 struct TcArgs {
   int M, N, K;
   int m_tiles, n_tiles, k_splits, kb_per_split, kb_total;
   float* C;
   long ldc;
-  const float* bias;     // TC_BIAS_RELU
+  const float* bias;     // TC_BIAS_RELU / _NCHW / TC_EMBED
   float* out2;           // TC_NOISY_WGRAD: grad_sigma
   const float* eps;      // TC_NOISY_WGRAD: weight_epsilon (same layout as C)
+  int ohw;               // TC_BIAS_RELU_NCHW: m = b*ohw + p -> C[(b*N + n)*ohw + p]
+  const float* feat;     // TC_EMBED: (batch, N) conv features, row m uses feat[m % batch]
+  int batch;
+  bf16 *o_hi, *o_lo;     // TC_EMBED: bf16 hi / lo images of the result, row-major (M, N)   (may be null)
+  bf16 *o_hiT, *o_loT;   // TC_EMBED: transposed (N, M) images                              (may be null)
 };
 
 template <int NSPLIT, int EPI>
@@ -235,8 +239,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
         tmem_ld32(trow + c, v);
         const int n0 = nt * TBN + c;
         if (m < p.M && n0 < p.N) {
-          float* crow = p.C + (long)m * p.ldc + n0;
           if (EPI == TC_STORE || EPI == TC_BIAS_RELU) {
+            float* crow = p.C + (long)m * p.ldc + n0;
             if (n0 + 32 <= p.N) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
@@ -250,18 +254,71 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
                 *reinterpret_cast<float4*>(crow + j) = o;
               }
             } else {
-              for (int j = 0; j < 32 && n0 + j < p.N; ++j) {
-                float o = __uint_as_float(v[j]);
-                if (EPI == TC_BIAS_RELU) o = fmaxf(o + p.bias[n0 + j], 0.f);
-                crow[j] = o;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                if (n0 + j < p.N) {
+                  float o = __uint_as_float(v[j]);
+                  if (EPI == TC_BIAS_RELU) o = fmaxf(o + p.bias[n0 + j], 0.f);
+                  crow[j] = o;
+                }
               }
             }
+          } else if (EPI == TC_BIAS_RELU_NCHW) {
+            const int b = m / p.ohw, pp = m - b * p.ohw;
+            float* cb = p.C + ((long)b * p.N + n0) * p.ohw + pp;   // lanes = consecutive pp: coalesced per n
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < p.N) cb[(long)j * p.ohw] = fmaxf(__uint_as_float(v[j]) + p.bias[n0 + j], 0.f);
+          } else if (EPI == TC_EMBED) {
+            // x = feat[b] * relu(acc + bias)   (model.py:146-151); N % 32 == 0 is required by the host wrapper
+            const float* fr = p.feat + (long)(m % p.batch) * p.N + n0;
+            const long o = (long)m * p.N + n0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              float x[8];
+              uint32_t ph[4], pl[4];
+              {
+                const float4 f0 = __ldg(reinterpret_cast<const float4*>(fr + j));
+                const float4 f1 = __ldg(reinterpret_cast<const float4*>(fr + j + 4));
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j + 4));
+                const float ff[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                for (int t = 0; t < 8; ++t) x[t] = ff[t] * fmaxf(__uint_as_float(v[j + t]) + bb[t], 0.f);
+              }
+#pragma unroll
+              for (int t = 0; t < 8; t += 2) {
+                const bf16 h0 = __float2bfloat16_rn(x[t]), h1 = __float2bfloat16_rn(x[t + 1]);
+                const bf16 l0 = __float2bfloat16_rn(x[t] - __bfloat162float(h0));
+                const bf16 l1 = __float2bfloat16_rn(x[t + 1] - __bfloat162float(h1));
+                ph[t / 2] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                pl[t / 2] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                if (p.o_hiT) { p.o_hiT[(long)(n0 + j + t) * p.M + m] = h0; p.o_hiT[(long)(n0 + j + t + 1) * p.M + m] = h1; }
+                if (p.o_loT) { p.o_loT[(long)(n0 + j + t) * p.M + m] = l0; p.o_loT[(long)(n0 + j + t + 1) * p.M + m] = l1; }
+              }
+              if (p.C) {
+                *reinterpret_cast<float4*>(p.C + o + j) = make_float4(x[0], x[1], x[2], x[3]);
+                *reinterpret_cast<float4*>(p.C + o + j + 4) = make_float4(x[4], x[5], x[6], x[7]);
+              }
+              if (p.o_hi) *reinterpret_cast<uint4*>(p.o_hi + o + j) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+              if (p.o_lo) *reinterpret_cast<uint4*>(p.o_lo + o + j) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+            }
           } else {
-            for (int j = 0; j < 32 && n0 + j < p.N; ++j) {
-              const float o = __uint_as_float(v[j]);
-              atomicAdd(crow + j, o);
-              if (EPI == TC_NOISY_WGRAD)
-                atomicAdd(p.out2 + (long)m * p.ldc + n0 + j, o * p.eps[(long)m * p.ldc + n0 + j]);
+            float* crow = p.C + (long)m * p.ldc + n0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (n0 + j < p.N) {
+                const float o = __uint_as_float(v[j]);
+                if (p.k_splits == 1) {   // sole contributor: += without atomics
+                  crow[j] += o;
+                  if (EPI == TC_NOISY_WGRAD) p.out2[(long)m * p.ldc + n0 + j] += o * p.eps[(long)m * p.ldc + n0 + j];
+                } else {
+                  atomicAdd(crow + j, o);
+                  if (EPI == TC_NOISY_WGRAD)
+                    atomicAdd(p.out2 + (long)m * p.ldc + n0 + j, o * p.eps[(long)m * p.ldc + n0 + j]);
+                }
+              }
             }
           }
         }
@@ -331,7 +388,8 @@ static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUt
 
 // C (+)= A * B^T on the tensor cores.  A (M,K), B (N,K) bf16 row-major (K % 8 == 0); *_lo may be null (NSPLIT 1).
 int gemm_bf16_tc(int M, int N, int K, const bf16* A_hi, const bf16* A_lo, const bf16* B_hi, const bf16* B_lo, float* C,
-                 long ldc, int epi, const float* bias, float* out2, const float* eps, int split_k, cudaStream_t s) {
+                 long ldc, int epi, const float* bias, float* out2, const float* eps, int split_k, cudaStream_t s,
+                 const TcExtra* ex) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if (K % 8) return (int)cudaErrorInvalidValue;
   const bool split3 = A_lo != nullptr && B_lo != nullptr;
@@ -360,6 +418,10 @@ int gemm_bf16_tc(int M, int N, int K, const bf16* A_hi, const bf16* A_lo, const 
   p.k_splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
   if (p.k_splits > 1 && epi != TC_ATOMIC && epi != TC_NOISY_WGRAD) return (int)cudaErrorInvalidValue;
   p.C = C; p.ldc = ldc; p.bias = bias; p.out2 = out2; p.eps = eps;
+  p.ohw = ex ? ex->ohw : 1; p.feat = ex ? ex->feat : nullptr; p.batch = ex ? ex->batch : 1;
+  p.o_hi = ex ? ex->o_hi : nullptr; p.o_lo = ex ? ex->o_lo : nullptr;
+  p.o_hiT = ex ? ex->o_hiT : nullptr; p.o_loT = ex ? ex->o_loT : nullptr;
+  if (epi == TC_EMBED && (N % 32)) return (int)cudaErrorInvalidValue;
 #define RIQN_TC_GO(NS, EP) return launch_tc<NS, EP>(ma_hi, ma_lo, mb_hi, mb_lo, p, s)
   if (split3) {
     switch (epi) {
@@ -367,6 +429,8 @@ int gemm_bf16_tc(int M, int N, int K, const bf16* A_hi, const bf16* A_lo, const 
       case TC_BIAS_RELU: RIQN_TC_GO(3, TC_BIAS_RELU);
       case TC_ATOMIC: RIQN_TC_GO(3, TC_ATOMIC);
       case TC_NOISY_WGRAD: RIQN_TC_GO(3, TC_NOISY_WGRAD);
+      case TC_BIAS_RELU_NCHW: RIQN_TC_GO(3, TC_BIAS_RELU_NCHW);
+      case TC_EMBED: RIQN_TC_GO(3, TC_EMBED);
     }
   } else {
     switch (epi) {
@@ -374,6 +438,8 @@ int gemm_bf16_tc(int M, int N, int K, const bf16* A_hi, const bf16* A_lo, const 
       case TC_BIAS_RELU: RIQN_TC_GO(1, TC_BIAS_RELU);
       case TC_ATOMIC: RIQN_TC_GO(1, TC_ATOMIC);
       case TC_NOISY_WGRAD: RIQN_TC_GO(1, TC_NOISY_WGRAD);
+      case TC_BIAS_RELU_NCHW: RIQN_TC_GO(1, TC_BIAS_RELU_NCHW);
+      case TC_EMBED: RIQN_TC_GO(1, TC_EMBED);
     }
   }
 #undef RIQN_TC_GO
@@ -435,5 +501,5 @@ RIQN_API int riqn_gemm_bf16_tc(int M, int N, int K, const void* a_hi, const void
                                int split_k, void* stream) {
   riqn::note_launches(1);
   return gemm_bf16_tc(M, N, K, (const bf16*)a_hi, (const bf16*)a_lo, (const bf16*)b_hi, (const bf16*)b_lo, c, ldc, epilogue,
-                      bias, out2, eps, split_k, (cudaStream_t)stream);
+                      bias, out2, eps, split_k, (cudaStream_t)stream, nullptr);
 }

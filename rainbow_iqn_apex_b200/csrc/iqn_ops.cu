@@ -47,6 +47,81 @@ __global__ void cos_embed_kernel(long R, int E, const float* __restrict__ tau, f
   cosv[idx] = cosf(__fmul_rn(ipi, tau[idx / E]));
 }
 
+// Same values as bf16 (hi, lo) operand images for the tensor-core embedding product, plus the transposed hi image
+// (E, R) the iqn_fc weight-gradient product consumes.
+__global__ void cos_embed_bf16_kernel(long R, int E, const float* __restrict__ tau, __nv_bfloat16* __restrict__ hi,
+                                      __nv_bfloat16* __restrict__ lo, __nv_bfloat16* __restrict__ hiT) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= R * E) return;
+  const int i = (int)(idx % E) + 1;
+  const long r = idx / E;
+  const float ipi = __fmul_rn((float)i, 3.14159274101257324f);
+  const float c = cosf(__fmul_rn(ipi, tau[r]));
+  const __nv_bfloat16 h = __float2bfloat16_rn(c);
+  hi[idx] = h;
+  if (lo) lo[idx] = __float2bfloat16_rn(c - __bfloat162float(h));
+  if (hiT) hiT[(long)(i - 1) * R + r] = h;
+}
+
+// Backward through x = feat[b] (.) phi[r] on bf16 operand images, tile-transposing on the way:
+//   x = x_hi (+ x_lo);  dpre = dX * feat * 1{x>0}  -> dpreT (F, R) bf16 (K-major operand of the dW_e product)
+//   dfeat[b,f] = (sum_q dX * x) / feat ;  dbe[f] += sum_r dpre
+// Block = 32 features x 32 samples, looping over the Nq quantile rows of those samples.
+__global__ void embed_bwd_tile_kernel(int B, int Nq, int F, const __nv_bfloat16* __restrict__ x_hi,
+                                      const __nv_bfloat16* __restrict__ x_lo, const float* __restrict__ feat,
+                                      const float* __restrict__ dX, __nv_bfloat16* __restrict__ dpreT,
+                                      float* __restrict__ dfeat, float* __restrict__ dbe) {
+  __shared__ float tile[32][33];
+  __shared__ float red[8][32];
+  const int f0 = blockIdx.x * 32, b0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  const long R = (long)B * Nq;
+  float facc[4] = {0.f, 0.f, 0.f, 0.f}, ft[4];
+  float bacc = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int b = b0 + ty + 8 * i, f = f0 + tx;
+    ft[i] = (b < B && f < F) ? feat[(long)b * F + f] : 0.f;
+  }
+  for (int q = 0; q < Nq; ++q) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int b = b0 + ty + 8 * i, f = f0 + tx;
+      float dp = 0.f;
+      if (b < B && f < F) {
+        const long o = ((long)q * B + b) * F + f;
+        float x = __bfloat162float(x_hi[o]);
+        if (x_lo) x += __bfloat162float(x_lo[o]);
+        const float dx = dX[o];
+        facc[i] = fmaf(dx, x, facc[i]);
+        dp = x > 0.f ? dx * ft[i] : 0.f;
+        bacc += dp;
+      }
+      tile[ty + 8 * i][tx] = dp;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int f = f0 + ty + 8 * i, b = b0 + tx;
+      if (f < F && b < B) dpreT[(long)f * R + (long)q * B + b] = __float2bfloat16_rn(tile[tx][ty + 8 * i]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int b = b0 + ty + 8 * i, f = f0 + tx;
+    if (b < B && f < F) dfeat[(long)b * F + f] = ft[i] > 0.f ? facc[i] / ft[i] : 0.f;
+  }
+  red[ty][tx] = bacc;
+  __syncthreads();
+  if (ty == 0) {
+    float v = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v += red[j][tx];
+    if (f0 + tx < F) atomicAdd(&dbe[f0 + tx], v);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // NoisyLinear: (optional) eps_w = eps_out (x) eps_in, then W_eff = mu + sigma*eps_w, b_eff likewise
 // (model.py:39-53).  training == 0 gives the eval-mode weights (mu only).
@@ -354,6 +429,51 @@ RIQN_API int riqn_quantile_embed_fwd(int batch, int num_quantiles, int embed_dim
   e.feat = feat;
   e.batch = batch;
   return gemm_f32((int)R, feat_dim, embed_dim, cosv, embed_dim, 1, iqn_w, embed_dim, 1, x, feat_dim, EPI_EMBED, e, 1, s);
+}
+
+// Tensor-core embedding: cos -> bf16 (hi, lo); x = feat (.) relu(cos W_e^T + b_e) computed by the tcgen05 GEMM whose
+// epilogue writes the bf16 operand images of x directly (x_hi/x_lo row-major for the head product, x_hiT/x_loT
+// transposed for its weight gradient) and, only if x32 != NULL, the fp32 matrix.
+RIQN_API int riqn_quantile_embed_fwd_tc(int batch, int num_quantiles, int embed_dim, int feat_dim, const float* tau,
+                                        const float* feat, const void* iqn_w_hi, const void* iqn_w_lo, const float* iqn_b,
+                                        void* cos_hi, void* cos_lo, void* cosT_hi, float* x32, void* x_hi, void* x_lo,
+                                        void* x_hiT, void* x_loT, void* stream) {
+  riqn::note_launches(2);
+  cudaStream_t s = (cudaStream_t)stream;
+  const long R = (long)batch * num_quantiles;
+  cos_embed_bf16_kernel<<<riqn_cdiv(R * embed_dim, 256), 256, 0, s>>>(R, embed_dim, tau, (__nv_bfloat16*)cos_hi,
+                                                                     (__nv_bfloat16*)cos_lo, (__nv_bfloat16*)cosT_hi);
+  RIQN_LAUNCH_CHECK();
+  TcExtra ex;
+  ex.feat = feat;
+  ex.batch = batch;
+  ex.o_hi = (__nv_bfloat16*)x_hi;
+  ex.o_lo = (__nv_bfloat16*)x_lo;
+  ex.o_hiT = (__nv_bfloat16*)x_hiT;
+  ex.o_loT = (__nv_bfloat16*)x_loT;
+  return gemm_bf16_tc((int)R, feat_dim, embed_dim, (const __nv_bfloat16*)cos_hi, (const __nv_bfloat16*)cos_lo,
+                      (const __nv_bfloat16*)iqn_w_hi, cos_lo ? (const __nv_bfloat16*)iqn_w_lo : nullptr, x32, feat_dim,
+                      TC_EMBED, iqn_b, nullptr, nullptr, 1, s, &ex);
+}
+
+// Backward on bf16 operands: dx (fp32, from the head dgrad) -> dfeat (overwritten), grad_iqn_b / grad_iqn_w accumulated.
+// dpreT (feat_dim, rows) bf16 is workspace.  rows % 8 == 0.
+RIQN_API int riqn_quantile_embed_bwd_tc(int batch, int num_quantiles, int embed_dim, int feat_dim, const void* x_hi,
+                                        const void* x_lo, const float* feat, const void* cosT_hi, const float* dx,
+                                        void* dpreT, float* dfeat, float* grad_iqn_w, float* grad_iqn_b, void* stream) {
+  riqn::note_launches(2);
+  cudaStream_t s = (cudaStream_t)stream;
+  const long R = (long)batch * num_quantiles;
+  if (R % 8) return (int)cudaErrorInvalidValue;
+  dim3 grid((feat_dim + 31) / 32, (batch + 31) / 32);
+  embed_bwd_tile_kernel<<<grid, 256, 0, s>>>(batch, num_quantiles, feat_dim, (const __nv_bfloat16*)x_hi,
+                                             (const __nv_bfloat16*)x_lo, feat, dx, (__nv_bfloat16*)dpreT, dfeat, grad_iqn_b);
+  RIQN_LAUNCH_CHECK();
+  const int m_tiles = (feat_dim + 127) / 128;
+  const int split = (148 + m_tiles - 1) / m_tiles;
+  // dWe[f, i] += sum_r dpre[r, f] * cos[r, i]
+  return gemm_bf16_tc(feat_dim, embed_dim, (int)R, (const __nv_bfloat16*)dpreT, nullptr, (const __nv_bfloat16*)cosT_hi, nullptr,
+                      grad_iqn_w, embed_dim, TC_ATOMIC, nullptr, nullptr, nullptr, split, s, nullptr);
 }
 
 RIQN_API int riqn_quantile_embed_bwd(int batch, int num_quantiles, int embed_dim, int feat_dim, const float* x,

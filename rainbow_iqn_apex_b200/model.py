@@ -33,7 +33,7 @@ _ALIGN = 64  # floats; arena groups start on 256-byte boundaries
 #   "bf16"  : tcgen05 tensor cores, operands rounded to bf16 once, fp32 accumulation in TMEM
 #   "fp32"  : CUDA-core fp32 GEMM (gemm_simt.cu), the cross-check path
 PRECISION = {"fwd": os.environ.get("RIQN_FWD_PRECISION", "bf16x3"), "bwd": os.environ.get("RIQN_BWD_PRECISION", "bf16")}
-WGRAD_SPLIT_K = int(os.environ.get("RIQN_WGRAD_SPLIT_K", "6"))
+WGRAD_SPLIT_K = int(os.environ.get("RIQN_WGRAD_SPLIT_K", "1"))
 
 
 def set_precision(fwd=None, bwd=None):
@@ -279,7 +279,7 @@ class DQN(nn.Module):
     def _refresh_tc_operands(self):
         """bf16 (hi, lo) images of the composed hidden-layer weights for the tcgen05 path: (2*hid, 3136) K-major for
         the forward product and the transposed (3136, 2*hid) copy the data-gradient product consumes."""
-        if self.rainbow_only or (PRECISION["fwd"] == "fp32" and PRECISION["bwd"] == "fp32") or not self._flat.is_cuda:
+        if (PRECISION["fwd"] == "fp32" and PRECISION["bwd"] == "fp32") or not self._flat.is_cuda:
             return
         dev = self._flat.device
         if getattr(self, "_w_hi", None) is None or self._w_hi.device != dev:
@@ -287,8 +287,20 @@ class DQN(nn.Module):
             mk = lambda *sh: torch.empty(*sh, dtype=torch.bfloat16, device=dev)
             self._w_hi, self._w_lo = mk(n, FEAT), mk(n, FEAT)
             self._w_hiT, self._w_loT = mk(FEAT, n), mk(FEAT, n)
+            self._conv_ops = {}
+            for name, conv in (("conv1", self.conv1), ("conv2", self.conv2), ("conv3", self.conv3)):
+                co, k = conv.weight.shape[0], conv.weight[0].numel()
+                self._conv_ops[name] = (mk(co, k), mk(co, k), mk(k, co))
+            if not self.rainbow_only:
+                self._iqn_ops = (mk(FEAT, self.quantile_embedding_dim), mk(FEAT, self.quantile_embedding_dim))
         call("riqn_split_bf16", 2 * self.hidden, FEAT, ptr(self._w_eff_h), ptr(self._w_hi), ptr(self._w_lo),
              ptr(self._w_hiT), ptr(self._w_loT))
+        for name, conv in (("conv1", self.conv1), ("conv2", self.conv2), ("conv3", self.conv3)):
+            hi, lo, hiT = self._conv_ops[name]
+            call("riqn_split_bf16", hi.shape[0], hi.shape[1], ptr(conv.weight), ptr(hi), ptr(lo), ptr(hiT), None)
+        if not self.rainbow_only:
+            call("riqn_split_bf16", FEAT, self.quantile_embedding_dim, ptr(self.iqn_fc.weight), ptr(self._iqn_ops[0]),
+                 ptr(self._iqn_ops[1]), None, None)
 
     def draw_quantiles(self, n):
         tau = torch.empty(n, 1, device=self._flat.device)
@@ -311,18 +323,35 @@ class DQN(nn.Module):
         g1 = _geom(B, self.history, 84, 32, 8, 4, 1, in_bstride=x.stride(0))
         g2 = _geom(B, 32, 20, 64, 4, 2, 0)
         g3 = _geom(B, 64, 9, 64, 3, 1, 0)
-        col1 = torch.empty(B * 400, self.history * 64, device=dev)
-        out1 = torch.empty(B, 32, 20, 20, device=dev)
-        call("riqn_conv_fwd", g1, ptr(x), is_u8, ptr(self.conv1.weight), ptr(self.conv1.bias), ptr(col1), ptr(out1))
-        col2 = torch.empty(B * 81, 512, device=dev)
-        out2 = torch.empty(B, 64, 9, 9, device=dev)
-        call("riqn_conv_fwd", g2, ptr(out1), 0, ptr(self.conv2.weight), ptr(self.conv2.bias), ptr(col2), ptr(out2))
-        col3 = torch.empty(B * 49, 576, device=dev)
-        out3 = torch.empty(B, 64, 7, 7, device=dev)
-        call("riqn_conv_fwd", g3, ptr(out2), 0, ptr(self.conv3.weight), ptr(self.conv3.bias), ptr(col3), ptr(out3))
+        geoms, convs = (g1, g2, g3), (self.conv1, self.conv2, self.conv3)
+        outs = (torch.empty(B, 32, 20, 20, device=dev), torch.empty(B, 64, 9, 9, device=dev),
+                torch.empty(B, 64, 7, 7, device=dev))
+        ins = (x, outs[0], outs[1])
+        fwd = PRECISION["fwd"]
+        # the backward runs on the tensor cores when it is bf16 and every im2col row count is a multiple of 8
+        bwd_tc = keep is not None and PRECISION["bwd"] == "bf16" and fwd != "fp32" and all((g.B * g.OH * g.OW) % 8 == 0 for g in geoms)
+        need_col32 = keep is not None and not bwd_tc
+        cols, colTs = [None] * 3, [None] * 3
+        for i, (g, conv, inp, out) in enumerate(zip(geoms, convs, ins, outs)):
+            M, K = g.B * g.OH * g.OW, g.Cin * g.KH * g.KW
+            u8 = is_u8 if i == 0 else 0
+            if fwd == "fp32":
+                cols[i] = torch.empty(M, K, device=dev)
+                call("riqn_conv_fwd", g, ptr(inp), u8, ptr(conv.weight), ptr(conv.bias), ptr(cols[i]), ptr(out))
+            else:
+                w_hi, w_lo, _ = self._conv_ops["conv%d" % (i + 1)]
+                col_hi = torch.empty(M, K, dtype=torch.bfloat16, device=dev)
+                col_lo = torch.empty(M, K, dtype=torch.bfloat16, device=dev) if fwd == "bf16x3" else None
+                if bwd_tc:
+                    colTs[i] = torch.empty(K, M, dtype=torch.bfloat16, device=dev)
+                call("riqn_conv_fwd_tc", g, ptr(inp), u8, ptr(w_hi), ptr(w_lo), ptr(conv.bias), ptr(col_hi), ptr(col_lo),
+                     ptr(colTs[i]), ptr(out))
+                if need_col32:
+                    cols[i] = torch.empty(M, K, device=dev)
+                    call("riqn_im2col_f32", g, ptr(inp), u8, ptr(cols[i]))
         if keep is not None:
-            keep.update(x=x, g=(g1, g2, g3), col=(col1, col2, col3), out=(out1, out2, out3))
-        return out3.view(B, FEAT)
+            keep.update(x=x, g=geoms, col=tuple(cols), colT=tuple(colTs), out=outs, bwd_tc=bwd_tc)
+        return outs[2].view(B, FEAT)
 
     def iqn_head(self, feat, num_quantiles, tau, keep=None):
         """Quantile embedding, Hadamard, noisy hidden layers, z-layers, dueling.  model.py:131-157"""
@@ -330,30 +359,43 @@ class DQN(nn.Module):
         R = B * num_quantiles
         dev = feat.device
         E, hid, A = self.quantile_embedding_dim, self.hidden, self.action_space
-        cosv = torch.empty(R, E, device=dev)
-        xt = torch.empty(R, FEAT, device=dev)
-        call("riqn_quantile_embed_fwd", B, num_quantiles, E, FEAT, ptr(tau), ptr(feat), ptr(self.iqn_fc.weight),
-             ptr(self.iqn_fc.bias), ptr(cosv), ptr(xt))
+        fwd, bwd = PRECISION["fwd"], PRECISION["bwd"]
+        bf = lambda *sh: torch.empty(*sh, dtype=torch.bfloat16, device=dev)
         h = torch.empty(R, 2 * hid, device=dev)
-        fwd = PRECISION["fwd"]
-        want_t = keep is not None and PRECISION["bwd"] != "fp32" and R % 8 == 0
-        tc = None
-        if fwd != "fp32" or want_t:
-            bf = lambda *sh: torch.empty(*sh, dtype=torch.bfloat16, device=dev)
-            x3 = fwd == "bf16x3"
-            t3 = want_t and PRECISION["bwd"] == "bf16x3"
-            tc = dict(x_hi=bf(R, FEAT) if fwd != "fp32" else None, x_lo=bf(R, FEAT) if x3 else None,
-                      x_hiT=bf(FEAT, R) if want_t else None, x_loT=bf(FEAT, R) if t3 else None)
-            call("riqn_split_bf16", R, FEAT, ptr(xt), ptr(tc["x_hi"]), ptr(tc["x_lo"]), ptr(tc["x_hiT"]), ptr(tc["x_loT"]))
+        bwd_tc = keep is not None and bwd != "fp32" and R % 8 == 0      # head wgrad/dgrad on the tensor cores
+        emb_tc = keep is not None and bwd == "bf16" and fwd != "fp32" and R % 8 == 0   # embedding backward on tensor cores
+        cosv = xt = tc = None
         if fwd == "fp32":
+            cosv = torch.empty(R, E, device=dev)
+            xt = torch.empty(R, FEAT, device=dev)
+            call("riqn_quantile_embed_fwd", B, num_quantiles, E, FEAT, ptr(tau), ptr(feat), ptr(self.iqn_fc.weight),
+                 ptr(self.iqn_fc.bias), ptr(cosv), ptr(xt))
+            if bwd_tc:
+                tc = dict(x_hi=None, x_lo=None, x_hiT=bf(FEAT, R), x_loT=bf(FEAT, R) if bwd == "bf16x3" else None)
+                call("riqn_split_bf16", R, FEAT, ptr(xt), None, None, ptr(tc["x_hiT"]), ptr(tc["x_loT"]))
             call("riqn_noisy_linear_fwd", R, FEAT, 2 * hid, ptr(xt), ptr(self._w_eff_h), ptr(self._b_eff_h), ptr(h))
         else:
+            x3 = fwd == "bf16x3"
+            need_x32 = keep is not None and not emb_tc           # the fp32 CUDA-core embedding backward reads x
+            tc = dict(x_hi=bf(R, FEAT), x_lo=bf(R, FEAT) if x3 else None,
+                      x_hiT=bf(FEAT, R) if bwd_tc else None, x_loT=bf(FEAT, R) if (bwd_tc and bwd == "bf16x3") else None,
+                      cos_hi=bf(R, E), cos_lo=bf(R, E) if x3 else None, cosT_hi=bf(E, R) if emb_tc else None)
+            if need_x32:
+                xt = torch.empty(R, FEAT, device=dev)
+                cosv = torch.empty(R, E, device=dev)
+            call("riqn_quantile_embed_fwd_tc", B, num_quantiles, E, FEAT, ptr(tau), ptr(feat), ptr(self._iqn_ops[0]),
+                 ptr(self._iqn_ops[1]), ptr(self.iqn_fc.bias), ptr(tc["cos_hi"]), ptr(tc["cos_lo"]), ptr(tc["cosT_hi"]),
+                 ptr(xt), ptr(tc["x_hi"]), ptr(tc["x_lo"]), ptr(tc["x_hiT"]), ptr(tc["x_loT"]))
+            if need_x32:   # fp32 cos for the CUDA-core dW_e product
+                call("riqn_quantile_embed_fwd", B, num_quantiles, E, FEAT, ptr(tau), ptr(feat), ptr(self.iqn_fc.weight),
+                     ptr(self.iqn_fc.bias), ptr(cosv), ptr(xt))
             call("riqn_gemm_bf16_tc", R, 2 * hid, FEAT, ptr(tc["x_hi"]), ptr(tc["x_lo"]), ptr(self._w_hi),
-                 ptr(self._w_lo) if fwd == "bf16x3" else None, ptr(h), 2 * hid, 1, ptr(self._b_eff_h), None, None, 1)
+                 ptr(self._w_lo) if x3 else None, ptr(h), 2 * hid, 1, ptr(self._b_eff_h), None, None, 1)
         q = torch.empty(R, A, device=dev)
         call("riqn_dueling_fwd", R, hid, A, ptr(h), ptr(self._w_eff_z), ptr(self._b_eff_z), ptr(q))
         if keep is not None:
-            keep.update(feat=feat, cos=cosv, xt=xt, h=h, q=q, tau=tau, num_quantiles=num_quantiles, tc=tc)
+            keep.update(feat=feat, cos=cosv, xt=xt, h=h, q=q, tau=tau, num_quantiles=num_quantiles, tc=tc,
+                        head_bwd_tc=bwd_tc, emb_bwd_tc=emb_tc)
         return q
 
     def forward(self, x, num_quantiles=None, log=False, tau=None, keep=None, fresh_weights=False):
@@ -397,7 +439,7 @@ class DQN(nn.Module):
         bwd = PRECISION["bwd"]
         tc = keep.get("tc")
         # [h_v | h_a] are adjacent in every arena, so one (2*hid, 3136) product serves both layers
-        if bwd == "fp32" or tc is None or tc["x_hiT"] is None:
+        if not keep["head_bwd_tc"]:
             call("riqn_noisy_linear_wgrad", R, FEAT, 2 * hid, ptr(dh), ptr(keep["xt"]), ptr(hv.weight_epsilon),
                  ptr(hv.bias_epsilon), ptr(dbs), ptr(gv(hv.weight_mu)), ptr(gv(hv.weight_sigma)), ptr(gv(hv.bias_mu)),
                  ptr(gv(hv.bias_sigma)))
@@ -418,25 +460,36 @@ class DQN(nn.Module):
             call("riqn_gemm_bf16_tc", R, FEAT, 2 * hid, ptr(dh_hi), ptr(dh_lo), ptr(self._w_hiT),
                  ptr(self._w_loT) if b3 else None, ptr(dx), FEAT, 0, None, None, None, 1)
         dfeat = torch.empty(B, FEAT, device=dev)
-        call("riqn_quantile_embed_bwd", B, Nq, E, FEAT, ptr(keep["xt"]), ptr(keep["feat"]), ptr(keep["cos"]), ptr(dx),
-             ptr(dfeat), ptr(gv(self.iqn_fc.weight)), ptr(gv(self.iqn_fc.bias)))
+        if keep["emb_bwd_tc"]:
+            dpreT = torch.empty(FEAT, R, dtype=torch.bfloat16, device=dev)
+            call("riqn_quantile_embed_bwd_tc", B, Nq, E, FEAT, ptr(tc["x_hi"]), ptr(tc["x_lo"]), ptr(keep["feat"]),
+                 ptr(tc["cosT_hi"]), ptr(dx), ptr(dpreT), ptr(dfeat), ptr(gv(self.iqn_fc.weight)), ptr(gv(self.iqn_fc.bias)))
+        else:
+            call("riqn_quantile_embed_bwd", B, Nq, E, FEAT, ptr(keep["xt"]), ptr(keep["feat"]), ptr(keep["cos"]), ptr(dx),
+                 ptr(dfeat), ptr(gv(self.iqn_fc.weight)), ptr(gv(self.iqn_fc.bias)))
         self.backward_trunk(keep, dfeat)
 
     def backward_trunk(self, keep, dfeat):
-        (g1, g2, g3), (col1, col2, col3), (out1, out2, out3) = keep["g"], keep["col"], keep["out"]
+        (g1, g2, g3), (out1, out2, out3) = keep["g"], keep["out"]
         dev = dfeat.device
         gv = self.grad_view
-        B = out1.shape[0]
-        d_out2 = torch.empty_like(out2)
-        dY3 = torch.empty(B * 49, 64, device=dev)
-        dcol3 = torch.empty_like(col3)
-        call("riqn_conv_bwd", g3, ptr(dfeat), ptr(out3), ptr(col3), ptr(self.conv3.weight), ptr(dY3), ptr(dcol3),
-             ptr(gv(self.conv3.weight)), ptr(gv(self.conv3.bias)), ptr(d_out2))
-        d_out1 = torch.empty_like(out1)
-        dY2 = torch.empty(B * 81, 64, device=dev)
-        dcol2 = torch.empty_like(col2)
-        call("riqn_conv_bwd", g2, ptr(d_out2), ptr(out2), ptr(col2), ptr(self.conv2.weight), ptr(dY2), ptr(dcol2),
-             ptr(gv(self.conv2.weight)), ptr(gv(self.conv2.bias)), ptr(d_out1))
-        dY1 = torch.empty(B * 400, 32, device=dev)
-        call("riqn_conv_bwd", g1, ptr(d_out1), ptr(out1), ptr(col1), ptr(self.conv1.weight), ptr(dY1), None,
-             ptr(gv(self.conv1.weight)), ptr(gv(self.conv1.bias)), None)
+        convs = (self.conv1, self.conv2, self.conv3)
+        douts = [None, None, dfeat]
+        for i in (2, 1, 0):
+            g, conv, out = keep["g"][i], convs[i], keep["out"][i]
+            M, K = g.B * g.OH * g.OW, g.Cin * g.KH * g.KW
+            din = torch.empty_like(keep["out"][i - 1]) if i > 0 else None
+            if keep["bwd_tc"]:
+                _, _, wT_hi = self._conv_ops["conv%d" % (i + 1)]
+                dY = torch.empty(M, g.Cout, dtype=torch.bfloat16, device=dev) if i > 0 else None
+                dYT = torch.empty(g.Cout, M, dtype=torch.bfloat16, device=dev)
+                dcol = torch.empty(M, K, device=dev) if i > 0 else None
+                call("riqn_conv_bwd_tc", g, ptr(douts[i]), ptr(out), ptr(keep["colT"][i]), ptr(wT_hi), ptr(dY), ptr(dYT),
+                     ptr(dcol), ptr(gv(conv.weight)), ptr(gv(conv.bias)), ptr(din))
+            else:
+                dY = torch.empty(M, g.Cout, device=dev)
+                dcol = torch.empty(M, K, device=dev) if i > 0 else None
+                call("riqn_conv_bwd", g, ptr(douts[i]), ptr(out), ptr(keep["col"][i]), ptr(conv.weight), ptr(dY), ptr(dcol),
+                     ptr(gv(conv.weight)), ptr(gv(conv.bias)), ptr(din))
+            if i > 0:
+                douts[i - 1] = din

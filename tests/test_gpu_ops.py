@@ -47,13 +47,13 @@ def test_trunk_u8_and_f32(cuda_dev, nets):
     ref = net.conv_trunk(p, torch.from_numpy(b["states"]).float().div_(255)).numpy()
     got_u8 = d.trunk(torch.from_numpy(b["states"]).to(cuda_dev)).cpu().numpy()
     got_f32 = d.trunk(torch.from_numpy(b["states"]).float().div_(255).to(cuda_dev)).cpu().numpy()
-    assert rel_err(got_u8, ref) < 1e-5
+    assert rel_err(got_u8, ref) < 3e-5      # split-bf16x3 tensor-core convolution
     assert np.array_equal(got_u8, got_f32)          # u8 ingest == fp32/255 ingest, bit for bit
     # strided window view (B, 7, 84, 84)[:, 3:7]
     win = torch.from_numpy(np.concatenate([b["states"][:, :3], b["next_states"]], axis=1)).to(cuda_dev)
     got_view = d.trunk(win[:, 3:7]).cpu().numpy()
     ref2 = net.conv_trunk(p, torch.from_numpy(b["next_states"]).float().div_(255)).numpy()
-    assert rel_err(got_view, ref2) < 1e-5
+    assert rel_err(got_view, ref2) < 3e-5
 
 
 def test_forward_injected(cuda_dev, nets):
@@ -70,18 +70,21 @@ def test_forward_injected(cuda_dev, nets):
     k2 = {}
     q, tau_out = d.forward(torch.from_numpy(b["states"]).to(cuda_dev), Nq, tau=tau, keep=k2, fresh_weights=True)
     assert torch.equal(tau_out.cpu(), tau)
-    assert rel_err(k2["cos"].cpu().numpy(), keep["cos"].numpy()) < 2e-6
-    assert rel_err(k2["xt"].cpu().numpy(), keep["x"].numpy()) < 1e-5
-    assert rel_err(k2["h"][:, :512].cpu().numpy(), keep["h_v"].numpy()) < 5e-5   # split-bf16x3 tensor-core product
-    assert rel_err(k2["h"][:, 512:].cpu().numpy(), keep["h_a"].numpy()) < 5e-5
-    assert rel_err(q.cpu().numpy(), ref.numpy()) < 5e-5
+    tc = k2["tc"]
+    cos_gpu = (tc["cos_hi"].float() + tc["cos_lo"].float()).cpu().numpy()          # bf16 hi + lo images
+    x_gpu = (tc["x_hi"].float() + tc["x_lo"].float()).cpu().numpy()
+    assert rel_err(cos_gpu, keep["cos"].numpy()) < 2e-5
+    assert rel_err(x_gpu, keep["x"].numpy()) < 3e-5
+    assert rel_err(k2["h"][:, :512].cpu().numpy(), keep["h_v"].numpy()) < 1e-4   # split-bf16x3 tensor-core products
+    assert rel_err(k2["h"][:, 512:].cpu().numpy(), keep["h_a"].numpy()) < 1e-4
+    assert rel_err(q.cpu().numpy(), ref.numpy()) < 1e-4
     # stored epsilons == outer product of the injected factors (model.py:39-43), bit for bit
     assert torch.equal(d.fcnoisy_h_a.weight_epsilon.cpu(), torch.outer(noise["fcnoisy_h_a"][1], noise["fcnoisy_h_a"][0]))
     # eval mode uses mu only (model.py:52-53)
     d.eval()
     q_eval, _ = d.forward(torch.from_numpy(b["states"]).to(cuda_dev), Nq, tau=tau)
     ref_eval = net.dqn_forward_iqn(p, torch.from_numpy(b["states"]).float().div_(255), Nq, tau, training=False)
-    assert rel_err(q_eval.cpu().numpy(), ref_eval.numpy()) < 5e-5
+    assert rel_err(q_eval.cpu().numpy(), ref_eval.numpy()) < 1e-4
     d.train()
 
 

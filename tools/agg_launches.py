@@ -11,8 +11,9 @@ agg = collections.defaultdict(lambda: [0, 0.0])
 for r in rows:
     v = float(r[vi].replace(",", ""))
     v = v / 1e3 if r[ui] in ("ns", "nsecond") else v * 1e3 if r[ui] in ("ms", "msecond") else v
-    agg[r[ki]][0] += 1
-    agg[r[ki]][1] += v
+    name = r[ki].split('(')[0].replace('void ', '')
+    agg[name][0] += 1
+    agg[name][1] += v
 nsteps = max(agg["adam_kernel"][0], 1)
 tot = sum(v[1] for v in agg.values())
 print(f"# {len(rows)} launches, {nsteps} learner steps (adam_kernel count); cold-cache serialised times: compare SHARES")
