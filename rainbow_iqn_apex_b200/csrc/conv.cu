@@ -151,6 +151,44 @@ __global__ void im2col_bf16_kernel(riqn_conv_geom g, const T* __restrict__ in, b
   }
 }
 
+// uint8 specialisation: the 256 possible pixels are converted once per block into a packed (hi | lo << 16) table, so
+// the per-element work is one byte load + one shared-memory lookup (bit-identical to x / 255.0f then hi/lo split).
+__global__ void im2col_bf16_u8_kernel(riqn_conv_geom g, const uint8_t* __restrict__ in, bf16* __restrict__ hi, bf16* __restrict__ lo) {
+  __shared__ uint32_t lut[256];
+  {
+    const float x = (float)threadIdx.x / 255.0f;
+    const bf16 h = __float2bfloat16_rn(x);
+    const bf16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+    if (threadIdx.x < 256) lut[threadIdx.x] = (uint32_t)__bfloat16_as_ushort(h) | ((uint32_t)__bfloat16_as_ushort(l) << 16);
+  }
+  __syncthreads();
+  const int K = g.Cin * g.KH * g.KW, K8 = K / 8;
+  const long total = (long)g.B * g.OH * g.OW * K8;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int k0 = (int)(idx % K8) * 8;
+    const long m = idx / K8;
+    const int ow = (int)(m % g.OW), oh = (int)((m / g.OW) % g.OH);
+    const long b = m / ((long)g.OW * g.OH);
+    int kw = k0 % g.KW, kh = (k0 / g.KW) % g.KH, c = k0 / (g.KW * g.KH);
+    const uint8_t* base = in + b * g.in_bstride;
+    const int ih0 = oh * g.stride - g.pad, iw0 = ow * g.stride - g.pad;
+    uint32_t e[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int ih = ih0 + kh, iw = iw0 + kw;
+      e[t] = (ih >= 0 && ih < g.H && iw >= 0 && iw < g.W) ? lut[base[((long)c * g.H + ih) * g.W + iw]] : 0u;
+      if (++kw == g.KW) { kw = 0; if (++kh == g.KH) { kh = 0; ++c; } }
+    }
+    uint4 h, l;
+    h.x = (e[0] & 0xffffu) | (e[1] << 16); h.y = (e[2] & 0xffffu) | (e[3] << 16);
+    h.z = (e[4] & 0xffffu) | (e[5] << 16); h.w = (e[6] & 0xffffu) | (e[7] << 16);
+    l.x = (e[0] >> 16) | (e[1] & 0xffff0000u); l.y = (e[2] >> 16) | (e[3] & 0xffff0000u);
+    l.z = (e[4] >> 16) | (e[5] & 0xffff0000u); l.w = (e[6] >> 16) | (e[7] & 0xffff0000u);
+    *reinterpret_cast<uint4*>(hi + m * K + k0) = h;
+    if (lo) *reinterpret_cast<uint4*>(lo + m * K + k0) = l;
+  }
+}
+
 // colT (K, M): one thread = 8 consecutive m of one k  (M % 8 == 0)
 template <typename T>
 __global__ void im2col_bf16_t_kernel(riqn_conv_geom g, const T* __restrict__ in, bf16* __restrict__ hiT) {
@@ -278,7 +316,7 @@ RIQN_API int riqn_conv_fwd_tc(const riqn_conv_geom* g, const void* in, int in_is
   const long M = (long)g->B * g->OH * g->OW;
   const int K = g->Cin * g->KH * g->KW;
   if (K % 8 || (colT_hi && M % 8)) return (int)cudaErrorInvalidValue;
-  if (in_is_u8) im2col_bf16_kernel<uint8_t><<<grid_for(M * K / 8), 256, 0, s>>>(*g, (const uint8_t*)in, (bf16*)col_hi, (bf16*)col_lo);
+  if (in_is_u8) im2col_bf16_u8_kernel<<<grid_for(M * K / 8), 256, 0, s>>>(*g, (const uint8_t*)in, (bf16*)col_hi, (bf16*)col_lo);
   else im2col_bf16_kernel<float><<<grid_for(M * K / 8), 256, 0, s>>>(*g, (const float*)in, (bf16*)col_hi, (bf16*)col_lo);
   RIQN_LAUNCH_CHECK();
   if (colT_hi) {

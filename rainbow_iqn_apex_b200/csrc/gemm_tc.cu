@@ -28,7 +28,8 @@ namespace riqn {
 using bf16 = __nv_bfloat16;
 
 constexpr int TBM = 128, TBN = 256, TBK = 64, UMMA_K = 16;
-constexpr int TC_THREADS = 192;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int EPI_WARPS = 8;     // two warps per TMEM lane quarter, each draining half of the 256 accumulator columns
+constexpr int TC_THREADS = 64 + 32 * EPI_WARPS;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, then epilogue
 constexpr uint32_t TMEM_COLS = 512;
 
 
@@ -147,7 +148,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -166,7 +167,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
       uint32_t phase = 0;
       for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
         const int ks = u % p.k_splits, t = u / p.k_splits;
-        const int mt = t % p.m_tiles, nt = t / p.m_tiles;
+        const int nt = t % p.n_tiles, mt = t / p.n_tiles;   // n fastest: the A tile is shared by the n-tiles in flight
         const int kb0 = ks * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
@@ -223,10 +224,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
   } else {
     // ------------------------------------------------------------------ epilogue warps (TMEM -> registers -> HBM)
     const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32) are the ones this warp may read
+    const int chalf = (warp - 2) >> 2;            // which half of the accumulator columns this warp drains
     int local = 0;
     for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++local) {
       const int t = u / p.k_splits;
-      const int mt = t % p.m_tiles, nt = t / p.m_tiles;
+      const int nt = t % p.n_tiles, mt = t / p.n_tiles;
       const int as = local & 1;
       const uint32_t aphase = (local >> 1) & 1;
       mbar_wait(&tfull[as], aphase);
@@ -234,7 +236,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
       const int m = mt * TBM + quarter * 32 + lane;
       const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * TBN;
 #pragma unroll 1
-      for (int c = 0; c < TBN; c += 32) {
+      for (int c = chalf * (TBN / 2); c < (chalf + 1) * (TBN / 2); c += 32) {
         uint32_t v[32];
         tmem_ld32(trow + c, v);
         const int n0 = nt * TBN + c;

@@ -199,17 +199,26 @@ __global__ void z_dueling_fwd_kernel(long R, int A, const float* __restrict__ H,
 // Double-DQN action: a*[b] = argmax_a mean_k q[k*B+b, a]               (compute_loss_iqn.py:238-245)
 // ------------------------------------------------------------------------------------------------
 __global__ void argmax_mean_kernel(int B, int K, int A, const float* __restrict__ q, int64_t* __restrict__ a_star) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  // one warp per transition, lane a (< A <= 32) sums its action's K quantile values in order k = 0..K-1
+  const int b = (int)(((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
   if (b >= B) return;
-  float best = 0.f;
-  int arg = 0;
-  for (int a = 0; a < A; ++a) {
-    float s = 0.f;
-    for (int k = 0; k < K; ++k) s += q[((long)k * B + b) * A + a];
+  float s = -INFINITY;
+  if (lane < A) {
+    s = 0.f;
+    for (int k = 0; k < K; ++k) s += q[((long)k * B + b) * A + lane];
     s /= (float)K;
-    if (a == 0 || s > best) { best = s; arg = a; }
   }
-  a_star[b] = arg;
+  // argmax with the first maximal index winning (torch.argmax)
+  float best = s;
+  int arg = lane;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+    if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+  }
+  if (lane == 0) a_star[b] = arg;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -600,7 +609,8 @@ RIQN_API int riqn_z_wgrad(long rows, int hidden, int action_space, const float* 
 RIQN_API int riqn_argmax_mean(int batch, int num_quantiles, int action_space, const float* q, long long* a_star,
                               void* stream) {
   riqn::note_launches(1);
-  argmax_mean_kernel<<<riqn_cdiv(batch, 128), 128, 0, (cudaStream_t)stream>>>(batch, num_quantiles, action_space, q,
+  if (action_space > 32) return (int)cudaErrorInvalidValue;
+  argmax_mean_kernel<<<riqn_cdiv((long)batch * 32, 128), 128, 0, (cudaStream_t)stream>>>(batch, num_quantiles, action_space, q,
                                                                             (int64_t*)a_star);
   return (int)cudaGetLastError();
 }

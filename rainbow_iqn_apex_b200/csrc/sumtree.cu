@@ -22,23 +22,18 @@ namespace riqn {
 // (redis_memory.py:276-287).  Single CTA; thread 0 runs the Fisher-Yates shuffle in shared memory.
 __global__ void stratified_kernel(int n, uint64_t seed, uint64_t stream, const double* __restrict__ tree,
                                   double* __restrict__ values) {
-  extern __shared__ int perm[];
+  // the shuffle: stratum s goes to output slot rank(key_s), keys = Philox draws (ties broken by index)
+  extern __shared__ uint32_t keys[];
   const double seg = tree[0] / (double)n;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) perm[i] = i;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) keys[i] = Philox::draw(seed, stream ^ 0x5bd1e995ull, (uint64_t)i).x;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int i = n - 1; i > 0; --i) {
-      const uint4 r = Philox::draw(seed, stream ^ 0x5bd1e995ull, (uint64_t)i);
-      const int j = (int)(((uint64_t)r.x * (uint64_t)(i + 1)) >> 32);
-      const int t = perm[i]; perm[i] = perm[j]; perm[j] = t;
-    }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const int s = perm[i];
+  for (int s = threadIdx.x; s < n; s += blockDim.x) {
+    const uint32_t me = keys[s];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) rank += (keys[j] < me) || (keys[j] == me && j < s);
     const uint4 r = Philox::draw(seed, stream, (uint64_t)s);
     const double a = (double)s * seg, b = (double)(s + 1) * seg;
-    values[i] = __dadd_rn(a, __dmul_rn(b - a, Philox::u01d(r.x, r.y)));   // a + (b-a)*u, no FMA contraction
+    values[rank] = __dadd_rn(a, __dmul_rn(b - a, Philox::u01d(r.x, r.y)));   // a + (b-a)*u, no FMA contraction
   }
 }
 
