@@ -59,7 +59,8 @@ def make_data_parallel(learner, group=None):
         net._tau_stream_offset = rank << 40
         for _, m in net.noisy_layers():
             m._noise_calls = 0
-        net.compose_weights()
+        if net._flat.is_cuda:
+            net.compose_weights()
     learner.process_group = group if group is not None else dist.group.WORLD
     learner.optimiser.grad_scale = 1.0 / world
     return learner
