@@ -52,6 +52,16 @@ def peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture (profiles/r01_traffic.json); None if absent."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    return d.get("dominant_kernel_dram_bytes_per_launch")
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -194,7 +204,7 @@ def run_ours(args):
     hms = sum(a_.elapsed_time(b_) for a_, b_, _ in evs)
     head_tf = flops / (hms * 1e-3) / 1e12 if hms > 0 else 0.0
     roof = {"kernel": label, "bound": "tensor", "achieved": head_tf, "peak": pk["tf_sust"], "unit": "TFLOP/s",
-            "frac": head_tf / pk["tf_sust"], "traffic": None, "peak_source": pk["src"] + " bf16 sustained (in-step)",
+            "frac": head_tf / pk["tf_sust"], "traffic": ncu_traffic(), "peak_source": pk["src"] + " bf16 sustained (in-step)",
             "share_of_step": hms / ms, "mma_passes": passes, "tensor_pipe_frac": passes * head_tf / pk["tf_sust"],
             "precision": dict(_model.PRECISION), "us_per_launch": hms * 1e3 / max(len(evs), 1)}
     lk = per["riqn_iqn_loss_fwd_bwd"]
@@ -259,10 +269,10 @@ def run_ours(args):
 
 
 # ------------------------------------------------------------------------------------------ CPU arms
-def oracle_learner(batch):
+def oracle_learner(batch, threads=None):
     """The oracle port of Learner.learn (oracle/losses.py) on the host CPU cores."""
     from oracle import cases, losses, network as net
-    torch.set_num_threads(os.cpu_count())
+    torch.set_num_threads(threads or os.cpu_count())
     params = net.make_params(123)
     p_on, p_tg = net.to_torch(params, requires_grad=True), net.to_torch(params)
     adam = losses.Adam([k for k in p_on if net.is_trainable(k)], lr=5e-5, eps=3.125e-4)
@@ -281,8 +291,26 @@ def oracle_learner(batch):
     return step
 
 
+def best_threads():
+    """torch's intra-op scaling on many-core hosts is not monotonic (128 threads were 10x slower than 32 on the GPU
+    box): probe a small step at a few thread counts and keep the fastest, so the CPU arm is not handicapped."""
+    n = os.cpu_count() or 8
+    cands = sorted({c for c in (n, n // 2, 64, 32, 16, 8) if 1 <= c <= n}, reverse=True)
+    best, best_t = cands[0], float("inf")
+    for c in cands:
+        step = oracle_learner(16, c)
+        step(0)
+        t0 = time.perf_counter()
+        step(1)
+        dt = time.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = c, dt
+    return best
+
+
 def cpu_baseline(max_seconds=25.0):
-    step = oracle_learner(B)
+    threads = best_threads()
+    step = oracle_learner(B, threads)
     t0 = time.perf_counter()
     step(0)                                     # warm-up (also sizes the sample)
     t1 = time.perf_counter() - t0
@@ -304,16 +332,18 @@ def run_reference(args):
         return
     world = args.gpus
     # bound the run: each step is a sample of `bs` of the 512 transitions, scaled linearly to a full step
-    probe = oracle_learner(64)
-    t0 = time.perf_counter()
+    threads = best_threads()
+    probe = oracle_learner(64, threads)
     probe(0)
+    t0 = time.perf_counter()
+    probe(1)
     t64 = time.perf_counter() - t0
     budget = 150.0
     total_steps = args.steps + max(args.warmup, 1)
     bs = B
     while bs > 32 and (t64 * bs / 64) * total_steps > budget:
         bs //= 2
-    step = oracle_learner(bs)
+    step = oracle_learner(bs, threads)
     for i in range(max(args.warmup, 1)):
         step(i)
     t0 = time.perf_counter()
@@ -338,7 +368,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--replay-capacity", type=int, default=1 << 19)

@@ -173,6 +173,34 @@ int riqn_iqn_loss_fwd_bwd(int batch, int n_tau, int n_tau_prime, int action_spac
                           float* dtheta, float* theta_out, float* target_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Rainbow-only (C51) head and loss            replaces rainbowiqn/model.py:120-129, rainbowiqn/agent.py:77-141
+ * ---------------------------------------------------------------------------------------------- */
+/* zv (batch, atoms), za (batch, A*atoms) -> q = v + a - mean_a a; p / logp (batch, A, atoms) = (log_)softmax over
+ * atoms (either may be NULL); a_star (may be NULL) = argmax_a sum_j support[j] p[b,a,j]  (agent.py:92-99). */
+int riqn_c51_head_fwd(int batch, int action_space, int atoms, const float* zv, const float* za, const float* support,
+                      float* p, float* logp, long long* a_star, void* stream);
+/* Bellman projection of p_target[b, a_star[b], :] onto the support (agent.py:104-133, incl. the l == u fix),
+ * loss[b] = -sum_j m_j logp_online[b, actions[b], j] (agent.py:141) and dq (batch, atoms) = dloss/dq[b, actions[b], :].
+ * m_out (batch, atoms) optional. */
+int riqn_c51_loss_fwd_bwd(int batch, int action_space, int atoms, const float* logp_online, const float* p_target,
+                          const long long* actions, const long long* a_star, const float* returns,
+                          const float* nonterminals, const float* support, float gamma_n, float v_min, float v_max,
+                          float delta_z, float* loss, float* dq, float* m_out, void* stream);
+/* dzv (batch, atoms), dza (batch, A*atoms) from dq scaled by gscale[b] (dueling backward). */
+int riqn_c51_head_bwd(int batch, int action_space, int atoms, const float* dq, const float* gscale,
+                      const long long* actions, float* dzv, float* dza, void* stream);
+/* grad[i] = 0 where act[i] <= 0. */
+int riqn_relu_mask(long n, const float* act, float* grad, void* stream);
+/* Strided fp32 linear-layer helpers for the small z-layers: y = x w^T + bias (optional ReLU); dx = dy w;
+ * grad_mu += dy^T x, grad_sigma += (dy^T x) * weight_epsilon. */
+int riqn_linear_fwd_ld(long rows, int in_features, int out_features, const float* x, long ldx, const float* w,
+                       const float* bias, float* y, long ldy, int relu, void* stream);
+int riqn_linear_dgrad_ld(long rows, int in_features, int out_features, const float* dy, long lddy, const float* w,
+                         float* dx, long lddx, void* stream);
+int riqn_noisy_wgrad_ld(long rows, int in_features, int out_features, const float* dy, long lddy, const float* x, long ldx,
+                        const float* weight_epsilon, float* grad_mu, float* grad_sigma, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Optimiser                              replaces torch.optim.Adam.step, agent.py:43 / learner.py:24
  * ---------------------------------------------------------------------------------------------- */
 /* One Adam step over a flat arena of n fp32 parameters; `step` is the 1-based step count; grads are

@@ -47,6 +47,14 @@ SIGNATURES = {
     "riqn_argmax_mean": [C.c_int, C.c_int, C.c_int, _P, _P, _P],
     "riqn_iqn_loss_fwd_bwd": [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, C.c_float, C.c_float,
                               _P, _P, _P, _P, _P],
+    "riqn_c51_head_fwd": [C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P],
+    "riqn_c51_loss_fwd_bwd": [C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, C.c_float, C.c_float, C.c_float,
+                              C.c_float, _P, _P, _P, _P],
+    "riqn_c51_head_bwd": [C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P],
+    "riqn_relu_mask": [C.c_long, _P, _P, _P],
+    "riqn_linear_fwd_ld": [C.c_long, C.c_int, C.c_int, _P, C.c_long, _P, _P, _P, C.c_long, C.c_int, _P],
+    "riqn_linear_dgrad_ld": [C.c_long, C.c_int, C.c_int, _P, C.c_long, _P, _P, C.c_long, _P],
+    "riqn_noisy_wgrad_ld": [C.c_long, C.c_int, C.c_int, _P, C.c_long, _P, C.c_long, _P, _P, _P, _P],
     "riqn_adam_step": [C.c_long, _P, _P, _P, _P, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _P],
     "riqn_sumtree_stratified": [C.c_int, C.c_ulonglong, C.c_ulonglong, _P, _P, _P],
     "riqn_sumtree_sample": [C.c_int, C.c_long, C.c_int, _P, _P, _P, C.c_int, C.c_int, _P, _P, _P, _P],

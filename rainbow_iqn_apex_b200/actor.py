@@ -7,6 +7,7 @@ import random
 import numpy as np
 import torch
 
+from ._lib import call, ptr
 from .agent import Agent
 from .learner import MODEL_WEIGHT_STR
 
@@ -22,7 +23,9 @@ class Actor(Agent):
                 p = self.online_net(state.unsqueeze(0))
                 return (p * self.support).sum(2).argmax(1).item()
             quantile_values, _ = self.online_net(state.unsqueeze(0), self.num_quantile_samples)
-            return quantile_values.mean(0).argmax(0).item()
+            a = torch.empty(1, dtype=torch.int64, device=state.device)
+            call("riqn_argmax_mean", 1, self.num_quantile_samples, self.action_space, ptr(quantile_values), ptr(a))
+            return int(a.item())
 
     def act_batch(self, states_u8):
         """Batched greedy actions for many environments at once: states (E, history, 84, 84) uint8 -> (E,)."""
@@ -31,7 +34,9 @@ class Actor(Agent):
                 return (self.online_net(states_u8) * self.support).sum(2).argmax(1)
             E = states_u8.shape[0]
             q, _ = self.online_net(states_u8, self.num_quantile_samples)
-            return q.view(self.num_quantile_samples, E, self.action_space).mean(0).argmax(1)
+            a = torch.empty(E, dtype=torch.int64, device=q.device)
+            call("riqn_argmax_mean", E, self.num_quantile_samples, self.action_space, ptr(q), ptr(a))
+            return a
 
     def act_e_greedy(self, state_buffer, epsilon=0.001):
         """actor.py:27-34"""

@@ -141,6 +141,7 @@ class DQN(nn.Module):
         self.conv3 = nn.Conv2d(64, 64, 3)
         if self.rainbow_only:
             self.atoms = args.atoms
+            self._v_min, self._v_max = args.V_min, args.V_max
             zv, za = self.atoms, action_space * self.atoms
         else:
             self.quantile_embedding_dim = args.quantile_embedding_dim
@@ -301,6 +302,12 @@ class DQN(nn.Module):
         if not self.rainbow_only:
             call("riqn_split_bf16", FEAT, self.quantile_embedding_dim, ptr(self.iqn_fc.weight), ptr(self._iqn_ops[0]),
                  ptr(self._iqn_ops[1]), None, None)
+
+    def _support(self, dev):
+        """z-support of the categorical head (agent.py:54-57); only used when forward() is called without an Agent."""
+        if getattr(self, "_support_t", None) is None or self._support_t.device != dev:
+            self._support_t = torch.linspace(self._v_min, self._v_max, self.atoms).to(dev)
+        return self._support_t
 
     def draw_quantiles(self, n):
         tau = torch.empty(n, 1, device=self._flat.device)

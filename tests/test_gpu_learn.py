@@ -239,3 +239,67 @@ def test_full_size_config2_vs_oracle(cuda_dev, batch):
     lg, lo = loss.cpu().numpy(), o_loss.numpy()
     assert np.max(np.abs(lg[ok] - lo[ok]) / np.abs(lo[ok])) < 1e-3          # north_star tolerance
     assert np.max(np.abs(lg[ok] - lo[ok]) / np.abs(lo[ok])) < LOSS_TOL      # what fp32 CUDA achieves
+
+
+# ----------------------------------------------------------------------------------------------- C51 (rainbow_only)
+def test_c51_learn_matches_reference_golden(cuda_dev, golden_dir):
+    """BASELINE config 3 path: categorical loss (agent.py:77-141) + backward + Adam against the fixtures recorded from
+    the unmodified reference (two consecutive Learner.learn calls)."""
+    from rainbow_iqn_apex_b200 import Learner
+    g = np.load(os.path.join(golden_dir, "c51_small.npz"))
+    seed, batch, steps = int(g["seed"]), int(g["batch"]), int(g["steps"])
+    lr = Learner(make_args(cuda_dev, batch, rainbow_only=True), 18, None)
+    load_params(lr.online_net, net.make_params(seed, rainbow_only=True))
+    lr.update_target_net()
+    lr.train()
+    for s in range(steps):
+        b = cases.make_batch(seed + 10 + s, batch)
+        lr._inject = dict(noises=cases.make_noises(seed + 30 + s, rainbow_only=True), taus=None)
+        st, ac, rt, nx, nt = _dev_batch(b, cuda_dev)
+        w = torch.from_numpy(b["weights"]).to(cuda_dev)
+        _, loss = lr.learn(FakeMem((np.arange(batch), st, ac, rt, nx, nt, w)), None)
+        assert np.max(np.abs(loss.cpu().numpy() - g[f"loss_{s}"]) / np.abs(g[f"loss_{s}"])) < LOSS_TOL
+        for k, p in lr.online_net.named_parameters():
+            gd, ref = digest(p.grad), g[f"grad_{s}_{k}"]
+            gtol = 5e-2 if k.startswith(("conv1", "conv2")) else 2e-3
+            assert abs(gd[2] - ref[2]) <= gtol * ref[2] + 1e-9, (k, gd[:3], ref[:3])
+            pd, pref = digest(p), g[f"param_{s}_{k}"]
+            assert np.allclose(pd[2:], pref[2:], rtol=1e-5, atol=5e-6), k
+
+
+def test_c51_loss_api_vs_oracle(cuda_dev):
+    from rainbow_iqn_apex_b200 import Agent
+    batch, seed = 16, 777
+    params = net.make_params(seed, rainbow_only=True)
+    ag = Agent(make_args(cuda_dev, batch, rainbow_only=True), 18, None)
+    load_params(ag.online_net, params)
+    ag.update_target_net()
+    b = cases.make_batch(seed + 1, batch)
+    noises = cases.make_noises(seed + 3, rainbow_only=True)
+    ag._inject = dict(noises=noises, taus=None)
+    dbg = {}
+    st, ac, rt, nx, nt = _dev_batch(b, cuda_dev)
+    loss = ag.compute_loss_actor_or_learner(st, ac, rt, nx, nt, debug=dbg)
+    w = torch.from_numpy(b["weights"]).to(cuda_dev)
+    ag.online_net.zero_grad()
+    (w * loss).mean().backward()
+    p_on, p_tg = net.to_torch(params, requires_grad=True), net.to_torch(params)
+    keep = {}
+    o_loss = losses.c51_loss(p_on, p_tg, *cases.batch_to_torch(b), noises, keep=keep)
+    (torch.from_numpy(b["weights"]) * o_loss).mean().backward()
+    assert torch.equal(dbg["a_star"].cpu(), keep["a_star"])
+    assert rel_err(dbg["m"].cpu().numpy(), keep["m"].numpy()) < 1e-4
+    assert np.max(np.abs(loss.detach().cpu().numpy() - o_loss.detach().numpy()) / np.abs(o_loss.detach().numpy())) < LOSS_TOL
+    for k in ("fcnoisy_z_a.weight_mu", "fcnoisy_z_v.weight_sigma", "fcnoisy_h_a.weight_mu", "fcnoisy_h_v.bias_sigma", "conv3.weight"):
+        gg, gr = dict(ag.online_net.named_parameters())[k].grad.cpu(), p_on[k].grad
+        cos = float((gg * gr).sum() / (gg.norm() * gr.norm() + 1e-30))
+        assert cos > 0.999, (k, cos)
+    # Actor.act on the categorical head (actor.py:19-21) agrees with the oracle's expected-value argmax
+    from rainbow_iqn_apex_b200 import Actor
+    actor = Actor(make_args(cuda_dev, batch, rainbow_only=True), 18, None)
+    load_params(actor.online_net, params)
+    actor.eval()
+    frames = [b["states"][0, i] for i in range(4)]
+    a = actor.act(frames)
+    p_eval = net.dqn_forward_c51(net.to_torch(params), torch.from_numpy(b["states"][:1]).float().div_(255), 18, 51, training=False)
+    assert a == int((p_eval * torch.linspace(-10, 10, 51)).sum(2).argmax(1))
