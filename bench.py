@@ -147,43 +147,59 @@ def run_ours(args):
     mem = ReplayMemory(a, None)
     fill_replay(mem, args.replay_capacity, dev, 1000 + rank)
 
-    def step():
-        idxs, loss = learner.learn(mem, None)
-        mem.update_priorities(idxs, loss)
-        return loss
-
     def barrier():
         if world > 1:
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
+    def step():
+        return learner.learn_and_update(mem)[1]
+
+    # ---- pass 1 (eager, not the headline): per-entry-point device times for the roofline section
+    for _ in range(3):
         step()
     barrier()
     timed_names = ("riqn_gemm_bf16_tc", "riqn_noisy_linear_fwd", "riqn_iqn_loss_fwd_bwd", "riqn_split_bf16",
                    "riqn_quantile_embed_fwd_tc", "riqn_quantile_embed_bwd_tc", "riqn_conv_fwd_tc", "riqn_conv_bwd_tc",
                    "riqn_dueling_fwd", "riqn_dueling_bwd", "riqn_z_wgrad", "riqn_adam_step", "riqn_frame_gather",
                    "riqn_sumtree_sample", "riqn_sumtree_update", "riqn_noisy_compose")
-    clocks = ClockSampler(local)
-    clocks.start()
-    launches0 = _lib.launch_count()
+    prof_steps = 5
     timers = _lib.time_entry_points(timed_names)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = _lib.launch_count()
+    e0.record()
+    t_host0 = time.perf_counter()
+    for _ in range(prof_steps):
+        step()
+    host_issue_ms = (time.perf_counter() - t_host0) * 1e3 / prof_steps     # CPU time to enqueue one eager step
+    e1.record()
+    barrier()
+    _lib.time_entry_points(None)
+    launches_per_step = (_lib.launch_count() - launches0) // prof_steps
+    eager_ms = e0.elapsed_time(e1) / prof_steps
+
+    # ---- pass 2 (headline): the whole step captured once in a CUDA graph and replayed
+    if not args.no_graph:
+        learner.enable_cuda_graph(mem)
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
     barrier()
     e0.record()
     for _ in range(args.steps):
         loss = step()
     e1.record()
     barrier()
-    _lib.time_entry_points(None)
-    launches = _lib.launch_count() - launches0
+    launches = launches_per_step * args.steps          # kernels executed in the timed region (graph replays them)
     clk = clocks.stop()
     ms = parallel.allreduce_max(e0.elapsed_time(e1), dev)
     ms_per_step = ms / args.steps
     value = world * 1000.0 / ms_per_step
     assert torch.isfinite(loss).all()
 
-    # per-entry-point device time from the CUDA events recorded on the launching stream
+    # per-entry-point device time from the CUDA events recorded on the launching stream (eager pass)
     per = {}
     for name, evs in timers.items():
         per[name] = dict(ms_total=sum(a_.elapsed_time(b_) for a_, b_, _ in evs), calls=len(evs))
@@ -191,22 +207,19 @@ def run_ours(args):
     from rainbow_iqn_apex_b200 import model as _model
     # dominant kernel: the hidden NoisyLinear products.  Algorithmic FLOPs = 2*M*N*K per launch; the
     # split-bf16x3 mode issues 3 MMAs per algorithmic multiply-add, reported as mma_passes.
-    if timers["riqn_gemm_bf16_tc"]:
-        evs = timers["riqn_gemm_bf16_tc"]
-        label = "gemm_tc_kernel (tcgen05.mma + TMA; NoisyLinear fwd/dgrad/wgrad, %d launches/step)" % (len(evs) // args.steps)
-        flops = sum(2.0 * a_[0] * a_[1] * a_[2] for _, _, a_ in evs)
-        passes = sum((3 if a_[4] else 1) * 2.0 * a_[0] * a_[1] * a_[2] for _, _, a_ in evs) / flops
-    else:
-        evs = timers["riqn_noisy_linear_fwd"]
-        label = "gemm_simt_kernel (fp32 CUDA cores; NoisyLinear fwd, 3 launches/step)"
-        flops = sum(2.0 * a_[0] * a_[1] * a_[2] for _, _, a_ in evs)
-        passes = 1.0
+    def _is_head(a_):
+        return min(a_[0], a_[1]) >= 1024 and a_[2] >= 1024
+    evs = [e for e in timers["riqn_gemm_bf16_tc"] if _is_head(e[2])]
+    label = "gemm_tc_kernel (tcgen05.mma + TMA; NoisyLinear fwd x3 / dgrad / wgrad, %d launches/step)" % (len(evs) // prof_steps)
+    flops = sum(2.0 * a_[0] * a_[1] * a_[2] for _, _, a_ in evs)
+    passes = sum((3 if a_[4] else 1) * 2.0 * a_[0] * a_[1] * a_[2] for _, _, a_ in evs) / max(flops, 1.0)
     hms = sum(a_.elapsed_time(b_) for a_, b_, _ in evs)
     head_tf = flops / (hms * 1e-3) / 1e12 if hms > 0 else 0.0
     roof = {"kernel": label, "bound": "tensor", "achieved": head_tf, "peak": pk["tf_sust"], "unit": "TFLOP/s",
             "frac": head_tf / pk["tf_sust"], "traffic": ncu_traffic(), "peak_source": pk["src"] + " bf16 sustained (in-step)",
-            "share_of_step": hms / ms, "mma_passes": passes, "tensor_pipe_frac": passes * head_tf / pk["tf_sust"],
-            "precision": dict(_model.PRECISION), "us_per_launch": hms * 1e3 / max(len(evs), 1)}
+            "share_of_step": hms / (eager_ms * prof_steps), "mma_passes": passes,
+            "tensor_pipe_frac": passes * head_tf / pk["tf_sust"], "precision": dict(_model.PRECISION),
+            "us_per_launch": hms * 1e3 / max(len(evs), 1), "timed": "CUDA events around each launch, eager pass"}
     lk = per["riqn_iqn_loss_fwd_bwd"]
     loss_bytes = 4 * B * (N_TAU + N_TAU_P + N_TAU) + 4 * B * N_TAU + B * (4 + 4 + 8 + 8 + 4)   # SURVEY 8d gathered form
     loss_us = lk["ms_total"] * 1e3 / max(lk["calls"], 1)
@@ -218,23 +231,26 @@ def run_ours(args):
     # ---- end-to-end through the reference-facing API with HOST buffers (pinned), H2D/D2H inside the timed region
     pool = []
     for _ in range(4):
-        idxs, st, ac, rt, nx, nt, w = mem.sample(B)
-        pool.append(tuple(t.contiguous().cpu().pin_memory() for t in (idxs, st, ac, rt, nx, nt, w)))
+        smp = mem.sample(B)
+        pool.append(tuple(t.contiguous().cpu().pin_memory() for t in smp))
     h2d = sum(t.numel() * t.element_size() for t in pool[0])
     d2h = B * 4
+    if not args.no_graph:
+        learner.enable_batch_graph(mem, tuple(t.contiguous() for t in mem.sample(B)))
 
     def e2e_step(i):
         host = pool[i % len(pool)]
-        idxs, st, ac, rt, nx, nt, w = (t.to(dev, non_blocking=True) for t in host)
-        loss = learner.learn_on_batch(st, ac, rt, nx, nt, w)
-        loss_host = loss.cpu()                                   # D2H + sync: the result the caller consumes
-        mem.update_priorities(idxs, loss)
-        return loss_host
+        if not args.no_graph:
+            loss = learner.learn_on_host_batch(host)               # async H2D into static buffers + graph replay
+        else:
+            idxs, st, ac, rt, nx, nt, w = (t.to(dev, non_blocking=True) for t in host)
+            loss = learner.learn_on_batch(st, ac, rt, nx, nt, w)
+            mem.update_priorities(idxs, loss)
+        return loss.cpu()                                          # D2H + sync: the result the caller consumes
 
     for i in range(3):
         e2e_step(i)
     barrier()
-    t0 = time.perf_counter()
     e0.record()
     for i in range(args.steps):
         e2e_step(i)
@@ -255,9 +271,10 @@ def run_ours(args):
                    "l2": "inputs larger than L2 (fresh prioritized minibatch from a %.1f GB replay shard each step; "
                          ">2 GB of activations streamed per step)" % (args.replay_capacity * 7056 / 1e9)},
         "frames_per_s": value * B * 4, "transitions_per_s": value * B,
-        "clocks": clk, "e2e": e2e, "gpu_launches": launches,
+        "clocks": clk, "e2e": e2e, "gpu_launches": launches, "cuda_graph": not args.no_graph,
+        "eager": {"ms_per_step": eager_ms, "host_issue_ms_per_step": host_issue_ms},
         "roofline": roof, "roofline_iqn_loss": roof_loss,
-        "kernel_ms_per_step": {k: v["ms_total"] / args.steps for k, v in per.items()},
+        "kernel_ms_per_step": {k: v["ms_total"] / prof_steps for k, v in per.items()},
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(max_seconds=25.0)
@@ -373,6 +390,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--replay-capacity", type=int, default=1 << 19)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

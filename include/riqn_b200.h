@@ -32,6 +32,17 @@ long long riqn_launch_count(void);
 /* 1 if the running device is compute capability 10.x (sm_100a cubins only), else 0; <0 on CUDA error. */
 int riqn_device_ok(void);
 
+/* Per-step scalars that change from one learner step to the next, kept in DEVICE memory so that a whole step can be
+ * captured once in a CUDA graph and replayed: entry points taking `dyn` read these instead of their by-value arguments
+ * when dyn != NULL (the host rewrites the 32-byte struct with one async copy before each replay). */
+typedef struct riqn_dyn_state {
+  unsigned long long rng_offset;   /* added to every Philox stream id (advance by >= 64 per step)          */
+  float adam_neg_step_size;        /* -(lr / (1 - beta1^t))                                                 */
+  float adam_sqrt_bc2;             /* sqrt(1 - beta2^t)                                                     */
+  double is_capacity;              /* current replay fill, ReplayRedisMemory.sample_byte capacity (:467)    */
+  double is_beta;                  /* priority_weight beta (annealed by the caller, launch_learner.py:167)  */
+} riqn_dyn_state;
+
 /* ------------------------------------------------------------------------------------------------
  * Conv trunk                                     replaces nn.Conv2d x3 + ReLU, rainbowiqn/model.py:65-67,115-118
  * ---------------------------------------------------------------------------------------------- */
@@ -75,9 +86,11 @@ int riqn_conv_bwd_tc(const riqn_conv_geom* g, const float* dout, const float* ou
  * Randomness                       replaces torch normal_/uniform_ draws, model.py:32-37 and :131-134
  * ---------------------------------------------------------------------------------------------- */
 /* out[i] ~ U(0,1): the quantile fractions tau.  Philox4x32-10 keyed by (seed, stream_id). */
-int riqn_fill_uniform(long n, unsigned long long seed, unsigned long long stream_id, float* out, void* stream);
+int riqn_fill_uniform(long n, unsigned long long seed, unsigned long long stream_id, float* out,
+                      const riqn_dyn_state* dyn, void* stream);
 /* out[i] = sign(x) sqrt|x|, x ~ N(0,1): NoisyLinear._scale_noise (model.py:32-37). */
-int riqn_noisy_sample(long n, unsigned long long seed, unsigned long long stream_id, float* out, void* stream);
+int riqn_noisy_sample(long n, unsigned long long seed, unsigned long long stream_id, float* out,
+                      const riqn_dyn_state* dyn, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * NoisyLinear                                             replaces rainbowiqn/model.py:9-53
@@ -206,7 +219,7 @@ int riqn_noisy_wgrad_ld(long rows, int in_features, int out_features, const floa
 /* One Adam step over a flat arena of n fp32 parameters; `step` is the 1-based step count; grads are
  * multiplied by grad_scale first (1/world_size after a gradient all-reduce). */
 int riqn_adam_step(long n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int step, float lr,
-                   float beta1, float beta2, float eps, float grad_scale, void* stream);
+                   float beta1, float beta2, float eps, float grad_scale, const riqn_dyn_state* dyn, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Prioritized replay: sum-tree          replaces RedisSegmentTree / ReplayRedisMemory, redis_memory.py
@@ -214,7 +227,7 @@ int riqn_adam_step(long n, float* params, const float* grads, float* exp_avg, fl
  * ---------------------------------------------------------------------------------------------- */
 /* Stratified sample values, one per segment of total/n, shuffled (redis_memory.py:276-287). n <= 12000. */
 int riqn_sumtree_stratified(int n, unsigned long long seed, unsigned long long stream_id, const double* tree,
-                            double* values, void* stream);
+                            double* values, const riqn_dyn_state* dyn, void* stream);
 /* Descent (_retrieve_multiple_values :205-229) + transform_to_valid_tree_indexes (:242-264) + priority
  * read (:315-321).  index_actor: per-actor write heads (int64).  Bit-exact with the reference. */
 int riqn_sumtree_sample(int n, long capacity, int actor_capacity, const double* tree, const double* values,
@@ -223,7 +236,8 @@ int riqn_sumtree_sample(int n, long capacity, int actor_capacity, const double* 
 /* Importance-sampling weights (sample_byte :465-475); n_nonpositive (device int, may be NULL) counts the
  * priorities <= 0 that were replaced by 1/capacity (:446-456). */
 int riqn_sumtree_is_weights(int n, const double* tree, const double* priorities, double current_capacity,
-                            double priority_weight, double* w64, float* w32, int* n_nonpositive, void* stream);
+                            double priority_weight, double* w64, float* w32, int* n_nonpositive,
+                            const riqn_dyn_state* dyn, void* stream);
 /* update_priorities / update_multiple_value / _propagate_multiple_values (:557-573,139-151,94-105).
  * apply_pow != 0: new = np.power(loss, float32(priority_exponent)) first.  new_priorities (n floats) and
  * diff_scratch (n doubles) are outputs/workspace; *max_priority (device double) is raised if needed.

@@ -12,7 +12,9 @@ int colsum_atomic(long M, int N, const float* X, float* out, cudaStream_t s);
 // ------------------------------------------------------------------------------------------------
 // RNG fills
 // ------------------------------------------------------------------------------------------------
-__global__ void fill_uniform_kernel(long n, uint64_t seed, uint64_t stream, float* __restrict__ out) {
+__global__ void fill_uniform_kernel(long n, uint64_t seed, uint64_t stream, float* __restrict__ out,
+                                    const riqn_dyn_state* __restrict__ dyn) {
+  if (dyn) stream += dyn->rng_offset;
   const long i4 = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i4 * 4 >= n) return;
   const uint4 r = Philox::draw(seed, stream, (uint64_t)i4);
@@ -22,7 +24,9 @@ __global__ void fill_uniform_kernel(long n, uint64_t seed, uint64_t stream, floa
 }
 
 // f(x) = sign(x) sqrt|x| of x ~ N(0,1)            (NoisyLinear._scale_noise, model.py:32-37)
-__global__ void fill_scaled_normal_kernel(long n, uint64_t seed, uint64_t stream, float* __restrict__ out) {
+__global__ void fill_scaled_normal_kernel(long n, uint64_t seed, uint64_t stream, float* __restrict__ out,
+                                          const riqn_dyn_state* __restrict__ dyn) {
+  if (dyn) stream += dyn->rng_offset;
   const long i4 = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i4 * 4 >= n) return;
   const uint4 r = Philox::draw(seed, stream, (uint64_t)i4);
@@ -379,7 +383,8 @@ __global__ void embed_bwd_elem_kernel(int B, int Nq, int F, const float* __restr
 // ------------------------------------------------------------------------------------------------
 __global__ void adam_kernel(long n, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, float neg_step_size, float sqrt_bc2, float eps, float b1, float b2,
-                            float grad_scale) {
+                            float grad_scale, const riqn_dyn_state* __restrict__ dyn) {
+  if (dyn) { neg_step_size = dyn->adam_neg_step_size; sqrt_bc2 = dyn->adam_sqrt_bc2; }
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     const float gi = g[i] * grad_scale;
     const float mi = m[i] + (gi - m[i]) * (1.f - b1);           // lerp_, as torch
@@ -400,17 +405,19 @@ static inline int grid_for(long total, int per = 256) {
 
 using namespace riqn;
 
-RIQN_API int riqn_fill_uniform(long n, unsigned long long seed, unsigned long long stream_id, float* out, void* stream) {
+RIQN_API int riqn_fill_uniform(long n, unsigned long long seed, unsigned long long stream_id, float* out,
+                               const riqn_dyn_state* dyn, void* stream) {
   riqn::note_launches(1);
   if (n <= 0) return 0;
-  fill_uniform_kernel<<<riqn_cdiv((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(n, seed, stream_id, out);
+  fill_uniform_kernel<<<riqn_cdiv((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(n, seed, stream_id, out, dyn);
   return (int)cudaGetLastError();
 }
 
-RIQN_API int riqn_noisy_sample(long n, unsigned long long seed, unsigned long long stream_id, float* out, void* stream) {
+RIQN_API int riqn_noisy_sample(long n, unsigned long long seed, unsigned long long stream_id, float* out,
+                               const riqn_dyn_state* dyn, void* stream) {
   riqn::note_launches(1);
   if (n <= 0) return 0;
-  fill_scaled_normal_kernel<<<riqn_cdiv((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(n, seed, stream_id, out);
+  fill_scaled_normal_kernel<<<riqn_cdiv((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(n, seed, stream_id, out, dyn);
   return (int)cudaGetLastError();
 }
 
@@ -632,11 +639,12 @@ RIQN_API int riqn_iqn_loss_fwd_bwd(int batch, int n_tau, int n_tau_prime, int ac
 }
 
 RIQN_API int riqn_adam_step(long n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int step,
-                            float lr, float beta1, float beta2, float eps, float grad_scale, void* stream) {
+                            float lr, float beta1, float beta2, float eps, float grad_scale, const riqn_dyn_state* dyn,
+                            void* stream) {
   riqn::note_launches(1);
   const double bc1 = 1.0 - pow((double)beta1, (double)step);
   const double bc2 = 1.0 - pow((double)beta2, (double)step);
   adam_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(n, params, grads, exp_avg, exp_avg_sq, (float)(-(lr / bc1)),
-                                                            (float)sqrt(bc2), eps, beta1, beta2, grad_scale);
+                                                            (float)sqrt(bc2), eps, beta1, beta2, grad_scale, dyn);
   return (int)cudaGetLastError();
 }

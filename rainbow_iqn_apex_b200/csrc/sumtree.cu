@@ -21,7 +21,8 @@ namespace riqn {
 // samples[i] = a + (b - a) * u_i, a = i*seg, b = (i+1)*seg (CPython random.uniform), then shuffled
 // (redis_memory.py:276-287).  Single CTA; thread 0 runs the Fisher-Yates shuffle in shared memory.
 __global__ void stratified_kernel(int n, uint64_t seed, uint64_t stream, const double* __restrict__ tree,
-                                  double* __restrict__ values) {
+                                  double* __restrict__ values, const riqn_dyn_state* __restrict__ dyn) {
+  if (dyn) stream += dyn->rng_offset;
   // the shuffle: stratum s goes to output slot rank(key_s), keys = Philox draws (ties broken by index)
   extern __shared__ uint32_t keys[];
   const double seg = tree[0] / (double)n;
@@ -103,7 +104,8 @@ __global__ void sumtree_sample_kernel(int n, long C, int actor_cap, const double
 // is reported so the host can apply the reference's resample-first policy if it wants to.
 __global__ void is_weights_kernel(int n, const double* __restrict__ tree, const double* __restrict__ priorities,
                                   double capacity, double beta, double* __restrict__ w64, float* __restrict__ w32,
-                                  int* __restrict__ n_nonpositive) {
+                                  int* __restrict__ n_nonpositive, const riqn_dyn_state* __restrict__ dyn) {
+  if (dyn) { capacity = dyn->is_capacity; beta = dyn->is_beta; }
   __shared__ double red[32];
   __shared__ int cnt;
   if (threadIdx.x == 0) cnt = 0;
@@ -348,10 +350,10 @@ __global__ void frame_gather_kernel(int B, int actor_cap, int history, int n_ste
 using namespace riqn;
 
 RIQN_API int riqn_sumtree_stratified(int n, unsigned long long seed, unsigned long long stream_id, const double* tree,
-                                     double* values, void* stream) {
+                                     double* values, const riqn_dyn_state* dyn, void* stream) {
   riqn::note_launches(1);
   if (n <= 0 || n > 12000) return (int)cudaErrorInvalidValue;
-  stratified_kernel<<<1, 1024, sizeof(int) * n, (cudaStream_t)stream>>>(n, seed, stream_id, tree, values);
+  stratified_kernel<<<1, 1024, sizeof(int) * n, (cudaStream_t)stream>>>(n, seed, stream_id, tree, values, dyn);
   return (int)cudaGetLastError();
 }
 
@@ -368,10 +370,11 @@ RIQN_API int riqn_sumtree_sample(int n, long capacity, int actor_capacity, const
 }
 
 RIQN_API int riqn_sumtree_is_weights(int n, const double* tree, const double* priorities, double current_capacity,
-                                     double priority_weight, double* w64, float* w32, int* n_nonpositive, void* stream) {
+                                     double priority_weight, double* w64, float* w32, int* n_nonpositive,
+                                     const riqn_dyn_state* dyn, void* stream) {
   riqn::note_launches(1);
   is_weights_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(n, tree, priorities, current_capacity, priority_weight, w64,
-                                                          w32, n_nonpositive);
+                                                          w32, n_nonpositive, dyn);
   return (int)cudaGetLastError();
 }
 

@@ -19,7 +19,8 @@ STEP_LEARNER_STR = "step_learner:"     # rainbowiqn/constants.py:14
 class Learner(Agent):
     def __init__(self, args, action_space, redis_servor):
         super().__init__(args, action_space, redis_servor)
-        self.process_group = None  # set by parallel.DataParallelLearner
+        self.process_group = None  # set by parallel.make_data_parallel
+        self._graph = None         # CUDA-graph mode (enable_cuda_graph)
 
     def learn(self, mem_redis, mp_queue):
         sample = mem_redis.get_sample_from_mp_queue(mp_queue)
@@ -46,6 +47,106 @@ class Learner(Agent):
             torch.distributed.all_reduce(on._flat_grad, group=self.process_group)
         self.optimiser.step()                                                   # learner.py:24
         return loss
+
+    # ------------------------------------------------------------------ whole step: sample -> learn -> priority update
+    def learn_and_update(self, mem):
+        """One learner iteration against a device-resident ReplayMemory: prioritized sample, Learner.learn and
+        ReplayMemory.update_priorities of the sampled leaves (launch_learner.py:173-197 without the host queues).
+        Replays the captured CUDA graph when enable_cuda_graph(mem) was called.  Returns (tree_idxs, loss); in graph
+        mode these are static buffers that the next call overwrites."""
+        if self._graph is not None and mem is self._graph_mem:
+            dyn = self._dyn
+            nss, sbc = self.optimiser.bias_corrections(self.optimiser._step + 1)
+            dyn.write(nss, sbc, mem.transitions.get_current_capacity(), mem.priority_weight)
+            self._graph.replay()
+            self.optimiser._step += 1
+            return self._graph_out
+        idxs, loss = self.learn(mem, None)
+        mem.update_priorities(idxs, loss)
+        return idxs, loss
+
+    def _step_body(self, mem):
+        dyn = self._dyn
+        self.online_net.begin_step(dyn)
+        self.target_net.begin_step(dyn)
+        mem.transitions._draws_in_step = 0
+        idxs, loss = self.learn(mem, None)
+        mem.update_priorities(idxs, loss)
+        return idxs, loss
+
+    def enable_cuda_graph(self, mem, warmup=3):
+        """Capture learn_and_update(mem) in a CUDA graph (shapes are static: batch_size, N, N', K).  Everything that
+        changes between steps lives on the device: Philox stream offsets, Adam bias corrections, beta and the replay
+        fill are read from a riqn_dyn_state struct that is refreshed by one 32-byte async copy per step."""
+        from .dynstate import DynState
+        dev = self.online_net._flat.device
+        self._dyn = DynState(dev)
+        self.optimiser._dyn = self._dyn
+        mem.transitions._dyn = self._dyn
+        step0 = self.optimiser._step
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for i in range(warmup):                      # eager warm-up on the capture stream (allocator, attributes)
+                nss, sbc = self.optimiser.bias_corrections(self.optimiser._step + 1)
+                self._dyn.write(nss, sbc, mem.transitions.get_current_capacity(), mem.priority_weight)
+                self._step_body(mem)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        nss, sbc = self.optimiser.bias_corrections(self.optimiser._step + 1)
+        self._dyn.write(nss, sbc, mem.transitions.get_current_capacity(), mem.priority_weight)
+        with torch.cuda.graph(graph):
+            out = self._step_body(mem)
+        # the capture itself does not execute the step: undo the host-side counter it advanced, then run it once
+        self.optimiser._step = step0 + warmup
+        self._graph, self._graph_mem, self._graph_out = graph, mem, out
+        return self
+
+    def enable_batch_graph(self, mem, example):
+        """Second captured graph for minibatches that arrive from the HOST (the reference's mp-queue hand-off,
+        learner.py:16): static device input buffers, filled by async copies from pinned host tensors, then
+        learn_on_batch + update_priorities replayed.  ``example`` = (idxs, states, actions, returns, next_states,
+        nonterminals, weights) device tensors defining the shapes.  Requires enable_cuda_graph(mem) first."""
+        assert self._graph is not None and mem is self._graph_mem
+        self._bg_in = tuple(t.clone() for t in example)
+
+        def body():
+            self.online_net.begin_step(self._dyn)
+            self.target_net.begin_step(self._dyn)
+            idxs, st, ac, rt, nx, nt, w = self._bg_in
+            loss = self.learn_on_batch(st, ac, rt, nx, nt, w)
+            mem.update_priorities(idxs, loss)
+            return loss
+
+        step0 = self.optimiser._step
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                nss, sbc = self.optimiser.bias_corrections(self.optimiser._step + 1)
+                self._dyn.write(nss, sbc, mem.transitions.get_current_capacity(), mem.priority_weight)
+                body()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = body()
+        self.optimiser._step = step0 + 2
+        self._bgraph, self._bg_out = graph, out
+        return self
+
+    def learn_on_host_batch(self, host_batch):
+        """host_batch: pinned host tensors (idxs, states u8, actions, returns, next_states u8, nonterminals, weights).
+        H2D copies + one graph replay; returns the device loss (B,) (static buffer)."""
+        for d, h in zip(self._bg_in, host_batch):
+            d.copy_(h, non_blocking=True)
+        mem = self._graph_mem
+        nss, sbc = self.optimiser.bias_corrections(self.optimiser._step + 1)
+        self._dyn.write(nss, sbc, mem.transitions.get_current_capacity(), mem.priority_weight)
+        self._bgraph.replay()
+        self.optimiser._step += 1
+        return self._bg_out
 
     # north_star spellings
     update_target = Agent.update_target_net

@@ -65,6 +65,8 @@ class NoisyLinear(nn.Module):
         self._w_eff = None
         self._b_eff = None
         self._noise_calls = 0
+        self._calls_in_step = 0
+        self._dyn = None    # DynState in CUDA-graph mode (set by Learner.enable_cuda_graph)
         self._layer_id = 0  # distinct Philox streams per layer (set by DQN)
         self.reset_parameters()
 
@@ -92,10 +94,14 @@ class NoisyLinear(nn.Module):
         if eps_in is None:
             if seed is None:
                 seed = int(torch.randint(0, 2 ** 62, (1,)).item())
-            base = (self._layer_id << 40) + 2 * self._noise_calls
-            call("riqn_noisy_sample", self.in_features, seed, base, ptr(self._eps_in))
-            call("riqn_noisy_sample", self.out_features, seed, base + 1, ptr(self._eps_out))
+            dyn = self._dyn
+            # graph mode: static per-step index (the device-side rng_offset advances the stream every step)
+            idx = self._calls_in_step if dyn is not None else self._noise_calls
+            base = (self._layer_id << 40) + 2 * idx
+            call("riqn_noisy_sample", self.in_features, seed, base, ptr(self._eps_in), dyn.ptr() if dyn else None)
+            call("riqn_noisy_sample", self.out_features, seed, base + 1, ptr(self._eps_out), dyn.ptr() if dyn else None)
             self._noise_calls += 1
+            self._calls_in_step += 1
         else:
             self._eps_in.copy_(eps_in)
             self._eps_out.copy_(eps_out)
@@ -156,6 +162,8 @@ class DQN(nn.Module):
         for i, m in enumerate((self.fcnoisy_h_v, self.fcnoisy_h_a, self.fcnoisy_z_v, self.fcnoisy_z_a)):
             m._layer_id = i + 1
         self._tau_calls = 0
+        self._tau_in_step = 0
+        self._dyn = None
         self._tau_stream_offset = 0   # rank-private quantile stream under data parallelism
         self._rng_seed = int(torch.randint(0, 2 ** 62, (1,)).item())
         self._flatten()
@@ -309,10 +317,22 @@ class DQN(nn.Module):
             self._support_t = torch.linspace(self._v_min, self._v_max, self.atoms).to(dev)
         return self._support_t
 
+    def begin_step(self, dyn=None):
+        """Reset the per-step Philox stream indices (CUDA-graph mode keeps them static across replays)."""
+        self._dyn = dyn
+        self._tau_in_step = 0
+        for _, m in self.noisy_layers():
+            m._dyn = dyn
+            m._calls_in_step = 0
+
     def draw_quantiles(self, n):
         tau = torch.empty(n, 1, device=self._flat.device)
-        call("riqn_fill_uniform", n, self._rng_seed ^ 0x7A75, self._tau_stream_offset + self._tau_calls, ptr(tau))
+        dyn = getattr(self, "_dyn", None)
+        idx = self._tau_in_step if dyn is not None else self._tau_calls
+        call("riqn_fill_uniform", n, self._rng_seed ^ 0x7A75, self._tau_stream_offset + idx, ptr(tau),
+             dyn.ptr() if dyn else None)
         self._tau_calls += 1
+        self._tau_in_step += 1
         return tau
 
     # ------------------------------------------------------------------ forward pieces

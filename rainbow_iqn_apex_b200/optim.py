@@ -17,6 +17,7 @@ class Adam(torch.optim.Optimizer):
         self._bind()
         self._step = 0
         self.grad_scale = 1.0  # set to 1/world_size by the data-parallel learner
+        self._dyn = None       # DynState in CUDA-graph mode
 
     def _bind(self):
         ps = [p for g in self.param_groups for p in g["params"]]
@@ -55,7 +56,13 @@ class Adam(torch.optim.Optimizer):
         g = self.param_groups[0]
         call("riqn_adam_step", self._flat.numel(), ptr(self._flat), ptr(grad_flat), ptr(self._exp_avg),
              ptr(self._exp_avg_sq), self._step, float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]),
-             float(g["eps"]), float(self.grad_scale))
+             float(g["eps"]), float(self.grad_scale), self._dyn.ptr() if self._dyn is not None else None)
+
+    def bias_corrections(self, step):
+        """(-(lr / (1 - b1^t)), sqrt(1 - b2^t)) of step t, as torch.optim.Adam computes them."""
+        g = self.param_groups[0]
+        b1, b2 = g["betas"]
+        return -(g["lr"] / (1.0 - b1 ** step)), (1.0 - b2 ** step) ** 0.5
 
     def _rebind_after_move(self):
         old_m, old_v = self._exp_avg, self._exp_avg_sq

@@ -31,6 +31,8 @@ class SegmentTree:
         self.store_frames = store_frames
         self._rng_seed = int(torch.randint(0, 2 ** 62, (1,)).item())
         self._draws = 0
+        self._draws_in_step = 0
+        self._dyn = None
         self.initialize_redis_database()
 
     # -------------------------------------------------------------- init / bookkeeping
@@ -132,8 +134,12 @@ class SegmentTree:
         dev = self.device
         if samples is None:
             samples = torch.empty(batch_size, dtype=torch.float64, device=dev)
-            call("riqn_sumtree_stratified", batch_size, self._rng_seed, self._draws, ptr(self.tree), ptr(samples))
+            dyn = self._dyn
+            idx = self._draws_in_step if dyn is not None else self._draws
+            call("riqn_sumtree_stratified", batch_size, self._rng_seed, idx, ptr(self.tree), ptr(samples),
+                 dyn.ptr() if dyn else None)
             self._draws += 1
+            self._draws_in_step += 1
         else:
             samples = torch.as_tensor(samples, dtype=torch.float64).to(dev).contiguous()
         tree_idx = torch.empty(batch_size, dtype=torch.int64, device=dev)
@@ -172,7 +178,8 @@ class ReplayMemory:
         w32 = torch.empty(batch_size, dtype=torch.float32, device=self.device)
         self.last_nonpositive = torch.zeros(1, dtype=torch.int32, device=self.device)
         call("riqn_sumtree_is_weights", batch_size, ptr(tr.tree), ptr(pri), float(tr.get_current_capacity()),
-             float(self.priority_weight), ptr(w64), ptr(w32), ptr(self.last_nonpositive))
+             float(self.priority_weight), ptr(w64), ptr(w32), ptr(self.last_nonpositive),
+             tr._dyn.ptr() if tr._dyn is not None else None)
         return tree_idx, data_idx, pri, w64, w32
 
     def assemble(self, data_idx):

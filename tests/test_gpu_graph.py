@@ -1,0 +1,76 @@
+"""GPU: the CUDA-graph learner step (Learner.enable_cuda_graph) equals the eager step driven by the same device-resident
+per-step state (Philox offsets, Adam bias corrections, beta / capacity), and advances its randomness every replay."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import load_params, make_args
+from oracle import cases, network as net
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(dev, seed):
+    from rainbow_iqn_apex_b200 import Learner, ReplayMemory
+    torch.manual_seed(seed)
+    cfg = cases.iqn_cfg(16, 16, 8)
+    args = make_args(dev, 16, cfg, nb_actor=1, actor_capacity=512)
+    lr = Learner(args, 18, None)
+    load_params(lr.online_net, net.make_params(5))
+    lr.update_target_net()
+    mem = ReplayMemory(args, None)
+    rs = np.random.RandomState(1)
+    n = 512
+    mem.transitions.append_arrays(0, 0, np.arange(n) % 97, rs.randint(0, 256, (n, 84, 84)).astype(np.uint8),
+                                  rs.randint(0, 18, n), rs.randint(-1, 2, n).astype(np.float32), rs.uniform(size=n) < 0.03,
+                                  (rs.uniform(0.1, 1, n) ** 0.2).astype(np.float32))
+    for obj, sd in ((lr.online_net, 11), (lr.target_net, 12), (mem.transitions, 13)):
+        obj._rng_seed = sd
+    return lr, mem
+
+
+def test_graph_replay_matches_eager_with_same_dyn_state(cuda_dev):
+    from rainbow_iqn_apex_b200.dynstate import DynState
+    a, mem_a = _setup(cuda_dev, 0)
+    b, mem_b = _setup(cuda_dev, 0)
+    a.enable_cuda_graph(mem_a, warmup=2)              # 2 eager warm-up steps, then capture
+    # b: the same steps, all eager, through the same body / dyn protocol
+    b._dyn = DynState(cuda_dev)
+    b.optimiser._dyn = b._dyn
+    mem_b.transitions._dyn = b._dyn
+
+    def eager_step():
+        nss, sbc = b.optimiser.bias_corrections(b.optimiser._step + 1)
+        b._dyn.write(nss, sbc, mem_b.transitions.get_current_capacity(), mem_b.priority_weight)
+        return b._step_body(mem_b)
+
+    for _ in range(2):
+        eager_step()
+    b._dyn.epoch += 1                                  # the write issued right before the capture
+    losses = []
+    for i in range(3):
+        ia, la = a.learn_and_update(mem_a)
+        ib, lb = eager_step()
+        assert torch.equal(ia, ib)                     # same prioritized sample (device RNG driven by the same state)
+        assert torch.allclose(la, lb, rtol=1e-5, atol=1e-7)
+        losses.append(la.clone())
+    assert a.optimiser._step == b.optimiser._step == 5
+    assert torch.allclose(a.online_net._flat, b.online_net._flat, rtol=0, atol=1e-6)
+    assert torch.allclose(mem_a.transitions.tree, mem_b.transitions.tree, rtol=1e-6, atol=0)
+    assert not torch.equal(losses[0], losses[1])       # fresh noise / quantiles / samples every replay
+    assert torch.isfinite(torch.stack(losses)).all()
+    assert not torch.equal(a.online_net._flat, a.target_net._flat)
+
+
+def test_host_batch_graph(cuda_dev):
+    lr, mem = _setup(cuda_dev, 1)
+    lr.enable_cuda_graph(mem, warmup=2)
+    lr.enable_batch_graph(mem, tuple(t.contiguous() for t in mem.sample(16)))
+    host = tuple(t.contiguous().cpu().pin_memory() for t in mem.sample(16))
+    before = lr.online_net._flat.clone()
+    l1 = lr.learn_on_host_batch(host).clone()
+    l2 = lr.learn_on_host_batch(host).clone()
+    assert torch.isfinite(l1).all() and not torch.equal(l1, l2)
+    assert not torch.equal(before, lr.online_net._flat)
+    new_pri = mem.transitions.tree[host[0].to(cuda_dev)]
+    assert torch.allclose(new_pri.float(), l2.pow(0.2), rtol=1e-5)      # priorities of the batch were updated

@@ -151,7 +151,7 @@ def test_adam_matches_torch(cuda_dev):
         p_ref.grad = torch.from_numpy(g.copy())
         opt.step()
         gd = torch.from_numpy(g).to(cuda_dev)
-        call("riqn_adam_step", n, ptr(p), ptr(gd), ptr(m), ptr(v), step, 5e-5, 0.9, 0.999, 3.125e-4, 1.0)
+        call("riqn_adam_step", n, ptr(p), ptr(gd), ptr(m), ptr(v), step, 5e-5, 0.9, 0.999, 3.125e-4, 1.0, None)
         assert np.allclose(p.cpu().numpy(), p_ref.detach().numpy(), rtol=0, atol=2.5e-7)   # <= 1 fp32 ulp of |p| < 4
         upd, upd_ref = p.cpu().numpy() - p0, p_ref.detach().numpy() - p0
         assert rel_err(upd, upd_ref) < 5e-3
@@ -162,14 +162,14 @@ def test_device_rng_statistics(cuda_dev):
     call, ptr = _call()
     n = 1 << 20
     u = torch.empty(n, device=cuda_dev)
-    call("riqn_fill_uniform", n, 1234, 0, ptr(u))
+    call("riqn_fill_uniform", n, 1234, 0, ptr(u), None)
     u2 = torch.empty(n, device=cuda_dev)
-    call("riqn_fill_uniform", n, 1234, 1, ptr(u2))
+    call("riqn_fill_uniform", n, 1234, 1, ptr(u2), None)
     a = u.cpu().numpy().astype(np.float64)
     assert 0 < a.min() and a.max() < 1 and abs(a.mean() - 0.5) < 2e-3 and abs(a.var() - 1 / 12) < 1e-3
     assert abs(np.corrcoef(a, u2.cpu().numpy())[0, 1]) < 5e-3
     z = torch.empty(n, device=cuda_dev)
-    call("riqn_noisy_sample", n, 99, 0, ptr(z))
+    call("riqn_noisy_sample", n, 99, 0, ptr(z), None)
     f = z.cpu().numpy().astype(np.float64)
     x = np.sign(f) * f * f                      # invert f(x) = sign(x) sqrt|x|  -> N(0,1)
     assert abs(x.mean()) < 5e-3 and abs(x.var() - 1) < 1e-2 and abs((x ** 4).mean() - 3) < 0.1

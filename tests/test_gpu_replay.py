@@ -158,14 +158,14 @@ def test_device_stratified_sampler(cuda_dev):
     from rainbow_iqn_apex_b200._lib import call, ptr
     n = 2560
     vals = torch.empty(n, dtype=torch.float64, device=cuda_dev)
-    call("riqn_sumtree_stratified", n, 42, 0, ptr(tr.tree), ptr(vals))
+    call("riqn_sumtree_stratified", n, 42, 0, ptr(tr.tree), ptr(vals), None)
     v = vals.cpu().numpy()
     seg = tr.total() / n
     strata = np.floor(v / seg).astype(np.int64)
     assert sorted(strata.tolist()) == list(range(n))
     assert not np.array_equal(strata, np.arange(n))          # shuffled
     vals2 = torch.empty(n, dtype=torch.float64, device=cuda_dev)
-    call("riqn_sumtree_stratified", n, 42, 1, ptr(tr.tree), ptr(vals2))
+    call("riqn_sumtree_stratified", n, 42, 1, ptr(tr.tree), ptr(vals2), None)
     assert not np.array_equal(v, vals2.cpu().numpy())
     out = mem.sample(512)
     assert out[1].shape == (512, 4, 84, 84) and out[1].dtype == torch.uint8 and out[6].max().item() == 1.0
