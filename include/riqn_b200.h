@@ -159,11 +159,17 @@ int riqn_quantile_embed_bwd_tc(int batch, int num_quantiles, int embed_dim, int 
 int riqn_dueling_fwd(long rows, int hidden, int action_space, const float* h, const float* wz, const float* bz,
                      float* q, void* stream);
 /* Backward for the gathered action: dq[r, actions[b]] = dtheta[r] * gscale[b].  Writes dh (rows, 2*hidden),
- * already masked by h > 0, and dz (rows, 32) = [dv, da_0.., 0..] for riqn_z_wgrad. */
+ * already masked by h > 0, and dz (rows, 32) = [dv, da_0.., 0..] for riqn_z_wgrad; dz_t_bf16 (may be NULL) is the
+ * bf16 transposed (32, rows) image for riqn_z_wgrad_tc. */
 int riqn_dueling_bwd(long rows, int batch, int hidden, int action_space, const float* h, const float* wz,
                      const float* dtheta, const float* gscale, const long long* actions, float* dh, float* dz,
-                     void* stream);
+                     void* dz_t_bf16, void* stream);
 /* Parameter gradients of the two z-layers (accumulated): dwz_scratch 32*2*hidden floats, dbz_scratch 32. */
+/* Same with the reduction dz^T h on the tensor cores: dz_t (32, rows) and h_t (2*hidden, rows) bf16 (rows % 8 == 0). */
+int riqn_z_wgrad_tc(long rows, int hidden, int action_space, const void* dz_t, const void* h_t, const float* dz,
+                    float* dwz_scratch, float* dbz_scratch, const float* eps_w_zv, const float* eps_b_zv,
+                    const float* eps_w_za, const float* eps_b_za, float* g_mu_zv, float* g_sig_zv, float* g_bmu_zv,
+                    float* g_bsig_zv, float* g_mu_za, float* g_sig_za, float* g_bmu_za, float* g_bsig_za, void* stream);
 int riqn_z_wgrad(long rows, int hidden, int action_space, const float* dz, const float* h, float* dwz_scratch,
                  float* dbz_scratch, const float* eps_w_zv, const float* eps_b_zv, const float* eps_w_za,
                  const float* eps_b_za, float* g_mu_zv, float* g_sig_zv, float* g_bmu_zv, float* g_bsig_zv,
@@ -272,10 +278,11 @@ int riqn_frame_gather(int batch, int actor_capacity, int history, int n_step, co
 int riqn_split_bf16(long rows, int cols, const float* src, void* hi, void* lo, void* hi_t, void* lo_t, void* stream);
 /* C (+)= A B^T with A (M,K), B (N,K) row-major bf16, K % 8 == 0, fp32 accumulation in TMEM.  a_lo/b_lo non-NULL
  * selects the split-bf16 x3 (fp32-faithful) product.  epilogue: 0 store, 1 relu(acc+bias[n]), 2 atomicAdd into C,
- * 3 atomicAdd into C and acc*eps[m,n] into out2 (NoisyLinear dmu / dsigma).  split_k > 1 needs 2 or 3. */
+ * 3 atomicAdd into C and acc*eps[m,n] into out2 (NoisyLinear dmu / dsigma).  split_k > 1 needs 2 or 3.
+ * c_t_bf16 (may be NULL; epilogue 1 only): bf16 transposed (N, M) image of the result. */
 int riqn_gemm_bf16_tc(int M, int N, int K, const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo,
                       float* c, long ldc, int epilogue, const float* bias, float* out2, const float* eps, int split_k,
-                      void* stream);
+                      void* c_t_bf16, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Test hook: plain strided fp32 product C[m,n] = sum_k A[m*sAm + k*sAk] * B[n*sBn + k*sBk].

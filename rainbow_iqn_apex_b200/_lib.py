@@ -42,8 +42,9 @@ SIGNATURES = {
     "riqn_quantile_embed_bwd_tc": [C.c_int, C.c_int, C.c_int, C.c_int] + [_P] * 10,
     "riqn_quantile_embed_bwd": [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P],
     "riqn_dueling_fwd": [C.c_long, C.c_int, C.c_int, _P, _P, _P, _P, _P],
-    "riqn_dueling_bwd": [C.c_long, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P],
+    "riqn_dueling_bwd": [C.c_long, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "riqn_z_wgrad": [C.c_long, C.c_int, C.c_int] + [_P] * 17,
+    "riqn_z_wgrad_tc": [C.c_long, C.c_int, C.c_int] + [_P] * 18,
     "riqn_argmax_mean": [C.c_int, C.c_int, C.c_int, _P, _P, _P],
     "riqn_iqn_loss_fwd_bwd": [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, C.c_float, C.c_float,
                               _P, _P, _P, _P, _P],
@@ -63,7 +64,7 @@ SIGNATURES = {
     "riqn_replay_append": [C.c_int, C.c_int, C.c_int, C.c_int] + [_P] * 11,
     "riqn_frame_gather": [C.c_int, C.c_int, C.c_int, C.c_int] + [_P] * 12,
     "riqn_split_bf16": [C.c_long, C.c_int, _P, _P, _P, _P, _P, _P],
-    "riqn_gemm_bf16_tc": [C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, C.c_long, C.c_int, _P, _P, _P, C.c_int, _P],
+    "riqn_gemm_bf16_tc": [C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, C.c_long, C.c_int, _P, _P, _P, C.c_int, _P, _P],
     "riqn_gemm_f32": [C.c_int, C.c_int, C.c_int, _P, C.c_long, C.c_long, _P, C.c_long, C.c_long, _P, C.c_long, _P],
 }
 

@@ -76,6 +76,45 @@ __global__ void col2im_kernel(riqn_conv_geom g, const float* __restrict__ dcol, 
   }
 }
 
+// Same scatter with coalesced reads: one block per (sample, chunk of CC input channels) streams that sample's dcol rows
+// (the CC*KH*KW gradients of a row are contiguous) and accumulates into a shared-memory image tile, written out once.
+__global__ void col2im_tile_kernel(riqn_conv_geom g, int CC, const float* __restrict__ dcol, float* __restrict__ din) {
+  extern __shared__ float acc[];     // CC * H * W
+  const int K = g.Cin * g.KH * g.KW, khw = g.KH * g.KW, ohw = g.OH * g.OW, hw = g.H * g.W;
+  const int chunks = g.Cin / CC;
+  const long b = blockIdx.x / chunks;
+  const int c0 = (blockIdx.x % chunks) * CC;
+  for (int i = threadIdx.x; i < CC * hw; i += blockDim.x) acc[i] = 0.f;
+  __syncthreads();
+  const int per_row = CC * khw;
+  const float* base = dcol + b * ohw * (long)K + (long)c0 * khw;
+  for (int e = threadIdx.x; e < ohw * per_row; e += blockDim.x) {
+    const int m = e / per_row, j = e - m * per_row;
+    const int c = j / khw, r = j - c * khw;
+    const int kh = r / g.KW, kw = r - kh * g.KW;
+    const int oh = m / g.OW, ow = m - oh * g.OW;
+    const int ih = oh * g.stride + kh - g.pad, iw = ow * g.stride + kw - g.pad;
+    if (ih >= 0 && ih < g.H && iw >= 0 && iw < g.W) atomicAdd(&acc[c * hw + ih * g.W + iw], base[(long)m * K + j]);
+  }
+  __syncthreads();
+  float* out = din + (b * g.Cin + c0) * hw;
+  for (int i = threadIdx.x; i < CC * hw; i += blockDim.x) out[i] = acc[i];
+}
+
+static int col2im(const riqn_conv_geom* g, const float* dcol, float* din, cudaStream_t s) {
+  const int hw = g->H * g->W;
+  int CC = g->Cin;
+  while (CC > 1 && ((long)CC * hw * 4 > 16 * 1024 || g->Cin % CC)) --CC;
+  if ((long)CC * hw * 4 <= 48 * 1024) {
+    col2im_tile_kernel<<<g->B * (g->Cin / CC), 256, (size_t)CC * hw * 4, s>>>(*g, CC, dcol, din);
+  } else {
+    long total = (long)g->B * g->Cin * hw;
+    long blocks = (total + 255) / 256;
+    col2im_kernel<<<(int)(blocks > 148L * 32 ? 148L * 32 : blocks), 256, 0, s>>>(*g, dcol, din);
+  }
+  return (int)cudaGetLastError();
+}
+
 // out[n] += sum_m X[m, n]
 __global__ void colsum_atomic_kernel(long M, int N, const float* __restrict__ X, float* __restrict__ out, int rows_per_block) {
   const int n = blockIdx.x * 128 + (threadIdx.x & 127);
@@ -299,8 +338,8 @@ RIQN_API int riqn_conv_bwd(const riqn_conv_geom* g, const float* dout, const flo
     // dcol[m, k] = sum_c dY[m, c] * W[c, k]
     rc = gemm_f32((int)M, K, g->Cout, dY, g->Cout, 1, w, 1, K, dcol, K, EPI_STORE, e, 1, s);
     if (rc) return rc;
-    col2im_kernel<<<grid_for((long)g->B * g->Cin * g->H * g->W), 256, 0, s>>>(*g, dcol, din);
-    RIQN_LAUNCH_CHECK();
+    rc = col2im(g, dcol, din, s);
+    if (rc) return rc;
   }
   return 0;
 }
@@ -353,8 +392,8 @@ RIQN_API int riqn_conv_bwd_tc(const riqn_conv_geom* g, const float* dout, const 
     rc = gemm_bf16_tc((int)M, K, g->Cout, (const bf16*)dY_hi, nullptr, (const bf16*)wT_hi, nullptr, dcol, K, TC_STORE, nullptr,
                       nullptr, nullptr, 1, s, nullptr);
     if (rc) return rc;
-    col2im_kernel<<<grid_for((long)g->B * g->Cin * g->H * g->W), 256, 0, s>>>(*g, dcol, din);
-    RIQN_LAUNCH_CHECK();
+    rc = col2im(g, dcol, din, s);
+    if (rc) return rc;
   }
   return 0;
 }

@@ -254,6 +254,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
                   o.z = fmaxf(o.z + b.z, 0.f); o.w = fmaxf(o.w + b.w, 0.f);
                 }
                 *reinterpret_cast<float4*>(crow + j) = o;
+                if (EPI == TC_BIAS_RELU && p.o_hiT) {   // bf16 (N, M) image: lanes = consecutive m -> coalesced
+                  p.o_hiT[(long)(n0 + j) * p.M + m] = __float2bfloat16_rn(o.x);
+                  p.o_hiT[(long)(n0 + j + 1) * p.M + m] = __float2bfloat16_rn(o.y);
+                  p.o_hiT[(long)(n0 + j + 2) * p.M + m] = __float2bfloat16_rn(o.z);
+                  p.o_hiT[(long)(n0 + j + 3) * p.M + m] = __float2bfloat16_rn(o.w);
+                }
               }
             } else {
 #pragma unroll
@@ -262,6 +268,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
                   float o = __uint_as_float(v[j]);
                   if (EPI == TC_BIAS_RELU) o = fmaxf(o + p.bias[n0 + j], 0.f);
                   crow[j] = o;
+                  if (EPI == TC_BIAS_RELU && p.o_hiT) p.o_hiT[(long)(n0 + j) * p.M + m] = __float2bfloat16_rn(o);
                 }
               }
             }
@@ -500,8 +507,10 @@ RIQN_API int riqn_split_bf16(long rows, int cols, const float* src, void* hi, vo
 
 RIQN_API int riqn_gemm_bf16_tc(int M, int N, int K, const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo,
                                float* c, long ldc, int epilogue, const float* bias, float* out2, const float* eps,
-                               int split_k, void* stream) {
+                               int split_k, void* c_t_bf16, void* stream) {
   riqn::note_launches(1);
+  TcExtra ex;
+  ex.o_hiT = (bf16*)c_t_bf16;
   return gemm_bf16_tc(M, N, K, (const bf16*)a_hi, (const bf16*)a_lo, (const bf16*)b_hi, (const bf16*)b_lo, c, ldc, epilogue,
-                      bias, out2, eps, split_k, (cudaStream_t)stream, nullptr);
+                      bias, out2, eps, split_k, (cudaStream_t)stream, &ex);
 }

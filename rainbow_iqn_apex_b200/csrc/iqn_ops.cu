@@ -288,7 +288,7 @@ template <int HID>
 __global__ void z_dueling_bwd_kernel(long R, int B, int A, const float* __restrict__ H, const float* __restrict__ Wz,
                                      const float* __restrict__ dtheta, const float* __restrict__ gscale,
                                      const int64_t* __restrict__ actions, float* __restrict__ dH,
-                                     float* __restrict__ dz) {
+                                     float* __restrict__ dz, __nv_bfloat16* __restrict__ dzT) {
   extern __shared__ float sW[];  // (1+A)*HID weights + HID colmean
   float* wbar = sW + (1 + A) * HID;
   for (int i = threadIdx.x; i < (1 + A) * HID; i += blockDim.x) sW[i] = Wz[i];
@@ -315,6 +315,7 @@ __global__ void z_dueling_bwd_kernel(long R, int B, int A, const float* __restri
     if (lane == 0) z = g;
     else if (lane <= A) z = g * ((lane - 1 == act ? 1.f : 0.f) - 1.f / (float)A);
     dz[r * 32 + lane] = z;
+    if (dzT) dzT[(long)lane * R + r] = __float2bfloat16_rn(z);
   }
 }
 
@@ -577,7 +578,7 @@ RIQN_API int riqn_dueling_fwd(long rows, int hidden, int action_space, const flo
 
 RIQN_API int riqn_dueling_bwd(long rows, int batch, int hidden, int action_space, const float* h, const float* wz,
                               const float* dtheta, const float* gscale, const long long* actions, float* dh, float* dz,
-                              void* stream) {
+                              void* dz_t_bf16, void* stream) {
   riqn::note_launches(1);
   if (hidden != 512 || action_space > 31) return (int)cudaErrorInvalidValue;
   const size_t smem = sizeof(float) * ((1 + action_space) * hidden + hidden);
@@ -587,7 +588,7 @@ RIQN_API int riqn_dueling_bwd(long rows, int batch, int hidden, int action_space
     attr = true;
   }
   z_dueling_bwd_kernel<512><<<148 * 4, 256, smem, (cudaStream_t)stream>>>(rows, batch, action_space, h, wz, dtheta, gscale,
-                                                                       (const int64_t*)actions, dh, dz);
+                                                                       (const int64_t*)actions, dh, dz, (__nv_bfloat16*)dz_t_bf16);
   return (int)cudaGetLastError();
 }
 
@@ -604,6 +605,31 @@ RIQN_API int riqn_z_wgrad(long rows, int hidden, int action_space, const float* 
   int split = 32;
   if ((long)split * 64 > rows) split = (int)((rows + 63) / 64);
   int rc = gemm_f32(32, W, (int)rows, dz, 1, 32, h, 1, W, dwz_scratch, W, EPI_ATOMIC, e, split, s);
+  if (rc) return rc;
+  rc = colsum_atomic(rows, 32, dz, dbz_scratch, s);
+  if (rc) return rc;
+  z_wgrad_finish_kernel<<<riqn_cdiv((long)action_space * hidden, 256), 256, 0, s>>>(
+      action_space, hidden, dwz_scratch, dbz_scratch, eps_w_zv, eps_b_zv, eps_w_za, eps_b_za, g_mu_zv, g_sig_zv, g_bmu_zv,
+      g_bsig_zv, g_mu_za, g_sig_za, g_bmu_za, g_bsig_za);
+  return (int)cudaGetLastError();
+}
+
+RIQN_API int riqn_z_wgrad_tc(long rows, int hidden, int action_space, const void* dz_t, const void* h_t, const float* dz,
+                             float* dwz_scratch, float* dbz_scratch, const float* eps_w_zv, const float* eps_b_zv,
+                             const float* eps_w_za, const float* eps_b_za, float* g_mu_zv, float* g_sig_zv, float* g_bmu_zv,
+                             float* g_bsig_zv, float* g_mu_za, float* g_sig_za, float* g_bmu_za, float* g_bsig_za,
+                             void* stream) {
+  riqn::note_launches(3);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int W = 2 * hidden;
+  if (rows % 8) return (int)cudaErrorInvalidValue;
+  RIQN_CUDA(cudaMemsetAsync(dwz_scratch, 0, sizeof(float) * 32 * W, s));
+  RIQN_CUDA(cudaMemsetAsync(dbz_scratch, 0, sizeof(float) * 32, s));
+  const int n_tiles = (W + 255) / 256;
+  const int split = (148 + n_tiles - 1) / n_tiles;
+  // dWz[z, j] = sum_r dz[r, z] * h[r, j]
+  int rc = gemm_bf16_tc(32, W, (int)rows, (const __nv_bfloat16*)dz_t, nullptr, (const __nv_bfloat16*)h_t, nullptr, dwz_scratch, W,
+                        TC_ATOMIC, nullptr, nullptr, nullptr, split, s, nullptr);
   if (rc) return rc;
   rc = colsum_atomic(rows, 32, dz, dbz_scratch, s);
   if (rc) return rc;

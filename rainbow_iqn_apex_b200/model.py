@@ -416,8 +416,9 @@ class DQN(nn.Module):
             if need_x32:   # fp32 cos for the CUDA-core dW_e product
                 call("riqn_quantile_embed_fwd", B, num_quantiles, E, FEAT, ptr(tau), ptr(feat), ptr(self.iqn_fc.weight),
                      ptr(self.iqn_fc.bias), ptr(cosv), ptr(xt))
+            tc["hT"] = bf(2 * hid, R) if bwd_tc else None      # bf16 (1024, R) image of h for the z-layer weight gradient
             call("riqn_gemm_bf16_tc", R, 2 * hid, FEAT, ptr(tc["x_hi"]), ptr(tc["x_lo"]), ptr(self._w_hi),
-                 ptr(self._w_lo) if x3 else None, ptr(h), 2 * hid, 1, ptr(self._b_eff_h), None, None, 1)
+                 ptr(self._w_lo) if x3 else None, ptr(h), 2 * hid, 1, ptr(self._b_eff_h), None, None, 1, ptr(tc["hT"]))
         q = torch.empty(R, A, device=dev)
         call("riqn_dueling_fwd", R, hid, A, ptr(h), ptr(self._w_eff_z), ptr(self._b_eff_z), ptr(q))
         if keep is not None:
@@ -453,18 +454,24 @@ class DQN(nn.Module):
         gv = self.grad_view
         dh = torch.empty(R, 2 * hid, device=dev)
         dz = torch.empty(R, 32, device=dev)
+        tc = keep.get("tc")
+        z_tc = bool(keep["head_bwd_tc"]) and tc is not None and tc.get("hT") is not None
+        dzT = torch.empty(32, R, dtype=torch.bfloat16, device=dev) if z_tc else None
         call("riqn_dueling_bwd", R, B, hid, A, ptr(keep["h"]), ptr(self._w_eff_z), ptr(dtheta), ptr(gscale),
-             ptr(actions), ptr(dh), ptr(dz))
+             ptr(actions), ptr(dh), ptr(dz), ptr(dzT))
         dwz = torch.empty(32, 2 * hid, device=dev)
         dbz = torch.empty(32, device=dev)
-        call("riqn_z_wgrad", R, hid, A, ptr(dz), ptr(keep["h"]), ptr(dwz), ptr(dbz),
-             ptr(zv.weight_epsilon), ptr(zv.bias_epsilon), ptr(za.weight_epsilon), ptr(za.bias_epsilon),
-             ptr(gv(zv.weight_mu)), ptr(gv(zv.weight_sigma)), ptr(gv(zv.bias_mu)), ptr(gv(zv.bias_sigma)),
-             ptr(gv(za.weight_mu)), ptr(gv(za.weight_sigma)), ptr(gv(za.bias_mu)), ptr(gv(za.bias_sigma)))
+        zargs = (ptr(dwz), ptr(dbz), ptr(zv.weight_epsilon), ptr(zv.bias_epsilon), ptr(za.weight_epsilon),
+                 ptr(za.bias_epsilon), ptr(gv(zv.weight_mu)), ptr(gv(zv.weight_sigma)), ptr(gv(zv.bias_mu)),
+                 ptr(gv(zv.bias_sigma)), ptr(gv(za.weight_mu)), ptr(gv(za.weight_sigma)), ptr(gv(za.bias_mu)),
+                 ptr(gv(za.bias_sigma)))
+        if z_tc:
+            call("riqn_z_wgrad_tc", R, hid, A, ptr(dzT), ptr(tc["hT"]), ptr(dz), *zargs)
+        else:
+            call("riqn_z_wgrad", R, hid, A, ptr(dz), ptr(keep["h"]), *zargs)
         dbs = torch.empty(2 * hid, device=dev)
         dx = torch.empty(R, FEAT, device=dev)
         bwd = PRECISION["bwd"]
-        tc = keep.get("tc")
         # [h_v | h_a] are adjacent in every arena, so one (2*hid, 3136) product serves both layers
         if not keep["head_bwd_tc"]:
             call("riqn_noisy_linear_wgrad", R, FEAT, 2 * hid, ptr(dh), ptr(keep["xt"]), ptr(hv.weight_epsilon),
@@ -480,12 +487,12 @@ class DQN(nn.Module):
             # dW[o, i] = sum_r dh[r, o] x[r, i]  -> dmu += dW, dsigma += dW * eps   (split-K, atomics)
             call("riqn_gemm_bf16_tc", 2 * hid, FEAT, R, ptr(dh_hiT), ptr(dh_loT), ptr(tc["x_hiT"]),
                  ptr(tc["x_loT"]) if b3 else None, ptr(gv(hv.weight_mu)), FEAT, 3, None, ptr(gv(hv.weight_sigma)),
-                 ptr(hv.weight_epsilon), WGRAD_SPLIT_K)
+                 ptr(hv.weight_epsilon), WGRAD_SPLIT_K, None)
             call("riqn_noisy_bias_grad", R, 2 * hid, ptr(dh), ptr(hv.bias_epsilon), ptr(dbs), ptr(gv(hv.bias_mu)),
                  ptr(gv(hv.bias_sigma)))
             # dx[r, i] = sum_o dh[r, o] W_eff[o, i]
             call("riqn_gemm_bf16_tc", R, FEAT, 2 * hid, ptr(dh_hi), ptr(dh_lo), ptr(self._w_hiT),
-                 ptr(self._w_loT) if b3 else None, ptr(dx), FEAT, 0, None, None, None, 1)
+                 ptr(self._w_loT) if b3 else None, ptr(dx), FEAT, 0, None, None, None, 1, None)
         dfeat = torch.empty(B, FEAT, device=dev)
         if keep["emb_bwd_tc"]:
             dpreT = torch.empty(FEAT, R, dtype=torch.bfloat16, device=dev)

