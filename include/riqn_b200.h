@@ -80,7 +80,16 @@ int riqn_conv_fwd_tc(const riqn_conv_geom* g, const void* in, int in_is_u8, cons
 /* Backward on the tensor cores (bf16 operands, fp32 accumulate): wT_hi (K, Cout) bf16; dY_hi (M, Cout) and dYT_hi
  * (Cout, M) bf16 workspaces; dcol fp32 (M, K) workspace; dw/dbias accumulated; din may be NULL. */
 int riqn_conv_bwd_tc(const riqn_conv_geom* g, const float* dout, const float* out, const void* colT_hi, const void* wT_hi,
-                     void* dY_hi, void* dYT_hi, float* dcol, float* dw, float* dbias, float* din, void* stream);
+                     void* dY_hi, void* dYT_hi, float* dcol, float* dw, float* dbias, float* din, float wgrad_scale,
+                     void* stream);
+/* First layer on raw uint8 frames: pixel values 0..255 are exact in bf16, so the im2col operand has no lo image and the
+ * reference's /255 (redis_memory.py:527-536) is folded into the weights: ws_hi / ws_lo = bf16 images of weight/255
+ * (ws_lo == NULL: single-bf16 product).  col_px (M, K) and colT_px (K, M; may be NULL) hold pixel values; pass
+ * wgrad_scale = 1/255 to riqn_conv_bwd_tc when it consumes colT_px.  in: 16-byte aligned, in_bstride % 16 == 0. */
+int riqn_conv_fwd_tc_u8(const riqn_conv_geom* g, const unsigned char* in, const void* ws_hi, const void* ws_lo,
+                        const float* bias, void* col_px, void* colT_px, float* out, void* stream);
+/* split of (src * scale): bf16 hi / lo images of a scaled matrix (e.g. weight/255). */
+int riqn_split_bf16_scaled(long rows, int cols, const float* src, float scale, void* hi, void* lo, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Randomness                       replaces torch normal_/uniform_ draws, model.py:32-37 and :131-134

@@ -228,6 +228,56 @@ __global__ void im2col_bf16_u8_kernel(riqn_conv_geom g, const uint8_t* __restric
   }
 }
 
+// Raw-pixel im2col for the first layer: one block per sample stages the uint8 frame stack in shared memory (coalesced
+// 16-byte loads), then writes col (M, K) -- and colT (K, M) for the backward -- with the pixel VALUES 0..255 as bf16
+// (exact); the 1/255 of the reference (redis_memory.py:527-536) is folded into the weights / the gradient scale.
+__global__ void im2col_u8_staged_kernel(riqn_conv_geom g, const uint8_t* __restrict__ in, bf16* __restrict__ col,
+                                        bf16* __restrict__ colT) {
+  extern __shared__ __align__(16) uint8_t img[];
+  const int chw = g.Cin * g.H * g.W, K = g.Cin * g.KH * g.KW, K8 = K / 8, ohw = g.OH * g.OW;
+  const long b = blockIdx.x;
+  const uint4* src = reinterpret_cast<const uint4*>(in + b * g.in_bstride);
+  for (int i = threadIdx.x; i < chw / 16; i += blockDim.x) reinterpret_cast<uint4*>(img)[i] = src[i];
+  __syncthreads();
+  auto px = [&](int c, int ih, int iw) -> uint32_t {
+    if (ih < 0 || ih >= g.H || iw < 0 || iw >= g.W) return 0u;
+    return __float_as_uint((float)img[(c * g.H + ih) * g.W + iw]) >> 16;     // exact bf16 bits of 0..255
+  };
+  if (col) {
+    for (int item = threadIdx.x; item < ohw * K8; item += blockDim.x) {
+      const int m = item / K8, k0 = (item - m * K8) * 8;
+      const int oh = m / g.OW, ow = m - oh * g.OW;
+      int kw = k0 % g.KW, kh = (k0 / g.KW) % g.KH, c = k0 / (g.KW * g.KH);
+      const int ih0 = oh * g.stride - g.pad, iw0 = ow * g.stride - g.pad;
+      uint32_t e[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        e[t] = px(c, ih0 + kh, iw0 + kw);
+        if (++kw == g.KW) { kw = 0; if (++kh == g.KH) { kh = 0; ++c; } }
+      }
+      *reinterpret_cast<uint4*>(col + (b * ohw + m) * K + k0) =
+          make_uint4(e[0] | (e[1] << 16), e[2] | (e[3] << 16), e[4] | (e[5] << 16), e[6] | (e[7] << 16));
+    }
+  }
+  if (colT) {
+    const long M = (long)g.B * ohw;
+    const int M8 = ohw / 8;
+    for (int item = threadIdx.x; item < K * M8; item += blockDim.x) {
+      const int k = item / M8, m0 = (item - k * M8) * 8;
+      const int kw = k % g.KW, kh = (k / g.KW) % g.KH, c = k / (g.KW * g.KH);
+      int oh = m0 / g.OW, ow = m0 - oh * g.OW;
+      uint32_t e[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        e[t] = px(c, oh * g.stride + kh - g.pad, ow * g.stride + kw - g.pad);
+        if (++ow == g.OW) { ow = 0; ++oh; }
+      }
+      *reinterpret_cast<uint4*>(colT + (long)k * M + b * ohw + m0) =
+          make_uint4(e[0] | (e[1] << 16), e[2] | (e[3] << 16), e[4] | (e[5] << 16), e[6] | (e[7] << 16));
+    }
+  }
+}
+
 // colT (K, M): one thread = 8 consecutive m of one k  (M % 8 == 0)
 template <typename T>
 __global__ void im2col_bf16_t_kernel(riqn_conv_geom g, const T* __restrict__ in, bf16* __restrict__ hiT) {
@@ -369,9 +419,31 @@ RIQN_API int riqn_conv_fwd_tc(const riqn_conv_geom* g, const void* in, int in_is
                       col_lo ? (const bf16*)w_lo : nullptr, out, g->Cout, TC_BIAS_RELU_NCHW, bias, nullptr, nullptr, 1, s, &ex);
 }
 
+// First layer on raw uint8 pixels: A = pixel values (exact in bf16, no lo image), B = bf16 hi (+lo) of weight/255.
+RIQN_API int riqn_conv_fwd_tc_u8(const riqn_conv_geom* g, const unsigned char* in, const void* ws_hi, const void* ws_lo,
+                                 const float* bias, void* col_px, void* colT_px, float* out, void* stream) {
+  riqn::note_launches(2);
+  cudaStream_t s = (cudaStream_t)stream;
+  const long M = (long)g->B * g->OH * g->OW;
+  const int K = g->Cin * g->KH * g->KW, chw = g->Cin * g->H * g->W, ohw = g->OH * g->OW;
+  if (K % 8 || chw % 16 || g->in_bstride % 16 || (reinterpret_cast<uintptr_t>(in) & 15) || (colT_px && ohw % 8) || chw > 96 * 1024)
+    return (int)cudaErrorInvalidValue;
+  static bool attr = false;
+  if (!attr) {
+    RIQN_CUDA(cudaFuncSetAttribute(im2col_u8_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    attr = true;
+  }
+  im2col_u8_staged_kernel<<<g->B, 256, chw, s>>>(*g, in, (bf16*)col_px, (bf16*)colT_px);
+  RIQN_LAUNCH_CHECK();
+  TcExtra ex;
+  ex.ohw = ohw;
+  return gemm_bf16_tc((int)M, g->Cout, K, (const bf16*)col_px, nullptr, (const bf16*)ws_hi, (const bf16*)ws_lo, out, g->Cout,
+                      TC_BIAS_RELU_NCHW, bias, nullptr, nullptr, 1, s, &ex);
+}
+
 RIQN_API int riqn_conv_bwd_tc(const riqn_conv_geom* g, const float* dout, const float* out, const void* colT_hi,
                               const void* wT_hi, void* dY_hi, void* dYT_hi, float* dcol, float* dw, float* dbias, float* din,
-                              void* stream) {
+                              float wgrad_scale, void* stream) {
   riqn::note_launches(din ? 4 : 2);
   cudaStream_t s = (cudaStream_t)stream;
   const long M = (long)g->B * g->OH * g->OW;
@@ -384,8 +456,10 @@ RIQN_API int riqn_conv_bwd_tc(const riqn_conv_geom* g, const float* dout, const 
   // dW[c, k] += sum_m dY[m, c] * col[m, k]      (K' = M is long: split it over every SM)
   const int n_tiles = (K + 255) / 256;
   int split = (148 + n_tiles - 1) / n_tiles;
+  TcExtra ex;
+  ex.alpha = wgrad_scale;          // 1/255 when colT holds raw pixel values
   int rc = gemm_bf16_tc(g->Cout, K, (int)M, (const bf16*)dYT_hi, nullptr, (const bf16*)colT_hi, nullptr, dw, K, TC_ATOMIC,
-                        nullptr, nullptr, nullptr, split, s, nullptr);
+                        nullptr, nullptr, nullptr, split, s, &ex);
   if (rc) return rc;
   if (din) {
     // dcol[m, k] = sum_c dY[m, c] * W[c, k]

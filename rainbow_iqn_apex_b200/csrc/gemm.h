@@ -35,6 +35,7 @@ enum TcEpi { TC_STORE = 0, TC_BIAS_RELU = 1, TC_ATOMIC = 2, TC_NOISY_WGRAD = 3, 
 
 struct TcExtra {
   int ohw = 1;
+  float alpha = 1.0f;
   const float* feat = nullptr;
   int batch = 1;
   __nv_bfloat16 *o_hi = nullptr, *o_lo = nullptr, *o_hiT = nullptr, *o_loT = nullptr;

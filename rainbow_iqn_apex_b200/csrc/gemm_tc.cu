@@ -33,12 +33,15 @@ constexpr int TC_THREADS = 64 + 32 * EPI_WARPS;  // warp 0: TMA producer, warp 1
 constexpr uint32_t TMEM_COLS = 512;
 
 
+// NSPLIT 1: a_hi*b_hi.  NSPLIT 3: a_hi*b_hi + a_hi*b_lo + a_lo*b_hi.  NSPLIT 2: A is exact in bf16 (e.g. uint8 pixels),
+// only B is split: a_hi*b_hi + a_hi*b_lo.
 template <int NSPLIT>
 struct TcCfg {
-  static constexpr int kOps = NSPLIT == 1 ? 1 : 2;                                   // hi (+ lo) per operand
+  static constexpr int kAOps = NSPLIT == 3 ? 2 : 1, kBOps = NSPLIT == 1 ? 1 : 2;     // hi (+ lo) images per operand
+  static constexpr int kOps = kAOps;                                                 // (A images; B tile starts after them)
   static constexpr int kStages = NSPLIT == 1 ? 4 : 2;
   static constexpr uint32_t kABytes = TBM * TBK * 2, kBBytes = TBN * TBK * 2;
-  static constexpr uint32_t kStageBytes = kOps * (kABytes + kBBytes);                // 48 KB or 96 KB
+  static constexpr uint32_t kStageBytes = kAOps * kABytes + kBOps * kBBytes;         // 48 / 80 / 96 KB
   static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
@@ -122,6 +125,7 @@ struct TcArgs {
   const float* bias;     // TC_BIAS_RELU / _NCHW / TC_EMBED
   float* out2;           // TC_NOISY_WGRAD: grad_sigma
   const float* eps;      // TC_NOISY_WGRAD: weight_epsilon (same layout as C)
+  float alpha;           // TC_ATOMIC: scale applied to the accumulator
   int ohw;               // TC_BIAS_RELU_NCHW: m = b*ohw + p -> C[(b*N + n)*ohw + p]
   const float* feat;     // TC_EMBED: (batch, N) conv features, row m uses feat[m % batch]
   int batch;
@@ -175,10 +179,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
           mbar_expect_tx(&full[stage], Cfg::kStageBytes);
           tma_load_2d(s, &mapA_hi, kb * TBK, mt * TBM, &full[stage]);
           tma_load_2d(s + Cfg::kOps * Cfg::kABytes, &mapB_hi, kb * TBK, nt * TBN, &full[stage]);
-          if (NSPLIT == 3) {
-            tma_load_2d(s + Cfg::kABytes, &mapA_lo, kb * TBK, mt * TBM, &full[stage]);
-            tma_load_2d(s + 2 * Cfg::kABytes + Cfg::kBBytes, &mapB_lo, kb * TBK, nt * TBN, &full[stage]);
-          }
+          if (NSPLIT == 3) tma_load_2d(s + Cfg::kABytes, &mapA_lo, kb * TBK, mt * TBM, &full[stage]);
+          if (NSPLIT >= 2)
+            tma_load_2d(s + Cfg::kAOps * Cfg::kABytes + Cfg::kBBytes, &mapB_lo, kb * TBK, nt * TBN, &full[stage]);
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -208,12 +211,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
             const uint32_t koff = k * UMMA_K * 2;   // bytes along K inside the 128 B swizzle row
             const uint64_t a_hi = umma_desc_k128(sa + koff), b_hi = umma_desc_k128(sb + koff);
             umma_bf16(tmem_d, a_hi, b_hi, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            if (NSPLIT == 3) {
-              const uint64_t a_lo = umma_desc_k128(sa + Cfg::kABytes + koff);
-              const uint64_t b_lo = umma_desc_k128(sb + Cfg::kBBytes + koff);
-              umma_bf16(tmem_d, a_hi, b_lo, idesc, 1u);
-              umma_bf16(tmem_d, a_lo, b_hi, idesc, 1u);
-            }
+            if (NSPLIT >= 2) umma_bf16(tmem_d, a_hi, umma_desc_k128(sb + Cfg::kBBytes + koff), idesc, 1u);
+            if (NSPLIT == 3) umma_bf16(tmem_d, umma_desc_k128(sa + Cfg::kABytes + koff), b_hi, idesc, 1u);
           }
           umma_commit(&empty[stage]);             // smem slot free once these MMAs retire
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
@@ -318,7 +317,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               if (n0 + j < p.N) {
-                const float o = __uint_as_float(v[j]);
+                const float o = __uint_as_float(v[j]) * (EPI == TC_ATOMIC ? p.alpha : 1.f);
                 if (p.k_splits == 1) {   // sole contributor: += without atomics
                   crow[j] += o;
                   if (EPI == TC_NOISY_WGRAD) p.out2[(long)m * p.ldc + n0 + j] += o * p.eps[(long)m * p.ldc + n0 + j];
@@ -402,19 +401,21 @@ int gemm_bf16_tc(int M, int N, int K, const bf16* A_hi, const bf16* A_lo, const 
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if (K % 8) return (int)cudaErrorInvalidValue;
   const bool split3 = A_lo != nullptr && B_lo != nullptr;
+  const bool split2 = A_lo == nullptr && B_lo != nullptr;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int rc = make_map(&ma_hi, A_hi, M, K, TBM);
   if (rc) return rc;
   rc = make_map(&mb_hi, B_hi, N, K, TBN);
   if (rc) return rc;
+  ma_lo = ma_hi;
+  mb_lo = mb_hi;
   if (split3) {
     rc = make_map(&ma_lo, A_lo, M, K, TBM);
     if (rc) return rc;
+  }
+  if (split3 || split2) {
     rc = make_map(&mb_lo, B_lo, N, K, TBN);
     if (rc) return rc;
-  } else {
-    ma_lo = ma_hi;
-    mb_lo = mb_hi;
   }
   TcArgs p;
   p.M = M; p.N = N; p.K = K;
@@ -427,6 +428,7 @@ int gemm_bf16_tc(int M, int N, int K, const bf16* A_hi, const bf16* A_lo, const 
   p.k_splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
   if (p.k_splits > 1 && epi != TC_ATOMIC && epi != TC_NOISY_WGRAD) return (int)cudaErrorInvalidValue;
   p.C = C; p.ldc = ldc; p.bias = bias; p.out2 = out2; p.eps = eps;
+  p.alpha = ex ? ex->alpha : 1.f;
   p.ohw = ex ? ex->ohw : 1; p.feat = ex ? ex->feat : nullptr; p.batch = ex ? ex->batch : 1;
   p.o_hi = ex ? ex->o_hi : nullptr; p.o_lo = ex ? ex->o_lo : nullptr;
   p.o_hiT = ex ? ex->o_hiT : nullptr; p.o_loT = ex ? ex->o_loT : nullptr;
@@ -440,6 +442,12 @@ int gemm_bf16_tc(int M, int N, int K, const bf16* A_hi, const bf16* A_lo, const 
       case TC_NOISY_WGRAD: RIQN_TC_GO(3, TC_NOISY_WGRAD);
       case TC_BIAS_RELU_NCHW: RIQN_TC_GO(3, TC_BIAS_RELU_NCHW);
       case TC_EMBED: RIQN_TC_GO(3, TC_EMBED);
+    }
+  } else if (split2) {
+    switch (epi) {
+      case TC_BIAS_RELU_NCHW: RIQN_TC_GO(2, TC_BIAS_RELU_NCHW);
+      case TC_STORE: RIQN_TC_GO(2, TC_STORE);
+      default: return (int)cudaErrorInvalidValue;
     }
   } else {
     switch (epi) {
@@ -498,6 +506,23 @@ int split_bf16(long rows, int cols, const float* src, bf16* hi, bf16* lo, bf16* 
 }  // namespace riqn
 
 using namespace riqn;
+
+__global__ void split_bf16_scaled_kernel(long n, const float* __restrict__ src, float scale, riqn::bf16* __restrict__ hi,
+                                         riqn::bf16* __restrict__ lo) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = __fdiv_rn(src[i], scale);      // weight / 255, like the reference divides the pixel
+  const riqn::bf16 h = __float2bfloat16_rn(x);
+  hi[i] = h;
+  if (lo) lo[i] = __float2bfloat16_rn(x - __bfloat162float(h));
+}
+
+RIQN_API int riqn_split_bf16_scaled(long rows, int cols, const float* src, float scale, void* hi, void* lo, void* stream) {
+  riqn::note_launches(1);
+  const long n = rows * cols;
+  split_bf16_scaled_kernel<<<riqn_cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(n, src, scale, (riqn::bf16*)hi, (riqn::bf16*)lo);
+  return (int)cudaGetLastError();
+}
 
 RIQN_API int riqn_split_bf16(long rows, int cols, const float* src, void* hi, void* lo, void* hi_t, void* lo_t,
                              void* stream) {

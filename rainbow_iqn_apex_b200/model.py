@@ -300,6 +300,8 @@ class DQN(nn.Module):
             for name, conv in (("conv1", self.conv1), ("conv2", self.conv2), ("conv3", self.conv3)):
                 co, k = conv.weight.shape[0], conv.weight[0].numel()
                 self._conv_ops[name] = (mk(co, k), mk(co, k), mk(k, co))
+            k1 = self.conv1.weight[0].numel()
+            self._conv1_px_ops = (mk(32, k1), mk(32, k1))      # bf16 hi / lo of conv1.weight / 255 (uint8 ingest)
             if not self.rainbow_only:
                 self._iqn_ops = (mk(FEAT, self.quantile_embedding_dim), mk(FEAT, self.quantile_embedding_dim))
         call("riqn_split_bf16", 2 * self.hidden, FEAT, ptr(self._w_eff_h), ptr(self._w_hi), ptr(self._w_lo),
@@ -307,6 +309,8 @@ class DQN(nn.Module):
         for name, conv in (("conv1", self.conv1), ("conv2", self.conv2), ("conv3", self.conv3)):
             hi, lo, hiT = self._conv_ops[name]
             call("riqn_split_bf16", hi.shape[0], hi.shape[1], ptr(conv.weight), ptr(hi), ptr(lo), ptr(hiT), None)
+        call("riqn_split_bf16_scaled", 32, self._conv1_px_ops[0].shape[1], ptr(self.conv1.weight), 255.0,
+             ptr(self._conv1_px_ops[0]), ptr(self._conv1_px_ops[1]))
         if not self.rainbow_only:
             call("riqn_split_bf16", FEAT, self.quantile_embedding_dim, ptr(self.iqn_fc.weight), ptr(self._iqn_ops[0]),
                  ptr(self._iqn_ops[1]), None, None)
@@ -359,12 +363,25 @@ class DQN(nn.Module):
         bwd_tc = keep is not None and PRECISION["bwd"] == "bf16" and fwd != "fp32" and all((g.B * g.OH * g.OW) % 8 == 0 for g in geoms)
         need_col32 = keep is not None and not bwd_tc
         cols, colTs = [None] * 3, [None] * 3
+        px_scale = 1.0
         for i, (g, conv, inp, out) in enumerate(zip(geoms, convs, ins, outs)):
             M, K = g.B * g.OH * g.OW, g.Cin * g.KH * g.KW
             u8 = is_u8 if i == 0 else 0
             if fwd == "fp32":
                 cols[i] = torch.empty(M, K, device=dev)
                 call("riqn_conv_fwd", g, ptr(inp), u8, ptr(conv.weight), ptr(conv.bias), ptr(cols[i]), ptr(out))
+            elif i == 0 and u8 and x.stride(0) % 16 == 0 and x.data_ptr() % 16 == 0:
+                # raw-pixel path: pixel values are exact in bf16, /255 folded into the weights
+                ws_hi, ws_lo = self._conv1_px_ops
+                col_px = torch.empty(M, K, dtype=torch.bfloat16, device=dev)
+                if bwd_tc:
+                    colTs[i] = torch.empty(K, M, dtype=torch.bfloat16, device=dev)
+                    px_scale = 1.0 / 255.0
+                call("riqn_conv_fwd_tc_u8", g, ptr(inp), ptr(ws_hi), ptr(ws_lo) if fwd == "bf16x3" else None, ptr(conv.bias),
+                     ptr(col_px), ptr(colTs[i]), ptr(out))
+                if need_col32:
+                    cols[i] = torch.empty(M, K, device=dev)
+                    call("riqn_im2col_f32", g, ptr(inp), u8, ptr(cols[i]))
             else:
                 w_hi, w_lo, _ = self._conv_ops["conv%d" % (i + 1)]
                 col_hi = torch.empty(M, K, dtype=torch.bfloat16, device=dev)
@@ -377,7 +394,7 @@ class DQN(nn.Module):
                     cols[i] = torch.empty(M, K, device=dev)
                     call("riqn_im2col_f32", g, ptr(inp), u8, ptr(cols[i]))
         if keep is not None:
-            keep.update(x=x, g=geoms, col=tuple(cols), colT=tuple(colTs), out=outs, bwd_tc=bwd_tc)
+            keep.update(x=x, g=geoms, col=tuple(cols), colT=tuple(colTs), out=outs, bwd_tc=bwd_tc, px_scale=px_scale)
         return outs[2].view(B, FEAT)
 
     def iqn_head(self, feat, num_quantiles, tau, keep=None):
@@ -519,7 +536,7 @@ class DQN(nn.Module):
                 dYT = torch.empty(g.Cout, M, dtype=torch.bfloat16, device=dev)
                 dcol = torch.empty(M, K, device=dev) if i > 0 else None
                 call("riqn_conv_bwd_tc", g, ptr(douts[i]), ptr(out), ptr(keep["colT"][i]), ptr(wT_hi), ptr(dY), ptr(dYT),
-                     ptr(dcol), ptr(gv(conv.weight)), ptr(gv(conv.bias)), ptr(din))
+                     ptr(dcol), ptr(gv(conv.weight)), ptr(gv(conv.bias)), ptr(din), keep["px_scale"] if i == 0 else 1.0)
             else:
                 dY = torch.empty(M, g.Cout, device=dev)
                 dcol = torch.empty(M, K, device=dev) if i > 0 else None

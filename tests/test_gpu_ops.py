@@ -48,7 +48,8 @@ def test_trunk_u8_and_f32(cuda_dev, nets):
     got_u8 = d.trunk(torch.from_numpy(b["states"]).to(cuda_dev)).cpu().numpy()
     got_f32 = d.trunk(torch.from_numpy(b["states"]).float().div_(255).to(cuda_dev)).cpu().numpy()
     assert rel_err(got_u8, ref) < 3e-5      # split-bf16x3 tensor-core convolution
-    assert np.array_equal(got_u8, got_f32)          # u8 ingest == fp32/255 ingest, bit for bit
+    # uint8 ingest folds the /255 into the weights (pixel values are exact bf16 operands); fp32 ingest splits x/255
+    assert rel_err(got_u8, got_f32) < 1e-5
     # strided window view (B, 7, 84, 84)[:, 3:7]
     win = torch.from_numpy(np.concatenate([b["states"][:, :3], b["next_states"]], axis=1)).to(cuda_dev)
     got_view = d.trunk(win[:, 3:7]).cpu().numpy()
