@@ -10,8 +10,10 @@
  *   - every function returns 0 on success or a cudaError_t value; nothing is allocated inside, all
  *     buffers are caller-owned DEVICE pointers unless stated; work is enqueued on `stream`
  *     (a cudaStream_t passed as void*) and is stream-ordered, re-entrant per stream;
- *   - fp32 tensors row-major; head rows are quantile-major, r = q * batch + b
- *     (reference rainbowiqn/model.py:149, compute_loss_iqn.py:238-310);
+ *   - fp32 tensors row-major.  tau, q and dtheta use the reference's quantile-major rows r = q * batch + b
+ *     (rainbowiqn/model.py:149, compute_loss_iqn.py:238-310); the head-internal matrices (cos, x, h, dh, dz and
+ *     their bf16 images) use sample-major rows r' = b * num_quantiles + q, which makes the Hadamard operand
+ *     feat[b,:] a warp-broadcast and the reduction over a sample's quantiles contiguous;
  *   - `long long*` index buffers are int64 like the reference's torch.int64 / numpy int64.
  *
  * Each entry point cites the reference code it replaces (paths relative to /root/reference).
@@ -133,7 +135,8 @@ int riqn_noisy_bias_grad(long rows, int out_features, const float* dh, const flo
 /* ------------------------------------------------------------------------------------------------
  * Quantile embedding                                      replaces rainbowiqn/model.py:136-151
  * ---------------------------------------------------------------------------------------------- */
-/* cosv[r,i] = cos(fl(fl(i+1)*fl(pi)) * tau[r]);  x[r,:] = feat[r % batch,:] * relu(cosv[r,:] iqn_w^T + iqn_b).
+/* cosv[r',i] = cos(fl(fl(i+1)*fl(pi)) * tau[q*batch+b]);  x[r',:] = feat[b,:] * relu(cosv[r',:] iqn_w^T + iqn_b),
+ * r' = b*num_quantiles + q (sample-major output rows, quantile-major tau).
  * tau (rows), feat (batch, feat_dim), iqn_w (feat_dim, embed_dim); cosv (rows, embed_dim) and
  * x (rows, feat_dim) are outputs, rows = batch * num_quantiles. */
 int riqn_quantile_embed_fwd(int batch, int num_quantiles, int embed_dim, int feat_dim, const float* tau,
@@ -165,8 +168,8 @@ int riqn_quantile_embed_bwd_tc(int batch, int num_quantiles, int embed_dim, int 
  * ---------------------------------------------------------------------------------------------- */
 /* h (rows, 2*hidden) = [value-stream hidden | advantage-stream hidden]; wz (1+A, hidden) = effective
  * weights of fcnoisy_z_v (row 0) and fcnoisy_z_a; bz (1+A).  q (rows, A) = v + a - mean_a a. */
-int riqn_dueling_fwd(long rows, int hidden, int action_space, const float* h, const float* wz, const float* bz,
-                     float* q, void* stream);
+int riqn_dueling_fwd(long rows, int batch, int hidden, int action_space, const float* h, const float* wz,
+                     const float* bz, float* q, void* stream);
 /* Backward for the gathered action: dq[r, actions[b]] = dtheta[r] * gscale[b].  Writes dh (rows, 2*hidden),
  * already masked by h > 0, and dz (rows, 32) = [dv, da_0.., 0..] for riqn_z_wgrad; dz_t_bf16 (may be NULL) is the
  * bf16 transposed (32, rows) image for riqn_z_wgrad_tc. */

@@ -43,7 +43,7 @@ SIGNATURES = {
     "riqn_quantile_embed_fwd_tc": [C.c_int, C.c_int, C.c_int, C.c_int] + [_P] * 14,
     "riqn_quantile_embed_bwd_tc": [C.c_int, C.c_int, C.c_int, C.c_int] + [_P] * 10,
     "riqn_quantile_embed_bwd": [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P],
-    "riqn_dueling_fwd": [C.c_long, C.c_int, C.c_int, _P, _P, _P, _P, _P],
+    "riqn_dueling_fwd": [C.c_long, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P],
     "riqn_dueling_bwd": [C.c_long, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "riqn_z_wgrad": [C.c_long, C.c_int, C.c_int] + [_P] * 17,
     "riqn_z_wgrad_tc": [C.c_long, C.c_int, C.c_int] + [_P] * 18,

@@ -10,7 +10,7 @@ enum Epi {
   EPI_STORE = 0,           // C = alpha*acc
   EPI_BIAS_RELU = 1,       // C = relu(acc + bias[n])
   EPI_BIAS_RELU_NCHW = 2,  // m = b*ohw + p ; C[(b*N + n)*ohw + p] = relu(acc + bias[n])
-  EPI_EMBED = 3,           // C = feat[(m % batch)*N + n] * relu(acc + bias[n])     (model.py:146-151)
+  EPI_EMBED = 3,           // C = feat[(m / batch)*N + n] * relu(acc + bias[n]), batch = rows per sample (model.py:146-151)
   EPI_ATOMIC = 4,          // C += alpha*acc (atomicAdd; split-K capable)
   EPI_NOISY_WGRAD = 5,     // C += acc ; out2 += acc * eps[m,n]  (dL/dmu, dL/dsigma of NoisyLinear)
   EPI_BIAS = 6,            // C = acc + bias[n]

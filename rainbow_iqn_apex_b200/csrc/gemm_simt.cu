@@ -24,7 +24,7 @@ __device__ __forceinline__ void epi_one(float v, int m, int n, int N, float* __r
     const int b = m / e.ohw, p = m - b * e.ohw;
     C[((long)b * N + n) * e.ohw + p] = fmaxf(v + e.bias[n], 0.f);
   } else if (EPI == EPI_EMBED) {
-    C[(long)m * ldc + n] = e.feat[(long)(m % e.batch) * N + n] * fmaxf(v + e.bias[n], 0.f);
+    C[(long)m * ldc + n] = e.feat[(long)(m / e.batch) * N + n] * fmaxf(v + e.bias[n], 0.f);
   } else if (EPI == EPI_ATOMIC) {
     atomicAdd(&C[(long)m * ldc + n], e.alpha * v);
   } else if (EPI == EPI_NOISY_WGRAD) {
@@ -128,7 +128,7 @@ gemm_simt_kernel(int M, int N, int K, const float* __restrict__ A, long sAm, lon
             v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
           }
           if (EPI == EPI_EMBED) {
-            const float4 f = *reinterpret_cast<const float4*>(&e.feat[(long)(m % e.batch) * N + n]);
+            const float4 f = *reinterpret_cast<const float4*>(&e.feat[(long)(m / e.batch) * N + n]);
             v.x *= f.x; v.y *= f.y; v.z *= f.z; v.w *= f.w;
           }
         }

@@ -127,7 +127,7 @@ struct TcArgs {
   const float* eps;      // TC_NOISY_WGRAD: weight_epsilon (same layout as C)
   float alpha;           // TC_ATOMIC: scale applied to the accumulator
   int ohw;               // TC_BIAS_RELU_NCHW: m = b*ohw + p -> C[(b*N + n)*ohw + p]
-  const float* feat;     // TC_EMBED: (batch, N) conv features, row m uses feat[m % batch]
+  const float* feat;     // TC_EMBED: (samples, N) conv features, row m uses feat[m / batch] (batch = rows per sample)
   int batch;
   bf16 *o_hi, *o_lo;     // TC_EMBED: bf16 hi / lo images of the result, row-major (M, N)   (may be null)
   bf16 *o_hiT, *o_loT;   // TC_EMBED: transposed (N, M) images                              (may be null)
@@ -279,7 +279,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
               if (n0 + j < p.N) cb[(long)j * p.ohw] = fmaxf(__uint_as_float(v[j]) + p.bias[n0 + j], 0.f);
           } else if (EPI == TC_EMBED) {
             // x = feat[b] * relu(acc + bias)   (model.py:146-151); N % 32 == 0 is required by the host wrapper
-            const float* fr = p.feat + (long)(m % p.batch) * p.N + n0;
+            const float* fr = p.feat + (long)(m / p.batch) * p.N + n0;   // batch = rows per sample: warp-broadcast when 32 | Nq
             const long o = (long)m * p.N + n0;
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {

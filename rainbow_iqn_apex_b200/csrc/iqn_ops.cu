@@ -1,7 +1,10 @@
 // IQN head of the DQN and the quantile-Huber loss (reference rainbowiqn/model.py:9-53,130-157 and
 // rainbowiqn/compute_loss_iqn.py:216-358) as CUDA ops behind the C-ABI in include/riqn_b200.h.
 //
-// Row convention everywhere: r = q * B + b  (quantile-major, model.py:149; compute_loss_iqn.py:238-310).
+// Row conventions: the reference tiles rows quantile-major, r = q*B + b (model.py:149; compute_loss_iqn.py:238-310);
+// tau, q and dtheta cross the C-ABI in that order.  INTERNALLY (cos, x, h, dh, dz) rows are sample-major,
+// r' = b*Nq + q, so that the 32 lanes of a warp belong to one sample: the Hadamard operand feat[b,:] is then a
+// warp-broadcast load and the reduction over a sample's quantiles is contiguous.
 #include "common.cuh"
 #include "gemm.h"
 #include "../../include/riqn_b200.h"
@@ -43,24 +46,28 @@ __global__ void fill_scaled_normal_kernel(long n, uint64_t seed, uint64_t stream
 // ------------------------------------------------------------------------------------------------
 // Quantile embedding input: cos(fl(fl(i) * fl(pi)) * tau), i = 1..E          (model.py:136-144)
 // ------------------------------------------------------------------------------------------------
-__global__ void cos_embed_kernel(long R, int E, const float* __restrict__ tau, float* __restrict__ cosv) {
+__global__ void cos_embed_kernel(int B, int Nq, int E, const float* __restrict__ tau, float* __restrict__ cosv) {
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= R * E) return;
+  if (idx >= (long)B * Nq * E) return;
   const int i = (int)(idx % E) + 1;
+  const long r = idx / E;                                   // sample-major row b*Nq + q
+  const int b = (int)(r / Nq), q = (int)(r - (long)b * Nq);
   const float ipi = __fmul_rn((float)i, 3.14159274101257324f);
-  cosv[idx] = cosf(__fmul_rn(ipi, tau[idx / E]));
+  cosv[idx] = cosf(__fmul_rn(ipi, tau[(long)q * B + b]));   // tau arrives quantile-major
 }
 
 // Same values as bf16 (hi, lo) operand images for the tensor-core embedding product, plus the transposed hi image
 // (E, R) the iqn_fc weight-gradient product consumes.
-__global__ void cos_embed_bf16_kernel(long R, int E, const float* __restrict__ tau, __nv_bfloat16* __restrict__ hi,
+__global__ void cos_embed_bf16_kernel(int B, int Nq, int E, const float* __restrict__ tau, __nv_bfloat16* __restrict__ hi,
                                       __nv_bfloat16* __restrict__ lo, __nv_bfloat16* __restrict__ hiT) {
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long R = (long)B * Nq;
   if (idx >= R * E) return;
   const int i = (int)(idx % E) + 1;
-  const long r = idx / E;
+  const long r = idx / E;                                   // sample-major row b*Nq + q
+  const int b = (int)(r / Nq), q = (int)(r - (long)b * Nq);
   const float ipi = __fmul_rn((float)i, 3.14159274101257324f);
-  const float c = cosf(__fmul_rn(ipi, tau[r]));
+  const float c = cosf(__fmul_rn(ipi, tau[(long)q * B + b]));
   const __nv_bfloat16 h = __float2bfloat16_rn(c);
   hi[idx] = h;
   if (lo) lo[idx] = __float2bfloat16_rn(c - __bfloat162float(h));
@@ -70,35 +77,32 @@ __global__ void cos_embed_bf16_kernel(long R, int E, const float* __restrict__ t
 // Backward through x = feat[b] (.) phi[r] on bf16 operand images, tile-transposing on the way:
 //   x = x_hi (+ x_lo);  dpre = dX * feat * 1{x>0}  -> dpreT (F, R) bf16 (K-major operand of the dW_e product)
 //   dfeat[b,f] = (sum_q dX * x) / feat ;  dbe[f] += sum_r dpre
-// Block = 32 features x 32 samples, looping over the Nq quantile rows of those samples.
+// Rows are sample-major, so one block = one sample x 32 features walks that sample's Nq contiguous rows in groups
+// of 32 and writes each transposed group as full 64-byte segments.
 __global__ void embed_bwd_tile_kernel(int B, int Nq, int F, const __nv_bfloat16* __restrict__ x_hi,
                                       const __nv_bfloat16* __restrict__ x_lo, const float* __restrict__ feat,
                                       const float* __restrict__ dX, __nv_bfloat16* __restrict__ dpreT,
                                       float* __restrict__ dfeat, float* __restrict__ dbe) {
   __shared__ float tile[32][33];
-  __shared__ float red[8][32];
-  const int f0 = blockIdx.x * 32, b0 = blockIdx.y * 32;
+  __shared__ float red[2][8][32];
+  const int f0 = blockIdx.x * 32, b = blockIdx.y;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
   const long R = (long)B * Nq;
-  float facc[4] = {0.f, 0.f, 0.f, 0.f}, ft[4];
-  float bacc = 0.f;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int b = b0 + ty + 8 * i, f = f0 + tx;
-    ft[i] = (b < B && f < F) ? feat[(long)b * F + f] : 0.f;
-  }
-  for (int q = 0; q < Nq; ++q) {
+  const int f = f0 + tx;
+  const float ft = f < F ? feat[(long)b * F + f] : 0.f;
+  float facc = 0.f, bacc = 0.f;
+  for (int q0 = 0; q0 < Nq; q0 += 32) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const int b = b0 + ty + 8 * i, f = f0 + tx;
+      const int q = q0 + ty + 8 * i;
       float dp = 0.f;
-      if (b < B && f < F) {
-        const long o = ((long)q * B + b) * F + f;
+      if (q < Nq && f < F) {
+        const long o = ((long)b * Nq + q) * F + f;
         float x = __bfloat162float(x_hi[o]);
         if (x_lo) x += __bfloat162float(x_lo[o]);
         const float dx = dX[o];
-        facc[i] = fmaf(dx, x, facc[i]);
-        dp = x > 0.f ? dx * ft[i] : 0.f;
+        facc = fmaf(dx, x, facc);
+        dp = x > 0.f ? dx * ft : 0.f;
         bacc += dp;
       }
       tile[ty + 8 * i][tx] = dp;
@@ -106,23 +110,20 @@ __global__ void embed_bwd_tile_kernel(int B, int Nq, int F, const __nv_bfloat16*
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const int f = f0 + ty + 8 * i, b = b0 + tx;
-      if (f < F && b < B) dpreT[(long)f * R + (long)q * B + b] = __float2bfloat16_rn(tile[tx][ty + 8 * i]);
+      const int ff = f0 + ty + 8 * i, q = q0 + tx;
+      if (ff < F && q < Nq) dpreT[(long)ff * R + (long)b * Nq + q] = __float2bfloat16_rn(tile[tx][ty + 8 * i]);
     }
     __syncthreads();
   }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int b = b0 + ty + 8 * i, f = f0 + tx;
-    if (b < B && f < F) dfeat[(long)b * F + f] = ft[i] > 0.f ? facc[i] / ft[i] : 0.f;
-  }
-  red[ty][tx] = bacc;
+  red[0][ty][tx] = facc;
+  red[1][ty][tx] = bacc;
   __syncthreads();
-  if (ty == 0) {
-    float v = 0.f;
+  if (ty == 0 && f < F) {
+    float fs = 0.f, bs = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v += red[j][tx];
-    if (f0 + tx < F) atomicAdd(&dbe[f0 + tx], v);
+    for (int j = 0; j < 8; ++j) { fs += red[0][j][tx]; bs += red[1][j][tx]; }
+    dfeat[(long)b * F + f] = ft > 0.f ? fs / ft : 0.f;
+    atomicAdd(&dbe[f], bs);
   }
 }
 
@@ -166,7 +167,7 @@ __global__ void noisy_compose_kernel(int out_f, int in_f, const float* __restric
 // One warp per row.
 // ------------------------------------------------------------------------------------------------
 template <int HID>
-__global__ void z_dueling_fwd_kernel(long R, int A, const float* __restrict__ H, const float* __restrict__ Wz,
+__global__ void z_dueling_fwd_kernel(long R, int B, int A, const float* __restrict__ H, const float* __restrict__ Wz,
                                      const float* __restrict__ bz, float* __restrict__ q) {
   extern __shared__ float sW[];  // (1+A) * HID
   for (int i = threadIdx.x; i < (1 + A) * HID; i += blockDim.x) sW[i] = Wz[i];
@@ -195,7 +196,9 @@ __global__ void z_dueling_fwd_kernel(long R, int A, const float* __restrict__ H,
       asum += a;
       if (lane == k) mine = a;
     }
-    if (lane < A) q[r * A + lane] = v + mine - asum / (float)A;
+    const int Nq = (int)(R / B);
+    const long b = r / Nq, qi = r - b * Nq;                 // sample-major row -> quantile-major output row
+    if (lane < A) q[(qi * B + b) * A + lane] = v + mine - asum / (float)A;
   }
 }
 
@@ -301,8 +304,9 @@ __global__ void z_dueling_bwd_kernel(long R, int B, int A, const float* __restri
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   for (long r = (long)blockIdx.x * wpb + warp; r < R; r += (long)gridDim.x * wpb) {
-    const int b = (int)(r % B);
-    const float g = dtheta[r] * gscale[b];
+    const int Nq = (int)(R / B);
+    const int b = (int)(r / Nq);                            // sample-major rows; dtheta arrives quantile-major
+    const float g = dtheta[(r - (long)b * Nq) * B + b] * gscale[b];
     const int act = (int)actions[b];
     const float* h = H + r * (2 * HID);
     float* o = dH + r * (2 * HID);
@@ -371,7 +375,8 @@ __global__ void embed_bwd_elem_kernel(int B, int Nq, int F, const float* __restr
   const float ft = feat[idx];
   float acc = 0.f;
   for (int q = 0; q < Nq; ++q) {
-    const long o = (long)q * B * F + idx;
+    const long bb = idx / F;
+    const long o = ((bb * Nq + q) * F) + (idx - bb * F);     // sample-major rows
     const float x = X[o], dx = dX[o];
     acc = fmaf(dx, x, acc);
     dX[o] = x > 0.f ? dx * ft : 0.f;
@@ -439,12 +444,12 @@ RIQN_API int riqn_quantile_embed_fwd(int batch, int num_quantiles, int embed_dim
   riqn::note_launches(2);
   cudaStream_t s = (cudaStream_t)stream;
   const long R = (long)batch * num_quantiles;
-  cos_embed_kernel<<<riqn_cdiv(R * embed_dim, 256), 256, 0, s>>>(R, embed_dim, tau, cosv);
+  cos_embed_kernel<<<riqn_cdiv(R * embed_dim, 256), 256, 0, s>>>(batch, num_quantiles, embed_dim, tau, cosv);
   RIQN_LAUNCH_CHECK();
   EpiArgs e;
   e.bias = iqn_b;
   e.feat = feat;
-  e.batch = batch;
+  e.batch = num_quantiles;     // rows per sample (sample-major rows): feat row = m / num_quantiles
   return gemm_f32((int)R, feat_dim, embed_dim, cosv, embed_dim, 1, iqn_w, embed_dim, 1, x, feat_dim, EPI_EMBED, e, 1, s);
 }
 
@@ -458,12 +463,12 @@ RIQN_API int riqn_quantile_embed_fwd_tc(int batch, int num_quantiles, int embed_
   riqn::note_launches(2);
   cudaStream_t s = (cudaStream_t)stream;
   const long R = (long)batch * num_quantiles;
-  cos_embed_bf16_kernel<<<riqn_cdiv(R * embed_dim, 256), 256, 0, s>>>(R, embed_dim, tau, (__nv_bfloat16*)cos_hi,
+  cos_embed_bf16_kernel<<<riqn_cdiv(R * embed_dim, 256), 256, 0, s>>>(batch, num_quantiles, embed_dim, tau, (__nv_bfloat16*)cos_hi,
                                                                      (__nv_bfloat16*)cos_lo, (__nv_bfloat16*)cosT_hi);
   RIQN_LAUNCH_CHECK();
   TcExtra ex;
   ex.feat = feat;
-  ex.batch = batch;
+  ex.batch = num_quantiles;    // rows per sample
   ex.o_hi = (__nv_bfloat16*)x_hi;
   ex.o_lo = (__nv_bfloat16*)x_lo;
   ex.o_hiT = (__nv_bfloat16*)x_hiT;
@@ -482,7 +487,7 @@ RIQN_API int riqn_quantile_embed_bwd_tc(int batch, int num_quantiles, int embed_
   cudaStream_t s = (cudaStream_t)stream;
   const long R = (long)batch * num_quantiles;
   if (R % 8) return (int)cudaErrorInvalidValue;
-  dim3 grid((feat_dim + 31) / 32, (batch + 31) / 32);
+  dim3 grid((feat_dim + 31) / 32, batch);
   embed_bwd_tile_kernel<<<grid, 256, 0, s>>>(batch, num_quantiles, feat_dim, (const __nv_bfloat16*)x_hi,
                                              (const __nv_bfloat16*)x_lo, feat, dx, (__nv_bfloat16*)dpreT, dfeat, grad_iqn_b);
   RIQN_LAUNCH_CHECK();
@@ -562,8 +567,8 @@ RIQN_API int riqn_noisy_bias_grad(long rows, int out_features, const float* dh, 
   return (int)cudaGetLastError();
 }
 
-RIQN_API int riqn_dueling_fwd(long rows, int hidden, int action_space, const float* h, const float* wz, const float* bz,
-                              float* q, void* stream) {
+RIQN_API int riqn_dueling_fwd(long rows, int batch, int hidden, int action_space, const float* h, const float* wz,
+                              const float* bz, float* q, void* stream) {
   riqn::note_launches(1);
   if (hidden != 512 || action_space > 31) return (int)cudaErrorInvalidValue;
   const size_t smem = sizeof(float) * (1 + action_space) * hidden;
@@ -572,7 +577,7 @@ RIQN_API int riqn_dueling_fwd(long rows, int hidden, int action_space, const flo
     RIQN_CUDA(cudaFuncSetAttribute(z_dueling_fwd_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     attr = true;
   }
-  z_dueling_fwd_kernel<512><<<148 * 4, 256, smem, (cudaStream_t)stream>>>(rows, action_space, h, wz, bz, q);
+  z_dueling_fwd_kernel<512><<<148 * 4, 256, smem, (cudaStream_t)stream>>>(rows, batch, action_space, h, wz, bz, q);
   return (int)cudaGetLastError();
 }
 

@@ -437,7 +437,7 @@ class DQN(nn.Module):
             call("riqn_gemm_bf16_tc", R, 2 * hid, FEAT, ptr(tc["x_hi"]), ptr(tc["x_lo"]), ptr(self._w_hi),
                  ptr(self._w_lo) if x3 else None, ptr(h), 2 * hid, 1, ptr(self._b_eff_h), None, None, 1, ptr(tc["hT"]))
         q = torch.empty(R, A, device=dev)
-        call("riqn_dueling_fwd", R, hid, A, ptr(h), ptr(self._w_eff_z), ptr(self._b_eff_z), ptr(q))
+        call("riqn_dueling_fwd", R, B, hid, A, ptr(h), ptr(self._w_eff_z), ptr(self._b_eff_z), ptr(q))
         if keep is not None:
             keep.update(feat=feat, cos=cosv, xt=xt, h=h, q=q, tau=tau, num_quantiles=num_quantiles, tc=tc,
                         head_bwd_tc=bwd_tc, emb_bwd_tc=emb_tc)

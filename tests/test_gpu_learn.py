@@ -92,6 +92,12 @@ def test_learn_matches_reference_golden(cuda_dev, golden_dir, name):
                 assert np.allclose(pd, pref, rtol=1e-5, atol=1e-6), k
 
 
+def _qmajor(t, batch):
+    """head-internal rows are sample-major (b*Nq + q); the oracle's are quantile-major (q*B + b)."""
+    nq = t.shape[0] // batch
+    return t.reshape(batch, nq, -1).transpose(0, 1).reshape(batch * nq, -1)
+
+
 def _tie_mask(keep_oracle, a_star_gpu, tol=1e-5):
     """Samples whose double-DQN argmax differs only because the top-2 oracle Q-means are within tol."""
     a_ref = keep_oracle["a_star"].numpy()
@@ -148,7 +154,7 @@ def test_loss_api_and_autograd_vs_oracle(cuda_dev, precision, batch, cfg, mode):
     gk = dbg["keep"]
     flips = sum(int(((a.cpu() > 0) != (b_ > 0)).sum()) for a, b_ in
                 ((gk["out"][0], keep["o1"]), (gk["out"][1], keep["o2"]), (gk["out"][2], keep["o3"]),
-                 (gk["h"][:, :512], keep["h_v"]), (gk["h"][:, 512:], keep["h_a"])))
+                 (_qmajor(gk["h"], batch)[:, :512], keep["h_v"]), (_qmajor(gk["h"], batch)[:, 512:], keep["h_a"])))
     if not ties.any():
         for k, g_ref in o_grads.items():
             gg = grads_gpu[k]

@@ -72,12 +72,17 @@ def test_forward_injected(cuda_dev, nets):
     q, tau_out = d.forward(torch.from_numpy(b["states"]).to(cuda_dev), Nq, tau=tau, keep=k2, fresh_weights=True)
     assert torch.equal(tau_out.cpu(), tau)
     tc = k2["tc"]
-    cos_gpu = (tc["cos_hi"].float() + tc["cos_lo"].float()).cpu().numpy()          # bf16 hi + lo images
-    x_gpu = (tc["x_hi"].float() + tc["x_lo"].float()).cpu().numpy()
+
+    def qmajor(t):   # head-internal rows are sample-major (b*Nq + q); the oracle's are quantile-major (q*B + b)
+        return t.reshape(B, Nq, -1).transpose(0, 1).reshape(B * Nq, -1)
+
+    cos_gpu = qmajor(tc["cos_hi"].float() + tc["cos_lo"].float()).cpu().numpy()    # bf16 hi + lo images
+    x_gpu = qmajor(tc["x_hi"].float() + tc["x_lo"].float()).cpu().numpy()
     assert rel_err(cos_gpu, keep["cos"].numpy()) < 2e-5
     assert rel_err(x_gpu, keep["x"].numpy()) < 3e-5
-    assert rel_err(k2["h"][:, :512].cpu().numpy(), keep["h_v"].numpy()) < 1e-4   # split-bf16x3 tensor-core products
-    assert rel_err(k2["h"][:, 512:].cpu().numpy(), keep["h_a"].numpy()) < 1e-4
+    h_gpu = qmajor(k2["h"])
+    assert rel_err(h_gpu[:, :512].cpu().numpy(), keep["h_v"].numpy()) < 1e-4   # split-bf16x3 tensor-core products
+    assert rel_err(h_gpu[:, 512:].cpu().numpy(), keep["h_a"].numpy()) < 1e-4
     assert rel_err(q.cpu().numpy(), ref.numpy()) < 1e-4
     # stored epsilons == outer product of the injected factors (model.py:39-43), bit for bit
     assert torch.equal(d.fcnoisy_h_a.weight_epsilon.cpu(), torch.outer(noise["fcnoisy_h_a"][1], noise["fcnoisy_h_a"][0]))
