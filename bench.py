@@ -238,10 +238,14 @@ def run_ours(args):
     if not args.no_graph:
         learner.enable_batch_graph(mem, tuple(t.contiguous() for t in mem.sample(B)))
 
+    if not args.no_graph:
+        learner.prefetch_host_batch(pool[0])
+
     def e2e_step(i):
         host = pool[i % len(pool)]
         if not args.no_graph:
-            loss = learner.learn_on_host_batch(host)               # async H2D into static buffers + graph replay
+            loss = learner.learn_on_host_batch()                   # consumes the prefetched batch: D2D + graph replay
+            learner.prefetch_host_batch(pool[(i + 1) % len(pool)])  # H2D of the NEXT batch overlaps this step
         else:
             idxs, st, ac, rt, nx, nt, w = (t.to(dev, non_blocking=True) for t in host)
             loss = learner.learn_on_batch(st, ac, rt, nx, nt, w)

@@ -136,11 +136,34 @@ class Learner(Agent):
         self._bgraph, self._bg_out = graph, out
         return self
 
-    def learn_on_host_batch(self, host_batch):
-        """host_batch: pinned host tensors (idxs, states u8, actions, returns, next_states u8, nonterminals, weights).
-        H2D copies + one graph replay; returns the device loss (B,) (static buffer)."""
-        for d, h in zip(self._bg_in, host_batch):
-            d.copy_(h, non_blocking=True)
+    def prefetch_host_batch(self, host_batch):
+        """Start the H2D copy of a FUTURE minibatch on a side stream (double-buffered device staging), so that it
+        overlaps the current step -- what the reference's sampler subprocess + mp queue achieve on the host
+        (launch_learner.py:24-50).  The next learn_on_host_batch() consumes it."""
+        if not hasattr(self, "_pf_stream"):
+            self._pf_stream = torch.cuda.Stream()
+            self._pf_buf = [tuple(torch.empty_like(t) for t in self._bg_in) for _ in range(2)]
+            self._pf_slot, self._pf_event = 0, None
+        slot = self._pf_slot ^ 1
+        self._pf_stream.wait_stream(torch.cuda.current_stream())      # staging slot no longer read by an older step
+        with torch.cuda.stream(self._pf_stream):
+            for d, h in zip(self._pf_buf[slot], host_batch):
+                d.copy_(h, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+        self._pf_slot, self._pf_event = slot, ev
+
+    def learn_on_host_batch(self, host_batch=None):
+        """host_batch: pinned host tensors (idxs, states u8, actions, returns, next_states u8, nonterminals, weights),
+        or None to consume the batch started by prefetch_host_batch().  H2D copies + one graph replay; returns the
+        device loss (B,) (static buffer)."""
+        if host_batch is None:
+            torch.cuda.current_stream().wait_event(self._pf_event)
+            for d, src in zip(self._bg_in, self._pf_buf[self._pf_slot]):
+                d.copy_(src, non_blocking=True)                          # device-to-device, 29 MB
+        else:
+            for d, h in zip(self._bg_in, host_batch):
+                d.copy_(h, non_blocking=True)
         mem = self._graph_mem
         nss, sbc = self.optimiser.bias_corrections(self.optimiser._step + 1)
         self._dyn.write(nss, sbc, mem.transitions.get_current_capacity(), mem.priority_weight)

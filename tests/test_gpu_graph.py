@@ -75,3 +75,9 @@ def test_host_batch_graph(cuda_dev):
     assert not torch.equal(before, lr.online_net._flat)
     new_pri = mem.transitions.tree[host[0].to(cuda_dev)]
     assert torch.allclose(new_pri.float(), l2.pow(0.2), rtol=1e-5)      # priorities of the batch were updated
+    # prefetched path: same batch through the side-stream staging gives a valid step too
+    lr.prefetch_host_batch(host)
+    l3 = lr.learn_on_host_batch().clone()
+    lr.prefetch_host_batch(host)
+    l4 = lr.learn_on_host_batch().clone()
+    assert torch.isfinite(l3).all() and torch.isfinite(l4).all() and not torch.equal(l3, l4)
