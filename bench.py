@@ -386,6 +386,16 @@ def run_reference(args):
     print(json.dumps(out))
 
 
+def watchdog(seconds):
+    """Hard stop: a benchmark must never hang a GPU box (e.g. a collective waiting for a dead rank)."""
+    def run():
+        time.sleep(seconds)
+        sys.stderr.write(f"bench.py watchdog: no result after {seconds}s, aborting\n")
+        sys.stderr.flush()
+        os._exit(3)
+    threading.Thread(target=run, daemon=True).start()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -395,7 +405,9 @@ def main():
     ap.add_argument("--replay-capacity", type=int, default=1 << 19)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
+    ap.add_argument("--max-seconds", type=int, default=900, help="watchdog: abort the process after this long")
     args = ap.parse_args()
+    watchdog(args.max_seconds)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -21,6 +21,7 @@ class Learner(Agent):
         super().__init__(args, action_space, redis_servor)
         self.process_group = None  # set by parallel.make_data_parallel
         self._graph = None         # CUDA-graph mode (enable_cuda_graph)
+        self._graph_post = None
 
     def learn(self, mem_redis, mp_queue):
         sample = mem_redis.get_sample_from_mp_queue(mp_queue)
@@ -30,6 +31,18 @@ class Learner(Agent):
 
     def learn_on_batch(self, states, actions, returns, next_states, nonterminals, weights):
         """learner.py:18-24 on an already assembled minibatch.  Returns the per-transition loss (B,)."""
+        loss = self.compute_gradients(states, actions, returns, next_states, nonterminals, weights)
+        self.apply_gradients()
+        return loss
+
+    def apply_gradients(self):
+        """Gradient all-reduce (data-parallel replicas) + Adam.  learner.py:24"""
+        if self.process_group is not None:
+            torch.distributed.all_reduce(self.online_net._flat_grad, group=self.process_group)
+        self.optimiser.step()
+
+    def compute_gradients(self, states, actions, returns, next_states, nonterminals, weights):
+        """loss -> zero_grad -> backward of (weights*loss).mean()   (learner.py:18-23); gradients land in the arena."""
         on = self.online_net
         dev = on._flat.device
         weights = weights.to(dev, torch.float32)
@@ -43,9 +56,6 @@ class Learner(Agent):
                 self, states, actions, returns, next_states, nonterminals, keep_graph=True)
             on.zero_grad()                                                      # learner.py:22
             on.backward_iqn(keep, dtheta, weights / weights.shape[0], actions)  # learner.py:23
-        if self.process_group is not None:
-            torch.distributed.all_reduce(on._flat_grad, group=self.process_group)
-        self.optimiser.step()                                                   # learner.py:24
         return loss
 
     # ------------------------------------------------------------------ whole step: sample -> learn -> priority update
@@ -59,19 +69,36 @@ class Learner(Agent):
             nss, sbc = self.optimiser.bias_corrections(self.optimiser._step + 1)
             dyn.write(nss, sbc, mem.transitions.get_current_capacity(), mem.priority_weight)
             self._graph.replay()
+            if self._graph_post is not None:          # data parallel: the collective stays outside the graphs
+                torch.distributed.all_reduce(self.online_net._flat_grad, group=self.process_group)
+                self._graph_post.replay()
             self.optimiser._step += 1
             return self._graph_out
         idxs, loss = self.learn(mem, None)
         mem.update_priorities(idxs, loss)
         return idxs, loss
 
-    def _step_body(self, mem):
+    def _step_pre(self, mem):
+        """sample -> three forwards -> loss -> backward (gradients in the arena)."""
         dyn = self._dyn
         self.online_net.begin_step(dyn)
         self.target_net.begin_step(dyn)
         mem.transitions._draws_in_step = 0
-        idxs, loss = self.learn(mem, None)
+        idxs, states, actions, returns, next_states, nonterminals, weights = mem.get_sample_from_mp_queue(None)
+        loss = self.compute_gradients(states, actions, returns, next_states, nonterminals, weights)
+        return idxs, loss
+
+    def _step_post(self, mem, idxs, loss, allreduce=True):
+        """(all-reduce) -> Adam -> priority update."""
+        if allreduce:
+            self.apply_gradients()
+        else:
+            self.optimiser.step()
         mem.update_priorities(idxs, loss)
+
+    def _step_body(self, mem):
+        idxs, loss = self._step_pre(mem)
+        self._step_post(mem, idxs, loss)
         return idxs, loss
 
     def enable_cuda_graph(self, mem, warmup=3):
@@ -96,11 +123,20 @@ class Learner(Agent):
         graph = torch.cuda.CUDAGraph()
         nss, sbc = self.optimiser.bias_corrections(self.optimiser._step + 1)
         self._dyn.write(nss, sbc, mem.transitions.get_current_capacity(), mem.priority_weight)
-        with torch.cuda.graph(graph):
-            out = self._step_body(mem)
-        # the capture itself does not execute the step: undo the host-side counter it advanced, then run it once
+        post = None
+        if self.process_group is None:
+            with torch.cuda.graph(graph):
+                out = self._step_body(mem)
+        else:
+            # data parallel: two graphs around an EAGER all-reduce (NCCL is kept out of stream capture)
+            with torch.cuda.graph(graph):
+                out = self._step_pre(mem)
+            post = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(post, pool=graph.pool()):
+                self._step_post(mem, out[0], out[1], allreduce=False)
+        # the capture itself does not execute the step: undo the host-side counter it advanced
         self.optimiser._step = step0 + warmup
-        self._graph, self._graph_mem, self._graph_out = graph, mem, out
+        self._graph, self._graph_post, self._graph_mem, self._graph_out = graph, post, mem, out
         return self
 
     def enable_batch_graph(self, mem, example):
@@ -111,12 +147,15 @@ class Learner(Agent):
         assert self._graph is not None and mem is self._graph_mem
         self._bg_in = tuple(t.clone() for t in example)
 
-        def body():
+        def pre():
             self.online_net.begin_step(self._dyn)
             self.target_net.begin_step(self._dyn)
             idxs, st, ac, rt, nx, nt, w = self._bg_in
-            loss = self.learn_on_batch(st, ac, rt, nx, nt, w)
-            mem.update_priorities(idxs, loss)
+            return self.compute_gradients(st, ac, rt, nx, nt, w)
+
+        def body():
+            loss = pre()
+            self._step_post(mem, self._bg_in[0], loss)
             return loss
 
         step0 = self.optimiser._step
@@ -130,10 +169,18 @@ class Learner(Agent):
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            out = body()
+        post = None
+        if self.process_group is None:
+            with torch.cuda.graph(graph):
+                out = body()
+        else:
+            with torch.cuda.graph(graph):
+                out = pre()
+            post = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(post, pool=graph.pool()):
+                self._step_post(mem, self._bg_in[0], out, allreduce=False)
         self.optimiser._step = step0 + 2
-        self._bgraph, self._bg_out = graph, out
+        self._bgraph, self._bgraph_post, self._bg_out = graph, post, out
         return self
 
     def prefetch_host_batch(self, host_batch):
@@ -168,6 +215,9 @@ class Learner(Agent):
         nss, sbc = self.optimiser.bias_corrections(self.optimiser._step + 1)
         self._dyn.write(nss, sbc, mem.transitions.get_current_capacity(), mem.priority_weight)
         self._bgraph.replay()
+        if self._bgraph_post is not None:
+            torch.distributed.all_reduce(self.online_net._flat_grad, group=self.process_group)
+            self._bgraph_post.replay()
         self.optimiser._step += 1
         return self._bg_out
 

@@ -66,6 +66,19 @@ def make_data_parallel(learner, group=None):
     return learner
 
 
+def publish_parameters(agent, src=0, group=None):
+    """Ape-X parameter publication over the collective fabric: the learner rank broadcasts its flat parameter arena
+    (26.9 MB; the epsilon buffers are not sent -- actors resample noise, launch_actor.py:76-77) and every other rank
+    (actor GPUs) receives it.  Replaces Learner.save_to_redis / Actor.load_weight_from_redis (learner.py:28-36,
+    actor.py:36-39), which ship a torch.save blob through Redis every weight_synchro_frequency steps."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    net = agent.online_net
+    dist.broadcast(net._flat, src=src, group=group)
+    if dist.get_rank(group) != src and net._flat.is_cuda:
+        net.compose_weights()
+
+
 def allreduce_max(value, device):
     t = torch.tensor([value], dtype=torch.float64, device=device)
     if dist.is_initialized() and dist.get_world_size() > 1:

@@ -48,6 +48,14 @@ def _worker(rank, world, port, out):
     on._flat_grad.fill_(float(rank + 1))
     dist.all_reduce(on._flat_grad, group=learner.process_group)
     assert float(on.conv1.weight.grad.flatten()[0]) == sum(range(1, world + 1))
+    # 3. Ape-X parameter publication: rank 0 (learner) -> everyone (actors)
+    agent = SimpleNamespace(online_net=on)
+    if rank == 0:
+        on._flat.add_(1.0)
+    parallel.publish_parameters(agent, src=0)
+    ref = on._flat.clone()
+    dist.broadcast(ref, src=0)
+    assert torch.equal(ref, on._flat)
     assert parallel.shard_batch(4096, world) == 4096 // world
     assert parallel.allreduce_max(float(rank), torch.device("cpu")) == world - 1
     out.put((rank, "ok"))
