@@ -236,6 +236,7 @@ __global__ void im2col_u8_staged_kernel(riqn_conv_geom g, const uint8_t* __restr
   extern __shared__ __align__(16) uint8_t img[];
   const int chw = g.Cin * g.H * g.W, K = g.Cin * g.KH * g.KW, K8 = K / 8, ohw = g.OH * g.OW;
   const long b = blockIdx.x;
+  const int part = blockIdx.y, parts = gridDim.y;            // several blocks share a sample: more CTAs than SMs
   const uint4* src = reinterpret_cast<const uint4*>(in + b * g.in_bstride);
   for (int i = threadIdx.x; i < chw / 16; i += blockDim.x) reinterpret_cast<uint4*>(img)[i] = src[i];
   __syncthreads();
@@ -244,7 +245,7 @@ __global__ void im2col_u8_staged_kernel(riqn_conv_geom g, const uint8_t* __restr
     return __float_as_uint((float)img[(c * g.H + ih) * g.W + iw]) >> 16;     // exact bf16 bits of 0..255
   };
   if (col) {
-    for (int item = threadIdx.x; item < ohw * K8; item += blockDim.x) {
+    for (int item = part * blockDim.x + threadIdx.x; item < ohw * K8; item += parts * blockDim.x) {
       const int m = item / K8, k0 = (item - m * K8) * 8;
       const int oh = m / g.OW, ow = m - oh * g.OW;
       int kw = k0 % g.KW, kh = (k0 / g.KW) % g.KH, c = k0 / (g.KW * g.KH);
@@ -262,7 +263,7 @@ __global__ void im2col_u8_staged_kernel(riqn_conv_geom g, const uint8_t* __restr
   if (colT) {
     const long M = (long)g.B * ohw;
     const int M8 = ohw / 8;
-    for (int item = threadIdx.x; item < K * M8; item += blockDim.x) {
+    for (int item = part * blockDim.x + threadIdx.x; item < K * M8; item += parts * blockDim.x) {
       const int k = item / M8, m0 = (item - k * M8) * 8;
       const int kw = k % g.KW, kh = (k / g.KW) % g.KH, c = k / (g.KW * g.KH);
       int oh = m0 / g.OW, ow = m0 - oh * g.OW;
@@ -433,7 +434,7 @@ RIQN_API int riqn_conv_fwd_tc_u8(const riqn_conv_geom* g, const unsigned char* i
     RIQN_CUDA(cudaFuncSetAttribute(im2col_u8_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     attr = true;
   }
-  im2col_u8_staged_kernel<<<g->B, 256, chw, s>>>(*g, in, (bf16*)col_px, (bf16*)colT_px);
+  im2col_u8_staged_kernel<<<dim3(g->B, 4), 256, chw, s>>>(*g, in, (bf16*)col_px, (bf16*)colT_px);
   RIQN_LAUNCH_CHECK();
   TcExtra ex;
   ex.ohw = ohw;

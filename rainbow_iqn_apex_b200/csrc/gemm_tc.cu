@@ -27,21 +27,21 @@ namespace riqn {
 
 using bf16 = __nv_bfloat16;
 
-constexpr int TBM = 128, TBN = 256, TBK = 64, UMMA_K = 16;
+constexpr int TBM = 128, TBK = 64, UMMA_K = 16;   // tile N (BN) is a template parameter: 256, or 64 / 32 for narrow outputs
 constexpr int EPI_WARPS = 8;     // two warps per TMEM lane quarter, each draining half of the 256 accumulator columns
 constexpr int TC_THREADS = 64 + 32 * EPI_WARPS;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, then epilogue
-constexpr uint32_t TMEM_COLS = 512;
 
 
 // NSPLIT 1: a_hi*b_hi.  NSPLIT 3: a_hi*b_hi + a_hi*b_lo + a_lo*b_hi.  NSPLIT 2: A is exact in bf16 (e.g. uint8 pixels),
 // only B is split: a_hi*b_hi + a_hi*b_lo.
-template <int NSPLIT>
+template <int NSPLIT, int BN>
 struct TcCfg {
   static constexpr int kAOps = NSPLIT == 3 ? 2 : 1, kBOps = NSPLIT == 1 ? 1 : 2;     // hi (+ lo) images per operand
   static constexpr int kOps = kAOps;                                                 // (A images; B tile starts after them)
-  static constexpr int kStages = NSPLIT == 1 ? 4 : 2;
-  static constexpr uint32_t kABytes = TBM * TBK * 2, kBBytes = TBN * TBK * 2;
-  static constexpr uint32_t kStageBytes = kAOps * kABytes + kBOps * kBBytes;         // 48 / 80 / 96 KB
+  static constexpr uint32_t kABytes = TBM * TBK * 2, kBBytes = BN * TBK * 2;
+  static constexpr uint32_t kStageBytes = kAOps * kABytes + kBOps * kBBytes;         // 48 / 80 / 96 KB at BN = 256
+  static constexpr int kStages = (192 * 1024) / kStageBytes > 6 ? 6 : (192 * 1024) / kStageBytes;
+  static constexpr uint32_t kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;                   // two accumulator buffers (power of 2)
   static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
@@ -133,11 +133,13 @@ struct TcArgs {
   bf16 *o_hiT, *o_loT;   // TC_EMBED: transposed (N, M) images                              (may be null)
 };
 
-template <int NSPLIT, int EPI>
+template <int NSPLIT, int EPI, int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
                const __grid_constant__ CUtensorMap mapB_hi, const __grid_constant__ CUtensorMap mapB_lo, TcArgs p) {
-  using Cfg = TcCfg<NSPLIT>;
+  using Cfg = TcCfg<NSPLIT, BN>;
+  constexpr int TBN = BN;
+  constexpr uint32_t TMEM_COLS = Cfg::kTmemCols;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
@@ -234,8 +236,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
       tc_fence_after();
       const int m = mt * TBM + quarter * 32 + lane;
       const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * TBN;
+      constexpr int HALF = TBN >= 64 ? TBN / 2 : TBN;        // BN = 32: the second warp set has no columns to drain
 #pragma unroll 1
-      for (int c = chalf * (TBN / 2); c < (chalf + 1) * (TBN / 2); c += 32) {
+      for (int c = chalf * HALF; c < (chalf + 1) * HALF && c < TBN; c += 32) {
         uint32_t v[32];
         tmem_ld32(trow + c, v);
         const int n0 = nt * TBN + c;
@@ -372,13 +375,13 @@ static int make_map(CUtensorMap* map, const bf16* base, long rows, long K, int b
   return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
 }
 
-template <int NSPLIT, int EPI>
+template <int NSPLIT, int EPI, int BN>
 static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
                      const TcArgs& p, cudaStream_t s) {
-  using Cfg = TcCfg<NSPLIT>;
+  using Cfg = TcCfg<NSPLIT, BN>;
   static bool attr = false;
   if (!attr) {
-    RIQN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<NSPLIT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    RIQN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<NSPLIT, EPI, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)Cfg::kSmemBytes));
     attr = true;
   }
@@ -390,7 +393,7 @@ static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUt
   }
   const int units = p.m_tiles * p.n_tiles * p.k_splits;
   const int grid = units < sms ? units : sms;
-  gemm_tc_kernel<NSPLIT, EPI><<<grid, TC_THREADS, Cfg::kSmemBytes, s>>>(a_hi, a_lo, b_hi, b_lo, p);
+  gemm_tc_kernel<NSPLIT, EPI, BN><<<grid, TC_THREADS, Cfg::kSmemBytes, s>>>(a_hi, a_lo, b_hi, b_lo, p);
   return (int)cudaGetLastError();
 }
 
@@ -402,10 +405,13 @@ int gemm_bf16_tc(int M, int N, int K, const bf16* A_hi, const bf16* A_lo, const 
   if (K % 8) return (int)cudaErrorInvalidValue;
   const bool split3 = A_lo != nullptr && B_lo != nullptr;
   const bool split2 = A_lo == nullptr && B_lo != nullptr;
+  // narrow outputs (conv channels, embedding width) get narrow tiles; only the epilogues that occur with them exist
+  const bool narrow_ok = epi == TC_BIAS_RELU_NCHW || ((epi == TC_ATOMIC || epi == TC_STORE) && !split3 && !split2);
+  const int bn = (narrow_ok && N <= 32) ? 32 : (narrow_ok && N <= 64) ? 64 : 256;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int rc = make_map(&ma_hi, A_hi, M, K, TBM);
   if (rc) return rc;
-  rc = make_map(&mb_hi, B_hi, N, K, TBN);
+  rc = make_map(&mb_hi, B_hi, N, K, bn);
   if (rc) return rc;
   ma_lo = ma_hi;
   mb_lo = mb_hi;
@@ -414,13 +420,13 @@ int gemm_bf16_tc(int M, int N, int K, const bf16* A_hi, const bf16* A_lo, const 
     if (rc) return rc;
   }
   if (split3 || split2) {
-    rc = make_map(&mb_lo, B_lo, N, K, TBN);
+    rc = make_map(&mb_lo, B_lo, N, K, bn);
     if (rc) return rc;
   }
   TcArgs p;
   p.M = M; p.N = N; p.K = K;
   p.m_tiles = (M + TBM - 1) / TBM;
-  p.n_tiles = (N + TBN - 1) / TBN;
+  p.n_tiles = (N + bn - 1) / bn;
   p.kb_total = (K + TBK - 1) / TBK;
   if (split_k < 1) split_k = 1;
   if (split_k > p.kb_total) split_k = p.kb_total;
@@ -433,32 +439,36 @@ int gemm_bf16_tc(int M, int N, int K, const bf16* A_hi, const bf16* A_lo, const 
   p.o_hi = ex ? ex->o_hi : nullptr; p.o_lo = ex ? ex->o_lo : nullptr;
   p.o_hiT = ex ? ex->o_hiT : nullptr; p.o_loT = ex ? ex->o_loT : nullptr;
   if (epi == TC_EMBED && (N % 32)) return (int)cudaErrorInvalidValue;
-#define RIQN_TC_GO(NS, EP) return launch_tc<NS, EP>(ma_hi, ma_lo, mb_hi, mb_lo, p, s)
+#define RIQN_TC_GO(NS, EP) return launch_tc<NS, EP, 256>(ma_hi, ma_lo, mb_hi, mb_lo, p, s)
+#define RIQN_TC_NARROW(NS, EP)                                                                  \
+  if (bn == 32) return launch_tc<NS, EP, 32>(ma_hi, ma_lo, mb_hi, mb_lo, p, s);                  \
+  if (bn == 64) return launch_tc<NS, EP, 64>(ma_hi, ma_lo, mb_hi, mb_lo, p, s)
   if (split3) {
     switch (epi) {
       case TC_STORE: RIQN_TC_GO(3, TC_STORE);
       case TC_BIAS_RELU: RIQN_TC_GO(3, TC_BIAS_RELU);
       case TC_ATOMIC: RIQN_TC_GO(3, TC_ATOMIC);
       case TC_NOISY_WGRAD: RIQN_TC_GO(3, TC_NOISY_WGRAD);
-      case TC_BIAS_RELU_NCHW: RIQN_TC_GO(3, TC_BIAS_RELU_NCHW);
+      case TC_BIAS_RELU_NCHW: RIQN_TC_NARROW(3, TC_BIAS_RELU_NCHW); RIQN_TC_GO(3, TC_BIAS_RELU_NCHW);
       case TC_EMBED: RIQN_TC_GO(3, TC_EMBED);
     }
   } else if (split2) {
     switch (epi) {
-      case TC_BIAS_RELU_NCHW: RIQN_TC_GO(2, TC_BIAS_RELU_NCHW);
+      case TC_BIAS_RELU_NCHW: RIQN_TC_NARROW(2, TC_BIAS_RELU_NCHW); RIQN_TC_GO(2, TC_BIAS_RELU_NCHW);
       case TC_STORE: RIQN_TC_GO(2, TC_STORE);
       default: return (int)cudaErrorInvalidValue;
     }
   } else {
     switch (epi) {
-      case TC_STORE: RIQN_TC_GO(1, TC_STORE);
+      case TC_STORE: RIQN_TC_NARROW(1, TC_STORE); RIQN_TC_GO(1, TC_STORE);
       case TC_BIAS_RELU: RIQN_TC_GO(1, TC_BIAS_RELU);
-      case TC_ATOMIC: RIQN_TC_GO(1, TC_ATOMIC);
+      case TC_ATOMIC: RIQN_TC_NARROW(1, TC_ATOMIC); RIQN_TC_GO(1, TC_ATOMIC);
       case TC_NOISY_WGRAD: RIQN_TC_GO(1, TC_NOISY_WGRAD);
-      case TC_BIAS_RELU_NCHW: RIQN_TC_GO(1, TC_BIAS_RELU_NCHW);
+      case TC_BIAS_RELU_NCHW: RIQN_TC_NARROW(1, TC_BIAS_RELU_NCHW); RIQN_TC_GO(1, TC_BIAS_RELU_NCHW);
       case TC_EMBED: RIQN_TC_GO(1, TC_EMBED);
     }
   }
+#undef RIQN_TC_NARROW
 #undef RIQN_TC_GO
   return (int)cudaErrorInvalidValue;
 }
