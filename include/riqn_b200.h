@@ -87,9 +87,10 @@ int riqn_conv_bwd_tc(const riqn_conv_geom* g, const float* dout, const float* ou
 /* First layer on raw uint8 frames: pixel values 0..255 are exact in bf16, so the im2col operand has no lo image and the
  * reference's /255 (redis_memory.py:527-536) is folded into the weights: ws_hi / ws_lo = bf16 images of weight/255
  * (ws_lo == NULL: single-bf16 product).  col_px (M, K) and colT_px (K, M; may be NULL) hold pixel values; pass
- * wgrad_scale = 1/255 to riqn_conv_bwd_tc when it consumes colT_px.  in: 16-byte aligned, in_bstride % 16 == 0. */
+ * wgrad_scale = 1/255 to riqn_conv_bwd_tc when it consumes colT_px.  in: 16-byte aligned, in_bstride % 16 == 0.
+ * reuse_col != 0: col_px already holds the im2col of `in` (the online and target passes over next_states share it). */
 int riqn_conv_fwd_tc_u8(const riqn_conv_geom* g, const unsigned char* in, const void* ws_hi, const void* ws_lo,
-                        const float* bias, void* col_px, void* colT_px, float* out, void* stream);
+                        const float* bias, void* col_px, void* colT_px, float* out, int reuse_col, void* stream);
 /* split of (src * scale): bf16 hi / lo images of a scaled matrix (e.g. weight/255). */
 int riqn_split_bf16_scaled(long rows, int cols, const float* src, float scale, void* hi, void* lo, void* stream);
 

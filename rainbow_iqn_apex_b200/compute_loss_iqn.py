@@ -38,11 +38,12 @@ def loss_core(agent, states, actions, returns, next_states, nonterminals, keep_g
     dev = states.device
 
     on.reset_noise(noises[0])                                                       # :234
-    q_sel, _ = on.forward(next_states, K, tau=taus[0], fresh_weights=True)          # :235-237
+    cache = {}   # conv1's pixel im2col of next_states is shared by the online and the target pass
+    q_sel, _ = on.forward(next_states, K, tau=taus[0], fresh_weights=True, col_cache=cache)   # :235-237
     a_star = torch.empty(B, dtype=torch.int64, device=dev)
     call("riqn_argmax_mean", B, K, A, ptr(q_sel), ptr(a_star))                      # :238-245
     tg.reset_noise(noises[1])                                                       # :255
-    q_tgt, _ = tg.forward(next_states, Np, tau=taus[1], fresh_weights=True)         # :256-258
+    q_tgt, _ = tg.forward(next_states, Np, tau=taus[1], fresh_weights=True, col_cache=cache)  # :256-258
     on.reset_noise(noises[2])                                                       # :289
     keep = {} if keep_graph else None
     q_on, tau = on.forward(states, N, tau=taus[2], keep=keep, fresh_weights=True)   # :290

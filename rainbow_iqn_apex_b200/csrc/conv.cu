@@ -422,8 +422,8 @@ RIQN_API int riqn_conv_fwd_tc(const riqn_conv_geom* g, const void* in, int in_is
 
 // First layer on raw uint8 pixels: A = pixel values (exact in bf16, no lo image), B = bf16 hi (+lo) of weight/255.
 RIQN_API int riqn_conv_fwd_tc_u8(const riqn_conv_geom* g, const unsigned char* in, const void* ws_hi, const void* ws_lo,
-                                 const float* bias, void* col_px, void* colT_px, float* out, void* stream) {
-  riqn::note_launches(2);
+                                 const float* bias, void* col_px, void* colT_px, float* out, int reuse_col, void* stream) {
+  riqn::note_launches(reuse_col ? 1 : 2);
   cudaStream_t s = (cudaStream_t)stream;
   const long M = (long)g->B * g->OH * g->OW;
   const int K = g->Cin * g->KH * g->KW, chw = g->Cin * g->H * g->W, ohw = g->OH * g->OW;
@@ -434,8 +434,10 @@ RIQN_API int riqn_conv_fwd_tc_u8(const riqn_conv_geom* g, const unsigned char* i
     RIQN_CUDA(cudaFuncSetAttribute(im2col_u8_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     attr = true;
   }
-  im2col_u8_staged_kernel<<<dim3(g->B, 4), 256, chw, s>>>(*g, in, (bf16*)col_px, (bf16*)colT_px);
-  RIQN_LAUNCH_CHECK();
+  if (!reuse_col) {      // reuse_col: col_px already holds this input's im2col (another network's pass over it)
+    im2col_u8_staged_kernel<<<dim3(g->B, 4), 256, chw, s>>>(*g, in, (bf16*)col_px, (bf16*)colT_px);
+    RIQN_LAUNCH_CHECK();
+  }
   TcExtra ex;
   ex.ohw = ohw;
   return gemm_bf16_tc((int)M, g->Cout, K, (const bf16*)col_px, nullptr, (const bf16*)ws_hi, (const bf16*)ws_lo, out, g->Cout,

@@ -340,7 +340,7 @@ class DQN(nn.Module):
         return tau
 
     # ------------------------------------------------------------------ forward pieces
-    def trunk(self, x, keep=None):
+    def trunk(self, x, keep=None, col_cache=None):
         """conv1-3 + ReLU -> (B, 3136).  x: (B, history, 84, 84) uint8 (scaled by 1/255 on the fly) or
         fp32; may be a view with a larger batch stride (the replay window).  model.py:115-118"""
         _lib.require_device()
@@ -373,12 +373,16 @@ class DQN(nn.Module):
             elif i == 0 and u8 and x.stride(0) % 16 == 0 and x.data_ptr() % 16 == 0:
                 # raw-pixel path: pixel values are exact in bf16, /255 folded into the weights
                 ws_hi, ws_lo = self._conv1_px_ops
-                col_px = torch.empty(M, K, dtype=torch.bfloat16, device=dev)
+                ckey = (x.data_ptr(), tuple(x.shape), tuple(x.stride()))
+                reuse = col_cache is not None and ckey in col_cache and not bwd_tc
+                col_px = col_cache[ckey] if reuse else torch.empty(M, K, dtype=torch.bfloat16, device=dev)
+                if col_cache is not None:
+                    col_cache[ckey] = col_px          # the pixel im2col does not depend on the network's weights
                 if bwd_tc:
                     colTs[i] = torch.empty(K, M, dtype=torch.bfloat16, device=dev)
                     px_scale = 1.0 / 255.0
                 call("riqn_conv_fwd_tc_u8", g, ptr(inp), ptr(ws_hi), ptr(ws_lo) if fwd == "bf16x3" else None, ptr(conv.bias),
-                     ptr(col_px), ptr(colTs[i]), ptr(out))
+                     ptr(col_px), ptr(colTs[i]), ptr(out), 1 if reuse else 0)
                 if need_col32:
                     cols[i] = torch.empty(M, K, device=dev)
                     call("riqn_im2col_f32", g, ptr(inp), u8, ptr(cols[i]))
@@ -443,14 +447,14 @@ class DQN(nn.Module):
                         head_bwd_tc=bwd_tc, emb_bwd_tc=emb_tc)
         return q
 
-    def forward(self, x, num_quantiles=None, log=False, tau=None, keep=None, fresh_weights=False):
+    def forward(self, x, num_quantiles=None, log=False, tau=None, keep=None, fresh_weights=False, col_cache=None):
         """model.py:112-157.  Returns (q, quantiles) in IQN mode."""
         if self.rainbow_only:
             from . import c51
             return c51.forward(self, x, log=log, keep=keep, fresh_weights=fresh_weights)
         if not fresh_weights:
             self.compose_weights()
-        feat = self.trunk(x, keep)
+        feat = self.trunk(x, keep, col_cache)
         if tau is None:
             tau = self.draw_quantiles(num_quantiles * x.shape[0])
         else:
