@@ -42,7 +42,9 @@ struct TcCfg {
   static constexpr uint32_t kStageBytes = kAOps * kABytes + kBOps * kBBytes;         // 48 / 80 / 96 KB at BN = 256
   static constexpr int kStages = (192 * 1024) / kStageBytes > 6 ? 6 : (192 * 1024) / kStageBytes;
   static constexpr uint32_t kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;                   // two accumulator buffers (power of 2)
-  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr uint32_t kEpiStage = 32 * 32 * 4;  // per epilogue warp: 32 rows x 32 words for the store transpose
+  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + EPI_WARPS * kEpiStage;
+  static_assert(kSmemBytes <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
 };
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
@@ -117,6 +119,47 @@ __device__ __forceinline__ uint32_t umma_idesc_bf16(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+// The accumulator arrives with one ROW per lane (tcgen05.ld 32x32b): storing it directly makes every store instruction
+// touch 32 different lines with 16-byte pieces (~2 TB/s).  These helpers transpose a 32x32 chunk through a padded
+// per-warp shared-memory tile so that each store instruction writes one full row segment (128 B fp32 / 64 B bf16).
+// Tile rows are 32 words (128 B) apart and the 16-byte piece j of row r lives at piece slot j ^ (r & 7), so that both the
+// deposit (a quarter-warp = 8 rows, same j) and the drain (a quarter-warp = one row, 8 pieces) are bank-conflict free.
+// Each lane deposits its row with 8 STS.128; then every instruction moves FOUR rows: lane l handles piece (l & 7) of
+// row (l >> 3).
+constexpr int kStRow = 32;
+__device__ __forceinline__ void stage_row(uint32_t* st, const uint32_t (&w)[32], int lane) {
+  __syncwarp();
+  uint4* dst = reinterpret_cast<uint4*>(st + lane * kStRow);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) dst[j ^ (lane & 7)] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+  __syncwarp();
+}
+__device__ __forceinline__ void warp_store_rows_f32(uint32_t* st, const uint32_t (&w)[32], int lane, float* base, long ld,
+                                                    int rows_valid) {
+  stage_row(st, w, lane);
+  const int sub = lane >> 3, piece = lane & 7;
+#pragma unroll
+  for (int r0 = 0; r0 < 32; r0 += 4) {
+    const int r = r0 + sub;
+    if (r < rows_valid)
+      *reinterpret_cast<uint4*>(base + (long)r * ld + piece * 4) = *reinterpret_cast<const uint4*>(st + r * kStRow + ((piece ^ (r & 7)) * 4));
+  }
+}
+// w[0..15] = hi pairs (cols 2k, 2k+1), w[16..31] = lo pairs: pieces 0-3 go to the hi image, 4-7 to the lo image
+__device__ __forceinline__ void warp_store_rows_bf16(uint32_t* st, const uint32_t (&w)[32], int lane, bf16* hi_base,
+                                                     bf16* lo_base, long ld, int rows_valid) {
+  stage_row(st, w, lane);
+  const int sub = lane >> 3, piece = lane & 7;
+  bf16* dstb = piece < 4 ? hi_base : lo_base;
+  if (dstb == nullptr) return;
+#pragma unroll
+  for (int r0 = 0; r0 < 32; r0 += 4) {
+    const int r = r0 + sub;
+    if (r < rows_valid)
+      *reinterpret_cast<uint4*>(dstb + (long)r * ld + (piece & 3) * 8) = *reinterpret_cast<const uint4*>(st + r * kStRow + ((piece ^ (r & 7)) * 4));
+  }
+}
+
 struct TcArgs {
   int M, N, K;
   int m_tiles, n_tiles, k_splits, kb_per_split, kb_total;
@@ -148,6 +191,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
   uint64_t* tfull = bars + 2 * Cfg::kStages;   // [2]        MMA -> epilogue
   uint64_t* tempty = tfull + 2;                // [2]        epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint32_t* epi_stage = reinterpret_cast<uint32_t*>(smem + Cfg::kStages * Cfg::kStageBytes + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_units = p.m_tiles * p.n_tiles * p.k_splits;
@@ -237,6 +281,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
       const int m = mt * TBM + quarter * 32 + lane;
       const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * TBN;
       constexpr int HALF = TBN >= 64 ? TBN / 2 : TBN;        // BN = 32: the second warp set has no columns to drain
+      const float* embed_feat_row = nullptr;
+      if (EPI == TC_EMBED) embed_feat_row = p.feat + (long)((m < p.M ? m : 0) / p.batch) * p.N;
 #pragma unroll 1
       for (int c = chalf * HALF; c < (chalf + 1) * HALF && c < TBN; c += 32) {
         uint32_t v[32];
@@ -245,7 +291,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
         if (m < p.M && n0 < p.N) {
           if (EPI == TC_STORE || EPI == TC_BIAS_RELU) {
             float* crow = p.C + (long)m * p.ldc + n0;
-            if (n0 + 32 <= p.N) {
+            if (EPI == TC_STORE && n0 + 32 <= p.N) {
+              // handled below with the whole warp (coalesced row stores)
+            } else if (n0 + 32 <= p.N) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
                 float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
@@ -281,40 +329,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
             for (int j = 0; j < 32; ++j)
               if (n0 + j < p.N) cb[(long)j * p.ohw] = fmaxf(__uint_as_float(v[j]) + p.bias[n0 + j], 0.f);
           } else if (EPI == TC_EMBED) {
-            // x = feat[b] * relu(acc + bias)   (model.py:146-151); N % 32 == 0 is required by the host wrapper
-            const float* fr = p.feat + (long)(m / p.batch) * p.N + n0;   // batch = rows per sample: warp-broadcast when 32 | Nq
-            const long o = (long)m * p.N + n0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              float x[8];
-              uint32_t ph[4], pl[4];
-              {
-                const float4 f0 = __ldg(reinterpret_cast<const float4*>(fr + j));
-                const float4 f1 = __ldg(reinterpret_cast<const float4*>(fr + j + 4));
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
-                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j + 4));
-                const float ff[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
-                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-                for (int t = 0; t < 8; ++t) x[t] = ff[t] * fmaxf(__uint_as_float(v[j + t]) + bb[t], 0.f);
-              }
-#pragma unroll
-              for (int t = 0; t < 8; t += 2) {
-                const bf16 h0 = __float2bfloat16_rn(x[t]), h1 = __float2bfloat16_rn(x[t + 1]);
-                const bf16 l0 = __float2bfloat16_rn(x[t] - __bfloat162float(h0));
-                const bf16 l1 = __float2bfloat16_rn(x[t + 1] - __bfloat162float(h1));
-                ph[t / 2] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                pl[t / 2] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-                if (p.o_hiT) { p.o_hiT[(long)(n0 + j + t) * p.M + m] = h0; p.o_hiT[(long)(n0 + j + t + 1) * p.M + m] = h1; }
-                if (p.o_loT) { p.o_loT[(long)(n0 + j + t) * p.M + m] = l0; p.o_loT[(long)(n0 + j + t + 1) * p.M + m] = l1; }
-              }
-              if (p.C) {
-                *reinterpret_cast<float4*>(p.C + o + j) = make_float4(x[0], x[1], x[2], x[3]);
-                *reinterpret_cast<float4*>(p.C + o + j + 4) = make_float4(x[4], x[5], x[6], x[7]);
-              }
-              if (p.o_hi) *reinterpret_cast<uint4*>(p.o_hi + o + j) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-              if (p.o_lo) *reinterpret_cast<uint4*>(p.o_lo + o + j) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
-            }
+            // handled below with the whole warp
           } else {
             float* crow = p.C + (long)m * p.ldc + n0;
 #pragma unroll
@@ -330,6 +345,65 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
                     atomicAdd(p.out2 + (long)m * p.ldc + n0 + j, o * p.eps[(long)m * p.ldc + n0 + j]);
                 }
               }
+            }
+          }
+        }
+        if ((EPI == TC_STORE || EPI == TC_EMBED) && n0 + 32 <= p.N) {
+          uint32_t* st = epi_stage + (warp - 2) * (32 * kStRow);
+          const int m_base = mt * TBM + quarter * 32;
+          const int rows_valid = min(32, p.M - m_base);            // warp-uniform
+          if (rows_valid > 0) {
+            if (EPI == TC_STORE) {
+              warp_store_rows_f32(st, v, lane, p.C + (long)m_base * p.ldc + n0, p.ldc, rows_valid);
+            } else {
+              // x = feat[b] * relu(acc + bias)   (model.py:146-151); N % 32 == 0 is required by the host wrapper
+              const bool row_ok = m < p.M;
+              const float* fr = embed_feat_row + n0;                 // warp-broadcast when 32 | rows per sample
+              const float* br = p.bias + n0;
+              uint32_t hw[32];   // [0..15] hi pairs (cols 2k, 2k+1), [16..31] lo pairs
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 f = __ldg(reinterpret_cast<const float4*>(fr + j));
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(br + j));
+                const float x0 = f.x * fmaxf(__uint_as_float(v[j]) + bb.x, 0.f);
+                const float x1 = f.y * fmaxf(__uint_as_float(v[j + 1]) + bb.y, 0.f);
+                const float x2 = f.z * fmaxf(__uint_as_float(v[j + 2]) + bb.z, 0.f);
+                const float x3 = f.w * fmaxf(__uint_as_float(v[j + 3]) + bb.w, 0.f);
+                // packed conversions: one cvt.rn.bf16x2.f32 per pair, hi recovered with a shift / mask
+                const __nv_bfloat162 h01 = __floats2bfloat162_rn(x0, x1), h23 = __floats2bfloat162_rn(x2, x3);
+                const uint32_t w01 = *reinterpret_cast<const uint32_t*>(&h01), w23 = *reinterpret_cast<const uint32_t*>(&h23);
+                const __nv_bfloat162 l01 = __floats2bfloat162_rn(x0 - __uint_as_float(w01 << 16),
+                                                                 x1 - __uint_as_float(w01 & 0xffff0000u));
+                const __nv_bfloat162 l23 = __floats2bfloat162_rn(x2 - __uint_as_float(w23 << 16),
+                                                                 x3 - __uint_as_float(w23 & 0xffff0000u));
+                hw[j / 2] = w01;
+                hw[j / 2 + 1] = w23;
+                hw[16 + j / 2] = *reinterpret_cast<const uint32_t*>(&l01);
+                hw[16 + j / 2 + 1] = *reinterpret_cast<const uint32_t*>(&l23);
+                v[j] = __float_as_uint(x0); v[j + 1] = __float_as_uint(x1);
+                v[j + 2] = __float_as_uint(x2); v[j + 3] = __float_as_uint(x3);
+              }
+              // transposed (N, M) images: lane pairs exchange words so that each lane stores TWO consecutive rows of one
+              // column (even lanes column 2k, odd lanes column 2k+1): 32-bit stores, 64 B contiguous per column (M even)
+              const uint32_t sel = (lane & 1) ? 0x3276u : 0x5410u;
+#pragma unroll
+              for (int img = 0; img < 2; ++img) {
+                bf16* tb = img == 0 ? p.o_hiT : p.o_loT;
+                if (tb != nullptr) {                                   // warp-uniform
+                  uint32_t* tp = reinterpret_cast<uint32_t*>(tb + (long)(n0 + (lane & 1)) * p.M + (m & ~1));
+                  const long step = p.M;                               // 2 columns = 2*M bf16 = M words
+#pragma unroll
+                  for (int k = 0; k < 16; ++k) {
+                    const uint32_t mine = hw[img * 16 + k];
+                    const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, 1);
+                    if (row_ok) tp[(long)k * step] = __byte_perm(mine, other, sel);
+                  }
+                }
+              }
+              if (p.C) warp_store_rows_f32(st, v, lane, p.C + (long)m_base * p.N + n0, p.N, rows_valid);
+              if (p.o_hi || p.o_lo)
+                warp_store_rows_bf16(st, hw, lane, p.o_hi ? p.o_hi + (long)m_base * p.N + n0 : nullptr,
+                                     p.o_lo ? p.o_lo + (long)m_base * p.N + n0 : nullptr, p.N, rows_valid);
             }
           }
         }
@@ -438,7 +512,7 @@ int gemm_bf16_tc(int M, int N, int K, const bf16* A_hi, const bf16* A_lo, const 
   p.ohw = ex ? ex->ohw : 1; p.feat = ex ? ex->feat : nullptr; p.batch = ex ? ex->batch : 1;
   p.o_hi = ex ? ex->o_hi : nullptr; p.o_lo = ex ? ex->o_lo : nullptr;
   p.o_hiT = ex ? ex->o_hiT : nullptr; p.o_loT = ex ? ex->o_loT : nullptr;
-  if (epi == TC_EMBED && (N % 32)) return (int)cudaErrorInvalidValue;
+  if (epi == TC_EMBED && ((N % 32) || (M % 2))) return (int)cudaErrorInvalidValue;
 #define RIQN_TC_GO(NS, EP) return launch_tc<NS, EP, 256>(ma_hi, ma_lo, mb_hi, mb_lo, p, s)
 #define RIQN_TC_NARROW(NS, EP)                                                                  \
   if (bn == 32) return launch_tc<NS, EP, 32>(ma_hi, ma_lo, mb_hi, mb_lo, p, s);                  \
