@@ -160,6 +160,22 @@ __device__ __forceinline__ void warp_store_rows_bf16(uint32_t* st, const uint32_
   }
 }
 
+// Transposed (N, M) bf16 image of a chunk whose 16 words hold the column pairs (2k, 2k+1) of this lane's row: lane pairs
+// exchange words so that each lane stores TWO consecutive rows of ONE column (even lanes column 2k, odd lanes 2k+1) --
+// 32-bit stores, 64 B contiguous per column.  M must be even.
+__device__ __forceinline__ void store_transposed_pairs(bf16* tb, const uint32_t* w16, int n0, int m, int M, int lane,
+                                                       bool row_ok) {
+  const uint32_t sel = (lane & 1) ? 0x3276u : 0x5410u;
+  uint32_t* tp = reinterpret_cast<uint32_t*>(tb + (long)(n0 + (lane & 1)) * M + (m & ~1));
+  const long step = M;   // 2 columns = 2*M bf16 = M words
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const uint32_t mine = w16[k];
+    const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, 1);
+    if (row_ok) tp[(long)k * step] = __byte_perm(mine, other, sel);
+  }
+}
+
 struct TcArgs {
   int M, N, K;
   int m_tiles, n_tiles, k_splits, kb_per_split, kb_total;
@@ -276,22 +292,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
       const int nt = t % p.n_tiles, mt = t / p.n_tiles;
       const int as = local & 1;
       const uint32_t aphase = (local >> 1) & 1;
-      mbar_wait(&tfull[as], aphase);
-      tc_fence_after();
       const int m = mt * TBM + quarter * 32 + lane;
-      const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * TBN;
       constexpr int HALF = TBN >= 64 ? TBN / 2 : TBN;        // BN = 32: the second warp set has no columns to drain
       const float* embed_feat_row = nullptr;
-      if (EPI == TC_EMBED) embed_feat_row = p.feat + (long)((m < p.M ? m : 0) / p.batch) * p.N;
+      if (EPI == TC_EMBED) {
+        embed_feat_row = p.feat + (long)((m < p.M ? m : 0) / p.batch) * p.N;
+        const int nf = nt * TBN + chalf * HALF;                // first chunk's feat / bias lines -> L1 while the MMA finishes
+        if (nf + 32 <= p.N) {
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(embed_feat_row + nf));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(p.bias + nf));
+        }
+      }
+      mbar_wait(&tfull[as], aphase);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * TBN;
 #pragma unroll 1
       for (int c = chalf * HALF; c < (chalf + 1) * HALF && c < TBN; c += 32) {
+        const int n0 = nt * TBN + c;
+        if (EPI == TC_EMBED && c + 32 < (chalf + 1) * HALF && n0 + 64 <= p.N) {   // next chunk's feat / bias lines -> L1
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(embed_feat_row + n0 + 32));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(p.bias + n0 + 32));
+        }
         uint32_t v[32];
         tmem_ld32(trow + c, v);
-        const int n0 = nt * TBN + c;
         if (m < p.M && n0 < p.N) {
           if (EPI == TC_STORE || EPI == TC_BIAS_RELU) {
             float* crow = p.C + (long)m * p.ldc + n0;
-            if (EPI == TC_STORE && n0 + 32 <= p.N) {
+            if (n0 + 32 <= p.N && (EPI == TC_STORE || (p.M & 1) == 0)) {
               // handled below with the whole warp (coalesced row stores)
             } else if (n0 + 32 <= p.N) {
 #pragma unroll
@@ -348,12 +375,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
             }
           }
         }
-        if ((EPI == TC_STORE || EPI == TC_EMBED) && n0 + 32 <= p.N) {
+        if ((EPI == TC_STORE || EPI == TC_EMBED || (EPI == TC_BIAS_RELU && (p.M & 1) == 0)) && n0 + 32 <= p.N) {
           uint32_t* st = epi_stage + (warp - 2) * (32 * kStRow);
           const int m_base = mt * TBM + quarter * 32;
           const int rows_valid = min(32, p.M - m_base);            // warp-uniform
           if (rows_valid > 0) {
             if (EPI == TC_STORE) {
+              warp_store_rows_f32(st, v, lane, p.C + (long)m_base * p.ldc + n0, p.ldc, rows_valid);
+            } else if (EPI == TC_BIAS_RELU) {
+              const float* br = p.bias + n0;
+              uint32_t hw[16];
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(br + j));
+                const float x0 = fmaxf(__uint_as_float(v[j]) + bb.x, 0.f), x1 = fmaxf(__uint_as_float(v[j + 1]) + bb.y, 0.f);
+                const float x2 = fmaxf(__uint_as_float(v[j + 2]) + bb.z, 0.f), x3 = fmaxf(__uint_as_float(v[j + 3]) + bb.w, 0.f);
+                const __nv_bfloat162 h01 = __floats2bfloat162_rn(x0, x1), h23 = __floats2bfloat162_rn(x2, x3);
+                hw[j / 2] = *reinterpret_cast<const uint32_t*>(&h01);
+                hw[j / 2 + 1] = *reinterpret_cast<const uint32_t*>(&h23);
+                v[j] = __float_as_uint(x0); v[j + 1] = __float_as_uint(x1);
+                v[j + 2] = __float_as_uint(x2); v[j + 3] = __float_as_uint(x3);
+              }
+              if (p.o_hiT) store_transposed_pairs(p.o_hiT, hw, n0, m, p.M, lane, m < p.M);
               warp_store_rows_f32(st, v, lane, p.C + (long)m_base * p.ldc + n0, p.ldc, rows_valid);
             } else {
               // x = feat[b] * relu(acc + bias)   (model.py:146-151); N % 32 == 0 is required by the host wrapper
@@ -383,23 +426,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
                 v[j] = __float_as_uint(x0); v[j + 1] = __float_as_uint(x1);
                 v[j + 2] = __float_as_uint(x2); v[j + 3] = __float_as_uint(x3);
               }
-              // transposed (N, M) images: lane pairs exchange words so that each lane stores TWO consecutive rows of one
-              // column (even lanes column 2k, odd lanes column 2k+1): 32-bit stores, 64 B contiguous per column (M even)
-              const uint32_t sel = (lane & 1) ? 0x3276u : 0x5410u;
-#pragma unroll
-              for (int img = 0; img < 2; ++img) {
-                bf16* tb = img == 0 ? p.o_hiT : p.o_loT;
-                if (tb != nullptr) {                                   // warp-uniform
-                  uint32_t* tp = reinterpret_cast<uint32_t*>(tb + (long)(n0 + (lane & 1)) * p.M + (m & ~1));
-                  const long step = p.M;                               // 2 columns = 2*M bf16 = M words
-#pragma unroll
-                  for (int k = 0; k < 16; ++k) {
-                    const uint32_t mine = hw[img * 16 + k];
-                    const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, 1);
-                    if (row_ok) tp[(long)k * step] = __byte_perm(mine, other, sel);
-                  }
-                }
-              }
+              if (p.o_hiT) store_transposed_pairs(p.o_hiT, hw, n0, m, p.M, lane, row_ok);        // warp-uniform tests
+              if (p.o_loT) store_transposed_pairs(p.o_loT, hw + 16, n0, m, p.M, lane, row_ok);
               if (p.C) warp_store_rows_f32(st, v, lane, p.C + (long)m_base * p.N + n0, p.N, rows_valid);
               if (p.o_hi || p.o_lo)
                 warp_store_rows_bf16(st, hw, lane, p.o_hi ? p.o_hi + (long)m_base * p.N + n0 : nullptr,
