@@ -244,7 +244,36 @@ __global__ void im2col_u8_staged_kernel(riqn_conv_geom g, const uint8_t* __restr
     if (ih < 0 || ih >= g.H || iw < 0 || iw >= g.W) return 0u;
     return __float_as_uint((float)img[(c * g.H + ih) * g.W + iw]) >> 16;     // exact bf16 bits of 0..255
   };
-  if (col) {
+  // Fast path (the Atari first layer: 8-wide rows, stride 4, pad 1, nothing hangs over the right / bottom edge): a
+  // kernel row is bytes 4*ow-1 .. 4*ow+6 of an image row = byte 3 of word ow-1, word ow, bytes 0..2 of word ow+1.
+  const bool fast = g.KW == 8 && g.stride == 4 && g.pad == 1 && (g.W & 3) == 0 && (g.OW - 1) * 4 + 6 < g.W &&
+                    (g.OH - 1) * 4 - 1 + g.KH - 1 < g.H;
+  auto cvt2 = [](uint32_t w, uint32_t sa, uint32_t sb) -> uint32_t {      // two bytes of w -> two bf16 (exact)
+    const float fa = __uint_as_float(__byte_perm(w, 0x4B000000u, sa)) - 8388608.0f;
+    const float fb = __uint_as_float(__byte_perm(w, 0x4B000000u, sb)) - 8388608.0f;
+    return __byte_perm(__float_as_uint(fa), __float_as_uint(fb), 0x7632);
+  };
+  if (col && fast) {
+    const uint32_t* img32 = reinterpret_cast<const uint32_t*>(img);
+    const int wpr = g.W >> 2;                                   // words per image row
+    for (int item = part * blockDim.x + threadIdx.x; item < ohw * K8; item += parts * blockDim.x) {
+      const int m = item / K8, kr = item - m * K8;              // kr = c * KH + kh
+      const int oh = m / g.OW, ow = m - oh * g.OW;
+      const int c = kr / g.KH, kh = kr - c * g.KH;
+      const int ih = oh * 4 - 1 + kh;
+      uint4 o = make_uint4(0u, 0u, 0u, 0u);
+      if (ih >= 0) {
+        const uint32_t* rowp = img32 + (c * g.H + ih) * wpr + ow;
+        const uint32_t w0 = ow > 0 ? rowp[-1] : 0u, w1 = rowp[0], w2 = rowp[1];
+        const uint32_t a = __byte_perm(w0, w1, 0x0043);          // bytes: w0.3, w1.0   (upper two unused)
+        o.x = cvt2(a, 0x7650, 0x7651);
+        o.y = cvt2(w1, 0x7651, 0x7652);
+        o.z = cvt2(__byte_perm(w1, w2, 0x0043), 0x7650, 0x7651);
+        o.w = cvt2(w2, 0x7651, 0x7652);
+      }
+      *reinterpret_cast<uint4*>(col + (b * ohw + m) * K + kr * 8) = o;
+    }
+  } else if (col) {
     for (int item = part * blockDim.x + threadIdx.x; item < ohw * K8; item += parts * blockDim.x) {
       const int m = item / K8, k0 = (item - m * K8) * 8;
       const int oh = m / g.OW, ow = m - oh * g.OW;
@@ -276,6 +305,50 @@ __global__ void im2col_u8_staged_kernel(riqn_conv_geom g, const uint8_t* __restr
       *reinterpret_cast<uint4*>(colT + (long)k * M + b * ohw + m0) =
           make_uint4(e[0] | (e[1] << 16), e[2] | (e[3] << 16), e[4] | (e[5] << 16), e[6] | (e[7] << 16));
     }
+  }
+}
+
+// fp32 NCHW input, staged: one block per sample converts its input ONCE into packed (hi | lo << 16) words in shared
+// memory (coalesced 16-byte loads; the plain kernel converts every pixel KH*KW/stride^2 times), then assembles the
+// (M, K) hi / lo rows from shared memory with 32-bit index arithmetic.  Bit-identical to im2col_bf16_kernel.
+__global__ void __launch_bounds__(256) im2col_f32_staged_kernel(riqn_conv_geom g, const float* __restrict__ in,
+                                                                bf16* __restrict__ hi, bf16* __restrict__ lo) {
+  extern __shared__ __align__(16) uint32_t simg[];
+  const int chw = g.Cin * g.H * g.W, K = g.Cin * g.KH * g.KW, K8 = K / 8, ohw = g.OH * g.OW;
+  const long b = blockIdx.x;
+  const float4* src = reinterpret_cast<const float4*>(in + b * g.in_bstride);
+  for (int i = threadIdx.x; i < chw / 4; i += blockDim.x) {
+    const float4 v = __ldg(src + i);
+    const float x[4] = {v.x, v.y, v.z, v.w};
+    uint32_t w[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const bf16 h = __float2bfloat16_rn(x[t]);
+      const bf16 l = __float2bfloat16_rn(x[t] - __bfloat162float(h));
+      w[t] = (uint32_t)__bfloat16_as_ushort(h) | ((uint32_t)__bfloat16_as_ushort(l) << 16);
+    }
+    reinterpret_cast<uint4*>(simg)[i] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  __syncthreads();
+  const int hw = g.H * g.W;
+  for (int item = threadIdx.x; item < ohw * K8; item += blockDim.x) {
+    const int m = item / K8, k0 = (item - m * K8) * 8;
+    const int oh = m / g.OW, ow = m - oh * g.OW;
+    int kw = k0 % g.KW, kh = (k0 / g.KW) % g.KH, c = k0 / (g.KW * g.KH);
+    const int ih0 = oh * g.stride - g.pad, iw0 = ow * g.stride - g.pad;
+    uint32_t e[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int ih = ih0 + kh, iw = iw0 + kw;
+      e[t] = ((unsigned)ih < (unsigned)g.H && (unsigned)iw < (unsigned)g.W) ? simg[c * hw + ih * g.W + iw] : 0u;
+      if (++kw == g.KW) { kw = 0; if (++kh == g.KH) { kh = 0; ++c; } }
+    }
+    const long o = (b * ohw + m) * K + k0;
+    *reinterpret_cast<uint4*>(hi + o) = make_uint4(__byte_perm(e[0], e[1], 0x5410), __byte_perm(e[2], e[3], 0x5410),
+                                                   __byte_perm(e[4], e[5], 0x5410), __byte_perm(e[6], e[7], 0x5410));
+    if (lo)
+      *reinterpret_cast<uint4*>(lo + o) = make_uint4(__byte_perm(e[0], e[1], 0x7632), __byte_perm(e[2], e[3], 0x7632),
+                                                     __byte_perm(e[4], e[5], 0x7632), __byte_perm(e[6], e[7], 0x7632));
   }
 }
 
@@ -407,7 +480,19 @@ RIQN_API int riqn_conv_fwd_tc(const riqn_conv_geom* g, const void* in, int in_is
   const int K = g->Cin * g->KH * g->KW;
   if (K % 8 || (colT_hi && M % 8)) return (int)cudaErrorInvalidValue;
   if (in_is_u8) im2col_bf16_u8_kernel<<<grid_for(M * K / 8), 256, 0, s>>>(*g, (const uint8_t*)in, (bf16*)col_hi, (bf16*)col_lo);
-  else im2col_bf16_kernel<float><<<grid_for(M * K / 8), 256, 0, s>>>(*g, (const float*)in, (bf16*)col_hi, (bf16*)col_lo);
+  else {
+    const int chw = g->Cin * g->H * g->W;
+    if (chw % 4 == 0 && g->in_bstride % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && chw * 4 <= 96 * 1024) {
+      static bool attr = false;
+      if (!attr) {
+        RIQN_CUDA(cudaFuncSetAttribute(im2col_f32_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        attr = true;
+      }
+      im2col_f32_staged_kernel<<<g->B, 256, (size_t)chw * 4, s>>>(*g, (const float*)in, (bf16*)col_hi, (bf16*)col_lo);
+    } else {
+      im2col_bf16_kernel<float><<<grid_for(M * K / 8), 256, 0, s>>>(*g, (const float*)in, (bf16*)col_hi, (bf16*)col_lo);
+    }
+  }
   RIQN_LAUNCH_CHECK();
   if (colT_hi) {
     if (in_is_u8) im2col_bf16_t_kernel<uint8_t><<<grid_for(M * K / 8), 256, 0, s>>>(*g, (const uint8_t*)in, (bf16*)colT_hi);

@@ -127,6 +127,92 @@ __global__ void embed_bwd_tile_kernel(int B, int Nq, int F, const __nv_bfloat16*
   }
 }
 
+// Wide variant (Nq even): one block = one sample x 128 features; lane owns 4 consecutive features (16-byte dX loads,
+// 8-byte x loads), warp w owns rows q = w, w+8, ... so that all of a thread's loads are in flight together.  dpre goes
+// through an XOR-swizzled shared tile as (q, q+1) bf16 pairs and leaves as full 128-byte rows of dpreT.
+__global__ void __launch_bounds__(256) embed_bwd_wide_kernel(int B, int Nq, int F, const __nv_bfloat16* __restrict__ x_hi,
+                                                             const __nv_bfloat16* __restrict__ x_lo,
+                                                             const float* __restrict__ feat, const float* __restrict__ dX,
+                                                             __nv_bfloat16* __restrict__ dpreT, float* __restrict__ dfeat,
+                                                             float* __restrict__ dbe) {
+  __shared__ uint32_t tile[128][32];      // [feature][pair of rows], column index XOR-ed with (feature >> 2) & 31
+  __shared__ float red[2][8][128];
+  const int f0 = blockIdx.x * 128, b = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long R = (long)B * Nq;
+  const int fl = 4 * lane, f = f0 + fl;                 // F % 4 == 0 is checked by the host
+  const bool f_ok = f < F;
+  float4 ft = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (f_ok) ft = *reinterpret_cast<const float4*>(feat + (long)b * F + f);
+  float facc[4] = {0.f, 0.f, 0.f, 0.f}, bacc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int q0 = 0; q0 < Nq; q0 += 64) {
+    // rows handled by this thread in this pass: q0 + 2*(warp + 8*i) + {0, 1}, i < 4
+    float4 dx[8];
+    uint2 xh[8], xl[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int q = q0 + 2 * (warp + 8 * (i >> 1)) + (i & 1);
+      dx[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      xh[i] = make_uint2(0u, 0u);
+      xl[i] = make_uint2(0u, 0u);
+      if (q < Nq && f_ok) {
+        const long o = ((long)b * Nq + q) * F + f;
+        dx[i] = __ldg(reinterpret_cast<const float4*>(dX + o));
+        xh[i] = __ldg(reinterpret_cast<const uint2*>(x_hi + o));
+        if (x_lo) xl[i] = __ldg(reinterpret_cast<const uint2*>(x_lo + o));
+      }
+    }
+    uint32_t pk[4][4];                                   // [pair][feature]
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float x[4] = {__uint_as_float(xh[i].x << 16) + __uint_as_float(xl[i].x << 16),
+                          __uint_as_float(xh[i].x & 0xffff0000u) + __uint_as_float(xl[i].x & 0xffff0000u),
+                          __uint_as_float(xh[i].y << 16) + __uint_as_float(xl[i].y << 16),
+                          __uint_as_float(xh[i].y & 0xffff0000u) + __uint_as_float(xl[i].y & 0xffff0000u)};
+      const float d[4] = {dx[i].x, dx[i].y, dx[i].z, dx[i].w};
+      const float fv[4] = {ft.x, ft.y, ft.z, ft.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        facc[j] = fmaf(d[j], x[j], facc[j]);
+        const float dp = x[j] > 0.f ? d[j] * fv[j] : 0.f;
+        bacc[j] += dp;
+        const uint32_t hb = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(dp));
+        if (i & 1) pk[i >> 1][j] |= hb << 16; else pk[i >> 1][j] = hb;
+      }
+    }
+#pragma unroll
+    for (int pr = 0; pr < 4; ++pr) {
+      const int col = warp + 8 * pr;                     // pair index within the 64-row pass
+#pragma unroll
+      for (int j = 0; j < 4; ++j) tile[fl + j][col ^ lane] = pk[pr][j];      // ((fl + j) >> 2) & 31 == lane
+    }
+    __syncthreads();
+    // feature row ff: 32 lanes x one (q, q+1) pair = 128 contiguous bytes of dpreT
+#pragma unroll 4
+    for (int ff = warp; ff < 128; ff += 8) {
+      const int q = q0 + 2 * lane;
+      if (f0 + ff < F && q < Nq)
+        *reinterpret_cast<uint32_t*>(dpreT + (long)(f0 + ff) * R + (long)b * Nq + q) = tile[ff][lane ^ ((ff >> 2) & 31)];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    red[0][warp][fl + j] = facc[j];
+    red[1][warp][fl + j] = bacc[j];
+  }
+  __syncthreads();
+  if (threadIdx.x < 128 && f0 + threadIdx.x < F) {
+    const int t = threadIdx.x;
+    float fs = 0.f, bs = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { fs += red[0][j][t]; bs += red[1][j][t]; }
+    const float fv = feat[(long)b * F + f0 + t];
+    dfeat[(long)b * F + f0 + t] = fv > 0.f ? fs / fv : 0.f;
+    atomicAdd(&dbe[f0 + t], bs);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // NoisyLinear: (optional) eps_w = eps_out (x) eps_in, then W_eff = mu + sigma*eps_w, b_eff likewise
 // (model.py:39-53).  training == 0 gives the eval-mode weights (mu only).
@@ -199,6 +285,82 @@ __global__ void z_dueling_fwd_kernel(long R, int B, int A, const float* __restri
     const int Nq = (int)(R / B);
     const long b = r / Nq, qi = r - b * Nq;                 // sample-major row -> quantile-major output row
     if (lane < A) q[(qi * B + b) * A + lane] = v + mine - asum / (float)A;
+  }
+}
+
+// Four rows per warp: every weight fetched from shared memory (16-byte reads) is used for four rows, all 32 row loads
+// of a thread are in flight together, and the four dot products of one output are reduced with 6 shuffles (a
+// transpose-reduce over lane bits 4 and 3, then a butterfly over bits 2..0): lane l ends up with the sums of row
+// rr(l) = 2*bit3(l) + bit4(l), and the 8 lanes of a row share out the A advantages.
+template <int HID>
+__global__ void __launch_bounds__(256) z_dueling_fwd4_kernel(long R, int B, int A, const float* __restrict__ H,
+                                                             const float* __restrict__ Wz, const float* __restrict__ bz,
+                                                             float* __restrict__ q) {
+  extern __shared__ float sW[];  // (1+A) * HID
+  for (int i = threadIdx.x; i < (1 + A) * HID / 4; i += blockDim.x)
+    reinterpret_cast<float4*>(sW)[i] = reinterpret_cast<const float4*>(Wz)[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  constexpr int T = HID / 128;
+  const int Nq = (int)(R / B);
+  const int my_rr = ((lane >> 3) & 1) * 2 + ((lane >> 4) & 1), my_j = lane & 7;
+  for (long r0 = ((long)blockIdx.x * wpb + warp) * 4; r0 < R; r0 += (long)gridDim.x * wpb * 4) {
+    float4 hv[4][T], ha[4][T];
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+      const long r = r0 + rr < R ? r0 + rr : R - 1;
+      const float4* h = reinterpret_cast<const float4*>(H + r * (2 * HID));
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        hv[rr][t] = __ldg(h + lane + 32 * t);
+        ha[rr][t] = __ldg(h + HID / 4 + lane + 32 * t);
+      }
+    }
+    float v = 0.f, asum = 0.f, mine0 = 0.f, mine1 = 0.f, mine2 = 0.f;
+    for (int k = 0; k <= A; ++k) {
+      const float4* wk = reinterpret_cast<const float4*>(sW + k * HID);
+      float p[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        const float4 w = wk[lane + 32 * t];
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+          const float4 x = k == 0 ? hv[rr][t] : ha[rr][t];
+          p[rr] = fmaf(x.x, w.x, p[rr]);
+          p[rr] = fmaf(x.y, w.y, p[rr]);
+          p[rr] = fmaf(x.z, w.z, p[rr]);
+          p[rr] = fmaf(x.w, w.w, p[rr]);
+        }
+      }
+      const bool b4 = lane & 16, b3 = lane & 8;
+      const float a01 = (b4 ? p[1] : p[0]) + __shfl_xor_sync(0xffffffffu, b4 ? p[0] : p[1], 16);
+      const float a23 = (b4 ? p[3] : p[2]) + __shfl_xor_sync(0xffffffffu, b4 ? p[2] : p[3], 16);
+      float c = (b3 ? a23 : a01) + __shfl_xor_sync(0xffffffffu, b3 ? a01 : a23, 8);
+      c += __shfl_xor_sync(0xffffffffu, c, 4);
+      c += __shfl_xor_sync(0xffffffffu, c, 2);
+      c += __shfl_xor_sync(0xffffffffu, c, 1);
+      c += bz[k];
+      if (k == 0) {
+        v = c;
+      } else {
+        asum += c;
+        const int a = k - 1;
+        if ((a & 7) == my_j) {                          // A <= 24 on this path
+          if (a < 8) mine0 = c; else if (a < 16) mine1 = c; else mine2 = c;
+        }
+      }
+    }
+    const long r = r0 + my_rr;
+    if (r < R) {
+      const long b = r / Nq, qi = r - b * Nq;                 // sample-major row -> quantile-major output row
+      float* out = q + (qi * B + b) * A;
+#pragma unroll
+      for (int g = 0; g < 3; ++g) {
+        const int a = my_j + 8 * g;
+        const float mg = g == 0 ? mine0 : (g == 1 ? mine1 : mine2);
+        if (a < A) out[a] = v + mg - asum / (float)A;
+      }
+    }
   }
 }
 
@@ -487,9 +649,15 @@ RIQN_API int riqn_quantile_embed_bwd_tc(int batch, int num_quantiles, int embed_
   cudaStream_t s = (cudaStream_t)stream;
   const long R = (long)batch * num_quantiles;
   if (R % 8) return (int)cudaErrorInvalidValue;
-  dim3 grid((feat_dim + 31) / 32, batch);
-  embed_bwd_tile_kernel<<<grid, 256, 0, s>>>(batch, num_quantiles, feat_dim, (const __nv_bfloat16*)x_hi,
-                                             (const __nv_bfloat16*)x_lo, feat, dx, (__nv_bfloat16*)dpreT, dfeat, grad_iqn_b);
+  if (num_quantiles % 2 == 0 && feat_dim % 4 == 0) {
+    dim3 grid((feat_dim + 127) / 128, batch);
+    embed_bwd_wide_kernel<<<grid, 256, 0, s>>>(batch, num_quantiles, feat_dim, (const __nv_bfloat16*)x_hi,
+                                               (const __nv_bfloat16*)x_lo, feat, dx, (__nv_bfloat16*)dpreT, dfeat, grad_iqn_b);
+  } else {
+    dim3 grid((feat_dim + 31) / 32, batch);
+    embed_bwd_tile_kernel<<<grid, 256, 0, s>>>(batch, num_quantiles, feat_dim, (const __nv_bfloat16*)x_hi,
+                                               (const __nv_bfloat16*)x_lo, feat, dx, (__nv_bfloat16*)dpreT, dfeat, grad_iqn_b);
+  }
   RIQN_LAUNCH_CHECK();
   const int m_tiles = (feat_dim + 127) / 128;
   const int split = (148 + m_tiles - 1) / m_tiles;
@@ -577,7 +745,16 @@ RIQN_API int riqn_dueling_fwd(long rows, int batch, int hidden, int action_space
     RIQN_CUDA(cudaFuncSetAttribute(z_dueling_fwd_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     attr = true;
   }
-  z_dueling_fwd_kernel<512><<<148 * 4, 256, smem, (cudaStream_t)stream>>>(rows, batch, action_space, h, wz, bz, q);
+  if (action_space <= 24) {
+    static bool attr4 = false;
+    if (!attr4) {
+      RIQN_CUDA(cudaFuncSetAttribute(z_dueling_fwd4_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      attr4 = true;
+    }
+    z_dueling_fwd4_kernel<512><<<148, 256, smem, (cudaStream_t)stream>>>(rows, batch, action_space, h, wz, bz, q);
+  } else {
+    z_dueling_fwd_kernel<512><<<148 * 4, 256, smem, (cudaStream_t)stream>>>(rows, batch, action_space, h, wz, bz, q);
+  }
   return (int)cudaGetLastError();
 }
 
