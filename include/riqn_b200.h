@@ -115,6 +115,28 @@ int riqn_noisy_compose(int out_features, int in_features, const float* weight_mu
                        float* weight_epsilon, const float* eps_in, const float* eps_out, const float* bias_mu,
                        const float* bias_sigma, float* bias_epsilon, float* w_eff, float* b_eff, int training,
                        void* stream);
+
+/* One NoisyLinear layer of a network-wide noise reset (riqn_noisy_reset_net). */
+typedef struct riqn_noisy_layer {
+  int out_features, in_features;                 /* in_features % 4 == 0 */
+  const float* weight_mu;
+  const float* weight_sigma;
+  float* weight_epsilon;                         /* (out, in): eps_out (x) eps_in is written here */
+  const float* bias_mu;
+  const float* bias_sigma;
+  float* bias_epsilon;                           /* (out) */
+  float* eps_in;                                 /* (in)  factor vector f(eps_in): drawn here when sample != 0 */
+  float* eps_out;                                /* (out) factor vector f(eps_out) */
+  float* w_eff;                                  /* (out, in) mu + sigma * eps   (mu when training == 0) */
+  float* b_eff;                                  /* (out) */
+  unsigned long long stream_in, stream_out;      /* Philox stream ids of the two draws */
+} riqn_noisy_layer;
+
+/* DQN.reset_noise() for all NoisyLinear layers of one network in two launches (model.py:159-162 -> :39-43 -> :32-37):
+ * draw every factor vector (sample != 0; same values as riqn_noisy_sample on the same seed / stream ids), then
+ * compose every layer like riqn_noisy_compose.  layers is a HOST array of n_layers <= 8 descriptors. */
+int riqn_noisy_reset_net(int n_layers, const riqn_noisy_layer* layers, unsigned long long seed, int sample, int training,
+                         const riqn_dyn_state* dyn, void* stream);
 /* h = relu(x w_eff^T + b_eff)   (the hidden layers fcnoisy_h_v | fcnoisy_h_a concatenated along out_features,
  * model.py:153-154 with the F.relu folded in). */
 int riqn_noisy_linear_fwd(long rows, int in_features, int out_features, const float* x, const float* w_eff,

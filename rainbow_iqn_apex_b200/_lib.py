@@ -20,6 +20,14 @@ class ConvGeom(C.Structure):
                 ("OW", C.c_int), ("in_bstride", C.c_long)]
 
 
+class NoisyLayer(C.Structure):
+    """riqn_noisy_layer (include/riqn_b200.h)"""
+    _fields_ = [("out_features", C.c_int), ("in_features", C.c_int), ("weight_mu", _P), ("weight_sigma", _P),
+                ("weight_epsilon", _P), ("bias_mu", _P), ("bias_sigma", _P), ("bias_epsilon", _P), ("eps_in", _P),
+                ("eps_out", _P), ("w_eff", _P), ("b_eff", _P), ("stream_in", C.c_ulonglong),
+                ("stream_out", C.c_ulonglong)]
+
+
 # name -> argtypes (everything returns int).  Must list every symbol of include/riqn_b200.h.
 SIGNATURES = {
     "riqn_version": [],
@@ -35,6 +43,7 @@ SIGNATURES = {
     "riqn_fill_uniform": [C.c_long, C.c_ulonglong, C.c_ulonglong, _P, _P, _P],
     "riqn_noisy_sample": [C.c_long, C.c_ulonglong, C.c_ulonglong, _P, _P, _P],
     "riqn_noisy_compose": [C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, _P],
+    "riqn_noisy_reset_net": [C.c_int, C.POINTER(NoisyLayer), C.c_ulonglong, C.c_int, C.c_int, _P, _P],
     "riqn_noisy_linear_fwd": [C.c_long, C.c_int, C.c_int, _P, _P, _P, _P, _P],
     "riqn_noisy_linear_dgrad": [C.c_long, C.c_int, C.c_int, _P, _P, _P, _P],
     "riqn_noisy_linear_wgrad": [C.c_long, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],

@@ -246,6 +246,64 @@ __global__ void noisy_compose_kernel(int out_f, int in_f, const float* __restric
   }
 }
 
+// Network-wide variants: the (<= 8) layers of a network travel by value in the launch parameters.
+struct NoisyNet {
+  riqn_noisy_layer l[8];
+  int n;
+  int blk_end[16];     // exclusive prefix of blocks per segment (fill: 2 per layer) / per layer (compose)
+};
+
+__global__ void noisy_fill_net_kernel(NoisyNet net, uint64_t seed, const riqn_dyn_state* __restrict__ dyn) {
+  int seg = 0;
+  while (seg < 2 * net.n - 1 && (int)blockIdx.x >= net.blk_end[seg]) ++seg;
+  const riqn_noisy_layer& L = net.l[seg >> 1];
+  const bool is_out = seg & 1;
+  const long n = is_out ? L.out_features : L.in_features;
+  float* out = is_out ? L.eps_out : L.eps_in;
+  uint64_t stream = is_out ? L.stream_out : L.stream_in;
+  if (dyn) stream += dyn->rng_offset;
+  const long i4 = (long)(blockIdx.x - (seg ? net.blk_end[seg - 1] : 0)) * blockDim.x + threadIdx.x;
+  if (i4 * 4 >= n) return;
+  const uint4 r = Philox::draw(seed, stream, (uint64_t)i4);                 // identical to fill_scaled_normal_kernel
+  const float u0 = Philox::u01(r.x), u1 = Philox::u01(r.y), u2 = Philox::u01(r.z), u3 = Philox::u01(r.w);
+  const float ra = sqrtf(-2.f * logf(u0)), rb = sqrtf(-2.f * logf(u2));
+  float s0, c0, s1, c1;
+  sincospif(2.f * u1, &s0, &c0);
+  sincospif(2.f * u3, &s1, &c1);
+  const float z[4] = {ra * c0, ra * s0, rb * c1, rb * s1};
+  for (int j = 0; j < 4; ++j)
+    if (i4 * 4 + j < n) out[i4 * 4 + j] = copysignf(sqrtf(fabsf(z[j])), z[j]);
+}
+
+// one thread = 4 consecutive inputs of one output row (16-byte accesses); block ranges per layer from blk_end
+__global__ void noisy_compose_net_kernel(NoisyNet net, int training) {
+  int li = 0;
+  while (li < net.n - 1 && (int)blockIdx.x >= net.blk_end[li]) ++li;
+  const riqn_noisy_layer& L = net.l[li];
+  const int in4 = L.in_features >> 2;
+  const int total = L.out_features * in4;
+  const int idx = (blockIdx.x - (li ? net.blk_end[li - 1] : 0)) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int o = idx / in4, i = (idx - o * in4) * 4;
+  const float eo = L.eps_out[o];
+  const float4 ei = *reinterpret_cast<const float4*>(L.eps_in + i);
+  const long off = (long)o * L.in_features + i;
+  const float4 e = make_float4(__fmul_rn(eo, ei.x), __fmul_rn(eo, ei.y), __fmul_rn(eo, ei.z), __fmul_rn(eo, ei.w));
+  *reinterpret_cast<float4*>(L.weight_epsilon + off) = e;
+  const float4 mu = *reinterpret_cast<const float4*>(L.weight_mu + off);
+  float4 w = mu;
+  if (training) {
+    const float4 sg = *reinterpret_cast<const float4*>(L.weight_sigma + off);
+    w = make_float4(__fadd_rn(mu.x, __fmul_rn(sg.x, e.x)), __fadd_rn(mu.y, __fmul_rn(sg.y, e.y)),
+                    __fadd_rn(mu.z, __fmul_rn(sg.z, e.z)), __fadd_rn(mu.w, __fmul_rn(sg.w, e.w)));
+  }
+  *reinterpret_cast<float4*>(L.w_eff + off) = w;
+  if (i == 0) {
+    L.bias_epsilon[o] = eo;
+    L.b_eff[o] = training ? __fadd_rn(L.bias_mu[o], __fmul_rn(L.bias_sigma[o], eo)) : L.bias_mu[o];
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // z-layers + dueling: q[r,a] = v + a_a - mean_a(a)                           (model.py:153-156)
 //   H (R, 2*hid): [:, :hid] value stream hidden, [:, hid:] advantage stream hidden (post-ReLU)
@@ -597,6 +655,42 @@ RIQN_API int riqn_noisy_compose(int out_features, int in_features, const float* 
   noisy_compose_kernel<<<grid_for((long)out_features * in_features), 256, 0, (cudaStream_t)stream>>>(
       out_features, in_features, weight_mu, weight_sigma, weight_epsilon, eps_in, eps_out, bias_mu, bias_sigma,
       bias_epsilon, w_eff, b_eff, training);
+  return (int)cudaGetLastError();
+}
+
+RIQN_API int riqn_noisy_reset_net(int n_layers, const riqn_noisy_layer* layers, unsigned long long seed, int sample,
+                                  int training, const riqn_dyn_state* dyn, void* stream) {
+  if (n_layers < 1 || n_layers > 8 || layers == nullptr) return (int)cudaErrorInvalidValue;
+  cudaStream_t s = (cudaStream_t)stream;
+  NoisyNet net;
+  net.n = n_layers;
+  for (int i = 0; i < n_layers; ++i) {
+    net.l[i] = layers[i];
+    const riqn_noisy_layer& L = layers[i];
+    if (L.in_features % 4 || L.out_features < 1 || (reinterpret_cast<uintptr_t>(L.eps_in) & 15) ||
+        (reinterpret_cast<uintptr_t>(L.weight_mu) & 15) || (reinterpret_cast<uintptr_t>(L.weight_sigma) & 15) ||
+        (reinterpret_cast<uintptr_t>(L.weight_epsilon) & 15) || (reinterpret_cast<uintptr_t>(L.w_eff) & 15))
+      return (int)cudaErrorInvalidValue;
+  }
+  if (sample) {
+    riqn::note_launches(1);
+    int blocks = 0;
+    for (int i = 0; i < n_layers; ++i) {
+      blocks += (int)riqn_cdiv((layers[i].in_features + 3) / 4, 256);
+      net.blk_end[2 * i] = blocks;
+      blocks += (int)riqn_cdiv((layers[i].out_features + 3) / 4, 256);
+      net.blk_end[2 * i + 1] = blocks;
+    }
+    noisy_fill_net_kernel<<<blocks, 256, 0, s>>>(net, seed, dyn);
+    RIQN_LAUNCH_CHECK();
+  }
+  riqn::note_launches(1);
+  int blocks = 0;
+  for (int i = 0; i < n_layers; ++i) {
+    blocks += (int)riqn_cdiv((long)layers[i].out_features * (layers[i].in_features / 4), 256);
+    net.blk_end[i] = blocks;
+  }
+  noisy_compose_net_kernel<<<blocks, 256, 0, s>>>(net, training);
   return (int)cudaGetLastError();
 }
 

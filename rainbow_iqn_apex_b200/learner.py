@@ -123,6 +123,7 @@ class Learner(Agent):
         graph = torch.cuda.CUDAGraph()
         nss, sbc = self.optimiser.bias_corrections(self.optimiser._step + 1)
         self._dyn.write(nss, sbc, mem.transitions.get_current_capacity(), mem.priority_weight)
+        self.online_net._static_ops_dirty = True     # the captured step must rebuild the conv / iqn_fc operand images
         post = None
         if self.process_group is None:
             with torch.cuda.graph(graph):
@@ -169,6 +170,7 @@ class Learner(Agent):
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
+        self.online_net._static_ops_dirty = True
         post = None
         if self.process_group is None:
             with torch.cuda.graph(graph):

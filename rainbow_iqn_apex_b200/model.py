@@ -23,7 +23,7 @@ import torch
 from torch import nn
 
 from . import _lib
-from ._lib import ConvGeom, call, ptr
+from ._lib import ConvGeom, NoisyLayer, call, ptr
 
 FEAT = 3136
 _ALIGN = 64  # floats; arena groups start on 256-byte boundaries
@@ -167,6 +167,8 @@ class DQN(nn.Module):
         self._tau_stream_offset = 0   # rank-private quantile stream under data parallelism
         self._rng_seed = int(torch.randint(0, 2 ** 62, (1,)).item())
         self._flatten()
+        # anything that rewrites the noise-free weights must invalidate their cached bf16 operand images
+        self.register_load_state_dict_post_hook(lambda module, _incompatible: setattr(module, "_static_ops_dirty", True))
         if self._flat.is_cuda:
             self.reset_noise()
 
@@ -210,6 +212,7 @@ class DQN(nn.Module):
                 p._riqn_offset = off
                 i += 1
         self._flat, self._flat_grad = flat, flat_grad
+        self._static_ops_dirty = True
         # epsilon arena: [h_v.weight_epsilon | h_a.weight_epsilon], h bias eps, [z_v | z_a] weight eps, z bias eps
         hv, ha, zv, za = self.fcnoisy_h_v, self.fcnoisy_h_a, self.fcnoisy_z_v, self.fcnoisy_z_a
         eg = [[(hv, "weight_epsilon"), (ha, "weight_epsilon")], [(hv, "bias_epsilon"), (ha, "bias_epsilon")],
@@ -270,24 +273,66 @@ class DQN(nn.Module):
 
     # ------------------------------------------------------------------ noise
     def reset_noise(self, noise=None):
-        """model.py:159-162.  ``noise``: optional {layer_name: (f(eps_in), f(eps_out))} injection."""
-        for name, module in self.noisy_layers():
+        """model.py:159-162.  ``noise``: optional {layer_name: (f(eps_in), f(eps_out))} injection.
+        All NoisyLinear layers are redrawn and recomposed by ONE riqn_noisy_reset_net call (two launches)."""
+        layers = self.noisy_layers()
+        if not self._flat.is_cuda or any(m.in_features % 4 for _, m in layers):
+            for name, module in layers:
+                if noise is not None:
+                    e_in, e_out = noise[name]
+                    module.reset_noise(e_in.to(self._flat.device), e_out.to(self._flat.device))
+                else:
+                    module.reset_noise(seed=self._rng_seed)
+            self._refresh_tc_operands()
+            return
+        desc = self._noisy_desc()
+        for k, (name, m) in enumerate(layers):
             if noise is not None:
                 e_in, e_out = noise[name]
-                module.reset_noise(e_in.to(self._flat.device), e_out.to(self._flat.device))
+                m._eps_in.copy_(e_in)
+                m._eps_out.copy_(e_out)
             else:
-                module.reset_noise(seed=self._rng_seed)
+                # graph mode: static per-step index (the device-side rng_offset advances the stream every step)
+                idx = m._calls_in_step if m._dyn is not None else m._noise_calls
+                base = (m._layer_id << 40) + 2 * idx
+                desc[k].stream_in, desc[k].stream_out = base, base + 1
+                m._noise_calls += 1
+                m._calls_in_step += 1
+        dyn = layers[0][1]._dyn
+        seed = self._rng_seed
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        call("riqn_noisy_reset_net", len(layers), desc, seed, 0 if noise is not None else 1, 1 if self.training else 0,
+             dyn.ptr() if (dyn is not None and noise is None) else None)
         self._refresh_tc_operands()
+
+    def _noisy_desc(self):
+        """Cached riqn_noisy_layer[] for riqn_noisy_reset_net (all pointers are static arena / scratch addresses)."""
+        layers = self.noisy_layers()
+        key = tuple(m.weight_mu.data_ptr() for _, m in layers) + (self._flat.data_ptr(),)
+        if getattr(self, "_noisy_desc_key", None) != key:
+            arr = (NoisyLayer * len(layers))()
+            for k, (_, m) in enumerate(layers):
+                m._ensure_scratch()
+                d = arr[k]
+                d.out_features, d.in_features = m.out_features, m.in_features
+                d.weight_mu, d.weight_sigma, d.weight_epsilon = ptr(m.weight_mu), ptr(m.weight_sigma), ptr(m.weight_epsilon)
+                d.bias_mu, d.bias_sigma, d.bias_epsilon = ptr(m.bias_mu), ptr(m.bias_sigma), ptr(m.bias_epsilon)
+                d.eps_in, d.eps_out, d.w_eff, d.b_eff = ptr(m._eps_in), ptr(m._eps_out), ptr(m._w_eff), ptr(m._b_eff)
+            self._noisy_desc_arr, self._noisy_desc_key = arr, key
+        return self._noisy_desc_arr
 
     def compose_weights(self):
         """Recompute the effective weights from the stored epsilons (after load_state_dict / optimiser steps)."""
         for _, module in self.noisy_layers():
             module._compose()
-        self._refresh_tc_operands()
+        self._refresh_tc_operands(force=True)
 
-    def _refresh_tc_operands(self):
+    def _refresh_tc_operands(self, force=False):
         """bf16 (hi, lo) images of the composed hidden-layer weights for the tcgen05 path: (2*hid, 3136) K-major for
-        the forward product and the transposed (3136, 2*hid) copy the data-gradient product consumes."""
+        the forward product and the transposed (3136, 2*hid) copy the data-gradient product consumes.  The images of
+        the noise-free weights (convolutions, iqn_fc) are only rebuilt when those weights may have changed: after an
+        optimiser step (optim.Adam marks the owner), after compose_weights() (``force``), or on first use."""
         if (PRECISION["fwd"] == "fp32" and PRECISION["bwd"] == "fp32") or not self._flat.is_cuda:
             return
         dev = self._flat.device
@@ -297,6 +342,7 @@ class DQN(nn.Module):
             self._w_hi, self._w_lo = mk(n, FEAT), mk(n, FEAT)
             self._w_hiT, self._w_loT = mk(FEAT, n), mk(FEAT, n)
             self._conv_ops = {}
+            self._static_ops_dirty = True
             for name, conv in (("conv1", self.conv1), ("conv2", self.conv2), ("conv3", self.conv3)):
                 co, k = conv.weight.shape[0], conv.weight[0].numel()
                 self._conv_ops[name] = (mk(co, k), mk(co, k), mk(k, co))
@@ -306,6 +352,9 @@ class DQN(nn.Module):
                 self._iqn_ops = (mk(FEAT, self.quantile_embedding_dim), mk(FEAT, self.quantile_embedding_dim))
         call("riqn_split_bf16", 2 * self.hidden, FEAT, ptr(self._w_eff_h), ptr(self._w_hi), ptr(self._w_lo),
              ptr(self._w_hiT), ptr(self._w_loT))
+        if not (force or getattr(self, "_static_ops_dirty", True)):
+            return
+        self._static_ops_dirty = False
         for name, conv in (("conv1", self.conv1), ("conv2", self.conv2), ("conv3", self.conv3)):
             hi, lo, hiT = self._conv_ops[name]
             call("riqn_split_bf16", hi.shape[0], hi.shape[1], ptr(conv.weight), ptr(hi), ptr(lo), ptr(hiT), None)

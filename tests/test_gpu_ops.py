@@ -179,3 +179,43 @@ def test_device_rng_statistics(cuda_dev):
     f = z.cpu().numpy().astype(np.float64)
     x = np.sign(f) * f * f                      # invert f(x) = sign(x) sqrt|x|  -> N(0,1)
     assert abs(x.mean()) < 5e-3 and abs(x.var() - 1) < 1e-2 and abs((x ** 4).mean() - 3) < 0.1
+
+
+def test_noisy_reset_net_matches_per_layer_calls(cuda_dev):
+    """riqn_noisy_reset_net (two launches per network) draws and composes exactly what riqn_noisy_sample +
+    riqn_noisy_compose produce layer by layer on the same seed / stream ids (model.py:32-43,159-162)."""
+    from rainbow_iqn_apex_b200._lib import NoisyLayer
+    call, ptr = _call()
+    shapes = [(512, 3136), (512, 3136), (1, 512), (18, 512)]
+    seed, g = 4242, torch.Generator().manual_seed(5)
+    keep, desc = [], (NoisyLayer * len(shapes))()
+    for k, (o, i) in enumerate(shapes):
+        t = dict(mu=torch.randn(o, i, generator=g), sg=torch.rand(o, i, generator=g), bmu=torch.randn(o, generator=g),
+                 bsg=torch.rand(o, generator=g))
+        t = {n: v.to(cuda_dev) for n, v in t.items()}
+        for n, shp in (("eps", (o, i)), ("beps", (o,)), ("ein", (i,)), ("eout", (o,)), ("w", (o, i)), ("b", (o,))):
+            t[n] = torch.zeros(*shp, device=cuda_dev)
+            t[n + "_ref"] = torch.zeros(*shp, device=cuda_dev)
+        keep.append(t)
+        d = desc[k]
+        d.out_features, d.in_features = o, i
+        d.weight_mu, d.weight_sigma, d.weight_epsilon = ptr(t["mu"]), ptr(t["sg"]), ptr(t["eps"])
+        d.bias_mu, d.bias_sigma, d.bias_epsilon = ptr(t["bmu"]), ptr(t["bsg"]), ptr(t["beps"])
+        d.eps_in, d.eps_out, d.w_eff, d.b_eff = ptr(t["ein"]), ptr(t["eout"]), ptr(t["w"]), ptr(t["b"])
+        d.stream_in, d.stream_out = (k << 40) + 6, (k << 40) + 7
+    call("riqn_noisy_reset_net", len(shapes), desc, seed, 1, 1, None)
+    for k, (o, i) in enumerate(shapes):
+        t = keep[k]
+        call("riqn_noisy_sample", i, seed, (k << 40) + 6, ptr(t["ein_ref"]), None)
+        call("riqn_noisy_sample", o, seed, (k << 40) + 7, ptr(t["eout_ref"]), None)
+        call("riqn_noisy_compose", o, i, ptr(t["mu"]), ptr(t["sg"]), ptr(t["eps_ref"]), ptr(t["ein_ref"]),
+             ptr(t["eout_ref"]), ptr(t["bmu"]), ptr(t["bsg"]), ptr(t["beps_ref"]), ptr(t["w_ref"]), ptr(t["b_ref"]), 1)
+        for n in ("ein", "eout", "eps", "beps", "w", "b"):
+            assert torch.equal(t[n], t[n + "_ref"]), (k, n)
+        # and it is the reference formula: W = mu + sigma * (eps_out (x) eps_in)
+        assert torch.equal(t["w"], t["mu"] + t["sg"] * torch.outer(t["eout"], t["ein"]))
+    # eval mode: the effective weights are the means; sample = 0 keeps the given factor vectors
+    ein0 = keep[0]["ein"].clone()
+    call("riqn_noisy_reset_net", len(shapes), desc, seed + 1, 0, 0, None)
+    assert torch.equal(keep[0]["ein"], ein0) and torch.equal(keep[0]["w"], keep[0]["mu"])
+    assert torch.equal(keep[3]["b"], keep[3]["bmu"])
