@@ -160,6 +160,46 @@ __device__ __forceinline__ void warp_store_rows_bf16(uint32_t* st, const uint32_
   }
 }
 
+// C += alpha * acc (and out2 += alpha * acc * eps for the NoisyLinear weight gradient) on full 128-byte row segments:
+// plain 16-byte read-modify-writes when this CTA is the only contributor, red.global.add.v4.f32 under split-K.
+template <bool NOISY>
+__device__ __forceinline__ void warp_accum_rows_f32(uint32_t* st, const uint32_t (&w)[32], int lane, float* c, float* out2,
+                                                    const float* eps, long ld, int rows_valid, bool atomic, float alpha) {
+  stage_row(st, w, lane);
+  const int sub = lane >> 3, piece = lane & 7;
+#pragma unroll
+  for (int r0 = 0; r0 < 32; r0 += 4) {
+    const int r = r0 + sub;
+    if (r < rows_valid) {
+      float4 a = *reinterpret_cast<const float4*>(st + r * kStRow + ((piece ^ (r & 7)) * 4));
+      a.x *= alpha; a.y *= alpha; a.z *= alpha; a.w *= alpha;
+      const long off = (long)r * ld + piece * 4;
+      float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (NOISY) {
+        e = *reinterpret_cast<const float4*>(eps + off);
+        e.x *= a.x; e.y *= a.y; e.z *= a.z; e.w *= a.w;
+      }
+      if (!atomic) {
+        float4 o = *reinterpret_cast<const float4*>(c + off);
+        o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+        *reinterpret_cast<float4*>(c + off) = o;
+        if (NOISY) {
+          float4 o2 = *reinterpret_cast<const float4*>(out2 + off);
+          o2.x += e.x; o2.y += e.y; o2.z += e.z; o2.w += e.w;
+          *reinterpret_cast<float4*>(out2 + off) = o2;
+        }
+      } else {
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(c + off), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w)
+                     : "memory");
+        if (NOISY)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out2 + off), "f"(e.x), "f"(e.y), "f"(e.z),
+                       "f"(e.w)
+                       : "memory");
+      }
+    }
+  }
+}
+
 // Transposed (N, M) bf16 image of a chunk whose 16 words hold the column pairs (2k, 2k+1) of this lane's row: lane pairs
 // exchange words so that each lane stores TWO consecutive rows of ONE column (even lanes column 2k, odd lanes 2k+1) --
 // 32-bit stores, 64 B contiguous per column.  M must be even.
@@ -185,6 +225,7 @@ struct TcArgs {
   float* out2;           // TC_NOISY_WGRAD: grad_sigma
   const float* eps;      // TC_NOISY_WGRAD: weight_epsilon (same layout as C)
   float alpha;           // TC_ATOMIC: scale applied to the accumulator
+  int vec_acc;           // TC_ATOMIC / TC_NOISY_WGRAD: C (out2, eps) rows are 16-byte aligned -> vectorised accumulate
   int ohw;               // TC_BIAS_RELU_NCHW: m = b*ohw + p -> C[(b*N + n)*ohw + p]
   const float* feat;     // TC_EMBED: (samples, N) conv features, row m uses feat[m / batch] (batch = rows per sample)
   int batch;
@@ -357,7 +398,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
               if (n0 + j < p.N) cb[(long)j * p.ohw] = fmaxf(__uint_as_float(v[j]) + p.bias[n0 + j], 0.f);
           } else if (EPI == TC_EMBED) {
             // handled below with the whole warp
-          } else {
+          } else if (!(p.vec_acc && n0 + 32 <= p.N)) {
             float* crow = p.C + (long)m * p.ldc + n0;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -375,13 +416,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
             }
           }
         }
-        if ((EPI == TC_STORE || EPI == TC_EMBED || (EPI == TC_BIAS_RELU && (p.M & 1) == 0)) && n0 + 32 <= p.N) {
+        if ((EPI == TC_STORE || EPI == TC_EMBED || (EPI == TC_BIAS_RELU && (p.M & 1) == 0) ||
+             ((EPI == TC_ATOMIC || EPI == TC_NOISY_WGRAD) && p.vec_acc)) && n0 + 32 <= p.N) {
           uint32_t* st = epi_stage + (warp - 2) * (32 * kStRow);
           const int m_base = mt * TBM + quarter * 32;
           const int rows_valid = min(32, p.M - m_base);            // warp-uniform
           if (rows_valid > 0) {
             if (EPI == TC_STORE) {
               warp_store_rows_f32(st, v, lane, p.C + (long)m_base * p.ldc + n0, p.ldc, rows_valid);
+            } else if (EPI == TC_ATOMIC) {
+              warp_accum_rows_f32<false>(st, v, lane, p.C + (long)m_base * p.ldc + n0, nullptr, nullptr, p.ldc, rows_valid,
+                                         p.k_splits > 1, p.alpha);
+            } else if (EPI == TC_NOISY_WGRAD) {
+              const long o0 = (long)m_base * p.ldc + n0;
+              warp_accum_rows_f32<true>(st, v, lane, p.C + o0, p.out2 + o0, p.eps + o0, p.ldc, rows_valid, p.k_splits > 1,
+                                        1.f);
             } else if (EPI == TC_BIAS_RELU) {
               const float* br = p.bias + n0;
               uint32_t hw[16];
@@ -537,6 +586,8 @@ int gemm_bf16_tc(int M, int N, int K, const bf16* A_hi, const bf16* A_lo, const 
   if (p.k_splits > 1 && epi != TC_ATOMIC && epi != TC_NOISY_WGRAD) return (int)cudaErrorInvalidValue;
   p.C = C; p.ldc = ldc; p.bias = bias; p.out2 = out2; p.eps = eps;
   p.alpha = ex ? ex->alpha : 1.f;
+  p.vec_acc = (ldc % 4 == 0) && (reinterpret_cast<uintptr_t>(C) & 15) == 0 && (reinterpret_cast<uintptr_t>(out2) & 15) == 0 &&
+              (reinterpret_cast<uintptr_t>(eps) & 15) == 0;
   p.ohw = ex ? ex->ohw : 1; p.feat = ex ? ex->feat : nullptr; p.batch = ex ? ex->batch : 1;
   p.o_hi = ex ? ex->o_hi : nullptr; p.o_lo = ex ? ex->o_lo : nullptr;
   p.o_hiT = ex ? ex->o_hiT : nullptr; p.o_loT = ex ? ex->o_loT : nullptr;

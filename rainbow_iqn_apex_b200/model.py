@@ -33,7 +33,7 @@ _ALIGN = 64  # floats; arena groups start on 256-byte boundaries
 #   "bf16"  : tcgen05 tensor cores, operands rounded to bf16 once, fp32 accumulation in TMEM
 #   "fp32"  : CUDA-core fp32 GEMM (gemm_simt.cu), the cross-check path
 PRECISION = {"fwd": os.environ.get("RIQN_FWD_PRECISION", "bf16x3"), "bwd": os.environ.get("RIQN_BWD_PRECISION", "bf16")}
-WGRAD_SPLIT_K = int(os.environ.get("RIQN_WGRAD_SPLIT_K", "1"))
+WGRAD_SPLIT_K = int(os.environ.get("RIQN_WGRAD_SPLIT_K", "4"))
 
 
 def set_precision(fwd=None, bwd=None):
