@@ -199,6 +199,12 @@ int riqn_dueling_fwd(long rows, int batch, int hidden, int action_space, const f
 int riqn_dueling_bwd(long rows, int batch, int hidden, int action_space, const float* h, const float* wz,
                      const float* dtheta, const float* gscale, const long long* actions, float* dh, float* dz,
                      void* dz_t_bf16, void* stream);
+/* Same backward for bf16 tensor-core consumers (rows % 8 == 0): instead of the fp32 dh it writes dh_hi (rows, 2*hidden)
+ * and its transpose dh_hi_t (2*hidden, rows) as bf16, and dh_colsum (2*hidden) = the fp32 column sums of dh (zeroed
+ * here; pass it to riqn_noisy_bias_grad with dh == NULL). */
+int riqn_dueling_bwd_bf16(long rows, int batch, int hidden, int action_space, const float* h, const float* wz,
+                          const float* dtheta, const float* gscale, const long long* actions, void* dh_hi, void* dh_hi_t,
+                          float* dh_colsum, float* dz, void* dz_t_bf16, void* stream);
 /* Parameter gradients of the two z-layers (accumulated): dwz_scratch 32*2*hidden floats, dbz_scratch 32. */
 /* Same with the reduction dz^T h on the tensor cores: dz_t (32, rows) and h_t (2*hidden, rows) bf16 (rows % 8 == 0). */
 int riqn_z_wgrad_tc(long rows, int hidden, int action_space, const void* dz_t, const void* h_t, const float* dz,

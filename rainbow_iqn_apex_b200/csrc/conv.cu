@@ -406,6 +406,53 @@ __global__ void conv_dy_bf16_kernel(int B, int Cout, int ohw, const float* __res
   }
 }
 
+// Tiled variant (Cout <= 64, Cout % 8 == 0): one block = 64 consecutive pixels x all channels.  NCHW reads and the dYT
+// writes are coalesced along the pixels; the (M, Cout) image leaves through a shared tile as 16-byte row pieces.
+__global__ void __launch_bounds__(256) conv_dy_tile_kernel(int B, int Cout, int ohw, const float* __restrict__ dout,
+                                                           const float* __restrict__ out, bf16* __restrict__ dY,
+                                                           bf16* __restrict__ dYT, float* __restrict__ dbias) {
+  __shared__ __align__(16) unsigned short tile[64][66];
+  const long M = (long)B * ohw, m0 = (long)blockIdx.x * 64;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  long src0[2];
+  bool ok[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const long m = m0 + lane + 32 * h;
+    ok[h] = m < M;
+    const long b = ok[h] ? m / ohw : 0;
+    src0[h] = b * Cout * ohw + (ok[h] ? m - b * ohw : 0);       // + c * ohw
+  }
+  for (int c = warp; c < Cout; c += 8) {
+    float acc = 0.f;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float v = 0.f;
+      if (ok[h]) {
+        const long src = src0[h] + (long)c * ohw;
+        v = out[src] > 0.f ? dout[src] : 0.f;
+      }
+      const bf16 hb = __float2bfloat16_rn(v);
+      if (ok[h]) dYT[(long)c * M + m0 + lane + 32 * h] = hb;
+      tile[lane + 32 * h][c] = __bfloat16_as_ushort(hb);
+      acc += v;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) atomicAdd(&dbias[c], acc);
+  }
+  __syncthreads();
+  if (dY) {
+    const int ppr = Cout >> 3;                                   // 16-byte pieces per row
+    for (int idx = threadIdx.x; idx < 64 * ppr; idx += blockDim.x) {
+      const int r = idx / ppr, pc = idx - r * ppr;
+      if (m0 + r < M) {
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(&tile[r][pc * 8]);
+        *reinterpret_cast<uint4*>(dY + (m0 + r) * Cout + pc * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+  }
+}
+
 static inline int grid_for(long total) {
   long b = (total + 255) / 256;
   return (int)(b > 148L * 32 ? 148L * 32 : (b < 1 ? 1 : b));
@@ -538,8 +585,13 @@ RIQN_API int riqn_conv_bwd_tc(const riqn_conv_geom* g, const float* dout, const 
   const int K = g->Cin * g->KH * g->KW;
   const int ohw = g->OH * g->OW;
   if (M % 8 || g->Cout % 8) return (int)cudaErrorInvalidValue;
-  dim3 grid((unsigned)((M + 256 * 8 - 1) / (256 * 8)), g->Cout);
-  conv_dy_bf16_kernel<<<grid, 256, 0, s>>>(g->B, g->Cout, ohw, dout, out, din ? (bf16*)dY_hi : nullptr, (bf16*)dYT_hi, dbias);
+  if (g->Cout <= 64) {
+    conv_dy_tile_kernel<<<(unsigned)((M + 63) / 64), 256, 0, s>>>(g->B, g->Cout, ohw, dout, out,
+                                                                 din ? (bf16*)dY_hi : nullptr, (bf16*)dYT_hi, dbias);
+  } else {
+    dim3 grid((unsigned)((M + 256 * 8 - 1) / (256 * 8)), g->Cout);
+    conv_dy_bf16_kernel<<<grid, 256, 0, s>>>(g->B, g->Cout, ohw, dout, out, din ? (bf16*)dY_hi : nullptr, (bf16*)dYT_hi, dbias);
+  }
   RIQN_LAUNCH_CHECK();
   // dW[c, k] += sum_m dY[m, c] * col[m, k]      (K' = M is long: split it over every SM)
   const int n_tiles = (K + 255) / 256;
@@ -551,11 +603,23 @@ RIQN_API int riqn_conv_bwd_tc(const riqn_conv_geom* g, const float* dout, const 
   if (rc) return rc;
   if (din) {
     // dcol[m, k] = sum_c dY[m, c] * W[c, k]
-    rc = gemm_bf16_tc((int)M, K, g->Cout, (const bf16*)dY_hi, nullptr, (const bf16*)wT_hi, nullptr, dcol, K, TC_STORE, nullptr,
-                      nullptr, nullptr, 1, s, nullptr);
-    if (rc) return rc;
-    rc = col2im(g, dcol, din, s);
-    if (rc) return rc;
+    if (g->pad == 0) {
+      // fused col2im: the accumulators are added straight into din (never materialising dcol)
+      RIQN_CUDA(cudaMemsetAsync(din, 0, sizeof(float) * (size_t)g->B * g->Cin * g->H * g->W, s));
+      TcExtra ci;
+      ci.ohw = ohw;
+      ci.ci_h = g->H; ci.ci_w = g->W; ci.ci_cin = g->Cin; ci.ci_kh = g->KH; ci.ci_kw = g->KW;
+      ci.ci_stride = g->stride; ci.ci_ow = g->OW;
+      rc = gemm_bf16_tc((int)M, K, g->Cout, (const bf16*)dY_hi, nullptr, (const bf16*)wT_hi, nullptr, din, K, TC_COL2IM,
+                        nullptr, nullptr, nullptr, 1, s, &ci);
+      if (rc) return rc;
+    } else {
+      rc = gemm_bf16_tc((int)M, K, g->Cout, (const bf16*)dY_hi, nullptr, (const bf16*)wT_hi, nullptr, dcol, K, TC_STORE,
+                        nullptr, nullptr, nullptr, 1, s, nullptr);
+      if (rc) return rc;
+      rc = col2im(g, dcol, din, s);
+      if (rc) return rc;
+    }
   }
   return 0;
 }

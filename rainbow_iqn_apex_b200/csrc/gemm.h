@@ -31,7 +31,8 @@ int gemm_f32(int M, int N, int K, const float* A, long sAm, long sAk, const floa
              float* C, long ldc, int epi, const EpiArgs& e, int split_k, cudaStream_t stream);
 
 // ---- tcgen05 / TMA path (gemm_tc.cu) ---------------------------------------------------------------------------
-enum TcEpi { TC_STORE = 0, TC_BIAS_RELU = 1, TC_ATOMIC = 2, TC_NOISY_WGRAD = 3, TC_BIAS_RELU_NCHW = 4, TC_EMBED = 5 };
+enum TcEpi { TC_STORE = 0, TC_BIAS_RELU = 1, TC_ATOMIC = 2, TC_NOISY_WGRAD = 3, TC_BIAS_RELU_NCHW = 4, TC_EMBED = 5,
+             TC_COL2IM = 6 };
 
 struct TcExtra {
   int ohw = 1;
@@ -39,6 +40,8 @@ struct TcExtra {
   const float* feat = nullptr;
   int batch = 1;
   __nv_bfloat16 *o_hi = nullptr, *o_lo = nullptr, *o_hiT = nullptr, *o_loT = nullptr;
+  // TC_COL2IM: row m = (b, oh, ow), column n = (c, kh, kw); C is the NCHW image gradient (pad == 0), accumulated into
+  int ci_h = 0, ci_w = 0, ci_cin = 0, ci_kh = 0, ci_kw = 0, ci_stride = 0, ci_ow = 0;
 };
 
 // C (+)= A B^T, A (M,K) / B (N,K) row-major bf16 (K % 8 == 0); *_lo non-null selects the split-bf16 x3 product.

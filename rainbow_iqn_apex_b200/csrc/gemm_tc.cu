@@ -227,6 +227,7 @@ struct TcArgs {
   float alpha;           // TC_ATOMIC: scale applied to the accumulator
   int vec_acc;           // TC_ATOMIC / TC_NOISY_WGRAD: C (out2, eps) rows are 16-byte aligned -> vectorised accumulate
   int ohw;               // TC_BIAS_RELU_NCHW: m = b*ohw + p -> C[(b*N + n)*ohw + p]
+  int ci_h, ci_w, ci_cin, ci_kh, ci_kw, ci_stride, ci_ow;   // TC_COL2IM geometry (pad == 0)
   const float* feat;     // TC_EMBED: (samples, N) conv features, row m uses feat[m / batch] (batch = rows per sample)
   int batch;
   bf16 *o_hi, *o_lo;     // TC_EMBED: bf16 hi / lo images of the result, row-major (M, N)   (may be null)
@@ -396,7 +397,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (n0 + j < p.N) cb[(long)j * p.ohw] = fmaxf(__uint_as_float(v[j]) + p.bias[n0 + j], 0.f);
-          } else if (EPI == TC_EMBED) {
+          } else if (EPI == TC_EMBED || EPI == TC_COL2IM) {
             // handled below with the whole warp
           } else if (!(p.vec_acc && n0 + 32 <= p.N)) {
             float* crow = p.C + (long)m * p.ldc + n0;
@@ -414,6 +415,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
                 }
               }
             }
+          }
+        }
+        if (EPI == TC_COL2IM && n0 < p.N) {
+          // din[b, c, oh*s + kh, ow*s + kw] += dcol[m, (c, kh, kw)]: lane j decodes column n0 + j once, the offsets are
+          // broadcast by shuffle; lanes = consecutive output pixels, so one red instruction touches a few lines
+          const int khw = p.ci_kh * p.ci_kw;
+          const int kcol = n0 + lane;
+          int coff = -1;
+          if (kcol < p.N) {
+            const int c = kcol / khw, r = kcol - c * khw;
+            const int kh = r / p.ci_kw, kw = r - kh * p.ci_kw;
+            coff = (c * p.ci_h + kh) * p.ci_w + kw;
+          }
+          const bool row_ok = m < p.M;
+          const int mm = row_ok ? m : 0;
+          const int b = mm / p.ohw, pp = mm - b * p.ohw;
+          const int oh = pp / p.ci_ow, ow = pp - oh * p.ci_ow;
+          float* base = p.C + ((long)b * p.ci_cin * p.ci_h + oh * p.ci_stride) * p.ci_w + ow * p.ci_stride;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int off = __shfl_sync(0xffffffffu, coff, j);
+            if (row_ok && off >= 0)
+              asm volatile("red.global.add.f32 [%0], %1;" ::"l"(base + off), "f"(__uint_as_float(v[j])) : "memory");
           }
         }
         if ((EPI == TC_STORE || EPI == TC_EMBED || (EPI == TC_BIAS_RELU && (p.M & 1) == 0) ||
@@ -589,6 +613,9 @@ int gemm_bf16_tc(int M, int N, int K, const bf16* A_hi, const bf16* A_lo, const 
   p.vec_acc = (ldc % 4 == 0) && (reinterpret_cast<uintptr_t>(C) & 15) == 0 && (reinterpret_cast<uintptr_t>(out2) & 15) == 0 &&
               (reinterpret_cast<uintptr_t>(eps) & 15) == 0;
   p.ohw = ex ? ex->ohw : 1; p.feat = ex ? ex->feat : nullptr; p.batch = ex ? ex->batch : 1;
+  p.ci_h = ex ? ex->ci_h : 0; p.ci_w = ex ? ex->ci_w : 0; p.ci_cin = ex ? ex->ci_cin : 0; p.ci_kh = ex ? ex->ci_kh : 0;
+  p.ci_kw = ex ? ex->ci_kw : 0; p.ci_stride = ex ? ex->ci_stride : 0; p.ci_ow = ex ? ex->ci_ow : 0;
+  if (epi == TC_COL2IM && (ex == nullptr || p.ci_kh * p.ci_kw * p.ci_cin != N || split3 || split2)) return (int)cudaErrorInvalidValue;
   p.o_hi = ex ? ex->o_hi : nullptr; p.o_lo = ex ? ex->o_lo : nullptr;
   p.o_hiT = ex ? ex->o_hiT : nullptr; p.o_loT = ex ? ex->o_loT : nullptr;
   if (epi == TC_EMBED && ((N % 32) || (M % 2))) return (int)cudaErrorInvalidValue;
@@ -614,6 +641,7 @@ int gemm_bf16_tc(int M, int N, int K, const bf16* A_hi, const bf16* A_lo, const 
   } else {
     switch (epi) {
       case TC_STORE: RIQN_TC_NARROW(1, TC_STORE); RIQN_TC_GO(1, TC_STORE);
+      case TC_COL2IM: RIQN_TC_GO(1, TC_COL2IM);
       case TC_BIAS_RELU: RIQN_TC_GO(1, TC_BIAS_RELU);
       case TC_ATOMIC: RIQN_TC_NARROW(1, TC_ATOMIC); RIQN_TC_GO(1, TC_ATOMIC);
       case TC_NOISY_WGRAD: RIQN_TC_GO(1, TC_NOISY_WGRAD);

@@ -543,6 +543,112 @@ __global__ void z_dueling_bwd_kernel(long R, int B, int A, const float* __restri
   }
 }
 
+// bf16-operand variant: the data gradient leaves directly as the two bf16 images the tensor-core products consume
+// (dh_hi (R, 2*HID) for the dgrad, dh_hiT (2*HID, R) for the wgrad) plus its fp32 column sums (bias gradients); the fp32
+// dH matrix is never written.  One block = 32 consecutive rows; the transposed image goes through an XOR-swizzled
+// shared tile (16-byte chunk c/8 of row r sits in slot (c/8) ^ ((r >> 3) & 3)) and leaves as 64-byte column segments.
+template <int HID>
+__global__ void __launch_bounds__(256) z_dueling_bwd_bf16_kernel(long R, int B, int A, const float* __restrict__ H,
+                                                                 const float* __restrict__ Wz,
+                                                                 const float* __restrict__ dtheta,
+                                                                 const float* __restrict__ gscale,
+                                                                 const int64_t* __restrict__ actions,
+                                                                 __nv_bfloat16* __restrict__ dh_hi,
+                                                                 __nv_bfloat16* __restrict__ dh_hiT,
+                                                                 float* __restrict__ colsum, float* __restrict__ dz,
+                                                                 __nv_bfloat16* __restrict__ dzT) {
+  extern __shared__ __align__(16) float sW[];          // (1+A)*HID weights | HID colmean | 2*HID column sums | tile
+  float* wbar = sW + (1 + A) * HID;
+  float* cs = wbar + HID;
+  uint4* tile = reinterpret_cast<uint4*>(cs + 2 * HID);   // [32 rows][128 chunks of 8 bf16]
+  for (int i = threadIdx.x; i < (1 + A) * HID / 4; i += blockDim.x)
+    reinterpret_cast<float4*>(sW)[i] = reinterpret_cast<const float4*>(Wz)[i];
+  for (int i = threadIdx.x; i < 2 * HID; i += blockDim.x) cs[i] = 0.f;
+  __syncthreads();
+  for (int j = threadIdx.x; j < HID; j += blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < A; ++k) s += sW[(1 + k) * HID + j];
+    wbar[j] = s / (float)A;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long r0 = (long)blockIdx.x * 32;
+  const int Nq = (int)(R / B);
+  float bs[4][8];
+#pragma unroll
+  for (int it = 0; it < 4; ++it)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) bs[it][i] = 0.f;
+  for (int rr = 0; rr < 4; ++rr) {
+    const int rl = warp * 4 + rr;
+    const long r = r0 + rl;
+    const bool ok = r < R;
+    const long rc = ok ? r : 0;
+    const int b = (int)(rc / Nq);                            // sample-major rows; dtheta arrives quantile-major
+    const float g = ok ? dtheta[(rc - (long)b * Nq) * B + b] * gscale[b] : 0.f;
+    const int act = (int)actions[b];
+    const float* wa = sW + (1 + act) * HID;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int chunk = lane + 32 * it, c0 = chunk * 8, j0 = c0 & (HID - 1);
+      float hv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (ok) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(H + r * (2 * HID) + c0));
+        const float4 c = __ldg(reinterpret_cast<const float4*>(H + r * (2 * HID) + c0 + 4));
+        hv[0] = a.x; hv[1] = a.y; hv[2] = a.z; hv[3] = a.w; hv[4] = c.x; hv[5] = c.y; hv[6] = c.z; hv[7] = c.w;
+      }
+      float val[8];
+      if (it < 2) {                                            // value stream: dv * w_zv
+#pragma unroll
+        for (int i = 0; i < 8; ++i) val[i] = hv[i] > 0.f ? g * sW[j0 + i] : 0.f;
+      } else {                                                 // advantage stream: g * (W_za[act] - colmean)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) val[i] = hv[i] > 0.f ? g * (wa[j0 + i] - wbar[j0 + i]) : 0.f;
+      }
+      uint32_t w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(val[2 * i], val[2 * i + 1]);
+        w[i] = *reinterpret_cast<const uint32_t*>(&h2);
+        bs[it][2 * i] += val[2 * i];
+        bs[it][2 * i + 1] += val[2 * i + 1];
+      }
+      const uint4 pk = make_uint4(w[0], w[1], w[2], w[3]);
+      if (ok) *reinterpret_cast<uint4*>(dh_hi + r * (2 * HID) + c0) = pk;
+      tile[rl * 128 + (chunk ^ ((rl >> 3) & 3))] = pk;
+    }
+    if (ok) {
+      float z = 0.f;
+      if (lane == 0) z = g;
+      else if (lane <= A) z = g * ((lane - 1 == act ? 1.f : 0.f) - 1.f / (float)A);
+      dz[r * 32 + lane] = z;
+      if (dzT) dzT[(long)lane * R + r] = __float2bfloat16_rn(z);
+    }
+  }
+#pragma unroll
+  for (int it = 0; it < 4; ++it)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) atomicAdd(&cs[(lane + 32 * it) * 8 + i], bs[it][i]);
+  __syncthreads();
+  // transposed image: item = (column c, piece p of 8 rows); a warp covers 8 columns x 4 pieces = 8 x 64 contiguous bytes
+  const unsigned short* t16 = reinterpret_cast<const unsigned short*>(tile);
+  for (int item = threadIdx.x; item < 2 * HID * 4; item += blockDim.x) {
+    const int c = item >> 2, piece = item & 3;
+    if (r0 + 8 * piece + 7 < R) {
+      const int slot = (c >> 3) ^ piece;
+      uint32_t w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const unsigned short lo = t16[((8 * piece + 2 * i) * 128 + slot) * 8 + (c & 7)];
+        const unsigned short hi = t16[((8 * piece + 2 * i + 1) * 128 + slot) * 8 + (c & 7)];
+        w[i] = (uint32_t)lo | ((uint32_t)hi << 16);
+      }
+      *reinterpret_cast<uint4*>(dh_hiT + (long)c * R + r0 + 8 * piece) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  }
+  for (int c = threadIdx.x; c < 2 * HID; c += blockDim.x) atomicAdd(&colsum[c], cs[c]);
+}
+
 // dWz (32, 2*HID) from dz^T * H  ->  parameter gradients of the two noisy z-layers.
 //   z_v: weight (1,HID) = dWz[0, :HID] ; z_a: weight (A,HID) = dWz[1+k, HID:]
 //   dmu += g ; dsigma += g * eps          (model.py:45-53)
@@ -819,11 +925,13 @@ RIQN_API int riqn_noisy_linear_wgrad(long rows, int in_features, int out_feature
 
 RIQN_API int riqn_noisy_bias_grad(long rows, int out_features, const float* dh, const float* bias_epsilon,
                                   float* db_scratch, float* grad_bias_mu, float* grad_bias_sigma, void* stream) {
-  riqn::note_launches(2);
+  riqn::note_launches(dh ? 2 : 1);
   cudaStream_t s = (cudaStream_t)stream;
-  RIQN_CUDA(cudaMemsetAsync(db_scratch, 0, sizeof(float) * out_features, s));
-  int rc = colsum_atomic(rows, out_features, dh, db_scratch, s);
-  if (rc) return rc;
+  if (dh) {            // dh == NULL: db_scratch already holds the column sums (riqn_dueling_bwd_bf16)
+    RIQN_CUDA(cudaMemsetAsync(db_scratch, 0, sizeof(float) * out_features, s));
+    int rc = colsum_atomic(rows, out_features, dh, db_scratch, s);
+    if (rc) return rc;
+  }
   noisy_bias_grad_kernel<<<riqn_cdiv(out_features, 256), 256, 0, s>>>(out_features, db_scratch, bias_epsilon,
                                                                     grad_bias_mu, grad_bias_sigma);
   return (int)cudaGetLastError();
@@ -865,6 +973,25 @@ RIQN_API int riqn_dueling_bwd(long rows, int batch, int hidden, int action_space
   }
   z_dueling_bwd_kernel<512><<<148 * 4, 256, smem, (cudaStream_t)stream>>>(rows, batch, action_space, h, wz, dtheta, gscale,
                                                                        (const int64_t*)actions, dh, dz, (__nv_bfloat16*)dz_t_bf16);
+  return (int)cudaGetLastError();
+}
+
+RIQN_API int riqn_dueling_bwd_bf16(long rows, int batch, int hidden, int action_space, const float* h, const float* wz,
+                                   const float* dtheta, const float* gscale, const long long* actions, void* dh_hi,
+                                   void* dh_hi_t, float* dh_colsum, float* dz, void* dz_t_bf16, void* stream) {
+  riqn::note_launches(1);
+  if (hidden != 512 || action_space > 31 || rows % 8) return (int)cudaErrorInvalidValue;
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t smem = sizeof(float) * ((1 + action_space) * hidden + hidden + 2 * hidden) + 32 * 128 * 16;
+  static bool attr = false;
+  if (!attr) {
+    RIQN_CUDA(cudaFuncSetAttribute(z_dueling_bwd_bf16_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr = true;
+  }
+  RIQN_CUDA(cudaMemsetAsync(dh_colsum, 0, sizeof(float) * 2 * hidden, s));
+  z_dueling_bwd_bf16_kernel<512><<<(unsigned)((rows + 31) / 32), 256, smem, s>>>(
+      rows, batch, action_space, h, wz, dtheta, gscale, (const int64_t*)actions, (__nv_bfloat16*)dh_hi,
+      (__nv_bfloat16*)dh_hi_t, dh_colsum, dz, (__nv_bfloat16*)dz_t_bf16);
   return (int)cudaGetLastError();
 }
 

@@ -522,13 +522,23 @@ class DQN(nn.Module):
         hid, A, E = self.hidden, self.action_space, self.quantile_embedding_dim
         hv, ha, zv, za = self.fcnoisy_h_v, self.fcnoisy_h_a, self.fcnoisy_z_v, self.fcnoisy_z_a
         gv = self.grad_view
-        dh = torch.empty(R, 2 * hid, device=dev)
         dz = torch.empty(R, 32, device=dev)
         tc = keep.get("tc")
         z_tc = bool(keep["head_bwd_tc"]) and tc is not None and tc.get("hT") is not None
         dzT = torch.empty(32, R, dtype=torch.bfloat16, device=dev) if z_tc else None
-        call("riqn_dueling_bwd", R, B, hid, A, ptr(keep["h"]), ptr(self._w_eff_z), ptr(dtheta), ptr(gscale),
-             ptr(actions), ptr(dh), ptr(dz), ptr(dzT))
+        dbs = torch.empty(2 * hid, device=dev)
+        # bf16 backward: dh leaves the dueling backward directly as the bf16 operand images (+ its column sums)
+        fused_dh = bool(keep["head_bwd_tc"]) and PRECISION["bwd"] == "bf16" and R % 8 == 0
+        if fused_dh:
+            dh = None
+            dh_hi = torch.empty(R, 2 * hid, dtype=torch.bfloat16, device=dev)
+            dh_hiT = torch.empty(2 * hid, R, dtype=torch.bfloat16, device=dev)
+            call("riqn_dueling_bwd_bf16", R, B, hid, A, ptr(keep["h"]), ptr(self._w_eff_z), ptr(dtheta), ptr(gscale),
+                 ptr(actions), ptr(dh_hi), ptr(dh_hiT), ptr(dbs), ptr(dz), ptr(dzT))
+        else:
+            dh = torch.empty(R, 2 * hid, device=dev)
+            call("riqn_dueling_bwd", R, B, hid, A, ptr(keep["h"]), ptr(self._w_eff_z), ptr(dtheta), ptr(gscale),
+                 ptr(actions), ptr(dh), ptr(dz), ptr(dzT))
         dwz = torch.empty(32, 2 * hid, device=dev)
         dbz = torch.empty(32, device=dev)
         zargs = (ptr(dwz), ptr(dbz), ptr(zv.weight_epsilon), ptr(zv.bias_epsilon), ptr(za.weight_epsilon),
@@ -539,7 +549,6 @@ class DQN(nn.Module):
             call("riqn_z_wgrad_tc", R, hid, A, ptr(dzT), ptr(tc["hT"]), ptr(dz), *zargs)
         else:
             call("riqn_z_wgrad", R, hid, A, ptr(dz), ptr(keep["h"]), *zargs)
-        dbs = torch.empty(2 * hid, device=dev)
         dx = torch.empty(R, FEAT, device=dev)
         bwd = PRECISION["bwd"]
         # [h_v | h_a] are adjacent in every arena, so one (2*hid, 3136) product serves both layers
@@ -551,15 +560,16 @@ class DQN(nn.Module):
         else:
             bf = lambda *sh: torch.empty(*sh, dtype=torch.bfloat16, device=dev)
             b3 = bwd == "bf16x3"
-            dh_hi, dh_hiT = bf(R, 2 * hid), bf(2 * hid, R)
             dh_lo, dh_loT = (bf(R, 2 * hid), bf(2 * hid, R)) if b3 else (None, None)
-            call("riqn_split_bf16", R, 2 * hid, ptr(dh), ptr(dh_hi), ptr(dh_lo), ptr(dh_hiT), ptr(dh_loT))
+            if not fused_dh:
+                dh_hi, dh_hiT = bf(R, 2 * hid), bf(2 * hid, R)
+                call("riqn_split_bf16", R, 2 * hid, ptr(dh), ptr(dh_hi), ptr(dh_lo), ptr(dh_hiT), ptr(dh_loT))
             # dW[o, i] = sum_r dh[r, o] x[r, i]  -> dmu += dW, dsigma += dW * eps   (split-K, atomics)
             call("riqn_gemm_bf16_tc", 2 * hid, FEAT, R, ptr(dh_hiT), ptr(dh_loT), ptr(tc["x_hiT"]),
                  ptr(tc["x_loT"]) if b3 else None, ptr(gv(hv.weight_mu)), FEAT, 3, None, ptr(gv(hv.weight_sigma)),
                  ptr(hv.weight_epsilon), WGRAD_SPLIT_K, None)
-            call("riqn_noisy_bias_grad", R, 2 * hid, ptr(dh), ptr(hv.bias_epsilon), ptr(dbs), ptr(gv(hv.bias_mu)),
-                 ptr(gv(hv.bias_sigma)))
+            call("riqn_noisy_bias_grad", R, 2 * hid, ptr(dh) if dh is not None else None, ptr(hv.bias_epsilon), ptr(dbs),
+                 ptr(gv(hv.bias_mu)), ptr(gv(hv.bias_sigma)))
             # dx[r, i] = sum_o dh[r, o] W_eff[o, i]
             call("riqn_gemm_bf16_tc", R, FEAT, 2 * hid, ptr(dh_hi), ptr(dh_lo), ptr(self._w_hiT),
                  ptr(self._w_loT) if b3 else None, ptr(dx), FEAT, 0, None, None, None, 1, None)
