@@ -79,6 +79,23 @@ int riqn_im2col_f32(const riqn_conv_geom* g, const void* in, int in_is_u8, float
  * (K, M), if non-NULL, is also written for riqn_conv_bwd_tc (needs B*OH*OW % 8 == 0). */
 int riqn_conv_fwd_tc(const riqn_conv_geom* g, const void* in, int in_is_u8, const void* w_hi, const void* w_lo,
                      const float* bias, void* col_hi, void* col_lo, void* colT_hi, float* out, void* stream);
+/* Strip convolution: the forward of nn.Conv2d + ReLU (model.py:65-67,115-118) with NO im2col matrix.  With kernel edge
+ * k = t*stride the padded input is cut into stride x stride blocks (block matrix: B*G*G rows of stride^2*Cin values,
+ * G = OH + t - 1) and the outputs are laid on the same G x G grid, so that every k-block of the implicit im2col matrix
+ * is a 2-D tile of the block matrix at a row offset (TMA).  Requires stride^2*Cin % 64 == 0, Cout <= 64.
+ *   riqn_s2d_u8: uint8 frame stack -> block matrix a_px (B*G*G, stride^2*Cin) bf16 of raw pixel values, within-block
+ *                order (c, iy, ix); the 1/255 of redis_memory.py:527-536 is folded into the weights.
+ *   riqn_conv_fwd_strip: a_hi / a_lo (lo may be NULL) block matrices; w_hi / w_lo (Cout, K) bf16 weights with K
+ *                ordered (dy, dx, within-block); out (B, Cout, OH, OW) fp32 = relu(conv + bias); next_hi / next_lo (may be
+ *                NULL) receive the result as the NEXT layer's block matrix (block edge next_stride, grid next_grid,
+ *                within-block order (iy, ix, c)).
+ *   riqn_im2col_bf16_t: the transposed bf16 im2col (K, M) alone, the wgrad operand of riqn_conv_bwd_tc. */
+int riqn_s2d_u8(const riqn_conv_geom* g, const unsigned char* in, void* a_px, void* stream);
+int riqn_conv_fwd_strip(const riqn_conv_geom* g, const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo,
+                        const float* bias, float* out, void* next_hi, void* next_lo, int next_stride, int next_grid,
+                        void* stream);
+int riqn_im2col_bf16_t(const riqn_conv_geom* g, const void* in, int in_is_u8, void* colT_hi, void* stream);
+
 /* Backward on the tensor cores (bf16 operands, fp32 accumulate): wT_hi (K, Cout) bf16; dY_hi (M, Cout) and dYT_hi
  * (Cout, M) bf16 workspaces; dcol fp32 (M, K) workspace; dw/dbias accumulated; din may be NULL. */
 int riqn_conv_bwd_tc(const riqn_conv_geom* g, const float* dout, const float* out, const void* colT_hi, const void* wT_hi,

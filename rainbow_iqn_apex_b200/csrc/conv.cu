@@ -453,6 +453,38 @@ __global__ void __launch_bounds__(256) conv_dy_tile_kernel(int B, int Cout, int 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Strip convolution (forward without an im2col matrix).  With kernel edge k = t * stride, cut the (zero-padded) input
+// into stride x stride blocks: block row r = (b, gy, gx) holds Kc = stride^2 * Cin values, and the im2col row of output
+// (b, oy, ox) is the concatenation of the t x t blocks (oy + dy, ox + dx).  Laying the OUTPUTS on the same G x G block
+// grid (G = OH + t - 1; only gy < OH, gx < OW are real) makes k-block (dy, dx) of an output tile the block rows
+// m0 + dy*G + dx ... : a plain 2-D TMA tile of the block matrix at a row offset (gemm_tc.cu, TC_CONV).
+// ---------------------------------------------------------------------------------------------------------------
+// First layer: uint8 frames -> block matrix of raw pixel values (exact in bf16), within-block order (c, iy, ix).
+__global__ void __launch_bounds__(256) s2d_u8_kernel(riqn_conv_geom g, int G, const uint8_t* __restrict__ in,
+                                                     bf16* __restrict__ a_px) {
+  extern __shared__ __align__(16) uint8_t img[];
+  const int chw = g.Cin * g.H * g.W, s = g.stride, ss = s * s, Kc = ss * g.Cin, K8 = Kc / 8;
+  const long b = blockIdx.x;
+  const uint4* src = reinterpret_cast<const uint4*>(in + b * g.in_bstride);
+  for (int i = threadIdx.x; i < chw / 16; i += blockDim.x) reinterpret_cast<uint4*>(img)[i] = src[i];
+  __syncthreads();
+  for (int item = threadIdx.x; item < G * G * K8; item += blockDim.x) {
+    const int r = item / K8, k0 = (item - r * K8) * 8;
+    const int gy = r / G, gx = r - gy * G;
+    uint32_t e[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int k = k0 + t, c = k / ss, rem = k - c * ss, iy = rem / s, ix = rem - iy * s;
+      const int y = gy * s + iy - g.pad, x = gx * s + ix - g.pad;
+      e[t] = ((unsigned)y < (unsigned)g.H && (unsigned)x < (unsigned)g.W)
+                 ? __float_as_uint((float)img[(c * g.H + y) * g.W + x]) >> 16 : 0u;
+    }
+    *reinterpret_cast<uint4*>(a_px + (b * G * G + r) * Kc + k0) =
+        make_uint4(e[0] | (e[1] << 16), e[2] | (e[3] << 16), e[4] | (e[5] << 16), e[6] | (e[7] << 16));
+  }
+}
+
 static inline int grid_for(long total) {
   long b = (total + 255) / 256;
   return (int)(b > 148L * 32 ? 148L * 32 : (b < 1 ? 1 : b));
@@ -574,6 +606,70 @@ RIQN_API int riqn_conv_fwd_tc_u8(const riqn_conv_geom* g, const unsigned char* i
   ex.ohw = ohw;
   return gemm_bf16_tc((int)M, g->Cout, K, (const bf16*)col_px, nullptr, (const bf16*)ws_hi, (const bf16*)ws_lo, out, g->Cout,
                       TC_BIAS_RELU_NCHW, bias, nullptr, nullptr, 1, s, &ex);
+}
+
+static int strip_params(const riqn_conv_geom* g, int* t, int* G, int* kc) {
+  if (g->KH != g->KW || g->stride < 1 || g->KH % g->stride) return 1;
+  *t = g->KH / g->stride;
+  *G = g->OH + *t - 1;
+  const int Kc = g->stride * g->stride * g->Cin;
+  if (g->OH != g->OW || Kc % 64 || g->OH != (g->H + 2 * g->pad - g->KH) / g->stride + 1) return 1;
+  *kc = Kc / 64;
+  return 0;
+}
+
+RIQN_API int riqn_s2d_u8(const riqn_conv_geom* g, const unsigned char* in, void* a_px, void* stream) {
+  riqn::note_launches(1);
+  int t, G, kc;
+  const int chw = g->Cin * g->H * g->W;
+  if (strip_params(g, &t, &G, &kc) || chw % 16 || g->in_bstride % 16 || (reinterpret_cast<uintptr_t>(in) & 15) ||
+      chw > 96 * 1024)
+    return (int)cudaErrorInvalidValue;
+  static bool attr = false;
+  if (!attr) {
+    RIQN_CUDA(cudaFuncSetAttribute(s2d_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    attr = true;
+  }
+  s2d_u8_kernel<<<g->B, 256, chw, (cudaStream_t)stream>>>(*g, G, in, (bf16*)a_px);
+  return (int)cudaGetLastError();
+}
+
+RIQN_API int riqn_conv_fwd_strip(const riqn_conv_geom* g, const void* a_hi, const void* a_lo, const void* w_hi,
+                                 const void* w_lo, const float* bias, float* out, void* next_hi, void* next_lo,
+                                 int next_stride, int next_grid, void* stream) {
+  riqn::note_launches(1);
+  int t, G, kc;
+  if (strip_params(g, &t, &G, &kc) || g->Cout > 64 || (next_hi && (next_stride < 1 || next_grid < 1)))
+    return (int)cudaErrorInvalidValue;
+  TcExtra ex;
+  ex.strip_t = t; ex.strip_G = G; ex.strip_kc = kc;
+  ex.cv_oh = g->OH; ex.cv_ow = g->OW;
+  ex.nx_hi = (bf16*)next_hi; ex.nx_lo = (bf16*)next_lo; ex.nx_s = next_stride; ex.nx_G = next_grid;
+  return gemm_bf16_tc(g->B * G * G, g->Cout, g->Cin * g->KH * g->KW, (const bf16*)a_hi, (const bf16*)a_lo, (const bf16*)w_hi,
+                      (const bf16*)w_lo, out, g->Cout, TC_CONV, bias, nullptr, nullptr, 1, (cudaStream_t)stream, &ex);
+}
+
+// bf16 transposed im2col (K, M) alone -- the wgrad operand of riqn_conv_bwd_tc when the forward ran as a strip
+// convolution.  in_is_u8: raw pixel VALUES are written (pass wgrad_scale = 1/255 to riqn_conv_bwd_tc).
+RIQN_API int riqn_im2col_bf16_t(const riqn_conv_geom* g, const void* in, int in_is_u8, void* colT_hi, void* stream) {
+  riqn::note_launches(1);
+  cudaStream_t s = (cudaStream_t)stream;
+  const long M = (long)g->B * g->OH * g->OW;
+  const int K = g->Cin * g->KH * g->KW, chw = g->Cin * g->H * g->W, ohw = g->OH * g->OW;
+  if (K % 8 || M % 8) return (int)cudaErrorInvalidValue;
+  if (in_is_u8) {
+    if (chw % 16 || g->in_bstride % 16 || (reinterpret_cast<uintptr_t>(in) & 15) || ohw % 8 || chw > 96 * 1024)
+      return (int)cudaErrorInvalidValue;
+    static bool attr = false;
+    if (!attr) {
+      RIQN_CUDA(cudaFuncSetAttribute(im2col_u8_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      attr = true;
+    }
+    im2col_u8_staged_kernel<<<dim3(g->B, 4), 256, chw, s>>>(*g, (const unsigned char*)in, nullptr, (bf16*)colT_hi);
+  } else {
+    im2col_bf16_t_kernel<float><<<grid_for(M * K / 8), 256, 0, s>>>(*g, (const float*)in, (bf16*)colT_hi);
+  }
+  return (int)cudaGetLastError();
 }
 
 RIQN_API int riqn_conv_bwd_tc(const riqn_conv_geom* g, const float* dout, const float* out, const void* colT_hi,

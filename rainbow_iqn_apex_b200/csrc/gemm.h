@@ -32,7 +32,7 @@ int gemm_f32(int M, int N, int K, const float* A, long sAm, long sAk, const floa
 
 // ---- tcgen05 / TMA path (gemm_tc.cu) ---------------------------------------------------------------------------
 enum TcEpi { TC_STORE = 0, TC_BIAS_RELU = 1, TC_ATOMIC = 2, TC_NOISY_WGRAD = 3, TC_BIAS_RELU_NCHW = 4, TC_EMBED = 5,
-             TC_COL2IM = 6 };
+             TC_COL2IM = 6, TC_CONV = 7 };
 
 struct TcExtra {
   int ohw = 1;
@@ -42,9 +42,16 @@ struct TcExtra {
   __nv_bfloat16 *o_hi = nullptr, *o_lo = nullptr, *o_hiT = nullptr, *o_loT = nullptr;
   // TC_COL2IM: row m = (b, oh, ow), column n = (c, kh, kw); C is the NCHW image gradient (pad == 0), accumulated into
   int ci_h = 0, ci_w = 0, ci_cin = 0, ci_kh = 0, ci_kw = 0, ci_stride = 0, ci_ow = 0;
+  // Strip convolution (TC_CONV): A is the space-to-depth image (B*G*G rows of strip_kc*64 values); k-block kb reads rows
+  // m0 + dy*G + dx (shift = kb / strip_kc = dy*strip_t + dx), columns (kb % strip_kc)*64.  Row m = (b, gy, gx) on the
+  // G x G grid is a real output iff gy < cv_oh and gx < cv_ow; C is the NCHW fp32 output (relu(acc + bias)); nx_hi / nx_lo
+  // (may be null) receive the bf16 images in the NEXT layer's space-to-depth layout (block edge nx_s, grid nx_G).
+  int strip_t = 0, strip_G = 0, strip_kc = 0, cv_oh = 0, cv_ow = 0, nx_s = 0, nx_G = 0;
+  __nv_bfloat16 *nx_hi = nullptr, *nx_lo = nullptr;
 };
 
 // C (+)= A B^T, A (M,K) / B (N,K) row-major bf16 (K % 8 == 0); *_lo non-null selects the split-bf16 x3 product.
+// (TC_CONV: M = B*G*G grid rows, K = strip_t^2 * strip_kc * 64.)
 int gemm_bf16_tc(int M, int N, int K, const __nv_bfloat16* A_hi, const __nv_bfloat16* A_lo, const __nv_bfloat16* B_hi,
                  const __nv_bfloat16* B_lo, float* C, long ldc, int epi, const float* bias, float* out2, const float* eps,
                  int split_k, cudaStream_t s, const TcExtra* ex);

@@ -127,26 +127,39 @@ __device__ __forceinline__ uint32_t umma_idesc_bf16(int m, int n) {
 // Each lane deposits its row with 8 STS.128; then every instruction moves FOUR rows: lane l handles piece (l & 7) of
 // row (l >> 3).
 constexpr int kStRow = 32;
-__device__ __forceinline__ void stage_row(uint32_t* st, const uint32_t (&w)[32], int lane) {
+// explicit shared-space accesses: the staging pointer comes from an integer-aligned base, which the compiler would
+// otherwise treat as a generic address (LD/ST instead of LDS/STS)
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+// st: 32-bit shared address of this warp's 32 x 32-word staging tile
+__device__ __forceinline__ void stage_row(uint32_t st, const uint32_t (&w)[32], int lane) {
   __syncwarp();
-  uint4* dst = reinterpret_cast<uint4*>(st + lane * kStRow);
+  const uint32_t row = st + lane * (kStRow * 4);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) dst[j ^ (lane & 7)] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+  for (int j = 0; j < 8; ++j) sts128(row + ((j ^ (lane & 7)) << 4), w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
   __syncwarp();
 }
-__device__ __forceinline__ void warp_store_rows_f32(uint32_t* st, const uint32_t (&w)[32], int lane, float* base, long ld,
+__device__ __forceinline__ uint4 staged_piece(uint32_t st, int r, int piece) {
+  return lds128(st + r * (kStRow * 4) + ((piece ^ (r & 7)) << 4));
+}
+__device__ __forceinline__ void warp_store_rows_f32(uint32_t st, const uint32_t (&w)[32], int lane, float* base, long ld,
                                                     int rows_valid) {
   stage_row(st, w, lane);
   const int sub = lane >> 3, piece = lane & 7;
 #pragma unroll
   for (int r0 = 0; r0 < 32; r0 += 4) {
     const int r = r0 + sub;
-    if (r < rows_valid)
-      *reinterpret_cast<uint4*>(base + (long)r * ld + piece * 4) = *reinterpret_cast<const uint4*>(st + r * kStRow + ((piece ^ (r & 7)) * 4));
+    if (r < rows_valid) *reinterpret_cast<uint4*>(base + (long)r * ld + piece * 4) = staged_piece(st, r, piece);
   }
 }
 // w[0..15] = hi pairs (cols 2k, 2k+1), w[16..31] = lo pairs: pieces 0-3 go to the hi image, 4-7 to the lo image
-__device__ __forceinline__ void warp_store_rows_bf16(uint32_t* st, const uint32_t (&w)[32], int lane, bf16* hi_base,
+__device__ __forceinline__ void warp_store_rows_bf16(uint32_t st, const uint32_t (&w)[32], int lane, bf16* hi_base,
                                                      bf16* lo_base, long ld, int rows_valid) {
   stage_row(st, w, lane);
   const int sub = lane >> 3, piece = lane & 7;
@@ -155,15 +168,14 @@ __device__ __forceinline__ void warp_store_rows_bf16(uint32_t* st, const uint32_
 #pragma unroll
   for (int r0 = 0; r0 < 32; r0 += 4) {
     const int r = r0 + sub;
-    if (r < rows_valid)
-      *reinterpret_cast<uint4*>(dstb + (long)r * ld + (piece & 3) * 8) = *reinterpret_cast<const uint4*>(st + r * kStRow + ((piece ^ (r & 7)) * 4));
+    if (r < rows_valid) *reinterpret_cast<uint4*>(dstb + (long)r * ld + (piece & 3) * 8) = staged_piece(st, r, piece);
   }
 }
 
 // C += alpha * acc (and out2 += alpha * acc * eps for the NoisyLinear weight gradient) on full 128-byte row segments:
 // plain 16-byte read-modify-writes when this CTA is the only contributor, red.global.add.v4.f32 under split-K.
 template <bool NOISY>
-__device__ __forceinline__ void warp_accum_rows_f32(uint32_t* st, const uint32_t (&w)[32], int lane, float* c, float* out2,
+__device__ __forceinline__ void warp_accum_rows_f32(uint32_t st, const uint32_t (&w)[32], int lane, float* c, float* out2,
                                                     const float* eps, long ld, int rows_valid, bool atomic, float alpha) {
   stage_row(st, w, lane);
   const int sub = lane >> 3, piece = lane & 7;
@@ -171,8 +183,9 @@ __device__ __forceinline__ void warp_accum_rows_f32(uint32_t* st, const uint32_t
   for (int r0 = 0; r0 < 32; r0 += 4) {
     const int r = r0 + sub;
     if (r < rows_valid) {
-      float4 a = *reinterpret_cast<const float4*>(st + r * kStRow + ((piece ^ (r & 7)) * 4));
-      a.x *= alpha; a.y *= alpha; a.z *= alpha; a.w *= alpha;
+      const uint4 au = staged_piece(st, r, piece);
+      float4 a = make_float4(__uint_as_float(au.x) * alpha, __uint_as_float(au.y) * alpha, __uint_as_float(au.z) * alpha,
+                             __uint_as_float(au.w) * alpha);
       const long off = (long)r * ld + piece * 4;
       float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
       if (NOISY) {
@@ -232,6 +245,8 @@ struct TcArgs {
   int batch;
   bf16 *o_hi, *o_lo;     // TC_EMBED: bf16 hi / lo images of the result, row-major (M, N)   (may be null)
   bf16 *o_hiT, *o_loT;   // TC_EMBED: transposed (N, M) images                              (may be null)
+  int strip_t, strip_G, strip_kc, cv_oh, cv_ow, nx_s, nx_G;   // TC_CONV (see gemm.h)
+  bf16 *nx_hi, *nx_lo;
 };
 
 template <int NSPLIT, int EPI, int BN>
@@ -249,7 +264,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
   uint64_t* tfull = bars + 2 * Cfg::kStages;   // [2]        MMA -> epilogue
   uint64_t* tempty = tfull + 2;                // [2]        epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  uint32_t* epi_stage = reinterpret_cast<uint32_t*>(smem + Cfg::kStages * Cfg::kStageBytes + 256);
+  const uint32_t epi_stage = (uint32_t)__cvta_generic_to_shared(smem + Cfg::kStages * Cfg::kStageBytes + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_units = p.m_tiles * p.n_tiles * p.k_splits;
@@ -281,9 +296,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* s = smem + stage * Cfg::kStageBytes;
           mbar_expect_tx(&full[stage], Cfg::kStageBytes);
-          tma_load_2d(s, &mapA_hi, kb * TBK, mt * TBM, &full[stage]);
+          int a_col = kb * TBK, a_row = mt * TBM;
+          if (EPI == TC_CONV) {     // strip convolution: shifted rows of the space-to-depth image
+            const int sft = kb / p.strip_kc, dy = sft / p.strip_t;
+            a_col = (kb - sft * p.strip_kc) * TBK;
+            a_row += dy * p.strip_G + (sft - dy * p.strip_t);
+          }
+          tma_load_2d(s, &mapA_hi, a_col, a_row, &full[stage]);
           tma_load_2d(s + Cfg::kOps * Cfg::kABytes, &mapB_hi, kb * TBK, nt * TBN, &full[stage]);
-          if (NSPLIT == 3) tma_load_2d(s + Cfg::kABytes, &mapA_lo, kb * TBK, mt * TBM, &full[stage]);
+          if (NSPLIT == 3) tma_load_2d(s + Cfg::kABytes, &mapA_lo, a_col, a_row, &full[stage]);
           if (NSPLIT >= 2)
             tma_load_2d(s + Cfg::kAOps * Cfg::kABytes + Cfg::kBBytes, &mapB_lo, kb * TBK, nt * TBN, &full[stage]);
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
@@ -397,6 +418,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (n0 + j < p.N) cb[(long)j * p.ohw] = fmaxf(__uint_as_float(v[j]) + p.bias[n0 + j], 0.f);
+          } else if (EPI == TC_CONV) {
+            const int gg = p.strip_G * p.strip_G;
+            const int b = m / gg, rem = m - b * gg;
+            const int gy = rem / p.strip_G, gx = rem - gy * p.strip_G;
+            if (gy < p.cv_oh && gx < p.cv_ow) {
+              float x[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) x[j] = n0 + j < p.N ? fmaxf(__uint_as_float(v[j]) + p.bias[n0 + j], 0.f) : 0.f;
+              const int plane = p.cv_oh * p.cv_ow;
+              float* cb = p.C + ((long)b * p.N + n0) * plane + gy * p.cv_ow + gx;     // lanes = consecutive gx
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (n0 + j < p.N) cb[(long)j * plane] = x[j];
+              if (p.nx_hi != nullptr && n0 + 32 <= p.N) {
+                // this pixel's channels are contiguous in the next layer's space-to-depth row: 64-byte pieces
+                const int sn = p.nx_s, by = gy / sn, bx = gx / sn;
+                const long r = ((long)b * p.nx_G + by) * p.nx_G + bx;
+                const long o = r * ((long)sn * sn * p.N) + (long)((gy - by * sn) * sn + (gx - bx * sn)) * p.N + n0;
+                uint32_t wh[16], wl[16];
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                  const __nv_bfloat162 h2 = __floats2bfloat162_rn(x[j], x[j + 1]);
+                  const uint32_t hw = *reinterpret_cast<const uint32_t*>(&h2);
+                  const __nv_bfloat162 l2 = __floats2bfloat162_rn(x[j] - __uint_as_float(hw << 16),
+                                                                  x[j + 1] - __uint_as_float(hw & 0xffff0000u));
+                  wh[j / 2] = hw;
+                  wl[j / 2] = *reinterpret_cast<const uint32_t*>(&l2);
+                }
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                  reinterpret_cast<uint4*>(p.nx_hi + o)[q4] = make_uint4(wh[4 * q4], wh[4 * q4 + 1], wh[4 * q4 + 2], wh[4 * q4 + 3]);
+                  if (p.nx_lo)
+                    reinterpret_cast<uint4*>(p.nx_lo + o)[q4] = make_uint4(wl[4 * q4], wl[4 * q4 + 1], wl[4 * q4 + 2], wl[4 * q4 + 3]);
+                }
+              }
+            }
           } else if (EPI == TC_EMBED || EPI == TC_COL2IM) {
             // handled below with the whole warp
           } else if (!(p.vec_acc && n0 + 32 <= p.N)) {
@@ -442,7 +499,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
         }
         if ((EPI == TC_STORE || EPI == TC_EMBED || (EPI == TC_BIAS_RELU && (p.M & 1) == 0) ||
              ((EPI == TC_ATOMIC || EPI == TC_NOISY_WGRAD) && p.vec_acc)) && n0 + 32 <= p.N) {
-          uint32_t* st = epi_stage + (warp - 2) * (32 * kStRow);
+          const uint32_t st = epi_stage + (warp - 2) * (32 * kStRow * 4);
           const int m_base = mt * TBM + quarter * 32;
           const int rows_valid = min(32, p.M - m_base);            // warp-uniform
           if (rows_valid > 0) {
@@ -581,17 +638,22 @@ int gemm_bf16_tc(int M, int N, int K, const bf16* A_hi, const bf16* A_lo, const 
   const bool split3 = A_lo != nullptr && B_lo != nullptr;
   const bool split2 = A_lo == nullptr && B_lo != nullptr;
   // narrow outputs (conv channels, embedding width) get narrow tiles; only the epilogues that occur with them exist
-  const bool narrow_ok = epi == TC_BIAS_RELU_NCHW || ((epi == TC_ATOMIC || epi == TC_STORE) && !split3 && !split2);
+  const bool narrow_ok = epi == TC_BIAS_RELU_NCHW || epi == TC_CONV || ((epi == TC_ATOMIC || epi == TC_STORE) && !split3 && !split2);
+  const bool strip = epi == TC_CONV;
+  if (strip && (ex == nullptr || ex->strip_t < 1 || ex->strip_kc < 1 || ex->strip_G < 1 || N > 64 ||
+                K != ex->strip_t * ex->strip_t * ex->strip_kc * TBK || (ex->nx_hi && (N % 32))))
+    return (int)cudaErrorInvalidValue;
+  const long a_k = strip ? (long)ex->strip_kc * TBK : K;       // row length of the A image
   const int bn = (narrow_ok && N <= 32) ? 32 : (narrow_ok && N <= 64) ? 64 : 256;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
-  int rc = make_map(&ma_hi, A_hi, M, K, TBM);
+  int rc = make_map(&ma_hi, A_hi, M, a_k, TBM);
   if (rc) return rc;
   rc = make_map(&mb_hi, B_hi, N, K, bn);
   if (rc) return rc;
   ma_lo = ma_hi;
   mb_lo = mb_hi;
   if (split3) {
-    rc = make_map(&ma_lo, A_lo, M, K, TBM);
+    rc = make_map(&ma_lo, A_lo, M, a_k, TBM);
     if (rc) return rc;
   }
   if (split3 || split2) {
@@ -615,6 +677,9 @@ int gemm_bf16_tc(int M, int N, int K, const bf16* A_hi, const bf16* A_lo, const 
   p.ohw = ex ? ex->ohw : 1; p.feat = ex ? ex->feat : nullptr; p.batch = ex ? ex->batch : 1;
   p.ci_h = ex ? ex->ci_h : 0; p.ci_w = ex ? ex->ci_w : 0; p.ci_cin = ex ? ex->ci_cin : 0; p.ci_kh = ex ? ex->ci_kh : 0;
   p.ci_kw = ex ? ex->ci_kw : 0; p.ci_stride = ex ? ex->ci_stride : 0; p.ci_ow = ex ? ex->ci_ow : 0;
+  p.strip_t = ex ? ex->strip_t : 0; p.strip_G = ex ? ex->strip_G : 0; p.strip_kc = ex ? ex->strip_kc : 0;
+  p.cv_oh = ex ? ex->cv_oh : 0; p.cv_ow = ex ? ex->cv_ow : 0; p.nx_s = ex ? ex->nx_s : 0; p.nx_G = ex ? ex->nx_G : 0;
+  p.nx_hi = ex ? ex->nx_hi : nullptr; p.nx_lo = ex ? ex->nx_lo : nullptr;
   if (epi == TC_COL2IM && (ex == nullptr || p.ci_kh * p.ci_kw * p.ci_cin != N || split3 || split2)) return (int)cudaErrorInvalidValue;
   p.o_hi = ex ? ex->o_hi : nullptr; p.o_lo = ex ? ex->o_lo : nullptr;
   p.o_hiT = ex ? ex->o_hiT : nullptr; p.o_loT = ex ? ex->o_loT : nullptr;
@@ -630,11 +695,13 @@ int gemm_bf16_tc(int M, int N, int K, const bf16* A_hi, const bf16* A_lo, const 
       case TC_ATOMIC: RIQN_TC_GO(3, TC_ATOMIC);
       case TC_NOISY_WGRAD: RIQN_TC_GO(3, TC_NOISY_WGRAD);
       case TC_BIAS_RELU_NCHW: RIQN_TC_NARROW(3, TC_BIAS_RELU_NCHW); RIQN_TC_GO(3, TC_BIAS_RELU_NCHW);
+      case TC_CONV: RIQN_TC_NARROW(3, TC_CONV); break;
       case TC_EMBED: RIQN_TC_GO(3, TC_EMBED);
     }
   } else if (split2) {
     switch (epi) {
       case TC_BIAS_RELU_NCHW: RIQN_TC_NARROW(2, TC_BIAS_RELU_NCHW); RIQN_TC_GO(2, TC_BIAS_RELU_NCHW);
+      case TC_CONV: RIQN_TC_NARROW(2, TC_CONV); break;
       case TC_STORE: RIQN_TC_GO(2, TC_STORE);
       default: return (int)cudaErrorInvalidValue;
     }
@@ -646,6 +713,7 @@ int gemm_bf16_tc(int M, int N, int K, const bf16* A_hi, const bf16* A_lo, const 
       case TC_ATOMIC: RIQN_TC_NARROW(1, TC_ATOMIC); RIQN_TC_GO(1, TC_ATOMIC);
       case TC_NOISY_WGRAD: RIQN_TC_GO(1, TC_NOISY_WGRAD);
       case TC_BIAS_RELU_NCHW: RIQN_TC_NARROW(1, TC_BIAS_RELU_NCHW); RIQN_TC_GO(1, TC_BIAS_RELU_NCHW);
+      case TC_CONV: RIQN_TC_NARROW(1, TC_CONV); break;
       case TC_EMBED: RIQN_TC_GO(1, TC_EMBED);
     }
   }

@@ -34,6 +34,7 @@ _ALIGN = 64  # floats; arena groups start on 256-byte boundaries
 #   "fp32"  : CUDA-core fp32 GEMM (gemm_simt.cu), the cross-check path
 PRECISION = {"fwd": os.environ.get("RIQN_FWD_PRECISION", "bf16x3"), "bwd": os.environ.get("RIQN_BWD_PRECISION", "bf16")}
 WGRAD_SPLIT_K = int(os.environ.get("RIQN_WGRAD_SPLIT_K", "4"))
+_NO_STRIP = os.environ.get("RIQN_NO_STRIP_CONV", "0") == "1"      # fall back to the explicit-im2col forward
 
 
 def set_precision(fwd=None, bwd=None):
@@ -122,6 +123,23 @@ class NoisyLinear(nn.Module):
         call("riqn_gemm_f32", x.shape[0], self.out_features, self.in_features, ptr(x), self.in_features, 1,
              ptr(self._w_eff), self.in_features, 1, ptr(out), self.out_features)
         return out + self._b_eff
+
+
+def _strip_perm(cin, k, stride, first):
+    """Column permutation of a (Cout, Cin*k*k) weight for the strip convolution: new index (dy, dx, within-block) ->
+    original index c*k*k + kh*k + kw, with kh = stride*dy + iy, kw = stride*dx + ix.  Within a block the first layer
+    (uint8 frames, riqn_s2d_u8) is ordered (c, iy, ix); later layers (written by the previous layer's epilogue) are
+    ordered (iy, ix, c)."""
+    t = k // stride
+    idx = []
+    for dy in range(t):
+        for dx in range(t):
+            if first:
+                order = [(c, iy, ix) for c in range(cin) for iy in range(stride) for ix in range(stride)]
+            else:
+                order = [(c, iy, ix) for iy in range(stride) for ix in range(stride) for c in range(cin)]
+            idx += [c * k * k + (stride * dy + iy) * k + (stride * dx + ix) for c, iy, ix in order]
+    return torch.tensor(idx, dtype=torch.long)
 
 
 def _geom(batch, cin, h, cout, k, stride, pad, in_bstride=None):
@@ -360,6 +378,20 @@ class DQN(nn.Module):
             call("riqn_split_bf16", hi.shape[0], hi.shape[1], ptr(conv.weight), ptr(hi), ptr(lo), ptr(hiT), None)
         call("riqn_split_bf16_scaled", 32, self._conv1_px_ops[0].shape[1], ptr(self.conv1.weight), 255.0,
              ptr(self._conv1_px_ops[0]), ptr(self._conv1_px_ops[1]))
+        # strip-convolution weights: K reordered to (dy, dx, within-block) -- see riqn_conv_fwd_strip
+        if getattr(self, "_strip_ops", None) is None or self._strip_ops["conv1"][0].device != dev:
+            self._strip_perm = {n: _strip_perm(cin, k, st, first).to(dev) for n, cin, k, st, first in
+                                (("conv1", self.history, 8, 4, True), ("conv2", 32, 4, 2, False), ("conv3", 64, 3, 1, False))}
+            self._strip_ops = {n: (torch.empty(co, pm.numel(), dtype=torch.bfloat16, device=dev),
+                                   torch.empty(co, pm.numel(), dtype=torch.bfloat16, device=dev))
+                               for (n, pm), co in zip(self._strip_perm.items(), (32, 64, 64))}
+        for name, conv in (("conv1", self.conv1), ("conv2", self.conv2), ("conv3", self.conv3)):
+            hi, lo = self._strip_ops[name]
+            wp = conv.weight.detach().reshape(hi.shape[0], -1).index_select(1, self._strip_perm[name])
+            if name == "conv1":
+                call("riqn_split_bf16_scaled", hi.shape[0], hi.shape[1], ptr(wp), 255.0, ptr(hi), ptr(lo))
+            else:
+                call("riqn_split_bf16", hi.shape[0], hi.shape[1], ptr(wp), ptr(hi), ptr(lo), None, None)
         if not self.rainbow_only:
             call("riqn_split_bf16", FEAT, self.quantile_embedding_dim, ptr(self.iqn_fc.weight), ptr(self._iqn_ops[0]),
                  ptr(self._iqn_ops[1]), None, None)
@@ -413,6 +445,43 @@ class DQN(nn.Module):
         need_col32 = keep is not None and not bwd_tc
         cols, colTs = [None] * 3, [None] * 3
         px_scale = 1.0
+        strip = (fwd != "fp32" and is_u8 and x.stride(0) % 16 == 0 and x.data_ptr() % 16 == 0 and self.history * 16 == 64
+                 and not _NO_STRIP)
+        if strip:
+            # strip convolution (riqn_conv_fwd_strip): no im2col matrices in the forward; each layer's epilogue writes
+            # the next layer's block matrix.  Block grids: G = OH + k/stride - 1 = 21, 10, 9.
+            x3 = fwd == "bf16x3"
+            bf = lambda *sh: torch.empty(*sh, dtype=torch.bfloat16, device=dev)
+            ckey = ("s2d", x.data_ptr(), tuple(x.shape), tuple(x.stride()))
+            if col_cache is not None and ckey in col_cache:
+                a1 = col_cache[ckey]                 # the pixel block matrix does not depend on the network's weights
+            else:
+                a1 = bf(B * 21 * 21, 16 * self.history)
+                call("riqn_s2d_u8", g1, ptr(x), ptr(a1))
+                if col_cache is not None:
+                    col_cache[ckey] = a1
+            a2_hi, a2_lo = bf(B * 100, 128), (bf(B * 100, 128) if x3 else None)
+            a3_hi, a3_lo = bf(B * 81, 64), (bf(B * 81, 64) if x3 else None)
+            ops = self._strip_ops
+            call("riqn_conv_fwd_strip", g1, ptr(a1), None, ptr(ops["conv1"][0]), ptr(ops["conv1"][1]) if x3 else None,
+                 ptr(self.conv1.bias), ptr(outs[0]), ptr(a2_hi), ptr(a2_lo), 2, 10)
+            call("riqn_conv_fwd_strip", g2, ptr(a2_hi), ptr(a2_lo), ptr(ops["conv2"][0]), ptr(ops["conv2"][1]) if x3 else None,
+                 ptr(self.conv2.bias), ptr(outs[1]), ptr(a3_hi), ptr(a3_lo), 1, 9)
+            call("riqn_conv_fwd_strip", g3, ptr(a3_hi), ptr(a3_lo), ptr(ops["conv3"][0]), ptr(ops["conv3"][1]) if x3 else None,
+                 ptr(self.conv3.bias), ptr(outs[2]), None, None, 0, 0)
+            if keep is not None:                     # operands of the backward products
+                for i, (g, inp) in enumerate(zip(geoms, ins)):
+                    M, K = g.B * g.OH * g.OW, g.Cin * g.KH * g.KW
+                    if bwd_tc:
+                        colTs[i] = bf(K, M)
+                        call("riqn_im2col_bf16_t", g, ptr(inp), 1 if i == 0 else 0, ptr(colTs[i]))
+                    else:
+                        cols[i] = torch.empty(M, K, device=dev)
+                        call("riqn_im2col_f32", g, ptr(inp), 1 if i == 0 else 0, ptr(cols[i]))
+                if bwd_tc:
+                    px_scale = 1.0 / 255.0
+                keep.update(x=x, g=geoms, col=tuple(cols), colT=tuple(colTs), out=outs, bwd_tc=bwd_tc, px_scale=px_scale)
+            return outs[2].view(B, FEAT)
         for i, (g, conv, inp, out) in enumerate(zip(geoms, convs, ins, outs)):
             M, K = g.B * g.OH * g.OW, g.Cin * g.KH * g.KW
             u8 = is_u8 if i == 0 else 0
