@@ -341,6 +341,11 @@ int riqn_split_bf16(long rows, int cols, const float* src, void* hi, void* lo, v
 int riqn_gemm_bf16_tc(int M, int N, int K, const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo,
                       float* c, long ldc, int epilogue, const float* bias, float* out2, const float* eps, int split_k,
                       void* c_t_bf16, void* stream);
+/* C (+)= A^T B with A (K, M) and B (K, N) row-major bf16 (M % 8 == 0, N % 8 == 0): the reduction runs over the ROWS, so
+ * a weight gradient dW = dY^T X is taken straight from the row-major activations (MN-major tcgen05 operands, no
+ * transposed copies).  epilogue 0 / 2 / 3 as above (2, 3 scale the accumulator by alpha); single-bf16 product. */
+int riqn_gemm_bf16_tc_mn(int M, int N, int K, const void* a_km, const void* b_kn, float* c, long ldc, int epilogue,
+                         float* out2, const float* eps, float alpha, int split_k, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Test hook: plain strided fp32 product C[m,n] = sum_k A[m*sAm + k*sAk] * B[n*sBn + k*sBk].

@@ -412,45 +412,54 @@ __global__ void __launch_bounds__(256) conv_dy_tile_kernel(int B, int Cout, int 
                                                            const float* __restrict__ out, bf16* __restrict__ dY,
                                                            bf16* __restrict__ dYT, float* __restrict__ dbias) {
   __shared__ __align__(16) unsigned short tile[64][66];
-  const long M = (long)B * ohw, m0 = (long)blockIdx.x * 64;
+  __shared__ float bsum[64];
+  const long M = (long)B * ohw;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  long src0[2];
-  bool ok[2];
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const long m = m0 + lane + 32 * h;
-    ok[h] = m < M;
-    const long b = ok[h] ? m / ohw : 0;
-    src0[h] = b * Cout * ohw + (ok[h] ? m - b * ohw : 0);       // + c * ohw
-  }
-  for (int c = warp; c < Cout; c += 8) {
-    float acc = 0.f;
+  if (threadIdx.x < 64) bsum[threadIdx.x] = 0.f;
+  __syncthreads();
+  const long n_tiles = (M + 63) / 64;
+  for (long tix = blockIdx.x; tix < n_tiles; tix += gridDim.x) {     // persistent: the bias partials stay in the block
+    const long m0 = tix * 64;
+    long src0[2];
+    bool ok[2];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      float v = 0.f;
-      if (ok[h]) {
-        const long src = src0[h] + (long)c * ohw;
-        v = out[src] > 0.f ? dout[src] : 0.f;
-      }
-      const bf16 hb = __float2bfloat16_rn(v);
-      if (ok[h]) dYT[(long)c * M + m0 + lane + 32 * h] = hb;
-      tile[lane + 32 * h][c] = __bfloat16_as_ushort(hb);
-      acc += v;
+      const long m = m0 + lane + 32 * h;
+      ok[h] = m < M;
+      const long b = ok[h] ? m / ohw : 0;
+      src0[h] = b * Cout * ohw + (ok[h] ? m - b * ohw : 0);       // + c * ohw
     }
-    acc = warp_sum(acc);
-    if (lane == 0) atomicAdd(&dbias[c], acc);
-  }
-  __syncthreads();
-  if (dY) {
-    const int ppr = Cout >> 3;                                   // 16-byte pieces per row
-    for (int idx = threadIdx.x; idx < 64 * ppr; idx += blockDim.x) {
-      const int r = idx / ppr, pc = idx - r * ppr;
-      if (m0 + r < M) {
-        const uint32_t* w = reinterpret_cast<const uint32_t*>(&tile[r][pc * 8]);
-        *reinterpret_cast<uint4*>(dY + (m0 + r) * Cout + pc * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+    for (int c = warp; c < Cout; c += 8) {
+      float acc = 0.f;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float v = 0.f;
+        if (ok[h]) {
+          const long src = src0[h] + (long)c * ohw;
+          v = out[src] > 0.f ? dout[src] : 0.f;
+        }
+        const bf16 hb = __float2bfloat16_rn(v);
+        if (ok[h]) dYT[(long)c * M + m0 + lane + 32 * h] = hb;
+        tile[lane + 32 * h][c] = __bfloat16_as_ushort(hb);
+        acc += v;
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) bsum[c] += acc;                               // channel c belongs to this warp only
+    }
+    __syncthreads();
+    if (dY) {
+      const int ppr = Cout >> 3;                                   // 16-byte pieces per row
+      for (int idx = threadIdx.x; idx < 64 * ppr; idx += blockDim.x) {
+        const int r = idx / ppr, pc = idx - r * ppr;
+        if (m0 + r < M) {
+          const uint32_t* w = reinterpret_cast<const uint32_t*>(&tile[r][pc * 8]);
+          *reinterpret_cast<uint4*>(dY + (m0 + r) * Cout + pc * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
       }
     }
+    __syncthreads();
   }
+  if (threadIdx.x < Cout) atomicAdd(&dbias[threadIdx.x], bsum[threadIdx.x]);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -469,6 +478,38 @@ __global__ void __launch_bounds__(256) s2d_u8_kernel(riqn_conv_geom g, int G, co
   const uint4* src = reinterpret_cast<const uint4*>(in + b * g.in_bstride);
   for (int i = threadIdx.x; i < chw / 16; i += blockDim.x) reinterpret_cast<uint4*>(img)[i] = src[i];
   __syncthreads();
+  const bool fast = s == 4 && g.pad == 1 && (g.W & 3) == 0 && (G - 1) * 4 + 2 < g.W && (G - 1) * 4 + 2 < g.H;
+  if (fast) {
+    // item = (block r, channel c, row pair iy0 in {0, 2}): bytes 4*gx-1 .. 4*gx+2 of two image rows = byte 3 of word
+    // gx-1 and bytes 0..2 of word gx; converted with the 2^23 trick (exact)
+    const uint32_t* img32 = reinterpret_cast<const uint32_t*>(img);
+    const int wpr = g.W >> 2;
+    auto cvt2 = [](uint32_t w, uint32_t sa, uint32_t sb) -> uint32_t {
+      const float fa = __uint_as_float(__byte_perm(w, 0x4B000000u, sa)) - 8388608.0f;
+      const float fb = __uint_as_float(__byte_perm(w, 0x4B000000u, sb)) - 8388608.0f;
+      return __byte_perm(__float_as_uint(fa), __float_as_uint(fb), 0x7632);
+    };
+    for (int item = threadIdx.x; item < G * G * K8; item += blockDim.x) {
+      const int r = item / K8, q = item - r * K8;               // q = c * 2 + (iy0 / 2)
+      const int gy = r / G, gx = r - gy * G, c = q >> 1, iy0 = (q & 1) * 2;
+      uint32_t o[4];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int y = gy * 4 + iy0 + h - 1;
+        uint32_t w0 = 0u, w1 = 0u;
+        if (y >= 0) {
+          const uint32_t* rowp = img32 + (c * g.H + y) * wpr + gx;
+          w0 = gx > 0 ? rowp[-1] : 0u;
+          w1 = rowp[0];
+        }
+        const uint32_t a = __byte_perm(w0, w1, 0x0043);          // bytes: w0.3, w1.0
+        o[2 * h] = cvt2(a, 0x7650, 0x7651);
+        o[2 * h + 1] = cvt2(w1, 0x7651, 0x7652);
+      }
+      *reinterpret_cast<uint4*>(a_px + (b * G * G + r) * Kc + q * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    return;
+  }
   for (int item = threadIdx.x; item < G * G * K8; item += blockDim.x) {
     const int r = item / K8, k0 = (item - r * K8) * 8;
     const int gy = r / G, gx = r - gy * G;
@@ -682,7 +723,8 @@ RIQN_API int riqn_conv_bwd_tc(const riqn_conv_geom* g, const float* dout, const 
   const int ohw = g->OH * g->OW;
   if (M % 8 || g->Cout % 8) return (int)cudaErrorInvalidValue;
   if (g->Cout <= 64) {
-    conv_dy_tile_kernel<<<(unsigned)((M + 63) / 64), 256, 0, s>>>(g->B, g->Cout, ohw, dout, out,
+    const long tiles = (M + 63) / 64;
+    conv_dy_tile_kernel<<<(unsigned)(tiles < 148 * 4 ? tiles : 148 * 4), 256, 0, s>>>(g->B, g->Cout, ohw, dout, out,
                                                                  din ? (bf16*)dY_hi : nullptr, (bf16*)dYT_hi, dbias);
   } else {
     dim3 grid((unsigned)((M + 256 * 8 - 1) / (256 * 8)), g->Cout);

@@ -114,6 +114,12 @@ __device__ __forceinline__ uint64_t umma_desc_k128(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
          ((uint64_t)2 << 61);
 }
+// MN-major, 128-byte-swizzled operand tile (cute/atom/mma_traits_sm100.hpp, make_umma_desc<Major::MN>): k-rows of 64
+// MN-elements (128 B), 8-row swizzle atoms SBO = 1024 B apart along K, further 64-element MN slabs LBO = 8192 B apart.
+__device__ __forceinline__ uint64_t umma_desc_mn128(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(8192 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
 // kind::f16 instruction descriptor: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, K-major both, N>>3 [17,23), M>>4 [24,29)
 __device__ __forceinline__ uint32_t umma_idesc_bf16(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
@@ -246,6 +252,7 @@ struct TcArgs {
   bf16 *o_hi, *o_lo;     // TC_EMBED: bf16 hi / lo images of the result, row-major (M, N)   (may be null)
   bf16 *o_hiT, *o_loT;   // TC_EMBED: transposed (N, M) images                              (may be null)
   int strip_t, strip_G, strip_kc, cv_oh, cv_ow, nx_s, nx_G;   // TC_CONV (see gemm.h)
+  int mn_major, wg_t, wg_G, wg_kc;                             // MN-major operands / strip weight gradient (gemm.h)
   bf16 *nx_hi, *nx_lo;
 };
 
@@ -296,6 +303,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* s = smem + stage * Cfg::kStageBytes;
           mbar_expect_tx(&full[stage], Cfg::kStageBytes);
+          if (NSPLIT == 1 && p.mn_major) {
+            // (K, MN) row-major operands: 64 x 64 boxes, inner coordinate = MN offset, outer = reduction row
+            const int kk = kb * TBK;
+#pragma unroll
+            for (int i = 0; i < TBM / 64; ++i) tma_load_2d(s + i * 8192, &mapA_hi, mt * TBM + 64 * i, kk, &full[stage]);
+#pragma unroll
+            for (int i = 0; i < (TBN >= 64 ? TBN / 64 : 1); ++i) {
+              int b_in = nt * TBN + 64 * i, b_row = kk;
+              if (p.wg_t) {                        // strip weight gradient: this 64-column slab has its own row shift
+                const int slab = b_in >> 6, sft = slab / p.wg_kc, dy = sft / p.wg_t;
+                b_in = (slab - sft * p.wg_kc) << 6;
+                b_row += dy * p.wg_G + (sft - dy * p.wg_t);
+              }
+              tma_load_2d(s + Cfg::kOps * Cfg::kABytes + i * 8192, &mapB_hi, b_in, b_row, &full[stage]);
+            }
+            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+            continue;
+          }
           int a_col = kb * TBK, a_row = mt * TBM;
           if (EPI == TC_CONV) {     // strip convolution: shifted rows of the space-to-depth image
             const int sft = kb / p.strip_kc, dy = sft / p.strip_t;
@@ -331,6 +356,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint32_t sb = sa + Cfg::kOps * Cfg::kABytes;
+          if (NSPLIT == 1 && p.mn_major) {
+#pragma unroll
+            for (int k = 0; k < TBK / UMMA_K; ++k) {
+              const uint32_t koff = k * (UMMA_K / 8) * 1024;   // 16 reduction rows = two 8-row swizzle atoms
+              umma_bf16(tmem_d, umma_desc_mn128(sa + koff), umma_desc_mn128(sb + koff), idesc | (1u << 15) | (1u << 16),
+                        (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(&empty[stage]);
+            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+            continue;
+          }
 #pragma unroll
           for (int k = 0; k < TBK / UMMA_K; ++k) {
             const uint32_t koff = k * UMMA_K * 2;   // bytes along K inside the 128 B swizzle row
@@ -644,12 +680,27 @@ int gemm_bf16_tc(int M, int N, int K, const bf16* A_hi, const bf16* A_lo, const 
                 K != ex->strip_t * ex->strip_t * ex->strip_kc * TBK || (ex->nx_hi && (N % 32))))
     return (int)cudaErrorInvalidValue;
   const long a_k = strip ? (long)ex->strip_kc * TBK : K;       // row length of the A image
-  const int bn = (narrow_ok && N <= 32) ? 32 : (narrow_ok && N <= 64) ? 64 : 256;
+  const bool mn = ex != nullptr && ex->mn_major != 0;
+  if (mn) {
+    // A (K, M), B (K, N) row-major; only the plain single-bf16 product with full-width (or 64-wide) N tiles
+    if (split3 || split2 || (M % 8) || (N % 8)) return (int)cudaErrorInvalidValue;
+  }
+  const int bn = (ex != nullptr && ex->mn_major) ? ((narrow_ok && N <= 64) ? 64 : 256)
+                                                 : (narrow_ok && N <= 32) ? 32 : (narrow_ok && N <= 64) ? 64 : 256;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
-  int rc = make_map(&ma_hi, A_hi, M, a_k, TBM);
-  if (rc) return rc;
-  rc = make_map(&mb_hi, B_hi, N, K, bn);
-  if (rc) return rc;
+  int rc;
+  if (mn) {
+    const long b_cols = ex->wg_t ? (long)ex->wg_kc * TBK : N;      // strip weight gradient: B is the block matrix
+    rc = make_map(&ma_hi, A_hi, K, M, 64);
+    if (rc) return rc;
+    rc = make_map(&mb_hi, B_hi, K, b_cols, 64);
+    if (rc) return rc;
+  } else {
+    rc = make_map(&ma_hi, A_hi, M, a_k, TBM);
+    if (rc) return rc;
+    rc = make_map(&mb_hi, B_hi, N, K, bn);
+    if (rc) return rc;
+  }
   ma_lo = ma_hi;
   mb_lo = mb_hi;
   if (split3) {
@@ -680,6 +731,7 @@ int gemm_bf16_tc(int M, int N, int K, const bf16* A_hi, const bf16* A_lo, const 
   p.strip_t = ex ? ex->strip_t : 0; p.strip_G = ex ? ex->strip_G : 0; p.strip_kc = ex ? ex->strip_kc : 0;
   p.cv_oh = ex ? ex->cv_oh : 0; p.cv_ow = ex ? ex->cv_ow : 0; p.nx_s = ex ? ex->nx_s : 0; p.nx_G = ex ? ex->nx_G : 0;
   p.nx_hi = ex ? ex->nx_hi : nullptr; p.nx_lo = ex ? ex->nx_lo : nullptr;
+  p.mn_major = mn ? 1 : 0; p.wg_t = ex ? ex->wg_t : 0; p.wg_G = ex ? ex->wg_G : 0; p.wg_kc = ex ? ex->wg_kc : 0;
   if (epi == TC_COL2IM && (ex == nullptr || p.ci_kh * p.ci_kw * p.ci_cin != N || split3 || split2)) return (int)cudaErrorInvalidValue;
   p.o_hi = ex ? ex->o_hi : nullptr; p.o_lo = ex ? ex->o_lo : nullptr;
   p.o_hiT = ex ? ex->o_hiT : nullptr; p.o_loT = ex ? ex->o_loT : nullptr;
@@ -797,4 +849,15 @@ RIQN_API int riqn_gemm_bf16_tc(int M, int N, int K, const void* a_hi, const void
   ex.o_hiT = (bf16*)c_t_bf16;
   return gemm_bf16_tc(M, N, K, (const bf16*)a_hi, (const bf16*)a_lo, (const bf16*)b_hi, (const bf16*)b_lo, c, ldc, epilogue,
                       bias, out2, eps, split_k, (cudaStream_t)stream, &ex);
+}
+
+RIQN_API int riqn_gemm_bf16_tc_mn(int M, int N, int K, const void* a_km, const void* b_kn, float* c, long ldc, int epilogue,
+                                  float* out2, const float* eps, float alpha, int split_k, void* stream) {
+  riqn::note_launches(1);
+  if (epilogue != TC_STORE && epilogue != TC_ATOMIC && epilogue != TC_NOISY_WGRAD) return (int)cudaErrorInvalidValue;
+  TcExtra ex;
+  ex.mn_major = 1;
+  ex.alpha = alpha;
+  return gemm_bf16_tc(M, N, K, (const bf16*)a_km, nullptr, (const bf16*)b_kn, nullptr, c, ldc, epilogue, nullptr, out2, eps,
+                      split_k, (cudaStream_t)stream, &ex);
 }

@@ -572,13 +572,15 @@ __global__ void __launch_bounds__(256) z_dueling_bwd_bf16_kernel(long R, int B, 
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long r0 = (long)blockIdx.x * 32;
   const int Nq = (int)(R / B);
   float bs[4][8];
 #pragma unroll
   for (int it = 0; it < 4; ++it)
 #pragma unroll
     for (int i = 0; i < 8; ++i) bs[it][i] = 0.f;
+  const long n_blk = (R + 31) / 32;
+  for (long blk = blockIdx.x; blk < n_blk; blk += gridDim.x) {   // persistent: column sums stay in registers
+  const long r0 = blk * 32;
   for (int rr = 0; rr < 4; ++rr) {
     const int rl = warp * 4 + rr;
     const long r = r0 + rl;
@@ -625,10 +627,6 @@ __global__ void __launch_bounds__(256) z_dueling_bwd_bf16_kernel(long R, int B, 
       if (dzT) dzT[(long)lane * R + r] = __float2bfloat16_rn(z);
     }
   }
-#pragma unroll
-  for (int it = 0; it < 4; ++it)
-#pragma unroll
-    for (int i = 0; i < 8; ++i) atomicAdd(&cs[(lane + 32 * it) * 8 + i], bs[it][i]);
   __syncthreads();
   // transposed image: item = (column c, piece p of 8 rows); a warp covers 8 columns x 4 pieces = 8 x 64 contiguous bytes
   const unsigned short* t16 = reinterpret_cast<const unsigned short*>(tile);
@@ -646,6 +644,13 @@ __global__ void __launch_bounds__(256) z_dueling_bwd_bf16_kernel(long R, int B, 
       *reinterpret_cast<uint4*>(dh_hiT + (long)c * R + r0 + 8 * piece) = make_uint4(w[0], w[1], w[2], w[3]);
     }
   }
+  __syncthreads();                                               // the tile is rewritten by the next row block
+  }
+#pragma unroll
+  for (int it = 0; it < 4; ++it)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) atomicAdd(&cs[(lane + 32 * it) * 8 + i], bs[it][i]);
+  __syncthreads();
   for (int c = threadIdx.x; c < 2 * HID; c += blockDim.x) atomicAdd(&colsum[c], cs[c]);
 }
 
@@ -989,7 +994,8 @@ RIQN_API int riqn_dueling_bwd_bf16(long rows, int batch, int hidden, int action_
     attr = true;
   }
   RIQN_CUDA(cudaMemsetAsync(dh_colsum, 0, sizeof(float) * 2 * hidden, s));
-  z_dueling_bwd_bf16_kernel<512><<<(unsigned)((rows + 31) / 32), 256, smem, s>>>(
+  const long n_blk = (rows + 31) / 32;
+  z_dueling_bwd_bf16_kernel<512><<<(unsigned)(n_blk < 148 * 2 ? n_blk : 148 * 2), 256, smem, s>>>(
       rows, batch, action_space, h, wz, dtheta, gscale, (const int64_t*)actions, (__nv_bfloat16*)dh_hi,
       (__nv_bfloat16*)dh_hi_t, dh_colsum, dz, (__nv_bfloat16*)dz_t_bf16);
   return (int)cudaGetLastError();

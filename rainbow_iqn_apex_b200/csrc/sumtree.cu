@@ -187,16 +187,18 @@ __device__ __forceinline__ double np_block_sum(const double* a, int n) {
   return res;
 }
 
-__device__ double np_pairwise_sum(const double* a, int n) {
+// The recursion walk; leaf(off, len, ordinal) supplies the sum of the ordinal-th block (left to right).
+template <typename Leaf>
+__device__ __forceinline__ double np_pairwise_walk(int n, Leaf leaf) {
   int off[24], len[24], stage[24];
   double left[24];
-  int sp = 0;
+  int sp = 0, ordinal = 0;
   off[0] = 0; len[0] = n; stage[0] = 0; sp = 1;
   double ret = 0.0;
   while (sp > 0) {
     const int t = sp - 1;
     if (len[t] <= 128) {
-      ret = np_block_sum(a + off[t], len[t]);
+      ret = leaf(off[t], len[t], ordinal++);
       --sp;
       // hand the value to the ancestors that are waiting for it
       while (sp > 0) {
@@ -224,7 +226,53 @@ __device__ double np_pairwise_sum(const double* a, int n) {
   return ret;
 }
 
-// One CTA per tree depth d >= 1 (blockIdx.x = d - 1); the last CTA does the root.  For a node X at depth d
+__device__ double np_pairwise_sum(const double* a, int n) {
+  return np_pairwise_walk(n, [a](int off, int len, int) { return np_block_sum(a + off, len); });
+}
+
+// The same sum computed by a whole CTA with the SAME operation order: thread 0 lists the <= 128-element blocks, the 8
+// interleaved accumulators of every block run on separate threads, and thread 0 combines the block sums along the
+// recursion.  lo / ll (block offsets / lengths), racc (8 per block), bsum (1 per block): shared scratch for
+// n / 64 + 2 blocks.  Returns the sum on thread 0.
+__device__ double np_pairwise_sum_cta(const double* a, int n, int* lo, int* ll, double* racc, double* bsum, int* n_blocks) {
+  if (threadIdx.x == 0) {
+    int cnt = 0;
+    np_pairwise_walk(n, [&](int off, int len, int) { lo[cnt] = off; ll[cnt] = len; ++cnt; return 0.0; });
+    *n_blocks = cnt;
+  }
+  __syncthreads();
+  const int nb = *n_blocks;
+  for (int t = threadIdx.x; t < nb * 8; t += blockDim.x) {
+    const int blk = t >> 3, k = t & 7, len = ll[blk];
+    const double* x = a + lo[blk];
+    if (len >= 8) {
+      double r = x[k];
+      for (int i = 8; i < len - (len % 8); i += 8) r += x[i + k];
+      racc[t] = r;
+    }
+  }
+  __syncthreads();
+  for (int blk = threadIdx.x; blk < nb; blk += blockDim.x) {
+    const int len = ll[blk];
+    const double* x = a + lo[blk];
+    double res;
+    if (len < 8) {
+      res = 0.0;
+      for (int i = 0; i < len; ++i) res += x[i];
+    } else {
+      const double* r = racc + blk * 8;
+      res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+      for (int i = len - (len % 8); i < len; ++i) res += x[i];
+    }
+    bsum[blk] = res;
+  }
+  __syncthreads();
+  double ret = 0.0;
+  if (threadIdx.x == 0) ret = np_pairwise_walk(n, [bsum](int, int, int ordinal) { return bsum[ordinal]; });
+  return ret;
+}
+
+// gridDim.y CTAs per tree depth d >= 1 (blockIdx.x = d - 1) share the batch entries; the last x-row does the root.  For a node X at depth d
 // the reference applies, level by level, first the diffs of batch entries whose leaf is fewer parent steps
 // away (the shallower leaves of a non-power-of-two tree), then the deeper ones, each group in batch order
 // (redis_memory.py:94-105).  The first batch entry that touches X replays exactly that sequence of float64
@@ -236,9 +284,13 @@ __global__ void update_propagate_kernel(int n, int max_depth, double* __restrict
   double* sd = reinterpret_cast<double*>(node + n);
   int* steps = reinterpret_cast<int*>(sd + n);
   if ((int)blockIdx.x == max_depth) {  // root: tree[0] += np.sum(diffs)
+    if (blockIdx.y != 0) return;
     for (int j = threadIdx.x; j < n; j += blockDim.x) sd[j] = diff[j];
     __syncthreads();
-    if (threadIdx.x == 0) tree[0] = tree[0] + (0.0 + np_pairwise_sum(sd, n));
+    __shared__ int p_lo[66], p_ll[66], p_nb;
+    __shared__ double p_racc[66 * 8], p_bsum[66];
+    const double tot = np_pairwise_sum_cta(sd, n, p_lo, p_ll, p_racc, p_bsum, &p_nb);
+    if (threadIdx.x == 0) tree[0] = tree[0] + (0.0 + tot);
     return;
   }
   const int d = blockIdx.x + 1;
@@ -251,22 +303,29 @@ __global__ void update_propagate_kernel(int n, int max_depth, double* __restrict
     sd[j] = diff[j];
   }
   __syncthreads();
-  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+  // the batch entries of one depth are shared out over gridDim.y CTAs (each still sees all n entries)
+  for (int j = blockIdx.y * blockDim.x + threadIdx.x; j < n; j += gridDim.y * blockDim.x) {
     const int64_t me = node[j];
     if (me <= 0) continue;
-    bool leader = true;
-    int smin = steps[j], smax = steps[j];
+    // branch-free scans (all lanes of a warp walk the same k): first occurrence of my node and the range of steps
+    int first = n, smin = steps[j], smax = steps[j];
+#pragma unroll 4
     for (int k = 0; k < n; ++k) {
-      if (node[k] != me) continue;
-      if (k < j) { leader = false; break; }
-      smin = min(smin, steps[k]);
-      smax = max(smax, steps[k]);
+      const bool hit = node[k] == me;
+      const int st = steps[k];
+      first = min(first, hit ? k : n);
+      smin = hit ? min(smin, st) : smin;
+      smax = hit ? max(smax, st) : smax;
     }
-    if (!leader) continue;
+    if (first != j) continue;                       // another (earlier) batch entry owns this node
     double acc = tree[me];
-    for (int s = smin; s <= smax; ++s)
-      for (int k = j; k < n; ++k)
-        if (node[k] == me && steps[k] == s) acc += sd[k];
+    for (int s = smin; s <= smax; ++s) {
+#pragma unroll 4
+      for (int k = j; k < n; ++k) {
+        const double dk = sd[k];
+        if (node[k] == me && steps[k] == s) acc += dk;
+      }
+    }
     tree[me] = acc;
   }
 }
@@ -396,7 +455,9 @@ RIQN_API int riqn_sumtree_update(int n, long capacity, double* tree, const long 
     RIQN_CUDA(cudaFuncSetAttribute(update_propagate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     attr = true;
   }
-  update_propagate_kernel<<<max_depth + 1, 512, smem, s>>>(n, max_depth, tree, (const int64_t*)tree_idx, diff_scratch);
+  const int slices = (n + 127) / 128 < 8 ? (n + 127) / 128 : 8;
+  update_propagate_kernel<<<dim3(max_depth + 1, slices), 128, smem, s>>>(n, max_depth, tree, (const int64_t*)tree_idx,
+                                                                        diff_scratch);
   return (int)cudaGetLastError();
 }
 

@@ -67,3 +67,32 @@ def test_tc_gemm_splitk_atomic(cuda_dev, split3):
 def test_tc_gemm_many_tiles_persistent(cuda_dev):
     _run(cuda_dev, 4096, 2048, 1024, False, seed=6)           # 256 tiles > 148 SMs: accumulator ring wraps
     _run(cuda_dev, 8192, 1024, 512, True, epi=1, seed=7)
+
+
+def _run_mn(dev, M, N, K, epi=0, split_k=1, alpha=1.0, seed=0):
+    """C (+)= alpha * A^T B with A (K, M), B (K, N) row-major bf16 -- the MN-major operand mode."""
+    from rainbow_iqn_apex_b200._lib import call, ptr
+    rs = np.random.RandomState(seed)
+    A = _bf16_round(rs.standard_normal((K, M)).astype(np.float32))
+    B = _bf16_round((rs.standard_normal((K, N)) * 0.05).astype(np.float32))
+    a = torch.from_numpy(A).to(dev).to(torch.bfloat16)
+    b = torch.from_numpy(B).to(dev).to(torch.bfloat16)
+    c0 = rs.standard_normal((M, N)).astype(np.float32) if epi else np.zeros((M, N), np.float32)
+    c = torch.from_numpy(c0).to(dev)
+    eps = torch.from_numpy(rs.standard_normal((M, N)).astype(np.float32)).to(dev)
+    c2 = torch.zeros(M, N, device=dev)
+    call("riqn_gemm_bf16_tc_mn", M, N, K, ptr(a), ptr(b), ptr(c), N, epi, ptr(c2), ptr(eps), alpha, split_k)
+    torch.cuda.synchronize()
+    prod = A.astype(np.float64).T @ B.astype(np.float64)
+    ref = prod if epi == 0 else c0 + alpha * prod
+    assert rel_err(c.cpu().numpy(), ref) < 1e-5, (M, N, K, epi, split_k, rel_err(c.cpu().numpy(), ref))
+    if epi == 3:
+        assert rel_err(c2.cpu().numpy(), alpha * prod * eps.cpu().numpy().astype(np.float64)) < 1e-5
+
+
+def test_tc_gemm_mn_major(cuda_dev):
+    _run_mn(cuda_dev, 128, 256, 64)                                   # one tile, one k-block
+    _run_mn(cuda_dev, 128, 256, 512, seed=1)
+    _run_mn(cuda_dev, 64, 64, 200, seed=2)                            # narrow tile, ragged reduction
+    _run_mn(cuda_dev, 1024, 3136, 4096, epi=3, split_k=4, seed=3)     # NoisyLinear weight gradient shape
+    _run_mn(cuda_dev, 32, 576, 2000, epi=2, split_k=5, alpha=0.5, seed=4)   # conv weight gradient shape (Cout x K)

@@ -14,7 +14,7 @@ for r in rows:
     name = r[ki].split('(')[0].replace('void ', '')
     agg[name][0] += 1
     agg[name][1] += v
-nsteps = max(agg["adam_kernel"][0], 1)
+nsteps = max(agg["adam_kernel"][0], agg["riqn::adam_kernel"][0], 1)
 tot = sum(v[1] for v in agg.values())
 print(f"# {len(rows)} launches, {nsteps} learner steps (adam_kernel count); cold-cache serialised times: compare SHARES")
 print(f"# {'kernel':30s} {'launches/step':>13s} {'us/step':>10s} {'share':>7s}")
