@@ -197,10 +197,11 @@ int riqn_quantile_embed_fwd_tc(int batch, int num_quantiles, int embed_dim, int 
                                const float* feat, const void* iqn_w_hi, const void* iqn_w_lo, const float* iqn_b,
                                void* cos_hi, void* cos_lo, void* cos_t_hi, float* x32, void* x_hi, void* x_lo, void* x_hi_t,
                                void* x_lo_t, void* stream);
-/* Backward on bf16 operands (rows % 8 == 0): dx fp32 (rows, feat_dim) from the head dgrad; dpre_t (feat_dim, rows)
- * bf16 workspace; dfeat overwritten; grad_iqn_w / grad_iqn_b accumulated. */
+/* Backward on bf16 operands (rows % 8 == 0): dx fp32 (rows, feat_dim) from the head dgrad; cos_hi (rows, embed_dim)
+ * bf16 row-major (the forward's image); dpre (rows, feat_dim) bf16 workspace; dfeat overwritten; grad_iqn_w /
+ * grad_iqn_b accumulated. */
 int riqn_quantile_embed_bwd_tc(int batch, int num_quantiles, int embed_dim, int feat_dim, const void* x_hi, const void* x_lo,
-                               const float* feat, const void* cos_t_hi, const float* dx, void* dpre_t, float* dfeat,
+                               const float* feat, const void* cos_hi, const float* dx, void* dpre, float* dfeat,
                                float* grad_iqn_w, float* grad_iqn_b, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
@@ -211,20 +212,22 @@ int riqn_quantile_embed_bwd_tc(int batch, int num_quantiles, int embed_dim, int 
 int riqn_dueling_fwd(long rows, int batch, int hidden, int action_space, const float* h, const float* wz,
                      const float* bz, float* q, void* stream);
 /* Backward for the gathered action: dq[r, actions[b]] = dtheta[r] * gscale[b].  Writes dh (rows, 2*hidden),
- * already masked by h > 0, and dz (rows, 32) = [dv, da_0.., 0..] for riqn_z_wgrad; dz_t_bf16 (may be NULL) is the
- * bf16 transposed (32, rows) image for riqn_z_wgrad_tc. */
+ * already masked by h > 0, and dz (rows, 32) = [dv, da_0.., 0..] for riqn_z_wgrad; dz_bf16 (may be NULL) is its bf16
+ * image (rows, 32) for riqn_z_wgrad_tc. */
 int riqn_dueling_bwd(long rows, int batch, int hidden, int action_space, const float* h, const float* wz,
                      const float* dtheta, const float* gscale, const long long* actions, float* dh, float* dz,
-                     void* dz_t_bf16, void* stream);
+                     void* dz_bf16, void* stream);
 /* Same backward for bf16 tensor-core consumers (rows % 8 == 0): instead of the fp32 dh it writes dh_hi (rows, 2*hidden)
- * and its transpose dh_hi_t (2*hidden, rows) as bf16, and dh_colsum (2*hidden) = the fp32 column sums of dh (zeroed
- * here; pass it to riqn_noisy_bias_grad with dh == NULL). */
+ * as bf16 (and its transpose dh_hi_t (2*hidden, rows) if non-NULL), dh_colsum (2*hidden) = the fp32 column sums of dh
+ * (zeroed here; pass it to riqn_noisy_bias_grad with dh == NULL) and dz_bf16 (rows, 32), if non-NULL, the bf16 image of
+ * dz for riqn_z_wgrad_tc. */
 int riqn_dueling_bwd_bf16(long rows, int batch, int hidden, int action_space, const float* h, const float* wz,
                           const float* dtheta, const float* gscale, const long long* actions, void* dh_hi, void* dh_hi_t,
-                          float* dh_colsum, float* dz, void* dz_t_bf16, void* stream);
+                          float* dh_colsum, float* dz, void* dz_bf16, void* stream);
 /* Parameter gradients of the two z-layers (accumulated): dwz_scratch 32*2*hidden floats, dbz_scratch 32. */
-/* Same with the reduction dz^T h on the tensor cores: dz_t (32, rows) and h_t (2*hidden, rows) bf16 (rows % 8 == 0). */
-int riqn_z_wgrad_tc(long rows, int hidden, int action_space, const void* dz_t, const void* h_t, const float* dz,
+/* Same with the reduction dz^T h on the tensor cores, straight from the row-major bf16 images dz_bf16 (rows, 32) and
+ * h_bf16 (rows, 2*hidden) (rows % 8 == 0). */
+int riqn_z_wgrad_tc(long rows, int hidden, int action_space, const void* dz_bf16, const void* h_bf16, const float* dz,
                     float* dwz_scratch, float* dbz_scratch, const float* eps_w_zv, const float* eps_b_zv,
                     const float* eps_w_za, const float* eps_b_za, float* g_mu_zv, float* g_sig_zv, float* g_bmu_zv,
                     float* g_bsig_zv, float* g_mu_za, float* g_sig_za, float* g_bmu_za, float* g_bsig_za, void* stream);
@@ -337,10 +340,10 @@ int riqn_split_bf16(long rows, int cols, const float* src, void* hi, void* lo, v
 /* C (+)= A B^T with A (M,K), B (N,K) row-major bf16, K % 8 == 0, fp32 accumulation in TMEM.  a_lo/b_lo non-NULL
  * selects the split-bf16 x3 (fp32-faithful) product.  epilogue: 0 store, 1 relu(acc+bias[n]), 2 atomicAdd into C,
  * 3 atomicAdd into C and acc*eps[m,n] into out2 (NoisyLinear dmu / dsigma).  split_k > 1 needs 2 or 3.
- * c_t_bf16 (may be NULL; epilogue 1 only): bf16 transposed (N, M) image of the result. */
+ * c_t_bf16 / c_bf16 (may be NULL; epilogue 1 only): bf16 transposed (N, M) / row-major (M, N) images of the result. */
 int riqn_gemm_bf16_tc(int M, int N, int K, const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo,
                       float* c, long ldc, int epilogue, const float* bias, float* out2, const float* eps, int split_k,
-                      void* c_t_bf16, void* stream);
+                      void* c_t_bf16, void* c_bf16, void* stream);
 /* C (+)= A^T B with A (K, M) and B (K, N) row-major bf16 (M % 8 == 0, N % 8 == 0): the reduction runs over the ROWS, so
  * a weight gradient dW = dY^T X is taken straight from the row-major activations (MN-major tcgen05 operands, no
  * transposed copies).  epilogue 0 / 2 / 3 as above (2, 3 scale the accumulator by alpha); single-bf16 product. */

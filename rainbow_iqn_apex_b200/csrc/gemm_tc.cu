@@ -564,6 +564,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
               }
               if (p.o_hiT) store_transposed_pairs(p.o_hiT, hw, n0, m, p.M, lane, m < p.M);
               warp_store_rows_f32(st, v, lane, p.C + (long)m_base * p.ldc + n0, p.ldc, rows_valid);
+              if (p.o_hi) {                                     // bf16 row-major image (M, N): 64-byte row pieces
+                uint32_t hw2[32];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { hw2[j] = hw[j]; hw2[16 + j] = 0u; }
+                warp_store_rows_bf16(st, hw2, lane, p.o_hi + (long)m_base * p.N + n0, nullptr, p.N, rows_valid);
+              }
             } else {
               // x = feat[b] * relu(acc + bias)   (model.py:146-151); N % 32 == 0 is required by the host wrapper
               const bool row_ok = m < p.M;
@@ -843,10 +849,12 @@ RIQN_API int riqn_split_bf16(long rows, int cols, const float* src, void* hi, vo
 
 RIQN_API int riqn_gemm_bf16_tc(int M, int N, int K, const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo,
                                float* c, long ldc, int epilogue, const float* bias, float* out2, const float* eps,
-                               int split_k, void* c_t_bf16, void* stream) {
+                               int split_k, void* c_t_bf16, void* c_bf16, void* stream) {
   riqn::note_launches(1);
   TcExtra ex;
   ex.o_hiT = (bf16*)c_t_bf16;
+  ex.o_hi = (bf16*)c_bf16;
+  if (c_bf16 && (epilogue != TC_BIAS_RELU || (M & 1) || (N % 32))) return (int)cudaErrorInvalidValue;
   return gemm_bf16_tc(M, N, K, (const bf16*)a_hi, (const bf16*)a_lo, (const bf16*)b_hi, (const bf16*)b_lo, c, ldc, epilogue,
                       bias, out2, eps, split_k, (cudaStream_t)stream, &ex);
 }

@@ -74,46 +74,31 @@ __global__ void cos_embed_bf16_kernel(int B, int Nq, int E, const float* __restr
   if (hiT) hiT[(long)(i - 1) * R + r] = h;
 }
 
-// Backward through x = feat[b] (.) phi[r] on bf16 operand images, tile-transposing on the way:
-//   x = x_hi (+ x_lo);  dpre = dX * feat * 1{x>0}  -> dpreT (F, R) bf16 (K-major operand of the dW_e product)
+// Backward through x = feat[b] (.) phi[r] on bf16 operand images:
+//   x = x_hi (+ x_lo);  dpre = dX * feat * 1{x>0}  -> dpre (R, F) bf16 row-major (MN-major operand of the dW_e product)
 //   dfeat[b,f] = (sum_q dX * x) / feat ;  dbe[f] += sum_r dpre
-// Rows are sample-major, so one block = one sample x 32 features walks that sample's Nq contiguous rows in groups
-// of 32 and writes each transposed group as full 64-byte segments.
+// Rows are sample-major, so one block = one sample x 32 features walks that sample's Nq contiguous rows.
 __global__ void embed_bwd_tile_kernel(int B, int Nq, int F, const __nv_bfloat16* __restrict__ x_hi,
                                       const __nv_bfloat16* __restrict__ x_lo, const float* __restrict__ feat,
-                                      const float* __restrict__ dX, __nv_bfloat16* __restrict__ dpreT,
+                                      const float* __restrict__ dX, __nv_bfloat16* __restrict__ dpre,
                                       float* __restrict__ dfeat, float* __restrict__ dbe) {
-  __shared__ float tile[32][33];
   __shared__ float red[2][8][32];
   const int f0 = blockIdx.x * 32, b = blockIdx.y;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
-  const long R = (long)B * Nq;
   const int f = f0 + tx;
   const float ft = f < F ? feat[(long)b * F + f] : 0.f;
   float facc = 0.f, bacc = 0.f;
-  for (int q0 = 0; q0 < Nq; q0 += 32) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int q = q0 + ty + 8 * i;
-      float dp = 0.f;
-      if (q < Nq && f < F) {
-        const long o = ((long)b * Nq + q) * F + f;
-        float x = __bfloat162float(x_hi[o]);
-        if (x_lo) x += __bfloat162float(x_lo[o]);
-        const float dx = dX[o];
-        facc = fmaf(dx, x, facc);
-        dp = x > 0.f ? dx * ft : 0.f;
-        bacc += dp;
-      }
-      tile[ty + 8 * i][tx] = dp;
+  for (int q = ty; q < Nq; q += 8) {
+    if (f < F) {
+      const long o = ((long)b * Nq + q) * F + f;
+      float x = __bfloat162float(x_hi[o]);
+      if (x_lo) x += __bfloat162float(x_lo[o]);
+      const float dx = dX[o];
+      facc = fmaf(dx, x, facc);
+      const float dp = x > 0.f ? dx * ft : 0.f;
+      bacc += dp;
+      dpre[o] = __float2bfloat16_rn(dp);
     }
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int ff = f0 + ty + 8 * i, q = q0 + tx;
-      if (ff < F && q < Nq) dpreT[(long)ff * R + (long)b * Nq + q] = __float2bfloat16_rn(tile[tx][ty + 8 * i]);
-    }
-    __syncthreads();
   }
   red[0][ty][tx] = facc;
   red[1][ty][tx] = bacc;
@@ -128,14 +113,13 @@ __global__ void embed_bwd_tile_kernel(int B, int Nq, int F, const __nv_bfloat16*
 }
 
 // Wide variant (Nq even): one block = one sample x 128 features; lane owns 4 consecutive features (16-byte dX loads,
-// 8-byte x loads), warp w owns rows q = w, w+8, ... so that all of a thread's loads are in flight together.  dpre goes
-// through an XOR-swizzled shared tile as (q, q+1) bf16 pairs and leaves as full 128-byte rows of dpreT.
+// 8-byte x loads, 8-byte dpre stores), warp w owns rows q = 2w, 2w+1, 2w+16, ... so that all of a thread's loads are in
+// flight together.
 __global__ void __launch_bounds__(256) embed_bwd_wide_kernel(int B, int Nq, int F, const __nv_bfloat16* __restrict__ x_hi,
                                                              const __nv_bfloat16* __restrict__ x_lo,
                                                              const float* __restrict__ feat, const float* __restrict__ dX,
-                                                             __nv_bfloat16* __restrict__ dpreT, float* __restrict__ dfeat,
+                                                             __nv_bfloat16* __restrict__ dpre, float* __restrict__ dfeat,
                                                              float* __restrict__ dbe) {
-  __shared__ uint32_t tile[128][32];      // [feature][pair of rows], column index XOR-ed with (feature >> 2) & 31
   __shared__ float red[2][8][128];
   const int f0 = blockIdx.x * 128, b = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -162,39 +146,28 @@ __global__ void __launch_bounds__(256) embed_bwd_wide_kernel(int B, int Nq, int 
         if (x_lo) xl[i] = __ldg(reinterpret_cast<const uint2*>(x_lo + o));
       }
     }
-    uint32_t pk[4][4];                                   // [pair][feature]
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
+      const int q = q0 + 2 * (warp + 8 * (i >> 1)) + (i & 1);
       const float x[4] = {__uint_as_float(xh[i].x << 16) + __uint_as_float(xl[i].x << 16),
                           __uint_as_float(xh[i].x & 0xffff0000u) + __uint_as_float(xl[i].x & 0xffff0000u),
                           __uint_as_float(xh[i].y << 16) + __uint_as_float(xl[i].y << 16),
                           __uint_as_float(xh[i].y & 0xffff0000u) + __uint_as_float(xl[i].y & 0xffff0000u)};
       const float d[4] = {dx[i].x, dx[i].y, dx[i].z, dx[i].w};
       const float fv[4] = {ft.x, ft.y, ft.z, ft.w};
+      float dp[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         facc[j] = fmaf(d[j], x[j], facc[j]);
-        const float dp = x[j] > 0.f ? d[j] * fv[j] : 0.f;
-        bacc[j] += dp;
-        const uint32_t hb = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(dp));
-        if (i & 1) pk[i >> 1][j] |= hb << 16; else pk[i >> 1][j] = hb;
+        dp[j] = x[j] > 0.f ? d[j] * fv[j] : 0.f;
+        bacc[j] += dp[j];
+      }
+      if (q < Nq && f_ok) {                                  // dpre (R, F) row-major: 8 bytes per lane, 256 per warp
+        const __nv_bfloat162 p01 = __floats2bfloat162_rn(dp[0], dp[1]), p23 = __floats2bfloat162_rn(dp[2], dp[3]);
+        *reinterpret_cast<uint2*>(dpre + ((long)b * Nq + q) * F + f) =
+            make_uint2(*reinterpret_cast<const uint32_t*>(&p01), *reinterpret_cast<const uint32_t*>(&p23));
       }
     }
-#pragma unroll
-    for (int pr = 0; pr < 4; ++pr) {
-      const int col = warp + 8 * pr;                     // pair index within the 64-row pass
-#pragma unroll
-      for (int j = 0; j < 4; ++j) tile[fl + j][col ^ lane] = pk[pr][j];      // ((fl + j) >> 2) & 31 == lane
-    }
-    __syncthreads();
-    // feature row ff: 32 lanes x one (q, q+1) pair = 128 contiguous bytes of dpreT
-#pragma unroll 4
-    for (int ff = warp; ff < 128; ff += 8) {
-      const int q = q0 + 2 * lane;
-      if (f0 + ff < F && q < Nq)
-        *reinterpret_cast<uint32_t*>(dpreT + (long)(f0 + ff) * R + (long)b * Nq + q) = tile[ff][lane ^ ((ff >> 2) & 31)];
-    }
-    __syncthreads();
   }
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -511,7 +484,7 @@ template <int HID>
 __global__ void z_dueling_bwd_kernel(long R, int B, int A, const float* __restrict__ H, const float* __restrict__ Wz,
                                      const float* __restrict__ dtheta, const float* __restrict__ gscale,
                                      const int64_t* __restrict__ actions, float* __restrict__ dH,
-                                     float* __restrict__ dz, __nv_bfloat16* __restrict__ dzT) {
+                                     float* __restrict__ dz, __nv_bfloat16* __restrict__ dz_bf) {
   extern __shared__ float sW[];  // (1+A)*HID weights + HID colmean
   float* wbar = sW + (1 + A) * HID;
   for (int i = threadIdx.x; i < (1 + A) * HID; i += blockDim.x) sW[i] = Wz[i];
@@ -539,7 +512,7 @@ __global__ void z_dueling_bwd_kernel(long R, int B, int A, const float* __restri
     if (lane == 0) z = g;
     else if (lane <= A) z = g * ((lane - 1 == act ? 1.f : 0.f) - 1.f / (float)A);
     dz[r * 32 + lane] = z;
-    if (dzT) dzT[(long)lane * R + r] = __float2bfloat16_rn(z);
+    if (dz_bf) dz_bf[r * 32 + lane] = __float2bfloat16_rn(z);
   }
 }
 
@@ -556,7 +529,7 @@ __global__ void __launch_bounds__(256) z_dueling_bwd_bf16_kernel(long R, int B, 
                                                                  __nv_bfloat16* __restrict__ dh_hi,
                                                                  __nv_bfloat16* __restrict__ dh_hiT,
                                                                  float* __restrict__ colsum, float* __restrict__ dz,
-                                                                 __nv_bfloat16* __restrict__ dzT) {
+                                                                 __nv_bfloat16* __restrict__ dz_bf) {
   extern __shared__ __align__(16) float sW[];          // (1+A)*HID weights | HID colmean | 2*HID column sums | tile
   float* wbar = sW + (1 + A) * HID;
   float* cs = wbar + HID;
@@ -617,16 +590,17 @@ __global__ void __launch_bounds__(256) z_dueling_bwd_bf16_kernel(long R, int B, 
       }
       const uint4 pk = make_uint4(w[0], w[1], w[2], w[3]);
       if (ok) *reinterpret_cast<uint4*>(dh_hi + r * (2 * HID) + c0) = pk;
-      tile[rl * 128 + (chunk ^ ((rl >> 3) & 3))] = pk;
+      if (dh_hiT) tile[rl * 128 + (chunk ^ ((rl >> 3) & 3))] = pk;
     }
     if (ok) {
       float z = 0.f;
       if (lane == 0) z = g;
       else if (lane <= A) z = g * ((lane - 1 == act ? 1.f : 0.f) - 1.f / (float)A);
       dz[r * 32 + lane] = z;
-      if (dzT) dzT[(long)lane * R + r] = __float2bfloat16_rn(z);
+      if (dz_bf) dz_bf[r * 32 + lane] = __float2bfloat16_rn(z);     // (R, 32) row-major: MN-major operand of dWz
     }
   }
+  if (dh_hiT == nullptr) continue;                               // (warp-uniform) no transposed image wanted
   __syncthreads();
   // transposed image: item = (column c, piece p of 8 rows); a warp covers 8 columns x 4 pieces = 8 x 64 contiguous bytes
   const unsigned short* t16 = reinterpret_cast<const unsigned short*>(tile);
@@ -846,29 +820,31 @@ RIQN_API int riqn_quantile_embed_fwd_tc(int batch, int num_quantiles, int embed_
 }
 
 // Backward on bf16 operands: dx (fp32, from the head dgrad) -> dfeat (overwritten), grad_iqn_b / grad_iqn_w accumulated.
-// dpreT (feat_dim, rows) bf16 is workspace.  rows % 8 == 0.
+// cos_hi (rows, embed_dim) bf16 row-major (the forward's image); dpre (rows, feat_dim) bf16 is workspace.  rows % 8 == 0.
 RIQN_API int riqn_quantile_embed_bwd_tc(int batch, int num_quantiles, int embed_dim, int feat_dim, const void* x_hi,
-                                        const void* x_lo, const float* feat, const void* cosT_hi, const float* dx,
-                                        void* dpreT, float* dfeat, float* grad_iqn_w, float* grad_iqn_b, void* stream) {
+                                        const void* x_lo, const float* feat, const void* cos_hi, const float* dx,
+                                        void* dpre, float* dfeat, float* grad_iqn_w, float* grad_iqn_b, void* stream) {
   riqn::note_launches(2);
   cudaStream_t s = (cudaStream_t)stream;
   const long R = (long)batch * num_quantiles;
-  if (R % 8) return (int)cudaErrorInvalidValue;
+  if (R % 8 || feat_dim % 8 || embed_dim % 8) return (int)cudaErrorInvalidValue;
   if (num_quantiles % 2 == 0 && feat_dim % 4 == 0) {
     dim3 grid((feat_dim + 127) / 128, batch);
     embed_bwd_wide_kernel<<<grid, 256, 0, s>>>(batch, num_quantiles, feat_dim, (const __nv_bfloat16*)x_hi,
-                                               (const __nv_bfloat16*)x_lo, feat, dx, (__nv_bfloat16*)dpreT, dfeat, grad_iqn_b);
+                                               (const __nv_bfloat16*)x_lo, feat, dx, (__nv_bfloat16*)dpre, dfeat, grad_iqn_b);
   } else {
     dim3 grid((feat_dim + 31) / 32, batch);
     embed_bwd_tile_kernel<<<grid, 256, 0, s>>>(batch, num_quantiles, feat_dim, (const __nv_bfloat16*)x_hi,
-                                               (const __nv_bfloat16*)x_lo, feat, dx, (__nv_bfloat16*)dpreT, dfeat, grad_iqn_b);
+                                               (const __nv_bfloat16*)x_lo, feat, dx, (__nv_bfloat16*)dpre, dfeat, grad_iqn_b);
   }
   RIQN_LAUNCH_CHECK();
   const int m_tiles = (feat_dim + 127) / 128;
   const int split = (148 + m_tiles - 1) / m_tiles;
-  // dWe[f, i] += sum_r dpre[r, f] * cos[r, i]
-  return gemm_bf16_tc(feat_dim, embed_dim, (int)R, (const __nv_bfloat16*)dpreT, nullptr, (const __nv_bfloat16*)cosT_hi, nullptr,
-                      grad_iqn_w, embed_dim, TC_ATOMIC, nullptr, nullptr, nullptr, split, s, nullptr);
+  // dWe[f, i] += sum_r dpre[r, f] * cos[r, i]: both operands row-major, reduction over the rows (MN-major operands)
+  TcExtra ex;
+  ex.mn_major = 1;
+  return gemm_bf16_tc(feat_dim, embed_dim, (int)R, (const __nv_bfloat16*)dpre, nullptr, (const __nv_bfloat16*)cos_hi, nullptr,
+                      grad_iqn_w, embed_dim, TC_ATOMIC, nullptr, nullptr, nullptr, split, s, &ex);
 }
 
 RIQN_API int riqn_quantile_embed_bwd(int batch, int num_quantiles, int embed_dim, int feat_dim, const float* x,
@@ -967,7 +943,7 @@ RIQN_API int riqn_dueling_fwd(long rows, int batch, int hidden, int action_space
 
 RIQN_API int riqn_dueling_bwd(long rows, int batch, int hidden, int action_space, const float* h, const float* wz,
                               const float* dtheta, const float* gscale, const long long* actions, float* dh, float* dz,
-                              void* dz_t_bf16, void* stream) {
+                              void* dz_bf16, void* stream) {
   riqn::note_launches(1);
   if (hidden != 512 || action_space > 31) return (int)cudaErrorInvalidValue;
   const size_t smem = sizeof(float) * ((1 + action_space) * hidden + hidden);
@@ -977,13 +953,13 @@ RIQN_API int riqn_dueling_bwd(long rows, int batch, int hidden, int action_space
     attr = true;
   }
   z_dueling_bwd_kernel<512><<<148 * 4, 256, smem, (cudaStream_t)stream>>>(rows, batch, action_space, h, wz, dtheta, gscale,
-                                                                       (const int64_t*)actions, dh, dz, (__nv_bfloat16*)dz_t_bf16);
+                                                                       (const int64_t*)actions, dh, dz, (__nv_bfloat16*)dz_bf16);
   return (int)cudaGetLastError();
 }
 
 RIQN_API int riqn_dueling_bwd_bf16(long rows, int batch, int hidden, int action_space, const float* h, const float* wz,
                                    const float* dtheta, const float* gscale, const long long* actions, void* dh_hi,
-                                   void* dh_hi_t, float* dh_colsum, float* dz, void* dz_t_bf16, void* stream) {
+                                   void* dh_hi_t, float* dh_colsum, float* dz, void* dz_bf16, void* stream) {
   riqn::note_launches(1);
   if (hidden != 512 || action_space > 31 || rows % 8) return (int)cudaErrorInvalidValue;
   cudaStream_t s = (cudaStream_t)stream;
@@ -997,7 +973,7 @@ RIQN_API int riqn_dueling_bwd_bf16(long rows, int batch, int hidden, int action_
   const long n_blk = (rows + 31) / 32;
   z_dueling_bwd_bf16_kernel<512><<<(unsigned)(n_blk < 148 * 2 ? n_blk : 148 * 2), 256, smem, s>>>(
       rows, batch, action_space, h, wz, dtheta, gscale, (const int64_t*)actions, (__nv_bfloat16*)dh_hi,
-      (__nv_bfloat16*)dh_hi_t, dh_colsum, dz, (__nv_bfloat16*)dz_t_bf16);
+      (__nv_bfloat16*)dh_hi_t, dh_colsum, dz, (__nv_bfloat16*)dz_bf16);
   return (int)cudaGetLastError();
 }
 
@@ -1023,7 +999,7 @@ RIQN_API int riqn_z_wgrad(long rows, int hidden, int action_space, const float* 
   return (int)cudaGetLastError();
 }
 
-RIQN_API int riqn_z_wgrad_tc(long rows, int hidden, int action_space, const void* dz_t, const void* h_t, const float* dz,
+RIQN_API int riqn_z_wgrad_tc(long rows, int hidden, int action_space, const void* dz_bf16, const void* h_bf16, const float* dz,
                              float* dwz_scratch, float* dbz_scratch, const float* eps_w_zv, const float* eps_b_zv,
                              const float* eps_w_za, const float* eps_b_za, float* g_mu_zv, float* g_sig_zv, float* g_bmu_zv,
                              float* g_bsig_zv, float* g_mu_za, float* g_sig_za, float* g_bmu_za, float* g_bsig_za,
@@ -1036,9 +1012,11 @@ RIQN_API int riqn_z_wgrad_tc(long rows, int hidden, int action_space, const void
   RIQN_CUDA(cudaMemsetAsync(dbz_scratch, 0, sizeof(float) * 32, s));
   const int n_tiles = (W + 255) / 256;
   const int split = (148 + n_tiles - 1) / n_tiles;
-  // dWz[z, j] = sum_r dz[r, z] * h[r, j]
-  int rc = gemm_bf16_tc(32, W, (int)rows, (const __nv_bfloat16*)dz_t, nullptr, (const __nv_bfloat16*)h_t, nullptr, dwz_scratch, W,
-                        TC_ATOMIC, nullptr, nullptr, nullptr, split, s, nullptr);
+  // dWz[z, j] = sum_r dz[r, z] * h[r, j]: both operands row-major, reduction over the rows (MN-major operands)
+  TcExtra ex;
+  ex.mn_major = 1;
+  int rc = gemm_bf16_tc(32, W, (int)rows, (const __nv_bfloat16*)dz_bf16, nullptr, (const __nv_bfloat16*)h_bf16, nullptr,
+                        dwz_scratch, W, TC_ATOMIC, nullptr, nullptr, nullptr, split, s, &ex);
   if (rc) return rc;
   rc = colsum_atomic(rows, 32, dz, dbz_scratch, s);
   if (rc) return rc;

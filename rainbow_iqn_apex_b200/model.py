@@ -543,9 +543,12 @@ class DQN(nn.Module):
         else:
             x3 = fwd == "bf16x3"
             need_x32 = keep is not None and not emb_tc           # the fp32 CUDA-core embedding backward reads x
+            # bwd == "bf16": the weight-gradient products read the row-major images (MN-major operands): no transposes
+            mn = bwd_tc and bwd == "bf16"
             tc = dict(x_hi=bf(R, FEAT), x_lo=bf(R, FEAT) if x3 else None,
-                      x_hiT=bf(FEAT, R) if bwd_tc else None, x_loT=bf(FEAT, R) if (bwd_tc and bwd == "bf16x3") else None,
-                      cos_hi=bf(R, E), cos_lo=bf(R, E) if x3 else None, cosT_hi=bf(E, R) if emb_tc else None)
+                      x_hiT=bf(FEAT, R) if (bwd_tc and not mn) else None,
+                      x_loT=bf(FEAT, R) if (bwd_tc and bwd == "bf16x3") else None,
+                      cos_hi=bf(R, E), cos_lo=bf(R, E) if x3 else None, cosT_hi=None, mn=mn)
             if need_x32:
                 xt = torch.empty(R, FEAT, device=dev)
                 cosv = torch.empty(R, E, device=dev)
@@ -555,9 +558,9 @@ class DQN(nn.Module):
             if need_x32:   # fp32 cos for the CUDA-core dW_e product
                 call("riqn_quantile_embed_fwd", B, num_quantiles, E, FEAT, ptr(tau), ptr(feat), ptr(self.iqn_fc.weight),
                      ptr(self.iqn_fc.bias), ptr(cosv), ptr(xt))
-            tc["hT"] = bf(2 * hid, R) if bwd_tc else None      # bf16 (1024, R) image of h for the z-layer weight gradient
+            tc["h_hi"] = bf(R, 2 * hid) if (bwd_tc and R % 2 == 0) else None   # bf16 image of h for the z-layer weight gradient
             call("riqn_gemm_bf16_tc", R, 2 * hid, FEAT, ptr(tc["x_hi"]), ptr(tc["x_lo"]), ptr(self._w_hi),
-                 ptr(self._w_lo) if x3 else None, ptr(h), 2 * hid, 1, ptr(self._b_eff_h), None, None, 1, ptr(tc["hT"]))
+                 ptr(self._w_lo) if x3 else None, ptr(h), 2 * hid, 1, ptr(self._b_eff_h), None, None, 1, None, ptr(tc["h_hi"]))
         q = torch.empty(R, A, device=dev)
         call("riqn_dueling_fwd", R, B, hid, A, ptr(h), ptr(self._w_eff_z), ptr(self._b_eff_z), ptr(q))
         if keep is not None:
@@ -593,17 +596,17 @@ class DQN(nn.Module):
         gv = self.grad_view
         dz = torch.empty(R, 32, device=dev)
         tc = keep.get("tc")
-        z_tc = bool(keep["head_bwd_tc"]) and tc is not None and tc.get("hT") is not None
-        dzT = torch.empty(32, R, dtype=torch.bfloat16, device=dev) if z_tc else None
+        z_tc = bool(keep["head_bwd_tc"]) and tc is not None and tc.get("h_hi") is not None
+        dzT = torch.empty(R, 32, dtype=torch.bfloat16, device=dev) if z_tc else None       # (R, 32) row-major bf16 image
         dbs = torch.empty(2 * hid, device=dev)
         # bf16 backward: dh leaves the dueling backward directly as the bf16 operand images (+ its column sums)
-        fused_dh = bool(keep["head_bwd_tc"]) and PRECISION["bwd"] == "bf16" and R % 8 == 0
+        fused_dh = bool(keep["head_bwd_tc"]) and PRECISION["bwd"] == "bf16" and R % 8 == 0 and bool(tc and tc.get("mn"))
         if fused_dh:
             dh = None
             dh_hi = torch.empty(R, 2 * hid, dtype=torch.bfloat16, device=dev)
-            dh_hiT = torch.empty(2 * hid, R, dtype=torch.bfloat16, device=dev)
+            dh_hiT = None                            # the wgrad reads dh_hi itself (MN-major operand)
             call("riqn_dueling_bwd_bf16", R, B, hid, A, ptr(keep["h"]), ptr(self._w_eff_z), ptr(dtheta), ptr(gscale),
-                 ptr(actions), ptr(dh_hi), ptr(dh_hiT), ptr(dbs), ptr(dz), ptr(dzT))
+                 ptr(actions), ptr(dh_hi), None, ptr(dbs), ptr(dz), ptr(dzT))
         else:
             dh = torch.empty(R, 2 * hid, device=dev)
             call("riqn_dueling_bwd", R, B, hid, A, ptr(keep["h"]), ptr(self._w_eff_z), ptr(dtheta), ptr(gscale),
@@ -615,7 +618,7 @@ class DQN(nn.Module):
                  ptr(gv(zv.bias_sigma)), ptr(gv(za.weight_mu)), ptr(gv(za.weight_sigma)), ptr(gv(za.bias_mu)),
                  ptr(gv(za.bias_sigma)))
         if z_tc:
-            call("riqn_z_wgrad_tc", R, hid, A, ptr(dzT), ptr(tc["hT"]), ptr(dz), *zargs)
+            call("riqn_z_wgrad_tc", R, hid, A, ptr(dzT), ptr(tc["h_hi"]), ptr(dz), *zargs)
         else:
             call("riqn_z_wgrad", R, hid, A, ptr(dz), ptr(keep["h"]), *zargs)
         dx = torch.empty(R, FEAT, device=dev)
@@ -634,19 +637,23 @@ class DQN(nn.Module):
                 dh_hi, dh_hiT = bf(R, 2 * hid), bf(2 * hid, R)
                 call("riqn_split_bf16", R, 2 * hid, ptr(dh), ptr(dh_hi), ptr(dh_lo), ptr(dh_hiT), ptr(dh_loT))
             # dW[o, i] = sum_r dh[r, o] x[r, i]  -> dmu += dW, dsigma += dW * eps   (split-K, atomics)
-            call("riqn_gemm_bf16_tc", 2 * hid, FEAT, R, ptr(dh_hiT), ptr(dh_loT), ptr(tc["x_hiT"]),
-                 ptr(tc["x_loT"]) if b3 else None, ptr(gv(hv.weight_mu)), FEAT, 3, None, ptr(gv(hv.weight_sigma)),
-                 ptr(hv.weight_epsilon), WGRAD_SPLIT_K, None)
+            if fused_dh:
+                call("riqn_gemm_bf16_tc_mn", 2 * hid, FEAT, R, ptr(dh_hi), ptr(tc["x_hi"]), ptr(gv(hv.weight_mu)), FEAT, 3,
+                     ptr(gv(hv.weight_sigma)), ptr(hv.weight_epsilon), 1.0, WGRAD_SPLIT_K)
+            else:
+                call("riqn_gemm_bf16_tc", 2 * hid, FEAT, R, ptr(dh_hiT), ptr(dh_loT), ptr(tc["x_hiT"]),
+                     ptr(tc["x_loT"]) if b3 else None, ptr(gv(hv.weight_mu)), FEAT, 3, None, ptr(gv(hv.weight_sigma)),
+                     ptr(hv.weight_epsilon), WGRAD_SPLIT_K, None, None)
             call("riqn_noisy_bias_grad", R, 2 * hid, ptr(dh) if dh is not None else None, ptr(hv.bias_epsilon), ptr(dbs),
                  ptr(gv(hv.bias_mu)), ptr(gv(hv.bias_sigma)))
             # dx[r, i] = sum_o dh[r, o] W_eff[o, i]
             call("riqn_gemm_bf16_tc", R, FEAT, 2 * hid, ptr(dh_hi), ptr(dh_lo), ptr(self._w_hiT),
-                 ptr(self._w_loT) if b3 else None, ptr(dx), FEAT, 0, None, None, None, 1, None)
+                 ptr(self._w_loT) if b3 else None, ptr(dx), FEAT, 0, None, None, None, 1, None, None)
         dfeat = torch.empty(B, FEAT, device=dev)
         if keep["emb_bwd_tc"]:
-            dpreT = torch.empty(FEAT, R, dtype=torch.bfloat16, device=dev)
+            dpre = torch.empty(R, FEAT, dtype=torch.bfloat16, device=dev)
             call("riqn_quantile_embed_bwd_tc", B, Nq, E, FEAT, ptr(tc["x_hi"]), ptr(tc["x_lo"]), ptr(keep["feat"]),
-                 ptr(tc["cosT_hi"]), ptr(dx), ptr(dpreT), ptr(dfeat), ptr(gv(self.iqn_fc.weight)), ptr(gv(self.iqn_fc.bias)))
+                 ptr(tc["cos_hi"]), ptr(dx), ptr(dpre), ptr(dfeat), ptr(gv(self.iqn_fc.weight)), ptr(gv(self.iqn_fc.bias)))
         else:
             call("riqn_quantile_embed_bwd", B, Nq, E, FEAT, ptr(keep["xt"]), ptr(keep["feat"]), ptr(keep["cos"]), ptr(dx),
                  ptr(dfeat), ptr(gv(self.iqn_fc.weight)), ptr(gv(self.iqn_fc.bias)))

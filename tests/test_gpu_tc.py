@@ -30,7 +30,7 @@ def _run(dev, M, N, K, split3, epi=0, split_k=1, seed=0):
     eps = torch.from_numpy(rs.standard_normal((M, N)).astype(np.float32)).to(dev)
     c2 = torch.zeros(M, N, device=dev)
     call("riqn_gemm_bf16_tc", M, N, K, ptr(a_hi), ptr(a_lo), ptr(b_hi), ptr(b_lo), ptr(c), N, epi, ptr(bias), ptr(c2),
-         ptr(eps), split_k, None)
+         ptr(eps), split_k, None, None)
     torch.cuda.synchronize()
     if split3:
         ref = A.astype(np.float64) @ B.astype(np.float64).T
