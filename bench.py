@@ -161,7 +161,7 @@ def run_ours(args):
     barrier()
     timed_names = ("riqn_gemm_bf16_tc", "riqn_gemm_bf16_tc_mn", "riqn_noisy_linear_fwd", "riqn_iqn_loss_fwd_bwd", "riqn_split_bf16",
                    "riqn_quantile_embed_fwd_tc", "riqn_quantile_embed_bwd_tc", "riqn_conv_fwd_tc", "riqn_conv_bwd_tc",
-                   "riqn_conv_fwd_tc_u8", "riqn_conv_fwd_strip", "riqn_s2d_u8", "riqn_im2col_bf16_t", "riqn_dueling_fwd", "riqn_dueling_bwd", "riqn_dueling_bwd_bf16", "riqn_z_wgrad",
+                   "riqn_conv_fwd_tc_u8", "riqn_conv_fwd_strip", "riqn_conv_bwd_strip", "riqn_s2d_u8", "riqn_im2col_bf16_t", "riqn_dueling_fwd", "riqn_dueling_bwd", "riqn_dueling_bwd_bf16", "riqn_z_wgrad",
                    "riqn_z_wgrad_tc", "riqn_noisy_bias_grad", "riqn_adam_step", "riqn_frame_gather", "riqn_sumtree_sample",
                    "riqn_sumtree_update", "riqn_sumtree_is_weights", "riqn_noisy_compose", "riqn_noisy_reset_net",
                    "riqn_argmax_mean")

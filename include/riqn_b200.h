@@ -95,6 +95,14 @@ int riqn_conv_fwd_strip(const riqn_conv_geom* g, const void* a_hi, const void* a
                         const float* bias, float* out, void* next_hi, void* next_lo, int next_stride, int next_grid,
                         void* stream);
 int riqn_im2col_bf16_t(const riqn_conv_geom* g, const void* in, int in_is_u8, void* colT_hi, void* stream);
+/* Backward of a strip convolution on the tensor cores, again without im2col matrices: a_hi is the block matrix the
+ * forward read (riqn_s2d_u8 / the previous layer's next_hi); wT_hi (K, Cout) bf16 in the ORIGINAL k order (data
+ * gradient); perm (K ints): strip k order -> original k; dYg (B*G*G, Cout) bf16 and dwp_scratch (Cout*K floats)
+ * workspaces; dw / dbias accumulated; din (may be NULL; pad == 0 only) overwritten.  wgrad_scale = 1/255 when a_hi
+ * holds raw pixel values. */
+int riqn_conv_bwd_strip(const riqn_conv_geom* g, const float* dout, const float* out, const void* a_hi, const void* wT_hi,
+                        const int* perm, void* dYg, float* dwp_scratch, float* dw, float* dbias, float* din,
+                        float wgrad_scale, void* stream);
 
 /* Backward on the tensor cores (bf16 operands, fp32 accumulate): wT_hi (K, Cout) bf16; dY_hi (M, Cout) and dYT_hi
  * (Cout, M) bf16 workspaces; dcol fp32 (M, K) workspace; dw/dbias accumulated; din may be NULL. */

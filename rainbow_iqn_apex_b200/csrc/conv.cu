@@ -649,6 +649,68 @@ RIQN_API int riqn_conv_fwd_tc_u8(const riqn_conv_geom* g, const unsigned char* i
                       TC_BIAS_RELU_NCHW, bias, nullptr, nullptr, 1, s, &ex);
 }
 
+// dY on the strip grid: row m' = (b, gy, gx) of dYg (B*G*G, Cout) bf16 holds dout * (out > 0) for real outputs
+// (gy < OH, gx < OW) and zeros elsewhere; dbias accumulated.  One block = 64 grid rows x all channels (Cout <= 64).
+__global__ void __launch_bounds__(256) conv_dy_grid_kernel(int B, int Cout, int OH, int OW, int G,
+                                                           const float* __restrict__ dout, const float* __restrict__ out,
+                                                           bf16* __restrict__ dYg, float* __restrict__ dbias) {
+  __shared__ __align__(16) unsigned short tile[64][66];
+  __shared__ float bsum[64];
+  const long Mg = (long)B * G * G;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, ohw = OH * OW, gg = G * G;
+  if (threadIdx.x < 64) bsum[threadIdx.x] = 0.f;
+  __syncthreads();
+  const long n_tiles = (Mg + 63) / 64;
+  for (long tix = blockIdx.x; tix < n_tiles; tix += gridDim.x) {
+    const long m0 = tix * 64;
+    long src0[2];
+    bool ok[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const long m = m0 + lane + 32 * h;
+      const long b = m / gg;
+      const int rem = (int)(m - b * gg), gy = rem / G, gx = rem - gy * G;
+      ok[h] = m < Mg && gy < OH && gx < OW;
+      src0[h] = ok[h] ? b * Cout * ohw + gy * OW + gx : 0;          // + c * ohw
+    }
+    for (int c = warp; c < Cout; c += 8) {
+      float acc = 0.f;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float v = 0.f;
+        if (ok[h]) {
+          const long src = src0[h] + (long)c * ohw;
+          v = out[src] > 0.f ? dout[src] : 0.f;
+        }
+        tile[lane + 32 * h][c] = __bfloat16_as_ushort(__float2bfloat16_rn(v));
+        acc += v;
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) bsum[c] += acc;
+    }
+    __syncthreads();
+    const int ppr = Cout >> 3;
+    for (int idx = threadIdx.x; idx < 64 * ppr; idx += blockDim.x) {
+      const int r = idx / ppr, pc = idx - r * ppr;
+      if (m0 + r < Mg) {
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(&tile[r][pc * 8]);
+        *reinterpret_cast<uint4*>(dYg + (m0 + r) * Cout + pc * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < Cout) atomicAdd(&dbias[threadIdx.x], bsum[threadIdx.x]);
+}
+
+// dw[c, perm[k']] += dwp[c, k']: the strip weight gradient back into the (Cout, Cin*KH*KW) parameter order
+__global__ void unpermute_add_kernel(int Cout, int K, const float* __restrict__ dwp, const int* __restrict__ perm,
+                                     float* __restrict__ dw) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Cout * K) return;
+  const int c = idx / K, kp = idx - c * K;
+  dw[(long)c * K + perm[kp]] += dwp[idx];
+}
+
 static int strip_params(const riqn_conv_geom* g, int* t, int* G, int* kc) {
   if (g->KH != g->KW || g->stride < 1 || g->KH % g->stride) return 1;
   *t = g->KH / g->stride;
@@ -688,6 +750,49 @@ RIQN_API int riqn_conv_fwd_strip(const riqn_conv_geom* g, const void* a_hi, cons
   ex.nx_hi = (bf16*)next_hi; ex.nx_lo = (bf16*)next_lo; ex.nx_s = next_stride; ex.nx_G = next_grid;
   return gemm_bf16_tc(g->B * G * G, g->Cout, g->Cin * g->KH * g->KW, (const bf16*)a_hi, (const bf16*)a_lo, (const bf16*)w_hi,
                       (const bf16*)w_lo, out, g->Cout, TC_CONV, bias, nullptr, nullptr, 1, (cudaStream_t)stream, &ex);
+}
+
+// Backward of a strip convolution (bf16 operands, fp32 accumulate) without im2col matrices or transposes:
+//   dYg (B*G*G, Cout) = dout * (out > 0) on the strip grid;   dbias += column sums
+//   dW'[c, (shift, within)] = sum_m' dYg[m', c] * a_hi[m' + shift offset, within]   (MN-major operands, shifted rows)
+//   dw[c, perm[k']] += wgrad_scale * dW'[c, k']
+//   din += col2im(dYg * W)   (fused epilogue, pad == 0 only; din may be NULL)
+RIQN_API int riqn_conv_bwd_strip(const riqn_conv_geom* g, const float* dout, const float* out, const void* a_hi,
+                                 const void* wT_hi, const int* perm, void* dYg, float* dwp_scratch, float* dw, float* dbias,
+                                 float* din, float wgrad_scale, void* stream) {
+  riqn::note_launches(din ? 6 : 4);
+  cudaStream_t s = (cudaStream_t)stream;
+  int t, G, kc;
+  if (strip_params(g, &t, &G, &kc) || g->Cout > 64 || g->Cout % 8 || (din && g->pad != 0)) return (int)cudaErrorInvalidValue;
+  const long Mg = (long)g->B * G * G;
+  const int K = g->Cin * g->KH * g->KW;
+  const long tiles = (Mg + 63) / 64;
+  conv_dy_grid_kernel<<<(unsigned)(tiles < 148 * 4 ? tiles : 148 * 4), 256, 0, s>>>(g->B, g->Cout, g->OH, g->OW, G, dout, out,
+                                                                                (bf16*)dYg, dbias);
+  RIQN_LAUNCH_CHECK();
+  RIQN_CUDA(cudaMemsetAsync(dwp_scratch, 0, sizeof(float) * g->Cout * K, s));
+  TcExtra ex;
+  ex.mn_major = 1;
+  ex.wg_t = t; ex.wg_G = G; ex.wg_kc = kc;
+  ex.alpha = wgrad_scale;
+  const int n_tiles = (K + 255) / 256;
+  const int split = (148 + n_tiles - 1) / n_tiles;
+  int rc = gemm_bf16_tc(g->Cout, K, (int)Mg, (const bf16*)dYg, nullptr, (const bf16*)a_hi, nullptr, dwp_scratch, K, TC_ATOMIC,
+                        nullptr, nullptr, nullptr, split, s, &ex);
+  if (rc) return rc;
+  unpermute_add_kernel<<<(g->Cout * K + 255) / 256, 256, 0, s>>>(g->Cout, K, dwp_scratch, perm, dw);
+  RIQN_LAUNCH_CHECK();
+  if (din) {
+    RIQN_CUDA(cudaMemsetAsync(din, 0, sizeof(float) * (size_t)g->B * g->Cin * g->H * g->W, s));
+    TcExtra ci;
+    ci.ohw = G * G;
+    ci.ci_h = g->H; ci.ci_w = g->W; ci.ci_cin = g->Cin; ci.ci_kh = g->KH; ci.ci_kw = g->KW;
+    ci.ci_stride = g->stride; ci.ci_ow = g->OW; ci.ci_oh = g->OH; ci.ci_G = G;
+    rc = gemm_bf16_tc((int)Mg, K, g->Cout, (const bf16*)dYg, nullptr, (const bf16*)wT_hi, nullptr, din, K, TC_COL2IM, nullptr,
+                      nullptr, nullptr, 1, s, &ci);
+    if (rc) return rc;
+  }
+  return 0;
 }
 
 // bf16 transposed im2col (K, M) alone -- the wgrad operand of riqn_conv_bwd_tc when the forward ran as a strip

@@ -246,7 +246,7 @@ struct TcArgs {
   float alpha;           // TC_ATOMIC: scale applied to the accumulator
   int vec_acc;           // TC_ATOMIC / TC_NOISY_WGRAD: C (out2, eps) rows are 16-byte aligned -> vectorised accumulate
   int ohw;               // TC_BIAS_RELU_NCHW: m = b*ohw + p -> C[(b*N + n)*ohw + p]
-  int ci_h, ci_w, ci_cin, ci_kh, ci_kw, ci_stride, ci_ow;   // TC_COL2IM geometry (pad == 0)
+  int ci_h, ci_w, ci_cin, ci_kh, ci_kw, ci_stride, ci_ow, ci_G, ci_oh;   // TC_COL2IM geometry (pad == 0)
   const float* feat;     // TC_EMBED: (samples, N) conv features, row m uses feat[m / batch] (batch = rows per sample)
   int batch;
   bf16 *o_hi, *o_lo;     // TC_EMBED: bf16 hi / lo images of the result, row-major (M, N)   (may be null)
@@ -521,10 +521,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
             const int kh = r / p.ci_kw, kw = r - kh * p.ci_kw;
             coff = (c * p.ci_h + kh) * p.ci_w + kw;
           }
-          const bool row_ok = m < p.M;
+          bool row_ok = m < p.M;
           const int mm = row_ok ? m : 0;
-          const int b = mm / p.ohw, pp = mm - b * p.ohw;
-          const int oh = pp / p.ci_ow, ow = pp - oh * p.ci_ow;
+          const int b = mm / p.ohw, pp = mm - b * p.ohw;                 // ohw = G*G on the strip grid
+          const int rw = p.ci_G ? p.ci_G : p.ci_ow;
+          const int oh = pp / rw, ow = pp - oh * rw;
+          if (p.ci_G) row_ok = row_ok && oh < p.ci_oh && ow < p.ci_ow;   // grid rows beyond the real outputs carry zeros
           float* base = p.C + ((long)b * p.ci_cin * p.ci_h + oh * p.ci_stride) * p.ci_w + ow * p.ci_stride;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -676,7 +678,7 @@ int gemm_bf16_tc(int M, int N, int K, const bf16* A_hi, const bf16* A_lo, const 
                  long ldc, int epi, const float* bias, float* out2, const float* eps, int split_k, cudaStream_t s,
                  const TcExtra* ex) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
-  if (K % 8) return (int)cudaErrorInvalidValue;
+  if ((K % 8) && !(ex != nullptr && ex->mn_major)) return (int)cudaErrorInvalidValue;   // MN-major: K counts rows
   const bool split3 = A_lo != nullptr && B_lo != nullptr;
   const bool split2 = A_lo == nullptr && B_lo != nullptr;
   // narrow outputs (conv channels, embedding width) get narrow tiles; only the epilogues that occur with them exist
@@ -734,6 +736,7 @@ int gemm_bf16_tc(int M, int N, int K, const bf16* A_hi, const bf16* A_lo, const 
   p.ohw = ex ? ex->ohw : 1; p.feat = ex ? ex->feat : nullptr; p.batch = ex ? ex->batch : 1;
   p.ci_h = ex ? ex->ci_h : 0; p.ci_w = ex ? ex->ci_w : 0; p.ci_cin = ex ? ex->ci_cin : 0; p.ci_kh = ex ? ex->ci_kh : 0;
   p.ci_kw = ex ? ex->ci_kw : 0; p.ci_stride = ex ? ex->ci_stride : 0; p.ci_ow = ex ? ex->ci_ow : 0;
+  p.ci_G = ex ? ex->ci_G : 0; p.ci_oh = ex ? ex->ci_oh : 0;
   p.strip_t = ex ? ex->strip_t : 0; p.strip_G = ex ? ex->strip_G : 0; p.strip_kc = ex ? ex->strip_kc : 0;
   p.cv_oh = ex ? ex->cv_oh : 0; p.cv_ow = ex ? ex->cv_ow : 0; p.nx_s = ex ? ex->nx_s : 0; p.nx_G = ex ? ex->nx_G : 0;
   p.nx_hi = ex ? ex->nx_hi : nullptr; p.nx_lo = ex ? ex->nx_lo : nullptr;

@@ -382,6 +382,7 @@ class DQN(nn.Module):
         if getattr(self, "_strip_ops", None) is None or self._strip_ops["conv1"][0].device != dev:
             self._strip_perm = {n: _strip_perm(cin, k, st, first).to(dev) for n, cin, k, st, first in
                                 (("conv1", self.history, 8, 4, True), ("conv2", 32, 4, 2, False), ("conv3", 64, 3, 1, False))}
+            self._strip_perm32 = {n: pm.to(torch.int32) for n, pm in self._strip_perm.items()}
             self._strip_ops = {n: (torch.empty(co, pm.numel(), dtype=torch.bfloat16, device=dev),
                                    torch.empty(co, pm.numel(), dtype=torch.bfloat16, device=dev))
                                for (n, pm), co in zip(self._strip_perm.items(), (32, 64, 64))}
@@ -470,17 +471,17 @@ class DQN(nn.Module):
             call("riqn_conv_fwd_strip", g3, ptr(a3_hi), ptr(a3_lo), ptr(ops["conv3"][0]), ptr(ops["conv3"][1]) if x3 else None,
                  ptr(self.conv3.bias), ptr(outs[2]), None, None, 0, 0)
             if keep is not None:                     # operands of the backward products
-                for i, (g, inp) in enumerate(zip(geoms, ins)):
-                    M, K = g.B * g.OH * g.OW, g.Cin * g.KH * g.KW
-                    if bwd_tc:
-                        colTs[i] = bf(K, M)
-                        call("riqn_im2col_bf16_t", g, ptr(inp), 1 if i == 0 else 0, ptr(colTs[i]))
-                    else:
+                strip_bwd = None
+                if bwd_tc:                           # the strip backward reads the forward's block matrices
+                    strip_bwd = (a1, a2_hi, a3_hi)
+                    px_scale = 1.0 / 255.0
+                else:
+                    for i, (g, inp) in enumerate(zip(geoms, ins)):
+                        M, K = g.B * g.OH * g.OW, g.Cin * g.KH * g.KW
                         cols[i] = torch.empty(M, K, device=dev)
                         call("riqn_im2col_f32", g, ptr(inp), 1 if i == 0 else 0, ptr(cols[i]))
-                if bwd_tc:
-                    px_scale = 1.0 / 255.0
-                keep.update(x=x, g=geoms, col=tuple(cols), colT=tuple(colTs), out=outs, bwd_tc=bwd_tc, px_scale=px_scale)
+                keep.update(x=x, g=geoms, col=tuple(cols), colT=tuple(colTs), out=outs, bwd_tc=bwd_tc, px_scale=px_scale,
+                            strip_bwd=strip_bwd)
             return outs[2].view(B, FEAT)
         for i, (g, conv, inp, out) in enumerate(zip(geoms, convs, ins, outs)):
             M, K = g.B * g.OH * g.OW, g.Cin * g.KH * g.KW
@@ -669,7 +670,16 @@ class DQN(nn.Module):
             g, conv, out = keep["g"][i], convs[i], keep["out"][i]
             M, K = g.B * g.OH * g.OW, g.Cin * g.KH * g.KW
             din = torch.empty_like(keep["out"][i - 1]) if i > 0 else None
-            if keep["bwd_tc"]:
+            if keep["bwd_tc"] and keep.get("strip_bwd") is not None:
+                name = "conv%d" % (i + 1)
+                _, _, wT_hi = self._conv_ops[name]
+                G = g.OH + g.KH // g.stride - 1
+                dYg = torch.empty(g.B * G * G, g.Cout, dtype=torch.bfloat16, device=dev)
+                dwp = torch.empty(g.Cout, K, device=dev)
+                call("riqn_conv_bwd_strip", g, ptr(douts[i]), ptr(out), ptr(keep["strip_bwd"][i]), ptr(wT_hi),
+                     ptr(self._strip_perm32[name]), ptr(dYg), ptr(dwp), ptr(gv(conv.weight)), ptr(gv(conv.bias)), ptr(din),
+                     keep["px_scale"] if i == 0 else 1.0)
+            elif keep["bwd_tc"]:
                 _, _, wT_hi = self._conv_ops["conv%d" % (i + 1)]
                 dY = torch.empty(M, g.Cout, dtype=torch.bfloat16, device=dev) if i > 0 else None
                 dYT = torch.empty(g.Cout, M, dtype=torch.bfloat16, device=dev)
