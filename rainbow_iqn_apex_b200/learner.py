@@ -193,8 +193,14 @@ class Learner(Agent):
             self._pf_stream = torch.cuda.Stream()
             self._pf_buf = [tuple(torch.empty_like(t) for t in self._bg_in) for _ in range(2)]
             self._pf_slot, self._pf_event = 0, None
+            self._pf_read_done = [None, None]
+            self._pf_stream.wait_stream(torch.cuda.current_stream())   # fresh staging memory: order after its last user
         slot = self._pf_slot ^ 1
-        self._pf_stream.wait_stream(torch.cuda.current_stream())      # staging slot no longer read by an older step
+        # the staging slot must no longer be read by the (older) step that consumed it: wait for THAT step's
+        # device-to-device copies only, not for the compute enqueued since -- the H2D overlaps the current step
+        ev_read = self._pf_read_done[slot]
+        if ev_read is not None:
+            self._pf_stream.wait_event(ev_read)
         with torch.cuda.stream(self._pf_stream):
             for d, h in zip(self._pf_buf[slot], host_batch):
                 d.copy_(h, non_blocking=True)
@@ -210,6 +216,9 @@ class Learner(Agent):
             torch.cuda.current_stream().wait_event(self._pf_event)
             for d, src in zip(self._bg_in, self._pf_buf[self._pf_slot]):
                 d.copy_(src, non_blocking=True)                          # device-to-device, 29 MB
+            ev = torch.cuda.Event()
+            ev.record()
+            self._pf_read_done[self._pf_slot] = ev                       # this staging slot may be refilled from here on
         else:
             for d, h in zip(self._bg_in, host_batch):
                 d.copy_(h, non_blocking=True)
