@@ -96,11 +96,11 @@ int riqn_conv_fwd_strip(const riqn_conv_geom* g, const void* a_hi, const void* a
                         void* stream);
 int riqn_im2col_bf16_t(const riqn_conv_geom* g, const void* in, int in_is_u8, void* colT_hi, void* stream);
 /* Backward of a strip convolution on the tensor cores, again without im2col matrices: a_hi is the block matrix the
- * forward read (riqn_s2d_u8 / the previous layer's next_hi); wT_hi (K, Cout) bf16 in the ORIGINAL k order (data
- * gradient); perm (K ints): strip k order -> original k; dYg (B*G*G, Cout) bf16 and dwp_scratch (Cout*K floats)
+ * forward read (riqn_s2d_u8 / the previous layer's next_hi); w_hi (Cout, K) bf16 weight in the ORIGINAL k order (data
+ * gradient, read as an MN-major operand); perm (K ints): strip k order -> original k; dYg (B*G*G, Cout) bf16 and dwp_scratch (Cout*K floats)
  * workspaces; dw / dbias accumulated; din (may be NULL; pad == 0 only) overwritten.  wgrad_scale = 1/255 when a_hi
  * holds raw pixel values. */
-int riqn_conv_bwd_strip(const riqn_conv_geom* g, const float* dout, const float* out, const void* a_hi, const void* wT_hi,
+int riqn_conv_bwd_strip(const riqn_conv_geom* g, const float* dout, const float* out, const void* a_hi, const void* w_hi,
                         const int* perm, void* dYg, float* dwp_scratch, float* dw, float* dbias, float* din,
                         float wgrad_scale, void* stream);
 
@@ -352,10 +352,12 @@ int riqn_split_bf16(long rows, int cols, const float* src, void* hi, void* lo, v
 int riqn_gemm_bf16_tc(int M, int N, int K, const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo,
                       float* c, long ldc, int epilogue, const float* bias, float* out2, const float* eps, int split_k,
                       void* c_t_bf16, void* c_bf16, void* stream);
-/* C (+)= A^T B with A (K, M) and B (K, N) row-major bf16 (M % 8 == 0, N % 8 == 0): the reduction runs over the ROWS, so
- * a weight gradient dW = dY^T X is taken straight from the row-major activations (MN-major tcgen05 operands, no
- * transposed copies).  epilogue 0 / 2 / 3 as above (2, 3 scale the accumulator by alpha); single-bf16 product. */
-int riqn_gemm_bf16_tc_mn(int M, int N, int K, const void* a_km, const void* b_kn, float* c, long ldc, int epilogue,
+/* Products whose B operand is (K, N) row-major bf16 (MN-major tcgen05 operand, N % 8 == 0) -- no transposed copies:
+ *   a_is_km != 0: C (+)= A^T B with A (K, M) row-major (M % 8 == 0): the reduction runs over the ROWS of both, i.e. a
+ *                 weight gradient dW = dY^T X straight from the row-major activations;
+ *   a_is_km == 0: C (+)= A B with A (M, K) row-major (K % 8 == 0): a data gradient dX = dY W from the untransposed W.
+ * epilogue 0 / 2 / 3 as above (2, 3 scale the accumulator by alpha); single-bf16 product. */
+int riqn_gemm_bf16_tc_mn(int M, int N, int K, const void* a, const void* b_kn, int a_is_km, float* c, long ldc, int epilogue,
                          float* out2, const float* eps, float alpha, int split_k, void* stream);
 
 /* ------------------------------------------------------------------------------------------------

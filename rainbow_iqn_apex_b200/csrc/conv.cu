@@ -756,9 +756,9 @@ RIQN_API int riqn_conv_fwd_strip(const riqn_conv_geom* g, const void* a_hi, cons
 //   dYg (B*G*G, Cout) = dout * (out > 0) on the strip grid;   dbias += column sums
 //   dW'[c, (shift, within)] = sum_m' dYg[m', c] * a_hi[m' + shift offset, within]   (MN-major operands, shifted rows)
 //   dw[c, perm[k']] += wgrad_scale * dW'[c, k']
-//   din += col2im(dYg * W)   (fused epilogue, pad == 0 only; din may be NULL)
+//   din += col2im(dYg * W)   (W (Cout, K) as MN-major operand; fused epilogue, pad == 0 only; din may be NULL)
 RIQN_API int riqn_conv_bwd_strip(const riqn_conv_geom* g, const float* dout, const float* out, const void* a_hi,
-                                 const void* wT_hi, const int* perm, void* dYg, float* dwp_scratch, float* dw, float* dbias,
+                                 const void* w_hi, const int* perm, void* dYg, float* dwp_scratch, float* dw, float* dbias,
                                  float* din, float wgrad_scale, void* stream) {
   riqn::note_launches(din ? 6 : 4);
   cudaStream_t s = (cudaStream_t)stream;
@@ -772,7 +772,7 @@ RIQN_API int riqn_conv_bwd_strip(const riqn_conv_geom* g, const float* dout, con
   RIQN_LAUNCH_CHECK();
   RIQN_CUDA(cudaMemsetAsync(dwp_scratch, 0, sizeof(float) * g->Cout * K, s));
   TcExtra ex;
-  ex.mn_major = 1;
+  ex.mn_major = 3;
   ex.wg_t = t; ex.wg_G = G; ex.wg_kc = kc;
   ex.alpha = wgrad_scale;
   const int n_tiles = (K + 255) / 256;
@@ -788,7 +788,8 @@ RIQN_API int riqn_conv_bwd_strip(const riqn_conv_geom* g, const float* dout, con
     ci.ohw = G * G;
     ci.ci_h = g->H; ci.ci_w = g->W; ci.ci_cin = g->Cin; ci.ci_kh = g->KH; ci.ci_kw = g->KW;
     ci.ci_stride = g->stride; ci.ci_ow = g->OW; ci.ci_oh = g->OH; ci.ci_G = G;
-    rc = gemm_bf16_tc((int)Mg, K, g->Cout, (const bf16*)dYg, nullptr, (const bf16*)wT_hi, nullptr, din, K, TC_COL2IM, nullptr,
+    ci.mn_major = 2;               // B = the (Cout, K) weight itself, read as an MN-major operand (no transposed copy)
+    rc = gemm_bf16_tc((int)Mg, K, g->Cout, (const bf16*)dYg, nullptr, (const bf16*)w_hi, nullptr, din, K, TC_COL2IM, nullptr,
                       nullptr, nullptr, 1, s, &ci);
     if (rc) return rc;
   }

@@ -49,8 +49,9 @@ struct TcExtra {
   // (may be null) receive the bf16 images in the NEXT layer's space-to-depth layout (block edge nx_s, grid nx_G).
   int strip_t = 0, strip_G = 0, strip_kc = 0, cv_oh = 0, cv_ow = 0, nx_s = 0, nx_G = 0;
   __nv_bfloat16 *nx_hi = nullptr, *nx_lo = nullptr;
-  // MN-major operands (mn_major = 1): A is (K, M) and B is (K, N) row-major -- the reduction index is the ROW, as in a
-  // weight gradient dW = dY^T X taken straight from the row-major activations (no transposed copies).  NSPLIT 1 only.
+  // MN-major operands (mn_major bit 0: A is (K, M) row-major, bit 1: B is (K, N) row-major): the reduction index is the
+  // ROW, as in a weight gradient dW = dY^T X taken straight from the row-major activations, or a data gradient
+  // dX = dY W read from the untransposed weight (mn_major = 2).  NSPLIT 1 only.
   // wg_t > 0 additionally applies the strip-convolution shifts to B: column n = (shift, within-block) reads the rows
   // k + dy*wg_G + dx of a block matrix with wg_kc*64 columns (shift = n / (wg_kc*64) = dy*wg_t + dx).
   int mn_major = 0, wg_t = 0, wg_G = 0, wg_kc = 0;

@@ -304,19 +304,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
           uint8_t* s = smem + stage * Cfg::kStageBytes;
           mbar_expect_tx(&full[stage], Cfg::kStageBytes);
           if (NSPLIT == 1 && p.mn_major) {
-            // (K, MN) row-major operands: 64 x 64 boxes, inner coordinate = MN offset, outer = reduction row
+            // MN-major operand ((K, MN) row-major): 64 x 64 boxes, inner coordinate = MN offset, outer = reduction row.
+            // bit 0: A, bit 1: B; the other operand (if any) stays K-major.
             const int kk = kb * TBK;
+            if (p.mn_major & 1) {
 #pragma unroll
-            for (int i = 0; i < TBM / 64; ++i) tma_load_2d(s + i * 8192, &mapA_hi, mt * TBM + 64 * i, kk, &full[stage]);
+              for (int i = 0; i < TBM / 64; ++i) tma_load_2d(s + i * 8192, &mapA_hi, mt * TBM + 64 * i, kk, &full[stage]);
+            } else {
+              tma_load_2d(s, &mapA_hi, kk, mt * TBM, &full[stage]);
+            }
+            if (p.mn_major & 2) {
 #pragma unroll
-            for (int i = 0; i < (TBN >= 64 ? TBN / 64 : 1); ++i) {
-              int b_in = nt * TBN + 64 * i, b_row = kk;
-              if (p.wg_t) {                        // strip weight gradient: this 64-column slab has its own row shift
-                const int slab = b_in >> 6, sft = slab / p.wg_kc, dy = sft / p.wg_t;
-                b_in = (slab - sft * p.wg_kc) << 6;
-                b_row += dy * p.wg_G + (sft - dy * p.wg_t);
+              for (int i = 0; i < (TBN >= 64 ? TBN / 64 : 1); ++i) {
+                int b_in = nt * TBN + 64 * i, b_row = kk;
+                if (p.wg_t) {                        // strip weight gradient: this 64-column slab has its own row shift
+                  const int slab = b_in >> 6, sft = slab / p.wg_kc, dy = sft / p.wg_t;
+                  b_in = (slab - sft * p.wg_kc) << 6;
+                  b_row += dy * p.wg_G + (sft - dy * p.wg_t);
+                }
+                tma_load_2d(s + Cfg::kOps * Cfg::kABytes + i * 8192, &mapB_hi, b_in, b_row, &full[stage]);
               }
-              tma_load_2d(s + Cfg::kOps * Cfg::kABytes + i * 8192, &mapB_hi, b_in, b_row, &full[stage]);
+            } else {
+              tma_load_2d(s + Cfg::kOps * Cfg::kABytes, &mapB_hi, kk, nt * TBN, &full[stage]);
             }
             if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
             continue;
@@ -357,11 +366,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint32_t sb = sa + Cfg::kOps * Cfg::kABytes;
           if (NSPLIT == 1 && p.mn_major) {
+            const uint32_t idesc_mn = idesc | ((p.mn_major & 1) ? (1u << 15) : 0u) | ((p.mn_major & 2) ? (1u << 16) : 0u);
 #pragma unroll
             for (int k = 0; k < TBK / UMMA_K; ++k) {
-              const uint32_t koff = k * (UMMA_K / 8) * 1024;   // 16 reduction rows = two 8-row swizzle atoms
-              umma_bf16(tmem_d, umma_desc_mn128(sa + koff), umma_desc_mn128(sb + koff), idesc | (1u << 15) | (1u << 16),
-                        (kb > kb0 || k > 0) ? 1u : 0u);
+              const uint32_t koff_mn = k * (UMMA_K / 8) * 1024;   // MN-major: 16 reduction rows = two 8-row swizzle atoms
+              const uint32_t koff_k = k * UMMA_K * 2;             // K-major: bytes inside the 128 B swizzle row
+              const uint64_t da = (p.mn_major & 1) ? umma_desc_mn128(sa + koff_mn) : umma_desc_k128(sa + koff_k);
+              const uint64_t db = (p.mn_major & 2) ? umma_desc_mn128(sb + koff_mn) : umma_desc_k128(sb + koff_k);
+              umma_bf16(tmem_d, da, db, idesc_mn, (kb > kb0 || k > 0) ? 1u : 0u);
             }
             umma_commit(&empty[stage]);
             if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
@@ -411,6 +423,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
         if (EPI == TC_EMBED && c + 32 < (chalf + 1) * HALF && n0 + 64 <= p.N) {   // next chunk's feat / bias lines -> L1
           asm volatile("prefetch.global.L1 [%0];" ::"l"(embed_feat_row + n0 + 32));
           asm volatile("prefetch.global.L1 [%0];" ::"l"(p.bias + n0 + 32));
+        }
+        // embedding epilogue: this chunk's feat / bias values are requested BEFORE the accumulator load, so that
+        // their latency overlaps the TMEM read instead of following it
+        float4 ef[8], eb[8];
+        if (EPI == TC_EMBED && n0 + 32 <= p.N) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            ef[j] = __ldg(reinterpret_cast<const float4*>(embed_feat_row + n0) + j);
+            eb[j] = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j);
+          }
         }
         uint32_t v[32];
         tmem_ld32(trow + c, v);
@@ -575,13 +597,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
             } else {
               // x = feat[b] * relu(acc + bias)   (model.py:146-151); N % 32 == 0 is required by the host wrapper
               const bool row_ok = m < p.M;
-              const float* fr = embed_feat_row + n0;                 // warp-broadcast when 32 | rows per sample
-              const float* br = p.bias + n0;
               uint32_t hw[32];   // [0..15] hi pairs (cols 2k, 2k+1), [16..31] lo pairs
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
-                const float4 f = __ldg(reinterpret_cast<const float4*>(fr + j));
-                const float4 bb = __ldg(reinterpret_cast<const float4*>(br + j));
+                const float4 f = ef[j >> 2];                         // feat row: warp-broadcast when 32 | rows per sample
+                const float4 bb = eb[j >> 2];
                 const float x0 = f.x * fmaxf(__uint_as_float(v[j]) + bb.x, 0.f);
                 const float x1 = f.y * fmaxf(__uint_as_float(v[j + 1]) + bb.y, 0.f);
                 const float x2 = f.z * fmaxf(__uint_as_float(v[j + 2]) + bb.z, 0.f);
@@ -678,7 +698,7 @@ int gemm_bf16_tc(int M, int N, int K, const bf16* A_hi, const bf16* A_lo, const 
                  long ldc, int epi, const float* bias, float* out2, const float* eps, int split_k, cudaStream_t s,
                  const TcExtra* ex) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
-  if ((K % 8) && !(ex != nullptr && ex->mn_major)) return (int)cudaErrorInvalidValue;   // MN-major: K counts rows
+  if ((K % 8) && !(ex != nullptr && ex->mn_major == 3)) return (int)cudaErrorInvalidValue;   // both MN-major: K counts rows
   const bool split3 = A_lo != nullptr && B_lo != nullptr;
   const bool split2 = A_lo == nullptr && B_lo != nullptr;
   // narrow outputs (conv channels, embedding width) get narrow tiles; only the epilogues that occur with them exist
@@ -691,7 +711,9 @@ int gemm_bf16_tc(int M, int N, int K, const bf16* A_hi, const bf16* A_lo, const 
   const bool mn = ex != nullptr && ex->mn_major != 0;
   if (mn) {
     // A (K, M), B (K, N) row-major; only the plain single-bf16 product with full-width (or 64-wide) N tiles
-    if (split3 || split2 || (M % 8) || (N % 8)) return (int)cudaErrorInvalidValue;
+    if (split3 || split2 || ((ex->mn_major & 1) && (M % 8)) || ((ex->mn_major & 2) && (N % 8)) ||
+        (((ex->mn_major & 3) != 3) && (K % 8)))
+      return (int)cudaErrorInvalidValue;
   }
   const int bn = (ex != nullptr && ex->mn_major) ? ((narrow_ok && N <= 64) ? 64 : 256)
                                                  : (narrow_ok && N <= 32) ? 32 : (narrow_ok && N <= 64) ? 64 : 256;
@@ -699,9 +721,9 @@ int gemm_bf16_tc(int M, int N, int K, const bf16* A_hi, const bf16* A_lo, const 
   int rc;
   if (mn) {
     const long b_cols = ex->wg_t ? (long)ex->wg_kc * TBK : N;      // strip weight gradient: B is the block matrix
-    rc = make_map(&ma_hi, A_hi, K, M, 64);
+    rc = (ex->mn_major & 1) ? make_map(&ma_hi, A_hi, K, M, 64) : make_map(&ma_hi, A_hi, M, K, TBM);
     if (rc) return rc;
-    rc = make_map(&mb_hi, B_hi, K, b_cols, 64);
+    rc = (ex->mn_major & 2) ? make_map(&mb_hi, B_hi, K, b_cols, 64) : make_map(&mb_hi, B_hi, N, K, bn);
     if (rc) return rc;
   } else {
     rc = make_map(&ma_hi, A_hi, M, a_k, TBM);
@@ -740,7 +762,7 @@ int gemm_bf16_tc(int M, int N, int K, const bf16* A_hi, const bf16* A_lo, const 
   p.strip_t = ex ? ex->strip_t : 0; p.strip_G = ex ? ex->strip_G : 0; p.strip_kc = ex ? ex->strip_kc : 0;
   p.cv_oh = ex ? ex->cv_oh : 0; p.cv_ow = ex ? ex->cv_ow : 0; p.nx_s = ex ? ex->nx_s : 0; p.nx_G = ex ? ex->nx_G : 0;
   p.nx_hi = ex ? ex->nx_hi : nullptr; p.nx_lo = ex ? ex->nx_lo : nullptr;
-  p.mn_major = mn ? 1 : 0; p.wg_t = ex ? ex->wg_t : 0; p.wg_G = ex ? ex->wg_G : 0; p.wg_kc = ex ? ex->wg_kc : 0;
+  p.mn_major = mn ? ex->mn_major : 0; p.wg_t = ex ? ex->wg_t : 0; p.wg_G = ex ? ex->wg_G : 0; p.wg_kc = ex ? ex->wg_kc : 0;
   if (epi == TC_COL2IM && (ex == nullptr || p.ci_kh * p.ci_kw * p.ci_cin != N || split3 || split2)) return (int)cudaErrorInvalidValue;
   p.o_hi = ex ? ex->o_hi : nullptr; p.o_lo = ex ? ex->o_lo : nullptr;
   p.o_hiT = ex ? ex->o_hiT : nullptr; p.o_loT = ex ? ex->o_loT : nullptr;
@@ -862,13 +884,13 @@ RIQN_API int riqn_gemm_bf16_tc(int M, int N, int K, const void* a_hi, const void
                       bias, out2, eps, split_k, (cudaStream_t)stream, &ex);
 }
 
-RIQN_API int riqn_gemm_bf16_tc_mn(int M, int N, int K, const void* a_km, const void* b_kn, float* c, long ldc, int epilogue,
-                                  float* out2, const float* eps, float alpha, int split_k, void* stream) {
+RIQN_API int riqn_gemm_bf16_tc_mn(int M, int N, int K, const void* a, const void* b_kn, int a_is_km, float* c, long ldc,
+                                  int epilogue, float* out2, const float* eps, float alpha, int split_k, void* stream) {
   riqn::note_launches(1);
   if (epilogue != TC_STORE && epilogue != TC_ATOMIC && epilogue != TC_NOISY_WGRAD) return (int)cudaErrorInvalidValue;
   TcExtra ex;
-  ex.mn_major = 1;
+  ex.mn_major = a_is_km ? 3 : 2;
   ex.alpha = alpha;
-  return gemm_bf16_tc(M, N, K, (const bf16*)a_km, nullptr, (const bf16*)b_kn, nullptr, c, ldc, epilogue, nullptr, out2, eps,
+  return gemm_bf16_tc(M, N, K, (const bf16*)a, nullptr, (const bf16*)b_kn, nullptr, c, ldc, epilogue, nullptr, out2, eps,
                       split_k, (cudaStream_t)stream, &ex);
 }

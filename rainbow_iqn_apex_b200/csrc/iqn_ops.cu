@@ -842,7 +842,7 @@ RIQN_API int riqn_quantile_embed_bwd_tc(int batch, int num_quantiles, int embed_
   const int split = (148 + m_tiles - 1) / m_tiles;
   // dWe[f, i] += sum_r dpre[r, f] * cos[r, i]: both operands row-major, reduction over the rows (MN-major operands)
   TcExtra ex;
-  ex.mn_major = 1;
+  ex.mn_major = 3;
   return gemm_bf16_tc(feat_dim, embed_dim, (int)R, (const __nv_bfloat16*)dpre, nullptr, (const __nv_bfloat16*)cos_hi, nullptr,
                       grad_iqn_w, embed_dim, TC_ATOMIC, nullptr, nullptr, nullptr, split, s, &ex);
 }
@@ -1014,7 +1014,7 @@ RIQN_API int riqn_z_wgrad_tc(long rows, int hidden, int action_space, const void
   const int split = (148 + n_tiles - 1) / n_tiles;
   // dWz[z, j] = sum_r dz[r, z] * h[r, j]: both operands row-major, reduction over the rows (MN-major operands)
   TcExtra ex;
-  ex.mn_major = 1;
+  ex.mn_major = 3;
   int rc = gemm_bf16_tc(32, W, (int)rows, (const __nv_bfloat16*)dz_bf16, nullptr, (const __nv_bfloat16*)h_bf16, nullptr,
                         dwz_scratch, W, TC_ATOMIC, nullptr, nullptr, nullptr, split, s, &ex);
   if (rc) return rc;

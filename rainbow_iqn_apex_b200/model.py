@@ -368,8 +368,9 @@ class DQN(nn.Module):
             self._conv1_px_ops = (mk(32, k1), mk(32, k1))      # bf16 hi / lo of conv1.weight / 255 (uint8 ingest)
             if not self.rainbow_only:
                 self._iqn_ops = (mk(FEAT, self.quantile_embedding_dim), mk(FEAT, self.quantile_embedding_dim))
+        need_t = PRECISION["bwd"] != "bf16" or PRECISION["fwd"] == "fp32"   # bf16 backward reads W itself (MN-major operand)
         call("riqn_split_bf16", 2 * self.hidden, FEAT, ptr(self._w_eff_h), ptr(self._w_hi), ptr(self._w_lo),
-             ptr(self._w_hiT), ptr(self._w_loT))
+             ptr(self._w_hiT) if need_t else None, ptr(self._w_loT) if need_t else None)
         if not (force or getattr(self, "_static_ops_dirty", True)):
             return
         self._static_ops_dirty = False
@@ -639,7 +640,7 @@ class DQN(nn.Module):
                 call("riqn_split_bf16", R, 2 * hid, ptr(dh), ptr(dh_hi), ptr(dh_lo), ptr(dh_hiT), ptr(dh_loT))
             # dW[o, i] = sum_r dh[r, o] x[r, i]  -> dmu += dW, dsigma += dW * eps   (split-K, atomics)
             if fused_dh:
-                call("riqn_gemm_bf16_tc_mn", 2 * hid, FEAT, R, ptr(dh_hi), ptr(tc["x_hi"]), ptr(gv(hv.weight_mu)), FEAT, 3,
+                call("riqn_gemm_bf16_tc_mn", 2 * hid, FEAT, R, ptr(dh_hi), ptr(tc["x_hi"]), 1, ptr(gv(hv.weight_mu)), FEAT, 3,
                      ptr(gv(hv.weight_sigma)), ptr(hv.weight_epsilon), 1.0, WGRAD_SPLIT_K)
             else:
                 call("riqn_gemm_bf16_tc", 2 * hid, FEAT, R, ptr(dh_hiT), ptr(dh_loT), ptr(tc["x_hiT"]),
@@ -648,8 +649,12 @@ class DQN(nn.Module):
             call("riqn_noisy_bias_grad", R, 2 * hid, ptr(dh) if dh is not None else None, ptr(hv.bias_epsilon), ptr(dbs),
                  ptr(gv(hv.bias_mu)), ptr(gv(hv.bias_sigma)))
             # dx[r, i] = sum_o dh[r, o] W_eff[o, i]
-            call("riqn_gemm_bf16_tc", R, FEAT, 2 * hid, ptr(dh_hi), ptr(dh_lo), ptr(self._w_hiT),
-                 ptr(self._w_loT) if b3 else None, ptr(dx), FEAT, 0, None, None, None, 1, None, None)
+            if fused_dh:     # W_eff (2*hid, 3136) itself is the (K, N) operand: no transposed weight image
+                call("riqn_gemm_bf16_tc_mn", R, FEAT, 2 * hid, ptr(dh_hi), ptr(self._w_hi), 0, ptr(dx), FEAT, 0, None, None,
+                     1.0, 1)
+            else:
+                call("riqn_gemm_bf16_tc", R, FEAT, 2 * hid, ptr(dh_hi), ptr(dh_lo), ptr(self._w_hiT),
+                     ptr(self._w_loT) if b3 else None, ptr(dx), FEAT, 0, None, None, None, 1, None, None)
         dfeat = torch.empty(B, FEAT, device=dev)
         if keep["emb_bwd_tc"]:
             dpre = torch.empty(R, FEAT, dtype=torch.bfloat16, device=dev)
@@ -672,11 +677,11 @@ class DQN(nn.Module):
             din = torch.empty_like(keep["out"][i - 1]) if i > 0 else None
             if keep["bwd_tc"] and keep.get("strip_bwd") is not None:
                 name = "conv%d" % (i + 1)
-                _, _, wT_hi = self._conv_ops[name]
+                w_hi = self._conv_ops[name][0]                 # (Cout, K) in the original k order
                 G = g.OH + g.KH // g.stride - 1
                 dYg = torch.empty(g.B * G * G, g.Cout, dtype=torch.bfloat16, device=dev)
                 dwp = torch.empty(g.Cout, K, device=dev)
-                call("riqn_conv_bwd_strip", g, ptr(douts[i]), ptr(out), ptr(keep["strip_bwd"][i]), ptr(wT_hi),
+                call("riqn_conv_bwd_strip", g, ptr(douts[i]), ptr(out), ptr(keep["strip_bwd"][i]), ptr(w_hi),
                      ptr(self._strip_perm32[name]), ptr(dYg), ptr(dwp), ptr(gv(conv.weight)), ptr(gv(conv.bias)), ptr(din),
                      keep["px_scale"] if i == 0 else 1.0)
             elif keep["bwd_tc"]:

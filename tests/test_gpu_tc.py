@@ -69,11 +69,12 @@ def test_tc_gemm_many_tiles_persistent(cuda_dev):
     _run(cuda_dev, 8192, 1024, 512, True, epi=1, seed=7)
 
 
-def _run_mn(dev, M, N, K, epi=0, split_k=1, alpha=1.0, seed=0):
-    """C (+)= alpha * A^T B with A (K, M), B (K, N) row-major bf16 -- the MN-major operand mode."""
+def _run_mn(dev, M, N, K, epi=0, split_k=1, alpha=1.0, seed=0, a_is_km=1):
+    """C (+)= alpha * A^T B with A (K, M), B (K, N) row-major bf16 -- the MN-major operand mode; a_is_km = 0:
+    C (+)= alpha * A B with A (M, K) row-major (K-major A, MN-major B: a data gradient from the untransposed weight)."""
     from rainbow_iqn_apex_b200._lib import call, ptr
     rs = np.random.RandomState(seed)
-    A = _bf16_round(rs.standard_normal((K, M)).astype(np.float32))
+    A = _bf16_round(rs.standard_normal((K, M) if a_is_km else (M, K)).astype(np.float32))
     B = _bf16_round((rs.standard_normal((K, N)) * 0.05).astype(np.float32))
     a = torch.from_numpy(A).to(dev).to(torch.bfloat16)
     b = torch.from_numpy(B).to(dev).to(torch.bfloat16)
@@ -81,9 +82,9 @@ def _run_mn(dev, M, N, K, epi=0, split_k=1, alpha=1.0, seed=0):
     c = torch.from_numpy(c0).to(dev)
     eps = torch.from_numpy(rs.standard_normal((M, N)).astype(np.float32)).to(dev)
     c2 = torch.zeros(M, N, device=dev)
-    call("riqn_gemm_bf16_tc_mn", M, N, K, ptr(a), ptr(b), ptr(c), N, epi, ptr(c2), ptr(eps), alpha, split_k)
+    call("riqn_gemm_bf16_tc_mn", M, N, K, ptr(a), ptr(b), a_is_km, ptr(c), N, epi, ptr(c2), ptr(eps), alpha, split_k)
     torch.cuda.synchronize()
-    prod = A.astype(np.float64).T @ B.astype(np.float64)
+    prod = (A.astype(np.float64).T if a_is_km else A.astype(np.float64)) @ B.astype(np.float64)
     ref = prod if epi == 0 else c0 + alpha * prod
     assert rel_err(c.cpu().numpy(), ref) < 1e-5, (M, N, K, epi, split_k, rel_err(c.cpu().numpy(), ref))
     if epi == 3:
@@ -96,3 +97,6 @@ def test_tc_gemm_mn_major(cuda_dev):
     _run_mn(cuda_dev, 64, 64, 200, seed=2)                            # narrow tile, ragged reduction
     _run_mn(cuda_dev, 1024, 3136, 4096, epi=3, split_k=4, seed=3)     # NoisyLinear weight gradient shape
     _run_mn(cuda_dev, 32, 576, 2000, epi=2, split_k=5, alpha=0.5, seed=4)   # conv weight gradient shape (Cout x K)
+    # mixed majors: A (M, K) K-major, B (K, N) MN-major -- dX = dY W from the untransposed weight
+    _run_mn(cuda_dev, 300, 3136, 1024, seed=5, a_is_km=0)
+    _run_mn(cuda_dev, 128, 256, 64, seed=6, a_is_km=0)
