@@ -205,12 +205,12 @@ int riqn_quantile_embed_fwd_tc(int batch, int num_quantiles, int embed_dim, int 
                                const float* feat, const void* iqn_w_hi, const void* iqn_w_lo, const float* iqn_b,
                                void* cos_hi, void* cos_lo, void* cos_t_hi, float* x32, void* x_hi, void* x_lo, void* x_hi_t,
                                void* x_lo_t, void* stream);
-/* Backward on bf16 operands (rows % 8 == 0): dx fp32 (rows, feat_dim) from the head dgrad; cos_hi (rows, embed_dim)
- * bf16 row-major (the forward's image); dpre (rows, feat_dim) bf16 workspace; dfeat overwritten; grad_iqn_w /
- * grad_iqn_b accumulated. */
+/* Backward on bf16 operands (rows % 8 == 0): dx (rows, feat_dim) from the head dgrad, fp32 or (dx_is_bf16 != 0) bf16;
+ * x_lo may be NULL (x = x_hi); cos_hi (rows, embed_dim) bf16 row-major (the forward's image); dpre (rows, feat_dim) bf16
+ * workspace; dfeat overwritten; grad_iqn_w / grad_iqn_b accumulated. */
 int riqn_quantile_embed_bwd_tc(int batch, int num_quantiles, int embed_dim, int feat_dim, const void* x_hi, const void* x_lo,
-                               const float* feat, const void* cos_hi, const float* dx, void* dpre, float* dfeat,
-                               float* grad_iqn_w, float* grad_iqn_b, void* stream);
+                               const float* feat, const void* cos_hi, const void* dx, int dx_is_bf16, void* dpre,
+                               float* dfeat, float* grad_iqn_w, float* grad_iqn_b, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * z-layers + dueling aggregation                          replaces rainbowiqn/model.py:153-156
@@ -356,9 +356,10 @@ int riqn_gemm_bf16_tc(int M, int N, int K, const void* a_hi, const void* a_lo, c
  *   a_is_km != 0: C (+)= A^T B with A (K, M) row-major (M % 8 == 0): the reduction runs over the ROWS of both, i.e. a
  *                 weight gradient dW = dY^T X straight from the row-major activations;
  *   a_is_km == 0: C (+)= A B with A (M, K) row-major (K % 8 == 0): a data gradient dX = dY W from the untransposed W.
- * epilogue 0 / 2 / 3 as above (2, 3 scale the accumulator by alpha); single-bf16 product. */
+ * epilogue 0 / 2 / 3 as above (2, 3 scale the accumulator by alpha); single-bf16 product.  c_bf16 (may be NULL; epilogue 0,
+ * N % 32 == 0): write the result as bf16 (M, N) there INSTEAD of fp32 into c. */
 int riqn_gemm_bf16_tc_mn(int M, int N, int K, const void* a, const void* b_kn, int a_is_km, float* c, long ldc, int epilogue,
-                         float* out2, const float* eps, float alpha, int split_k, void* stream);
+                         float* out2, const float* eps, float alpha, int split_k, void* c_bf16, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Test hook: plain strided fp32 product C[m,n] = sum_k A[m*sAm + k*sAk] * B[n*sBn + k*sBk].

@@ -564,7 +564,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
           const int rows_valid = min(32, p.M - m_base);            // warp-uniform
           if (rows_valid > 0) {
             if (EPI == TC_STORE) {
-              warp_store_rows_f32(st, v, lane, p.C + (long)m_base * p.ldc + n0, p.ldc, rows_valid);
+              if (p.o_hi != nullptr) {                           // bf16 result (M, N) instead of fp32: 64-byte row pieces
+                uint32_t hw2[32];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+                  hw2[j] = *reinterpret_cast<const uint32_t*>(&h2);
+                  hw2[16 + j] = 0u;
+                }
+                warp_store_rows_bf16(st, hw2, lane, p.o_hi + (long)m_base * p.N + n0, nullptr, p.N, rows_valid);
+              } else {
+                warp_store_rows_f32(st, v, lane, p.C + (long)m_base * p.ldc + n0, p.ldc, rows_valid);
+              }
             } else if (EPI == TC_ATOMIC) {
               warp_accum_rows_f32<false>(st, v, lane, p.C + (long)m_base * p.ldc + n0, nullptr, nullptr, p.ldc, rows_valid,
                                          p.k_splits > 1, p.alpha);
@@ -885,10 +896,13 @@ RIQN_API int riqn_gemm_bf16_tc(int M, int N, int K, const void* a_hi, const void
 }
 
 RIQN_API int riqn_gemm_bf16_tc_mn(int M, int N, int K, const void* a, const void* b_kn, int a_is_km, float* c, long ldc,
-                                  int epilogue, float* out2, const float* eps, float alpha, int split_k, void* stream) {
+                                  int epilogue, float* out2, const float* eps, float alpha, int split_k, void* c_bf16,
+                                  void* stream) {
   riqn::note_launches(1);
   if (epilogue != TC_STORE && epilogue != TC_ATOMIC && epilogue != TC_NOISY_WGRAD) return (int)cudaErrorInvalidValue;
+  if (c_bf16 && (epilogue != TC_STORE || (N % 32))) return (int)cudaErrorInvalidValue;
   TcExtra ex;
+  ex.o_hi = (bf16*)c_bf16;
   ex.mn_major = a_is_km ? 3 : 2;
   ex.alpha = alpha;
   return gemm_bf16_tc(M, N, K, (const bf16*)a, nullptr, (const bf16*)b_kn, nullptr, c, ldc, epilogue, nullptr, out2, eps,

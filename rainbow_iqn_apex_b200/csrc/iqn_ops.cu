@@ -80,8 +80,9 @@ __global__ void cos_embed_bf16_kernel(int B, int Nq, int E, const float* __restr
 // Rows are sample-major, so one block = one sample x 32 features walks that sample's Nq contiguous rows.
 __global__ void embed_bwd_tile_kernel(int B, int Nq, int F, const __nv_bfloat16* __restrict__ x_hi,
                                       const __nv_bfloat16* __restrict__ x_lo, const float* __restrict__ feat,
-                                      const float* __restrict__ dX, __nv_bfloat16* __restrict__ dpre,
-                                      float* __restrict__ dfeat, float* __restrict__ dbe) {
+                                      const float* __restrict__ dX, const __nv_bfloat16* __restrict__ dXb,
+                                      __nv_bfloat16* __restrict__ dpre, float* __restrict__ dfeat,
+                                      float* __restrict__ dbe) {
   __shared__ float red[2][8][32];
   const int f0 = blockIdx.x * 32, b = blockIdx.y;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
@@ -93,7 +94,7 @@ __global__ void embed_bwd_tile_kernel(int B, int Nq, int F, const __nv_bfloat16*
       const long o = ((long)b * Nq + q) * F + f;
       float x = __bfloat162float(x_hi[o]);
       if (x_lo) x += __bfloat162float(x_lo[o]);
-      const float dx = dX[o];
+      const float dx = dXb ? __bfloat162float(dXb[o]) : dX[o];
       facc = fmaf(dx, x, facc);
       const float dp = x > 0.f ? dx * ft : 0.f;
       bacc += dp;
@@ -115,9 +116,11 @@ __global__ void embed_bwd_tile_kernel(int B, int Nq, int F, const __nv_bfloat16*
 // Wide variant (Nq even): one block = one sample x 128 features; lane owns 4 consecutive features (16-byte dX loads,
 // 8-byte x loads, 8-byte dpre stores), warp w owns rows q = 2w, 2w+1, 2w+16, ... so that all of a thread's loads are in
 // flight together.
+template <bool DXB, bool XLO>
 __global__ void __launch_bounds__(256) embed_bwd_wide_kernel(int B, int Nq, int F, const __nv_bfloat16* __restrict__ x_hi,
                                                              const __nv_bfloat16* __restrict__ x_lo,
                                                              const float* __restrict__ feat, const float* __restrict__ dX,
+                                                             const __nv_bfloat16* __restrict__ dXb,
                                                              __nv_bfloat16* __restrict__ dpre, float* __restrict__ dfeat,
                                                              float* __restrict__ dbe) {
   __shared__ float red[2][8][128];
@@ -141,9 +144,15 @@ __global__ void __launch_bounds__(256) embed_bwd_wide_kernel(int B, int Nq, int 
       xl[i] = make_uint2(0u, 0u);
       if (q < Nq && f_ok) {
         const long o = ((long)b * Nq + q) * F + f;
-        dx[i] = __ldg(reinterpret_cast<const float4*>(dX + o));
+        if (DXB) {                                             // bf16 dX: 8-byte loads
+          const uint2 d2 = __ldg(reinterpret_cast<const uint2*>(dXb + o));
+          dx[i] = make_float4(__uint_as_float(d2.x << 16), __uint_as_float(d2.x & 0xffff0000u), __uint_as_float(d2.y << 16),
+                              __uint_as_float(d2.y & 0xffff0000u));
+        } else {
+          dx[i] = __ldg(reinterpret_cast<const float4*>(dX + o));
+        }
         xh[i] = __ldg(reinterpret_cast<const uint2*>(x_hi + o));
-        if (x_lo) xl[i] = __ldg(reinterpret_cast<const uint2*>(x_lo + o));
+        if (XLO) xl[i] = __ldg(reinterpret_cast<const uint2*>(x_lo + o));
       }
     }
 #pragma unroll
@@ -182,6 +191,87 @@ __global__ void __launch_bounds__(256) embed_bwd_wide_kernel(int B, int Nq, int 
     for (int j = 0; j < 8; ++j) { fs += red[0][j][t]; bs += red[1][j][t]; }
     const float fv = feat[(long)b * F + f0 + t];
     dfeat[(long)b * F + f0 + t] = fv > 0.f ? fs / fv : 0.f;
+    atomicAdd(&dbe[f0 + t], bs);
+  }
+}
+
+// bf16-dX variant with 16-byte accesses throughout: lane owns 8 consecutive features (one block = one sample x 256
+// features), warp w owns rows q = w, w+8, ...; all of a thread's loads of a 64-row pass are in flight together.
+template <bool XLO>
+__global__ void __launch_bounds__(256) embed_bwd_wide8_kernel(int B, int Nq, int F, const __nv_bfloat16* __restrict__ x_hi,
+                                                              const __nv_bfloat16* __restrict__ x_lo,
+                                                              const float* __restrict__ feat,
+                                                              const __nv_bfloat16* __restrict__ dXb,
+                                                              __nv_bfloat16* __restrict__ dpre, float* __restrict__ dfeat,
+                                                              float* __restrict__ dbe) {
+  __shared__ float red[2][8][256];
+  const int f0 = blockIdx.x * 256, b = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int fl = 8 * lane, f = f0 + fl;                 // F % 8 == 0 is checked by the host
+  const bool f_ok = f < F;
+  float fv[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) fv[j] = 0.f;
+  if (f_ok) {
+    const float4 a = *reinterpret_cast<const float4*>(feat + (long)b * F + f);
+    const float4 c = *reinterpret_cast<const float4*>(feat + (long)b * F + f + 4);
+    fv[0] = a.x; fv[1] = a.y; fv[2] = a.z; fv[3] = a.w; fv[4] = c.x; fv[5] = c.y; fv[6] = c.z; fv[7] = c.w;
+  }
+  float facc[8], bacc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { facc[j] = 0.f; bacc[j] = 0.f; }
+  auto lo16 = [](uint32_t w) { return __uint_as_float(w << 16); };
+  auto hi16 = [](uint32_t w) { return __uint_as_float(w & 0xffff0000u); };
+  for (int q0 = 0; q0 < Nq; q0 += 64) {
+    uint4 dx[8], xh[8], xl[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int q = q0 + warp + 8 * i;
+      dx[i] = make_uint4(0u, 0u, 0u, 0u);
+      xh[i] = make_uint4(0u, 0u, 0u, 0u);
+      xl[i] = make_uint4(0u, 0u, 0u, 0u);
+      if (q < Nq && f_ok) {
+        const long o = ((long)b * Nq + q) * F + f;
+        dx[i] = __ldg(reinterpret_cast<const uint4*>(dXb + o));
+        xh[i] = __ldg(reinterpret_cast<const uint4*>(x_hi + o));
+        if (XLO) xl[i] = __ldg(reinterpret_cast<const uint4*>(x_lo + o));
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int q = q0 + warp + 8 * i;
+      const uint32_t dw[4] = {dx[i].x, dx[i].y, dx[i].z, dx[i].w}, hw[4] = {xh[i].x, xh[i].y, xh[i].z, xh[i].w},
+                     lw[4] = {xl[i].x, xl[i].y, xl[i].z, xl[i].w};
+      uint32_t ow[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float x0 = lo16(hw[k]) + lo16(lw[k]), x1 = hi16(hw[k]) + hi16(lw[k]);
+        const float d0 = lo16(dw[k]), d1 = hi16(dw[k]);
+        facc[2 * k] = fmaf(d0, x0, facc[2 * k]);
+        facc[2 * k + 1] = fmaf(d1, x1, facc[2 * k + 1]);
+        const float p0 = x0 > 0.f ? d0 * fv[2 * k] : 0.f, p1 = x1 > 0.f ? d1 * fv[2 * k + 1] : 0.f;
+        bacc[2 * k] += p0;
+        bacc[2 * k + 1] += p1;
+        const __nv_bfloat162 pp = __floats2bfloat162_rn(p0, p1);
+        ow[k] = *reinterpret_cast<const uint32_t*>(&pp);
+      }
+      if (q < Nq && f_ok)
+        *reinterpret_cast<uint4*>(dpre + ((long)b * Nq + q) * F + f) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    red[0][warp][fl + j] = facc[j];
+    red[1][warp][fl + j] = bacc[j];
+  }
+  __syncthreads();
+  const int t = threadIdx.x;
+  if (f0 + t < F) {
+    float fs = 0.f, bs = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { fs += red[0][j][t]; bs += red[1][j][t]; }
+    const float ftv = feat[(long)b * F + f0 + t];
+    dfeat[(long)b * F + f0 + t] = ftv > 0.f ? fs / ftv : 0.f;
     atomicAdd(&dbe[f0 + t], bs);
   }
 }
@@ -822,20 +912,38 @@ RIQN_API int riqn_quantile_embed_fwd_tc(int batch, int num_quantiles, int embed_
 // Backward on bf16 operands: dx (fp32, from the head dgrad) -> dfeat (overwritten), grad_iqn_b / grad_iqn_w accumulated.
 // cos_hi (rows, embed_dim) bf16 row-major (the forward's image); dpre (rows, feat_dim) bf16 is workspace.  rows % 8 == 0.
 RIQN_API int riqn_quantile_embed_bwd_tc(int batch, int num_quantiles, int embed_dim, int feat_dim, const void* x_hi,
-                                        const void* x_lo, const float* feat, const void* cos_hi, const float* dx,
-                                        void* dpre, float* dfeat, float* grad_iqn_w, float* grad_iqn_b, void* stream) {
+                                        const void* x_lo, const float* feat, const void* cos_hi, const void* dx,
+                                        int dx_is_bf16, void* dpre, float* dfeat, float* grad_iqn_w, float* grad_iqn_b,
+                                        void* stream) {
   riqn::note_launches(2);
   cudaStream_t s = (cudaStream_t)stream;
   const long R = (long)batch * num_quantiles;
   if (R % 8 || feat_dim % 8 || embed_dim % 8) return (int)cudaErrorInvalidValue;
   if (num_quantiles % 2 == 0 && feat_dim % 4 == 0) {
     dim3 grid((feat_dim + 127) / 128, batch);
-    embed_bwd_wide_kernel<<<grid, 256, 0, s>>>(batch, num_quantiles, feat_dim, (const __nv_bfloat16*)x_hi,
-                                               (const __nv_bfloat16*)x_lo, feat, dx, (__nv_bfloat16*)dpre, dfeat, grad_iqn_b);
+#define RIQN_EMB_BWD(DXB, XLO)                                                                                          \
+  embed_bwd_wide_kernel<DXB, XLO><<<grid, 256, 0, s>>>(batch, num_quantiles, feat_dim, (const __nv_bfloat16*)x_hi,        \
+                                                       (const __nv_bfloat16*)x_lo, feat, (const float*)dx,                \
+                                                       (const __nv_bfloat16*)dx, (__nv_bfloat16*)dpre, dfeat, grad_iqn_b)
+    if (dx_is_bf16 && feat_dim % 8 == 0) {
+      dim3 grid8((feat_dim + 255) / 256, batch);
+      if (x_lo)
+        embed_bwd_wide8_kernel<true><<<grid8, 256, 0, s>>>(batch, num_quantiles, feat_dim, (const __nv_bfloat16*)x_hi,
+                                                           (const __nv_bfloat16*)x_lo, feat, (const __nv_bfloat16*)dx,
+                                                           (__nv_bfloat16*)dpre, dfeat, grad_iqn_b);
+      else
+        embed_bwd_wide8_kernel<false><<<grid8, 256, 0, s>>>(batch, num_quantiles, feat_dim, (const __nv_bfloat16*)x_hi,
+                                                            nullptr, feat, (const __nv_bfloat16*)dx, (__nv_bfloat16*)dpre,
+                                                            dfeat, grad_iqn_b);
+    } else if (dx_is_bf16) { if (x_lo) RIQN_EMB_BWD(true, true); else RIQN_EMB_BWD(true, false); }
+    else            { if (x_lo) RIQN_EMB_BWD(false, true); else RIQN_EMB_BWD(false, false); }
+#undef RIQN_EMB_BWD
   } else {
     dim3 grid((feat_dim + 31) / 32, batch);
     embed_bwd_tile_kernel<<<grid, 256, 0, s>>>(batch, num_quantiles, feat_dim, (const __nv_bfloat16*)x_hi,
-                                               (const __nv_bfloat16*)x_lo, feat, dx, (__nv_bfloat16*)dpre, dfeat, grad_iqn_b);
+                                               (const __nv_bfloat16*)x_lo, feat, dx_is_bf16 ? nullptr : (const float*)dx,
+                                               dx_is_bf16 ? (const __nv_bfloat16*)dx : nullptr, (__nv_bfloat16*)dpre, dfeat,
+                                               grad_iqn_b);
   }
   RIQN_LAUNCH_CHECK();
   const int m_tiles = (feat_dim + 127) / 128;

@@ -623,8 +623,10 @@ class DQN(nn.Module):
             call("riqn_z_wgrad_tc", R, hid, A, ptr(dzT), ptr(tc["h_hi"]), ptr(dz), *zargs)
         else:
             call("riqn_z_wgrad", R, hid, A, ptr(dz), ptr(keep["h"]), *zargs)
-        dx = torch.empty(R, FEAT, device=dev)
         bwd = PRECISION["bwd"]
+        # bf16 backward: dx is consumed as a bf16 operand anyway, so the dgrad writes it as bf16 (half the traffic)
+        dx_bf16 = fused_dh and bool(keep["emb_bwd_tc"])
+        dx = torch.empty(R, FEAT, dtype=torch.bfloat16 if dx_bf16 else torch.float32, device=dev)
         # [h_v | h_a] are adjacent in every arena, so one (2*hid, 3136) product serves both layers
         if not keep["head_bwd_tc"]:
             call("riqn_noisy_linear_wgrad", R, FEAT, 2 * hid, ptr(dh), ptr(keep["xt"]), ptr(hv.weight_epsilon),
@@ -641,7 +643,7 @@ class DQN(nn.Module):
             # dW[o, i] = sum_r dh[r, o] x[r, i]  -> dmu += dW, dsigma += dW * eps   (split-K, atomics)
             if fused_dh:
                 call("riqn_gemm_bf16_tc_mn", 2 * hid, FEAT, R, ptr(dh_hi), ptr(tc["x_hi"]), 1, ptr(gv(hv.weight_mu)), FEAT, 3,
-                     ptr(gv(hv.weight_sigma)), ptr(hv.weight_epsilon), 1.0, WGRAD_SPLIT_K)
+                     ptr(gv(hv.weight_sigma)), ptr(hv.weight_epsilon), 1.0, WGRAD_SPLIT_K, None)
             else:
                 call("riqn_gemm_bf16_tc", 2 * hid, FEAT, R, ptr(dh_hiT), ptr(dh_loT), ptr(tc["x_hiT"]),
                      ptr(tc["x_loT"]) if b3 else None, ptr(gv(hv.weight_mu)), FEAT, 3, None, ptr(gv(hv.weight_sigma)),
@@ -650,16 +652,18 @@ class DQN(nn.Module):
                  ptr(gv(hv.bias_mu)), ptr(gv(hv.bias_sigma)))
             # dx[r, i] = sum_o dh[r, o] W_eff[o, i]
             if fused_dh:     # W_eff (2*hid, 3136) itself is the (K, N) operand: no transposed weight image
-                call("riqn_gemm_bf16_tc_mn", R, FEAT, 2 * hid, ptr(dh_hi), ptr(self._w_hi), 0, ptr(dx), FEAT, 0, None, None,
-                     1.0, 1)
+                call("riqn_gemm_bf16_tc_mn", R, FEAT, 2 * hid, ptr(dh_hi), ptr(self._w_hi), 0, None if dx_bf16 else ptr(dx), FEAT,
+                     0, None, None, 1.0, 1, ptr(dx) if dx_bf16 else None)
             else:
                 call("riqn_gemm_bf16_tc", R, FEAT, 2 * hid, ptr(dh_hi), ptr(dh_lo), ptr(self._w_hiT),
                      ptr(self._w_loT) if b3 else None, ptr(dx), FEAT, 0, None, None, None, 1, None, None)
         dfeat = torch.empty(B, FEAT, device=dev)
         if keep["emb_bwd_tc"]:
             dpre = torch.empty(R, FEAT, dtype=torch.bfloat16, device=dev)
-            call("riqn_quantile_embed_bwd_tc", B, Nq, E, FEAT, ptr(tc["x_hi"]), ptr(tc["x_lo"]), ptr(keep["feat"]),
-                 ptr(tc["cos_hi"]), ptr(dx), ptr(dpre), ptr(dfeat), ptr(gv(self.iqn_fc.weight)), ptr(gv(self.iqn_fc.bias)))
+            # bf16 backward: x = x_hi (the lo image only refines the forward)
+            call("riqn_quantile_embed_bwd_tc", B, Nq, E, FEAT, ptr(tc["x_hi"]), None if dx_bf16 else ptr(tc["x_lo"]),
+                 ptr(keep["feat"]), ptr(tc["cos_hi"]), ptr(dx), 1 if dx_bf16 else 0, ptr(dpre), ptr(dfeat),
+                 ptr(gv(self.iqn_fc.weight)), ptr(gv(self.iqn_fc.bias)))
         else:
             call("riqn_quantile_embed_bwd", B, Nq, E, FEAT, ptr(keep["xt"]), ptr(keep["feat"]), ptr(keep["cos"]), ptr(dx),
                  ptr(dfeat), ptr(gv(self.iqn_fc.weight)), ptr(gv(self.iqn_fc.bias)))

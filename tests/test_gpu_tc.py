@@ -82,7 +82,7 @@ def _run_mn(dev, M, N, K, epi=0, split_k=1, alpha=1.0, seed=0, a_is_km=1):
     c = torch.from_numpy(c0).to(dev)
     eps = torch.from_numpy(rs.standard_normal((M, N)).astype(np.float32)).to(dev)
     c2 = torch.zeros(M, N, device=dev)
-    call("riqn_gemm_bf16_tc_mn", M, N, K, ptr(a), ptr(b), a_is_km, ptr(c), N, epi, ptr(c2), ptr(eps), alpha, split_k)
+    call("riqn_gemm_bf16_tc_mn", M, N, K, ptr(a), ptr(b), a_is_km, ptr(c), N, epi, ptr(c2), ptr(eps), alpha, split_k, None)
     torch.cuda.synchronize()
     prod = (A.astype(np.float64).T if a_is_km else A.astype(np.float64)) @ B.astype(np.float64)
     ref = prod if epi == 0 else c0 + alpha * prod
@@ -100,6 +100,16 @@ def test_tc_gemm_mn_major(cuda_dev):
     # mixed majors: A (M, K) K-major, B (K, N) MN-major -- dX = dY W from the untransposed weight
     _run_mn(cuda_dev, 300, 3136, 1024, seed=5, a_is_km=0)
     _run_mn(cuda_dev, 128, 256, 64, seed=6, a_is_km=0)
+    # the same product written as bf16 instead of fp32 (the head data gradient feeding the embedding backward)
+    from rainbow_iqn_apex_b200._lib import call, ptr
+    rs = np.random.RandomState(7)
+    A, B = _bf16_round(rs.standard_normal((300, 1024)).astype(np.float32)), _bf16_round(rs.standard_normal((1024, 3136)).astype(np.float32) * 0.05)
+    a, b = torch.from_numpy(A).to(cuda_dev).to(torch.bfloat16), torch.from_numpy(B).to(cuda_dev).to(torch.bfloat16)
+    cb = torch.zeros(300, 3136, dtype=torch.bfloat16, device=cuda_dev)
+    call("riqn_gemm_bf16_tc_mn", 300, 3136, 1024, ptr(a), ptr(b), 0, None, 3136, 0, None, None, 1.0, 1, ptr(cb))
+    torch.cuda.synchronize()
+    ref = A.astype(np.float64) @ B.astype(np.float64)
+    assert rel_err(cb.float().cpu().numpy(), ref) < 4e-3          # one bf16 rounding of the result
 
 
 def _strip_layers():
