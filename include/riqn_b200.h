@@ -155,6 +155,8 @@ typedef struct riqn_noisy_layer {
   float* w_eff;                                  /* (out, in) mu + sigma * eps   (mu when training == 0) */
   float* b_eff;                                  /* (out) */
   unsigned long long stream_in, stream_out;      /* Philox stream ids of the two draws */
+  void* w_hi;                                    /* (out, in) bf16 image of w_eff for the tensor-core products, or NULL */
+  void* w_lo;                                    /* (out, in) bf16(w_eff - hi), or NULL */
 } riqn_noisy_layer;
 
 /* DQN.reset_noise() for all NoisyLinear layers of one network in two launches (model.py:159-162 -> :39-43 -> :32-37):

@@ -25,7 +25,7 @@ class NoisyLayer(C.Structure):
     _fields_ = [("out_features", C.c_int), ("in_features", C.c_int), ("weight_mu", _P), ("weight_sigma", _P),
                 ("weight_epsilon", _P), ("bias_mu", _P), ("bias_sigma", _P), ("bias_epsilon", _P), ("eps_in", _P),
                 ("eps_out", _P), ("w_eff", _P), ("b_eff", _P), ("stream_in", C.c_ulonglong),
-                ("stream_out", C.c_ulonglong)]
+                ("stream_out", C.c_ulonglong), ("w_hi", _P), ("w_lo", _P)]
 
 
 # name -> argtypes (everything returns int).  Must list every symbol of include/riqn_b200.h.

@@ -361,6 +361,17 @@ __global__ void noisy_compose_net_kernel(NoisyNet net, int training) {
                     __fadd_rn(mu.z, __fmul_rn(sg.z, e.z)), __fadd_rn(mu.w, __fmul_rn(sg.w, e.w)));
   }
   *reinterpret_cast<float4*>(L.w_eff + off) = w;
+  if (L.w_hi != nullptr) {           // bf16 operand images written here instead of by a separate split pass
+    const __nv_bfloat162 h01 = __floats2bfloat162_rn(w.x, w.y), h23 = __floats2bfloat162_rn(w.z, w.w);
+    const uint32_t u01 = *reinterpret_cast<const uint32_t*>(&h01), u23 = *reinterpret_cast<const uint32_t*>(&h23);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(L.w_hi) + off) = make_uint2(u01, u23);
+    if (L.w_lo != nullptr) {
+      const __nv_bfloat162 l01 = __floats2bfloat162_rn(w.x - __uint_as_float(u01 << 16), w.y - __uint_as_float(u01 & 0xffff0000u));
+      const __nv_bfloat162 l23 = __floats2bfloat162_rn(w.z - __uint_as_float(u23 << 16), w.w - __uint_as_float(u23 & 0xffff0000u));
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(L.w_lo) + off) =
+          make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+    }
+  }
   if (i == 0) {
     L.bias_epsilon[o] = eo;
     L.b_eff[o] = training ? __fadd_rn(L.bias_mu[o], __fmul_rn(L.bias_sigma[o], eo)) : L.bias_mu[o];

@@ -322,15 +322,22 @@ class DQN(nn.Module):
             seed = int(torch.randint(0, 2 ** 62, (1,)).item())
         call("riqn_noisy_reset_net", len(layers), desc, seed, 0 if noise is not None else 1, 1 if self.training else 0,
              dyn.ptr() if (dyn is not None and noise is None) else None)
-        self._refresh_tc_operands()
+        self._refresh_tc_operands(h_done=self._fuse_h_images())
 
     def _noisy_desc(self):
         """Cached riqn_noisy_layer[] for riqn_noisy_reset_net (all pointers are static arena / scratch addresses)."""
         layers = self.noisy_layers()
-        key = tuple(m.weight_mu.data_ptr() for _, m in layers) + (self._flat.data_ptr(),)
+        fuse = self._fuse_h_images()
+        w_hi = getattr(self, "_w_hi", None) if fuse else None
+        key = tuple(m.weight_mu.data_ptr() for _, m in layers) + (self._flat.data_ptr(), w_hi.data_ptr() if fuse else 0)
         if getattr(self, "_noisy_desc_key", None) != key:
             arr = (NoisyLayer * len(layers))()
-            for k, (_, m) in enumerate(layers):
+            for k, (name, m) in enumerate(layers):
+                if fuse and name in ("fcnoisy_h_v", "fcnoisy_h_a"):
+                    # the composed hidden-layer weights leave the compose kernel as bf16 (hi, lo) images as well
+                    row0 = 0 if name == "fcnoisy_h_v" else self.hidden
+                    arr[k].w_hi = self._w_hi.data_ptr() + row0 * FEAT * 2
+                    arr[k].w_lo = self._w_lo.data_ptr() + row0 * FEAT * 2
                 m._ensure_scratch()
                 d = arr[k]
                 d.out_features, d.in_features = m.out_features, m.in_features
@@ -340,19 +347,22 @@ class DQN(nn.Module):
             self._noisy_desc_arr, self._noisy_desc_key = arr, key
         return self._noisy_desc_arr
 
+    def _fuse_h_images(self):
+        """True when reset_noise() can let the compose kernel write the bf16 images of the hidden-layer weights (every
+        mode whose backward reads W itself; the transposed images of the other modes still come from riqn_split_bf16)."""
+        if not self._flat.is_cuda or PRECISION["fwd"] == "fp32" or PRECISION["bwd"] != "bf16":
+            return False
+        self._ensure_tc_buffers()
+        return True
+
     def compose_weights(self):
         """Recompute the effective weights from the stored epsilons (after load_state_dict / optimiser steps)."""
         for _, module in self.noisy_layers():
             module._compose()
         self._refresh_tc_operands(force=True)
 
-    def _refresh_tc_operands(self, force=False):
-        """bf16 (hi, lo) images of the composed hidden-layer weights for the tcgen05 path: (2*hid, 3136) K-major for
-        the forward product and the transposed (3136, 2*hid) copy the data-gradient product consumes.  The images of
-        the noise-free weights (convolutions, iqn_fc) are only rebuilt when those weights may have changed: after an
-        optimiser step (optim.Adam marks the owner), after compose_weights() (``force``), or on first use."""
-        if (PRECISION["fwd"] == "fp32" and PRECISION["bwd"] == "fp32") or not self._flat.is_cuda:
-            return
+    def _ensure_tc_buffers(self):
+        """Allocate the bf16 operand images once per device."""
         dev = self._flat.device
         if getattr(self, "_w_hi", None) is None or self._w_hi.device != dev:
             n = 2 * self.hidden
@@ -368,9 +378,20 @@ class DQN(nn.Module):
             self._conv1_px_ops = (mk(32, k1), mk(32, k1))      # bf16 hi / lo of conv1.weight / 255 (uint8 ingest)
             if not self.rainbow_only:
                 self._iqn_ops = (mk(FEAT, self.quantile_embedding_dim), mk(FEAT, self.quantile_embedding_dim))
+
+    def _refresh_tc_operands(self, force=False, h_done=False):
+        """bf16 (hi, lo) images of the composed hidden-layer weights for the tcgen05 path: (2*hid, 3136) K-major for
+        the forward product and the transposed (3136, 2*hid) copy the data-gradient product consumes.  The images of
+        the noise-free weights (convolutions, iqn_fc) are only rebuilt when those weights may have changed: after an
+        optimiser step (optim.Adam marks the owner), after compose_weights() (``force``), or on first use."""
+        if (PRECISION["fwd"] == "fp32" and PRECISION["bwd"] == "fp32") or not self._flat.is_cuda:
+            return
+        self._ensure_tc_buffers()
+        dev = self._flat.device
         need_t = PRECISION["bwd"] != "bf16" or PRECISION["fwd"] == "fp32"   # bf16 backward reads W itself (MN-major operand)
-        call("riqn_split_bf16", 2 * self.hidden, FEAT, ptr(self._w_eff_h), ptr(self._w_hi), ptr(self._w_lo),
-             ptr(self._w_hiT) if need_t else None, ptr(self._w_loT) if need_t else None)
+        if not h_done:
+            call("riqn_split_bf16", 2 * self.hidden, FEAT, ptr(self._w_eff_h), ptr(self._w_hi), ptr(self._w_lo),
+                 ptr(self._w_hiT) if need_t else None, ptr(self._w_loT) if need_t else None)
         if not (force or getattr(self, "_static_ops_dirty", True)):
             return
         self._static_ops_dirty = False
