@@ -673,20 +673,33 @@ __global__ void __launch_bounds__(256) conv_dy_grid_kernel(int B, int Cout, int 
       ok[h] = m < Mg && gy < OH && gx < OW;
       src0[h] = ok[h] ? b * Cout * ohw + gy * OW + gx : 0;          // + c * ohw
     }
-    for (int c = warp; c < Cout; c += 8) {
-      float acc = 0.f;
+    for (int c0 = warp; c0 < Cout; c0 += 32) {          // four channels (c0, +8, +16, +24) per pass: 16 loads in flight
+      float o_[4][2], d_[4][2];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        float v = 0.f;
-        if (ok[h]) {
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int c = c0 + 8 * u;
+          const bool on = ok[h] && c < Cout;
           const long src = src0[h] + (long)c * ohw;
-          v = out[src] > 0.f ? dout[src] : 0.f;
+          o_[u][h] = on ? __ldg(out + src) : 0.f;
+          d_[u][h] = on ? __ldg(dout + src) : 0.f;
         }
-        tile[lane + 32 * h][c] = __bfloat16_as_ushort(__float2bfloat16_rn(v));
-        acc += v;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int c = c0 + 8 * u;
+        if (c < Cout) {
+          float acc = 0.f;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const float v = o_[u][h] > 0.f ? d_[u][h] : 0.f;
+            tile[lane + 32 * h][c] = __bfloat16_as_ushort(__float2bfloat16_rn(v));
+            acc += v;
+          }
+          acc = warp_sum(acc);
+          if (lane == 0) bsum[c] += acc;
+        }
       }
-      acc = warp_sum(acc);
-      if (lane == 0) bsum[c] += acc;
     }
     __syncthreads();
     const int ppr = Cout >> 3;

@@ -425,9 +425,9 @@ __global__ void z_dueling_fwd_kernel(long R, int B, int A, const float* __restri
 // transpose-reduce over lane bits 4 and 3, then a butterfly over bits 2..0): lane l ends up with the sums of row
 // rr(l) = 2*bit3(l) + bit4(l), and the 8 lanes of a row share out the A advantages.
 template <int HID>
-__global__ void __launch_bounds__(256) z_dueling_fwd4_kernel(long R, int B, int A, const float* __restrict__ H,
-                                                             const float* __restrict__ Wz, const float* __restrict__ bz,
-                                                             float* __restrict__ q) {
+__global__ void __launch_bounds__(256, 2) z_dueling_fwd4_kernel(long R, int B, int A, const float* __restrict__ H,
+                                                                const float* __restrict__ Wz, const float* __restrict__ bz,
+                                                                float* __restrict__ q) {
   extern __shared__ float sW[];  // (1+A) * HID
   for (int i = threadIdx.x; i < (1 + A) * HID / 4; i += blockDim.x)
     reinterpret_cast<float4*>(sW)[i] = reinterpret_cast<const float4*>(Wz)[i];
@@ -436,50 +436,56 @@ __global__ void __launch_bounds__(256) z_dueling_fwd4_kernel(long R, int B, int 
   constexpr int T = HID / 128;
   const int Nq = (int)(R / B);
   const int my_rr = ((lane >> 3) & 1) * 2 + ((lane >> 4) & 1), my_j = lane & 7;
+  // one output: 4 rows x (T float4) against weight row k; returns the sum of row rr(lane) on every lane
+  auto dot4 = [&](const float4 (&hx)[4][T], int k) -> float {
+    const float4* wk = reinterpret_cast<const float4*>(sW + k * HID);
+    float p[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      const float4 w = wk[lane + 32 * t];
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+        const float4 x = hx[rr][t];
+        p[rr] = fmaf(x.x, w.x, p[rr]);
+        p[rr] = fmaf(x.y, w.y, p[rr]);
+        p[rr] = fmaf(x.z, w.z, p[rr]);
+        p[rr] = fmaf(x.w, w.w, p[rr]);
+      }
+    }
+    const bool b4 = lane & 16, b3 = lane & 8;
+    const float a01 = (b4 ? p[1] : p[0]) + __shfl_xor_sync(0xffffffffu, b4 ? p[0] : p[1], 16);
+    const float a23 = (b4 ? p[3] : p[2]) + __shfl_xor_sync(0xffffffffu, b4 ? p[2] : p[3], 16);
+    float c = (b3 ? a23 : a01) + __shfl_xor_sync(0xffffffffu, b3 ? a01 : a23, 8);
+    c += __shfl_xor_sync(0xffffffffu, c, 4);
+    c += __shfl_xor_sync(0xffffffffu, c, 2);
+    c += __shfl_xor_sync(0xffffffffu, c, 1);
+    return c;
+  };
   for (long r0 = ((long)blockIdx.x * wpb + warp) * 4; r0 < R; r0 += (long)gridDim.x * wpb * 4) {
-    float4 hv[4][T], ha[4][T];
+    // the two streams one after the other (64 data registers instead of 128: two blocks per SM)
+    float4 hx[4][T];
 #pragma unroll
     for (int rr = 0; rr < 4; ++rr) {
       const long r = r0 + rr < R ? r0 + rr : R - 1;
       const float4* h = reinterpret_cast<const float4*>(H + r * (2 * HID));
 #pragma unroll
-      for (int t = 0; t < T; ++t) {
-        hv[rr][t] = __ldg(h + lane + 32 * t);
-        ha[rr][t] = __ldg(h + HID / 4 + lane + 32 * t);
-      }
+      for (int t = 0; t < T; ++t) hx[rr][t] = __ldg(h + lane + 32 * t);
     }
-    float v = 0.f, asum = 0.f, mine0 = 0.f, mine1 = 0.f, mine2 = 0.f;
-    for (int k = 0; k <= A; ++k) {
-      const float4* wk = reinterpret_cast<const float4*>(sW + k * HID);
-      float p[4] = {0.f, 0.f, 0.f, 0.f};
+    const float v = dot4(hx, 0) + bz[0];
 #pragma unroll
-      for (int t = 0; t < T; ++t) {
-        const float4 w = wk[lane + 32 * t];
+    for (int rr = 0; rr < 4; ++rr) {
+      const long r = r0 + rr < R ? r0 + rr : R - 1;
+      const float4* h = reinterpret_cast<const float4*>(H + r * (2 * HID)) + HID / 4;
 #pragma unroll
-        for (int rr = 0; rr < 4; ++rr) {
-          const float4 x = k == 0 ? hv[rr][t] : ha[rr][t];
-          p[rr] = fmaf(x.x, w.x, p[rr]);
-          p[rr] = fmaf(x.y, w.y, p[rr]);
-          p[rr] = fmaf(x.z, w.z, p[rr]);
-          p[rr] = fmaf(x.w, w.w, p[rr]);
-        }
-      }
-      const bool b4 = lane & 16, b3 = lane & 8;
-      const float a01 = (b4 ? p[1] : p[0]) + __shfl_xor_sync(0xffffffffu, b4 ? p[0] : p[1], 16);
-      const float a23 = (b4 ? p[3] : p[2]) + __shfl_xor_sync(0xffffffffu, b4 ? p[2] : p[3], 16);
-      float c = (b3 ? a23 : a01) + __shfl_xor_sync(0xffffffffu, b3 ? a01 : a23, 8);
-      c += __shfl_xor_sync(0xffffffffu, c, 4);
-      c += __shfl_xor_sync(0xffffffffu, c, 2);
-      c += __shfl_xor_sync(0xffffffffu, c, 1);
-      c += bz[k];
-      if (k == 0) {
-        v = c;
-      } else {
-        asum += c;
-        const int a = k - 1;
-        if ((a & 7) == my_j) {                          // A <= 24 on this path
-          if (a < 8) mine0 = c; else if (a < 16) mine1 = c; else mine2 = c;
-        }
+      for (int t = 0; t < T; ++t) hx[rr][t] = __ldg(h + lane + 32 * t);
+    }
+    float asum = 0.f, mine0 = 0.f, mine1 = 0.f, mine2 = 0.f;
+    for (int k = 1; k <= A; ++k) {
+      const float c = dot4(hx, k) + bz[k];
+      asum += c;
+      const int a = k - 1;
+      if ((a & 7) == my_j) {                          // A <= 24 on this path
+        if (a < 8) mine0 = c; else if (a < 16) mine1 = c; else mine2 = c;
       }
     }
     const long r = r0 + my_rr;
@@ -1053,7 +1059,7 @@ RIQN_API int riqn_dueling_fwd(long rows, int batch, int hidden, int action_space
       RIQN_CUDA(cudaFuncSetAttribute(z_dueling_fwd4_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
       attr4 = true;
     }
-    z_dueling_fwd4_kernel<512><<<148, 256, smem, (cudaStream_t)stream>>>(rows, batch, action_space, h, wz, bz, q);
+    z_dueling_fwd4_kernel<512><<<148 * 2, 256, smem, (cudaStream_t)stream>>>(rows, batch, action_space, h, wz, bz, q);
   } else {
     z_dueling_fwd_kernel<512><<<148 * 4, 256, smem, (cudaStream_t)stream>>>(rows, batch, action_space, h, wz, bz, q);
   }
