@@ -230,8 +230,10 @@ int riqn_dueling_bwd(long rows, int batch, int hidden, int action_space, const f
 /* Same backward for bf16 tensor-core consumers (rows % 8 == 0): instead of the fp32 dh it writes dh_hi (rows, 2*hidden)
  * as bf16 (and its transpose dh_hi_t (2*hidden, rows) if non-NULL), dh_colsum (2*hidden) = the fp32 column sums of dh
  * (zeroed here; pass it to riqn_noisy_bias_grad with dh == NULL) and dz_bf16 (rows, 32), if non-NULL, the bf16 image of
- * dz for riqn_z_wgrad_tc. */
-int riqn_dueling_bwd_bf16(long rows, int batch, int hidden, int action_space, const float* h, const float* wz,
+ * dz for riqn_z_wgrad_tc.  Only the sign of h matters here (ReLU mask): h_bf16 (rows, 2*hidden), if non-NULL, is read
+ * instead of h. */
+int riqn_dueling_bwd_bf16(long rows, int batch, int hidden, int action_space, const float* h, const void* h_bf16,
+                          const float* wz,
                           const float* dtheta, const float* gscale, const long long* actions, void* dh_hi, void* dh_hi_t,
                           float* dh_colsum, float* dz, void* dz_bf16, void* stream);
 /* Parameter gradients of the two z-layers (accumulated): dwz_scratch 32*2*hidden floats, dbz_scratch 32. */

@@ -58,7 +58,7 @@ SIGNATURES = {
     "riqn_quantile_embed_bwd": [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P],
     "riqn_dueling_fwd": [C.c_long, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P],
     "riqn_dueling_bwd": [C.c_long, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P],
-    "riqn_dueling_bwd_bf16": [C.c_long, C.c_int, C.c_int, C.c_int] + [_P] * 11,
+    "riqn_dueling_bwd_bf16": [C.c_long, C.c_int, C.c_int, C.c_int] + [_P] * 12,
     "riqn_z_wgrad": [C.c_long, C.c_int, C.c_int] + [_P] * 17,
     "riqn_z_wgrad_tc": [C.c_long, C.c_int, C.c_int] + [_P] * 18,
     "riqn_argmax_mean": [C.c_int, C.c_int, C.c_int, _P, _P, _P],

@@ -629,6 +629,7 @@ __global__ void z_dueling_bwd_kernel(long R, int B, int A, const float* __restri
 // shared tile (16-byte chunk c/8 of row r sits in slot (c/8) ^ ((r >> 3) & 3)) and leaves as 64-byte column segments.
 template <int HID>
 __global__ void __launch_bounds__(256) z_dueling_bwd_bf16_kernel(long R, int B, int A, const float* __restrict__ H,
+                                                                 const __nv_bfloat16* __restrict__ Hb,
                                                                  const float* __restrict__ Wz,
                                                                  const float* __restrict__ dtheta,
                                                                  const float* __restrict__ gscale,
@@ -670,15 +671,35 @@ __global__ void __launch_bounds__(256) z_dueling_bwd_bf16_kernel(long R, int B, 
     const float g = ok ? dtheta[(rc - (long)b * Nq) * B + b] * gscale[b] : 0.f;
     const int act = (int)actions[b];
     const float* wa = sW + (1 + act) * HID;
+    // the ReLU mask only needs the SIGN of h: read the bf16 image when the forward left one (half the bytes); all of
+    // a row's loads are issued before the first use
+    float hrow[4][8];
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int c0 = (lane + 32 * it) * 8;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) hrow[it][i] = 0.f;
+      if (ok) {
+        if (Hb != nullptr) {
+          const uint4 u = __ldg(reinterpret_cast<const uint4*>(Hb + r * (2 * HID) + c0));
+          const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            hrow[it][2 * i] = __uint_as_float(w4[i] << 16);
+            hrow[it][2 * i + 1] = __uint_as_float(w4[i] & 0xffff0000u);
+          }
+        } else {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(H + r * (2 * HID) + c0));
+          const float4 c = __ldg(reinterpret_cast<const float4*>(H + r * (2 * HID) + c0 + 4));
+          hrow[it][0] = a.x; hrow[it][1] = a.y; hrow[it][2] = a.z; hrow[it][3] = a.w;
+          hrow[it][4] = c.x; hrow[it][5] = c.y; hrow[it][6] = c.z; hrow[it][7] = c.w;
+        }
+      }
+    }
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
       const int chunk = lane + 32 * it, c0 = chunk * 8, j0 = c0 & (HID - 1);
-      float hv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      if (ok) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(H + r * (2 * HID) + c0));
-        const float4 c = __ldg(reinterpret_cast<const float4*>(H + r * (2 * HID) + c0 + 4));
-        hv[0] = a.x; hv[1] = a.y; hv[2] = a.z; hv[3] = a.w; hv[4] = c.x; hv[5] = c.y; hv[6] = c.z; hv[7] = c.w;
-      }
+      const float (&hv)[8] = hrow[it];
       float val[8];
       if (it < 2) {                                            // value stream: dv * w_zv
 #pragma unroll
@@ -1082,7 +1103,8 @@ RIQN_API int riqn_dueling_bwd(long rows, int batch, int hidden, int action_space
   return (int)cudaGetLastError();
 }
 
-RIQN_API int riqn_dueling_bwd_bf16(long rows, int batch, int hidden, int action_space, const float* h, const float* wz,
+RIQN_API int riqn_dueling_bwd_bf16(long rows, int batch, int hidden, int action_space, const float* h, const void* h_bf16,
+                                   const float* wz,
                                    const float* dtheta, const float* gscale, const long long* actions, void* dh_hi,
                                    void* dh_hi_t, float* dh_colsum, float* dz, void* dz_bf16, void* stream) {
   riqn::note_launches(1);
@@ -1097,7 +1119,8 @@ RIQN_API int riqn_dueling_bwd_bf16(long rows, int batch, int hidden, int action_
   RIQN_CUDA(cudaMemsetAsync(dh_colsum, 0, sizeof(float) * 2 * hidden, s));
   const long n_blk = (rows + 31) / 32;
   z_dueling_bwd_bf16_kernel<512><<<(unsigned)(n_blk < 148 * 2 ? n_blk : 148 * 2), 256, smem, s>>>(
-      rows, batch, action_space, h, wz, dtheta, gscale, (const int64_t*)actions, (__nv_bfloat16*)dh_hi,
+      rows, batch, action_space, h, (const __nv_bfloat16*)h_bf16, wz, dtheta, gscale, (const int64_t*)actions,
+      (__nv_bfloat16*)dh_hi,
       (__nv_bfloat16*)dh_hi_t, dh_colsum, dz, (__nv_bfloat16*)dz_bf16);
   return (int)cudaGetLastError();
 }

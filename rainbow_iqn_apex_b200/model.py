@@ -628,7 +628,7 @@ class DQN(nn.Module):
             dh = None
             dh_hi = torch.empty(R, 2 * hid, dtype=torch.bfloat16, device=dev)
             dh_hiT = None                            # the wgrad reads dh_hi itself (MN-major operand)
-            call("riqn_dueling_bwd_bf16", R, B, hid, A, ptr(keep["h"]), ptr(self._w_eff_z), ptr(dtheta), ptr(gscale),
+            call("riqn_dueling_bwd_bf16", R, B, hid, A, ptr(keep["h"]), ptr(tc.get("h_hi")), ptr(self._w_eff_z), ptr(dtheta), ptr(gscale),
                  ptr(actions), ptr(dh_hi), None, ptr(dbs), ptr(dz), ptr(dzT))
         else:
             dh = torch.empty(R, 2 * hid, device=dev)
