@@ -789,7 +789,7 @@ RIQN_API int riqn_conv_bwd_strip(const riqn_conv_geom* g, const float* dout, con
   ex.wg_t = t; ex.wg_G = G; ex.wg_kc = kc;
   ex.alpha = wgrad_scale;
   const int n_tiles = (K + 255) / 256;
-  const int split = (148 + n_tiles - 1) / n_tiles;
+  const int split = tc_pick_split(n_tiles, (Mg + 63) / 64);
   int rc = gemm_bf16_tc(g->Cout, K, (int)Mg, (const bf16*)dYg, nullptr, (const bf16*)a_hi, nullptr, dwp_scratch, K, TC_ATOMIC,
                         nullptr, nullptr, nullptr, split, s, &ex);
   if (rc) return rc;

@@ -62,6 +62,23 @@ struct TcExtra {
 int gemm_bf16_tc(int M, int N, int K, const __nv_bfloat16* A_hi, const __nv_bfloat16* A_lo, const __nv_bfloat16* B_hi,
                  const __nv_bfloat16* B_lo, float* C, long ldc, int epi, const float* bias, float* out2, const float* eps,
                  int split_k, cudaStream_t s, const TcExtra* ex);
+// Split-K factor for a persistent grid of `sms` CTAs: `tiles` output tiles, `kb` reduction blocks of 64.  Minimises
+// (rounds of CTAs) x (k-blocks per unit), e.g. 25 tiles -> 11 splits (275 units, two full rounds) rather than 6
+// (150 units: a second round for two stragglers).
+inline int tc_pick_split(int tiles, long kb, int sms = 148) {
+  if (tiles < 1) tiles = 1;
+  if (kb < 1) kb = 1;
+  long best_cost = -1;
+  int best = 1;
+  const int smax = (int)(kb < 4L * sms ? kb : 4L * sms);
+  for (int s = 1; s <= smax; ++s) {
+    const long units = (long)tiles * s, rounds = (units + sms - 1) / sms, per = (kb + s - 1) / s;
+    const long cost = rounds * (per + 2);          // +2: fixed per-unit cost (pipeline fill, epilogue)
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = s; }
+  }
+  return best;
+}
+
 int split_bf16(long rows, int cols, const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, __nv_bfloat16* hiT,
                __nv_bfloat16* loT, cudaStream_t s);
 

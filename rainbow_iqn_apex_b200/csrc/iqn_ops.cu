@@ -985,7 +985,7 @@ RIQN_API int riqn_quantile_embed_bwd_tc(int batch, int num_quantiles, int embed_
   }
   RIQN_LAUNCH_CHECK();
   const int m_tiles = (feat_dim + 127) / 128;
-  const int split = (148 + m_tiles - 1) / m_tiles;
+  const int split = tc_pick_split(m_tiles, (R + 63) / 64);
   // dWe[f, i] += sum_r dpre[r, f] * cos[r, i]: both operands row-major, reduction over the rows (MN-major operands)
   TcExtra ex;
   ex.mn_major = 3;
@@ -1159,7 +1159,7 @@ RIQN_API int riqn_z_wgrad_tc(long rows, int hidden, int action_space, const void
   RIQN_CUDA(cudaMemsetAsync(dwz_scratch, 0, sizeof(float) * 32 * W, s));
   RIQN_CUDA(cudaMemsetAsync(dbz_scratch, 0, sizeof(float) * 32, s));
   const int n_tiles = (W + 255) / 256;
-  const int split = (148 + n_tiles - 1) / n_tiles;
+  const int split = tc_pick_split(n_tiles, (rows + 63) / 64);
   // dWz[z, j] = sum_r dz[r, z] * h[r, j]: both operands row-major, reduction over the rows (MN-major operands)
   TcExtra ex;
   ex.mn_major = 3;
