@@ -178,7 +178,8 @@ int riqn_noisy_linear_wgrad(long rows, int in_features, int out_features, const 
                             float* grad_weight_mu, float* grad_weight_sigma, float* grad_bias_mu,
                             float* grad_bias_sigma, void* stream);
 
-/* Bias half of the above alone (used when the weight half runs on the tensor cores). */
+/* Bias half of the above alone (used when the weight half runs on the tensor cores).  dh == NULL: db_scratch already holds
+ * the column sums of dh (riqn_dueling_bwd_bf16). */
 int riqn_noisy_bias_grad(long rows, int out_features, const float* dh, const float* bias_epsilon, float* db_scratch,
                          float* grad_bias_mu, float* grad_bias_sigma, void* stream);
 
