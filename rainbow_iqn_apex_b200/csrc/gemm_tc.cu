@@ -726,8 +726,20 @@ int gemm_bf16_tc(int M, int N, int K, const bf16* A_hi, const bf16* A_lo, const 
         (((ex->mn_major & 3) != 3) && (K % 8)))
       return (int)cudaErrorInvalidValue;
   }
-  const int bn = (ex != nullptr && ex->mn_major) ? ((narrow_ok && N <= 64) ? 64 : 256)
-                                                 : (narrow_ok && N <= 32) ? 32 : (narrow_ok && N <= 64) ? 64 : 256;
+  int bn = (ex != nullptr && ex->mn_major) ? ((narrow_ok && N <= 64) ? 64 : 256)
+                                           : (narrow_ok && N <= 32) ? 32 : (narrow_ok && N <= 64) ? 64 : 256;
+  if (epi == TC_BIAS_RELU && split3 && !(ex != nullptr && ex->mn_major) && N % 128 == 0) {
+    // head forward with few rows (K = 32 quantiles): 128-wide tiles when they fill the persistent grid's last round
+    // noticeably better (512 tiles = 3.46 rounds of 148 CTAs -> 1024 half tiles = 6.92 rounds)
+    const long mt = (M + TBM - 1) / TBM, t256 = mt * ((N + 255) / 256), t128 = mt * (N / 128);
+    auto eff = [](long t) { const long r = (t + 147) / 148; return (double)t / (double)(r * 148); };
+    if (eff(t128) > eff(t256) + 0.08) bn = 128;
+  }
+  if (epi == TC_CONV && bn == 64 && N == 64) {                  // same argument for the strip convolutions (conv3: 324 tiles)
+    const long mt = (M + TBM - 1) / TBM;
+    auto eff = [](long t) { const long r = (t + 147) / 148; return (double)t / (double)(r * 148); };
+    if (eff(2 * mt) > eff(mt) + 0.08) bn = 32;
+  }
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int rc;
   if (mn) {
@@ -785,7 +797,9 @@ int gemm_bf16_tc(int M, int N, int K, const bf16* A_hi, const bf16* A_lo, const 
   if (split3) {
     switch (epi) {
       case TC_STORE: RIQN_TC_GO(3, TC_STORE);
-      case TC_BIAS_RELU: RIQN_TC_GO(3, TC_BIAS_RELU);
+      case TC_BIAS_RELU:
+        if (bn == 128) return launch_tc<3, TC_BIAS_RELU, 128>(ma_hi, ma_lo, mb_hi, mb_lo, p, s);
+        RIQN_TC_GO(3, TC_BIAS_RELU);
       case TC_ATOMIC: RIQN_TC_GO(3, TC_ATOMIC);
       case TC_NOISY_WGRAD: RIQN_TC_GO(3, TC_NOISY_WGRAD);
       case TC_BIAS_RELU_NCHW: RIQN_TC_NARROW(3, TC_BIAS_RELU_NCHW); RIQN_TC_GO(3, TC_BIAS_RELU_NCHW);
