@@ -735,11 +735,7 @@ int gemm_bf16_tc(int M, int N, int K, const bf16* A_hi, const bf16* A_lo, const 
     auto eff = [](long t) { const long r = (t + 147) / 148; return (double)t / (double)(r * 148); };
     if (eff(t128) > eff(t256) + 0.08) bn = 128;
   }
-  if (epi == TC_CONV && bn == 64 && N == 64) {                  // same argument for the strip convolutions (conv3: 324 tiles)
-    const long mt = (M + TBM - 1) / TBM;
-    auto eff = [](long t) { const long r = (t + 147) / 148; return (double)t / (double)(r * 148); };
-    if (eff(2 * mt) > eff(mt) + 0.08) bn = 32;
-  }
+  // (32-wide tiles for conv3's 324 strip tiles were tried: slower -- only four epilogue warps drain a 32-column tile)
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int rc;
   if (mn) {
