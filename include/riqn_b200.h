@@ -350,6 +350,20 @@ int riqn_frame_gather(int batch, int actor_capacity, int history, int n_step, co
 /* fp32 (rows, cols) -> bf16 hi and lo = bf16(x - hi) (either may be NULL); hi_t / lo_t (may be NULL) receive the
  * transposed (cols, rows) copies the weight-gradient product consumes. */
 int riqn_split_bf16(long rows, int cols, const float* src, void* hi, void* lo, void* hi_t, void* lo_t, void* stream);
+/* Several small splits in ONE launch (the per-step refresh of the noise-free weight images): for each job
+ * out[r, c] = src[r, perm ? perm[c] : c] / div (div == 1: unscaled), written as hi / lo = bf16(x - hi) (lo, hi_t may be
+ * NULL; hi_t is the transposed (cols, rows) hi image).  Same values as riqn_split_bf16 / riqn_split_bf16_scaled on a
+ * column-permuted source.  jobs: HOST array of n_jobs <= 12. */
+typedef struct riqn_split_job {
+  const float* src;     /* (rows, cols) fp32 */
+  const int* perm;      /* cols ints or NULL */
+  int rows, cols;
+  float div;
+  void* hi;
+  void* lo;
+  void* hi_t;
+} riqn_split_job;
+int riqn_split_bf16_multi(int n_jobs, const riqn_split_job* jobs, void* stream);
 /* C (+)= A B^T with A (M,K), B (N,K) row-major bf16, K % 8 == 0, fp32 accumulation in TMEM.  a_lo/b_lo non-NULL
  * selects the split-bf16 x3 (fp32-faithful) product.  epilogue: 0 store, 1 relu(acc+bias[n]), 2 atomicAdd into C,
  * 3 atomicAdd into C and acc*eps[m,n] into out2 (NoisyLinear dmu / dsigma).  split_k > 1 needs 2 or 3.

@@ -28,6 +28,12 @@ class NoisyLayer(C.Structure):
                 ("stream_out", C.c_ulonglong), ("w_hi", _P), ("w_lo", _P)]
 
 
+class SplitJob(C.Structure):
+    """riqn_split_job (include/riqn_b200.h)"""
+    _fields_ = [("src", _P), ("perm", _P), ("rows", C.c_int), ("cols", C.c_int), ("div", C.c_float), ("hi", _P),
+                ("lo", _P), ("hi_t", _P)]
+
+
 # name -> argtypes (everything returns int).  Must list every symbol of include/riqn_b200.h.
 SIGNATURES = {
     "riqn_version": [],
@@ -79,6 +85,7 @@ SIGNATURES = {
     "riqn_sumtree_update": [C.c_int, C.c_long, _P, _P, _P, C.c_float, C.c_int, _P, _P, _P, _P],
     "riqn_replay_append": [C.c_int, C.c_int, C.c_int, C.c_int] + [_P] * 11,
     "riqn_frame_gather": [C.c_int, C.c_int, C.c_int, C.c_int] + [_P] * 12,
+    "riqn_split_bf16_multi": [C.c_int, C.POINTER(SplitJob), _P],
     "riqn_split_bf16": [C.c_long, C.c_int, _P, _P, _P, _P, _P, _P],
     "riqn_gemm_bf16_tc": [C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, C.c_long, C.c_int, _P, _P, _P, C.c_int, _P, _P, _P],
     "riqn_gemm_bf16_tc_mn": [C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, _P, C.c_long, C.c_int, _P, _P, C.c_float, C.c_int, _P, _P],

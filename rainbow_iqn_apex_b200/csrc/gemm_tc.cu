@@ -887,6 +887,43 @@ RIQN_API int riqn_split_bf16_scaled(long rows, int cols, const float* src, float
   return (int)cudaGetLastError();
 }
 
+struct SplitJobs {
+  riqn_split_job j[12];
+  int blk_end[12];
+  int n;
+};
+
+__global__ void split_bf16_multi_kernel(SplitJobs t) {
+  int ji = 0;
+  while (ji < t.n - 1 && (int)blockIdx.x >= t.blk_end[ji]) ++ji;
+  const riqn_split_job& J = t.j[ji];
+  const int idx = (blockIdx.x - (ji ? t.blk_end[ji - 1] : 0)) * blockDim.x + threadIdx.x;
+  if (idx >= J.rows * J.cols) return;
+  const int r = idx / J.cols, c = idx - r * J.cols;
+  float x = J.src[(long)r * J.cols + (J.perm ? J.perm[c] : c)];
+  if (J.div != 1.0f) x = __fdiv_rn(x, J.div);
+  const riqn::bf16 h = __float2bfloat16_rn(x);
+  reinterpret_cast<riqn::bf16*>(J.hi)[idx] = h;
+  if (J.lo) reinterpret_cast<riqn::bf16*>(J.lo)[idx] = __float2bfloat16_rn(x - __bfloat162float(h));
+  if (J.hi_t) reinterpret_cast<riqn::bf16*>(J.hi_t)[(long)c * J.rows + r] = h;
+}
+
+RIQN_API int riqn_split_bf16_multi(int n_jobs, const riqn_split_job* jobs, void* stream) {
+  riqn::note_launches(1);
+  if (n_jobs < 1 || n_jobs > 12 || jobs == nullptr) return (int)cudaErrorInvalidValue;
+  SplitJobs t;
+  t.n = n_jobs;
+  int blocks = 0;
+  for (int i = 0; i < n_jobs; ++i) {
+    if (jobs[i].src == nullptr || jobs[i].hi == nullptr || jobs[i].rows < 1 || jobs[i].cols < 1) return (int)cudaErrorInvalidValue;
+    t.j[i] = jobs[i];
+    blocks += (int)riqn_cdiv((long)jobs[i].rows * jobs[i].cols, 256);
+    t.blk_end[i] = blocks;
+  }
+  split_bf16_multi_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(t);
+  return (int)cudaGetLastError();
+}
+
 RIQN_API int riqn_split_bf16(long rows, int cols, const float* src, void* hi, void* lo, void* hi_t, void* lo_t,
                              void* stream) {
   riqn::note_launches(1);

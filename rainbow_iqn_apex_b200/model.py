@@ -23,7 +23,7 @@ import torch
 from torch import nn
 
 from . import _lib
-from ._lib import ConvGeom, NoisyLayer, call, ptr
+from ._lib import ConvGeom, NoisyLayer, SplitJob, call, ptr
 
 FEAT = 3136
 _ALIGN = 64  # floats; arena groups start on 256-byte boundaries
@@ -395,11 +395,6 @@ class DQN(nn.Module):
         if not (force or getattr(self, "_static_ops_dirty", True)):
             return
         self._static_ops_dirty = False
-        for name, conv in (("conv1", self.conv1), ("conv2", self.conv2), ("conv3", self.conv3)):
-            hi, lo, hiT = self._conv_ops[name]
-            call("riqn_split_bf16", hi.shape[0], hi.shape[1], ptr(conv.weight), ptr(hi), ptr(lo), ptr(hiT), None)
-        call("riqn_split_bf16_scaled", 32, self._conv1_px_ops[0].shape[1], ptr(self.conv1.weight), 255.0,
-             ptr(self._conv1_px_ops[0]), ptr(self._conv1_px_ops[1]))
         # strip-convolution weights: K reordered to (dy, dx, within-block) -- see riqn_conv_fwd_strip
         if getattr(self, "_strip_ops", None) is None or self._strip_ops["conv1"][0].device != dev:
             self._strip_perm = {n: _strip_perm(cin, k, st, first).to(dev) for n, cin, k, st, first in
@@ -408,16 +403,27 @@ class DQN(nn.Module):
             self._strip_ops = {n: (torch.empty(co, pm.numel(), dtype=torch.bfloat16, device=dev),
                                    torch.empty(co, pm.numel(), dtype=torch.bfloat16, device=dev))
                                for (n, pm), co in zip(self._strip_perm.items(), (32, 64, 64))}
-        for name, conv in (("conv1", self.conv1), ("conv2", self.conv2), ("conv3", self.conv3)):
-            hi, lo = self._strip_ops[name]
-            wp = conv.weight.detach().reshape(hi.shape[0], -1).index_select(1, self._strip_perm[name])
-            if name == "conv1":
-                call("riqn_split_bf16_scaled", hi.shape[0], hi.shape[1], ptr(wp), 255.0, ptr(hi), ptr(lo))
-            else:
-                call("riqn_split_bf16", hi.shape[0], hi.shape[1], ptr(wp), ptr(hi), ptr(lo), None, None)
-        if not self.rainbow_only:
-            call("riqn_split_bf16", FEAT, self.quantile_embedding_dim, ptr(self.iqn_fc.weight), ptr(self._iqn_ops[0]),
-                 ptr(self._iqn_ops[1]), None, None)
+            self._split_jobs = None
+        # every noise-free weight image in ONE launch (riqn_split_bf16_multi); the job table only holds static addresses
+        convs = (("conv1", self.conv1), ("conv2", self.conv2), ("conv3", self.conv3))
+        key = tuple(c.weight.data_ptr() for _, c in convs) + (self._strip_ops["conv1"][0].data_ptr(),)
+        if getattr(self, "_split_jobs", None) is None or self._split_jobs[0] != key:
+            specs = []
+            for name, conv in convs:
+                hi, lo, hiT = self._conv_ops[name]
+                specs.append((conv.weight, None, 1.0, hi, lo, hiT))                       # original k order (+ transpose)
+                shi, slo = self._strip_ops[name]
+                specs.append((conv.weight, self._strip_perm32[name], 255.0 if name == "conv1" else 1.0, shi, slo, None))
+            specs.append((self.conv1.weight, None, 255.0, self._conv1_px_ops[0], self._conv1_px_ops[1], None))
+            if not self.rainbow_only:
+                specs.append((self.iqn_fc.weight, None, 1.0, self._iqn_ops[0], self._iqn_ops[1], None))
+            arr = (SplitJob * len(specs))()
+            for j, (src, perm, div, hi, lo, hiT) in zip(arr, specs):
+                j.src, j.perm = src.data_ptr(), perm.data_ptr() if perm is not None else None
+                j.rows, j.cols, j.div = hi.shape[0], hi.shape[1], div
+                j.hi, j.lo, j.hi_t = hi.data_ptr(), lo.data_ptr(), hiT.data_ptr() if hiT is not None else None
+            self._split_jobs = (key, arr, len(specs))
+        call("riqn_split_bf16_multi", self._split_jobs[2], self._split_jobs[1])
 
     def _support(self, dev):
         """z-support of the categorical head (agent.py:54-57); only used when forward() is called without an Agent."""
