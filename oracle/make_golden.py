@@ -26,7 +26,7 @@ REF = "/root/reference"
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLD = os.path.join(os.path.dirname(HERE), "tests", "golden")
 
-from . import cases, losses, network as net, replay as oreplay, sumtree as osum  # noqa: E402
+from . import actor as oactor, cases, losses, network as net, replay as oreplay, sumtree as osum  # noqa: E402
 
 
 # --------------------------------------------------------------------------- reference harness
@@ -383,6 +383,73 @@ def golden_sumtree(name, actor_capacity, nb_actor, batch, rounds, seed):
     np.savez_compressed(os.path.join(GOLD, name + ".npz"), **rec)
 
 
+def golden_actor(name, batch_size, len_buffer, cfg, seed):
+    """Actor.act (actor.py:15-25) and Actor.compute_priorities (actor.py:41-124) of the unmodified reference on one
+    synthetic actor buffer (an episode end in the middle), plus the launch_actor.py:127-133 tail rule."""
+    from rainbowiqn.actor import Actor
+    params = net.make_params(seed)
+    inj = Injector()
+    for _ in range(2):
+        inj.push_noise(net.make_noise(99))
+    with inj:
+        actor = Actor(ref_args(batch_size, cfg), 18, None)
+    actor.online_net.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in params.items()})
+    actor.update_target_net()
+    actor.train()
+    rs = np.random.RandomState(seed)
+    n, hist = cfg["n_step"], 4
+    frames = rs.randint(0, 256, (len_buffer + hist - 1, 84, 84)).astype(np.uint8)
+    tab_state = [frames[i] for i in range(len(frames))]
+    tab_action = [int(a) for a in rs.randint(0, 18, len_buffer)]
+    tab_reward = [float(r) for r in rs.randint(-1, 2, len_buffer)]
+    tab_nonterminal = [True] * len_buffer
+    tab_nonterminal[len_buffer // 2] = False
+    K, Np, N = cfg["n_quantile"], cfg["n_tau_prime"], cfg["n_tau"]
+    ocfg = dict(cfg)
+    # --- act: reset_noise (launch_actor.py:76-77) then the greedy action
+    act_noise = net.make_noise(seed + 1)
+    act_tau = rs.uniform(0, 1, (K, 1)).astype(np.float32)
+    inj = Injector()
+    inj.push_noise(act_noise)
+    inj.push_tau(act_tau)
+    with inj:
+        actor.reset_noise()
+        a_ref = actor.act(tab_state[:hist])
+    p_on = net.apply_noise(net.to_torch(params), act_noise)
+    a_or, q_mean = oactor.act(p_on, tab_state[:hist], K, torch.from_numpy(act_tau))
+    assert a_ref == a_or, (a_ref, a_or)
+    # --- compute_priorities
+    n_tr = len_buffer - n
+    chunks = [(lo, min(lo + batch_size, n_tr)) for lo in range(0, n_tr, batch_size)]
+    noises = [cases.make_noises(seed + 100 + c) for c in range(len(chunks))]
+    taus = [tuple(rs.uniform(0, 1, (nq * (hi - lo), 1)).astype(np.float32) for nq in (K, Np, N)) for lo, hi in chunks]
+    inj = Injector()
+    for c in range(len(chunks)):
+        for k in range(3):
+            inj.push_noise(noises[c][k])
+        for t in taus[c]:
+            inj.push_tau(t)
+    # the reference interleaves reset_noise / forward per pass; the queues are consumed in the same relative order
+    with inj:
+        pri_ref = actor.compute_priorities(tab_state, tab_action, tab_reward, tab_nonterminal, 0.2)
+    assert not inj.noise_q and not inj.tau_q
+    pri_or = oactor.compute_priorities(net.to_torch(params), net.to_torch(params), tab_state, tab_action, tab_reward,
+                                       tab_nonterminal, 0.2, noises,
+                                       [tuple(torch.from_numpy(t) for t in tt) for tt in taus], ocfg, batch_size)
+    err = float(np.max(np.abs(pri_ref - pri_or) / np.abs(pri_ref)))
+    print(f"[{name}] act = {a_ref}; priorities max-rel-diff oracle vs reference = {err:.3e} over {n_tr} transitions")
+    assert err < 1e-5, err
+    rec = {"batch_size": batch_size, "len_buffer": len_buffer, "seed": seed, **{f"cfg_{k}": v for k, v in cfg.items()},
+           "frames": frames, "tab_action": np.array(tab_action), "tab_reward": np.array(tab_reward),
+           "tab_nonterminal": np.array(tab_nonterminal), "act_tau": act_tau, "act_action": a_ref,
+           "act_q_mean": q_mean.numpy(), "priorities": pri_ref,
+           "flushed": oactor.flush_priorities(pri_ref, 1.25, n)}
+    for c, tt in enumerate(taus):
+        for k, t in enumerate(tt):
+            rec[f"tau_{c}_{k}"] = t
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **rec)
+
+
 def main():
     _install_stubs()
     os.makedirs(GOLD, exist_ok=True)
@@ -392,6 +459,7 @@ def main():
     golden_c51("c51_small", batch=4, steps=2, seed=303)
     golden_sumtree("tree_pow2", actor_capacity=128, nb_actor=2, batch=32, rounds=3, seed=404)
     golden_sumtree("tree_npow2", actor_capacity=100, nb_actor=3, batch=40, rounds=3, seed=505)
+    golden_actor("actor_small", batch_size=8, len_buffer=22, cfg=cases.iqn_cfg(8, 8, 4), seed=606)
     print("golden fixtures written to", GOLD)
 
 

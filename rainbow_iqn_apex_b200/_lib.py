@@ -25,7 +25,7 @@ class NoisyLayer(C.Structure):
     _fields_ = [("out_features", C.c_int), ("in_features", C.c_int), ("weight_mu", _P), ("weight_sigma", _P),
                 ("weight_epsilon", _P), ("bias_mu", _P), ("bias_sigma", _P), ("bias_epsilon", _P), ("eps_in", _P),
                 ("eps_out", _P), ("w_eff", _P), ("b_eff", _P), ("stream_in", C.c_ulonglong),
-                ("stream_out", C.c_ulonglong), ("w_hi", _P), ("w_lo", _P)]
+                ("stream_out", C.c_ulonglong), ("w_hi", _P), ("w_lo", _P), ("w_fp16", C.c_int)]
 
 
 class SplitJob(C.Structure):
@@ -59,8 +59,8 @@ SIGNATURES = {
     "riqn_noisy_linear_wgrad": [C.c_long, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "riqn_noisy_bias_grad": [C.c_long, C.c_int, _P, _P, _P, _P, _P, _P],
     "riqn_quantile_embed_fwd": [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P],
-    "riqn_quantile_embed_fwd_tc": [C.c_int, C.c_int, C.c_int, C.c_int] + [_P] * 14,
-    "riqn_quantile_embed_bwd_tc": [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, C.c_int, _P, _P, _P, _P, _P],
+    "riqn_quantile_embed_fwd_tc": [C.c_int, C.c_int, C.c_int, C.c_int] + [_P] * 13 + [C.c_int, _P],
+    "riqn_quantile_embed_bwd_tc": [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, C.c_int, _P, _P, _P, _P, C.c_int, _P],
     "riqn_quantile_embed_bwd": [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P],
     "riqn_dueling_fwd": [C.c_long, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P],
     "riqn_dueling_bwd": [C.c_long, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P],
@@ -86,9 +86,9 @@ SIGNATURES = {
     "riqn_replay_append": [C.c_int, C.c_int, C.c_int, C.c_int] + [_P] * 11,
     "riqn_frame_gather": [C.c_int, C.c_int, C.c_int, C.c_int] + [_P] * 12,
     "riqn_split_bf16_multi": [C.c_int, C.POINTER(SplitJob), _P],
-    "riqn_split_bf16": [C.c_long, C.c_int, _P, _P, _P, _P, _P, _P],
-    "riqn_gemm_bf16_tc": [C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, C.c_long, C.c_int, _P, _P, _P, C.c_int, _P, _P, _P],
-    "riqn_gemm_bf16_tc_mn": [C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, _P, C.c_long, C.c_int, _P, _P, C.c_float, C.c_int, _P, _P],
+    "riqn_split_bf16": [C.c_long, C.c_int, _P, _P, _P, _P, _P, C.c_int, _P],
+    "riqn_gemm_bf16_tc": [C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, C.c_long, C.c_int, _P, _P, _P, C.c_int, _P, _P, C.c_int, _P],
+    "riqn_gemm_bf16_tc_mn": [C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, _P, C.c_long, C.c_int, _P, _P, C.c_float, C.c_int, _P, C.c_int, _P],
     "riqn_gemm_f32": [C.c_int, C.c_int, C.c_int, _P, C.c_long, C.c_long, _P, C.c_long, C.c_long, _P, C.c_long, _P],
 }
 

@@ -33,6 +33,8 @@ def loss_core(agent, states, actions, returns, next_states, nonterminals, keep_g
     A = agent.action_space
     K, Np, N = agent.num_quantile_samples, agent.num_tau_prime_samples, agent.num_tau_samples
     inj = getattr(agent, "_inject", None)
+    if isinstance(inj, list):            # a queue of injections: one per call (Actor.compute_priorities chunks)
+        inj = inj.pop(0) if inj else None
     noises = inj["noises"] if inj else (None, None, None)
     taus = inj["taus"] if inj else (None, None, None)
     dev = states.device

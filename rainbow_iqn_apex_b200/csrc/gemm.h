@@ -55,6 +55,9 @@ struct TcExtra {
   // wg_t > 0 additionally applies the strip-convolution shifts to B: column n = (shift, within-block) reads the rows
   // k + dy*wg_G + dx of a block matrix with wg_kc*64 columns (shift = n / (wg_kc*64) = dy*wg_t + dx).
   int mn_major = 0, wg_t = 0, wg_G = 0, wg_kc = 0;
+  // 16-bit operand formats: bit 0 = the A image holds fp16, bit 1 = the B image holds fp16 (otherwise bf16; single-pass
+  // products only), bit 2 = TC_EMBED writes o_hi as fp16 (no lo / transposed images)
+  int fmt = 0;
 };
 
 // C (+)= A B^T, A (M,K) / B (N,K) row-major bf16 (K % 8 == 0); *_lo non-null selects the split-bf16 x3 product.
@@ -80,6 +83,6 @@ inline int tc_pick_split(int tiles, long kb, int sms = 148) {
 }
 
 int split_bf16(long rows, int cols, const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, __nv_bfloat16* hiT,
-               __nv_bfloat16* loT, cudaStream_t s);
+               __nv_bfloat16* loT, cudaStream_t s, int fp16 = 0);
 
 }  // namespace riqn

@@ -121,8 +121,19 @@ __device__ __forceinline__ uint64_t umma_desc_mn128(uint32_t saddr) {
          ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
 // kind::f16 instruction descriptor: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, K-major both, N>>3 [17,23), M>>4 [24,29)
-__device__ __forceinline__ uint32_t umma_idesc_bf16(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+// (format field: 0 = fp16, 1 = bf16; A and B are independent, so a bf16 gradient can multiply an fp16 activation image)
+__device__ __forceinline__ uint32_t umma_idesc_bf16(int m, int n, int fmt = 0) {
+  return (1u << 4) | ((fmt & 1) ? 0u : (1u << 7)) | ((fmt & 2) ? 0u : (1u << 10)) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(m >> 4) << 24);
+}
+// two floats -> packed 16-bit pair (low half = a), fp16 or bf16
+__device__ __forceinline__ uint32_t pack16x2(float a, float b, bool f16) {
+  if (f16) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+  }
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
 }
 
 // The accumulator arrives with one ROW per lane (tcgen05.ld 32x32b): storing it directly makes every store instruction
@@ -254,6 +265,7 @@ struct TcArgs {
   int strip_t, strip_G, strip_kc, cv_oh, cv_ow, nx_s, nx_G;   // TC_CONV (see gemm.h)
   int mn_major, wg_t, wg_G, wg_kc;                             // MN-major operands / strip weight gradient (gemm.h)
   bf16 *nx_hi, *nx_lo;
+  int fmt;               // bit 0: A image is fp16, bit 1: B image is fp16 (else bf16), bit 2: o_hi is written as fp16
 };
 
 template <int NSPLIT, int EPI, int BN>
@@ -348,7 +360,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (one thread)
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(TBM, TBN);
+      const uint32_t idesc = umma_idesc_bf16(TBM, TBN, p.fmt);
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
@@ -617,17 +629,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
                 const float x1 = f.y * fmaxf(__uint_as_float(v[j + 1]) + bb.y, 0.f);
                 const float x2 = f.z * fmaxf(__uint_as_float(v[j + 2]) + bb.z, 0.f);
                 const float x3 = f.w * fmaxf(__uint_as_float(v[j + 3]) + bb.w, 0.f);
-                // packed conversions: one cvt.rn.bf16x2.f32 per pair, hi recovered with a shift / mask
-                const __nv_bfloat162 h01 = __floats2bfloat162_rn(x0, x1), h23 = __floats2bfloat162_rn(x2, x3);
-                const uint32_t w01 = *reinterpret_cast<const uint32_t*>(&h01), w23 = *reinterpret_cast<const uint32_t*>(&h23);
-                const __nv_bfloat162 l01 = __floats2bfloat162_rn(x0 - __uint_as_float(w01 << 16),
-                                                                 x1 - __uint_as_float(w01 & 0xffff0000u));
-                const __nv_bfloat162 l23 = __floats2bfloat162_rn(x2 - __uint_as_float(w23 << 16),
-                                                                 x3 - __uint_as_float(w23 & 0xffff0000u));
-                hw[j / 2] = w01;
-                hw[j / 2 + 1] = w23;
-                hw[16 + j / 2] = *reinterpret_cast<const uint32_t*>(&l01);
-                hw[16 + j / 2 + 1] = *reinterpret_cast<const uint32_t*>(&l23);
+                if (p.fmt & 4) {      // single fp16 image (11-bit significand): no lo image
+                  hw[j / 2] = pack16x2(x0, x1, true);
+                  hw[j / 2 + 1] = pack16x2(x2, x3, true);
+                  hw[16 + j / 2] = 0u;
+                  hw[16 + j / 2 + 1] = 0u;
+                } else {
+                  // packed conversions: one cvt.rn.bf16x2.f32 per pair, hi recovered with a shift / mask
+                  const __nv_bfloat162 h01 = __floats2bfloat162_rn(x0, x1), h23 = __floats2bfloat162_rn(x2, x3);
+                  const uint32_t w01 = *reinterpret_cast<const uint32_t*>(&h01), w23 = *reinterpret_cast<const uint32_t*>(&h23);
+                  const __nv_bfloat162 l01 = __floats2bfloat162_rn(x0 - __uint_as_float(w01 << 16),
+                                                                   x1 - __uint_as_float(w01 & 0xffff0000u));
+                  const __nv_bfloat162 l23 = __floats2bfloat162_rn(x2 - __uint_as_float(w23 << 16),
+                                                                   x3 - __uint_as_float(w23 & 0xffff0000u));
+                  hw[j / 2] = w01;
+                  hw[j / 2 + 1] = w23;
+                  hw[16 + j / 2] = *reinterpret_cast<const uint32_t*>(&l01);
+                  hw[16 + j / 2 + 1] = *reinterpret_cast<const uint32_t*>(&l23);
+                }
                 v[j] = __float_as_uint(x0); v[j + 1] = __float_as_uint(x1);
                 v[j + 2] = __float_as_uint(x2); v[j + 3] = __float_as_uint(x3);
               }
@@ -785,6 +804,9 @@ int gemm_bf16_tc(int M, int N, int K, const bf16* A_hi, const bf16* A_lo, const 
   if (epi == TC_COL2IM && (ex == nullptr || p.ci_kh * p.ci_kw * p.ci_cin != N || split3 || split2)) return (int)cudaErrorInvalidValue;
   p.o_hi = ex ? ex->o_hi : nullptr; p.o_lo = ex ? ex->o_lo : nullptr;
   p.o_hiT = ex ? ex->o_hiT : nullptr; p.o_loT = ex ? ex->o_loT : nullptr;
+  p.fmt = ex ? ex->fmt : 0;
+  if ((p.fmt & 3) && (split3 || split2)) return (int)cudaErrorInvalidValue;      // fp16 images are single-pass operands
+  if ((p.fmt & 4) && (epi != TC_EMBED || p.o_lo || p.o_hiT || p.o_loT)) return (int)cudaErrorInvalidValue;
   if (epi == TC_EMBED && ((N % 32) || (M % 2))) return (int)cudaErrorInvalidValue;
 #define RIQN_TC_GO(NS, EP) return launch_tc<NS, EP, 256>(ma_hi, ma_lo, mb_hi, mb_lo, p, s)
 #define RIQN_TC_NARROW(NS, EP)                                                                  \
@@ -829,7 +851,7 @@ int gemm_bf16_tc(int M, int N, int K, const bf16* A_hi, const bf16* A_lo, const 
 // ---------------------------------------------------------------------------------------------- operand producers
 // fp32 (rows, cols) -> bf16 hi (+ lo = bf16(x - hi)), optionally also transposed copies (cols, rows).
 __global__ void split_bf16_kernel(long rows, int cols, const float* __restrict__ src, bf16* __restrict__ hi,
-                                  bf16* __restrict__ lo, bf16* __restrict__ hiT, bf16* __restrict__ loT) {
+                                  bf16* __restrict__ lo, bf16* __restrict__ hiT, bf16* __restrict__ loT, int fp16) {
   __shared__ float tile[32][33];
   const long r0 = (long)blockIdx.y * 32;
   const int c0 = blockIdx.x * 32;
@@ -840,6 +862,10 @@ __global__ void split_bf16_kernel(long rows, int cols, const float* __restrict__
     float x = 0.f;
     if (r < rows && c < cols) {
       x = src[r * cols + c];
+      if (fp16) {                       // single fp16 image (host guarantees lo == hiT == NULL)
+        reinterpret_cast<__half*>(hi)[r * cols + c] = __float2half_rn(x);
+        continue;
+      }
       const bf16 h = __float2bfloat16_rn(x);
       if (hi) hi[r * cols + c] = h;
       if (lo) lo[r * cols + c] = __float2bfloat16_rn(x - __bfloat162float(h));
@@ -860,9 +886,10 @@ __global__ void split_bf16_kernel(long rows, int cols, const float* __restrict__
   }
 }
 
-int split_bf16(long rows, int cols, const float* src, bf16* hi, bf16* lo, bf16* hiT, bf16* loT, cudaStream_t s) {
+int split_bf16(long rows, int cols, const float* src, bf16* hi, bf16* lo, bf16* hiT, bf16* loT, cudaStream_t s, int fp16) {
+  if (fp16 && (hi == nullptr || lo != nullptr || hiT != nullptr || loT != nullptr)) return (int)cudaErrorInvalidValue;
   dim3 grid((cols + 31) / 32, (unsigned)((rows + 31) / 32));
-  split_bf16_kernel<<<grid, 256, 0, s>>>(rows, cols, src, hi, lo, hiT, loT);
+  split_bf16_kernel<<<grid, 256, 0, s>>>(rows, cols, src, hi, lo, hiT, loT, fp16);
   return (int)cudaGetLastError();
 }
 
@@ -924,19 +951,20 @@ RIQN_API int riqn_split_bf16_multi(int n_jobs, const riqn_split_job* jobs, void*
   return (int)cudaGetLastError();
 }
 
-RIQN_API int riqn_split_bf16(long rows, int cols, const float* src, void* hi, void* lo, void* hi_t, void* lo_t,
+RIQN_API int riqn_split_bf16(long rows, int cols, const float* src, void* hi, void* lo, void* hi_t, void* lo_t, int fp16,
                              void* stream) {
   riqn::note_launches(1);
-  return split_bf16(rows, cols, src, (bf16*)hi, (bf16*)lo, (bf16*)hi_t, (bf16*)lo_t, (cudaStream_t)stream);
+  return split_bf16(rows, cols, src, (bf16*)hi, (bf16*)lo, (bf16*)hi_t, (bf16*)lo_t, (cudaStream_t)stream, fp16);
 }
 
 RIQN_API int riqn_gemm_bf16_tc(int M, int N, int K, const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo,
                                float* c, long ldc, int epilogue, const float* bias, float* out2, const float* eps,
-                               int split_k, void* c_t_bf16, void* c_bf16, void* stream) {
+                               int split_k, void* c_t_bf16, void* c_bf16, int fmt, void* stream) {
   riqn::note_launches(1);
   TcExtra ex;
   ex.o_hiT = (bf16*)c_t_bf16;
   ex.o_hi = (bf16*)c_bf16;
+  ex.fmt = fmt & 3;
   if (c_bf16 && (epilogue != TC_BIAS_RELU || (M & 1) || (N % 32))) return (int)cudaErrorInvalidValue;
   return gemm_bf16_tc(M, N, K, (const bf16*)a_hi, (const bf16*)a_lo, (const bf16*)b_hi, (const bf16*)b_lo, c, ldc, epilogue,
                       bias, out2, eps, split_k, (cudaStream_t)stream, &ex);
@@ -944,7 +972,7 @@ RIQN_API int riqn_gemm_bf16_tc(int M, int N, int K, const void* a_hi, const void
 
 RIQN_API int riqn_gemm_bf16_tc_mn(int M, int N, int K, const void* a, const void* b_kn, int a_is_km, float* c, long ldc,
                                   int epilogue, float* out2, const float* eps, float alpha, int split_k, void* c_bf16,
-                                  void* stream) {
+                                  int fmt, void* stream) {
   riqn::note_launches(1);
   if (epilogue != TC_STORE && epilogue != TC_ATOMIC && epilogue != TC_NOISY_WGRAD) return (int)cudaErrorInvalidValue;
   if (c_bf16 && (epilogue != TC_STORE || (N % 32))) return (int)cudaErrorInvalidValue;
@@ -952,6 +980,7 @@ RIQN_API int riqn_gemm_bf16_tc_mn(int M, int N, int K, const void* a, const void
   ex.o_hi = (bf16*)c_bf16;
   ex.mn_major = a_is_km ? 3 : 2;
   ex.alpha = alpha;
+  ex.fmt = fmt & 3;
   return gemm_bf16_tc(M, N, K, (const bf16*)a, nullptr, (const bf16*)b_kn, nullptr, c, ldc, epilogue, nullptr, out2, eps,
                       split_k, (cudaStream_t)stream, &ex);
 }

@@ -54,6 +54,8 @@ class Learner(Agent):
         else:
             loss, dtheta, keep, actions = compute_loss_iqn.loss_core(
                 self, states, actions, returns, next_states, nonterminals, keep_graph=True)
+            if getattr(self, "_debug", None) is not None:                       # parity tests: the pass's activations
+                self._debug.update(keep=keep)
             on.zero_grad()                                                      # learner.py:22
             on.backward_iqn(keep, dtheta, weights / weights.shape[0], actions)  # learner.py:23
         return loss

@@ -31,6 +31,9 @@ _ALIGN = 64  # floats; arena groups start on 256-byte boundaries
 # Arithmetic of the hidden NoisyLinear products (x W^T, dh W, dh^T x -- 91% of the step's FLOPs):
 #   "bf16x3": tcgen05 tensor cores, every operand split into bf16 hi + lo, 3 MMAs per k-step (fp32-faithful)
 #   "bf16"  : tcgen05 tensor cores, operands rounded to bf16 once, fp32 accumulation in TMEM
+#   "fp16"  : (forward only) ONE tcgen05 pass on fp16 images of x and W (11-bit significands: the error of a tf32 product
+#             at the bf16 rate; activations / weights of this network sit far inside the fp16 range).  The small products
+#             (conv trunk, quantile embedding: 5% of the FLOPs) keep the split-bf16 x3 arithmetic.
 #   "fp32"  : CUDA-core fp32 GEMM (gemm_simt.cu), the cross-check path
 PRECISION = {"fwd": os.environ.get("RIQN_FWD_PRECISION", "bf16x3"), "bwd": os.environ.get("RIQN_BWD_PRECISION", "bf16")}
 WGRAD_SPLIT_K = int(os.environ.get("RIQN_WGRAD_SPLIT_K", "4"))
@@ -40,9 +43,16 @@ _NO_STRIP = os.environ.get("RIQN_NO_STRIP_CONV", "0") == "1"      # fall back to
 def set_precision(fwd=None, bwd=None):
     for k, v in (("fwd", fwd), ("bwd", bwd)):
         if v is not None:
-            if v not in ("bf16x3", "bf16", "fp32"):
+            if v not in ("bf16x3", "bf16", "fp32") + (("fp16",) if k == "fwd" else ()):
                 raise ValueError(v)
             PRECISION[k] = v
+    if PRECISION["fwd"] == "fp16" and PRECISION["bwd"] != "bf16":
+        raise ValueError("the fp16 forward pairs with the bf16 backward (mixed fp16 x bf16 tensor-core products)")
+
+
+def _small_x3():
+    """Split-bf16 x3 arithmetic for the conv trunk and the embedding product (both memory-bound)."""
+    return PRECISION["fwd"] in ("bf16x3", "fp16")
 
 
 class NoisyLinear(nn.Module):
@@ -329,7 +339,8 @@ class DQN(nn.Module):
         layers = self.noisy_layers()
         fuse = self._fuse_h_images()
         w_hi = getattr(self, "_w_hi", None) if fuse else None
-        key = tuple(m.weight_mu.data_ptr() for _, m in layers) + (self._flat.data_ptr(), w_hi.data_ptr() if fuse else 0)
+        f16 = PRECISION["fwd"] == "fp16"
+        key = tuple(m.weight_mu.data_ptr() for _, m in layers) + (self._flat.data_ptr(), w_hi.data_ptr() if fuse else 0, f16)
         if getattr(self, "_noisy_desc_key", None) != key:
             arr = (NoisyLayer * len(layers))()
             for k, (name, m) in enumerate(layers):
@@ -337,7 +348,8 @@ class DQN(nn.Module):
                     # the composed hidden-layer weights leave the compose kernel as bf16 (hi, lo) images as well
                     row0 = 0 if name == "fcnoisy_h_v" else self.hidden
                     arr[k].w_hi = self._w_hi.data_ptr() + row0 * FEAT * 2
-                    arr[k].w_lo = self._w_lo.data_ptr() + row0 * FEAT * 2
+                    arr[k].w_lo = None if f16 else self._w_lo.data_ptr() + row0 * FEAT * 2
+                    arr[k].w_fp16 = 1 if f16 else 0
                 m._ensure_scratch()
                 d = arr[k]
                 d.out_features, d.in_features = m.out_features, m.in_features
@@ -390,8 +402,9 @@ class DQN(nn.Module):
         dev = self._flat.device
         need_t = PRECISION["bwd"] != "bf16" or PRECISION["fwd"] == "fp32"   # bf16 backward reads W itself (MN-major operand)
         if not h_done:
-            call("riqn_split_bf16", 2 * self.hidden, FEAT, ptr(self._w_eff_h), ptr(self._w_hi), ptr(self._w_lo),
-                 ptr(self._w_hiT) if need_t else None, ptr(self._w_loT) if need_t else None)
+            f16 = PRECISION["fwd"] == "fp16"
+            call("riqn_split_bf16", 2 * self.hidden, FEAT, ptr(self._w_eff_h), ptr(self._w_hi), None if f16 else ptr(self._w_lo),
+                 ptr(self._w_hiT) if need_t else None, ptr(self._w_loT) if need_t else None, 1 if f16 else 0)
         if not (force or getattr(self, "_static_ops_dirty", True)):
             return
         self._static_ops_dirty = False
@@ -479,7 +492,7 @@ class DQN(nn.Module):
         if strip:
             # strip convolution (riqn_conv_fwd_strip): no im2col matrices in the forward; each layer's epilogue writes
             # the next layer's block matrix.  Block grids: G = OH + k/stride - 1 = 21, 10, 9.
-            x3 = fwd == "bf16x3"
+            x3 = _small_x3()
             bf = lambda *sh: torch.empty(*sh, dtype=torch.bfloat16, device=dev)
             ckey = ("s2d", x.data_ptr(), tuple(x.shape), tuple(x.stride()))
             if col_cache is not None and ckey in col_cache:
@@ -528,7 +541,7 @@ class DQN(nn.Module):
                 if bwd_tc:
                     colTs[i] = torch.empty(K, M, dtype=torch.bfloat16, device=dev)
                     px_scale = 1.0 / 255.0
-                call("riqn_conv_fwd_tc_u8", g, ptr(inp), ptr(ws_hi), ptr(ws_lo) if fwd == "bf16x3" else None, ptr(conv.bias),
+                call("riqn_conv_fwd_tc_u8", g, ptr(inp), ptr(ws_hi), ptr(ws_lo) if _small_x3() else None, ptr(conv.bias),
                      ptr(col_px), ptr(colTs[i]), ptr(out), 1 if reuse else 0)
                 if need_col32:
                     cols[i] = torch.empty(M, K, device=dev)
@@ -536,7 +549,7 @@ class DQN(nn.Module):
             else:
                 w_hi, w_lo, _ = self._conv_ops["conv%d" % (i + 1)]
                 col_hi = torch.empty(M, K, dtype=torch.bfloat16, device=dev)
-                col_lo = torch.empty(M, K, dtype=torch.bfloat16, device=dev) if fwd == "bf16x3" else None
+                col_lo = torch.empty(M, K, dtype=torch.bfloat16, device=dev) if _small_x3() else None
                 if bwd_tc:
                     colTs[i] = torch.empty(K, M, dtype=torch.bfloat16, device=dev)
                 call("riqn_conv_fwd_tc", g, ptr(inp), u8, ptr(w_hi), ptr(w_lo), ptr(conv.bias), ptr(col_hi), ptr(col_lo),
@@ -567,14 +580,16 @@ class DQN(nn.Module):
                  ptr(self.iqn_fc.bias), ptr(cosv), ptr(xt))
             if bwd_tc:
                 tc = dict(x_hi=None, x_lo=None, x_hiT=bf(FEAT, R), x_loT=bf(FEAT, R) if bwd == "bf16x3" else None)
-                call("riqn_split_bf16", R, FEAT, ptr(xt), None, None, ptr(tc["x_hiT"]), ptr(tc["x_loT"]))
+                call("riqn_split_bf16", R, FEAT, ptr(xt), None, None, ptr(tc["x_hiT"]), ptr(tc["x_loT"]), 0)
             call("riqn_noisy_linear_fwd", R, FEAT, 2 * hid, ptr(xt), ptr(self._w_eff_h), ptr(self._b_eff_h), ptr(h))
         else:
-            x3 = fwd == "bf16x3"
+            x3 = _small_x3()                                     # embedding product
+            f16 = fwd == "fp16"                                  # head product: one pass on fp16 images
+            head_x3 = fwd == "bf16x3"
             need_x32 = keep is not None and not emb_tc           # the fp32 CUDA-core embedding backward reads x
             # bwd == "bf16": the weight-gradient products read the row-major images (MN-major operands): no transposes
             mn = bwd_tc and bwd == "bf16"
-            tc = dict(x_hi=bf(R, FEAT), x_lo=bf(R, FEAT) if x3 else None,
+            tc = dict(x_hi=bf(R, FEAT), x_lo=bf(R, FEAT) if head_x3 else None, f16=f16,
                       x_hiT=bf(FEAT, R) if (bwd_tc and not mn) else None,
                       x_loT=bf(FEAT, R) if (bwd_tc and bwd == "bf16x3") else None,
                       cos_hi=bf(R, E), cos_lo=bf(R, E) if x3 else None, cosT_hi=None, mn=mn)
@@ -583,13 +598,14 @@ class DQN(nn.Module):
                 cosv = torch.empty(R, E, device=dev)
             call("riqn_quantile_embed_fwd_tc", B, num_quantiles, E, FEAT, ptr(tau), ptr(feat), ptr(self._iqn_ops[0]),
                  ptr(self._iqn_ops[1]), ptr(self.iqn_fc.bias), ptr(tc["cos_hi"]), ptr(tc["cos_lo"]), ptr(tc["cosT_hi"]),
-                 ptr(xt), ptr(tc["x_hi"]), ptr(tc["x_lo"]), ptr(tc["x_hiT"]), ptr(tc["x_loT"]))
+                 ptr(xt), ptr(tc["x_hi"]), ptr(tc["x_lo"]), ptr(tc["x_hiT"]), ptr(tc["x_loT"]), 1 if f16 else 0)
             if need_x32:   # fp32 cos for the CUDA-core dW_e product
                 call("riqn_quantile_embed_fwd", B, num_quantiles, E, FEAT, ptr(tau), ptr(feat), ptr(self.iqn_fc.weight),
                      ptr(self.iqn_fc.bias), ptr(cosv), ptr(xt))
             tc["h_hi"] = bf(R, 2 * hid) if (bwd_tc and R % 2 == 0) else None   # bf16 image of h for the z-layer weight gradient
             call("riqn_gemm_bf16_tc", R, 2 * hid, FEAT, ptr(tc["x_hi"]), ptr(tc["x_lo"]), ptr(self._w_hi),
-                 ptr(self._w_lo) if x3 else None, ptr(h), 2 * hid, 1, ptr(self._b_eff_h), None, None, 1, None, ptr(tc["h_hi"]))
+                 ptr(self._w_lo) if head_x3 else None, ptr(h), 2 * hid, 1, ptr(self._b_eff_h), None, None, 1, None, ptr(tc["h_hi"]),
+                 3 if f16 else 0)
         q = torch.empty(R, A, device=dev)
         call("riqn_dueling_fwd", R, B, hid, A, ptr(h), ptr(self._w_eff_z), ptr(self._b_eff_z), ptr(q))
         if keep is not None:
@@ -625,6 +641,7 @@ class DQN(nn.Module):
         gv = self.grad_view
         dz = torch.empty(R, 32, device=dev)
         tc = keep.get("tc")
+        fmt_b = 2 if (tc and tc.get("f16")) else 0          # the forward's x / W images are fp16: mixed bf16 x fp16 products
         z_tc = bool(keep["head_bwd_tc"]) and tc is not None and tc.get("h_hi") is not None
         dzT = torch.empty(R, 32, dtype=torch.bfloat16, device=dev) if z_tc else None       # (R, 32) row-major bf16 image
         dbs = torch.empty(2 * hid, device=dev)
@@ -666,31 +683,31 @@ class DQN(nn.Module):
             dh_lo, dh_loT = (bf(R, 2 * hid), bf(2 * hid, R)) if b3 else (None, None)
             if not fused_dh:
                 dh_hi, dh_hiT = bf(R, 2 * hid), bf(2 * hid, R)
-                call("riqn_split_bf16", R, 2 * hid, ptr(dh), ptr(dh_hi), ptr(dh_lo), ptr(dh_hiT), ptr(dh_loT))
+                call("riqn_split_bf16", R, 2 * hid, ptr(dh), ptr(dh_hi), ptr(dh_lo), ptr(dh_hiT), ptr(dh_loT), 0)
             # dW[o, i] = sum_r dh[r, o] x[r, i]  -> dmu += dW, dsigma += dW * eps   (split-K, atomics)
             if fused_dh:
                 call("riqn_gemm_bf16_tc_mn", 2 * hid, FEAT, R, ptr(dh_hi), ptr(tc["x_hi"]), 1, ptr(gv(hv.weight_mu)), FEAT, 3,
-                     ptr(gv(hv.weight_sigma)), ptr(hv.weight_epsilon), 1.0, WGRAD_SPLIT_K, None)
+                     ptr(gv(hv.weight_sigma)), ptr(hv.weight_epsilon), 1.0, WGRAD_SPLIT_K, None, fmt_b)
             else:
                 call("riqn_gemm_bf16_tc", 2 * hid, FEAT, R, ptr(dh_hiT), ptr(dh_loT), ptr(tc["x_hiT"]),
                      ptr(tc["x_loT"]) if b3 else None, ptr(gv(hv.weight_mu)), FEAT, 3, None, ptr(gv(hv.weight_sigma)),
-                     ptr(hv.weight_epsilon), WGRAD_SPLIT_K, None, None)
+                     ptr(hv.weight_epsilon), WGRAD_SPLIT_K, None, None, 0)
             call("riqn_noisy_bias_grad", R, 2 * hid, ptr(dh) if dh is not None else None, ptr(hv.bias_epsilon), ptr(dbs),
                  ptr(gv(hv.bias_mu)), ptr(gv(hv.bias_sigma)))
             # dx[r, i] = sum_o dh[r, o] W_eff[o, i]
             if fused_dh:     # W_eff (2*hid, 3136) itself is the (K, N) operand: no transposed weight image
                 call("riqn_gemm_bf16_tc_mn", R, FEAT, 2 * hid, ptr(dh_hi), ptr(self._w_hi), 0, None if dx_bf16 else ptr(dx), FEAT,
-                     0, None, None, 1.0, 1, ptr(dx) if dx_bf16 else None)
+                     0, None, None, 1.0, 1, ptr(dx) if dx_bf16 else None, fmt_b)
             else:
                 call("riqn_gemm_bf16_tc", R, FEAT, 2 * hid, ptr(dh_hi), ptr(dh_lo), ptr(self._w_hiT),
-                     ptr(self._w_loT) if b3 else None, ptr(dx), FEAT, 0, None, None, None, 1, None, None)
+                     ptr(self._w_loT) if b3 else None, ptr(dx), FEAT, 0, None, None, None, 1, None, None, 0)
         dfeat = torch.empty(B, FEAT, device=dev)
         if keep["emb_bwd_tc"]:
             dpre = torch.empty(R, FEAT, dtype=torch.bfloat16, device=dev)
             # bf16 backward: x = x_hi (the lo image only refines the forward)
             call("riqn_quantile_embed_bwd_tc", B, Nq, E, FEAT, ptr(tc["x_hi"]), None if dx_bf16 else ptr(tc["x_lo"]),
                  ptr(keep["feat"]), ptr(tc["cos_hi"]), ptr(dx), 1 if dx_bf16 else 0, ptr(dpre), ptr(dfeat),
-                 ptr(gv(self.iqn_fc.weight)), ptr(gv(self.iqn_fc.bias)))
+                 ptr(gv(self.iqn_fc.weight)), ptr(gv(self.iqn_fc.bias)), 1 if fmt_b else 0)
         else:
             call("riqn_quantile_embed_bwd", B, Nq, E, FEAT, ptr(keep["xt"]), ptr(keep["feat"]), ptr(keep["cos"]), ptr(dx),
                  ptr(dfeat), ptr(gv(self.iqn_fc.weight)), ptr(gv(self.iqn_fc.bias)))

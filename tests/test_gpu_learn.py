@@ -65,31 +65,47 @@ def test_learn_matches_reference_golden(cuda_dev, golden_dir, name):
     g = np.load(os.path.join(golden_dir, name + ".npz"))
     seed, batch, steps = int(g["seed"]), int(g["batch"]), int(g["steps"])
     cfg = _cfg(g)
-    lr = _learner(cuda_dev, batch, cfg, net.make_params(seed))
+    params_np = net.make_params(seed)
+    lr = _learner(cuda_dev, batch, cfg, params_np)
+    p_or = net.to_torch(params_np)
     for s in range(steps):
         b = cases.make_batch(seed + 10 + s, batch, n_step=cfg["n_step"], discount=cfg["discount"])
         taus = tuple(torch.from_numpy(t) for t in cases.make_taus(seed + 20 + s, batch, cfg))
         lr._inject = dict(noises=cases.make_noises(seed + 30 + s), taus=taus)
         st, ac, rt, nx, nt = _dev_batch(b, cuda_dev, fp32_frames=(s == 1))
         w = torch.from_numpy(b["weights"]).to(cuda_dev)
+        lr._debug = {}
         idxs, loss = lr.learn(FakeMem((np.arange(batch), st, ac, rt, nx, nt, w)), None)
         assert rel_err(loss.cpu().numpy(), g[f"loss_{s}"]) < LOSS_TOL
         assert np.max(np.abs(loss.cpu().numpy() - g[f"loss_{s}"]) / np.abs(g[f"loss_{s}"])) < 1e-3  # per transition
+        # ReLU kinks: with 4..32 samples a single pre-activation that rounds to opposite sides of 0 on the CPU and the
+        # GPU moves the conv1/conv2 gradients by percents.  Count them against the oracle's activations (the oracle
+        # equals the reference on these inputs -- asserted by make_golden.py): no flip -> the tight tolerance holds for
+        # every parameter; k flips -> the parameters upstream of them get 5% each.
+        keep_o = {}
+        with torch.no_grad():
+            losses.iqn_loss(p_or, net.to_torch(params_np), *cases.batch_to_torch(b), lr._inject["noises"],
+                            lr._inject["taus"], **cfg, keep=keep_o)
+        gk = lr._debug["keep"]
+        fl = [int(((a.cpu() > 0) != (b_ > 0)).sum()) for a, b_ in ((gk["out"][0], keep_o["o1"]), (gk["out"][1], keep_o["o2"]),
+                                                                   (gk["out"][2], keep_o["o3"]))]
+        upstream = {"conv1": sum(fl), "conv2": fl[1] + fl[2], "conv3": fl[2]}
         for k, p in lr.online_net.named_parameters():
             gd = digest(p.grad)
             ref = g[f"grad_{s}_{k}"]
-            # ReLU kinks: with 4..32 samples a single pre-activation that rounds to opposite sides of 0 on the
-            # CPU and the GPU moves the conv1/conv2 gradients by percents (iqn_small step 1 has exactly one such
-            # element in conv2's output; everything downstream of it stays at 1e-7).  Trunk tolerances allow
-            # for one flip; every other parameter is held to 1e-3.
-            gtol = 5e-2 if k.startswith(("conv1", "conv2")) else _grad_tol()
-            assert abs(gd[2] - ref[2]) <= gtol * ref[2] + 1e-9, (k, gd[:3], ref[:3])       # l2 norm
-            assert np.allclose(gd[3:], ref[3:], rtol=2 * gtol, atol=2 * gtol * ref[2] / np.sqrt(p.numel()) + 1e-9), k
+            nfl = upstream.get(k.split(".")[0], 0)
+            gtol = _grad_tol() if nfl == 0 else min(0.25, 5e-2 * nfl)
+            assert abs(gd[2] - ref[2]) <= gtol * ref[2] + 1e-9, (k, gd[:3], ref[:3], fl)       # l2 norm
+            assert np.allclose(gd[3:], ref[3:], rtol=2 * gtol, atol=2 * gtol * ref[2] / np.sqrt(p.numel()) + 1e-9), (k, fl)
             pd, pref = digest(p), g[f"param_{s}_{k}"]
-            if gtol > 1e-3:   # trunk: l2 norm and leading elements (signed sums amplify a kink flip)
+            if nfl or k.startswith(("conv1", "conv2")):   # l2 norm and leading elements (Adam's normalisation amplifies
+                # tiny-gradient elements of the signed sums)
                 assert np.allclose(pd[2:], pref[2:], rtol=1e-5, atol=5e-6), k
             else:
                 assert np.allclose(pd, pref, rtol=1e-5, atol=1e-6), k
+        # the oracle's parameters follow the reference's (param digests above): advance them for the next step's flip count
+        for k, p in lr.online_net.named_parameters():
+            p_or[k] = p.detach().cpu().clone()
 
 
 def _qmajor(t, batch):

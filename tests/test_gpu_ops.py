@@ -245,7 +245,7 @@ def test_split_bf16_multi_matches_single_calls(cuda_dev):
         if div != 1.0:
             call("riqn_split_bf16_scaled", src.shape[0], src.shape[1], ptr(sp), div, ptr(rh), ptr(rl))
         else:
-            call("riqn_split_bf16", src.shape[0], src.shape[1], ptr(sp), ptr(rh), ptr(rl), None, None)
+            call("riqn_split_bf16", src.shape[0], src.shape[1], ptr(sp), ptr(rh), ptr(rl), None, None, 0)
         assert torch.equal(hi, rh) and torch.equal(lo, rl)
         if hiT is not None:
             assert torch.equal(hiT, rh.t().contiguous())

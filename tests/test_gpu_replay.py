@@ -79,7 +79,9 @@ def test_replay_matches_reference_golden(cuda_dev, golden_dir, name):
         assert float(tr.max_priority.item()) == float(g[f"max_priority_{r}"])
 
 
-@pytest.mark.parametrize("cap,nb,batch", [(1 << 14, 1, 512), (5000, 3, 640), (1000, 7, 2560), (37, 1, 5)])
+@pytest.mark.parametrize("cap,nb,batch", [(1 << 14, 1, 512), (5000, 3, 640), (1000, 7, 2560), (37, 1, 5),
+                                          (1 << 19, 1, 2560),      # the benchmarked shard, B*queue_size draws
+                                          (500000, 1, 2560)])      # config-4 shard size: leaves at two depths
 def test_tree_random_vs_oracle(cuda_dev, cap, nb, batch):
     """Random append / sample / update rounds, pow2 and non-pow2 capacities, duplicates, write-head shifts."""
     rs = np.random.RandomState(cap + nb)

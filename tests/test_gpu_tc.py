@@ -22,15 +22,15 @@ def _run(dev, M, N, K, split3, epi=0, split_k=1, seed=0):
     b_hi = torch.empty(N, K, dtype=torch.bfloat16, device=dev)
     a_lo = torch.empty_like(a_hi) if split3 else None
     b_lo = torch.empty_like(b_hi) if split3 else None
-    call("riqn_split_bf16", M, K, ptr(a), ptr(a_hi), ptr(a_lo), None, None)
-    call("riqn_split_bf16", N, K, ptr(b), ptr(b_hi), ptr(b_lo), None, None)
+    call("riqn_split_bf16", M, K, ptr(a), ptr(a_hi), ptr(a_lo), None, None, 0)
+    call("riqn_split_bf16", N, K, ptr(b), ptr(b_hi), ptr(b_lo), None, None, 0)
     assert np.array_equal(a_hi.float().cpu().numpy(), _bf16_round(A))
     bias = torch.from_numpy(rs.standard_normal(N).astype(np.float32)).to(dev)
     c = torch.zeros(M, N, device=dev)
     eps = torch.from_numpy(rs.standard_normal((M, N)).astype(np.float32)).to(dev)
     c2 = torch.zeros(M, N, device=dev)
     call("riqn_gemm_bf16_tc", M, N, K, ptr(a_hi), ptr(a_lo), ptr(b_hi), ptr(b_lo), ptr(c), N, epi, ptr(bias), ptr(c2),
-         ptr(eps), split_k, None, None)
+         ptr(eps), split_k, None, None, 0)
     torch.cuda.synchronize()
     if split3:
         ref = A.astype(np.float64) @ B.astype(np.float64).T
@@ -82,7 +82,7 @@ def _run_mn(dev, M, N, K, epi=0, split_k=1, alpha=1.0, seed=0, a_is_km=1):
     c = torch.from_numpy(c0).to(dev)
     eps = torch.from_numpy(rs.standard_normal((M, N)).astype(np.float32)).to(dev)
     c2 = torch.zeros(M, N, device=dev)
-    call("riqn_gemm_bf16_tc_mn", M, N, K, ptr(a), ptr(b), a_is_km, ptr(c), N, epi, ptr(c2), ptr(eps), alpha, split_k, None)
+    call("riqn_gemm_bf16_tc_mn", M, N, K, ptr(a), ptr(b), a_is_km, ptr(c), N, epi, ptr(c2), ptr(eps), alpha, split_k, None, 0)
     torch.cuda.synchronize()
     prod = (A.astype(np.float64).T if a_is_km else A.astype(np.float64)) @ B.astype(np.float64)
     ref = prod if epi == 0 else c0 + alpha * prod
@@ -106,10 +106,39 @@ def test_tc_gemm_mn_major(cuda_dev):
     A, B = _bf16_round(rs.standard_normal((300, 1024)).astype(np.float32)), _bf16_round(rs.standard_normal((1024, 3136)).astype(np.float32) * 0.05)
     a, b = torch.from_numpy(A).to(cuda_dev).to(torch.bfloat16), torch.from_numpy(B).to(cuda_dev).to(torch.bfloat16)
     cb = torch.zeros(300, 3136, dtype=torch.bfloat16, device=cuda_dev)
-    call("riqn_gemm_bf16_tc_mn", 300, 3136, 1024, ptr(a), ptr(b), 0, None, 3136, 0, None, None, 1.0, 1, ptr(cb))
+    call("riqn_gemm_bf16_tc_mn", 300, 3136, 1024, ptr(a), ptr(b), 0, None, 3136, 0, None, None, 1.0, 1, ptr(cb), 0)
     torch.cuda.synchronize()
     ref = A.astype(np.float64) @ B.astype(np.float64)
     assert rel_err(cb.float().cpu().numpy(), ref) < 4e-3          # one bf16 rounding of the result
+
+
+@pytest.mark.parametrize("fmt", [1, 2, 3])
+def test_tc_gemm_fp16_and_mixed_formats(cuda_dev, fmt):
+    """tcgen05 kind::f16 takes the A and B formats independently: fp16 x fp16 (the single-pass head forward) and
+    bf16 x fp16 (backward: a bf16 gradient times the forward's fp16 activation / weight image), K-major and MN-major."""
+    from rainbow_iqn_apex_b200._lib import call, ptr
+    rs = np.random.RandomState(40 + fmt)
+    dta = torch.float16 if fmt & 1 else torch.bfloat16
+    dtb = torch.float16 if fmt & 2 else torch.bfloat16
+    M, N, K = 300, 1024, 3136
+    a = torch.from_numpy(rs.standard_normal((M, K)).astype(np.float32)).to(cuda_dev).to(dta)
+    b = torch.from_numpy((rs.standard_normal((N, K)) * 0.05).astype(np.float32)).to(cuda_dev).to(dtb)
+    bias = torch.from_numpy(rs.standard_normal(N).astype(np.float32)).to(cuda_dev)
+    c = torch.zeros(M, N, device=cuda_dev)
+    call("riqn_gemm_bf16_tc", M, N, K, ptr(a), None, ptr(b), None, ptr(c), N, 1, ptr(bias), None, None, 1, None, None, fmt)
+    ref = np.maximum(a.float().cpu().numpy().astype(np.float64) @ b.float().cpu().numpy().astype(np.float64).T
+                     + bias.cpu().numpy(), 0)
+    assert rel_err(c.cpu().numpy(), ref) < 1e-5, fmt
+    # MN-major B (K, N): dX = dY W and dW = dY^T X with the second operand in the other format
+    for a_is_km in (0, 1):
+        Mm, Nn, Kk = (300, 3136, 1024) if not a_is_km else (1024, 3136, 512)
+        a2 = torch.from_numpy(rs.standard_normal((Kk, Mm) if a_is_km else (Mm, Kk)).astype(np.float32)).to(cuda_dev).to(dta)
+        b2 = torch.from_numpy((rs.standard_normal((Kk, Nn)) * 0.05).astype(np.float32)).to(cuda_dev).to(dtb)
+        c2 = torch.zeros(Mm, Nn, device=cuda_dev)
+        call("riqn_gemm_bf16_tc_mn", Mm, Nn, Kk, ptr(a2), ptr(b2), a_is_km, ptr(c2), Nn, 0, None, None, 1.0, 1, None, fmt)
+        af = a2.float().cpu().numpy().astype(np.float64)
+        ref2 = (af.T if a_is_km else af) @ b2.float().cpu().numpy().astype(np.float64)
+        assert rel_err(c2.cpu().numpy(), ref2) < 1e-5, (fmt, a_is_km)
 
 
 def _strip_layers():
@@ -156,7 +185,7 @@ def test_strip_convolution_forward_and_backward(cuda_dev, batch):
         if i == 0:
             call("riqn_split_bf16_scaled", cout, K, ptr(wp), 255.0, ptr(w_hi), ptr(w_lo))
         else:
-            call("riqn_split_bf16", cout, K, ptr(wp), ptr(w_hi), ptr(w_lo), None, None)
+            call("riqn_split_bf16", cout, K, ptr(wp), ptr(w_hi), ptr(w_lo), None, None, 0)
         w_ops.append((wp, w_hi, w_lo))
         out = torch.zeros(batch, cout, gm.OH, gm.OH, device=dev)
         bd = b.to(dev)
@@ -184,7 +213,7 @@ def test_strip_convolution_forward_and_backward(cuda_dev, batch):
         K = cin * k * k
         G = grids[i]
         w_hi_orig = bf(cout, K)
-        call("riqn_split_bf16", cout, K, ptr(ws[i].reshape(cout, K).contiguous().to(dev)), ptr(w_hi_orig), None, None, None)
+        call("riqn_split_bf16", cout, K, ptr(ws[i].reshape(cout, K).contiguous().to(dev)), ptr(w_hi_orig), None, None, None, 0)
         dYg = bf(batch * G * G, cout)
         dwp = torch.zeros(cout, K, device=dev)
         dw = torch.zeros(cout, K, device=dev)

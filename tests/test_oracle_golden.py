@@ -5,7 +5,7 @@ import os
 import numpy as np
 import torch
 
-from oracle import cases, losses, network as net, replay as oreplay, sumtree as osum
+from oracle import actor as oactor, cases, losses, network as net, replay as oreplay, sumtree as osum
 
 
 def _cfg(g):
@@ -123,3 +123,34 @@ def test_tree_edge_cases():
     assert abs(t.tree[0] - (1.0 + 10.0 + 3.0)) < 1e-12
     idx = t.retrieve(np.array([0.0, 0.5, 1.0, 1.0001, 13.9999]))
     assert list(idx) == [7, 7, 7, 8, 9]
+
+
+def actor_case(g):
+    """Inputs of the actor fixture (shared with the GPU test): buffer lists, per-chunk noises / taus, cfg."""
+    cfg = _cfg(g)
+    seed, bs, lb = int(g["seed"]), int(g["batch_size"]), int(g["len_buffer"])
+    frames = g["frames"]
+    tab_state = [frames[i] for i in range(len(frames))]
+    tab_action = [int(a) for a in g["tab_action"]]
+    tab_reward = [float(r) for r in g["tab_reward"]]
+    tab_nonterminal = [bool(x) for x in g["tab_nonterminal"]]
+    n_chunks = -(-(lb - cfg["n_step"]) // bs)
+    noises = [cases.make_noises(seed + 100 + c) for c in range(n_chunks)]
+    taus = [tuple(torch.from_numpy(g[f"tau_{c}_{k}"]) for k in range(3)) for c in range(n_chunks)]
+    return cfg, seed, bs, tab_state, tab_action, tab_reward, tab_nonterminal, noises, taus
+
+
+def test_actor_small_matches_reference(golden_dir):
+    """Actor.act + Actor.compute_priorities + the max_priority tail rule against the recorded reference outputs."""
+    g = np.load(os.path.join(golden_dir, "actor_small.npz"))
+    cfg, seed, bs, tab_state, tab_action, tab_reward, tab_nonterminal, noises, taus = actor_case(g)
+    params = net.make_params(seed)
+    p_on = net.apply_noise(net.to_torch(params), net.make_noise(seed + 1))
+    a, q_mean = oactor.act(p_on, tab_state[:4], cfg["n_quantile"], torch.from_numpy(g["act_tau"]))
+    assert a == int(g["act_action"]) and np.allclose(q_mean.numpy(), g["act_q_mean"], rtol=1e-5, atol=1e-6)
+    pri = oactor.compute_priorities(net.to_torch(params), net.to_torch(params), tab_state, tab_action, tab_reward,
+                                    tab_nonterminal, 0.2, noises, taus, cfg, bs)
+    assert pri.shape == (int(g["len_buffer"]) - cfg["n_step"],)
+    assert np.allclose(pri, g["priorities"], rtol=1e-5, atol=0)
+    fl = oactor.flush_priorities(g["priorities"], 1.25, cfg["n_step"])
+    assert np.array_equal(fl, g["flushed"]) and np.all(fl[-cfg["n_step"]:] == 1.25)

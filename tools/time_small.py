@@ -7,7 +7,7 @@ def bf(*s): return torch.randn(*s, device=dev).to(torch.bfloat16)
 def run(M, N, K, reps=50):
     a, b = bf(M, K), bf(N, K)
     c = torch.zeros(M, N, device=dev)
-    go = lambda: call("riqn_gemm_bf16_tc", M, N, K, ptr(a), None, ptr(b), None, ptr(c), N, 0, None, None, None, 1, None, None)
+    go = lambda: call("riqn_gemm_bf16_tc", M, N, K, ptr(a), None, ptr(b), None, ptr(c), N, 0, None, None, None, 1, None, None, 0)
     for _ in range(5): go()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     g = torch.cuda.CUDAGraph()
