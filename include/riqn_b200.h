@@ -157,7 +157,7 @@ typedef struct riqn_noisy_layer {
   unsigned long long stream_in, stream_out;      /* Philox stream ids of the two draws */
   void* w_hi;                                    /* (out, in) bf16 image of w_eff for the tensor-core products, or NULL */
   void* w_lo;                                    /* (out, in) bf16(w_eff - hi), or NULL */
-  int w_fp16;                                    /* != 0: w_hi receives ONE fp16 image (w_lo ignored) -- fp16 head forward */
+  int w_fp16;                                    /* != 0: w_hi = fp16(w_eff), w_lo (or NULL) = bf16(w_eff) -- fp16 head forward */
 } riqn_noisy_layer;
 
 /* DQN.reset_noise() for all NoisyLinear layers of one network in two launches (model.py:159-162 -> :39-43 -> :32-37):
@@ -202,22 +202,22 @@ int riqn_quantile_embed_bwd(int batch, int num_quantiles, int embed_dim, int fea
 
 /* Tensor-core variants.  Forward: the tcgen05 GEMM's epilogue applies relu / bias / the Hadamard with feat and writes
  * the bf16 operand images of x directly: x_hi, x_lo (rows, feat_dim) for the NoisyLinear product, x_hi_t / x_lo_t
- * (feat_dim, rows) for its weight gradient (each may be NULL); x32 (may be NULL) is the fp32 matrix.  cos_hi / cos_lo
+ * (feat_dim, rows) for its weight gradient in the cross-check arithmetic modes (each may be NULL; the transposed images
+ * are split from x32 by a second launch and therefore need x32 != NULL); x32 (may be NULL) is the fp32 matrix.  cos_hi / cos_lo
  * (rows, embed_dim) and cos_t_hi (embed_dim, rows; may be NULL) are outputs too.  cos_lo == NULL selects the
  * single-bf16 product.  iqn_w_hi / iqn_w_lo: bf16 images of iqn_fc.weight (riqn_split_bf16). */
 int riqn_quantile_embed_fwd_tc(int batch, int num_quantiles, int embed_dim, int feat_dim, const float* tau,
                                const float* feat, const void* iqn_w_hi, const void* iqn_w_lo, const float* iqn_b,
                                void* cos_hi, void* cos_lo, void* cos_t_hi, float* x32, void* x_hi, void* x_lo, void* x_hi_t,
                                void* x_lo_t, int x_fp16, void* stream);
-/* x_fp16 != 0: x_hi receives ONE fp16 image of x (x_lo / x_hi_t / x_lo_t must be NULL): the operand of the single-pass fp16
- * head product (same tensor-core rate as bf16, 11-bit significand). */
+/* x_fp16 != 0: x_hi = fp16(x), the operand of the single-pass fp16 head product (same tensor-core rate as bf16, 11-bit
+ * significand), and x_lo (or NULL) = bf16(x), the operand of the bf16 backward; x_hi_t / x_lo_t must be NULL. */
 /* Backward on bf16 operands (rows % 8 == 0): dx (rows, feat_dim) from the head dgrad, fp32 or (dx_is_bf16 != 0) bf16;
  * x_lo may be NULL (x = x_hi); cos_hi (rows, embed_dim) bf16 row-major (the forward's image); dpre (rows, feat_dim) bf16
  * workspace; dfeat overwritten; grad_iqn_w / grad_iqn_b accumulated. */
 int riqn_quantile_embed_bwd_tc(int batch, int num_quantiles, int embed_dim, int feat_dim, const void* x_hi, const void* x_lo,
                                const float* feat, const void* cos_hi, const void* dx, int dx_is_bf16, void* dpre,
-                               float* dfeat, float* grad_iqn_w, float* grad_iqn_b, int x_fp16, void* stream);
-/* x_fp16 != 0: x_hi is the fp16 image written by riqn_quantile_embed_fwd_tc(x_fp16 = 1) (needs dx_is_bf16, x_lo == NULL). */
+                               float* dfeat, float* grad_iqn_w, float* grad_iqn_b, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * z-layers + dueling aggregation                          replaces rainbowiqn/model.py:153-156
@@ -354,7 +354,7 @@ int riqn_frame_gather(int batch, int actor_capacity, int history, int n_step, co
 /* fp32 (rows, cols) -> bf16 hi and lo = bf16(x - hi) (either may be NULL); hi_t / lo_t (may be NULL) receive the
  * transposed (cols, rows) copies the weight-gradient product consumes. */
 int riqn_split_bf16(long rows, int cols, const float* src, void* hi, void* lo, void* hi_t, void* lo_t, int fp16, void* stream);
-/* fp16 != 0: hi receives ONE fp16 image instead (lo / hi_t / lo_t must be NULL). */
+/* fp16 != 0: hi = fp16(x) and lo (or NULL) = bf16(x) instead (hi_t / lo_t must be NULL). */
 /* Several small splits in ONE launch (the per-step refresh of the noise-free weight images): for each job
  * out[r, c] = src[r, perm ? perm[c] : c] / div (div == 1: unscaled), written as hi / lo = bf16(x - hi) (lo, hi_t may be
  * NULL; hi_t is the transposed (cols, rows) hi image).  Same values as riqn_split_bf16 / riqn_split_bf16_scaled on a
@@ -376,8 +376,8 @@ int riqn_split_bf16_multi(int n_jobs, const riqn_split_job* jobs, void* stream);
 int riqn_gemm_bf16_tc(int M, int N, int K, const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo,
                       float* c, long ldc, int epilogue, const float* bias, float* out2, const float* eps, int split_k,
                       void* c_t_bf16, void* c_bf16, int fmt, void* stream);
-/* fmt (both GEMM entry points): bit 0 = the A image holds fp16, bit 1 = the B image holds fp16, otherwise bf16 (tcgen05
- * kind::f16 takes the two formats independently); fp16 images are single-pass operands (a_lo == b_lo == NULL). */
+/* fmt (both GEMM entry points): 0 = both operand images hold bf16, 3 = both hold fp16 (single-pass: a_lo == b_lo == NULL).
+ * 1 / 2 (mixed) are rejected: tcgen05 kind::f16 raises an illegal-instruction fault when A and B formats differ. */
 /* Products whose B operand is (K, N) row-major bf16 (MN-major tcgen05 operand, N % 8 == 0) -- no transposed copies:
  *   a_is_km != 0: C (+)= A^T B with A (K, M) row-major (M % 8 == 0): the reduction runs over the ROWS of both, i.e. a
  *                 weight gradient dW = dY^T X straight from the row-major activations;

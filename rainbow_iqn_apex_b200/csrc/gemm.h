@@ -55,8 +55,8 @@ struct TcExtra {
   // wg_t > 0 additionally applies the strip-convolution shifts to B: column n = (shift, within-block) reads the rows
   // k + dy*wg_G + dx of a block matrix with wg_kc*64 columns (shift = n / (wg_kc*64) = dy*wg_t + dx).
   int mn_major = 0, wg_t = 0, wg_G = 0, wg_kc = 0;
-  // 16-bit operand formats: bit 0 = the A image holds fp16, bit 1 = the B image holds fp16 (otherwise bf16; single-pass
-  // products only), bit 2 = TC_EMBED writes o_hi as fp16 (no lo / transposed images)
+  // 16-bit operand formats: 0 = both operand images bf16, 3 = both fp16 (single-pass products only; mixing the two is an
+  // illegal instruction), bit 2 = TC_EMBED writes o_hi as fp16(x) and o_lo (optional) as bf16(x) instead of hi / residual
   int fmt = 0;
 };
 

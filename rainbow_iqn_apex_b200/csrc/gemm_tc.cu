@@ -121,7 +121,8 @@ __device__ __forceinline__ uint64_t umma_desc_mn128(uint32_t saddr) {
          ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
 // kind::f16 instruction descriptor: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, K-major both, N>>3 [17,23), M>>4 [24,29)
-// (format field: 0 = fp16, 1 = bf16; A and B are independent, so a bf16 gradient can multiply an fp16 activation image)
+// (format field: 0 = fp16, 1 = bf16.  The descriptor has separate A / B fields, but a product that MIXES them is an
+  // illegal instruction on sm_100a (measured, round 2): both operands must share the format -> fmt is 0 or 3)
 __device__ __forceinline__ uint32_t umma_idesc_bf16(int m, int n, int fmt = 0) {
   return (1u << 4) | ((fmt & 1) ? 0u : (1u << 7)) | ((fmt & 2) ? 0u : (1u << 10)) | ((uint32_t)(n >> 3) << 17) |
          ((uint32_t)(m >> 4) << 24);
@@ -261,7 +262,7 @@ struct TcArgs {
   const float* feat;     // TC_EMBED: (samples, N) conv features, row m uses feat[m / batch] (batch = rows per sample)
   int batch;
   bf16 *o_hi, *o_lo;     // TC_EMBED: bf16 hi / lo images of the result, row-major (M, N)   (may be null)
-  bf16 *o_hiT, *o_loT;   // TC_EMBED: transposed (N, M) images                              (may be null)
+  bf16 *o_hiT, *o_loT;   // TC_BIAS_RELU: transposed (N, M) bf16 image of the result          (may be null)
   int strip_t, strip_G, strip_kc, cv_oh, cv_ow, nx_s, nx_G;   // TC_CONV (see gemm.h)
   int mn_major, wg_t, wg_G, wg_kc;                             // MN-major operands / strip weight gradient (gemm.h)
   bf16 *nx_hi, *nx_lo;
@@ -417,34 +418,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
       const uint32_t aphase = (local >> 1) & 1;
       const int m = mt * TBM + quarter * 32 + lane;
       constexpr int HALF = TBN >= 64 ? TBN / 2 : TBN;        // BN = 32: the second warp set has no columns to drain
+      // embedding epilogue: the Hadamard / bias math runs AFTER the staging transpose, where lane l owns the 4 columns of
+      // piece (l & 7) for the rows r0 + (l >> 3): one 16-byte feat load and one bias load per 32-column chunk instead of
+      // sixteen broadcast loads per thread (round 1: those loads were 60% of the kernel's LSU wavefronts)
+      const int e_piece = lane & 7, e_sub = lane >> 3;
+      const int e_mbase = mt * TBM + quarter * 32;
+      const bool e_one_sample = (p.batch & 31) == 0;          // sample-major rows: a warp's 32 rows share one feature row
       const float* embed_feat_row = nullptr;
-      if (EPI == TC_EMBED) {
-        embed_feat_row = p.feat + (long)((m < p.M ? m : 0) / p.batch) * p.N;
-        const int nf = nt * TBN + chalf * HALF;                // first chunk's feat / bias lines -> L1 while the MMA finishes
-        if (nf + 32 <= p.N) {
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(embed_feat_row + nf));
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(p.bias + nf));
-        }
-      }
+      if (EPI == TC_EMBED) embed_feat_row = p.feat + (long)((e_mbase < p.M ? e_mbase : 0) / p.batch) * p.N;
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * TBN;
 #pragma unroll 1
       for (int c = chalf * HALF; c < (chalf + 1) * HALF && c < TBN; c += 32) {
         const int n0 = nt * TBN + c;
-        if (EPI == TC_EMBED && c + 32 < (chalf + 1) * HALF && n0 + 64 <= p.N) {   // next chunk's feat / bias lines -> L1
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(embed_feat_row + n0 + 32));
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(p.bias + n0 + 32));
-        }
-        // embedding epilogue: this chunk's feat / bias values are requested BEFORE the accumulator load, so that
-        // their latency overlaps the TMEM read instead of following it
-        float4 ef[8], eb[8];
+        // this chunk's feat / bias values are requested BEFORE the accumulator load: their latency overlaps the TMEM read
+        float4 ef = make_float4(0.f, 0.f, 0.f, 0.f), eb = ef;
         if (EPI == TC_EMBED && n0 + 32 <= p.N) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            ef[j] = __ldg(reinterpret_cast<const float4*>(embed_feat_row + n0) + j);
-            eb[j] = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j);
-          }
+          eb = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + e_piece);
+          if (e_one_sample) ef = __ldg(reinterpret_cast<const float4*>(embed_feat_row + n0) + e_piece);
         }
         uint32_t v[32];
         tmem_ld32(trow + c, v);
@@ -618,44 +610,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
                 warp_store_rows_bf16(st, hw2, lane, p.o_hi + (long)m_base * p.N + n0, nullptr, p.N, rows_valid);
               }
             } else {
-              // x = feat[b] * relu(acc + bias)   (model.py:146-151); N % 32 == 0 is required by the host wrapper
-              const bool row_ok = m < p.M;
-              uint32_t hw[32];   // [0..15] hi pairs (cols 2k, 2k+1), [16..31] lo pairs
+              // x = feat[b] * relu(acc + bias)   (model.py:146-151); N % 32 == 0 is required by the host wrapper.
+              // Raw accumulators go through the staging transpose; each lane then finishes 4 columns of 8 rows and writes
+              // them as 8-byte pieces (a quarter-warp = one 64-byte row segment per image).
+              stage_row(st, v, lane);
+              const bool f16 = (p.fmt & 4) != 0;
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 f = ef[j >> 2];                         // feat row: warp-broadcast when 32 | rows per sample
-                const float4 bb = eb[j >> 2];
-                const float x0 = f.x * fmaxf(__uint_as_float(v[j]) + bb.x, 0.f);
-                const float x1 = f.y * fmaxf(__uint_as_float(v[j + 1]) + bb.y, 0.f);
-                const float x2 = f.z * fmaxf(__uint_as_float(v[j + 2]) + bb.z, 0.f);
-                const float x3 = f.w * fmaxf(__uint_as_float(v[j + 3]) + bb.w, 0.f);
-                if (p.fmt & 4) {      // single fp16 image (11-bit significand): no lo image
-                  hw[j / 2] = pack16x2(x0, x1, true);
-                  hw[j / 2 + 1] = pack16x2(x2, x3, true);
-                  hw[16 + j / 2] = 0u;
-                  hw[16 + j / 2 + 1] = 0u;
-                } else {
-                  // packed conversions: one cvt.rn.bf16x2.f32 per pair, hi recovered with a shift / mask
-                  const __nv_bfloat162 h01 = __floats2bfloat162_rn(x0, x1), h23 = __floats2bfloat162_rn(x2, x3);
-                  const uint32_t w01 = *reinterpret_cast<const uint32_t*>(&h01), w23 = *reinterpret_cast<const uint32_t*>(&h23);
-                  const __nv_bfloat162 l01 = __floats2bfloat162_rn(x0 - __uint_as_float(w01 << 16),
-                                                                   x1 - __uint_as_float(w01 & 0xffff0000u));
-                  const __nv_bfloat162 l23 = __floats2bfloat162_rn(x2 - __uint_as_float(w23 << 16),
-                                                                   x3 - __uint_as_float(w23 & 0xffff0000u));
-                  hw[j / 2] = w01;
-                  hw[j / 2 + 1] = w23;
-                  hw[16 + j / 2] = *reinterpret_cast<const uint32_t*>(&l01);
-                  hw[16 + j / 2 + 1] = *reinterpret_cast<const uint32_t*>(&l23);
+              for (int r0 = 0; r0 < 32; r0 += 4) {
+                const int r = r0 + e_sub;
+                if (r < rows_valid) {
+                  if (!e_one_sample)
+                    ef = __ldg(reinterpret_cast<const float4*>(p.feat + (long)((m_base + r) / p.batch) * p.N + n0) + e_piece);
+                  const uint4 au = staged_piece(st, r, e_piece);
+                  const float x0 = ef.x * fmaxf(__uint_as_float(au.x) + eb.x, 0.f);
+                  const float x1 = ef.y * fmaxf(__uint_as_float(au.y) + eb.y, 0.f);
+                  const float x2 = ef.z * fmaxf(__uint_as_float(au.z) + eb.z, 0.f);
+                  const float x3 = ef.w * fmaxf(__uint_as_float(au.w) + eb.w, 0.f);
+                  const long o = (long)(m_base + r) * p.N + n0 + e_piece * 4;
+                  if (p.C) *reinterpret_cast<float4*>(p.C + o) = make_float4(x0, x1, x2, x3);
+                  uint32_t w0, w1, l0, l1;
+                  if (f16) {            // fp16(x) feeds the single-pass head forward, bf16(x) the backward products
+                    w0 = pack16x2(x0, x1, true); w1 = pack16x2(x2, x3, true);
+                    l0 = pack16x2(x0, x1, false); l1 = pack16x2(x2, x3, false);
+                  } else {              // bf16 hi + residual lo (split-bf16 x3 head forward)
+                    w0 = pack16x2(x0, x1, false); w1 = pack16x2(x2, x3, false);
+                    l0 = pack16x2(x0 - __uint_as_float(w0 << 16), x1 - __uint_as_float(w0 & 0xffff0000u), false);
+                    l1 = pack16x2(x2 - __uint_as_float(w1 << 16), x3 - __uint_as_float(w1 & 0xffff0000u), false);
+                  }
+                  if (p.o_hi) *reinterpret_cast<uint2*>(p.o_hi + o) = make_uint2(w0, w1);
+                  if (p.o_lo) *reinterpret_cast<uint2*>(p.o_lo + o) = make_uint2(l0, l1);
                 }
-                v[j] = __float_as_uint(x0); v[j + 1] = __float_as_uint(x1);
-                v[j + 2] = __float_as_uint(x2); v[j + 3] = __float_as_uint(x3);
               }
-              if (p.o_hiT) store_transposed_pairs(p.o_hiT, hw, n0, m, p.M, lane, row_ok);        // warp-uniform tests
-              if (p.o_loT) store_transposed_pairs(p.o_loT, hw + 16, n0, m, p.M, lane, row_ok);
-              if (p.C) warp_store_rows_f32(st, v, lane, p.C + (long)m_base * p.N + n0, p.N, rows_valid);
-              if (p.o_hi || p.o_lo)
-                warp_store_rows_bf16(st, hw, lane, p.o_hi ? p.o_hi + (long)m_base * p.N + n0 : nullptr,
-                                     p.o_lo ? p.o_lo + (long)m_base * p.N + n0 : nullptr, p.N, rows_valid);
             }
           }
         }
@@ -806,8 +791,9 @@ int gemm_bf16_tc(int M, int N, int K, const bf16* A_hi, const bf16* A_lo, const 
   p.o_hiT = ex ? ex->o_hiT : nullptr; p.o_loT = ex ? ex->o_loT : nullptr;
   p.fmt = ex ? ex->fmt : 0;
   if ((p.fmt & 3) && (split3 || split2)) return (int)cudaErrorInvalidValue;      // fp16 images are single-pass operands
-  if ((p.fmt & 4) && (epi != TC_EMBED || p.o_lo || p.o_hiT || p.o_loT)) return (int)cudaErrorInvalidValue;
-  if (epi == TC_EMBED && ((N % 32) || (M % 2))) return (int)cudaErrorInvalidValue;
+  if ((p.fmt & 3) == 1 || (p.fmt & 3) == 2) return (int)cudaErrorInvalidValue;   // mixed fp16 x bf16: illegal instruction
+  if ((p.fmt & 4) && epi != TC_EMBED) return (int)cudaErrorInvalidValue;
+  if (epi == TC_EMBED && ((N % 32) || (M % 2) || p.o_hiT || p.o_loT)) return (int)cudaErrorInvalidValue;
 #define RIQN_TC_GO(NS, EP) return launch_tc<NS, EP, 256>(ma_hi, ma_lo, mb_hi, mb_lo, p, s)
 #define RIQN_TC_NARROW(NS, EP)                                                                  \
   if (bn == 32) return launch_tc<NS, EP, 32>(ma_hi, ma_lo, mb_hi, mb_lo, p, s);                  \
@@ -862,8 +848,9 @@ __global__ void split_bf16_kernel(long rows, int cols, const float* __restrict__
     float x = 0.f;
     if (r < rows && c < cols) {
       x = src[r * cols + c];
-      if (fp16) {                       // single fp16 image (host guarantees lo == hiT == NULL)
+      if (fp16) {                       // hi = fp16(x); lo (optional) = bf16(x), NOT a residual
         reinterpret_cast<__half*>(hi)[r * cols + c] = __float2half_rn(x);
+        if (lo) lo[r * cols + c] = __float2bfloat16_rn(x);
         continue;
       }
       const bf16 h = __float2bfloat16_rn(x);
@@ -887,7 +874,7 @@ __global__ void split_bf16_kernel(long rows, int cols, const float* __restrict__
 }
 
 int split_bf16(long rows, int cols, const float* src, bf16* hi, bf16* lo, bf16* hiT, bf16* loT, cudaStream_t s, int fp16) {
-  if (fp16 && (hi == nullptr || lo != nullptr || hiT != nullptr || loT != nullptr)) return (int)cudaErrorInvalidValue;
+  if (fp16 && (hi == nullptr || hiT != nullptr || loT != nullptr)) return (int)cudaErrorInvalidValue;
   dim3 grid((cols + 31) / 32, (unsigned)((rows + 31) / 32));
   split_bf16_kernel<<<grid, 256, 0, s>>>(rows, cols, src, hi, lo, hiT, loT, fp16);
   return (int)cudaGetLastError();

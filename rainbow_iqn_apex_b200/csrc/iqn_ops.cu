@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(256) embed_bwd_wide_kernel(int B, int Nq, int 
 
 // bf16-dX variant with 16-byte accesses throughout: lane owns 8 consecutive features (one block = one sample x 256
 // features), warp w owns rows q = w, w+8, ...; all of a thread's loads of a 64-row pass are in flight together.
-template <bool XLO, bool XF16 = false>
+template <bool XLO>
 __global__ void __launch_bounds__(256) embed_bwd_wide8_kernel(int B, int Nq, int F, const __nv_bfloat16* __restrict__ x_hi,
                                                               const __nv_bfloat16* __restrict__ x_lo,
                                                               const float* __restrict__ feat,
@@ -245,13 +245,7 @@ __global__ void __launch_bounds__(256) embed_bwd_wide8_kernel(int B, int Nq, int
       uint32_t ow[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        float x0, x1;
-        if (XF16) {            // the forward's x image is fp16 (single-pass fp16 head)
-          const float2 xf = __half22float2(*reinterpret_cast<const __half2*>(&hw[k]));
-          x0 = xf.x; x1 = xf.y;
-        } else {
-          x0 = lo16(hw[k]) + lo16(lw[k]); x1 = hi16(hw[k]) + hi16(lw[k]);
-        }
+        const float x0 = lo16(hw[k]) + lo16(lw[k]), x1 = hi16(hw[k]) + hi16(lw[k]);
         const float d0 = lo16(dw[k]), d1 = hi16(dw[k]);
         facc[2 * k] = fmaf(d0, x0, facc[2 * k]);
         facc[2 * k + 1] = fmaf(d1, x1, facc[2 * k + 1]);
@@ -367,10 +361,15 @@ __global__ void noisy_compose_net_kernel(NoisyNet net, int training) {
                     __fadd_rn(mu.z, __fmul_rn(sg.z, e.z)), __fadd_rn(mu.w, __fmul_rn(sg.w, e.w)));
   }
   *reinterpret_cast<float4*>(L.w_eff + off) = w;
-  if (L.w_hi != nullptr && L.w_fp16) {   // single fp16 operand image (fp16 head forward)
+  if (L.w_hi != nullptr && L.w_fp16) {   // fp16(w) for the single-pass head forward, bf16(w) (optional) for the data gradient
     const __half2 h01 = __floats2half2_rn(w.x, w.y), h23 = __floats2half2_rn(w.z, w.w);
     *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(L.w_hi) + off) =
         make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+    if (L.w_lo != nullptr) {
+      const __nv_bfloat162 b01 = __floats2bfloat162_rn(w.x, w.y), b23 = __floats2bfloat162_rn(w.z, w.w);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(L.w_lo) + off) =
+          make_uint2(*reinterpret_cast<const uint32_t*>(&b01), *reinterpret_cast<const uint32_t*>(&b23));
+    }
   } else if (L.w_hi != nullptr) {    // bf16 operand images written here instead of by a separate split pass
     const __nv_bfloat162 h01 = __floats2bfloat162_rn(w.x, w.y), h23 = __floats2bfloat162_rn(w.z, w.w);
     const uint32_t u01 = *reinterpret_cast<const uint32_t*>(&h01), u23 = *reinterpret_cast<const uint32_t*>(&h23);
@@ -950,12 +949,17 @@ RIQN_API int riqn_quantile_embed_fwd_tc(int batch, int num_quantiles, int embed_
   ex.batch = num_quantiles;    // rows per sample
   ex.o_hi = (__nv_bfloat16*)x_hi;
   ex.o_lo = (__nv_bfloat16*)x_lo;
-  ex.o_hiT = (__nv_bfloat16*)x_hiT;
-  ex.o_loT = (__nv_bfloat16*)x_loT;
-  ex.fmt = x_fp16 ? 4 : 0;       // x_hi leaves as ONE fp16 image (x_lo / transposes must be NULL)
-  return gemm_bf16_tc((int)R, feat_dim, embed_dim, (const __nv_bfloat16*)cos_hi, (const __nv_bfloat16*)cos_lo,
-                      (const __nv_bfloat16*)iqn_w_hi, cos_lo ? (const __nv_bfloat16*)iqn_w_lo : nullptr, x32, feat_dim,
-                      TC_EMBED, iqn_b, nullptr, nullptr, 1, s, &ex);
+  ex.fmt = x_fp16 ? 4 : 0;       // x_hi = fp16(x) (head forward operand), x_lo (optional) = bf16(x) (backward operand)
+  const bool want_t = x_hiT != nullptr || x_loT != nullptr;    // transposed images (cross-check arithmetic modes only)
+  if (want_t && (x32 == nullptr || x_fp16)) return (int)cudaErrorInvalidValue;
+  int rc = gemm_bf16_tc((int)R, feat_dim, embed_dim, (const __nv_bfloat16*)cos_hi, (const __nv_bfloat16*)cos_lo,
+                        (const __nv_bfloat16*)iqn_w_hi, cos_lo ? (const __nv_bfloat16*)iqn_w_lo : nullptr, x32, feat_dim,
+                        TC_EMBED, iqn_b, nullptr, nullptr, 1, s, &ex);
+  if (rc == 0 && want_t) {
+    riqn::note_launches(1);
+    rc = split_bf16(R, feat_dim, x32, nullptr, nullptr, (__nv_bfloat16*)x_hiT, (__nv_bfloat16*)x_loT, s);
+  }
+  return rc;
 }
 
 // Backward on bf16 operands: dx (fp32, from the head dgrad) -> dfeat (overwritten), grad_iqn_b / grad_iqn_w accumulated.
@@ -963,9 +967,8 @@ RIQN_API int riqn_quantile_embed_fwd_tc(int batch, int num_quantiles, int embed_
 RIQN_API int riqn_quantile_embed_bwd_tc(int batch, int num_quantiles, int embed_dim, int feat_dim, const void* x_hi,
                                         const void* x_lo, const float* feat, const void* cos_hi, const void* dx,
                                         int dx_is_bf16, void* dpre, float* dfeat, float* grad_iqn_w, float* grad_iqn_b,
-                                        int x_fp16, void* stream) {
+                                        void* stream) {
   riqn::note_launches(2);
-  if (x_fp16 && !(dx_is_bf16 && feat_dim % 8 == 0 && num_quantiles % 2 == 0 && x_lo == nullptr)) return (int)cudaErrorInvalidValue;
   cudaStream_t s = (cudaStream_t)stream;
   const long R = (long)batch * num_quantiles;
   if (R % 8 || feat_dim % 8 || embed_dim % 8) return (int)cudaErrorInvalidValue;
@@ -977,11 +980,7 @@ RIQN_API int riqn_quantile_embed_bwd_tc(int batch, int num_quantiles, int embed_
                                                        (const __nv_bfloat16*)dx, (__nv_bfloat16*)dpre, dfeat, grad_iqn_b)
     if (dx_is_bf16 && feat_dim % 8 == 0) {
       dim3 grid8((feat_dim + 255) / 256, batch);
-      if (x_fp16)
-        embed_bwd_wide8_kernel<false, true><<<grid8, 256, 0, s>>>(batch, num_quantiles, feat_dim, (const __nv_bfloat16*)x_hi,
-                                                                  nullptr, feat, (const __nv_bfloat16*)dx, (__nv_bfloat16*)dpre,
-                                                                  dfeat, grad_iqn_b);
-      else if (x_lo)
+      if (x_lo)
         embed_bwd_wide8_kernel<true><<<grid8, 256, 0, s>>>(batch, num_quantiles, feat_dim, (const __nv_bfloat16*)x_hi,
                                                            (const __nv_bfloat16*)x_lo, feat, (const __nv_bfloat16*)dx,
                                                            (__nv_bfloat16*)dpre, dfeat, grad_iqn_b);

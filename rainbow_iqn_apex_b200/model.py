@@ -35,7 +35,7 @@ _ALIGN = 64  # floats; arena groups start on 256-byte boundaries
 #             at the bf16 rate; activations / weights of this network sit far inside the fp16 range).  The small products
 #             (conv trunk, quantile embedding: 5% of the FLOPs) keep the split-bf16 x3 arithmetic.
 #   "fp32"  : CUDA-core fp32 GEMM (gemm_simt.cu), the cross-check path
-PRECISION = {"fwd": os.environ.get("RIQN_FWD_PRECISION", "bf16x3"), "bwd": os.environ.get("RIQN_BWD_PRECISION", "bf16")}
+PRECISION = {"fwd": os.environ.get("RIQN_FWD_PRECISION", "fp16"), "bwd": os.environ.get("RIQN_BWD_PRECISION", "bf16")}
 WGRAD_SPLIT_K = int(os.environ.get("RIQN_WGRAD_SPLIT_K", "4"))
 _NO_STRIP = os.environ.get("RIQN_NO_STRIP_CONV", "0") == "1"      # fall back to the explicit-im2col forward
 
@@ -47,7 +47,7 @@ def set_precision(fwd=None, bwd=None):
                 raise ValueError(v)
             PRECISION[k] = v
     if PRECISION["fwd"] == "fp16" and PRECISION["bwd"] != "bf16":
-        raise ValueError("the fp16 forward pairs with the bf16 backward (mixed fp16 x bf16 tensor-core products)")
+        raise ValueError("the fp16 forward pairs with the bf16 backward (it reads the bf16 images written beside the fp16 ones)")
 
 
 def _small_x3():
@@ -348,7 +348,7 @@ class DQN(nn.Module):
                     # the composed hidden-layer weights leave the compose kernel as bf16 (hi, lo) images as well
                     row0 = 0 if name == "fcnoisy_h_v" else self.hidden
                     arr[k].w_hi = self._w_hi.data_ptr() + row0 * FEAT * 2
-                    arr[k].w_lo = None if f16 else self._w_lo.data_ptr() + row0 * FEAT * 2
+                    arr[k].w_lo = self._w_lo.data_ptr() + row0 * FEAT * 2     # fp16 mode: bf16(w), the dgrad operand
                     arr[k].w_fp16 = 1 if f16 else 0
                 m._ensure_scratch()
                 d = arr[k]
@@ -403,7 +403,7 @@ class DQN(nn.Module):
         need_t = PRECISION["bwd"] != "bf16" or PRECISION["fwd"] == "fp32"   # bf16 backward reads W itself (MN-major operand)
         if not h_done:
             f16 = PRECISION["fwd"] == "fp16"
-            call("riqn_split_bf16", 2 * self.hidden, FEAT, ptr(self._w_eff_h), ptr(self._w_hi), None if f16 else ptr(self._w_lo),
+            call("riqn_split_bf16", 2 * self.hidden, FEAT, ptr(self._w_eff_h), ptr(self._w_hi), ptr(self._w_lo),
                  ptr(self._w_hiT) if need_t else None, ptr(self._w_loT) if need_t else None, 1 if f16 else 0)
         if not (force or getattr(self, "_static_ops_dirty", True)):
             return
@@ -589,13 +589,18 @@ class DQN(nn.Module):
             need_x32 = keep is not None and not emb_tc           # the fp32 CUDA-core embedding backward reads x
             # bwd == "bf16": the weight-gradient products read the row-major images (MN-major operands): no transposes
             mn = bwd_tc and bwd == "bf16"
-            tc = dict(x_hi=bf(R, FEAT), x_lo=bf(R, FEAT) if head_x3 else None, f16=f16,
+            # fp16 mode: x_hi = fp16(x) feeds the forward product; the gradient pass also keeps x_bf = bf16(x) (written into
+            # the lo slot by the same epilogue) for the weight-gradient product and the embedding backward
+            tc = dict(x_hi=torch.empty(R, FEAT, dtype=torch.float16 if f16 else torch.bfloat16, device=dev),
+                      x_lo=bf(R, FEAT) if (head_x3 or (f16 and keep is not None)) else None, f16=f16,
                       x_hiT=bf(FEAT, R) if (bwd_tc and not mn) else None,
                       x_loT=bf(FEAT, R) if (bwd_tc and bwd == "bf16x3") else None,
                       cos_hi=bf(R, E), cos_lo=bf(R, E) if x3 else None, cosT_hi=None, mn=mn)
             if need_x32:
                 xt = torch.empty(R, FEAT, device=dev)
                 cosv = torch.empty(R, E, device=dev)
+            elif tc["x_hiT"] is not None:                        # transposed images are split from the fp32 matrix
+                xt = torch.empty(R, FEAT, device=dev)
             call("riqn_quantile_embed_fwd_tc", B, num_quantiles, E, FEAT, ptr(tau), ptr(feat), ptr(self._iqn_ops[0]),
                  ptr(self._iqn_ops[1]), ptr(self.iqn_fc.bias), ptr(tc["cos_hi"]), ptr(tc["cos_lo"]), ptr(tc["cosT_hi"]),
                  ptr(xt), ptr(tc["x_hi"]), ptr(tc["x_lo"]), ptr(tc["x_hiT"]), ptr(tc["x_loT"]), 1 if f16 else 0)
@@ -603,7 +608,7 @@ class DQN(nn.Module):
                 call("riqn_quantile_embed_fwd", B, num_quantiles, E, FEAT, ptr(tau), ptr(feat), ptr(self.iqn_fc.weight),
                      ptr(self.iqn_fc.bias), ptr(cosv), ptr(xt))
             tc["h_hi"] = bf(R, 2 * hid) if (bwd_tc and R % 2 == 0) else None   # bf16 image of h for the z-layer weight gradient
-            call("riqn_gemm_bf16_tc", R, 2 * hid, FEAT, ptr(tc["x_hi"]), ptr(tc["x_lo"]), ptr(self._w_hi),
+            call("riqn_gemm_bf16_tc", R, 2 * hid, FEAT, ptr(tc["x_hi"]), ptr(tc["x_lo"]) if head_x3 else None, ptr(self._w_hi),
                  ptr(self._w_lo) if head_x3 else None, ptr(h), 2 * hid, 1, ptr(self._b_eff_h), None, None, 1, None, ptr(tc["h_hi"]),
                  3 if f16 else 0)
         q = torch.empty(R, A, device=dev)
@@ -641,7 +646,9 @@ class DQN(nn.Module):
         gv = self.grad_view
         dz = torch.empty(R, 32, device=dev)
         tc = keep.get("tc")
-        fmt_b = 2 if (tc and tc.get("f16")) else 0          # the forward's x / W images are fp16: mixed bf16 x fp16 products
+        f16 = bool(tc and tc.get("f16"))
+        x_bf = tc["x_lo"] if f16 else (tc["x_hi"] if tc else None)      # bf16 image of x (fp16 forward: the second image)
+        w_bf = self._w_lo if f16 else getattr(self, "_w_hi", None)      # bf16 image of W_eff
         z_tc = bool(keep["head_bwd_tc"]) and tc is not None and tc.get("h_hi") is not None
         dzT = torch.empty(R, 32, dtype=torch.bfloat16, device=dev) if z_tc else None       # (R, 32) row-major bf16 image
         dbs = torch.empty(2 * hid, device=dev)
@@ -686,8 +693,8 @@ class DQN(nn.Module):
                 call("riqn_split_bf16", R, 2 * hid, ptr(dh), ptr(dh_hi), ptr(dh_lo), ptr(dh_hiT), ptr(dh_loT), 0)
             # dW[o, i] = sum_r dh[r, o] x[r, i]  -> dmu += dW, dsigma += dW * eps   (split-K, atomics)
             if fused_dh:
-                call("riqn_gemm_bf16_tc_mn", 2 * hid, FEAT, R, ptr(dh_hi), ptr(tc["x_hi"]), 1, ptr(gv(hv.weight_mu)), FEAT, 3,
-                     ptr(gv(hv.weight_sigma)), ptr(hv.weight_epsilon), 1.0, WGRAD_SPLIT_K, None, fmt_b)
+                call("riqn_gemm_bf16_tc_mn", 2 * hid, FEAT, R, ptr(dh_hi), ptr(x_bf), 1, ptr(gv(hv.weight_mu)), FEAT, 3,
+                     ptr(gv(hv.weight_sigma)), ptr(hv.weight_epsilon), 1.0, WGRAD_SPLIT_K, None, 0)
             else:
                 call("riqn_gemm_bf16_tc", 2 * hid, FEAT, R, ptr(dh_hiT), ptr(dh_loT), ptr(tc["x_hiT"]),
                      ptr(tc["x_loT"]) if b3 else None, ptr(gv(hv.weight_mu)), FEAT, 3, None, ptr(gv(hv.weight_sigma)),
@@ -696,8 +703,8 @@ class DQN(nn.Module):
                  ptr(gv(hv.bias_mu)), ptr(gv(hv.bias_sigma)))
             # dx[r, i] = sum_o dh[r, o] W_eff[o, i]
             if fused_dh:     # W_eff (2*hid, 3136) itself is the (K, N) operand: no transposed weight image
-                call("riqn_gemm_bf16_tc_mn", R, FEAT, 2 * hid, ptr(dh_hi), ptr(self._w_hi), 0, None if dx_bf16 else ptr(dx), FEAT,
-                     0, None, None, 1.0, 1, ptr(dx) if dx_bf16 else None, fmt_b)
+                call("riqn_gemm_bf16_tc_mn", R, FEAT, 2 * hid, ptr(dh_hi), ptr(w_bf), 0, None if dx_bf16 else ptr(dx), FEAT,
+                     0, None, None, 1.0, 1, ptr(dx) if dx_bf16 else None, 0)
             else:
                 call("riqn_gemm_bf16_tc", R, FEAT, 2 * hid, ptr(dh_hi), ptr(dh_lo), ptr(self._w_hiT),
                      ptr(self._w_loT) if b3 else None, ptr(dx), FEAT, 0, None, None, None, 1, None, None, 0)
@@ -705,9 +712,9 @@ class DQN(nn.Module):
         if keep["emb_bwd_tc"]:
             dpre = torch.empty(R, FEAT, dtype=torch.bfloat16, device=dev)
             # bf16 backward: x = x_hi (the lo image only refines the forward)
-            call("riqn_quantile_embed_bwd_tc", B, Nq, E, FEAT, ptr(tc["x_hi"]), None if dx_bf16 else ptr(tc["x_lo"]),
+            call("riqn_quantile_embed_bwd_tc", B, Nq, E, FEAT, ptr(x_bf), None if (dx_bf16 or f16) else ptr(tc["x_lo"]),
                  ptr(keep["feat"]), ptr(tc["cos_hi"]), ptr(dx), 1 if dx_bf16 else 0, ptr(dpre), ptr(dfeat),
-                 ptr(gv(self.iqn_fc.weight)), ptr(gv(self.iqn_fc.bias)), 1 if fmt_b else 0)
+                 ptr(gv(self.iqn_fc.weight)), ptr(gv(self.iqn_fc.bias)))
         else:
             call("riqn_quantile_embed_bwd", B, Nq, E, FEAT, ptr(keep["xt"]), ptr(keep["feat"]), ptr(keep["cos"]), ptr(dx),
                  ptr(dfeat), ptr(gv(self.iqn_fc.weight)), ptr(gv(self.iqn_fc.bias)))

@@ -16,6 +16,13 @@ pytestmark = pytest.mark.gpu
 LOSS_TOL = 2e-4      # fp32 / split-bf16x3 forward products; the north_star bound is 1e-3
 
 
+def _loss_tol():
+    """Per-transition loss tolerance of the current forward arithmetic: the single-pass fp16 head (the default) measured
+    max 1.6e-4 at B=512 (tests/test_gpu_parity_full.py, forward table), split-bf16x3 / fp32 3e-6."""
+    from rainbow_iqn_apex_b200 import model
+    return {"fp16": 5e-4, "bf16": 1e-3}.get(model.PRECISION["fwd"], LOSS_TOL)
+
+
 def _grad_tol():
     """Norm-relative gradient tolerance of the current backward arithmetic (model.PRECISION)."""
     from rainbow_iqn_apex_b200 import model
@@ -76,7 +83,7 @@ def test_learn_matches_reference_golden(cuda_dev, golden_dir, name):
         w = torch.from_numpy(b["weights"]).to(cuda_dev)
         lr._debug = {}
         idxs, loss = lr.learn(FakeMem((np.arange(batch), st, ac, rt, nx, nt, w)), None)
-        assert rel_err(loss.cpu().numpy(), g[f"loss_{s}"]) < LOSS_TOL
+        assert rel_err(loss.cpu().numpy(), g[f"loss_{s}"]) < _loss_tol()
         assert np.max(np.abs(loss.cpu().numpy() - g[f"loss_{s}"]) / np.abs(g[f"loss_{s}"])) < 1e-3  # per transition
         # ReLU kinks: with 4..32 samples a single pre-activation that rounds to opposite sides of 0 on the CPU and the
         # GPU moves the conv1/conv2 gradients by percents.  Count them against the oracle's activations (the oracle
@@ -98,8 +105,8 @@ def test_learn_matches_reference_golden(cuda_dev, golden_dir, name):
             assert abs(gd[2] - ref[2]) <= gtol * ref[2] + 1e-9, (k, gd[:3], ref[:3], fl)       # l2 norm
             assert np.allclose(gd[3:], ref[3:], rtol=2 * gtol, atol=2 * gtol * ref[2] / np.sqrt(p.numel()) + 1e-9), (k, fl)
             pd, pref = digest(p), g[f"param_{s}_{k}"]
-            if nfl or k.startswith(("conv1", "conv2")):   # l2 norm and leading elements (Adam's normalisation amplifies
-                # tiny-gradient elements of the signed sums)
+            if nfl or _grad_tol() > 1e-3:   # l2 norm and leading elements (the signed sum over a tensor amplifies a kink
+                # flip, and with the bf16 backward the 1e-2 gradient noise of elements Adam normalises by sqrt(v))
                 assert np.allclose(pd[2:], pref[2:], rtol=1e-5, atol=5e-6), k
             else:
                 assert np.allclose(pd, pref, rtol=1e-5, atol=1e-6), k
@@ -127,15 +134,15 @@ def _tie_mask(keep_oracle, a_star_gpu, tol=1e-5):
     return diff
 
 
-@pytest.mark.parametrize("mode", [("fp32", "fp32"), ("bf16x3", "bf16x3"), ("bf16x3", "bf16"), ("bf16", "bf16")])
+@pytest.mark.parametrize("mode", [("fp32", "fp32"), ("bf16x3", "bf16x3"), ("bf16x3", "bf16"), ("bf16", "bf16"), ("fp16", "bf16")])
 @pytest.mark.parametrize("batch,cfg", [(16, cases.iqn_cfg(64, 64, 32)), (5, cases.iqn_cfg(16, 24, 8, kappa=0.5))])
 def test_loss_api_and_autograd_vs_oracle(cuda_dev, precision, batch, cfg, mode):
     """Agent.compute_loss_actor_or_learner + (weights*loss).mean().backward() + optimiser.step(), the exact
     call sequence of learner.py:18-24, against the oracle (autograd on CPU)."""
     from rainbow_iqn_apex_b200 import Agent
     precision(*mode)
-    loss_tol = 1e-3 if mode[0] == "bf16" else LOSS_TOL      # bf16 operands: the north_star bound itself
-    act_tol = 2e-3 if mode[0] == "bf16" else 1e-4
+    loss_tol = _loss_tol()                                  # bf16 operands: the north_star bound itself
+    act_tol = {"bf16": 2e-3, "fp16": 3e-4}.get(mode[0], 1e-4)
     seed = 900 + batch
     params = net.make_params(seed)
     ag = Agent(make_args(cuda_dev, batch, cfg), 18, None)
@@ -160,7 +167,7 @@ def test_loss_api_and_autograd_vs_oracle(cuda_dev, precision, batch, cfg, mode):
     keep = {}
     o_loss, o_grads = losses.learn_step(p_on, p_tg, adam, cases.batch_to_torch(b), torch.from_numpy(b["weights"]),
                                         noises, taus, cfg, keep=keep)
-    ties = _tie_mask(keep, dbg["a_star"].cpu().numpy(), tol=1e-3 if mode[0] == "bf16" else 1e-5)
+    ties = _tie_mask(keep, dbg["a_star"].cpu().numpy(), tol={"bf16": 1e-3, "fp16": 1e-4}.get(mode[0], 1e-5))
     ok = ~ties
     lg, lo = loss.detach().cpu().numpy(), o_loss.numpy()
     assert np.max(np.abs(lg[ok] - lo[ok]) / np.abs(lo[ok])) < loss_tol
@@ -177,7 +184,7 @@ def test_loss_api_and_autograd_vs_oracle(cuda_dev, precision, batch, cfg, mode):
             cos = float((gg * g_ref).sum() / (gg.norm() * g_ref.norm() + 1e-30))
             rel = float((gg - g_ref).norm() / (g_ref.norm() + 1e-30))
             if flips == 0:
-                assert cos > 0.999 and rel < (3e-2 if mode[0] == "bf16" else _grad_tol()), (k, cos, rel)   # SURVEY 8d gate: cos
+                assert cos > 0.999 and rel < (3e-2 if mode[0] in ("bf16", "fp16") else _grad_tol()), (k, cos, rel)   # SURVEY 8d gate: cos
                 assert np.allclose(dict(ag.online_net.named_parameters())[k].detach().cpu().numpy(),
                                    p_on[k].detach().numpy(), rtol=0, atol=1e-6 if _grad_tol() < 5e-3 else 5e-6), k
             else:
@@ -260,7 +267,7 @@ def test_full_size_config2_vs_oracle(cuda_dev, batch):
     assert ties.sum() <= 2
     lg, lo = loss.cpu().numpy(), o_loss.numpy()
     assert np.max(np.abs(lg[ok] - lo[ok]) / np.abs(lo[ok])) < 1e-3          # north_star tolerance
-    assert np.max(np.abs(lg[ok] - lo[ok]) / np.abs(lo[ok])) < LOSS_TOL      # what fp32 CUDA achieves
+    assert np.max(np.abs(lg[ok] - lo[ok]) / np.abs(lo[ok])) < _loss_tol()   # what the default arithmetic achieves
 
 
 # ----------------------------------------------------------------------------------------------- C51 (rainbow_only)

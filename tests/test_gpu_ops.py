@@ -77,20 +77,27 @@ def test_forward_injected(cuda_dev, nets):
         return t.reshape(B, Nq, -1).transpose(0, 1).reshape(B * Nq, -1)
 
     cos_gpu = qmajor(tc["cos_hi"].float() + tc["cos_lo"].float()).cpu().numpy()    # bf16 hi + lo images
-    x_gpu = qmajor(tc["x_hi"].float() + tc["x_lo"].float()).cpu().numpy()
     assert rel_err(cos_gpu, keep["cos"].numpy()) < 2e-5
-    assert rel_err(x_gpu, keep["x"].numpy()) < 3e-5
+    if tc["f16"]:     # default arithmetic: x leaves as fp16(x) (head forward operand) + bf16(x) (backward operand)
+        assert tc["x_hi"].dtype == torch.float16
+        assert rel_err(qmajor(tc["x_hi"].float()).cpu().numpy(), keep["x"].numpy()) < 5e-4
+        assert rel_err(qmajor(tc["x_lo"].float()).cpu().numpy(), keep["x"].numpy()) < 4e-3
+        htol = 3e-4
+    else:
+        x_gpu = qmajor(tc["x_hi"].float() + tc["x_lo"].float()).cpu().numpy()
+        assert rel_err(x_gpu, keep["x"].numpy()) < 3e-5
+        htol = 1e-4                                                              # split-bf16x3 tensor-core products
     h_gpu = qmajor(k2["h"])
-    assert rel_err(h_gpu[:, :512].cpu().numpy(), keep["h_v"].numpy()) < 1e-4   # split-bf16x3 tensor-core products
-    assert rel_err(h_gpu[:, 512:].cpu().numpy(), keep["h_a"].numpy()) < 1e-4
-    assert rel_err(q.cpu().numpy(), ref.numpy()) < 1e-4
+    assert rel_err(h_gpu[:, :512].cpu().numpy(), keep["h_v"].numpy()) < htol
+    assert rel_err(h_gpu[:, 512:].cpu().numpy(), keep["h_a"].numpy()) < htol
+    assert rel_err(q.cpu().numpy(), ref.numpy()) < htol
     # stored epsilons == outer product of the injected factors (model.py:39-43), bit for bit
     assert torch.equal(d.fcnoisy_h_a.weight_epsilon.cpu(), torch.outer(noise["fcnoisy_h_a"][1], noise["fcnoisy_h_a"][0]))
     # eval mode uses mu only (model.py:52-53)
     d.eval()
     q_eval, _ = d.forward(torch.from_numpy(b["states"]).to(cuda_dev), Nq, tau=tau)
     ref_eval = net.dqn_forward_iqn(p, torch.from_numpy(b["states"]).float().div_(255), Nq, tau, training=False)
-    assert rel_err(q_eval.cpu().numpy(), ref_eval.numpy()) < 1e-4
+    assert rel_err(q_eval.cpu().numpy(), ref_eval.numpy()) < htol
     d.train()
 
 

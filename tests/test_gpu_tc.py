@@ -112,33 +112,37 @@ def test_tc_gemm_mn_major(cuda_dev):
     assert rel_err(cb.float().cpu().numpy(), ref) < 4e-3          # one bf16 rounding of the result
 
 
-@pytest.mark.parametrize("fmt", [1, 2, 3])
-def test_tc_gemm_fp16_and_mixed_formats(cuda_dev, fmt):
-    """tcgen05 kind::f16 takes the A and B formats independently: fp16 x fp16 (the single-pass head forward) and
-    bf16 x fp16 (backward: a bf16 gradient times the forward's fp16 activation / weight image), K-major and MN-major."""
-    from rainbow_iqn_apex_b200._lib import call, ptr
-    rs = np.random.RandomState(40 + fmt)
-    dta = torch.float16 if fmt & 1 else torch.bfloat16
-    dtb = torch.float16 if fmt & 2 else torch.bfloat16
+def test_tc_gemm_fp16_operands(cuda_dev):
+    """fp16 x fp16 single-pass products (the head forward's arithmetic), K-major and MN-major; a product mixing fp16 and
+    bf16 images is refused (tcgen05 kind::f16 faults with an illegal instruction when the A / B formats differ)."""
+    from rainbow_iqn_apex_b200._lib import RiqnError, call, ptr
+    rs = np.random.RandomState(43)
     M, N, K = 300, 1024, 3136
-    a = torch.from_numpy(rs.standard_normal((M, K)).astype(np.float32)).to(cuda_dev).to(dta)
-    b = torch.from_numpy((rs.standard_normal((N, K)) * 0.05).astype(np.float32)).to(cuda_dev).to(dtb)
+    a = torch.from_numpy(rs.standard_normal((M, K)).astype(np.float32)).to(cuda_dev).half()
+    b = torch.from_numpy((rs.standard_normal((N, K)) * 0.05).astype(np.float32)).to(cuda_dev).half()
     bias = torch.from_numpy(rs.standard_normal(N).astype(np.float32)).to(cuda_dev)
     c = torch.zeros(M, N, device=cuda_dev)
-    call("riqn_gemm_bf16_tc", M, N, K, ptr(a), None, ptr(b), None, ptr(c), N, 1, ptr(bias), None, None, 1, None, None, fmt)
+    call("riqn_gemm_bf16_tc", M, N, K, ptr(a), None, ptr(b), None, ptr(c), N, 1, ptr(bias), None, None, 1, None, None, 3)
     ref = np.maximum(a.float().cpu().numpy().astype(np.float64) @ b.float().cpu().numpy().astype(np.float64).T
                      + bias.cpu().numpy(), 0)
-    assert rel_err(c.cpu().numpy(), ref) < 1e-5, fmt
-    # MN-major B (K, N): dX = dY W and dW = dY^T X with the second operand in the other format
+    assert rel_err(c.cpu().numpy(), ref) < 1e-5
     for a_is_km in (0, 1):
         Mm, Nn, Kk = (300, 3136, 1024) if not a_is_km else (1024, 3136, 512)
-        a2 = torch.from_numpy(rs.standard_normal((Kk, Mm) if a_is_km else (Mm, Kk)).astype(np.float32)).to(cuda_dev).to(dta)
-        b2 = torch.from_numpy((rs.standard_normal((Kk, Nn)) * 0.05).astype(np.float32)).to(cuda_dev).to(dtb)
+        a2 = torch.from_numpy(rs.standard_normal((Kk, Mm) if a_is_km else (Mm, Kk)).astype(np.float32)).to(cuda_dev).half()
+        b2 = torch.from_numpy((rs.standard_normal((Kk, Nn)) * 0.05).astype(np.float32)).to(cuda_dev).half()
         c2 = torch.zeros(Mm, Nn, device=cuda_dev)
-        call("riqn_gemm_bf16_tc_mn", Mm, Nn, Kk, ptr(a2), ptr(b2), a_is_km, ptr(c2), Nn, 0, None, None, 1.0, 1, None, fmt)
+        call("riqn_gemm_bf16_tc_mn", Mm, Nn, Kk, ptr(a2), ptr(b2), a_is_km, ptr(c2), Nn, 0, None, None, 1.0, 1, None, 3)
         af = a2.float().cpu().numpy().astype(np.float64)
         ref2 = (af.T if a_is_km else af) @ b2.float().cpu().numpy().astype(np.float64)
-        assert rel_err(c2.cpu().numpy(), ref2) < 1e-5, (fmt, a_is_km)
+        assert rel_err(c2.cpu().numpy(), ref2) < 1e-5, a_is_km
+    for fmt in (1, 2):
+        with pytest.raises(RiqnError):
+            call("riqn_gemm_bf16_tc", M, N, K, ptr(a), None, ptr(b), None, ptr(c), N, 1, ptr(bias), None, None, 1, None, None, fmt)
+    # fp16(x) + bf16(x) images from one split call (the compose_weights path of the fp16 forward)
+    src = torch.from_numpy(rs.standard_normal((64, 96)).astype(np.float32)).to(cuda_dev)
+    h, l = torch.empty(64, 96, dtype=torch.float16, device=cuda_dev), torch.empty(64, 96, dtype=torch.bfloat16, device=cuda_dev)
+    call("riqn_split_bf16", 64, 96, ptr(src), ptr(h), ptr(l), None, None, 1)
+    assert torch.equal(h, src.half()) and torch.equal(l, src.bfloat16())
 
 
 def _strip_layers():
