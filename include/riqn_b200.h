@@ -86,7 +86,8 @@ int riqn_conv_fwd_tc(const riqn_conv_geom* g, const void* in, int in_is_u8, cons
  *   riqn_s2d_u8: uint8 frame stack -> block matrix a_px (B*G*G, stride^2*Cin) bf16 of raw pixel values, within-block
  *                order (c, iy, ix); the 1/255 of redis_memory.py:527-536 is folded into the weights.
  *   riqn_conv_fwd_strip: a_hi / a_lo (lo may be NULL) block matrices; w_hi / w_lo (Cout, K) bf16 weights with K
- *                ordered (dy, dx, within-block); out (B, Cout, OH, OW) fp32 = relu(conv + bias); next_hi / next_lo (may be
+ *                ordered (dy, dx, within-block); out (B, Cout, OH, OW) fp32 = relu(conv + bias), or NULL when only the
+ *                next layer's images are wanted (no-grad passes); next_hi / next_lo (may be
  *                NULL) receive the result as the NEXT layer's block matrix (block edge next_stride, grid next_grid,
  *                within-block order (iy, ix, c)).
  *   riqn_im2col_bf16_t: the transposed bf16 im2col (K, M) alone, the wgrad operand of riqn_conv_bwd_tc. */

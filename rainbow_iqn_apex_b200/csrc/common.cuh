@@ -56,3 +56,16 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+
+// One-time PER-DEVICE initialisation (cudaFuncSetAttribute opt-ins, SM count): a process may drive several GPUs (learner
+// and actor networks on different devices), and the shared-memory opt-in is per device/context.  Idempotent work only:
+// two threads racing on the same device both perform it before either marks it done.
+struct PerDeviceOnce {
+  bool done[64] = {};
+  int sms[64] = {};
+  static int device() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return d & 63;
+  }
+};

@@ -603,10 +603,11 @@ RIQN_API int riqn_conv_fwd_tc(const riqn_conv_geom* g, const void* in, int in_is
   else {
     const int chw = g->Cin * g->H * g->W;
     if (chw % 4 == 0 && g->in_bstride % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && chw * 4 <= 96 * 1024) {
-      static bool attr = false;
-      if (!attr) {
+      static PerDeviceOnce attr_once;
+      const int attr_dev = PerDeviceOnce::device();
+      if (!attr_once.done[attr_dev]) {
         RIQN_CUDA(cudaFuncSetAttribute(im2col_f32_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        attr = true;
+        attr_once.done[attr_dev] = true;
       }
       im2col_f32_staged_kernel<<<g->B, 256, (size_t)chw * 4, s>>>(*g, (const float*)in, (bf16*)col_hi, (bf16*)col_lo);
     } else {
@@ -634,10 +635,11 @@ RIQN_API int riqn_conv_fwd_tc_u8(const riqn_conv_geom* g, const unsigned char* i
   const int K = g->Cin * g->KH * g->KW, chw = g->Cin * g->H * g->W, ohw = g->OH * g->OW;
   if (K % 8 || chw % 16 || g->in_bstride % 16 || (reinterpret_cast<uintptr_t>(in) & 15) || (colT_px && ohw % 8) || chw > 96 * 1024)
     return (int)cudaErrorInvalidValue;
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr_once;
+  const int attr_dev = PerDeviceOnce::device();
+  if (!attr_once.done[attr_dev]) {
     RIQN_CUDA(cudaFuncSetAttribute(im2col_u8_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    attr = true;
+    attr_once.done[attr_dev] = true;
   }
   if (!reuse_col) {      // reuse_col: col_px already holds this input's im2col (another network's pass over it)
     im2col_u8_staged_kernel<<<dim3(g->B, 4), 256, chw, s>>>(*g, in, (bf16*)col_px, (bf16*)colT_px);
@@ -741,10 +743,11 @@ RIQN_API int riqn_s2d_u8(const riqn_conv_geom* g, const unsigned char* in, void*
   if (strip_params(g, &t, &G, &kc) || chw % 16 || g->in_bstride % 16 || (reinterpret_cast<uintptr_t>(in) & 15) ||
       chw > 96 * 1024)
     return (int)cudaErrorInvalidValue;
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr_once;
+  const int attr_dev = PerDeviceOnce::device();
+  if (!attr_once.done[attr_dev]) {
     RIQN_CUDA(cudaFuncSetAttribute(s2d_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    attr = true;
+    attr_once.done[attr_dev] = true;
   }
   s2d_u8_kernel<<<g->B, 256, chw, (cudaStream_t)stream>>>(*g, G, in, (bf16*)a_px);
   return (int)cudaGetLastError();
@@ -820,10 +823,11 @@ RIQN_API int riqn_im2col_bf16_t(const riqn_conv_geom* g, const void* in, int in_
   if (in_is_u8) {
     if (chw % 16 || g->in_bstride % 16 || (reinterpret_cast<uintptr_t>(in) & 15) || ohw % 8 || chw > 96 * 1024)
       return (int)cudaErrorInvalidValue;
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr_once;
+    const int attr_dev = PerDeviceOnce::device();
+    if (!attr_once.done[attr_dev]) {
       RIQN_CUDA(cudaFuncSetAttribute(im2col_u8_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-      attr = true;
+      attr_once.done[attr_dev] = true;
     }
     im2col_u8_staged_kernel<<<dim3(g->B, 4), 256, chw, s>>>(*g, (const unsigned char*)in, nullptr, (bf16*)colT_hi);
   } else {

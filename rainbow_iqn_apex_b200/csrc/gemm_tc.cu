@@ -410,6 +410,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
     // ------------------------------------------------------------------ epilogue warps (TMEM -> registers -> HBM)
     const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32) are the ones this warp may read
     const int chalf = (warp - 2) >> 2;            // which half of the accumulator columns this warp drains
+    float conv_bias[32];
+    if (EPI == TC_CONV) {                         // one n-tile (N <= 64): this warp's 32 columns never change
+      constexpr int CH0 = TBN >= 64 ? TBN / 2 : TBN;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) conv_bias[j] = (chalf * CH0 + j < p.N && chalf * CH0 < TBN) ? p.bias[chalf * CH0 + j] : 0.f;
+    }
     int local = 0;
     for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++local) {
       const int t = u / p.k_splits;
@@ -480,43 +486,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (n0 + j < p.N) cb[(long)j * p.ohw] = fmaxf(__uint_as_float(v[j]) + p.bias[n0 + j], 0.f);
-          } else if (EPI == TC_CONV) {
-            const int gg = p.strip_G * p.strip_G;
-            const int b = m / gg, rem = m - b * gg;
-            const int gy = rem / p.strip_G, gx = rem - gy * p.strip_G;
-            if (gy < p.cv_oh && gx < p.cv_ow) {
-              float x[32];
-#pragma unroll
-              for (int j = 0; j < 32; ++j) x[j] = n0 + j < p.N ? fmaxf(__uint_as_float(v[j]) + p.bias[n0 + j], 0.f) : 0.f;
-              const int plane = p.cv_oh * p.cv_ow;
-              float* cb = p.C + ((long)b * p.N + n0) * plane + gy * p.cv_ow + gx;     // lanes = consecutive gx
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (n0 + j < p.N) cb[(long)j * plane] = x[j];
-              if (p.nx_hi != nullptr && n0 + 32 <= p.N) {
-                // this pixel's channels are contiguous in the next layer's space-to-depth row: 64-byte pieces
-                const int sn = p.nx_s, by = gy / sn, bx = gx / sn;
-                const long r = ((long)b * p.nx_G + by) * p.nx_G + bx;
-                const long o = r * ((long)sn * sn * p.N) + (long)((gy - by * sn) * sn + (gx - bx * sn)) * p.N + n0;
-                uint32_t wh[16], wl[16];
-#pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                  const __nv_bfloat162 h2 = __floats2bfloat162_rn(x[j], x[j + 1]);
-                  const uint32_t hw = *reinterpret_cast<const uint32_t*>(&h2);
-                  const __nv_bfloat162 l2 = __floats2bfloat162_rn(x[j] - __uint_as_float(hw << 16),
-                                                                  x[j + 1] - __uint_as_float(hw & 0xffff0000u));
-                  wh[j / 2] = hw;
-                  wl[j / 2] = *reinterpret_cast<const uint32_t*>(&l2);
-                }
-#pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4) {
-                  reinterpret_cast<uint4*>(p.nx_hi + o)[q4] = make_uint4(wh[4 * q4], wh[4 * q4 + 1], wh[4 * q4 + 2], wh[4 * q4 + 3]);
-                  if (p.nx_lo)
-                    reinterpret_cast<uint4*>(p.nx_lo + o)[q4] = make_uint4(wl[4 * q4], wl[4 * q4 + 1], wl[4 * q4 + 2], wl[4 * q4 + 3]);
-                }
-              }
-            }
-          } else if (EPI == TC_EMBED || EPI == TC_COL2IM) {
+          } else if (EPI == TC_EMBED || EPI == TC_COL2IM || EPI == TC_CONV) {
             // handled below with the whole warp
           } else if (!(p.vec_acc && n0 + 32 <= p.N)) {
             float* crow = p.C + (long)m * p.ldc + n0;
@@ -533,6 +503,53 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
                     atomicAdd(p.out2 + (long)m * p.ldc + n0 + j, o * p.eps[(long)m * p.ldc + n0 + j]);
                 }
               }
+            }
+          }
+        }
+        if (EPI == TC_CONV && n0 < p.N) {
+          // strip convolution: relu(acc + bias) -> (optional) fp32 NCHW output + the NEXT layer's space-to-depth images.
+          // The bias of this warp's 32 columns sits in registers for the whole kernel (N <= 64 = one n-tile); the image
+          // rows go through the staging transpose so that a quarter-warp writes one pixel's 64-byte channel run.
+          const int gg = p.strip_G * p.strip_G;
+          const int mm = m < p.M ? m : 0;
+          const int b = mm / gg, rem = mm - b * gg;
+          const int gy = rem / p.strip_G, gx = rem - gy * p.strip_G;
+          const bool valid = m < p.M && gy < p.cv_oh && gx < p.cv_ow;
+          float x[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = n0 + j < p.N ? fmaxf(__uint_as_float(v[j]) + conv_bias[j], 0.f) : 0.f;
+          if (p.C != nullptr && valid) {
+            const int plane = p.cv_oh * p.cv_ow;
+            float* cb = p.C + ((long)b * p.N + n0) * plane + gy * p.cv_ow + gx;     // lanes = consecutive gx
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < p.N) cb[(long)j * plane] = x[j];
+          }
+          if (p.nx_hi != nullptr && n0 + 32 <= p.N) {          // warp-uniform
+            // this pixel's channels are contiguous in the next layer's space-to-depth row
+            long o = -1;
+            if (valid) {
+              const int sn = p.nx_s, by = gy / sn, bx = gx / sn;
+              const long r = ((long)b * p.nx_G + by) * p.nx_G + bx;
+              o = r * ((long)sn * sn * p.N) + (long)((gy - by * sn) * sn + (gx - bx * sn)) * p.N + n0;
+            }
+            uint32_t hw[32];      // [0..15] hi pairs, [16..31] lo pairs
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              const uint32_t hwj = pack16x2(x[j], x[j + 1], false);
+              hw[j / 2] = hwj;
+              hw[16 + j / 2] = pack16x2(x[j] - __uint_as_float(hwj << 16), x[j + 1] - __uint_as_float(hwj & 0xffff0000u), false);
+            }
+            const uint32_t st = epi_stage + (warp - 2) * (32 * kStRow * 4);
+            stage_row(st, hw, lane);
+            const int sub = lane >> 3, piece = lane & 7;
+            bf16* dstb = piece < 4 ? p.nx_hi : p.nx_lo;
+#pragma unroll
+            for (int r0 = 0; r0 < 32; r0 += 4) {
+              const int r = r0 + sub;
+              const long orow = __shfl_sync(0xffffffffu, o, r);
+              if (orow >= 0 && dstb != nullptr)
+                *reinterpret_cast<uint4*>(dstb + orow + (piece & 3) * 8) = staged_piece(st, r, piece);
             }
           }
         }
@@ -690,17 +707,17 @@ template <int NSPLIT, int EPI, int BN>
 static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
                      const TcArgs& p, cudaStream_t s) {
   using Cfg = TcCfg<NSPLIT, BN>;
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr_once;
+  const int attr_dev = PerDeviceOnce::device();
+  if (!attr_once.done[attr_dev]) {
     RIQN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<NSPLIT, EPI, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)Cfg::kSmemBytes));
-    attr = true;
+    attr_once.done[attr_dev] = true;
   }
-  static int sms = 0;
+  int sms = attr_once.sms[attr_dev];
   if (!sms) {
-    int dev = 0;
-    RIQN_CUDA(cudaGetDevice(&dev));
-    RIQN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    RIQN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, attr_dev));
+    attr_once.sms[attr_dev] = sms;
   }
   const int units = p.m_tiles * p.n_tiles * p.k_splits;
   const int grid = units < sms ? units : sms;

@@ -1084,16 +1084,18 @@ RIQN_API int riqn_dueling_fwd(long rows, int batch, int hidden, int action_space
   riqn::note_launches(1);
   if (hidden != 512 || action_space > 31) return (int)cudaErrorInvalidValue;
   const size_t smem = sizeof(float) * (1 + action_space) * hidden;
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr_once;
+  const int attr_dev = PerDeviceOnce::device();
+  if (!attr_once.done[attr_dev]) {
     RIQN_CUDA(cudaFuncSetAttribute(z_dueling_fwd_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    attr = true;
+    attr_once.done[attr_dev] = true;
   }
   if (action_space <= 24) {
-    static bool attr4 = false;
-    if (!attr4) {
+    static PerDeviceOnce attr4_once;
+    const int attr4_dev = PerDeviceOnce::device();
+    if (!attr4_once.done[attr4_dev]) {
       RIQN_CUDA(cudaFuncSetAttribute(z_dueling_fwd4_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-      attr4 = true;
+      attr4_once.done[attr4_dev] = true;
     }
     z_dueling_fwd4_kernel<512><<<148 * 2, 256, smem, (cudaStream_t)stream>>>(rows, batch, action_space, h, wz, bz, q);
   } else {
@@ -1108,10 +1110,11 @@ RIQN_API int riqn_dueling_bwd(long rows, int batch, int hidden, int action_space
   riqn::note_launches(1);
   if (hidden != 512 || action_space > 31) return (int)cudaErrorInvalidValue;
   const size_t smem = sizeof(float) * ((1 + action_space) * hidden + hidden);
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr_once;
+  const int attr_dev = PerDeviceOnce::device();
+  if (!attr_once.done[attr_dev]) {
     RIQN_CUDA(cudaFuncSetAttribute(z_dueling_bwd_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    attr = true;
+    attr_once.done[attr_dev] = true;
   }
   z_dueling_bwd_kernel<512><<<148 * 4, 256, smem, (cudaStream_t)stream>>>(rows, batch, action_space, h, wz, dtheta, gscale,
                                                                        (const int64_t*)actions, dh, dz, (__nv_bfloat16*)dz_bf16);
@@ -1126,10 +1129,11 @@ RIQN_API int riqn_dueling_bwd_bf16(long rows, int batch, int hidden, int action_
   if (hidden != 512 || action_space > 31 || rows % 8) return (int)cudaErrorInvalidValue;
   cudaStream_t s = (cudaStream_t)stream;
   const size_t smem = sizeof(float) * ((1 + action_space) * hidden + hidden + 2 * hidden) + 32 * 128 * 16;
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr_once;
+  const int attr_dev = PerDeviceOnce::device();
+  if (!attr_once.done[attr_dev]) {
     RIQN_CUDA(cudaFuncSetAttribute(z_dueling_bwd_bf16_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    attr = true;
+    attr_once.done[attr_dev] = true;
   }
   RIQN_CUDA(cudaMemsetAsync(dh_colsum, 0, sizeof(float) * 2 * hidden, s));
   const long n_blk = (rows + 31) / 32;

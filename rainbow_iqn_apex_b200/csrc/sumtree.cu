@@ -450,10 +450,11 @@ RIQN_API int riqn_sumtree_update(int n, long capacity, double* tree, const long 
   int max_depth = 0;  // depth of the deepest leaf (index 2C-2)
   for (long i = 2 * capacity - 2; i > 0; i = (i - 1) / 2) ++max_depth;
   const size_t smem = (size_t)n * 20;
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr_once;
+  const int attr_dev = PerDeviceOnce::device();
+  if (!attr_once.done[attr_dev]) {
     RIQN_CUDA(cudaFuncSetAttribute(update_propagate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    attr = true;
+    attr_once.done[attr_dev] = true;
   }
   const int slices = (n + 127) / 128 < 8 ? (n + 127) / 128 : 8;
   update_propagate_kernel<<<dim3(max_depth + 1, slices), 128, smem, s>>>(n, max_depth, tree, (const int64_t*)tree_idx,

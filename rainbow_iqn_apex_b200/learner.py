@@ -80,9 +80,21 @@ class Learner(Agent):
         mem.update_priorities(idxs, loss)
         return idxs, loss
 
+    def _attach_dyn(self, mem, on):
+        """Route the per-step scalars (Philox offsets, Adam bias corrections, beta / capacity) through the device-resident
+        riqn_dyn_state -- ONLY while a step is being warmed up / captured.  A captured graph keeps the struct's address in its
+        kernel arguments; eager calls made after the capture (learn_and_update on another memory, mem.sample(),
+        optimiser.step(), reset_noise()) must read their by-value arguments again, not the last-written struct."""
+        dyn = self._dyn if on else None
+        self._dyn_on = bool(on)
+        self.optimiser._dyn = dyn
+        mem.transitions._dyn = dyn
+        self.online_net.begin_step(dyn)
+        self.target_net.begin_step(dyn)
+
     def _step_pre(self, mem):
         """sample -> three forwards -> loss -> backward (gradients in the arena)."""
-        dyn = self._dyn
+        dyn = self._dyn if getattr(self, "_dyn_on", False) else None
         self.online_net.begin_step(dyn)
         self.target_net.begin_step(dyn)
         mem.transitions._draws_in_step = 0
@@ -110,8 +122,7 @@ class Learner(Agent):
         from .dynstate import DynState
         dev = self.online_net._flat.device
         self._dyn = DynState(dev)
-        self.optimiser._dyn = self._dyn
-        mem.transitions._dyn = self._dyn
+        self._attach_dyn(mem, True)
         step0 = self.optimiser._step
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -140,6 +151,7 @@ class Learner(Agent):
         # the capture itself does not execute the step: undo the host-side counter it advanced
         self.optimiser._step = step0 + warmup
         self._graph, self._graph_post, self._graph_mem, self._graph_out = graph, post, mem, out
+        self._attach_dyn(mem, False)           # eager calls from here on use their by-value arguments again
         return self
 
     def enable_batch_graph(self, mem, example):
@@ -149,6 +161,7 @@ class Learner(Agent):
         nonterminals, weights) device tensors defining the shapes.  Requires enable_cuda_graph(mem) first."""
         assert self._graph is not None and mem is self._graph_mem
         self._bg_in = tuple(t.clone() for t in example)
+        self._attach_dyn(mem, True)
 
         def pre():
             self.online_net.begin_step(self._dyn)
@@ -185,6 +198,7 @@ class Learner(Agent):
                 self._step_post(mem, self._bg_in[0], out, allreduce=False)
         self.optimiser._step = step0 + 2
         self._bgraph, self._bgraph_post, self._bg_out = graph, post, out
+        self._attach_dyn(mem, False)
         return self
 
     def prefetch_host_batch(self, host_batch):

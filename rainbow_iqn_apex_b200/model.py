@@ -26,6 +26,9 @@ from . import _lib
 from ._lib import ConvGeom, NoisyLayer, SplitJob, call, ptr
 
 FEAT = 3136
+# Philox stream ids: CUDA-graph steps use (static per-step index + the device-side rng_offset = 64 * epoch); eager calls count
+# on the host.  The eager counters live in their own half of the id space so that the two can never reuse a stream.
+_EAGER_STREAMS = 1 << 39
 _ALIGN = 64  # floats; arena groups start on 256-byte boundaries
 
 # Arithmetic of the hidden NoisyLinear products (x W^T, dh W, dh^T x -- 91% of the step's FLOPs):
@@ -108,7 +111,7 @@ class NoisyLinear(nn.Module):
             dyn = self._dyn
             # graph mode: static per-step index (the device-side rng_offset advances the stream every step)
             idx = self._calls_in_step if dyn is not None else self._noise_calls
-            base = (self._layer_id << 40) + 2 * idx
+            base = (self._layer_id << 40) + 2 * idx + (0 if dyn is not None else _EAGER_STREAMS)
             call("riqn_noisy_sample", self.in_features, seed, base, ptr(self._eps_in), dyn.ptr() if dyn else None)
             call("riqn_noisy_sample", self.out_features, seed, base + 1, ptr(self._eps_out), dyn.ptr() if dyn else None)
             self._noise_calls += 1
@@ -322,7 +325,7 @@ class DQN(nn.Module):
             else:
                 # graph mode: static per-step index (the device-side rng_offset advances the stream every step)
                 idx = m._calls_in_step if m._dyn is not None else m._noise_calls
-                base = (m._layer_id << 40) + 2 * idx
+                base = (m._layer_id << 40) + 2 * idx + (0 if m._dyn is not None else _EAGER_STREAMS)
                 desc[k].stream_in, desc[k].stream_out = base, base + 1
                 m._noise_calls += 1
                 m._calls_in_step += 1
@@ -456,7 +459,7 @@ class DQN(nn.Module):
         tau = torch.empty(n, 1, device=self._flat.device)
         dyn = getattr(self, "_dyn", None)
         idx = self._tau_in_step if dyn is not None else self._tau_calls
-        call("riqn_fill_uniform", n, self._rng_seed ^ 0x7A75, self._tau_stream_offset + idx, ptr(tau),
+        call("riqn_fill_uniform", n, self._rng_seed ^ 0x7A75, self._tau_stream_offset + idx + (0 if dyn is not None else _EAGER_STREAMS), ptr(tau),
              dyn.ptr() if dyn else None)
         self._tau_calls += 1
         self._tau_in_step += 1
@@ -505,10 +508,12 @@ class DQN(nn.Module):
             a2_hi, a2_lo = bf(B * 100, 128), (bf(B * 100, 128) if x3 else None)
             a3_hi, a3_lo = bf(B * 81, 64), (bf(B * 81, 64) if x3 else None)
             ops = self._strip_ops
+            # the fp32 NCHW activations of conv1 / conv2 are only read by the backward (ReLU masks): no-grad passes skip them
+            o1, o2 = (ptr(outs[0]), ptr(outs[1])) if keep is not None else (None, None)
             call("riqn_conv_fwd_strip", g1, ptr(a1), None, ptr(ops["conv1"][0]), ptr(ops["conv1"][1]) if x3 else None,
-                 ptr(self.conv1.bias), ptr(outs[0]), ptr(a2_hi), ptr(a2_lo), 2, 10)
+                 ptr(self.conv1.bias), o1, ptr(a2_hi), ptr(a2_lo), 2, 10)
             call("riqn_conv_fwd_strip", g2, ptr(a2_hi), ptr(a2_lo), ptr(ops["conv2"][0]), ptr(ops["conv2"][1]) if x3 else None,
-                 ptr(self.conv2.bias), ptr(outs[1]), ptr(a3_hi), ptr(a3_lo), 1, 9)
+                 ptr(self.conv2.bias), o2, ptr(a3_hi), ptr(a3_lo), 1, 9)
             call("riqn_conv_fwd_strip", g3, ptr(a3_hi), ptr(a3_lo), ptr(ops["conv3"][0]), ptr(ops["conv3"][1]) if x3 else None,
                  ptr(self.conv3.bias), ptr(outs[2]), None, None, 0, 0)
             if keep is not None:                     # operands of the backward products

@@ -80,13 +80,16 @@ class SegmentTree:
     def update_multiple_value(self, tree_idx, values, apply_pow=False, exponent=0.0):
         """redis_memory.py:139-151 (+ the np.power of :560 when apply_pow).  tree_idx int64, values fp32."""
         n = tree_idx.numel()
+        if n > 4096:
+            # The reference reads ALL old leaves before it applies one batch (duplicates see the same old value); the
+            # kernel holds one batch of <= 4096 entries.  Splitting silently would change the result for duplicates that
+            # straddle a chunk boundary, so larger batches are the caller's decision (bench.py's fill loops over chunks).
+            raise ValueError("update_multiple_value takes at most 4096 entries per call (one reference batch)")
         new_pri = torch.empty(n, dtype=torch.float32, device=self.device)
-        for lo in range(0, n, 4096):  # the reference issues one update per batch; huge batches are chunked
-            hi = min(n, lo + 4096)
-            diff = torch.empty(hi - lo, dtype=torch.float64, device=self.device)
-            idx_c, val_c, out_c = tree_idx[lo:hi], values[lo:hi], new_pri[lo:hi]
-            call("riqn_sumtree_update", hi - lo, self.full_capacity, ptr(self.tree), ptr(idx_c), ptr(val_c),
-                 float(exponent), 1 if apply_pow else 0, ptr(out_c), ptr(diff), ptr(self.max_priority))
+        diff = torch.empty(n, dtype=torch.float64, device=self.device)
+        tree_idx, values = tree_idx.contiguous(), values.contiguous()
+        call("riqn_sumtree_update", n, self.full_capacity, ptr(self.tree), ptr(tree_idx), ptr(values),
+             float(exponent), 1 if apply_pow else 0, ptr(new_pri), ptr(diff), ptr(self.max_priority))
         return new_pri
 
     def append_arrays(self, id_actor, start, timesteps, frames, actions, rewards, dones, priorities, T_actor=0):
@@ -95,6 +98,8 @@ class SegmentTree:
         dev = self.device
         n = len(actions)
         cap = self.actor_capacity
+        if not self.store_frames:
+            raise RuntimeError("this SegmentTree was built with store_frames=False (tree only): no transition store")
         pos = (np.arange(start, start + n) % cap) + id_actor * cap
         tree_idx = torch.from_numpy(pos + self.full_capacity - 1).to(dev)
         pri = torch.as_tensor(np.asarray(priorities, np.float32)).to(dev)
@@ -136,7 +141,7 @@ class SegmentTree:
             samples = torch.empty(batch_size, dtype=torch.float64, device=dev)
             dyn = self._dyn
             idx = self._draws_in_step if dyn is not None else self._draws
-            call("riqn_sumtree_stratified", batch_size, self._rng_seed, idx, ptr(self.tree), ptr(samples),
+            call("riqn_sumtree_stratified", batch_size, self._rng_seed, idx + (0 if dyn is not None else 1 << 39), ptr(self.tree), ptr(samples),
                  dyn.ptr() if dyn else None)
             self._draws += 1
             self._draws_in_step += 1
@@ -169,22 +174,30 @@ class ReplayMemory:
         self.last_nonpositive = None
 
     def sample_indices(self, batch_size, samples=None):
-        """find_multiple_values + importance weights (redis_memory.py:424-475).  The resample-on-zero-priority
-        retry (:432-445) is replaced by the reference's own final fallback (:446-456, uniform 1/capacity),
-        applied on the device; the count of such samples is left in ``last_nonpositive`` (device int)."""
+        """find_multiple_values + importance weights (redis_memory.py:424-475), including the reference's resample loop:
+        while some sampled priority is <= 0 (a slot next to a write head of a partially filled segment) the batch is
+        redrawn, up to 10 times (:432-445); after that -- and always inside a captured CUDA graph or with injected
+        ``samples``, where a host-side retry is impossible -- the reference's final fallback applies (:446-456: those
+        probabilities become 1/capacity).  The count of such samples is left in ``last_nonpositive`` (device int)."""
         tr = self.transitions
-        pri, data_idx, tree_idx = tr.find_multiple_values(self.history, self.n, batch_size, samples)
-        w64 = torch.empty(batch_size, dtype=torch.float64, device=self.device)
-        w32 = torch.empty(batch_size, dtype=torch.float32, device=self.device)
-        self.last_nonpositive = torch.zeros(1, dtype=torch.int32, device=self.device)
-        call("riqn_sumtree_is_weights", batch_size, ptr(tr.tree), ptr(pri), float(tr.get_current_capacity()),
-             float(self.priority_weight), ptr(w64), ptr(w32), ptr(self.last_nonpositive),
-             tr._dyn.ptr() if tr._dyn is not None else None)
+        retry = samples is None and tr._dyn is None and not torch.cuda.is_current_stream_capturing()
+        for attempt in range(10 if retry else 1):
+            pri, data_idx, tree_idx = tr.find_multiple_values(self.history, self.n, batch_size, samples)
+            w64 = torch.empty(batch_size, dtype=torch.float64, device=self.device)
+            w32 = torch.empty(batch_size, dtype=torch.float32, device=self.device)
+            self.last_nonpositive = torch.zeros(1, dtype=torch.int32, device=self.device)
+            call("riqn_sumtree_is_weights", batch_size, ptr(tr.tree), ptr(pri), float(tr.get_current_capacity()),
+                 float(self.priority_weight), ptr(w64), ptr(w32), ptr(self.last_nonpositive),
+                 tr._dyn.ptr() if tr._dyn is not None else None)
+            if not retry or int(self.last_nonpositive.item()) == 0:       # one 4-byte read per eager sample
+                break
         return tree_idx, data_idx, pri, w64, w32
 
     def assemble(self, data_idx):
         """get_byte_multiple_transition + get_torch_tensor_from_byte_transition (:347-369, :479-541)."""
         tr = self.transitions
+        if not tr.store_frames:
+            raise RuntimeError("this replay was built with store_frames=False (tree only): nothing to assemble")
         B = data_idx.numel()
         L = self.history + self.n
         window = torch.empty(B, L, 84, 84, dtype=torch.uint8, device=self.device)

@@ -36,8 +36,7 @@ def test_graph_replay_matches_eager_with_same_dyn_state(cuda_dev):
     a.enable_cuda_graph(mem_a, warmup=2)              # 2 eager warm-up steps, then capture
     # b: the same steps, all eager, through the same body / dyn protocol
     b._dyn = DynState(cuda_dev)
-    b.optimiser._dyn = b._dyn
-    mem_b.transitions._dyn = b._dyn
+    b._attach_dyn(mem_b, True)
 
     def eager_step():
         nss, sbc = b.optimiser.bias_corrections(b.optimiser._step + 1)
@@ -68,6 +67,18 @@ def test_graph_replay_matches_eager_with_same_dyn_state(cuda_dev):
     assert not torch.equal(losses[0], losses[1])       # fresh noise / quantiles / samples every replay
     assert torch.isfinite(torch.stack(losses)).all()
     assert not torch.equal(a.online_net._flat, a.target_net._flat)
+    # after the capture the dyn state is detached: eager calls use their by-value arguments and the host counters again
+    assert a.optimiser._dyn is None and mem_a.transitions._dyn is None and a.online_net._dyn is None
+    step_before = a.optimiser._step
+    s1, s2 = mem_a.sample(16), mem_a.sample(16)
+    assert not torch.equal(s1[0], s2[0])               # fresh stratified draws (the eager counter advances)
+    from rainbow_iqn_apex_b200 import ReplayMemory
+    other = ReplayMemory(make_args(cuda_dev, 16, cases.iqn_cfg(16, 16, 8), nb_actor=1, actor_capacity=512), None)
+    other.transitions.append_arrays(0, 0, np.arange(512) % 97, np.zeros((512, 84, 84), np.uint8), np.zeros(512, np.int64),
+                                    np.ones(512, np.float32), np.zeros(512, bool), np.full(512, 0.5, np.float32))
+    p_before = a.online_net._flat.clone()
+    a.learn_and_update(other)                          # eager fall-through on a memory the graph was not captured for
+    assert a.optimiser._step == step_before + 1 and not torch.equal(p_before, a.online_net._flat)
 
 
 def test_host_batch_graph(cuda_dev):
