@@ -122,6 +122,28 @@ class SegmentTree:
         self.index_actor[id_actor] = int(self.index_actor_host[id_actor])
         self.step_actor[id_actor] = T_actor
 
+    def append_device(self, id_actor, start, timesteps, frames, actions, rewards, nonterminals, priorities, T_actor=None):
+        """append_actor_buffer (redis_memory.py:153-202) for buffers that already live on the device (actor GPUs,
+        apex.ActorPool): n consecutive steps of segment ``id_actor`` at ring position ``start``; no host staging."""
+        if not self.store_frames:
+            raise RuntimeError("this SegmentTree was built with store_frames=False (tree only): no transition store")
+        dev, cap = self.device, self.actor_capacity
+        n = int(actions.numel())
+        pos = (torch.arange(start, start + n, device=dev) % cap) + id_actor * cap
+        self.update_multiple_value(pos + self.full_capacity - 1, priorities.to(dev, torch.float32).contiguous())
+        fr = frames.to(dev, torch.uint8).reshape(n, FRAME).contiguous()
+        nt = nonterminals.to(dev, torch.uint8).contiguous()
+        ts_d, ac_d = timesteps.to(dev, torch.int32).contiguous(), actions.to(dev, torch.int32).contiguous()
+        rw_d = rewards.to(dev, torch.float32).contiguous()
+        call("riqn_replay_append", n, cap, id_actor, int(start), ptr(fr), ptr(ts_d), ptr(ac_d), ptr(rw_d), ptr(nt),
+             ptr(self.frames), ptr(self.timestep), ptr(self.action), ptr(self.reward), ptr(self.nonterminal))
+        if start + n >= cap:
+            self.is_full_actor[id_actor] = 1
+        self.index_actor_host[id_actor] = (start + n) % cap
+        self.index_actor[id_actor] = int(self.index_actor_host[id_actor])
+        if T_actor is not None:
+            self.step_actor[id_actor] = T_actor
+
     def append_actor_buffer(self, actor_buffer, actor_index_in_replay_memory, id_actor, priorities, T_actor):
         """redis_memory.py:153-202 with the reference's list-of-[timestep, frame, action, reward, done] buffer."""
         ts = np.array([b[0] for b in actor_buffer], np.int64)
@@ -195,6 +217,12 @@ class ReplayMemory:
 
     def assemble(self, data_idx):
         """get_byte_multiple_transition + get_torch_tensor_from_byte_transition (:347-369, :479-541)."""
+        window, actions, returns, nonterminals = self.assemble_window(data_idx)
+        return window[:, :self.history], actions, returns, window[:, self.n:self.n + self.history], nonterminals
+
+    def assemble_window(self, data_idx):
+        """The (B, history + n, 84, 84) uint8 frame window itself (states = window[:, :history], next_states =
+        window[:, n:n+history]) with actions / returns / nonterminals: what a replay shard ships to the learner rank."""
         tr = self.transitions
         if not tr.store_frames:
             raise RuntimeError("this replay was built with store_frames=False (tree only): nothing to assemble")
@@ -207,7 +235,7 @@ class ReplayMemory:
         call("riqn_frame_gather", B, tr.actor_capacity, self.history, self.n, ptr(data_idx), ptr(tr.frames),
              ptr(tr.timestep), ptr(tr.action), ptr(tr.reward), ptr(tr.nonterminal), ptr(self._gamma_pow), ptr(window),
              ptr(actions), ptr(returns), ptr(nonterminals))
-        return window[:, :self.history], actions, returns, window[:, self.n:self.n + self.history], nonterminals
+        return window, actions, returns, nonterminals
 
     def sample(self, batch_size, samples=None):
         """Everything Learner.learn needs, as device tensors:
