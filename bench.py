@@ -425,6 +425,110 @@ def c51_leg(dev, args):
             "value": 1000.0 / ms, "unit": "grad-steps/s", "steps": n, "mode": mode, "replay_capacity": cap}
 
 
+def run_apex(args):
+    """BASELINE configs[3] (`--topology apex`, N >= 2 ranks): rank 0 = learner (B = 512 per step), every other rank an actor
+    GPU that owns a prioritized replay shard (2^19 transitions by default, one segment per environment), steps
+    `--actor-envs` synthetic environments with batched greedy actions, computes initial priorities for each
+    `--actor-buffer`-step buffer and appends it to its shard.  Per learner step, all ranks in lock step: shard sampling
+    on the actor GPUs -> gather to the learner -> learn -> broadcast of the new losses -> priority update on the owning
+    shards; parameter broadcast every 100 learner steps.  Reports learner grad-steps/s and actor frames/s."""
+    from rainbow_iqn_apex_b200 import Actor, Learner, ReplayMemory, _lib, apex, parallel
+    rank, world, local = parallel.init_from_env()
+    if world < 2:
+        raise SystemExit("--topology apex needs >= 2 ranks (torch.distributed.run --nproc-per-node N)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    _lib.require_device()
+    torch.manual_seed(123 + rank)
+    topo = apex.ApexTopology(B, publish_every=100)
+    E, L = args.actor_envs, args.actor_buffer
+    if topo.is_learner:
+        agent = Learner(make_args(dev, 1), ACTIONS, None)
+        mem = pool = None
+    else:
+        a = make_args(dev, args.replay_capacity // E)
+        a.nb_actor = E
+        agent = Actor(a, ACTIONS, None)
+        mem = ReplayMemory(a, None)
+        fill_replay_segments(mem, dev, 1000 + rank)
+        pool = apex.ActorPool(agent, mem, E, L)
+        pool.write_index[:] = mem.transitions.index_actor_host          # continue behind the synthetic pre-fill
+        g = torch.Generator(device=dev).manual_seed(9000 + rank)
+        states = torch.randint(0, 256, (E, 4, 84, 84), dtype=torch.uint8, device=dev, generator=g)
+    agent.train()
+    parallel.publish_parameters(agent, src=0)                  # everyone starts from the learner's weights
+    flushed = [0]
+
+    def step():
+        nonlocal states
+        batch = topo.sample(mem, beta=0.4, device=dev)
+        if topo.is_learner:
+            _, _, st, ac, rt, nx, nt, w = batch
+            loss = agent.learn_on_batch(st, ac, rt, nx, nt, w).detach()
+        else:
+            loss = torch.empty(B, dtype=torch.float32, device=dev)
+            for _ in range(args.acts_per_step):                # acting overlaps the learner's step
+                act = pool.act(states)
+                nxt = torch.randint(0, 256, (E, 1, 84, 84), dtype=torch.uint8, device=dev, generator=g)
+                rew = (torch.randint(0, 3, (E,), device=dev, generator=g) - 1).float()
+                done = torch.rand(E, device=dev, generator=g) < 0.01
+                if pool.observe(states, act, rew, done):
+                    flushed[0] += pool.flush()
+                states = torch.cat([states[:, 1:], nxt], 1)
+        topo.route(loss, mem, None if topo.is_learner else batch)
+        topo.maybe_publish(agent)
+
+    def barrier():
+        torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0 = flushed[0]
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    clk = clocks.stop()
+    ms = parallel.allreduce_max(e0.elapsed_time(e1), dev)
+    appended = parallel.allreduce_sum(float(flushed[0] - f0), dev)
+    ms_per_step = ms / args.steps
+    env_steps = (world - 1) * E * args.acts_per_step * args.steps
+    out = {"metric": "Ape-X topology: learner grad-steps/sec (batch=512, N=N'=64) with %d actor GPUs" % (world - 1),
+           "value": 1000.0 / ms_per_step, "unit": "grad-steps/s", "n_gpus": world, "steps": args.steps,
+           "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "n/a", "vs_baseline": None,
+           "dtype": "fp16 fwd / bf16 bwd tensor-core products", "data": "synthetic", "impl": "ours",
+           "config": {"workload": "configs[3]: 1 learner + %d actor GPUs, sharded prioritized replay %d transitions, "
+                                  "NCCL parameter broadcast every 100 steps" % (world - 1, (world - 1) * args.replay_capacity),
+                      "batch": B, "shard_counts": topo.counts, "replay_capacity_per_shard": args.replay_capacity,
+                      "envs_per_actor_gpu": E, "actor_buffer": L, "acts_per_learner_step": args.acts_per_step},
+           "actor_env_steps_per_s": env_steps / (ms * 1e-3), "actor_frames_per_s": 4.0 * env_steps / (ms * 1e-3),
+           "transitions_appended_in_region": appended, "clocks": clk,
+           "exchange_bytes_per_step": {"windows_to_learner": B * 7 * 7056, "losses_broadcast": 4 * B, "parameters_every_100": 26903576}}
+    if rank == 0:
+        print(json.dumps(out))
+    torch.distributed.barrier()
+    torch.distributed.destroy_process_group()
+
+
+def fill_replay_segments(mem, device, seed):
+    """fill_replay for a shard with one segment per environment (setup, not timed)."""
+    tr = mem.transitions
+    cap = tr.full_capacity
+    fill_replay(mem, cap, device, seed)
+    heads = torch.randint(0, tr.actor_capacity, (tr.nb_actor,), generator=torch.Generator().manual_seed(seed))
+    for a in range(tr.nb_actor):
+        tr.index_actor_host[a] = int(heads[a])
+        tr.is_full_actor[a] = 1
+    tr.index_actor.copy_(heads.to(device))
+
+
 # ------------------------------------------------------------------------------------------ CPU arms
 def oracle_learner(batch, threads=None):
     """The oracle port of Learner.learn (oracle/losses.py) on the host CPU cores."""
@@ -540,6 +644,11 @@ def main():
     ap.add_argument("--replay-capacity", type=int, default=1 << 19)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-c51", action="store_true", help="skip the configs[2] (Rainbow-only) leg")
+    ap.add_argument("--topology", default="dp", choices=["dp", "apex"],
+                    help="dp: data-parallel learner (configs[1]/[4], the headline); apex: 1 learner + N-1 actor GPUs (configs[3])")
+    ap.add_argument("--actor-envs", type=int, default=128, help="apex: environments per actor GPU")
+    ap.add_argument("--actor-buffer", type=int, default=200, help="apex: steps per actor buffer flush (reference: 1000)")
+    ap.add_argument("--acts-per-step", type=int, default=1, help="apex: batched acting iterations per learner step")
     ap.add_argument("--blocks", type=int, default=5, help="timed regions of --steps steps each; the median is the headline")
     ap.add_argument("--sustained-seconds", type=float, default=3.0, help="length of the sustained leg (0 = skip)")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
@@ -548,6 +657,8 @@ def main():
     watchdog(args.max_seconds)
     if args.impl == "reference":
         run_reference(args)
+    elif args.topology == "apex":
+        run_apex(args)
     else:
         run_ours(args)
 

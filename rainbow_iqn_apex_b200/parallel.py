@@ -79,6 +79,13 @@ def publish_parameters(agent, src=0, group=None):
         net.compose_weights()
 
 
+def allreduce_sum(value, device):
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
 def allreduce_max(value, device):
     t = torch.tensor([value], dtype=torch.float64, device=device)
     if dist.is_initialized() and dist.get_world_size() > 1:

@@ -90,7 +90,7 @@ def test_tree_random_vs_oracle(cuda_dev, cap, nb, batch):
     ot = osum.SumTree(cap, nb)
     C = cap * nb
     for a in range(nb):
-        n = cap if cap <= 5000 else 4096
+        n = min(cap, 4096)                   # one reference batch per update call
         for lo in range(0, cap, n):
             m = min(n, cap - lo)
             pri = (rs.uniform(1e-3, 1, m) ** 0.2).astype(np.float32)
