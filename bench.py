@@ -191,7 +191,7 @@ def run_ours(args):
 
     # ---- pass 2 (headline): the whole step captured once in a CUDA graph and replayed
     if not args.no_graph:
-        learner.enable_cuda_graph(mem)
+        learner.enable_cuda_graph(mem, capture_collectives=not args.dp_eager_allreduce)
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
@@ -332,6 +332,8 @@ def run_ours(args):
         "blocks": {"n": len(block_ms), "steps_per_block": args.steps, "ms": block_ms, "min_ms_per_step": min(block_ms) / args.steps,
                    "max_ms_per_step": max(block_ms) / args.steps, "headline": "median block"},
         "sustained": sustained,
+        "dp_allreduce": (None if world == 1 else ("eager, between two graphs" if args.dp_eager_allreduce else
+                                                    "captured in the step graph; NoisyLinear bucket overlapped with the backward")),
         "frames_per_s": value * B * 4, "transitions_per_s": value * B,
         "clocks": clk, "e2e": e2e, "gpu_launches": launches, "cuda_graph": not args.no_graph,
         "eager": {"ms_per_step": eager_ms, "host_issue_ms_per_step": host_issue_ms},
@@ -644,6 +646,8 @@ def main():
     ap.add_argument("--replay-capacity", type=int, default=1 << 19)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-c51", action="store_true", help="skip the configs[2] (Rainbow-only) leg")
+    ap.add_argument("--dp-eager-allreduce", action="store_true",
+                    help="N > 1: keep the gradient all-reduce eager between two CUDA graphs (round-1 scheme) instead of capturing it")
     ap.add_argument("--topology", default="dp", choices=["dp", "apex"],
                     help="dp: data-parallel learner (configs[1]/[4], the headline); apex: 1 learner + N-1 actor GPUs (configs[3])")
     ap.add_argument("--actor-envs", type=int, default=128, help="apex: environments per actor GPU")

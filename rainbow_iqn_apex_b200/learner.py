@@ -20,6 +20,8 @@ class Learner(Agent):
     def __init__(self, args, action_space, redis_servor):
         super().__init__(args, action_space, redis_servor)
         self.process_group = None  # set by parallel.make_data_parallel
+        self._dp_stream = self._dp_tail = None
+        self.overlap_allreduce = True   # data parallel: start the NoisyLinear-gradient all-reduce inside the backward
         self._graph = None         # CUDA-graph mode (enable_cuda_graph)
         self._graph_post = None
 
@@ -35,10 +37,28 @@ class Learner(Agent):
         self.apply_gradients()
         return loss
 
+    def _start_tail_allreduce(self, offset):
+        """Called by DQN.backward_iqn once the NoisyLinear gradients (arena[offset:], 25.8 of 26.9 MB) are final: their
+        all-reduce runs on a side stream under the rest of the backward (head data gradient, embedding and trunk backward)."""
+        if self.process_group is None:
+            return
+        if getattr(self, "_dp_stream", None) is None:
+            self._dp_stream = torch.cuda.Stream()
+        self._dp_stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self._dp_stream):
+            torch.distributed.all_reduce(self.online_net._flat_grad[offset:], group=self.process_group)
+        self._dp_tail = offset
+
     def apply_gradients(self):
         """Gradient all-reduce (data-parallel replicas) + Adam.  learner.py:24"""
         if self.process_group is not None:
-            torch.distributed.all_reduce(self.online_net._flat_grad, group=self.process_group)
+            tail = getattr(self, "_dp_tail", None)
+            if tail is not None:             # the big bucket is already in flight: reduce the rest, then join
+                torch.distributed.all_reduce(self.online_net._flat_grad[:tail], group=self.process_group)
+                torch.cuda.current_stream().wait_stream(self._dp_stream)
+                self._dp_tail = None
+            else:
+                torch.distributed.all_reduce(self.online_net._flat_grad, group=self.process_group)
         self.optimiser.step()
 
     def compute_gradients(self, states, actions, returns, next_states, nonterminals, weights):
@@ -57,7 +77,9 @@ class Learner(Agent):
             if getattr(self, "_debug", None) is not None:                       # parity tests: the pass's activations
                 self._debug.update(keep=keep)
             on.zero_grad()                                                      # learner.py:22
+            on._grads_ready_hook = self._start_tail_allreduce if (self.process_group is not None and self.overlap_allreduce) else None
             on.backward_iqn(keep, dtheta, weights / weights.shape[0], actions)  # learner.py:23
+            on._grads_ready_hook = None
         return loss
 
     # ------------------------------------------------------------------ whole step: sample -> learn -> priority update
@@ -115,10 +137,14 @@ class Learner(Agent):
         self._step_post(mem, idxs, loss)
         return idxs, loss
 
-    def enable_cuda_graph(self, mem, warmup=3):
+    def enable_cuda_graph(self, mem, warmup=3, capture_collectives=True):
         """Capture learn_and_update(mem) in a CUDA graph (shapes are static: batch_size, N, N', K).  Everything that
         changes between steps lives on the device: Philox stream offsets, Adam bias corrections, beta and the replay
-        fill are read from a riqn_dyn_state struct that is refreshed by one 32-byte async copy per step."""
+        fill are read from a riqn_dyn_state struct that is refreshed by one 32-byte async copy per step.
+        Data parallel: the two NCCL all-reduces are captured too (ONE graph launch per step on every rank; the big bucket
+        overlaps the backward on a side stream inside the graph); capture_collectives=False keeps them eager between two
+        graphs (the round-1 scheme)."""
+        self._capture_collectives = bool(capture_collectives)
         from .dynstate import DynState
         dev = self.online_net._flat.device
         self._dyn = DynState(dev)
@@ -138,11 +164,12 @@ class Learner(Agent):
         self._dyn.write(nss, sbc, mem.transitions.get_current_capacity(), mem.priority_weight)
         self.online_net._static_ops_dirty = True     # the captured step must rebuild the conv / iqn_fc operand images
         post = None
-        if self.process_group is None:
+        if self.process_group is None or self._capture_collectives:
             with torch.cuda.graph(graph):
                 out = self._step_body(mem)
         else:
-            # data parallel: two graphs around an EAGER all-reduce (NCCL is kept out of stream capture)
+            # data parallel, eager collective: two graphs around one all-reduce of the whole arena
+            self.overlap_allreduce = False
             with torch.cuda.graph(graph):
                 out = self._step_pre(mem)
             post = torch.cuda.CUDAGraph()
@@ -187,7 +214,7 @@ class Learner(Agent):
         graph = torch.cuda.CUDAGraph()
         self.online_net._static_ops_dirty = True
         post = None
-        if self.process_group is None:
+        if self.process_group is None or getattr(self, "_capture_collectives", True):
             with torch.cuda.graph(graph):
                 out = body()
         else:

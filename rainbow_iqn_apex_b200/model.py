@@ -306,6 +306,7 @@ class DQN(nn.Module):
     def reset_noise(self, noise=None):
         """model.py:159-162.  ``noise``: optional {layer_name: (f(eps_in), f(eps_out))} injection.
         All NoisyLinear layers are redrawn and recomposed by ONE riqn_noisy_reset_net call (two launches)."""
+        self._noise_version = getattr(self, "_noise_version", 0) + 1     # backward passes check it: they read the LIVE weights
         layers = self.noisy_layers()
         if not self._flat.is_cuda or any(m.in_features % 4 for _, m in layers):
             for name, module in layers:
@@ -620,6 +621,7 @@ class DQN(nn.Module):
         call("riqn_dueling_fwd", R, B, hid, A, ptr(h), ptr(self._w_eff_z), ptr(self._b_eff_z), ptr(q))
         if keep is not None:
             keep.update(feat=feat, cos=cosv, xt=xt, h=h, q=q, tau=tau, num_quantiles=num_quantiles, tc=tc,
+                        noise_version=getattr(self, "_noise_version", 0),
                         head_bwd_tc=bwd_tc, emb_bwd_tc=emb_tc)
         return q
 
@@ -642,6 +644,9 @@ class DQN(nn.Module):
     def backward_iqn(self, keep, dtheta, gscale, actions):
         """Accumulate dL/dparams into the gradient arena for the forward recorded in ``keep``, where
         dL/dq[r, actions[b]] = dtheta[r] * gscale[b]  (r = quantile*B + b)."""
+        if keep.get("noise_version", None) != getattr(self, "_noise_version", 0):
+            raise RuntimeError("the network's noise was resampled between this forward pass and its backward: the composed "
+                               "weights / epsilons of the gradient pass are gone (call backward before the next reset_noise)")
         B = keep["feat"].shape[0]
         Nq = keep["num_quantiles"]
         R = B * Nq
@@ -706,6 +711,11 @@ class DQN(nn.Module):
                      ptr(hv.weight_epsilon), WGRAD_SPLIT_K, None, None, 0)
             call("riqn_noisy_bias_grad", R, 2 * hid, ptr(dh) if dh is not None else None, ptr(hv.bias_epsilon), ptr(dbs),
                  ptr(gv(hv.bias_mu)), ptr(gv(hv.bias_sigma)))
+            # from here on the gradients of every NoisyLinear layer (the arena from fcnoisy_h_v.weight_mu to its end, 96% of
+            # the bytes) are final: a data-parallel learner starts their all-reduce now, under the rest of the backward
+            hook = getattr(self, "_grads_ready_hook", None)
+            if hook is not None:
+                hook(self._offsets[id(hv.weight_mu)])
             # dx[r, i] = sum_o dh[r, o] W_eff[o, i]
             if fused_dh:     # W_eff (2*hid, 3136) itself is the (K, N) operand: no transposed weight image
                 call("riqn_gemm_bf16_tc_mn", R, FEAT, 2 * hid, ptr(dh_hi), ptr(w_bf), 0, None if dx_bf16 else ptr(dx), FEAT,
