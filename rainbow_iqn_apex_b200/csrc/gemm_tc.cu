@@ -28,23 +28,29 @@ namespace riqn {
 using bf16 = __nv_bfloat16;
 
 constexpr int TBM = 128, TBK = 64, UMMA_K = 16;   // tile N (BN) is a template parameter: 256, or 64 / 32 for narrow outputs
-constexpr int EPI_WARPS = 8;     // two warps per TMEM lane quarter, each draining half of the 256 accumulator columns
-constexpr int TC_THREADS = 64 + 32 * EPI_WARPS;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, then epilogue
+// Epilogue warps: a warp may only read the TMEM lane quarter (warp % 4), so they come in sets of four; each set drains an
+// equal share of the accumulator columns.  Two sets (8 warps) for the MMA-bound products; FOUR sets for the embedding
+// product, whose k = 64 mainloop is over in a microsecond and whose time is all epilogue latency (104 registers per
+// thread leave room for 18 warps per SM).
+constexpr int epi_warps(int epi) { return epi == TC_EMBED ? 16 : 8; }
+constexpr int tc_threads(int epi) { return 64 + 32 * epi_warps(epi); }  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner
+constexpr int MAX_EPI_WARPS = 16;
 
 
 // NSPLIT 1: a_hi*b_hi.  NSPLIT 3: a_hi*b_hi + a_hi*b_lo + a_lo*b_hi.  NSPLIT 2: A is exact in bf16 (e.g. uint8 pixels),
 // only B is split: a_hi*b_hi + a_hi*b_lo.
-template <int NSPLIT, int BN>
+template <int NSPLIT, int BN, int EPI>
 struct TcCfg {
   static constexpr int kAOps = NSPLIT == 3 ? 2 : 1, kBOps = NSPLIT == 1 ? 1 : 2;     // hi (+ lo) images per operand
   static constexpr int kOps = kAOps;                                                 // (A images; B tile starts after them)
   static constexpr uint32_t kABytes = TBM * TBK * 2, kBBytes = BN * TBK * 2;
   static constexpr uint32_t kStageBytes = kAOps * kABytes + kBOps * kBBytes;         // 48 / 80 / 96 KB at BN = 256
-  static constexpr int kStages = (192 * 1024) / kStageBytes > 6 ? 6 : (192 * 1024) / kStageBytes;
-  static constexpr uint32_t kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;                   // two accumulator buffers (power of 2)
   static constexpr uint32_t kEpiStage = 32 * 32 * 4;  // per epilogue warp: 32 rows x 32 words for the store transpose
-  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + EPI_WARPS * kEpiStage;
-  static_assert(kSmemBytes <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
+  static constexpr uint32_t kRingBytes = 224 * 1024 - epi_warps(EPI) * kEpiStage;      // 192 KB with two epilogue warp sets
+  static constexpr int kStages = kRingBytes / kStageBytes > 6 ? 6 : kRingBytes / kStageBytes;
+  static constexpr uint32_t kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;                   // two accumulator buffers (power of 2)
+  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + epi_warps(EPI) * kEpiStage;
+  static_assert(kSmemBytes <= 232448 && kStages >= 1, "exceeds the 227 KB per-CTA shared memory limit");
 };
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
@@ -270,10 +276,10 @@ struct TcArgs {
 };
 
 template <int NSPLIT, int EPI, int BN>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(tc_threads(EPI), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
                const __grid_constant__ CUtensorMap mapB_hi, const __grid_constant__ CUtensorMap mapB_lo, TcArgs p) {
-  using Cfg = TcCfg<NSPLIT, BN>;
+  using Cfg = TcCfg<NSPLIT, BN, EPI>;
   constexpr int TBN = BN;
   constexpr uint32_t TMEM_COLS = Cfg::kTmemCols;
   extern __shared__ uint8_t smem_raw[];
@@ -291,7 +297,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], EPI_WARPS); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], epi_warps(EPI)); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -412,7 +418,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
     const int chalf = (warp - 2) >> 2;            // which half of the accumulator columns this warp drains
     float conv_bias[32];
     if (EPI == TC_CONV) {                         // one n-tile (N <= 64): this warp's 32 columns never change
-      constexpr int CH0 = TBN >= 64 ? TBN / 2 : TBN;
+      constexpr int CH0 = TBN >= 64 ? TBN / 2 : TBN;     // (TC_CONV runs two warp sets)
 #pragma unroll
       for (int j = 0; j < 32; ++j) conv_bias[j] = (chalf * CH0 + j < p.N && chalf * CH0 < TBN) ? p.bias[chalf * CH0 + j] : 0.f;
     }
@@ -423,7 +429,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
       const int as = local & 1;
       const uint32_t aphase = (local >> 1) & 1;
       const int m = mt * TBM + quarter * 32 + lane;
-      constexpr int HALF = TBN >= 64 ? TBN / 2 : TBN;        // BN = 32: the second warp set has no columns to drain
+      constexpr int SETS = epi_warps(EPI) / 4;
+      constexpr int HALF = TBN >= 32 * SETS ? TBN / SETS : TBN;   // columns per warp set (BN = 32: only the first set has columns)
       // embedding epilogue: the Hadamard / bias math runs AFTER the staging transpose, where lane l owns the 4 columns of
       // piece (l & 7) for the rows r0 + (l >> 3): one 16-byte feat load and one bias load per 32-column chunk instead of
       // sixteen broadcast loads per thread (round 1: those loads were 60% of the kernel's LSU wavefronts)
@@ -632,30 +639,43 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
               // them as 8-byte pieces (a quarter-warp = one 64-byte row segment per image).
               stage_row(st, v, lane);
               const bool f16 = (p.fmt & 4) != 0;
-#pragma unroll
-              for (int r0 = 0; r0 < 32; r0 += 4) {
-                const int r = r0 + e_sub;
-                if (r < rows_valid) {
-                  if (!e_one_sample)
-                    ef = __ldg(reinterpret_cast<const float4*>(p.feat + (long)((m_base + r) / p.batch) * p.N + n0) + e_piece);
-                  const uint4 au = staged_piece(st, r, e_piece);
-                  const float x0 = ef.x * fmaxf(__uint_as_float(au.x) + eb.x, 0.f);
-                  const float x1 = ef.y * fmaxf(__uint_as_float(au.y) + eb.y, 0.f);
-                  const float x2 = ef.z * fmaxf(__uint_as_float(au.z) + eb.z, 0.f);
-                  const float x3 = ef.w * fmaxf(__uint_as_float(au.w) + eb.w, 0.f);
-                  const long o = (long)(m_base + r) * p.N + n0 + e_piece * 4;
+              const long o0 = (long)(m_base + e_sub) * p.N + n0 + e_piece * 4;
+              const long ostep = 4L * p.N;
+              auto emit = [&](int i, const uint4& a4, const float4& f) {
+                const float x0 = f.x * fmaxf(__uint_as_float(a4.x) + eb.x, 0.f);
+                const float x1 = f.y * fmaxf(__uint_as_float(a4.y) + eb.y, 0.f);
+                const float x2 = f.z * fmaxf(__uint_as_float(a4.z) + eb.z, 0.f);
+                const float x3 = f.w * fmaxf(__uint_as_float(a4.w) + eb.w, 0.f);
+                uint32_t w0, w1, l0, l1;
+                if (f16) {            // fp16(x) feeds the single-pass head forward, bf16(x) the backward products
+                  w0 = pack16x2(x0, x1, true); w1 = pack16x2(x2, x3, true);
+                  l0 = pack16x2(x0, x1, false); l1 = pack16x2(x2, x3, false);
+                } else {              // bf16 hi + residual lo (split-bf16 x3 head forward)
+                  w0 = pack16x2(x0, x1, false); w1 = pack16x2(x2, x3, false);
+                  l0 = pack16x2(x0 - __uint_as_float(w0 << 16), x1 - __uint_as_float(w0 & 0xffff0000u), false);
+                  l1 = pack16x2(x2 - __uint_as_float(w1 << 16), x3 - __uint_as_float(w1 & 0xffff0000u), false);
+                }
+                if (4 * i + e_sub < rows_valid) {
+                  const long o = o0 + i * ostep;
                   if (p.C) *reinterpret_cast<float4*>(p.C + o) = make_float4(x0, x1, x2, x3);
-                  uint32_t w0, w1, l0, l1;
-                  if (f16) {            // fp16(x) feeds the single-pass head forward, bf16(x) the backward products
-                    w0 = pack16x2(x0, x1, true); w1 = pack16x2(x2, x3, true);
-                    l0 = pack16x2(x0, x1, false); l1 = pack16x2(x2, x3, false);
-                  } else {              // bf16 hi + residual lo (split-bf16 x3 head forward)
-                    w0 = pack16x2(x0, x1, false); w1 = pack16x2(x2, x3, false);
-                    l0 = pack16x2(x0 - __uint_as_float(w0 << 16), x1 - __uint_as_float(w0 & 0xffff0000u), false);
-                    l1 = pack16x2(x2 - __uint_as_float(w1 << 16), x3 - __uint_as_float(w1 & 0xffff0000u), false);
-                  }
                   if (p.o_hi) *reinterpret_cast<uint2*>(p.o_hi + o) = make_uint2(w0, w1);
                   if (p.o_lo) *reinterpret_cast<uint2*>(p.o_lo + o) = make_uint2(l0, l1);
+                }
+              };
+              if (e_one_sample) {
+                // all eight 16-byte pieces of this lane are fetched back to back (one shared-memory latency instead of
+                // eight dependent ones: round 2's profile had the epilogue warps waiting on the first use of every piece)
+                uint4 au[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) au[i] = staged_piece(st, 4 * i + e_sub, e_piece);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) emit(i, au[i], ef);
+              } else {                // rows of several samples in one warp (fewer than 32 quantiles per sample): per-row feat
+#pragma unroll 1
+                for (int i = 0; i < 8; ++i) {
+                  const int rr = m_base + 4 * i + e_sub;
+                  const float4 f = __ldg(reinterpret_cast<const float4*>(p.feat + (long)((rr < p.M ? rr : 0) / p.batch) * p.N + n0) + e_piece);
+                  emit(i, staged_piece(st, 4 * i + e_sub, e_piece), f);
                 }
               }
             }
@@ -706,7 +726,7 @@ static int make_map(CUtensorMap* map, const bf16* base, long rows, long K, int b
 template <int NSPLIT, int EPI, int BN>
 static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
                      const TcArgs& p, cudaStream_t s) {
-  using Cfg = TcCfg<NSPLIT, BN>;
+  using Cfg = TcCfg<NSPLIT, BN, EPI>;
   static PerDeviceOnce attr_once;
   const int attr_dev = PerDeviceOnce::device();
   if (!attr_once.done[attr_dev]) {
@@ -721,7 +741,7 @@ static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUt
   }
   const int units = p.m_tiles * p.n_tiles * p.k_splits;
   const int grid = units < sms ? units : sms;
-  gemm_tc_kernel<NSPLIT, EPI, BN><<<grid, TC_THREADS, Cfg::kSmemBytes, s>>>(a_hi, a_lo, b_hi, b_lo, p);
+  gemm_tc_kernel<NSPLIT, EPI, BN><<<grid, tc_threads(EPI), Cfg::kSmemBytes, s>>>(a_hi, a_lo, b_hi, b_lo, p);
   return (int)cudaGetLastError();
 }
 
@@ -756,6 +776,7 @@ int gemm_bf16_tc(int M, int N, int K, const bf16* A_hi, const bf16* A_lo, const 
     auto eff = [](long t) { const long r = (t + 147) / 148; return (double)t / (double)(r * 148); };
     if (eff(t128) > eff(t256) + 0.08) bn = 128;
   }
+  if (epi == TC_EMBED) bn = 128;   // four epilogue warp sets x one 32-column chunk; 64 KB stages leave room for their staging
   // (32-wide tiles for conv3's 324 strip tiles were tried: slower -- only four epilogue warps drain a 32-column tile)
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int rc;
@@ -825,7 +846,7 @@ int gemm_bf16_tc(int M, int N, int K, const bf16* A_hi, const bf16* A_lo, const 
       case TC_NOISY_WGRAD: RIQN_TC_GO(3, TC_NOISY_WGRAD);
       case TC_BIAS_RELU_NCHW: RIQN_TC_NARROW(3, TC_BIAS_RELU_NCHW); RIQN_TC_GO(3, TC_BIAS_RELU_NCHW);
       case TC_CONV: RIQN_TC_NARROW(3, TC_CONV); break;
-      case TC_EMBED: RIQN_TC_GO(3, TC_EMBED);
+      case TC_EMBED: return launch_tc<3, TC_EMBED, 128>(ma_hi, ma_lo, mb_hi, mb_lo, p, s);
     }
   } else if (split2) {
     switch (epi) {
@@ -843,7 +864,7 @@ int gemm_bf16_tc(int M, int N, int K, const bf16* A_hi, const bf16* A_lo, const 
       case TC_NOISY_WGRAD: RIQN_TC_GO(1, TC_NOISY_WGRAD);
       case TC_BIAS_RELU_NCHW: RIQN_TC_NARROW(1, TC_BIAS_RELU_NCHW); RIQN_TC_GO(1, TC_BIAS_RELU_NCHW);
       case TC_CONV: RIQN_TC_NARROW(1, TC_CONV); break;
-      case TC_EMBED: RIQN_TC_GO(1, TC_EMBED);
+      case TC_EMBED: return launch_tc<1, TC_EMBED, 128>(ma_hi, ma_lo, mb_hi, mb_lo, p, s);
     }
   }
 #undef RIQN_TC_NARROW
