@@ -315,7 +315,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
-        const int ks = u % p.k_splits, t = u / p.k_splits;
+        // split-K units are k-split MAJOR: the CTAs in flight walk the SAME reduction range of all output tiles, so each
+        // operand slab is fetched from HBM once and shared through L2 (tile-major order read 2.7x the algorithmic bytes)
+        const int tiles = p.m_tiles * p.n_tiles;
+        const int ks = u / tiles, t = u - ks * tiles;
         const int nt = t % p.n_tiles, mt = t / p.n_tiles;   // n fastest: the A tile is shared by the n-tiles in flight
         const int kb0 = ks * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -372,7 +375,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
       uint32_t phase = 0;
       int local = 0;
       for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++local) {
-        const int ks = u % p.k_splits;
+        const int ks = u / (p.m_tiles * p.n_tiles);
         const int kb0 = ks * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
         const int as = local & 1;
         const uint32_t aphase = (local >> 1) & 1;
@@ -424,7 +427,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
     }
     int local = 0;
     for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++local) {
-      const int t = u / p.k_splits;
+      const int t = u % (p.m_tiles * p.n_tiles);
       const int nt = t % p.n_tiles, mt = t / p.n_tiles;
       const int as = local & 1;
       const uint32_t aphase = (local >> 1) & 1;
