@@ -352,9 +352,20 @@ def run_ours(args):
         out["cpu_baseline"] = cpu_baseline(max_seconds=25.0)
     if rank == 0:
         print(json.dumps(out))
+    finish(world)
+
+
+def finish(world):
+    """End of a run: all ranks meet once more, then leave WITHOUT tearing NCCL down.  destroy_process_group() (and the
+    interpreter's own teardown) can block forever when CUDA graphs that captured collectives are still alive (seen on
+    2 GPUs in round 2: the result line was out, the process never exited).  A benchmark process has nothing to clean up."""
+    sys.stdout.flush()
+    sys.stderr.flush()
     if world > 1:
+        torch.cuda.synchronize()
         torch.distributed.barrier()
-        torch.distributed.destroy_process_group()
+        torch.cuda.synchronize()
+        os._exit(0)
 
 
 def loss_kernel_point(dev, batch, pk):
@@ -515,8 +526,7 @@ def run_apex(args):
            "exchange_bytes_per_step": {"windows_to_learner": B * 7 * 7056, "losses_broadcast": 4 * B, "parameters_every_100": 26903576}}
     if rank == 0:
         print(json.dumps(out))
-    torch.distributed.barrier()
-    torch.distributed.destroy_process_group()
+    finish(world)
 
 
 def fill_replay_segments(mem, device, seed):
