@@ -34,7 +34,6 @@ constexpr int TBM = 128, TBK = 64, UMMA_K = 16;   // tile N (BN) is a template p
 // thread leave room for 18 warps per SM).
 constexpr int epi_warps(int epi) { return epi == TC_EMBED ? 16 : 8; }
 constexpr int tc_threads(int epi) { return 64 + 32 * epi_warps(epi); }  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner
-constexpr int MAX_EPI_WARPS = 16;
 
 
 // NSPLIT 1: a_hi*b_hi.  NSPLIT 3: a_hi*b_hi + a_hi*b_lo + a_lo*b_hi.  NSPLIT 2: A is exact in bf16 (e.g. uint8 pixels),
@@ -46,10 +45,12 @@ struct TcCfg {
   static constexpr uint32_t kABytes = TBM * TBK * 2, kBBytes = BN * TBK * 2;
   static constexpr uint32_t kStageBytes = kAOps * kABytes + kBOps * kBBytes;         // 48 / 80 / 96 KB at BN = 256
   static constexpr uint32_t kEpiStage = 32 * 32 * 4;  // per epilogue warp: 32 rows x 32 words for the store transpose
-  static constexpr uint32_t kRingBytes = 224 * 1024 - epi_warps(EPI) * kEpiStage;      // 192 KB with two epilogue warp sets
+  static constexpr uint32_t kFbBytes = EPI == TC_EMBED ? epi_warps(EPI) * 256 : 0;   // per-warp feat / bias broadcast patches
+  static constexpr uint32_t kRingBytes = 224 * 1024 - epi_warps(EPI) * kEpiStage - kFbBytes;   // 192 KB with two warp sets
   static constexpr int kStages = kRingBytes / kStageBytes > 6 ? 6 : kRingBytes / kStageBytes;
   static constexpr uint32_t kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;                   // two accumulator buffers (power of 2)
-  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + epi_warps(EPI) * kEpiStage;
+  static constexpr uint32_t kSmemBytes =
+      kStages * kStageBytes + 1024 /*align*/ + epi_warps(EPI) * kEpiStage + 256 /*barriers*/ + kFbBytes;
   static_assert(kSmemBytes <= 232448 && kStages >= 1, "exceeds the 227 KB per-CTA shared memory limit");
 };
 
@@ -84,6 +85,16 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
       : "memory");
 }
+// TMA store of a staged (rows x 32 elements) 16-bit tile; out-of-range rows / columns are clipped by the tensor map
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(reinterpret_cast<uint64_t>(map)),
+               "r"(c0), "r"(c1), "r"(src)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
@@ -253,7 +264,8 @@ __device__ __forceinline__ void store_transposed_pairs(bf16* tb, const uint32_t*
   }
 }
 
-struct TcArgs {
+struct alignas(64) TcArgs {
+  CUtensorMap mapO[2];   // TC_EMBED: TMA-store maps of o_hi / o_lo ((M, N) 16-bit row-major, box 32 x 32, 64-byte swizzle)
   int M, N, K;
   int m_tiles, n_tiles, k_splits, kb_per_split, kb_total;
   float* C;
@@ -278,19 +290,22 @@ struct TcArgs {
 template <int NSPLIT, int EPI, int BN>
 __global__ void __launch_bounds__(tc_threads(EPI), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
-               const __grid_constant__ CUtensorMap mapB_hi, const __grid_constant__ CUtensorMap mapB_lo, TcArgs p) {
+               const __grid_constant__ CUtensorMap mapB_hi, const __grid_constant__ CUtensorMap mapB_lo,
+               const __grid_constant__ TcArgs p) {
   using Cfg = TcCfg<NSPLIT, BN, EPI>;
   constexpr int TBN = BN;
   constexpr uint32_t TMEM_COLS = Cfg::kTmemCols;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  // layout: operand ring | per-warp epilogue staging tiles (4 KB each, 4 KB aligned) | barriers | feat / bias patches
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes + epi_warps(EPI) * Cfg::kEpiStage);
   uint64_t* full = bars;                       // [kStages]  TMA -> MMA
   uint64_t* empty = bars + Cfg::kStages;       // [kStages]  MMA -> TMA
   uint64_t* tfull = bars + 2 * Cfg::kStages;   // [2]        MMA -> epilogue
   uint64_t* tempty = tfull + 2;                // [2]        epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  const uint32_t epi_stage = (uint32_t)__cvta_generic_to_shared(smem + Cfg::kStages * Cfg::kStageBytes + 256);
+  const uint32_t epi_stage = (uint32_t)__cvta_generic_to_shared(smem + Cfg::kStages * Cfg::kStageBytes);
+  const uint32_t epi_fb = epi_stage + epi_warps(EPI) * Cfg::kEpiStage + 256;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_units = p.m_tiles * p.n_tiles * p.k_splits;
@@ -434,10 +449,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
       const int m = mt * TBM + quarter * 32 + lane;
       constexpr int SETS = epi_warps(EPI) / 4;
       constexpr int HALF = TBN >= 32 * SETS ? TBN / SETS : TBN;   // columns per warp set (BN = 32: only the first set has columns)
-      // embedding epilogue: the Hadamard / bias math runs AFTER the staging transpose, where lane l owns the 4 columns of
-      // piece (l & 7) for the rows r0 + (l >> 3): one 16-byte feat load and one bias load per 32-column chunk instead of
-      // sixteen broadcast loads per thread (round 1: those loads were 60% of the kernel's LSU wavefronts)
-      const int e_piece = lane & 7, e_sub = lane >> 3;
+      // embedding epilogue: lane = row.  The 32 feat / bias values of a chunk are fetched by ONE coalesced load per warp
+      // (lane j loads column j) and broadcast through a 256-byte shared-memory patch; the finished 16-bit tiles are staged
+      // in the TMA 64-byte-swizzle layout and leave through cp.async.bulk.tensor stores -- no per-thread global stores and
+      // no read-back of the staging tile (round 2: the LSU data pipe was the limiter of this kernel)
       const int e_mbase = mt * TBM + quarter * 32;
       const bool e_one_sample = (p.batch & 31) == 0;          // sample-major rows: a warp's 32 rows share one feature row
       const float* embed_feat_row = nullptr;
@@ -449,10 +464,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
       for (int c = chalf * HALF; c < (chalf + 1) * HALF && c < TBN; c += 32) {
         const int n0 = nt * TBN + c;
         // this chunk's feat / bias values are requested BEFORE the accumulator load: their latency overlaps the TMEM read
-        float4 ef = make_float4(0.f, 0.f, 0.f, 0.f), eb = ef;
+        float ef = 0.f, eb = 0.f;
         if (EPI == TC_EMBED && n0 + 32 <= p.N) {
-          eb = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + e_piece);
-          if (e_one_sample) ef = __ldg(reinterpret_cast<const float4*>(embed_feat_row + n0) + e_piece);
+          eb = __ldg(p.bias + n0 + lane);
+          if (e_one_sample) ef = __ldg(embed_feat_row + n0 + lane);
         }
         uint32_t v[32];
         tmem_ld32(trow + c, v);
@@ -554,13 +569,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
             stage_row(st, hw, lane);
             const int sub = lane >> 3, piece = lane & 7;
             bf16* dstb = piece < 4 ? p.nx_hi : p.nx_lo;
+            uint4 pc[8];                      // all pieces in flight before the first store (one shared-memory latency)
+            long orow[8];
 #pragma unroll
-            for (int r0 = 0; r0 < 32; r0 += 4) {
-              const int r = r0 + sub;
-              const long orow = __shfl_sync(0xffffffffu, o, r);
-              if (orow >= 0 && dstb != nullptr)
-                *reinterpret_cast<uint4*>(dstb + orow + (piece & 3) * 8) = staged_piece(st, r, piece);
+            for (int i = 0; i < 8; ++i) {
+              pc[i] = staged_piece(st, 4 * i + sub, piece);
+              orow[i] = __shfl_sync(0xffffffffu, o, 4 * i + sub);
             }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (orow[i] >= 0 && dstb != nullptr) *reinterpret_cast<uint4*>(dstb + orow[i] + (piece & 3) * 8) = pc[i];
           }
         }
         if (EPI == TC_COL2IM && n0 < p.N) {
@@ -638,48 +656,51 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
               }
             } else {
               // x = feat[b] * relu(acc + bias)   (model.py:146-151); N % 32 == 0 is required by the host wrapper.
-              // Raw accumulators go through the staging transpose; each lane then finishes 4 columns of 8 rows and writes
-              // them as 8-byte pieces (a quarter-warp = one 64-byte row segment per image).
-              stage_row(st, v, lane);
               const bool f16 = (p.fmt & 4) != 0;
-              const long o0 = (long)(m_base + e_sub) * p.N + n0 + e_piece * 4;
-              const long ostep = 4L * p.N;
-              auto emit = [&](int i, const uint4& a4, const float4& f) {
-                const float x0 = f.x * fmaxf(__uint_as_float(a4.x) + eb.x, 0.f);
-                const float x1 = f.y * fmaxf(__uint_as_float(a4.y) + eb.y, 0.f);
-                const float x2 = f.z * fmaxf(__uint_as_float(a4.z) + eb.z, 0.f);
-                const float x3 = f.w * fmaxf(__uint_as_float(a4.w) + eb.w, 0.f);
-                uint32_t w0, w1, l0, l1;
+              const uint32_t fb = epi_fb + (warp - 2) * 256;
+              const bool row_ok = m < p.M;
+              const float* frow = p.feat + (long)((row_ok ? m : 0) / p.batch) * p.N + n0;   // per-row feat (several samples per warp)
+              if (lane == 0) tma_store_wait_read();               // the previous tile's stores have read this staging tile
+              __syncwarp();
+              asm volatile("st.shared.b32 [%0], %1;" ::"r"(fb + lane * 4), "r"(__float_as_uint(ef)) : "memory");
+              asm volatile("st.shared.b32 [%0], %1;" ::"r"(fb + 128 + lane * 4), "r"(__float_as_uint(eb)) : "memory");
+              __syncwarp();
+              uint32_t w0[16], w1[16];                            // image 0 / image 1 column pairs of this lane's row
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const uint4 bu = lds128(fb + 128 + 16 * j);
+                uint4 fu;
+                if (e_one_sample) fu = lds128(fb + 16 * j);
+                else fu = __ldg(reinterpret_cast<const uint4*>(frow) + j);
+                const float x0 = __uint_as_float(fu.x) * fmaxf(__uint_as_float(v[4 * j]) + __uint_as_float(bu.x), 0.f);
+                const float x1 = __uint_as_float(fu.y) * fmaxf(__uint_as_float(v[4 * j + 1]) + __uint_as_float(bu.y), 0.f);
+                const float x2 = __uint_as_float(fu.z) * fmaxf(__uint_as_float(v[4 * j + 2]) + __uint_as_float(bu.z), 0.f);
+                const float x3 = __uint_as_float(fu.w) * fmaxf(__uint_as_float(v[4 * j + 3]) + __uint_as_float(bu.w), 0.f);
+                if (p.C && row_ok) *reinterpret_cast<float4*>(p.C + (long)m * p.N + n0 + 4 * j) = make_float4(x0, x1, x2, x3);
                 if (f16) {            // fp16(x) feeds the single-pass head forward, bf16(x) the backward products
-                  w0 = pack16x2(x0, x1, true); w1 = pack16x2(x2, x3, true);
-                  l0 = pack16x2(x0, x1, false); l1 = pack16x2(x2, x3, false);
+                  w0[2 * j] = pack16x2(x0, x1, true); w0[2 * j + 1] = pack16x2(x2, x3, true);
+                  w1[2 * j] = pack16x2(x0, x1, false); w1[2 * j + 1] = pack16x2(x2, x3, false);
                 } else {              // bf16 hi + residual lo (split-bf16 x3 head forward)
-                  w0 = pack16x2(x0, x1, false); w1 = pack16x2(x2, x3, false);
-                  l0 = pack16x2(x0 - __uint_as_float(w0 << 16), x1 - __uint_as_float(w0 & 0xffff0000u), false);
-                  l1 = pack16x2(x2 - __uint_as_float(w1 << 16), x3 - __uint_as_float(w1 & 0xffff0000u), false);
+                  const uint32_t h0 = pack16x2(x0, x1, false), h1 = pack16x2(x2, x3, false);
+                  w0[2 * j] = h0; w0[2 * j + 1] = h1;
+                  w1[2 * j] = pack16x2(x0 - __uint_as_float(h0 << 16), x1 - __uint_as_float(h0 & 0xffff0000u), false);
+                  w1[2 * j + 1] = pack16x2(x2 - __uint_as_float(h1 << 16), x3 - __uint_as_float(h1 & 0xffff0000u), false);
                 }
-                if (4 * i + e_sub < rows_valid) {
-                  const long o = o0 + i * ostep;
-                  if (p.C) *reinterpret_cast<float4*>(p.C + o) = make_float4(x0, x1, x2, x3);
-                  if (p.o_hi) *reinterpret_cast<uint2*>(p.o_hi + o) = make_uint2(w0, w1);
-                  if (p.o_lo) *reinterpret_cast<uint2*>(p.o_lo + o) = make_uint2(l0, l1);
-                }
-              };
-              if (e_one_sample) {
-                // all eight 16-byte pieces of this lane are fetched back to back (one shared-memory latency instead of
-                // eight dependent ones: round 2's profile had the epilogue warps waiting on the first use of every piece)
-                uint4 au[8];
+              }
+              // 32 rows x 64 bytes per image in the TMA SWIZZLE_64B layout: 16-byte chunk c of row r sits at chunk c ^ ((r >> 1) & 3)
+              const uint32_t srow = st + lane * 64;
+              const int sw = (lane >> 1) & 3;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) au[i] = staged_piece(st, 4 * i + e_sub, e_piece);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) emit(i, au[i], ef);
-              } else {                // rows of several samples in one warp (fewer than 32 quantiles per sample): per-row feat
-#pragma unroll 1
-                for (int i = 0; i < 8; ++i) {
-                  const int rr = m_base + 4 * i + e_sub;
-                  const float4 f = __ldg(reinterpret_cast<const float4*>(p.feat + (long)((rr < p.M ? rr : 0) / p.batch) * p.N + n0) + e_piece);
-                  emit(i, staged_piece(st, 4 * i + e_sub, e_piece), f);
-                }
+              for (int c = 0; c < 4; ++c) {
+                if (p.o_hi) sts128(srow + ((c ^ sw) << 4), w0[4 * c], w0[4 * c + 1], w0[4 * c + 2], w0[4 * c + 3]);
+                if (p.o_lo) sts128(srow + 2048 + ((c ^ sw) << 4), w1[4 * c], w1[4 * c + 1], w1[4 * c + 2], w1[4 * c + 3]);
+              }
+              fence_proxy_async();                                // generic-proxy writes -> visible to the TMA engine
+              __syncwarp();
+              if (lane == 0) {
+                if (p.o_hi) tma_store_2d(&p.mapO[0], st, n0, m_base);
+                if (p.o_lo) tma_store_2d(&p.mapO[1], st + 2048, n0, m_base);
+                tma_store_commit();
               }
             }
           }
@@ -690,6 +711,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
       if (lane == 0) mbar_arrive(&tempty[as]);
     }
   }
+  if (EPI == TC_EMBED && warp >= 2 && lane == 0) tma_store_wait_all();   // bulk stores read this CTA's shared memory
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -722,6 +744,20 @@ static int make_map(CUtensorMap* map, const bf16* base, long rows, long K, int b
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
+}
+
+// (rows, cols) row-major 16-bit matrix written by TMA stores of 32 x 32 boxes staged in the 64-byte-swizzle layout
+static int make_store_map(CUtensorMap* map, const bf16* base, long rows, long cols) {
+  auto enc = get_encode();
+  if (!enc) return (int)cudaErrorNotSupported;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)(cols * sizeof(bf16))};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
 }
@@ -835,6 +871,10 @@ int gemm_bf16_tc(int M, int N, int K, const bf16* A_hi, const bf16* A_lo, const 
   if ((p.fmt & 3) == 1 || (p.fmt & 3) == 2) return (int)cudaErrorInvalidValue;   // mixed fp16 x bf16: illegal instruction
   if ((p.fmt & 4) && epi != TC_EMBED) return (int)cudaErrorInvalidValue;
   if (epi == TC_EMBED && ((N % 32) || (M % 2) || p.o_hiT || p.o_loT)) return (int)cudaErrorInvalidValue;
+  if (epi == TC_EMBED) {            // the 16-bit images leave through TMA stores
+    if (p.o_hi && (rc = make_store_map(&p.mapO[0], p.o_hi, M, N))) return rc;
+    if (p.o_lo && (rc = make_store_map(&p.mapO[1], p.o_lo, M, N))) return rc;
+  }
 #define RIQN_TC_GO(NS, EP) return launch_tc<NS, EP, 256>(ma_hi, ma_lo, mb_hi, mb_lo, p, s)
 #define RIQN_TC_NARROW(NS, EP)                                                                  \
   if (bn == 32) return launch_tc<NS, EP, 32>(ma_hi, ma_lo, mb_hi, mb_lo, p, s);                  \
