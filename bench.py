@@ -471,13 +471,20 @@ def run_apex(args):
     agent.train()
     parallel.publish_parameters(agent, src=0)                  # everyone starts from the learner's weights
     flushed = [0]
+    graphed = [False]
 
     def step():
         nonlocal states
         batch = topo.sample(mem, beta=0.4, device=dev)
         if topo.is_learner:
             _, _, st, ac, rt, nx, nt, w = batch
-            loss = agent.learn_on_batch(st, ac, rt, nx, nt, w).detach()
+            if not args.no_graph and not graphed[0]:       # capture learn_on_batch once the first gathered batch fixes the shapes
+                agent.enable_learn_graph((st, ac, rt, nx, nt, w))
+                graphed[0] = True
+            if graphed[0]:
+                loss = agent.learn_on_graph((st, ac, rt, nx, nt, w)).detach()
+            else:
+                loss = agent.learn_on_batch(st, ac, rt, nx, nt, w).detach()
         else:
             loss = torch.empty(B, dtype=torch.float32, device=dev)
             for _ in range(args.acts_per_step):                # acting overlaps the learner's step

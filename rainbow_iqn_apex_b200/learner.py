@@ -110,7 +110,8 @@ class Learner(Agent):
         dyn = self._dyn if on else None
         self._dyn_on = bool(on)
         self.optimiser._dyn = dyn
-        mem.transitions._dyn = dyn
+        if mem is not None:
+            mem.transitions._dyn = dyn
         self.online_net.begin_step(dyn)
         self.target_net.begin_step(dyn)
 
@@ -227,6 +228,56 @@ class Learner(Agent):
         self._bgraph, self._bgraph_post, self._bg_out = graph, post, out
         self._attach_dyn(mem, False)
         return self
+
+    def enable_learn_graph(self, example):
+        """CUDA graph of learn_on_batch alone (no replay on this rank): the Ape-X learner, whose minibatch is gathered from
+        the actor GPUs' shards (apex.ApexTopology.sample).  ``example`` = (states, actions, returns, next_states,
+        nonterminals, weights) device tensors defining the shapes; learn_on_graph(batch) copies a batch into the static
+        inputs and replays.  Returns self."""
+        from .dynstate import DynState
+        if getattr(self, "_dyn", None) is None:
+            self._dyn = DynState(self.online_net._flat.device)
+        self._lg_in = tuple(t.contiguous().clone() for t in example)
+
+        def body():
+            self.online_net.begin_step(self._dyn)
+            self.target_net.begin_step(self._dyn)
+            loss = self.compute_gradients(*self._lg_in)
+            self.apply_gradients()
+            return loss
+
+        self._attach_dyn(None, True)
+        step0 = self.optimiser._step
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                nss, sbc = self.optimiser.bias_corrections(self.optimiser._step + 1)
+                self._dyn.write(nss, sbc, 1.0, 0.0)
+                body()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        nss, sbc = self.optimiser.bias_corrections(self.optimiser._step + 1)
+        self._dyn.write(nss, sbc, 1.0, 0.0)
+        self.online_net._static_ops_dirty = True
+        with torch.cuda.graph(graph):
+            out = body()
+        self.optimiser._step = step0 + 2
+        self._lgraph, self._lg_out = graph, out
+        self._attach_dyn(None, False)
+        return self
+
+    def learn_on_graph(self, batch):
+        """One learner step on ``batch`` (same shapes as enable_learn_graph's example) through the captured graph; returns
+        the per-transition loss (static buffer, overwritten by the next call)."""
+        for d, src in zip(self._lg_in, batch):
+            d.copy_(src, non_blocking=True)
+        nss, sbc = self.optimiser.bias_corrections(self.optimiser._step + 1)
+        self._dyn.write(nss, sbc, 1.0, 0.0)
+        self._lgraph.replay()
+        self.optimiser._step += 1
+        return self._lg_out
 
     def prefetch_host_batch(self, host_batch):
         """Start the H2D copy of a FUTURE minibatch on a side stream (double-buffered device staging), so that it
