@@ -14,7 +14,6 @@ int colsum_atomic(long M, int N, const float* X, float* out, cudaStream_t s);
 __global__ void c51_head_fwd_kernel(int A, int atoms, const float* __restrict__ zv, const float* __restrict__ za,
                                     const float* __restrict__ support, float* __restrict__ p, float* __restrict__ logp,
                                     int64_t* __restrict__ a_star) {
-  pdl_sync();
   extern __shared__ float sm[];      // amean[atoms] | ev[A]
   float* amean = sm;
   float* ev = sm + atoms;
@@ -68,7 +67,6 @@ __global__ void c51_loss_kernel(int A, int atoms, const float* __restrict__ logp
                                 const float* __restrict__ returns, const float* __restrict__ nonterminals,
                                 const float* __restrict__ support, float gamma_n, float vmin, float vmax, float delta_z,
                                 float* __restrict__ loss, float* __restrict__ dq, float* __restrict__ m_out) {
-  pdl_sync();
   extern __shared__ float sm[];      // m[atoms] | lo[atoms] | up[atoms] | wl[atoms] | wu[atoms]
   float* m = sm;
   int* lo = reinterpret_cast<int*>(sm + atoms);
@@ -117,7 +115,6 @@ __global__ void c51_loss_kernel(int A, int atoms, const float* __restrict__ logp
 // dzv[b,j] = g*dq[b,j] ; dza[b,a,j] = g*dq[b,j]*(1{a==act} - 1/A)
 __global__ void c51_head_bwd_kernel(int B, int A, int atoms, const float* __restrict__ dq, const float* __restrict__ gscale,
                                     const int64_t* __restrict__ actions, float* __restrict__ dzv, float* __restrict__ dza) {
-  pdl_sync();
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long)B * A * atoms) return;
   const int j = (int)(idx % atoms), a = (int)((idx / atoms) % A);
@@ -128,7 +125,6 @@ __global__ void c51_head_bwd_kernel(int B, int A, int atoms, const float* __rest
 }
 
 __global__ void relu_mask_kernel(long n, const float* __restrict__ act, float* __restrict__ grad) {
-  pdl_sync();
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n && !(act[i] > 0.f)) grad[i] = 0.f;
 }
@@ -141,7 +137,7 @@ RIQN_API int riqn_c51_head_fwd(int batch, int action_space, int atoms, const flo
                                const float* support, float* p, float* logp, long long* a_star, void* stream) {
   riqn::note_launches(1);
   if (atoms > 64) return (int)cudaErrorInvalidValue;
-  riqn::launch_pdl(c51_head_fwd_kernel, batch, 256, sizeof(float) * (atoms + action_space), (cudaStream_t)stream, 
+  c51_head_fwd_kernel<<<batch, 256, sizeof(float) * (atoms + action_space), (cudaStream_t)stream>>>(
       action_space, atoms, zv, za, support, p, logp, (int64_t*)a_star);
   return (int)cudaGetLastError();
 }
@@ -151,7 +147,7 @@ RIQN_API int riqn_c51_loss_fwd_bwd(int batch, int action_space, int atoms, const
                                    const float* nonterminals, const float* support, float gamma_n, float v_min, float v_max,
                                    float delta_z, float* loss, float* dq, float* m_out, void* stream) {
   riqn::note_launches(1);
-  riqn::launch_pdl(c51_loss_kernel, batch, 64, sizeof(float) * 5 * atoms, (cudaStream_t)stream, 
+  c51_loss_kernel<<<batch, 64, sizeof(float) * 5 * atoms, (cudaStream_t)stream>>>(
       action_space, atoms, logp_online, p_target, (const int64_t*)actions, (const int64_t*)a_star, returns, nonterminals,
       support, gamma_n, v_min, v_max, delta_z, loss, dq, m_out);
   return (int)cudaGetLastError();
@@ -161,14 +157,14 @@ RIQN_API int riqn_c51_head_bwd(int batch, int action_space, int atoms, const flo
                                const long long* actions, float* dzv, float* dza, void* stream) {
   riqn::note_launches(1);
   const long n = (long)batch * action_space * atoms;
-  riqn::launch_pdl(c51_head_bwd_kernel, riqn_cdiv(n, 256), 256, 0, (cudaStream_t)stream, batch, action_space, atoms, dq, gscale,
+  c51_head_bwd_kernel<<<riqn_cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(batch, action_space, atoms, dq, gscale,
                                                                           (const int64_t*)actions, dzv, dza);
   return (int)cudaGetLastError();
 }
 
 RIQN_API int riqn_relu_mask(long n, const float* act, float* grad, void* stream) {
   riqn::note_launches(1);
-  riqn::launch_pdl(relu_mask_kernel, riqn_cdiv(n, 256), 256, 0, (cudaStream_t)stream, n, act, grad);
+  relu_mask_kernel<<<riqn_cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(n, act, grad);
   return (int)cudaGetLastError();
 }
 

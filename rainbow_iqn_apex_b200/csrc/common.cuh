@@ -4,7 +4,6 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
-#include <stdlib.h>
 
 #define RIQN_API extern "C" __attribute__((visibility("default")))
 
@@ -21,47 +20,6 @@
   } while (0)
 
 namespace riqn { void note_launches(int n); }   // bookkeeping for riqn_launch_count()
-
-// ----------------------------------------------------------------------------------------------
-// Programmatic dependent launch (PDL).  Every kernel of the step starts with pdl_sync(): it first lets the NEXT kernel
-// of the stream begin launching (griddepcontrol.launch_dependents: the dependent grid is scheduled once every CTA of
-// this grid has started) and then waits until the PREVIOUS grid has completed and flushed its memory
-// (griddepcontrol.wait) before it touches anything.  With the launch attribute below, launch latency (and, in the tcgen05
-// GEMM, the barrier / TMEM prologue placed before the wait) overlaps the predecessor's tail instead of following it.
-// Safe by construction: nothing global is read or written before the wait, and waits chain transitively.
-// ----------------------------------------------------------------------------------------------
-__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_sync() {
-  pdl_trigger();
-  pdl_wait();
-}
-
-namespace riqn {
-// kernel<<<grid, block, smem, stream>>>(args...) with the programmatic-stream-serialization attribute (captured into
-// CUDA graphs as programmatic dependency edges).  RIQN_NO_PDL=1 in the environment launches plainly (A/B measurements).
-inline bool pdl_enabled() {
-  static const bool on = [] {
-    const char* e = getenv("RIQN_NO_PDL");
-    return !(e && e[0] == '1');
-  }();
-  return on;
-}
-template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid;
-  cfg.blockDim = block;
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
-}
-}  // namespace riqn
 
 static inline int riqn_cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 

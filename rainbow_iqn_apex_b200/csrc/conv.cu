@@ -23,7 +23,6 @@ __device__ __forceinline__ float load_px<float>(const float* p) { return *p; }
 // col[m, k] , m = (b, oh, ow), k = (cin, kh, kw)  -- k order == the (Cout, Cin*KH*KW) weight layout
 template <typename T>
 __global__ void im2col_kernel(riqn_conv_geom g, const T* __restrict__ in, float* __restrict__ col) {
-  pdl_sync();
   const int K = g.Cin * g.KH * g.KW;
   const long total = (long)g.B * g.OH * g.OW * K;
   for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -41,7 +40,6 @@ __global__ void im2col_kernel(riqn_conv_geom g, const T* __restrict__ in, float*
 // dY[m, c] = dout[b, c, p] * (out[b, c, p] > 0)      (ReLU backward + NCHW -> (M, Cout))
 __global__ void conv_dy_kernel(int B, int Cout, int ohw, const float* __restrict__ dout,
                                const float* __restrict__ out, float* __restrict__ dY) {
-  pdl_sync();
   const long total = (long)B * Cout * ohw;
   for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
     const int p = (int)(idx % ohw);
@@ -54,7 +52,6 @@ __global__ void conv_dy_kernel(int B, int Cout, int ohw, const float* __restrict
 
 // din[b, c, ih, iw] = sum_{kh,kw} dcol[(b,oh,ow), (c,kh,kw)]
 __global__ void col2im_kernel(riqn_conv_geom g, const float* __restrict__ dcol, float* __restrict__ din) {
-  pdl_sync();
   const int K = g.Cin * g.KH * g.KW;
   const long total = (long)g.B * g.Cin * g.H * g.W;
   for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -82,7 +79,6 @@ __global__ void col2im_kernel(riqn_conv_geom g, const float* __restrict__ dcol, 
 // Same scatter with coalesced reads: one block per (sample, chunk of CC input channels) streams that sample's dcol rows
 // (the CC*KH*KW gradients of a row are contiguous) and accumulates into a shared-memory image tile, written out once.
 __global__ void col2im_tile_kernel(riqn_conv_geom g, int CC, const float* __restrict__ dcol, float* __restrict__ din) {
-  pdl_sync();
   extern __shared__ float acc[];     // CC * H * W
   const int K = g.Cin * g.KH * g.KW, khw = g.KH * g.KW, ohw = g.OH * g.OW, hw = g.H * g.W;
   const int chunks = g.Cin / CC;
@@ -110,18 +106,17 @@ static int col2im(const riqn_conv_geom* g, const float* dcol, float* din, cudaSt
   int CC = g->Cin;
   while (CC > 1 && ((long)CC * hw * 4 > 16 * 1024 || g->Cin % CC)) --CC;
   if ((long)CC * hw * 4 <= 48 * 1024) {
-    riqn::launch_pdl(col2im_tile_kernel, g->B * (g->Cin / CC), 256, (size_t)CC * hw * 4, s, *g, CC, dcol, din);
+    col2im_tile_kernel<<<g->B * (g->Cin / CC), 256, (size_t)CC * hw * 4, s>>>(*g, CC, dcol, din);
   } else {
     long total = (long)g->B * g->Cin * hw;
     long blocks = (total + 255) / 256;
-    riqn::launch_pdl(col2im_kernel, (int)(blocks > 148L * 32 ? 148L * 32 : blocks), 256, 0, s, *g, dcol, din);
+    col2im_kernel<<<(int)(blocks > 148L * 32 ? 148L * 32 : blocks), 256, 0, s>>>(*g, dcol, din);
   }
   return (int)cudaGetLastError();
 }
 
 // out[n] += sum_m X[m, n]
 __global__ void colsum_atomic_kernel(long M, int N, const float* __restrict__ X, float* __restrict__ out, int rows_per_block) {
-  pdl_sync();
   const int n = blockIdx.x * 128 + (threadIdx.x & 127);
   const int half = threadIdx.x >> 7;
   if (n >= N) return;
@@ -135,7 +130,7 @@ __global__ void colsum_atomic_kernel(long M, int N, const float* __restrict__ X,
 int colsum_atomic(long M, int N, const float* X, float* out, cudaStream_t s) {
   int rows_per_block = 256;
   dim3 grid((N + 127) / 128, (unsigned)((M + rows_per_block - 1) / rows_per_block));
-  riqn::launch_pdl(colsum_atomic_kernel, grid, 256, 0, s, M, N, X, out, rows_per_block);
+  colsum_atomic_kernel<<<grid, 256, 0, s>>>(M, N, X, out, rows_per_block);
   return (int)cudaGetLastError();
 }
 
@@ -171,7 +166,6 @@ __device__ __forceinline__ void pack8(const float (&x)[8], uint4& hi, uint4& lo)
 // k is decoded once and then stepped without divisions.
 template <typename T>
 __global__ void im2col_bf16_kernel(riqn_conv_geom g, const T* __restrict__ in, bf16* __restrict__ hi, bf16* __restrict__ lo) {
-  pdl_sync();
   const int K = g.Cin * g.KH * g.KW, K8 = K / 8;
   const long total = (long)g.B * g.OH * g.OW * K8;
   for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -199,7 +193,6 @@ __global__ void im2col_bf16_kernel(riqn_conv_geom g, const T* __restrict__ in, b
 // uint8 specialisation: the 256 possible pixels are converted once per block into a packed (hi | lo << 16) table, so
 // the per-element work is one byte load + one shared-memory lookup (bit-identical to x / 255.0f then hi/lo split).
 __global__ void im2col_bf16_u8_kernel(riqn_conv_geom g, const uint8_t* __restrict__ in, bf16* __restrict__ hi, bf16* __restrict__ lo) {
-  pdl_sync();
   __shared__ uint32_t lut[256];
   {
     const float x = (float)threadIdx.x / 255.0f;
@@ -240,7 +233,6 @@ __global__ void im2col_bf16_u8_kernel(riqn_conv_geom g, const uint8_t* __restric
 // (exact); the 1/255 of the reference (redis_memory.py:527-536) is folded into the weights / the gradient scale.
 __global__ void im2col_u8_staged_kernel(riqn_conv_geom g, const uint8_t* __restrict__ in, bf16* __restrict__ col,
                                         bf16* __restrict__ colT) {
-  pdl_sync();
   extern __shared__ __align__(16) uint8_t img[];
   const int chw = g.Cin * g.H * g.W, K = g.Cin * g.KH * g.KW, K8 = K / 8, ohw = g.OH * g.OW;
   const long b = blockIdx.x;
@@ -321,7 +313,6 @@ __global__ void im2col_u8_staged_kernel(riqn_conv_geom g, const uint8_t* __restr
 // (M, K) hi / lo rows from shared memory with 32-bit index arithmetic.  Bit-identical to im2col_bf16_kernel.
 __global__ void __launch_bounds__(256) im2col_f32_staged_kernel(riqn_conv_geom g, const float* __restrict__ in,
                                                                 bf16* __restrict__ hi, bf16* __restrict__ lo) {
-  pdl_sync();
   extern __shared__ __align__(16) uint32_t simg[];
   const int chw = g.Cin * g.H * g.W, K = g.Cin * g.KH * g.KW, K8 = K / 8, ohw = g.OH * g.OW;
   const long b = blockIdx.x;
@@ -364,7 +355,6 @@ __global__ void __launch_bounds__(256) im2col_f32_staged_kernel(riqn_conv_geom g
 // colT (K, M): one thread = 8 consecutive m of one k  (M % 8 == 0)
 template <typename T>
 __global__ void im2col_bf16_t_kernel(riqn_conv_geom g, const T* __restrict__ in, bf16* __restrict__ hiT) {
-  pdl_sync();
   const int K = g.Cin * g.KH * g.KW;
   const long M = (long)g.B * g.OH * g.OW, M8 = M / 8;
   const long total = M8 * K;
@@ -392,7 +382,6 @@ __global__ void im2col_bf16_t_kernel(riqn_conv_geom g, const T* __restrict__ in,
 // gradient (sum over b, p) is reduced per channel on the way.
 __global__ void conv_dy_bf16_kernel(int B, int Cout, int ohw, const float* __restrict__ dout, const float* __restrict__ out,
                                     bf16* __restrict__ dY, bf16* __restrict__ dYT, float* __restrict__ dbias) {
-  pdl_sync();
   const int c = blockIdx.y;
   const long M = (long)B * ohw;
   float acc = 0.f;
@@ -422,7 +411,6 @@ __global__ void conv_dy_bf16_kernel(int B, int Cout, int ohw, const float* __res
 __global__ void __launch_bounds__(256) conv_dy_tile_kernel(int B, int Cout, int ohw, const float* __restrict__ dout,
                                                            const float* __restrict__ out, bf16* __restrict__ dY,
                                                            bf16* __restrict__ dYT, float* __restrict__ dbias) {
-  pdl_sync();
   __shared__ __align__(16) unsigned short tile[64][66];
   __shared__ float bsum[64];
   const long M = (long)B * ohw;
@@ -484,7 +472,6 @@ __global__ void __launch_bounds__(256) conv_dy_tile_kernel(int B, int Cout, int 
 // First layer: uint8 frames -> block matrix of raw pixel values (exact in bf16), within-block order (c, iy, ix).
 __global__ void __launch_bounds__(256) s2d_u8_kernel(riqn_conv_geom g, int G, const uint8_t* __restrict__ in,
                                                      bf16* __restrict__ a_px) {
-  pdl_sync();
   extern __shared__ __align__(16) uint8_t img[];
   const int chw = g.Cin * g.H * g.W, s = g.stride, ss = s * s, Kc = ss * g.Cin, K8 = Kc / 8;
   const long b = blockIdx.x;
@@ -554,8 +541,8 @@ RIQN_API int riqn_conv_fwd(const riqn_conv_geom* g, const void* in, int in_is_u8
   cudaStream_t s = (cudaStream_t)stream;
   const long M = (long)g->B * g->OH * g->OW;
   const int K = g->Cin * g->KH * g->KW;
-  if (in_is_u8) riqn::launch_pdl(im2col_kernel<uint8_t>, grid_for(M * K), 256, 0, s, *g, (const uint8_t*)in, col);
-  else riqn::launch_pdl(im2col_kernel<float>, grid_for(M * K), 256, 0, s, *g, (const float*)in, col);
+  if (in_is_u8) im2col_kernel<uint8_t><<<grid_for(M * K), 256, 0, s>>>(*g, (const uint8_t*)in, col);
+  else im2col_kernel<float><<<grid_for(M * K), 256, 0, s>>>(*g, (const float*)in, col);
   RIQN_LAUNCH_CHECK();
   EpiArgs e;
   e.bias = bias;
@@ -568,8 +555,8 @@ RIQN_API int riqn_im2col_f32(const riqn_conv_geom* g, const void* in, int in_is_
   cudaStream_t s = (cudaStream_t)stream;
   const long M = (long)g->B * g->OH * g->OW;
   const int K = g->Cin * g->KH * g->KW;
-  if (in_is_u8) riqn::launch_pdl(im2col_kernel<uint8_t>, grid_for(M * K), 256, 0, s, *g, (const uint8_t*)in, col);
-  else riqn::launch_pdl(im2col_kernel<float>, grid_for(M * K), 256, 0, s, *g, (const float*)in, col);
+  if (in_is_u8) im2col_kernel<uint8_t><<<grid_for(M * K), 256, 0, s>>>(*g, (const uint8_t*)in, col);
+  else im2col_kernel<float><<<grid_for(M * K), 256, 0, s>>>(*g, (const float*)in, col);
   return (int)cudaGetLastError();
 }
 
@@ -580,7 +567,7 @@ RIQN_API int riqn_conv_bwd(const riqn_conv_geom* g, const float* dout, const flo
   const long M = (long)g->B * g->OH * g->OW;
   const int K = g->Cin * g->KH * g->KW;
   const int ohw = g->OH * g->OW;
-  riqn::launch_pdl(conv_dy_kernel, grid_for(M * g->Cout), 256, 0, s, g->B, g->Cout, ohw, dout, out, dY);
+  conv_dy_kernel<<<grid_for(M * g->Cout), 256, 0, s>>>(g->B, g->Cout, ohw, dout, out, dY);
   RIQN_LAUNCH_CHECK();
   int rc = colsum_atomic(M, g->Cout, dY, dbias, s);
   if (rc) return rc;
@@ -612,7 +599,7 @@ RIQN_API int riqn_conv_fwd_tc(const riqn_conv_geom* g, const void* in, int in_is
   const long M = (long)g->B * g->OH * g->OW;
   const int K = g->Cin * g->KH * g->KW;
   if (K % 8 || (colT_hi && M % 8)) return (int)cudaErrorInvalidValue;
-  if (in_is_u8) riqn::launch_pdl(im2col_bf16_u8_kernel, grid_for(M * K / 8), 256, 0, s, *g, (const uint8_t*)in, (bf16*)col_hi, (bf16*)col_lo);
+  if (in_is_u8) im2col_bf16_u8_kernel<<<grid_for(M * K / 8), 256, 0, s>>>(*g, (const uint8_t*)in, (bf16*)col_hi, (bf16*)col_lo);
   else {
     const int chw = g->Cin * g->H * g->W;
     if (chw % 4 == 0 && g->in_bstride % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && chw * 4 <= 96 * 1024) {
@@ -622,15 +609,15 @@ RIQN_API int riqn_conv_fwd_tc(const riqn_conv_geom* g, const void* in, int in_is
         RIQN_CUDA(cudaFuncSetAttribute(im2col_f32_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         attr_once.done[attr_dev] = true;
       }
-      riqn::launch_pdl(im2col_f32_staged_kernel, g->B, 256, (size_t)chw * 4, s, *g, (const float*)in, (bf16*)col_hi, (bf16*)col_lo);
+      im2col_f32_staged_kernel<<<g->B, 256, (size_t)chw * 4, s>>>(*g, (const float*)in, (bf16*)col_hi, (bf16*)col_lo);
     } else {
-      riqn::launch_pdl(im2col_bf16_kernel<float>, grid_for(M * K / 8), 256, 0, s, *g, (const float*)in, (bf16*)col_hi, (bf16*)col_lo);
+      im2col_bf16_kernel<float><<<grid_for(M * K / 8), 256, 0, s>>>(*g, (const float*)in, (bf16*)col_hi, (bf16*)col_lo);
     }
   }
   RIQN_LAUNCH_CHECK();
   if (colT_hi) {
-    if (in_is_u8) riqn::launch_pdl(im2col_bf16_t_kernel<uint8_t>, grid_for(M * K / 8), 256, 0, s, *g, (const uint8_t*)in, (bf16*)colT_hi);
-    else riqn::launch_pdl(im2col_bf16_t_kernel<float>, grid_for(M * K / 8), 256, 0, s, *g, (const float*)in, (bf16*)colT_hi);
+    if (in_is_u8) im2col_bf16_t_kernel<uint8_t><<<grid_for(M * K / 8), 256, 0, s>>>(*g, (const uint8_t*)in, (bf16*)colT_hi);
+    else im2col_bf16_t_kernel<float><<<grid_for(M * K / 8), 256, 0, s>>>(*g, (const float*)in, (bf16*)colT_hi);
     RIQN_LAUNCH_CHECK();
   }
   TcExtra ex;
@@ -655,7 +642,7 @@ RIQN_API int riqn_conv_fwd_tc_u8(const riqn_conv_geom* g, const unsigned char* i
     attr_once.done[attr_dev] = true;
   }
   if (!reuse_col) {      // reuse_col: col_px already holds this input's im2col (another network's pass over it)
-    riqn::launch_pdl(im2col_u8_staged_kernel, dim3(g->B, 4), 256, chw, s, *g, in, (bf16*)col_px, (bf16*)colT_px);
+    im2col_u8_staged_kernel<<<dim3(g->B, 4), 256, chw, s>>>(*g, in, (bf16*)col_px, (bf16*)colT_px);
     RIQN_LAUNCH_CHECK();
   }
   TcExtra ex;
@@ -669,7 +656,6 @@ RIQN_API int riqn_conv_fwd_tc_u8(const riqn_conv_geom* g, const unsigned char* i
 __global__ void __launch_bounds__(256) conv_dy_grid_kernel(int B, int Cout, int OH, int OW, int G,
                                                            const float* __restrict__ dout, const float* __restrict__ out,
                                                            bf16* __restrict__ dYg, float* __restrict__ dbias) {
-  pdl_sync();
   __shared__ __align__(16) unsigned short tile[64][66];
   __shared__ float bsum[64];
   const long Mg = (long)B * G * G;
@@ -734,7 +720,6 @@ __global__ void __launch_bounds__(256) conv_dy_grid_kernel(int B, int Cout, int 
 // dw[c, perm[k']] += dwp[c, k']: the strip weight gradient back into the (Cout, Cin*KH*KW) parameter order
 __global__ void unpermute_add_kernel(int Cout, int K, const float* __restrict__ dwp, const int* __restrict__ perm,
                                      float* __restrict__ dw) {
-  pdl_sync();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= Cout * K) return;
   const int c = idx / K, kp = idx - c * K;
@@ -764,7 +749,7 @@ RIQN_API int riqn_s2d_u8(const riqn_conv_geom* g, const unsigned char* in, void*
     RIQN_CUDA(cudaFuncSetAttribute(s2d_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     attr_once.done[attr_dev] = true;
   }
-  riqn::launch_pdl(s2d_u8_kernel, g->B, 256, chw, (cudaStream_t)stream, *g, G, in, (bf16*)a_px);
+  s2d_u8_kernel<<<g->B, 256, chw, (cudaStream_t)stream>>>(*g, G, in, (bf16*)a_px);
   return (int)cudaGetLastError();
 }
 
@@ -798,7 +783,7 @@ RIQN_API int riqn_conv_bwd_strip(const riqn_conv_geom* g, const float* dout, con
   const long Mg = (long)g->B * G * G;
   const int K = g->Cin * g->KH * g->KW;
   const long tiles = (Mg + 63) / 64;
-  riqn::launch_pdl(conv_dy_grid_kernel, (unsigned)(tiles < 148 * 4 ? tiles : 148 * 4), 256, 0, s, g->B, g->Cout, g->OH, g->OW, G, dout, out,
+  conv_dy_grid_kernel<<<(unsigned)(tiles < 148 * 4 ? tiles : 148 * 4), 256, 0, s>>>(g->B, g->Cout, g->OH, g->OW, G, dout, out,
                                                                                 (bf16*)dYg, dbias);
   RIQN_LAUNCH_CHECK();
   RIQN_CUDA(cudaMemsetAsync(dwp_scratch, 0, sizeof(float) * g->Cout * K, s));
@@ -811,7 +796,7 @@ RIQN_API int riqn_conv_bwd_strip(const riqn_conv_geom* g, const float* dout, con
   int rc = gemm_bf16_tc(g->Cout, K, (int)Mg, (const bf16*)dYg, nullptr, (const bf16*)a_hi, nullptr, dwp_scratch, K, TC_ATOMIC,
                         nullptr, nullptr, nullptr, split, s, &ex);
   if (rc) return rc;
-  riqn::launch_pdl(unpermute_add_kernel, (g->Cout * K + 255) / 256, 256, 0, s, g->Cout, K, dwp_scratch, perm, dw);
+  unpermute_add_kernel<<<(g->Cout * K + 255) / 256, 256, 0, s>>>(g->Cout, K, dwp_scratch, perm, dw);
   RIQN_LAUNCH_CHECK();
   if (din) {
     RIQN_CUDA(cudaMemsetAsync(din, 0, sizeof(float) * (size_t)g->B * g->Cin * g->H * g->W, s));
@@ -844,9 +829,9 @@ RIQN_API int riqn_im2col_bf16_t(const riqn_conv_geom* g, const void* in, int in_
       RIQN_CUDA(cudaFuncSetAttribute(im2col_u8_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
       attr_once.done[attr_dev] = true;
     }
-    riqn::launch_pdl(im2col_u8_staged_kernel, dim3(g->B, 4), 256, chw, s, *g, (const unsigned char*)in, nullptr, (bf16*)colT_hi);
+    im2col_u8_staged_kernel<<<dim3(g->B, 4), 256, chw, s>>>(*g, (const unsigned char*)in, nullptr, (bf16*)colT_hi);
   } else {
-    riqn::launch_pdl(im2col_bf16_t_kernel<float>, grid_for(M * K / 8), 256, 0, s, *g, (const float*)in, (bf16*)colT_hi);
+    im2col_bf16_t_kernel<float><<<grid_for(M * K / 8), 256, 0, s>>>(*g, (const float*)in, (bf16*)colT_hi);
   }
   return (int)cudaGetLastError();
 }
@@ -862,11 +847,11 @@ RIQN_API int riqn_conv_bwd_tc(const riqn_conv_geom* g, const float* dout, const 
   if (M % 8 || g->Cout % 8) return (int)cudaErrorInvalidValue;
   if (g->Cout <= 64) {
     const long tiles = (M + 63) / 64;
-    riqn::launch_pdl(conv_dy_tile_kernel, (unsigned)(tiles < 148 * 4 ? tiles : 148 * 4), 256, 0, s, g->B, g->Cout, ohw, dout, out,
+    conv_dy_tile_kernel<<<(unsigned)(tiles < 148 * 4 ? tiles : 148 * 4), 256, 0, s>>>(g->B, g->Cout, ohw, dout, out,
                                                                  din ? (bf16*)dY_hi : nullptr, (bf16*)dYT_hi, dbias);
   } else {
     dim3 grid((unsigned)((M + 256 * 8 - 1) / (256 * 8)), g->Cout);
-    riqn::launch_pdl(conv_dy_bf16_kernel, grid, 256, 0, s, g->B, g->Cout, ohw, dout, out, din ? (bf16*)dY_hi : nullptr, (bf16*)dYT_hi, dbias);
+    conv_dy_bf16_kernel<<<grid, 256, 0, s>>>(g->B, g->Cout, ohw, dout, out, din ? (bf16*)dY_hi : nullptr, (bf16*)dYT_hi, dbias);
   }
   RIQN_LAUNCH_CHECK();
   // dW[c, k] += sum_m dY[m, c] * col[m, k]      (K' = M is long: split it over every SM)

@@ -38,7 +38,6 @@ __global__ void __launch_bounds__(NT, 2)
 gemm_simt_kernel(int M, int N, int K, const float* __restrict__ A, long sAm, long sAk,
                  const float* __restrict__ B, long sBn, long sBk, float* __restrict__ C, long ldc,
                  EpiArgs e, int kchunk) {
-  pdl_sync();
   __shared__ __align__(16) float As[2][BK][BM + 4];
   __shared__ __align__(16) float Bs[2][BK][BN + 4];
   const int tid = threadIdx.x;
@@ -154,7 +153,7 @@ static int launch_epi(int M, int N, int K, const float* A, long sAm, long sAk, c
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, split_k);
   const bool akc = (sAk == 1), bkc = (sBk == 1);
 #define RIQN_GEMM_GO(AK_, BK_) \
-  riqn::launch_pdl(gemm_simt_kernel<EPI, AK_, BK_>, grid, NT, 0, s, M, N, K, A, sAm, sAk, B, sBn, sBk, C, ldc, e, kchunk)
+  gemm_simt_kernel<EPI, AK_, BK_><<<grid, NT, 0, s>>>(M, N, K, A, sAm, sAk, B, sBn, sBk, C, ldc, e, kchunk)
   if (akc && bkc) RIQN_GEMM_GO(true, true);
   else if (akc) RIQN_GEMM_GO(true, false);
   else if (bkc) RIQN_GEMM_GO(false, true);

@@ -292,7 +292,6 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
                const __grid_constant__ CUtensorMap mapB_hi, const __grid_constant__ CUtensorMap mapB_lo,
                const __grid_constant__ TcArgs p) {
-  pdl_trigger();   // the next kernel may start launching; this one waits (below) after its own prologue
   using Cfg = TcCfg<NSPLIT, BN, EPI>;
   constexpr int TBN = BN;
   constexpr uint32_t TMEM_COLS = Cfg::kTmemCols;
@@ -324,7 +323,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();          // barriers initialised, TMEM allocated: from here on the kernel reads its predecessor's output
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -782,7 +780,7 @@ static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUt
   }
   const int units = p.m_tiles * p.n_tiles * p.k_splits;
   const int grid = units < sms ? units : sms;
-  riqn::launch_pdl(gemm_tc_kernel<NSPLIT, EPI, BN>, grid, tc_threads(EPI), Cfg::kSmemBytes, s, a_hi, a_lo, b_hi, b_lo, p);
+  gemm_tc_kernel<NSPLIT, EPI, BN><<<grid, tc_threads(EPI), Cfg::kSmemBytes, s>>>(a_hi, a_lo, b_hi, b_lo, p);
   return (int)cudaGetLastError();
 }
 
@@ -921,7 +919,6 @@ int gemm_bf16_tc(int M, int N, int K, const bf16* A_hi, const bf16* A_lo, const 
 // fp32 (rows, cols) -> bf16 hi (+ lo = bf16(x - hi)), optionally also transposed copies (cols, rows).
 __global__ void split_bf16_kernel(long rows, int cols, const float* __restrict__ src, bf16* __restrict__ hi,
                                   bf16* __restrict__ lo, bf16* __restrict__ hiT, bf16* __restrict__ loT, int fp16) {
-  pdl_sync();
   __shared__ float tile[32][33];
   const long r0 = (long)blockIdx.y * 32;
   const int c0 = blockIdx.x * 32;
@@ -960,7 +957,7 @@ __global__ void split_bf16_kernel(long rows, int cols, const float* __restrict__
 int split_bf16(long rows, int cols, const float* src, bf16* hi, bf16* lo, bf16* hiT, bf16* loT, cudaStream_t s, int fp16) {
   if (fp16 && (hi == nullptr || hiT != nullptr || loT != nullptr)) return (int)cudaErrorInvalidValue;
   dim3 grid((cols + 31) / 32, (unsigned)((rows + 31) / 32));
-  riqn::launch_pdl(split_bf16_kernel, grid, 256, 0, s, rows, cols, src, hi, lo, hiT, loT, fp16);
+  split_bf16_kernel<<<grid, 256, 0, s>>>(rows, cols, src, hi, lo, hiT, loT, fp16);
   return (int)cudaGetLastError();
 }
 
@@ -970,7 +967,6 @@ using namespace riqn;
 
 __global__ void split_bf16_scaled_kernel(long n, const float* __restrict__ src, float scale, riqn::bf16* __restrict__ hi,
                                          riqn::bf16* __restrict__ lo) {
-  pdl_sync();
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float x = __fdiv_rn(src[i], scale);      // weight / 255, like the reference divides the pixel
@@ -982,7 +978,7 @@ __global__ void split_bf16_scaled_kernel(long n, const float* __restrict__ src, 
 RIQN_API int riqn_split_bf16_scaled(long rows, int cols, const float* src, float scale, void* hi, void* lo, void* stream) {
   riqn::note_launches(1);
   const long n = rows * cols;
-  riqn::launch_pdl(split_bf16_scaled_kernel, riqn_cdiv(n, 256), 256, 0, (cudaStream_t)stream, n, src, scale, (riqn::bf16*)hi, (riqn::bf16*)lo);
+  split_bf16_scaled_kernel<<<riqn_cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(n, src, scale, (riqn::bf16*)hi, (riqn::bf16*)lo);
   return (int)cudaGetLastError();
 }
 
@@ -993,7 +989,6 @@ struct SplitJobs {
 };
 
 __global__ void split_bf16_multi_kernel(SplitJobs t) {
-  pdl_sync();
   int ji = 0;
   while (ji < t.n - 1 && (int)blockIdx.x >= t.blk_end[ji]) ++ji;
   const riqn_split_job& J = t.j[ji];
@@ -1020,7 +1015,7 @@ RIQN_API int riqn_split_bf16_multi(int n_jobs, const riqn_split_job* jobs, void*
     blocks += (int)riqn_cdiv((long)jobs[i].rows * jobs[i].cols, 256);
     t.blk_end[i] = blocks;
   }
-  riqn::launch_pdl(split_bf16_multi_kernel, blocks, 256, 0, (cudaStream_t)stream, t);
+  split_bf16_multi_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(t);
   return (int)cudaGetLastError();
 }
 

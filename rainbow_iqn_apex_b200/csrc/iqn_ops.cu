@@ -17,7 +17,6 @@ int colsum_atomic(long M, int N, const float* X, float* out, cudaStream_t s);
 // ------------------------------------------------------------------------------------------------
 __global__ void fill_uniform_kernel(long n, uint64_t seed, uint64_t stream, float* __restrict__ out,
                                     const riqn_dyn_state* __restrict__ dyn) {
-  pdl_sync();
   if (dyn) stream += dyn->rng_offset;
   const long i4 = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i4 * 4 >= n) return;
@@ -30,7 +29,6 @@ __global__ void fill_uniform_kernel(long n, uint64_t seed, uint64_t stream, floa
 // f(x) = sign(x) sqrt|x| of x ~ N(0,1)            (NoisyLinear._scale_noise, model.py:32-37)
 __global__ void fill_scaled_normal_kernel(long n, uint64_t seed, uint64_t stream, float* __restrict__ out,
                                           const riqn_dyn_state* __restrict__ dyn) {
-  pdl_sync();
   if (dyn) stream += dyn->rng_offset;
   const long i4 = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i4 * 4 >= n) return;
@@ -49,7 +47,6 @@ __global__ void fill_scaled_normal_kernel(long n, uint64_t seed, uint64_t stream
 // Quantile embedding input: cos(fl(fl(i) * fl(pi)) * tau), i = 1..E          (model.py:136-144)
 // ------------------------------------------------------------------------------------------------
 __global__ void cos_embed_kernel(int B, int Nq, int E, const float* __restrict__ tau, float* __restrict__ cosv) {
-  pdl_sync();
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long)B * Nq * E) return;
   const int i = (int)(idx % E) + 1;
@@ -63,7 +60,6 @@ __global__ void cos_embed_kernel(int B, int Nq, int E, const float* __restrict__
 // (E, R) the iqn_fc weight-gradient product consumes.
 __global__ void cos_embed_bf16_kernel(int B, int Nq, int E, const float* __restrict__ tau, __nv_bfloat16* __restrict__ hi,
                                       __nv_bfloat16* __restrict__ lo, __nv_bfloat16* __restrict__ hiT) {
-  pdl_sync();
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long R = (long)B * Nq;
   if (idx >= R * E) return;
@@ -87,7 +83,6 @@ __global__ void embed_bwd_tile_kernel(int B, int Nq, int F, const __nv_bfloat16*
                                       const float* __restrict__ dX, const __nv_bfloat16* __restrict__ dXb,
                                       __nv_bfloat16* __restrict__ dpre, float* __restrict__ dfeat,
                                       float* __restrict__ dbe) {
-  pdl_sync();
   __shared__ float red[2][8][32];
   const int f0 = blockIdx.x * 32, b = blockIdx.y;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
@@ -128,7 +123,6 @@ __global__ void __launch_bounds__(256) embed_bwd_wide_kernel(int B, int Nq, int 
                                                              const __nv_bfloat16* __restrict__ dXb,
                                                              __nv_bfloat16* __restrict__ dpre, float* __restrict__ dfeat,
                                                              float* __restrict__ dbe) {
-  pdl_sync();
   __shared__ float red[2][8][128];
   const int f0 = blockIdx.x * 128, b = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -210,7 +204,6 @@ __global__ void __launch_bounds__(256) embed_bwd_wide8_kernel(int B, int Nq, int
                                                               const __nv_bfloat16* __restrict__ dXb,
                                                               __nv_bfloat16* __restrict__ dpre, float* __restrict__ dfeat,
                                                               float* __restrict__ dbe) {
-  pdl_sync();
   __shared__ float red[2][8][256];
   const int f0 = blockIdx.x * 256, b = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -292,7 +285,6 @@ __global__ void noisy_compose_kernel(int out_f, int in_f, const float* __restric
                                      const float* __restrict__ eps_out, const float* __restrict__ bmu,
                                      const float* __restrict__ bsigma, float* __restrict__ beps,
                                      float* __restrict__ w_eff, float* __restrict__ b_eff, int training) {
-  pdl_sync();
   const long total = (long)out_f * in_f;
   for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
     const int o = (int)(idx / in_f), i = (int)(idx % in_f);
@@ -325,7 +317,6 @@ struct NoisyNet {
 };
 
 __global__ void noisy_fill_net_kernel(NoisyNet net, uint64_t seed, const riqn_dyn_state* __restrict__ dyn) {
-  pdl_sync();
   int seg = 0;
   while (seg < 2 * net.n - 1 && (int)blockIdx.x >= net.blk_end[seg]) ++seg;
   const riqn_noisy_layer& L = net.l[seg >> 1];
@@ -349,7 +340,6 @@ __global__ void noisy_fill_net_kernel(NoisyNet net, uint64_t seed, const riqn_dy
 
 // one thread = 4 consecutive inputs of one output row (16-byte accesses); block ranges per layer from blk_end
 __global__ void noisy_compose_net_kernel(NoisyNet net, int training) {
-  pdl_sync();
   int li = 0;
   while (li < net.n - 1 && (int)blockIdx.x >= net.blk_end[li]) ++li;
   const riqn_noisy_layer& L = net.l[li];
@@ -406,7 +396,6 @@ __global__ void noisy_compose_net_kernel(NoisyNet net, int training) {
 template <int HID>
 __global__ void z_dueling_fwd_kernel(long R, int B, int A, const float* __restrict__ H, const float* __restrict__ Wz,
                                      const float* __restrict__ bz, float* __restrict__ q) {
-  pdl_sync();
   extern __shared__ float sW[];  // (1+A) * HID
   for (int i = threadIdx.x; i < (1 + A) * HID; i += blockDim.x) sW[i] = Wz[i];
   __syncthreads();
@@ -448,7 +437,6 @@ template <int HID>
 __global__ void __launch_bounds__(256, 2) z_dueling_fwd4_kernel(long R, int B, int A, const float* __restrict__ H,
                                                                 const float* __restrict__ Wz, const float* __restrict__ bz,
                                                                 float* __restrict__ q) {
-  pdl_sync();
   extern __shared__ float sW[];  // (1+A) * HID
   for (int i = threadIdx.x; i < (1 + A) * HID / 4; i += blockDim.x)
     reinterpret_cast<float4*>(sW)[i] = reinterpret_cast<const float4*>(Wz)[i];
@@ -527,7 +515,6 @@ __global__ void __launch_bounds__(256, 2) z_dueling_fwd4_kernel(long R, int B, i
 // Double-DQN action: a*[b] = argmax_a mean_k q[k*B+b, a]               (compute_loss_iqn.py:238-245)
 // ------------------------------------------------------------------------------------------------
 __global__ void argmax_mean_kernel(int B, int K, int A, const float* __restrict__ q, int64_t* __restrict__ a_star) {
-  pdl_sync();
   // one warp per transition, lane a (< A <= 32) sums its action's K quantile values in order k = 0..K-1
   const int b = (int)(((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31;
@@ -564,7 +551,6 @@ __global__ void iqn_loss_kernel(int B, int N, int Np, int A, const float* __rest
                                 const float* __restrict__ returns, const float* __restrict__ nonterminals,
                                 float gamma_n, float kappa, float* __restrict__ loss, float* __restrict__ dtheta,
                                 float* __restrict__ theta_out, float* __restrict__ target_out) {
-  pdl_sync();
   extern __shared__ float sT[];  // Np targets + 32 reduction slots
   float* red = sT + Np;
   const int b = blockIdx.x, tid = threadIdx.x;
@@ -615,7 +601,6 @@ __global__ void z_dueling_bwd_kernel(long R, int B, int A, const float* __restri
                                      const float* __restrict__ dtheta, const float* __restrict__ gscale,
                                      const int64_t* __restrict__ actions, float* __restrict__ dH,
                                      float* __restrict__ dz, __nv_bfloat16* __restrict__ dz_bf) {
-  pdl_sync();
   extern __shared__ float sW[];  // (1+A)*HID weights + HID colmean
   float* wbar = sW + (1 + A) * HID;
   for (int i = threadIdx.x; i < (1 + A) * HID; i += blockDim.x) sW[i] = Wz[i];
@@ -662,7 +647,6 @@ __global__ void __launch_bounds__(256) z_dueling_bwd_bf16_kernel(long R, int B, 
                                                                  __nv_bfloat16* __restrict__ dh_hiT,
                                                                  float* __restrict__ colsum, float* __restrict__ dz,
                                                                  __nv_bfloat16* __restrict__ dz_bf) {
-  pdl_sync();
   extern __shared__ __align__(16) float sW[];          // (1+A)*HID weights | HID colmean | 2*HID column sums | tile
   float* wbar = sW + (1 + A) * HID;
   float* cs = wbar + HID;
@@ -789,7 +773,6 @@ __global__ void z_wgrad_finish_kernel(int A, int HID, const float* __restrict__ 
                                       const float* __restrict__ eps_w_za, const float* __restrict__ eps_b_za,
                                       float* g_mu_zv, float* g_sig_zv, float* g_bmu_zv, float* g_bsig_zv,
                                       float* g_mu_za, float* g_sig_za, float* g_bmu_za, float* g_bsig_za) {
-  pdl_sync();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < HID) {
     const float g = dWz[idx];
@@ -815,7 +798,6 @@ __global__ void z_wgrad_finish_kernel(int A, int HID, const float* __restrict__ 
 // dmu_b += db ; dsigma_b += db * eps_b
 __global__ void noisy_bias_grad_kernel(int n, const float* __restrict__ db, const float* __restrict__ eps_b,
                                        float* g_bmu, float* g_bsig) {
-  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   g_bmu[i] += db[i];
@@ -830,7 +812,6 @@ __global__ void noisy_bias_grad_kernel(int n, const float* __restrict__ db, cons
 // ------------------------------------------------------------------------------------------------
 __global__ void embed_bwd_elem_kernel(int B, int Nq, int F, const float* __restrict__ X, const float* __restrict__ feat,
                                       float* __restrict__ dX, float* __restrict__ dfeat) {
-  pdl_sync();
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long)B * F) return;
   const float ft = feat[idx];
@@ -851,7 +832,6 @@ __global__ void embed_bwd_elem_kernel(int B, int Nq, int F, const float* __restr
 __global__ void adam_kernel(long n, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, float neg_step_size, float sqrt_bc2, float eps, float b1, float b2,
                             float grad_scale, const riqn_dyn_state* __restrict__ dyn) {
-  pdl_sync();
   if (dyn) { neg_step_size = dyn->adam_neg_step_size; sqrt_bc2 = dyn->adam_sqrt_bc2; }
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     const float gi = g[i] * grad_scale;
@@ -877,7 +857,7 @@ RIQN_API int riqn_fill_uniform(long n, unsigned long long seed, unsigned long lo
                                const riqn_dyn_state* dyn, void* stream) {
   riqn::note_launches(1);
   if (n <= 0) return 0;
-  riqn::launch_pdl(fill_uniform_kernel, riqn_cdiv((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream, n, seed, stream_id, out, dyn);
+  fill_uniform_kernel<<<riqn_cdiv((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(n, seed, stream_id, out, dyn);
   return (int)cudaGetLastError();
 }
 
@@ -885,7 +865,7 @@ RIQN_API int riqn_noisy_sample(long n, unsigned long long seed, unsigned long lo
                                const riqn_dyn_state* dyn, void* stream) {
   riqn::note_launches(1);
   if (n <= 0) return 0;
-  riqn::launch_pdl(fill_scaled_normal_kernel, riqn_cdiv((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream, n, seed, stream_id, out, dyn);
+  fill_scaled_normal_kernel<<<riqn_cdiv((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(n, seed, stream_id, out, dyn);
   return (int)cudaGetLastError();
 }
 
@@ -894,7 +874,7 @@ RIQN_API int riqn_noisy_compose(int out_features, int in_features, const float* 
                                 const float* bias_sigma, float* bias_epsilon, float* w_eff, float* b_eff, int training,
                                 void* stream) {
   riqn::note_launches(1);
-  riqn::launch_pdl(noisy_compose_kernel, grid_for((long)out_features * in_features), 256, 0, (cudaStream_t)stream, 
+  noisy_compose_kernel<<<grid_for((long)out_features * in_features), 256, 0, (cudaStream_t)stream>>>(
       out_features, in_features, weight_mu, weight_sigma, weight_epsilon, eps_in, eps_out, bias_mu, bias_sigma,
       bias_epsilon, w_eff, b_eff, training);
   return (int)cudaGetLastError();
@@ -923,7 +903,7 @@ RIQN_API int riqn_noisy_reset_net(int n_layers, const riqn_noisy_layer* layers, 
       blocks += (int)riqn_cdiv((layers[i].out_features + 3) / 4, 256);
       net.blk_end[2 * i + 1] = blocks;
     }
-    riqn::launch_pdl(noisy_fill_net_kernel, blocks, 256, 0, s, net, seed, dyn);
+    noisy_fill_net_kernel<<<blocks, 256, 0, s>>>(net, seed, dyn);
     RIQN_LAUNCH_CHECK();
   }
   riqn::note_launches(1);
@@ -932,7 +912,7 @@ RIQN_API int riqn_noisy_reset_net(int n_layers, const riqn_noisy_layer* layers, 
     blocks += (int)riqn_cdiv((long)layers[i].out_features * (layers[i].in_features / 4), 256);
     net.blk_end[i] = blocks;
   }
-  riqn::launch_pdl(noisy_compose_net_kernel, blocks, 256, 0, s, net, training);
+  noisy_compose_net_kernel<<<blocks, 256, 0, s>>>(net, training);
   return (int)cudaGetLastError();
 }
 
@@ -942,7 +922,7 @@ RIQN_API int riqn_quantile_embed_fwd(int batch, int num_quantiles, int embed_dim
   riqn::note_launches(2);
   cudaStream_t s = (cudaStream_t)stream;
   const long R = (long)batch * num_quantiles;
-  riqn::launch_pdl(cos_embed_kernel, riqn_cdiv(R * embed_dim, 256), 256, 0, s, batch, num_quantiles, embed_dim, tau, cosv);
+  cos_embed_kernel<<<riqn_cdiv(R * embed_dim, 256), 256, 0, s>>>(batch, num_quantiles, embed_dim, tau, cosv);
   RIQN_LAUNCH_CHECK();
   EpiArgs e;
   e.bias = iqn_b;
@@ -961,7 +941,7 @@ RIQN_API int riqn_quantile_embed_fwd_tc(int batch, int num_quantiles, int embed_
   riqn::note_launches(2);
   cudaStream_t s = (cudaStream_t)stream;
   const long R = (long)batch * num_quantiles;
-  riqn::launch_pdl(cos_embed_bf16_kernel, riqn_cdiv(R * embed_dim, 256), 256, 0, s, batch, num_quantiles, embed_dim, tau, (__nv_bfloat16*)cos_hi,
+  cos_embed_bf16_kernel<<<riqn_cdiv(R * embed_dim, 256), 256, 0, s>>>(batch, num_quantiles, embed_dim, tau, (__nv_bfloat16*)cos_hi,
                                                                      (__nv_bfloat16*)cos_lo, (__nv_bfloat16*)cosT_hi);
   RIQN_LAUNCH_CHECK();
   TcExtra ex;
@@ -995,17 +975,17 @@ RIQN_API int riqn_quantile_embed_bwd_tc(int batch, int num_quantiles, int embed_
   if (num_quantiles % 2 == 0 && feat_dim % 4 == 0) {
     dim3 grid((feat_dim + 127) / 128, batch);
 #define RIQN_EMB_BWD(DXB, XLO)                                                                                          \
-  riqn::launch_pdl(embed_bwd_wide_kernel<DXB, XLO>, grid, 256, 0, s, batch, num_quantiles, feat_dim, (const __nv_bfloat16*)x_hi,        \
+  embed_bwd_wide_kernel<DXB, XLO><<<grid, 256, 0, s>>>(batch, num_quantiles, feat_dim, (const __nv_bfloat16*)x_hi,        \
                                                        (const __nv_bfloat16*)x_lo, feat, (const float*)dx,                \
                                                        (const __nv_bfloat16*)dx, (__nv_bfloat16*)dpre, dfeat, grad_iqn_b)
     if (dx_is_bf16 && feat_dim % 8 == 0) {
       dim3 grid8((feat_dim + 255) / 256, batch);
       if (x_lo)
-        riqn::launch_pdl(embed_bwd_wide8_kernel<true>, grid8, 256, 0, s, batch, num_quantiles, feat_dim, (const __nv_bfloat16*)x_hi,
+        embed_bwd_wide8_kernel<true><<<grid8, 256, 0, s>>>(batch, num_quantiles, feat_dim, (const __nv_bfloat16*)x_hi,
                                                            (const __nv_bfloat16*)x_lo, feat, (const __nv_bfloat16*)dx,
                                                            (__nv_bfloat16*)dpre, dfeat, grad_iqn_b);
       else
-        riqn::launch_pdl(embed_bwd_wide8_kernel<false>, grid8, 256, 0, s, batch, num_quantiles, feat_dim, (const __nv_bfloat16*)x_hi,
+        embed_bwd_wide8_kernel<false><<<grid8, 256, 0, s>>>(batch, num_quantiles, feat_dim, (const __nv_bfloat16*)x_hi,
                                                             nullptr, feat, (const __nv_bfloat16*)dx, (__nv_bfloat16*)dpre,
                                                             dfeat, grad_iqn_b);
     } else if (dx_is_bf16) { if (x_lo) RIQN_EMB_BWD(true, true); else RIQN_EMB_BWD(true, false); }
@@ -1013,7 +993,7 @@ RIQN_API int riqn_quantile_embed_bwd_tc(int batch, int num_quantiles, int embed_
 #undef RIQN_EMB_BWD
   } else {
     dim3 grid((feat_dim + 31) / 32, batch);
-    riqn::launch_pdl(embed_bwd_tile_kernel, grid, 256, 0, s, batch, num_quantiles, feat_dim, (const __nv_bfloat16*)x_hi,
+    embed_bwd_tile_kernel<<<grid, 256, 0, s>>>(batch, num_quantiles, feat_dim, (const __nv_bfloat16*)x_hi,
                                                (const __nv_bfloat16*)x_lo, feat, dx_is_bf16 ? nullptr : (const float*)dx,
                                                dx_is_bf16 ? (const __nv_bfloat16*)dx : nullptr, (__nv_bfloat16*)dpre, dfeat,
                                                grad_iqn_b);
@@ -1034,7 +1014,7 @@ RIQN_API int riqn_quantile_embed_bwd(int batch, int num_quantiles, int embed_dim
   riqn::note_launches(3);
   cudaStream_t s = (cudaStream_t)stream;
   const long R = (long)batch * num_quantiles;
-  riqn::launch_pdl(embed_bwd_elem_kernel, riqn_cdiv((long)batch * feat_dim, 256), 256, 0, s, batch, num_quantiles, feat_dim, x, feat,
+  embed_bwd_elem_kernel<<<riqn_cdiv((long)batch * feat_dim, 256), 256, 0, s>>>(batch, num_quantiles, feat_dim, x, feat,
                                                                              dx_inout, dfeat);
   RIQN_LAUNCH_CHECK();
   int rc = colsum_atomic(R, feat_dim, dx_inout, grad_iqn_b, s);
@@ -1080,7 +1060,7 @@ RIQN_API int riqn_noisy_linear_wgrad(long rows, int in_features, int out_feature
   RIQN_CUDA(cudaMemsetAsync(db_scratch, 0, sizeof(float) * out_features, s));
   rc = colsum_atomic(rows, out_features, dh, db_scratch, s);
   if (rc) return rc;
-  riqn::launch_pdl(noisy_bias_grad_kernel, riqn_cdiv(out_features, 256), 256, 0, s, out_features, db_scratch, bias_epsilon,
+  noisy_bias_grad_kernel<<<riqn_cdiv(out_features, 256), 256, 0, s>>>(out_features, db_scratch, bias_epsilon,
                                                                     grad_bias_mu, grad_bias_sigma);
   return (int)cudaGetLastError();
 }
@@ -1094,7 +1074,7 @@ RIQN_API int riqn_noisy_bias_grad(long rows, int out_features, const float* dh, 
     int rc = colsum_atomic(rows, out_features, dh, db_scratch, s);
     if (rc) return rc;
   }
-  riqn::launch_pdl(noisy_bias_grad_kernel, riqn_cdiv(out_features, 256), 256, 0, s, out_features, db_scratch, bias_epsilon,
+  noisy_bias_grad_kernel<<<riqn_cdiv(out_features, 256), 256, 0, s>>>(out_features, db_scratch, bias_epsilon,
                                                                     grad_bias_mu, grad_bias_sigma);
   return (int)cudaGetLastError();
 }
@@ -1117,9 +1097,9 @@ RIQN_API int riqn_dueling_fwd(long rows, int batch, int hidden, int action_space
       RIQN_CUDA(cudaFuncSetAttribute(z_dueling_fwd4_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
       attr4_once.done[attr4_dev] = true;
     }
-    riqn::launch_pdl(z_dueling_fwd4_kernel<512>, 148 * 2, 256, smem, (cudaStream_t)stream, rows, batch, action_space, h, wz, bz, q);
+    z_dueling_fwd4_kernel<512><<<148 * 2, 256, smem, (cudaStream_t)stream>>>(rows, batch, action_space, h, wz, bz, q);
   } else {
-    riqn::launch_pdl(z_dueling_fwd_kernel<512>, 148 * 4, 256, smem, (cudaStream_t)stream, rows, batch, action_space, h, wz, bz, q);
+    z_dueling_fwd_kernel<512><<<148 * 4, 256, smem, (cudaStream_t)stream>>>(rows, batch, action_space, h, wz, bz, q);
   }
   return (int)cudaGetLastError();
 }
@@ -1136,7 +1116,7 @@ RIQN_API int riqn_dueling_bwd(long rows, int batch, int hidden, int action_space
     RIQN_CUDA(cudaFuncSetAttribute(z_dueling_bwd_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     attr_once.done[attr_dev] = true;
   }
-  riqn::launch_pdl(z_dueling_bwd_kernel<512>, 148 * 4, 256, smem, (cudaStream_t)stream, rows, batch, action_space, h, wz, dtheta, gscale,
+  z_dueling_bwd_kernel<512><<<148 * 4, 256, smem, (cudaStream_t)stream>>>(rows, batch, action_space, h, wz, dtheta, gscale,
                                                                        (const int64_t*)actions, dh, dz, (__nv_bfloat16*)dz_bf16);
   return (int)cudaGetLastError();
 }
@@ -1157,7 +1137,7 @@ RIQN_API int riqn_dueling_bwd_bf16(long rows, int batch, int hidden, int action_
   }
   RIQN_CUDA(cudaMemsetAsync(dh_colsum, 0, sizeof(float) * 2 * hidden, s));
   const long n_blk = (rows + 31) / 32;
-  riqn::launch_pdl(z_dueling_bwd_bf16_kernel<512>, (unsigned)(n_blk < 148 * 2 ? n_blk : 148 * 2), 256, smem, s, 
+  z_dueling_bwd_bf16_kernel<512><<<(unsigned)(n_blk < 148 * 2 ? n_blk : 148 * 2), 256, smem, s>>>(
       rows, batch, action_space, h, (const __nv_bfloat16*)h_bf16, wz, dtheta, gscale, (const int64_t*)actions,
       (__nv_bfloat16*)dh_hi,
       (__nv_bfloat16*)dh_hi_t, dh_colsum, dz, (__nv_bfloat16*)dz_bf16);
@@ -1180,7 +1160,7 @@ RIQN_API int riqn_z_wgrad(long rows, int hidden, int action_space, const float* 
   if (rc) return rc;
   rc = colsum_atomic(rows, 32, dz, dbz_scratch, s);
   if (rc) return rc;
-  riqn::launch_pdl(z_wgrad_finish_kernel, riqn_cdiv((long)action_space * hidden, 256), 256, 0, s, 
+  z_wgrad_finish_kernel<<<riqn_cdiv((long)action_space * hidden, 256), 256, 0, s>>>(
       action_space, hidden, dwz_scratch, dbz_scratch, eps_w_zv, eps_b_zv, eps_w_za, eps_b_za, g_mu_zv, g_sig_zv, g_bmu_zv,
       g_bsig_zv, g_mu_za, g_sig_za, g_bmu_za, g_bsig_za);
   return (int)cudaGetLastError();
@@ -1207,7 +1187,7 @@ RIQN_API int riqn_z_wgrad_tc(long rows, int hidden, int action_space, const void
   if (rc) return rc;
   rc = colsum_atomic(rows, 32, dz, dbz_scratch, s);
   if (rc) return rc;
-  riqn::launch_pdl(z_wgrad_finish_kernel, riqn_cdiv((long)action_space * hidden, 256), 256, 0, s, 
+  z_wgrad_finish_kernel<<<riqn_cdiv((long)action_space * hidden, 256), 256, 0, s>>>(
       action_space, hidden, dwz_scratch, dbz_scratch, eps_w_zv, eps_b_zv, eps_w_za, eps_b_za, g_mu_zv, g_sig_zv, g_bmu_zv,
       g_bsig_zv, g_mu_za, g_sig_za, g_bmu_za, g_bsig_za);
   return (int)cudaGetLastError();
@@ -1217,7 +1197,7 @@ RIQN_API int riqn_argmax_mean(int batch, int num_quantiles, int action_space, co
                               void* stream) {
   riqn::note_launches(1);
   if (action_space > 32) return (int)cudaErrorInvalidValue;
-  riqn::launch_pdl(argmax_mean_kernel, riqn_cdiv((long)batch * 32, 128), 128, 0, (cudaStream_t)stream, batch, num_quantiles, action_space, q,
+  argmax_mean_kernel<<<riqn_cdiv((long)batch * 32, 128), 128, 0, (cudaStream_t)stream>>>(batch, num_quantiles, action_space, q,
                                                                             (int64_t*)a_star);
   return (int)cudaGetLastError();
 }
@@ -1232,7 +1212,7 @@ RIQN_API int riqn_iqn_loss_fwd_bwd(int batch, int n_tau, int n_tau_prime, int ac
   if (threads > 1024) threads = 1024;
   if (threads < 32) threads = 32;
   const size_t smem = sizeof(float) * (n_tau_prime + 32);
-  riqn::launch_pdl(iqn_loss_kernel, batch, threads, smem, (cudaStream_t)stream, 
+  iqn_loss_kernel<<<batch, threads, smem, (cudaStream_t)stream>>>(
       batch, n_tau, n_tau_prime, action_space, q_online, q_target, tau, (const int64_t*)actions, (const int64_t*)a_star,
       returns, nonterminals, gamma_n, kappa, loss, dtheta, theta_out, target_out);
   return (int)cudaGetLastError();
@@ -1244,7 +1224,7 @@ RIQN_API int riqn_adam_step(long n, float* params, const float* grads, float* ex
   riqn::note_launches(1);
   const double bc1 = 1.0 - pow((double)beta1, (double)step);
   const double bc2 = 1.0 - pow((double)beta2, (double)step);
-  riqn::launch_pdl(adam_kernel, grid_for(n), 256, 0, (cudaStream_t)stream, n, params, grads, exp_avg, exp_avg_sq, (float)(-(lr / bc1)),
+  adam_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(n, params, grads, exp_avg, exp_avg_sq, (float)(-(lr / bc1)),
                                                             (float)sqrt(bc2), eps, beta1, beta2, grad_scale, dyn);
   return (int)cudaGetLastError();
 }

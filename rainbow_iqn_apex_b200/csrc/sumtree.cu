@@ -22,7 +22,6 @@ namespace riqn {
 // (redis_memory.py:276-287).  Single CTA; thread 0 runs the Fisher-Yates shuffle in shared memory.
 __global__ void stratified_kernel(int n, uint64_t seed, uint64_t stream, const double* __restrict__ tree,
                                   double* __restrict__ values, const riqn_dyn_state* __restrict__ dyn) {
-  pdl_sync();
   if (dyn) stream += dyn->rng_offset;
   // the shuffle: stratum s goes to output slot rank(key_s), keys = Philox draws (ties broken by index)
   extern __shared__ uint32_t keys[];
@@ -46,7 +45,6 @@ __global__ void sumtree_sample_kernel(int n, long C, int actor_cap, const double
                                       const double* __restrict__ values, const int64_t* __restrict__ index_actor,
                                       int history, int n_step, int64_t* __restrict__ tree_idx,
                                       int64_t* __restrict__ data_idx, double* __restrict__ priorities) {
-  pdl_sync();
   const int lane = threadIdx.x & 31;
   const long q = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (q >= n) return;
@@ -107,7 +105,6 @@ __global__ void sumtree_sample_kernel(int n, long C, int actor_cap, const double
 __global__ void is_weights_kernel(int n, const double* __restrict__ tree, const double* __restrict__ priorities,
                                   double capacity, double beta, double* __restrict__ w64, float* __restrict__ w32,
                                   int* __restrict__ n_nonpositive, const riqn_dyn_state* __restrict__ dyn) {
-  pdl_sync();
   if (dyn) { capacity = dyn->is_capacity; beta = dyn->is_beta; }
   __shared__ double red[32];
   __shared__ int cnt;
@@ -149,7 +146,6 @@ __global__ void update_prepare_kernel(int n, const double* __restrict__ tree, co
                                       const float* __restrict__ loss, float exponent, int apply_pow,
                                       float* __restrict__ new_pri, double* __restrict__ diff,
                                       double* __restrict__ max_priority) {
-  pdl_sync();
   __shared__ float red[32];
   float mx = -INFINITY;
   for (int j = threadIdx.x; j < n; j += blockDim.x) {
@@ -283,7 +279,6 @@ __device__ double np_pairwise_sum_cta(const double* a, int n, int* lo, int* ll, 
 // adds, so every node is written by one thread only.
 __global__ void update_propagate_kernel(int n, int max_depth, double* __restrict__ tree,
                                         const int64_t* __restrict__ idx, const double* __restrict__ diff) {
-  pdl_sync();
   extern __shared__ unsigned char smem_raw[];
   int64_t* node = reinterpret_cast<int64_t*>(smem_raw);
   double* sd = reinterpret_cast<double*>(node + n);
@@ -347,7 +342,6 @@ __global__ void replay_append_kernel(int n, int actor_cap, int id_actor, int sta
                                      uint8_t* __restrict__ s_frames, int32_t* __restrict__ s_timestep,
                                      int32_t* __restrict__ s_action, float* __restrict__ s_reward,
                                      uint8_t* __restrict__ s_nonterminal) {
-  pdl_sync();
   const int i = blockIdx.x;
   const long slot = (long)((start + i) % actor_cap) + (long)id_actor * actor_cap;
   const uint4* src = reinterpret_cast<const uint4*>(frames + (long)i * FRAME_BYTES);
@@ -370,7 +364,6 @@ __global__ void frame_gather_kernel(int B, int actor_cap, int history, int n_ste
                                     const uint8_t* __restrict__ s_nonterminal, const double* __restrict__ gamma_pow,
                                     uint8_t* __restrict__ window, int64_t* __restrict__ actions,
                                     float* __restrict__ returns, float* __restrict__ nonterminals) {
-  pdl_sync();
   const int b = blockIdx.x;
   const int L = history + n_step;
   __shared__ long slots[16];
@@ -419,7 +412,7 @@ RIQN_API int riqn_sumtree_stratified(int n, unsigned long long seed, unsigned lo
                                      double* values, const riqn_dyn_state* dyn, void* stream) {
   riqn::note_launches(1);
   if (n <= 0 || n > 12000) return (int)cudaErrorInvalidValue;
-  riqn::launch_pdl(stratified_kernel, 1, 1024, sizeof(int) * n, (cudaStream_t)stream, n, seed, stream_id, tree, values, dyn);
+  stratified_kernel<<<1, 1024, sizeof(int) * n, (cudaStream_t)stream>>>(n, seed, stream_id, tree, values, dyn);
   return (int)cudaGetLastError();
 }
 
@@ -429,7 +422,7 @@ RIQN_API int riqn_sumtree_sample(int n, long capacity, int actor_capacity, const
   riqn::note_launches(1);
   if (n <= 0) return 0;
   const int warps_per_block = 4;
-  riqn::launch_pdl(sumtree_sample_kernel, riqn_cdiv(n, warps_per_block), warps_per_block * 32, 0, (cudaStream_t)stream, 
+  sumtree_sample_kernel<<<riqn_cdiv(n, warps_per_block), warps_per_block * 32, 0, (cudaStream_t)stream>>>(
       n, capacity, actor_capacity, tree, values, (const int64_t*)index_actor, history, n_step, (int64_t*)tree_idx,
       (int64_t*)data_idx, priorities);
   return (int)cudaGetLastError();
@@ -439,7 +432,7 @@ RIQN_API int riqn_sumtree_is_weights(int n, const double* tree, const double* pr
                                      double priority_weight, double* w64, float* w32, int* n_nonpositive,
                                      const riqn_dyn_state* dyn, void* stream) {
   riqn::note_launches(1);
-  riqn::launch_pdl(is_weights_kernel, 1, 1024, 0, (cudaStream_t)stream, n, tree, priorities, current_capacity, priority_weight, w64,
+  is_weights_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(n, tree, priorities, current_capacity, priority_weight, w64,
                                                           w32, n_nonpositive, dyn);
   return (int)cudaGetLastError();
 }
@@ -451,7 +444,7 @@ RIQN_API int riqn_sumtree_update(int n, long capacity, double* tree, const long 
   if (n <= 0) return 0;
   if (n > 4096) return (int)cudaErrorInvalidValue;  // shared-memory bound of the propagate kernel
   cudaStream_t s = (cudaStream_t)stream;
-  riqn::launch_pdl(update_prepare_kernel, 1, 1024, 0, s, n, tree, (const int64_t*)tree_idx, loss, priority_exponent, apply_pow,
+  update_prepare_kernel<<<1, 1024, 0, s>>>(n, tree, (const int64_t*)tree_idx, loss, priority_exponent, apply_pow,
                                            new_priorities, diff_scratch, max_priority);
   RIQN_LAUNCH_CHECK();
   int max_depth = 0;  // depth of the deepest leaf (index 2C-2)
@@ -464,7 +457,7 @@ RIQN_API int riqn_sumtree_update(int n, long capacity, double* tree, const long 
     attr_once.done[attr_dev] = true;
   }
   const int slices = (n + 127) / 128 < 8 ? (n + 127) / 128 : 8;
-  riqn::launch_pdl(update_propagate_kernel, dim3(max_depth + 1, slices), 128, smem, s, n, max_depth, tree, (const int64_t*)tree_idx,
+  update_propagate_kernel<<<dim3(max_depth + 1, slices), 128, smem, s>>>(n, max_depth, tree, (const int64_t*)tree_idx,
                                                                         diff_scratch);
   return (int)cudaGetLastError();
 }
@@ -475,7 +468,7 @@ RIQN_API int riqn_replay_append(int n, int actor_capacity, int id_actor, int sta
                                 float* s_reward, unsigned char* s_nonterminal, void* stream) {
   riqn::note_launches(1);
   if (n <= 0) return 0;
-  riqn::launch_pdl(replay_append_kernel, n, 128, 0, (cudaStream_t)stream, n, actor_capacity, id_actor, start, frames, timestep, action,
+  replay_append_kernel<<<n, 128, 0, (cudaStream_t)stream>>>(n, actor_capacity, id_actor, start, frames, timestep, action,
                                                             reward, nonterminal, s_frames, s_timestep, s_action, s_reward,
                                                             s_nonterminal);
   return (int)cudaGetLastError();
@@ -489,7 +482,7 @@ RIQN_API int riqn_frame_gather(int batch, int actor_capacity, int history, int n
   riqn::note_launches(1);
   if (batch <= 0) return 0;
   if (history + n_step > 16) return (int)cudaErrorInvalidValue;
-  riqn::launch_pdl(frame_gather_kernel, batch, 256, 0, (cudaStream_t)stream, batch, actor_capacity, history, n_step,
+  frame_gather_kernel<<<batch, 256, 0, (cudaStream_t)stream>>>(batch, actor_capacity, history, n_step,
                                                                (const int64_t*)data_idx, s_frames, s_timestep, s_action,
                                                                s_reward, s_nonterminal, gamma_pow, window,
                                                                (int64_t*)actions, returns, nonterminals);
