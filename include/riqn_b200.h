@@ -231,8 +231,10 @@ int riqn_dueling_fwd(long rows, int batch, int hidden, int action_space, const f
  * already masked by h > 0, and dz (rows, 32) = [dv, da_0.., 0..] for riqn_z_wgrad; dz_bf16 (may be NULL) is its bf16
  * image (rows, 32) for riqn_z_wgrad_tc. */
 int riqn_dueling_bwd(long rows, int batch, int hidden, int action_space, const float* h, const float* wz,
-                     const float* dtheta, const float* gscale, const long long* actions, float* dh, float* dz,
-                     void* dz_bf16, void* stream);
+                     const float* dtheta, const float* gscale, float gscale_mul, const long long* actions, float* dh,
+                     float* dz, void* dz_bf16, void* stream);
+/* (gscale_mul multiplies gscale[b]: the learner passes the IS weights and 1/B, learner.py:23's .mean(), without an extra
+ * elementwise launch) */
 /* Same backward for bf16 tensor-core consumers (rows % 8 == 0): instead of the fp32 dh it writes dh_hi (rows, 2*hidden)
  * as bf16 (and its transpose dh_hi_t (2*hidden, rows) if non-NULL), dh_colsum (2*hidden) = the fp32 column sums of dh
  * (zeroed here; pass it to riqn_noisy_bias_grad with dh == NULL) and dz_bf16 (rows, 32), if non-NULL, the bf16 image of
@@ -240,7 +242,8 @@ int riqn_dueling_bwd(long rows, int batch, int hidden, int action_space, const f
  * instead of h. */
 int riqn_dueling_bwd_bf16(long rows, int batch, int hidden, int action_space, const float* h, const void* h_bf16,
                           const float* wz,
-                          const float* dtheta, const float* gscale, const long long* actions, void* dh_hi, void* dh_hi_t,
+                          const float* dtheta, const float* gscale, float gscale_mul, const long long* actions, void* dh_hi,
+                          void* dh_hi_t,
                           float* dh_colsum, float* dz, void* dz_bf16, void* stream);
 /* Parameter gradients of the two z-layers (accumulated): dwz_scratch 32*2*hidden floats, dbz_scratch 32. */
 /* Same with the reduction dz^T h on the tensor cores, straight from the row-major bf16 images dz_bf16 (rows, 32) and
@@ -285,8 +288,10 @@ int riqn_c51_loss_fwd_bwd(int batch, int action_space, int atoms, const float* l
                           const float* nonterminals, const float* support, float gamma_n, float v_min, float v_max,
                           float delta_z, float* loss, float* dq, float* m_out, void* stream);
 /* dzv (batch, atoms), dza (batch, A*atoms) from dq scaled by gscale[b] (dueling backward). */
-int riqn_c51_head_bwd(int batch, int action_space, int atoms, const float* dq, const float* gscale,
+int riqn_c51_head_bwd(int batch, int action_space, int atoms, const float* dq, const float* gscale, float gscale_mul,
                       const long long* actions, float* dzv, float* dza, void* stream);
+/* n floats <- 0 (the gradient arena's zero_grad, learner.py:22): cudaMemsetAsync on the caller's stream. */
+int riqn_zero_f32(float* p, long n, void* stream);
 /* grad[i] = 0 where act[i] <= 0. */
 int riqn_relu_mask(long n, const float* act, float* grad, void* stream);
 /* Strided fp32 linear-layer helpers for the small z-layers: y = x w^T + bias (optional ReLU); dx = dy w;

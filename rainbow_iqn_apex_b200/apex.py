@@ -66,6 +66,32 @@ class ShardSample:
                     nonterminals=torch.zeros(n_max, dtype=torch.float32, device=device))
 
 
+def packed_bytes(n_max, history=4, n_step=3):
+    return n_max * ((history + n_step) * FRAME + 8 + 8 + 8 + 4 + 4) + 16
+
+
+def pack(sample, stat, n_max):
+    """One contiguous uint8 record per shard -- [windows | tree_idx | pri | actions | returns | nonterminals | shard total,
+    filled capacity] -- so that a learner batch costs ONE gather instead of eight (every section starts 8-byte aligned)."""
+    parts = [sample[k].reshape(n_max, -1).contiguous().view(torch.uint8).reshape(-1) for k in ShardSample.FIELDS]
+    return torch.cat(parts + [stat.contiguous().view(torch.uint8)])
+
+
+def unpack(buf, n_max, history=4, n_step=3):
+    """Views into a packed record (no copies).  Returns (sample dict, stat (2,) float64)."""
+    L = history + n_step
+    sizes = (("window", n_max * L * FRAME, torch.uint8), ("tree_idx", n_max * 8, torch.int64), ("pri", n_max * 8, torch.float64),
+             ("actions", n_max * 8, torch.int64), ("returns", n_max * 4, torch.float32), ("nonterminals", n_max * 4, torch.float32))
+    out, off = {}, 0
+    by_name = dict((n, (sz, dt)) for n, sz, dt in sizes)
+    for k in ShardSample.FIELDS:
+        sz, dt = by_name[k]
+        v = buf[off:off + sz].view(dt)
+        out[k] = v.view(n_max, L, 84, 84) if k == "window" else v
+        off += sz
+    return out, buf[off:off + 16].view(torch.float64)
+
+
 def sample_shard(mem, count, n_max, samples=None):
     """Actor-rank half of a learner sample: ``count`` prioritized transitions of this shard, padded to n_max rows."""
     tr = mem.transitions
@@ -221,30 +247,45 @@ class ApexTopology:
         self.shard = self.rank - 1
         self.steps = 0
 
-    def _gather(self, t):
-        """Gather same-shaped tensors to the learner (rank 0 contributes a dummy that is dropped)."""
-        out = [torch.empty_like(t) for _ in range(self.world)] if self.is_learner else None
-        dist.gather(t, out, dst=0, group=self.group)
-        return out[1:] if self.is_learner else None
-
-    def sample(self, mem=None, beta=0.4, device=None, history=4, n_step=3):
-        """Learner: returns the assembled batch (see assemble_batch).  Actor ranks: contribute and return their own
-        ShardSample (kept for route())."""
+    def sample_begin(self, mem=None, device=None, history=4, n_step=3):
+        """First half of a learner sample: every shard draws its transitions and ONE gather of the packed records is
+        enqueued (on the current stream).  Returns a ticket for sample_end().  The learner may call this for step t+1
+        before it learns on step t -- the reference's sampler process runs ahead of its learner the same way
+        (launch_learner.py:24-50, a queue of 5 batches) -- as long as every rank issues its collectives in the same order."""
+        nbytes = packed_bytes(self.n_max, history, n_step)
         if self.is_learner:
-            mine = ShardSample.empty(self.n_max, device, history, n_step)
-            stat = torch.zeros(2, dtype=torch.float64, device=device)
+            # two persistent receive sets (ping-pong): the gather of batch t+1 may run on a side stream while batch t is
+            # still being consumed, and stream-ordered allocations must not be recycled under it
+            if getattr(self, "_recv", None) is None:
+                self._recv = [[torch.zeros(nbytes, dtype=torch.uint8, device=device) for _ in range(self.world)]
+                              for _ in range(2)]
+                self._recv_i = 0
+            self._recv_i ^= 1
+            out = self._recv[self._recv_i]
+            mine, rec = None, out[0]
         else:
             mine = sample_shard(mem, self.counts[self.shard], self.n_max)
             stat = torch.stack([mem.transitions.tree[0], torch.tensor(float(mem.transitions.get_current_capacity()),
                                                                       dtype=torch.float64, device=mem.device)])
-        parts = {k: self._gather(mine[k]) for k in ShardSample.FIELDS}
-        stats = self._gather(stat)
+            rec, out = pack(mine, stat, self.n_max), None
+        dist.gather(rec, out, dst=0, group=self.group)
+        return dict(mine=mine, out=out, history=history, n_step=n_step)
+
+    def sample_end(self, ticket, beta=0.4):
+        """Learner: the assembled batch (see assemble_batch).  Actor ranks: their own ShardSample (kept for route())."""
         if not self.is_learner:
-            return mine
-        plist = [{k: parts[k][s] for k in ShardSample.FIELDS} for s in range(self.n_shards)]
-        totals = torch.stack([s[0] for s in stats])
-        filled = float(sum(float(s[1]) for s in stats))
-        return assemble_batch(plist, self.counts, totals, filled, beta, history, n_step)
+            return ticket["mine"]
+        h, n = ticket["history"], ticket["n_step"]
+        plist, stats = [], []
+        for s in range(self.n_shards):
+            smp, stat = unpack(ticket["out"][s + 1], self.n_max, h, n)
+            plist.append(smp)
+            stats.append(stat)
+        st = torch.stack(stats).cpu()                      # (S, 2): shard totals and filled capacities, one small D2H
+        return assemble_batch(plist, self.counts, st[:, 0].to(plist[0]["pri"].device), float(st[:, 1].sum()), beta, h, n)
+
+    def sample(self, mem=None, beta=0.4, device=None, history=4, n_step=3):
+        return self.sample_end(self.sample_begin(mem, device, history, n_step), beta)
 
     def route(self, loss, mem=None, sample=None):
         """Broadcast the learner's per-transition losses; each actor rank updates the leaves it sampled."""

@@ -87,7 +87,7 @@ def loss_core(agent, states, actions, returns, next_states, nonterminals, debug=
         debug.update(a_star=a_star, m=m_out, log_ps=log_ps)
     version = getattr(on, "_noise_version", 0)       # bumped by every DQN.reset_noise()
 
-    def backward(gscale):
+    def backward(gscale, gscale_mul=1.0):
         if getattr(on, "_noise_version", 0) != version:
             raise RuntimeError("the online network's noise was resampled between the C51 loss and its backward")
         hid = on.hidden
@@ -97,7 +97,7 @@ def loss_core(agent, states, actions, returns, next_states, nonterminals, debug=
         gscale = gscale.contiguous().float()
         dzv = torch.empty(B, atoms, device=dev)
         dza = torch.empty(B, A * atoms, device=dev)
-        call("riqn_c51_head_bwd", B, A, atoms, ptr(dq), ptr(gscale), ptr(actions), ptr(dzv), ptr(dza))
+        call("riqn_c51_head_bwd", B, A, atoms, ptr(dq), ptr(gscale), float(gscale_mul), ptr(actions), ptr(dzv), ptr(dza))
         dh = torch.empty(B, 2 * hid, device=dev)
         dhv, dha = dh[:, :hid], dh[:, hid:]
         hv, ha = h[:, :hid], h[:, hid:]

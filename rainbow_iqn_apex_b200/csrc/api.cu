@@ -21,3 +21,7 @@ void note_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); 
 }  // namespace riqn
 
 RIQN_API long long riqn_launch_count(void) { return riqn::g_launches.load(std::memory_order_relaxed); }
+
+RIQN_API int riqn_zero_f32(float* p, long n, void* stream) {
+  return (int)cudaMemsetAsync(p, 0, sizeof(float) * (size_t)n, (cudaStream_t)stream);
+}

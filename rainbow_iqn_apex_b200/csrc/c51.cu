@@ -113,13 +113,13 @@ __global__ void c51_loss_kernel(int A, int atoms, const float* __restrict__ logp
 }
 
 // dzv[b,j] = g*dq[b,j] ; dza[b,a,j] = g*dq[b,j]*(1{a==act} - 1/A)
-__global__ void c51_head_bwd_kernel(int B, int A, int atoms, const float* __restrict__ dq, const float* __restrict__ gscale,
+__global__ void c51_head_bwd_kernel(int B, int A, int atoms, const float* __restrict__ dq, const float* __restrict__ gscale, float gmul,
                                     const int64_t* __restrict__ actions, float* __restrict__ dzv, float* __restrict__ dza) {
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long)B * A * atoms) return;
   const int j = (int)(idx % atoms), a = (int)((idx / atoms) % A);
   const long b = idx / ((long)atoms * A);
-  const float g = dq[b * atoms + j] * gscale[b];
+  const float g = dq[b * atoms + j] * (gscale[b] * gmul);
   dza[idx] = g * ((a == (int)actions[b] ? 1.f : 0.f) - 1.f / (float)A);
   if (a == 0) dzv[b * atoms + j] = g;
 }
@@ -153,11 +153,11 @@ RIQN_API int riqn_c51_loss_fwd_bwd(int batch, int action_space, int atoms, const
   return (int)cudaGetLastError();
 }
 
-RIQN_API int riqn_c51_head_bwd(int batch, int action_space, int atoms, const float* dq, const float* gscale,
+RIQN_API int riqn_c51_head_bwd(int batch, int action_space, int atoms, const float* dq, const float* gscale, float gscale_mul,
                                const long long* actions, float* dzv, float* dza, void* stream) {
   riqn::note_launches(1);
   const long n = (long)batch * action_space * atoms;
-  c51_head_bwd_kernel<<<riqn_cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(batch, action_space, atoms, dq, gscale,
+  c51_head_bwd_kernel<<<riqn_cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(batch, action_space, atoms, dq, gscale, gscale_mul,
                                                                           (const int64_t*)actions, dzv, dza);
   return (int)cudaGetLastError();
 }

@@ -598,7 +598,7 @@ __global__ void iqn_loss_kernel(int B, int N, int Np, int A, const float* __rest
 // ------------------------------------------------------------------------------------------------
 template <int HID>
 __global__ void z_dueling_bwd_kernel(long R, int B, int A, const float* __restrict__ H, const float* __restrict__ Wz,
-                                     const float* __restrict__ dtheta, const float* __restrict__ gscale,
+                                     const float* __restrict__ dtheta, const float* __restrict__ gscale, float gmul,
                                      const int64_t* __restrict__ actions, float* __restrict__ dH,
                                      float* __restrict__ dz, __nv_bfloat16* __restrict__ dz_bf) {
   extern __shared__ float sW[];  // (1+A)*HID weights + HID colmean
@@ -615,7 +615,7 @@ __global__ void z_dueling_bwd_kernel(long R, int B, int A, const float* __restri
   for (long r = (long)blockIdx.x * wpb + warp; r < R; r += (long)gridDim.x * wpb) {
     const int Nq = (int)(R / B);
     const int b = (int)(r / Nq);                            // sample-major rows; dtheta arrives quantile-major
-    const float g = dtheta[(r - (long)b * Nq) * B + b] * gscale[b];
+    const float g = dtheta[(r - (long)b * Nq) * B + b] * (gscale[b] * gmul);
     const int act = (int)actions[b];
     const float* h = H + r * (2 * HID);
     float* o = dH + r * (2 * HID);
@@ -641,7 +641,7 @@ __global__ void __launch_bounds__(256) z_dueling_bwd_bf16_kernel(long R, int B, 
                                                                  const __nv_bfloat16* __restrict__ Hb,
                                                                  const float* __restrict__ Wz,
                                                                  const float* __restrict__ dtheta,
-                                                                 const float* __restrict__ gscale,
+                                                                 const float* __restrict__ gscale, float gmul,
                                                                  const int64_t* __restrict__ actions,
                                                                  __nv_bfloat16* __restrict__ dh_hi,
                                                                  __nv_bfloat16* __restrict__ dh_hiT,
@@ -677,7 +677,7 @@ __global__ void __launch_bounds__(256) z_dueling_bwd_bf16_kernel(long R, int B, 
     const bool ok = r < R;
     const long rc = ok ? r : 0;
     const int b = (int)(rc / Nq);                            // sample-major rows; dtheta arrives quantile-major
-    const float g = ok ? dtheta[(rc - (long)b * Nq) * B + b] * gscale[b] : 0.f;
+    const float g = ok ? dtheta[(rc - (long)b * Nq) * B + b] * (gscale[b] * gmul) : 0.f;
     const int act = (int)actions[b];
     const float* wa = sW + (1 + act) * HID;
     // the ReLU mask only needs the SIGN of h: read the bf16 image when the forward left one (half the bytes); all of
@@ -1105,7 +1105,7 @@ RIQN_API int riqn_dueling_fwd(long rows, int batch, int hidden, int action_space
 }
 
 RIQN_API int riqn_dueling_bwd(long rows, int batch, int hidden, int action_space, const float* h, const float* wz,
-                              const float* dtheta, const float* gscale, const long long* actions, float* dh, float* dz,
+                              const float* dtheta, const float* gscale, float gscale_mul, const long long* actions, float* dh, float* dz,
                               void* dz_bf16, void* stream) {
   riqn::note_launches(1);
   if (hidden != 512 || action_space > 31) return (int)cudaErrorInvalidValue;
@@ -1116,14 +1116,14 @@ RIQN_API int riqn_dueling_bwd(long rows, int batch, int hidden, int action_space
     RIQN_CUDA(cudaFuncSetAttribute(z_dueling_bwd_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     attr_once.done[attr_dev] = true;
   }
-  z_dueling_bwd_kernel<512><<<148 * 4, 256, smem, (cudaStream_t)stream>>>(rows, batch, action_space, h, wz, dtheta, gscale,
+  z_dueling_bwd_kernel<512><<<148 * 4, 256, smem, (cudaStream_t)stream>>>(rows, batch, action_space, h, wz, dtheta, gscale, gscale_mul,
                                                                        (const int64_t*)actions, dh, dz, (__nv_bfloat16*)dz_bf16);
   return (int)cudaGetLastError();
 }
 
 RIQN_API int riqn_dueling_bwd_bf16(long rows, int batch, int hidden, int action_space, const float* h, const void* h_bf16,
                                    const float* wz,
-                                   const float* dtheta, const float* gscale, const long long* actions, void* dh_hi,
+                                   const float* dtheta, const float* gscale, float gscale_mul, const long long* actions, void* dh_hi,
                                    void* dh_hi_t, float* dh_colsum, float* dz, void* dz_bf16, void* stream) {
   riqn::note_launches(1);
   if (hidden != 512 || action_space > 31 || rows % 8) return (int)cudaErrorInvalidValue;
@@ -1138,7 +1138,7 @@ RIQN_API int riqn_dueling_bwd_bf16(long rows, int batch, int hidden, int action_
   RIQN_CUDA(cudaMemsetAsync(dh_colsum, 0, sizeof(float) * 2 * hidden, s));
   const long n_blk = (rows + 31) / 32;
   z_dueling_bwd_bf16_kernel<512><<<(unsigned)(n_blk < 148 * 2 ? n_blk : 148 * 2), 256, smem, s>>>(
-      rows, batch, action_space, h, (const __nv_bfloat16*)h_bf16, wz, dtheta, gscale, (const int64_t*)actions,
+      rows, batch, action_space, h, (const __nv_bfloat16*)h_bf16, wz, dtheta, gscale, gscale_mul, (const int64_t*)actions,
       (__nv_bfloat16*)dh_hi,
       (__nv_bfloat16*)dh_hi_t, dh_colsum, dz, (__nv_bfloat16*)dz_bf16);
   return (int)cudaGetLastError();

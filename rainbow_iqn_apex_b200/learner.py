@@ -70,7 +70,7 @@ class Learner(Agent):
             from . import c51
             loss, bw = c51.loss_core(self, states, actions, returns, next_states, nonterminals)
             on.zero_grad()
-            bw(weights / weights.shape[0])
+            bw(weights, 1.0 / weights.shape[0])
         else:
             loss, dtheta, keep, actions = compute_loss_iqn.loss_core(
                 self, states, actions, returns, next_states, nonterminals, keep_graph=True)
@@ -78,7 +78,7 @@ class Learner(Agent):
                 self._debug.update(keep=keep)
             on.zero_grad()                                                      # learner.py:22
             on._grads_ready_hook = self._start_tail_allreduce if (self.process_group is not None and self.overlap_allreduce) else None
-            on.backward_iqn(keep, dtheta, weights / weights.shape[0], actions)  # learner.py:23
+            on.backward_iqn(keep, dtheta, weights.contiguous(), actions, 1.0 / weights.shape[0])  # learner.py:23 (.mean())
             on._grads_ready_hook = None
         return loss
 

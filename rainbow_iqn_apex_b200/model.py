@@ -288,7 +288,10 @@ class DQN(nn.Module):
 
     def zero_grad(self, set_to_none=False):
         """One memset over the gradient arena; the .grad views stay bound (learner.py:22)."""
-        self._flat_grad.zero_()
+        if self._flat_grad.is_cuda:
+            call("riqn_zero_f32", ptr(self._flat_grad), self._flat_grad.numel())
+        else:                       # CPU arenas exist only for the host-logic tests (gloo); nothing computes there
+            self._flat_grad.zero_()
         for grp in self._param_groups_in_arena_order():
             for p in grp:
                 if p.grad is None or p.grad.data_ptr() != self._flat_grad.data_ptr() + 4 * self._offsets[id(p)]:
@@ -641,9 +644,9 @@ class DQN(nn.Module):
         return q, tau
 
     # ------------------------------------------------------------------ backward of forward()
-    def backward_iqn(self, keep, dtheta, gscale, actions):
+    def backward_iqn(self, keep, dtheta, gscale, actions, gscale_mul=1.0):
         """Accumulate dL/dparams into the gradient arena for the forward recorded in ``keep``, where
-        dL/dq[r, actions[b]] = dtheta[r] * gscale[b]  (r = quantile*B + b)."""
+        dL/dq[r, actions[b]] = dtheta[r] * gscale[b] * gscale_mul  (r = quantile*B + b)."""
         if keep.get("noise_version", None) != getattr(self, "_noise_version", 0):
             raise RuntimeError("the network's noise was resampled between this forward pass and its backward: the composed "
                                "weights / epsilons of the gradient pass are gone (call backward before the next reset_noise)")
@@ -669,11 +672,11 @@ class DQN(nn.Module):
             dh_hi = torch.empty(R, 2 * hid, dtype=torch.bfloat16, device=dev)
             dh_hiT = None                            # the wgrad reads dh_hi itself (MN-major operand)
             call("riqn_dueling_bwd_bf16", R, B, hid, A, ptr(keep["h"]), ptr(tc.get("h_hi")), ptr(self._w_eff_z), ptr(dtheta), ptr(gscale),
-                 ptr(actions), ptr(dh_hi), None, ptr(dbs), ptr(dz), ptr(dzT))
+                 float(gscale_mul), ptr(actions), ptr(dh_hi), None, ptr(dbs), ptr(dz), ptr(dzT))
         else:
             dh = torch.empty(R, 2 * hid, device=dev)
             call("riqn_dueling_bwd", R, B, hid, A, ptr(keep["h"]), ptr(self._w_eff_z), ptr(dtheta), ptr(gscale),
-                 ptr(actions), ptr(dh), ptr(dz), ptr(dzT))
+                 float(gscale_mul), ptr(actions), ptr(dh), ptr(dz), ptr(dzT))
         dwz = torch.empty(32, 2 * hid, device=dev)
         dbz = torch.empty(32, device=dev)
         zargs = (ptr(dwz), ptr(dbz), ptr(zv.weight_epsilon), ptr(zv.bias_epsilon), ptr(za.weight_epsilon),

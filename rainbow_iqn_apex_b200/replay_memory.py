@@ -207,7 +207,7 @@ class ReplayMemory:
             pri, data_idx, tree_idx = tr.find_multiple_values(self.history, self.n, batch_size, samples)
             w64 = torch.empty(batch_size, dtype=torch.float64, device=self.device)
             w32 = torch.empty(batch_size, dtype=torch.float32, device=self.device)
-            self.last_nonpositive = torch.zeros(1, dtype=torch.int32, device=self.device)
+            self.last_nonpositive = torch.empty(1, dtype=torch.int32, device=self.device)    # written (not accumulated) by the kernel
             call("riqn_sumtree_is_weights", batch_size, ptr(tr.tree), ptr(pri), float(tr.get_current_capacity()),
                  float(self.priority_weight), ptr(w64), ptr(w32), ptr(self.last_nonpositive),
                  tr._dyn.ptr() if tr._dyn is not None else None)
