@@ -227,15 +227,6 @@ int riqn_quantile_embed_bwd_tc(int batch, int num_quantiles, int embed_dim, int 
  * weights of fcnoisy_z_v (row 0) and fcnoisy_z_a; bz (1+A).  q (rows, A) = v + a - mean_a a. */
 int riqn_dueling_fwd(long rows, int batch, int hidden, int action_space, const float* h, const float* wz,
                      const float* bz, float* q, void* stream);
-/* Hidden layers + z-layers + dueling in two launches (the head forward of the single-pass arithmetic modes): the tcgen05
- * product h = relu(x W^T + bias_h) (x (rows, in_features), w (2*hidden, in_features): 16-bit images, fmt 0 = bf16, 3 = fp16)
- * keeps h on chip -- its epilogue accumulates every row's z-layer dot products against wz and writes 4 x 2 partial sums per
- * row into zpart (8 * rows * 20 floats, workspace) -- and a second kernel adds them in a fixed order with bz and forms
- * q (rows, A) = v + a - mean_a a (rows quantile-major, like riqn_dueling_fwd).  h_bf16 (or NULL) receives the bf16 image of h
- * (backward operand / ReLU mask), h32 (or NULL) the fp32 matrix.  hidden % 256 == 0, action_space <= 18. */
-int riqn_head_fwd_fused(long rows, int batch, int in_features, int hidden, int action_space, const void* x, const void* w,
-                        const float* bias_h, const float* wz, const float* bz, float* zpart, float* q, void* h_bf16,
-                        float* h32, int fmt, void* stream);
 /* Backward for the gathered action: dq[r, actions[b]] = dtheta[r] * gscale[b].  Writes dh (rows, 2*hidden),
  * already masked by h > 0, and dz (rows, 32) = [dv, da_0.., 0..] for riqn_z_wgrad; dz_bf16 (may be NULL) is its bf16
  * image (rows, 32) for riqn_z_wgrad_tc. */

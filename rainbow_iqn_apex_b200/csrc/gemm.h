@@ -32,7 +32,7 @@ int gemm_f32(int M, int N, int K, const float* A, long sAm, long sAk, const floa
 
 // ---- tcgen05 / TMA path (gemm_tc.cu) ---------------------------------------------------------------------------
 enum TcEpi { TC_STORE = 0, TC_BIAS_RELU = 1, TC_ATOMIC = 2, TC_NOISY_WGRAD = 3, TC_BIAS_RELU_NCHW = 4, TC_EMBED = 5,
-             TC_COL2IM = 6, TC_CONV = 7, TC_HEAD = 8 };
+             TC_COL2IM = 6, TC_CONV = 7 };
 
 struct TcExtra {
   int ohw = 1;
@@ -58,13 +58,6 @@ struct TcExtra {
   // 16-bit operand formats: 0 = both operand images bf16, 3 = both fp16 (single-pass products only; mixing the two is an
   // illegal instruction), bit 2 = TC_EMBED writes o_hi as fp16(x) and o_lo (optional) as bf16(x) instead of hi / residual
   int fmt = 0;
-  // TC_HEAD (IQN head forward fused with the z-layers): h = relu(acc + bias) is NOT written as fp32 (o_hi, optional, is its
-  // bf16 image for the backward); every epilogue warp accumulates the z-layer dot products of its 32 rows x 128 columns --
-  // value stream (columns < hidden): 1 output, advantage stream: z_A outputs -- against zw ((1 + z_A, hidden) fp32) and
-  // writes them to zpart[(slot * M + row) * 20 + k], slot = n_tile * 2 + column half (k = 0: value, 1 + a: advantage a).
-  const float* zw = nullptr;
-  float* zpart = nullptr;
-  int z_A = 0, z_hid = 0;
 };
 
 // C (+)= A B^T, A (M,K) / B (N,K) row-major bf16 (K % 8 == 0); *_lo non-null selects the split-bf16 x3 product.

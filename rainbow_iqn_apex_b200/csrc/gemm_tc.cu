@@ -45,8 +45,7 @@ struct TcCfg {
   static constexpr uint32_t kABytes = TBM * TBK * 2, kBBytes = BN * TBK * 2;
   static constexpr uint32_t kStageBytes = kAOps * kABytes + kBOps * kBBytes;         // 48 / 80 / 96 KB at BN = 256
   static constexpr uint32_t kEpiStage = 32 * 32 * 4;  // per epilogue warp: 32 rows x 32 words for the store transpose
-  // per-warp feat / bias broadcast patches (TC_EMBED) or the double-buffered z-weight slice of a tile (TC_HEAD: 18 x 256 fp32)
-  static constexpr uint32_t kFbBytes = EPI == TC_EMBED ? epi_warps(EPI) * 256 : (EPI == TC_HEAD ? 2 * 18 * 256 * 4 : 0);
+  static constexpr uint32_t kFbBytes = EPI == TC_EMBED ? epi_warps(EPI) * 256 : 0;   // per-warp feat / bias broadcast patches
   static constexpr uint32_t kRingBytes = 224 * 1024 - epi_warps(EPI) * kEpiStage - kFbBytes;   // 192 KB with two warp sets
   static constexpr int kStages = kRingBytes / kStageBytes > 6 ? 6 : kRingBytes / kStageBytes;
   static constexpr uint32_t kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;                   // two accumulator buffers (power of 2)
@@ -286,9 +285,6 @@ struct alignas(64) TcArgs {
   int mn_major, wg_t, wg_G, wg_kc;                             // MN-major operands / strip weight gradient (gemm.h)
   bf16 *nx_hi, *nx_lo;
   int fmt;               // bit 0: A image is fp16, bit 1: B image is fp16 (else bf16), bit 2: o_hi is written as fp16
-  const float* zw;       // TC_HEAD: z-layer weights (1 + z_A, z_hid)
-  float* zpart;          // TC_HEAD: partial z sums, [(slot * M + row) * 20 + k]
-  int z_A, z_hid;
 };
 
 template <int NSPLIT, int EPI, int BN>
@@ -461,27 +457,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
       const bool e_one_sample = (p.batch & 31) == 0;          // sample-major rows: a warp's 32 rows share one feature row
       const float* embed_feat_row = nullptr;
       if (EPI == TC_EMBED) embed_feat_row = p.feat + (long)((e_mbase < p.M ? e_mbase : 0) / p.batch) * p.N;
-      float zv = 0.f, za[18];
-      if (EPI == TC_HEAD) {
-        // this tile's slice of the z-layer weights -> shared memory (double buffered: one named barrier per tile suffices,
-        // a warp can only reach tile i+2 after every warp has left tile i)
-#pragma unroll
-        for (int a = 0; a < 18; ++a) za[a] = 0.f;
-        float* zsb = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + epi_warps(EPI) * Cfg::kEpiStage + 256) +
-                     (local & 1) * (18 * 256);
-        const int te = (warp - 2) * 32 + lane;               // 0..255 over the epilogue warps
-        const int tiles_v = p.z_hid / TBN;                    // n-tiles of the value stream
-        if (nt < tiles_v) {
-          zsb[te] = p.zw[nt * TBN + te];
-        } else {
-          const float4* src = reinterpret_cast<const float4*>(p.zw + (long)p.z_hid + (nt - tiles_v) * TBN);
-          for (int i = te; i < p.z_A * (TBN / 4); i += 256) {
-            const int a = i / (TBN / 4), q4 = i - a * (TBN / 4);
-            reinterpret_cast<float4*>(zsb)[a * (TBN / 4) + q4] = src[(long)a * (p.z_hid / 4) + q4];
-          }
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-      }
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * TBN;
@@ -536,7 +511,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (n0 + j < p.N) cb[(long)j * p.ohw] = fmaxf(__uint_as_float(v[j]) + p.bias[n0 + j], 0.f);
-          } else if (EPI == TC_EMBED || EPI == TC_COL2IM || EPI == TC_CONV || EPI == TC_HEAD) {
+          } else if (EPI == TC_EMBED || EPI == TC_COL2IM || EPI == TC_CONV) {
             // handled below with the whole warp
           } else if (!(p.vec_acc && n0 + 32 <= p.N)) {
             float* crow = p.C + (long)m * p.ldc + n0;
@@ -604,61 +579,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
 #pragma unroll
             for (int i = 0; i < 8; ++i)
               if (orow[i] >= 0 && dstb != nullptr) *reinterpret_cast<uint4*>(dstb + orow[i] + (piece & 3) * 8) = pc[i];
-          }
-        }
-        if (EPI == TC_HEAD) {
-          // h = relu(acc + bias); z-layer partial sums of this lane's row against the shared-memory weight slice
-          const uint32_t zs = epi_stage + epi_warps(EPI) * Cfg::kEpiStage + 256 + (local & 1) * (18 * 256 * 4) + c * 4;
-          const bool value_tile = nt < p.z_hid / TBN;
-          float hc[32];
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
-            hc[j] = fmaxf(__uint_as_float(v[j]) + bb.x, 0.f);
-            hc[j + 1] = fmaxf(__uint_as_float(v[j + 1]) + bb.y, 0.f);
-            hc[j + 2] = fmaxf(__uint_as_float(v[j + 2]) + bb.z, 0.f);
-            hc[j + 3] = fmaxf(__uint_as_float(v[j + 3]) + bb.w, 0.f);
-          }
-          if (value_tile) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const uint4 w4 = lds128(zs + 16 * j);
-              zv = fmaf(hc[4 * j], __uint_as_float(w4.x), zv);
-              zv = fmaf(hc[4 * j + 1], __uint_as_float(w4.y), zv);
-              zv = fmaf(hc[4 * j + 2], __uint_as_float(w4.z), zv);
-              zv = fmaf(hc[4 * j + 3], __uint_as_float(w4.w), zv);
-            }
-          } else {
-#pragma unroll
-            for (int a = 0; a < 18; ++a) {
-              if (a < p.z_A) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  const uint4 w4 = lds128(zs + a * (TBN * 4) + 16 * j);
-                  za[a] = fmaf(hc[4 * j], __uint_as_float(w4.x), za[a]);
-                  za[a] = fmaf(hc[4 * j + 1], __uint_as_float(w4.y), za[a]);
-                  za[a] = fmaf(hc[4 * j + 2], __uint_as_float(w4.z), za[a]);
-                  za[a] = fmaf(hc[4 * j + 3], __uint_as_float(w4.w), za[a]);
-                }
-              }
-            }
-          }
-          const uint32_t st = epi_stage + (warp - 2) * (32 * kStRow * 4);
-          const int m_base = mt * TBM + quarter * 32;
-          const int rows_valid = min(32, p.M - m_base);
-          if (rows_valid > 0 && (p.o_hi != nullptr || p.C != nullptr)) {
-            if (p.C != nullptr) {
-              uint32_t hu[32];
-#pragma unroll
-              for (int j = 0; j < 32; ++j) hu[j] = __float_as_uint(hc[j]);
-              warp_store_rows_f32(st, hu, lane, p.C + (long)m_base * p.ldc + n0, p.ldc, rows_valid);
-            }
-            if (p.o_hi != nullptr) {                            // bf16 image of h: the backward's operand / ReLU mask
-              uint32_t hw2[32];
-#pragma unroll
-              for (int j = 0; j < 16; ++j) { hw2[j] = pack16x2(hc[2 * j], hc[2 * j + 1], false); hw2[16 + j] = 0u; }
-              warp_store_rows_bf16(st, hw2, lane, p.o_hi + (long)m_base * p.N + n0, nullptr, p.N, rows_valid);
-            }
           }
         }
         if (EPI == TC_COL2IM && n0 < p.N) {
@@ -784,16 +704,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
               }
             }
           }
-        }
-      }
-      if (EPI == TC_HEAD && m < p.M) {
-        float* zp = p.zpart + ((long)(nt * 2 + chalf) * p.M + m) * 20;
-        if (nt < p.z_hid / TBN) {
-          zp[0] = zv;
-        } else {
-#pragma unroll
-          for (int a = 0; a < 18; ++a)
-            if (a < p.z_A) zp[1 + a] = za[a];
         }
       }
       tc_fence_before();
@@ -957,10 +867,6 @@ int gemm_bf16_tc(int M, int N, int K, const bf16* A_hi, const bf16* A_lo, const 
   p.o_hi = ex ? ex->o_hi : nullptr; p.o_lo = ex ? ex->o_lo : nullptr;
   p.o_hiT = ex ? ex->o_hiT : nullptr; p.o_loT = ex ? ex->o_loT : nullptr;
   p.fmt = ex ? ex->fmt : 0;
-  p.zw = ex ? ex->zw : nullptr; p.zpart = ex ? ex->zpart : nullptr; p.z_A = ex ? ex->z_A : 0; p.z_hid = ex ? ex->z_hid : 0;
-  if (epi == TC_HEAD && (split3 || split2 || mn || !p.zw || !p.zpart || p.z_A < 1 || p.z_A > 18 || p.z_hid % 256 || N != 2 * p.z_hid ||
-                         (N % 256) || !bias))
-    return (int)cudaErrorInvalidValue;
   if ((p.fmt & 3) && (split3 || split2)) return (int)cudaErrorInvalidValue;      // fp16 images are single-pass operands
   if ((p.fmt & 3) == 1 || (p.fmt & 3) == 2) return (int)cudaErrorInvalidValue;   // mixed fp16 x bf16: illegal instruction
   if ((p.fmt & 4) && epi != TC_EMBED) return (int)cudaErrorInvalidValue;
@@ -997,7 +903,6 @@ int gemm_bf16_tc(int M, int N, int K, const bf16* A_hi, const bf16* A_lo, const 
       case TC_STORE: RIQN_TC_NARROW(1, TC_STORE); RIQN_TC_GO(1, TC_STORE);
       case TC_COL2IM: RIQN_TC_GO(1, TC_COL2IM);
       case TC_BIAS_RELU: RIQN_TC_GO(1, TC_BIAS_RELU);
-      case TC_HEAD: RIQN_TC_GO(1, TC_HEAD);
       case TC_ATOMIC: RIQN_TC_NARROW(1, TC_ATOMIC); RIQN_TC_GO(1, TC_ATOMIC);
       case TC_NOISY_WGRAD: RIQN_TC_GO(1, TC_NOISY_WGRAD);
       case TC_BIAS_RELU_NCHW: RIQN_TC_NARROW(1, TC_BIAS_RELU_NCHW); RIQN_TC_GO(1, TC_BIAS_RELU_NCHW);

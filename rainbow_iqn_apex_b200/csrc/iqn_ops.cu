@@ -511,27 +511,6 @@ __global__ void __launch_bounds__(256, 2) z_dueling_fwd4_kernel(long R, int B, i
   }
 }
 
-// Second stage of the fused head forward (riqn_head_fwd_fused): the tcgen05 GEMM's epilogue left, per row, 8 partial z sums
-// (4 n-tiles x 2 column halves; value stream in slots 0..3, advantage stream in slots 4..7).  One warp per row adds them
-// in a FIXED order (run-to-run deterministic), adds the z biases and forms q = v + a - mean_a(a), quantile-major output.
-__global__ void z_dueling_finish_kernel(long R, int B, int A, int slots_v, int slots, const float* __restrict__ zpart,
-                                        const float* __restrict__ bz, float* __restrict__ q) {
-  const long r = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (r >= R) return;
-  float v = bz[0];
-  for (int s = 0; s < slots_v; ++s) v += zpart[((long)s * R + r) * 20];
-  float adv = 0.f;
-  if (lane < A) {
-    adv = bz[1 + lane];
-    for (int s = slots_v; s < slots; ++s) adv += zpart[((long)s * R + r) * 20 + 1 + lane];
-  }
-  const float asum = warp_sum(lane < A ? adv : 0.f);
-  const int Nq = (int)(R / B);
-  const long b = r / Nq, qi = r - b * Nq;                   // sample-major row -> quantile-major output row
-  if (lane < A) q[(qi * B + b) * A + lane] = v + adv - asum / (float)A;
-}
-
 // ------------------------------------------------------------------------------------------------
 // Double-DQN action: a*[b] = argmax_a mean_k q[k*B+b, a]               (compute_loss_iqn.py:238-245)
 // ------------------------------------------------------------------------------------------------
@@ -1122,29 +1101,6 @@ RIQN_API int riqn_dueling_fwd(long rows, int batch, int hidden, int action_space
   } else {
     z_dueling_fwd_kernel<512><<<148 * 4, 256, smem, (cudaStream_t)stream>>>(rows, batch, action_space, h, wz, bz, q);
   }
-  return (int)cudaGetLastError();
-}
-
-// Hidden NoisyLinear product + z-layers + dueling in two launches: h = relu(x W^T + b) never reaches HBM as fp32 (h_bf16,
-// optional, is the bf16 image the backward needs); q (rows, A) quantile-major like riqn_dueling_fwd.
-RIQN_API int riqn_head_fwd_fused(long rows, int batch, int in_features, int hidden, int action_space, const void* x,
-                                 const void* w, const float* bias_h, const float* wz, const float* bz, float* zpart, float* q,
-                                 void* h_bf16, float* h32, int fmt, void* stream) {
-  riqn::note_launches(2);
-  if (hidden % 256 || action_space < 1 || action_space > 18 || rows % batch || (fmt != 0 && fmt != 3)) return (int)cudaErrorInvalidValue;
-  cudaStream_t s = (cudaStream_t)stream;
-  TcExtra ex;
-  ex.fmt = fmt;
-  ex.o_hi = (__nv_bfloat16*)h_bf16;
-  ex.zw = wz;
-  ex.zpart = zpart;
-  ex.z_A = action_space;
-  ex.z_hid = hidden;
-  int rc = gemm_bf16_tc((int)rows, 2 * hidden, in_features, (const __nv_bfloat16*)x, nullptr, (const __nv_bfloat16*)w, nullptr, h32,
-                        2 * hidden, TC_HEAD, bias_h, nullptr, nullptr, 1, s, &ex);
-  if (rc) return rc;
-  const int slots_v = 2 * (hidden / 256), slots = 2 * slots_v;
-  z_dueling_finish_kernel<<<riqn_cdiv(rows * 32, 256), 256, 0, s>>>(rows, batch, action_space, slots_v, slots, zpart, bz, q);
   return (int)cudaGetLastError();
 }
 

@@ -41,7 +41,6 @@ _ALIGN = 64  # floats; arena groups start on 256-byte boundaries
 PRECISION = {"fwd": os.environ.get("RIQN_FWD_PRECISION", "fp16"), "bwd": os.environ.get("RIQN_BWD_PRECISION", "bf16")}
 WGRAD_SPLIT_K = int(os.environ.get("RIQN_WGRAD_SPLIT_K", "4"))
 _NO_STRIP = os.environ.get("RIQN_NO_STRIP_CONV", "0") == "1"      # fall back to the explicit-im2col forward
-_NO_FUSED_HEAD = os.environ.get("RIQN_NO_FUSED_HEAD", "0") == "1"  # A/B switch: separate head GEMM + dueling kernel
 
 
 def set_precision(fwd=None, bwd=None):
@@ -579,7 +578,7 @@ class DQN(nn.Module):
         E, hid, A = self.quantile_embedding_dim, self.hidden, self.action_space
         fwd, bwd = PRECISION["fwd"], PRECISION["bwd"]
         bf = lambda *sh: torch.empty(*sh, dtype=torch.bfloat16, device=dev)
-        h = None
+        h = torch.empty(R, 2 * hid, device=dev)
         bwd_tc = keep is not None and bwd != "fp32" and R % 8 == 0      # head wgrad/dgrad on the tensor cores
         emb_tc = keep is not None and bwd == "bf16" and fwd != "fp32" and R % 8 == 0   # embedding backward on tensor cores
         cosv = xt = tc = None
@@ -591,7 +590,6 @@ class DQN(nn.Module):
             if bwd_tc:
                 tc = dict(x_hi=None, x_lo=None, x_hiT=bf(FEAT, R), x_loT=bf(FEAT, R) if bwd == "bf16x3" else None)
                 call("riqn_split_bf16", R, FEAT, ptr(xt), None, None, ptr(tc["x_hiT"]), ptr(tc["x_loT"]), 0)
-            h = torch.empty(R, 2 * hid, device=dev)
             call("riqn_noisy_linear_fwd", R, FEAT, 2 * hid, ptr(xt), ptr(self._w_eff_h), ptr(self._b_eff_h), ptr(h))
         else:
             x3 = _small_x3()                                     # embedding product
@@ -619,23 +617,11 @@ class DQN(nn.Module):
                 call("riqn_quantile_embed_fwd", B, num_quantiles, E, FEAT, ptr(tau), ptr(feat), ptr(self.iqn_fc.weight),
                      ptr(self.iqn_fc.bias), ptr(cosv), ptr(xt))
             tc["h_hi"] = bf(R, 2 * hid) if (bwd_tc and R % 2 == 0) else None   # bf16 image of h for the z-layer weight gradient
-            fused = (not head_x3 and A <= 18 and hid % 256 == 0 and not _NO_FUSED_HEAD and
-                     (keep is None or (mn and R % 8 == 0 and tc["h_hi"] is not None)))   # the bf16 backward never reads fp32 h
-            if fused:
-                # single-pass modes: h stays on chip -- the GEMM epilogue feeds the z-layers, q comes out of a 2-launch pair
-                # and no fp32 h is written (the backward reads the bf16 image)
-                q = torch.empty(R, A, device=dev)
-                zpart = torch.empty(4 * (hid // 256) * R * 20, device=dev)
-                call("riqn_head_fwd_fused", R, B, FEAT, hid, A, ptr(tc["x_hi"]), ptr(self._w_hi), ptr(self._b_eff_h),
-                     ptr(self._w_eff_z), ptr(self._b_eff_z), ptr(zpart), ptr(q), ptr(tc["h_hi"]), None, 3 if f16 else 0)
-            else:
-                h = torch.empty(R, 2 * hid, device=dev)
-                call("riqn_gemm_bf16_tc", R, 2 * hid, FEAT, ptr(tc["x_hi"]), ptr(tc["x_lo"]) if head_x3 else None, ptr(self._w_hi),
-                     ptr(self._w_lo) if head_x3 else None, ptr(h), 2 * hid, 1, ptr(self._b_eff_h), None, None, 1, None, ptr(tc["h_hi"]),
-                     3 if f16 else 0)
-        if h is not None:
-            q = torch.empty(R, A, device=dev)
-            call("riqn_dueling_fwd", R, B, hid, A, ptr(h), ptr(self._w_eff_z), ptr(self._b_eff_z), ptr(q))
+            call("riqn_gemm_bf16_tc", R, 2 * hid, FEAT, ptr(tc["x_hi"]), ptr(tc["x_lo"]) if head_x3 else None, ptr(self._w_hi),
+                 ptr(self._w_lo) if head_x3 else None, ptr(h), 2 * hid, 1, ptr(self._b_eff_h), None, None, 1, None, ptr(tc["h_hi"]),
+                 3 if f16 else 0)
+        q = torch.empty(R, A, device=dev)
+        call("riqn_dueling_fwd", R, B, hid, A, ptr(h), ptr(self._w_eff_z), ptr(self._b_eff_z), ptr(q))
         if keep is not None:
             keep.update(feat=feat, cos=cosv, xt=xt, h=h, q=q, tau=tau, num_quantiles=num_quantiles, tc=tc,
                         noise_version=getattr(self, "_noise_version", 0),

@@ -115,12 +115,6 @@ def test_learn_matches_reference_golden(cuda_dev, golden_dir, name):
             p_or[k] = p.detach().cpu().clone()
 
 
-def _h_of(gk):
-    """Hidden activations of a recorded pass: fp32 when the pass wrote them, else the bf16 image (fused head forward) --
-    only their SIGN is used (ReLU-kink flip counting)."""
-    return gk["h"] if gk["h"] is not None else gk["tc"]["h_hi"].float()
-
-
 def _qmajor(t, batch):
     """head-internal rows are sample-major (b*Nq + q); the oracle's are quantile-major (q*B + b)."""
     nq = t.shape[0] // batch
@@ -183,7 +177,7 @@ def test_loss_api_and_autograd_vs_oracle(cuda_dev, precision, batch, cfg, mode):
     gk = dbg["keep"]
     flips = sum(int(((a.cpu() > 0) != (b_ > 0)).sum()) for a, b_ in
                 ((gk["out"][0], keep["o1"]), (gk["out"][1], keep["o2"]), (gk["out"][2], keep["o3"]),
-                 (_qmajor(_h_of(gk), batch)[:, :512], keep["h_v"]), (_qmajor(_h_of(gk), batch)[:, 512:], keep["h_a"])))
+                 (_qmajor(gk["h"], batch)[:, :512], keep["h_v"]), (_qmajor(gk["h"], batch)[:, 512:], keep["h_a"])))
     if not ties.any():
         for k, g_ref in o_grads.items():
             gg = grads_gpu[k]

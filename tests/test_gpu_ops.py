@@ -87,12 +87,9 @@ def test_forward_injected(cuda_dev, nets):
         x_gpu = qmajor(tc["x_hi"].float() + tc["x_lo"].float()).cpu().numpy()
         assert rel_err(x_gpu, keep["x"].numpy()) < 3e-5
         htol = 1e-4                                                              # split-bf16x3 tensor-core products
-    if k2["h"] is not None:
-        h_gpu, hh = qmajor(k2["h"]), htol
-    else:            # fused head forward: h never leaves the chip as fp32; the bf16 image (backward operand) is what exists
-        h_gpu, hh = qmajor(tc["h_hi"].float()), 4e-3
-    assert rel_err(h_gpu[:, :512].cpu().numpy(), keep["h_v"].numpy()) < hh
-    assert rel_err(h_gpu[:, 512:].cpu().numpy(), keep["h_a"].numpy()) < hh
+    h_gpu = qmajor(k2["h"])
+    assert rel_err(h_gpu[:, :512].cpu().numpy(), keep["h_v"].numpy()) < htol
+    assert rel_err(h_gpu[:, 512:].cpu().numpy(), keep["h_a"].numpy()) < htol
     assert rel_err(q.cpu().numpy(), ref.numpy()) < htol
     # stored epsilons == outer product of the injected factors (model.py:39-43), bit for bit
     assert torch.equal(d.fcnoisy_h_a.weight_epsilon.cpu(), torch.outer(noise["fcnoisy_h_a"][1], noise["fcnoisy_h_a"][0]))

@@ -21,7 +21,7 @@ import torch
 
 from helpers import load_params, make_args, rel_err
 from oracle import actor as oactor, cases, losses, network as net
-from test_gpu_learn import FakeMem, _dev_batch, _h_of, _learner, _qmajor, _tie_mask, precision  # noqa: F401
+from test_gpu_learn import FakeMem, _dev_batch, _learner, _qmajor, _tie_mask, precision  # noqa: F401
 from test_oracle_golden import actor_case
 
 pytestmark = pytest.mark.gpu
@@ -43,7 +43,7 @@ def _rel_loss(lg, lo, ok):
 
 def _flips(gk, keep, batch):
     pairs = ((gk["out"][0], keep["o1"]), (gk["out"][1], keep["o2"]), (gk["out"][2], keep["o3"]),
-             (_qmajor(_h_of(gk), batch)[:, :512], keep["h_v"]), (_qmajor(_h_of(gk), batch)[:, 512:], keep["h_a"]))
+             (_qmajor(gk["h"], batch)[:, :512], keep["h_v"]), (_qmajor(gk["h"], batch)[:, 512:], keep["h_a"]))
     return [int(((a.cpu() > 0) != (b_ > 0)).sum()) for a, b_ in pairs]
 
 
