@@ -472,19 +472,14 @@ def run_apex(args):
     parallel.publish_parameters(agent, src=0)                  # everyone starts from the learner's weights
     flushed = [0]
     graphed = [False]
-    side = torch.cuda.Stream() if topo.is_learner else None
-    ticket = [topo.sample_begin(mem, dev)]                 # batch 0; from then on batch t+1 is sampled / gathered during step t
-
     def step():
         nonlocal states
-        if topo.is_learner:
-            torch.cuda.current_stream().wait_stream(side)  # the prefetched gather has landed
-        batch = topo.sample_end(ticket[0], beta=0.4)
+        # all ranks: ONE gather of the shards' (pre-sampled, packed) parts; the GPUs are otherwise idle at this point, so the
+        # collective does not compete with the persistent GEMMs for SMs (a side-stream prefetch under the learner's step
+        # measured 7.5 ms/step on 8 GPUs: NCCL's CTAs wait for the 148-CTA kernels to end)
+        batch = topo.sample(mem, beta=0.4, device=dev)
         if topo.is_learner:
             _, _, st, ac, rt, nx, nt, w = batch
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):                  # next batch: its gather overlaps this step's compute (one step of
-                ticket[0] = topo.sample_begin(None, dev)   # priority staleness, the reference's sampler queue has five)
             if not args.no_graph and not graphed[0]:       # capture learn_on_batch once the first gathered batch fixes the shapes
                 agent.enable_learn_graph((st, ac, rt, nx, nt, w))
                 graphed[0] = True
@@ -493,7 +488,6 @@ def run_apex(args):
             else:
                 loss = agent.learn_on_batch(st, ac, rt, nx, nt, w).detach()
         else:
-            ticket[0] = topo.sample_begin(mem, dev)
             loss = torch.empty(B, dtype=torch.float32, device=dev)
             for _ in range(args.acts_per_step):                # acting overlaps the learner's step
                 act = pool.act(states)
@@ -505,6 +499,8 @@ def run_apex(args):
                 states = torch.cat([states[:, 1:], nxt], 1)
         topo.route(loss, mem, None if topo.is_learner else batch)
         topo.maybe_publish(agent)
+        if not topo.is_learner:
+            topo.presample(mem)                                # the shard's part of the next batch, drawn after this step's update
 
     def barrier():
         torch.distributed.barrier()

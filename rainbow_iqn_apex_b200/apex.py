@@ -247,11 +247,18 @@ class ApexTopology:
         self.shard = self.rank - 1
         self.steps = 0
 
+    def presample(self, mem):
+        """Actor ranks: draw this shard's part of the NEXT learner batch now (tree descent + window gather + packing), so that
+        the gather at the start of the next step finds it ready.  Called right after route(): the draw already sees the
+        priorities of the step that just finished."""
+        mine = sample_shard(mem, self.counts[self.shard], self.n_max)
+        stat = torch.stack([mem.transitions.tree[0], torch.tensor(float(mem.transitions.get_current_capacity()),
+                                                                  dtype=torch.float64, device=mem.device)])
+        self._ready = (mine, pack(mine, stat, self.n_max))
+
     def sample_begin(self, mem=None, device=None, history=4, n_step=3):
-        """First half of a learner sample: every shard draws its transitions and ONE gather of the packed records is
-        enqueued (on the current stream).  Returns a ticket for sample_end().  The learner may call this for step t+1
-        before it learns on step t -- the reference's sampler process runs ahead of its learner the same way
-        (launch_learner.py:24-50, a queue of 5 batches) -- as long as every rank issues its collectives in the same order."""
+        """First half of a learner sample: ONE gather of the packed per-shard records (on the current stream; the shards'
+        parts come from presample(), or are drawn here).  Returns a ticket for sample_end()."""
         nbytes = packed_bytes(self.n_max, history, n_step)
         if self.is_learner:
             # two persistent receive sets (ping-pong): the gather of batch t+1 may run on a side stream while batch t is
@@ -264,10 +271,9 @@ class ApexTopology:
             out = self._recv[self._recv_i]
             mine, rec = None, out[0]
         else:
-            mine = sample_shard(mem, self.counts[self.shard], self.n_max)
-            stat = torch.stack([mem.transitions.tree[0], torch.tensor(float(mem.transitions.get_current_capacity()),
-                                                                      dtype=torch.float64, device=mem.device)])
-            rec, out = pack(mine, stat, self.n_max), None
+            if getattr(self, "_ready", None) is None:
+                self.presample(mem)
+            (mine, rec), self._ready, out = self._ready, None, None
         dist.gather(rec, out, dst=0, group=self.group)
         return dict(mine=mine, out=out, history=history, n_step=n_step)
 
