@@ -94,7 +94,11 @@ int riqn_conv_fwd_tc(const riqn_conv_geom* g, const void* in, int in_is_u8, cons
 int riqn_s2d_u8(const riqn_conv_geom* g, const unsigned char* in, void* a_px, void* stream);
 int riqn_conv_fwd_strip(const riqn_conv_geom* g, const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo,
                         const float* bias, float* out, void* next_hi, void* next_lo, int next_stride, int next_grid,
-                        void* stream);
+                        const void* w2_hi, const void* w2_lo, const float* bias2, int share_a, void* stream);
+/* w2_hi != NULL: TWO networks in one launch (the online and the target trunk over the same next_states): g->B counts both
+ * halves of a stacked batch, samples [0, B/2) use w_hi / w_lo / bias, samples [B/2, B) use w2_hi / w2_lo / bias2; outputs and
+ * next-layer images are the stacked (B, ...) tensors.  share_a != 0: the A image holds B/2 samples read by both halves (first
+ * layer: the pixel block matrix).  Needs (B/2)*G*G % 128 == 0. */
 int riqn_im2col_bf16_t(const riqn_conv_geom* g, const void* in, int in_is_u8, void* colT_hi, void* stream);
 /* Backward of a strip convolution on the tensor cores, again without im2col matrices: a_hi is the block matrix the
  * forward read (riqn_s2d_u8 / the previous layer's next_hi); w_hi (Cout, K) bf16 weight in the ORIGINAL k order (data

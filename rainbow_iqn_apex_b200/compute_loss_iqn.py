@@ -8,6 +8,8 @@ the parameters' ``.grad`` (views of the gradient arena), exactly where the refer
 Three network passes, in the reference's order and with a fresh noise sample before each
 (:234, :255, :289): online(next_states, K) -> a*; target(next_states, N') -> targets; online(states, N).
 """
+import os
+
 import torch
 
 from ._lib import call, ptr
@@ -41,11 +43,14 @@ def loss_core(agent, states, actions, returns, next_states, nonterminals, keep_g
 
     on.reset_noise(noises[0])                                                       # :234
     cache = {}   # conv1's pixel im2col of next_states is shared by the online and the target pass
-    q_sel, _ = on.forward(next_states, K, tau=taus[0], fresh_weights=True, col_cache=cache)   # :235-237
+    # both no-grad passes read next_states: their conv trunks (noise-free weights) run as ONE stacked batch, three launches
+    pair = on.trunk_pair(tg, next_states) if not (on.rainbow_only or os.environ.get("RIQN_NO_TRUNK_PAIR") == "1") else None
+    f_on, f_tg = pair if pair is not None else (None, None)
+    q_sel, _ = on.forward(next_states, K, tau=taus[0], fresh_weights=True, col_cache=cache, feat=f_on)   # :235-237
     a_star = torch.empty(B, dtype=torch.int64, device=dev)
     call("riqn_argmax_mean", B, K, A, ptr(q_sel), ptr(a_star))                      # :238-245
     tg.reset_noise(noises[1])                                                       # :255
-    q_tgt, _ = tg.forward(next_states, Np, tau=taus[1], fresh_weights=True, col_cache=cache)  # :256-258
+    q_tgt, _ = tg.forward(next_states, Np, tau=taus[1], fresh_weights=True, col_cache=cache, feat=f_tg)  # :256-258
     on.reset_noise(noises[2])                                                       # :289
     keep = {} if keep_graph else None
     q_on, tau = on.forward(states, N, tau=taus[2], keep=keep, fresh_weights=True)   # :290

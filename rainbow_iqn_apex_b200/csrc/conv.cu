@@ -755,12 +755,20 @@ RIQN_API int riqn_s2d_u8(const riqn_conv_geom* g, const unsigned char* in, void*
 
 RIQN_API int riqn_conv_fwd_strip(const riqn_conv_geom* g, const void* a_hi, const void* a_lo, const void* w_hi,
                                  const void* w_lo, const float* bias, float* out, void* next_hi, void* next_lo,
-                                 int next_stride, int next_grid, void* stream) {
+                                 int next_stride, int next_grid, const void* w2_hi, const void* w2_lo, const float* bias2,
+                                 int share_a, void* stream) {
   riqn::note_launches(1);
   int t, G, kc;
   if (strip_params(g, &t, &G, &kc) || g->Cout > 64 || (next_hi && (next_stride < 1 || next_grid < 1)))
     return (int)cudaErrorInvalidValue;
   TcExtra ex;
+  if (w2_hi != nullptr) {           // two networks over one stacked batch: g->B counts BOTH halves
+    const long rows = (long)g->B * G * G;
+    if ((g->B & 1) || (rows / 2) % 128 || bias2 == nullptr || (w_lo != nullptr) != (w2_lo != nullptr)) return (int)cudaErrorInvalidValue;
+    ex.grp_mt = (int)(rows / 2 / 128);
+    ex.b2_hi = (const bf16*)w2_hi; ex.b2_lo = (const bf16*)w2_lo; ex.bias2 = bias2;
+    if (share_a) { ex.a_wrap = 1; ex.a_rows = rows / 2; }
+  }
   ex.strip_t = t; ex.strip_G = G; ex.strip_kc = kc;
   ex.cv_oh = g->OH; ex.cv_ow = g->OW;
   ex.nx_hi = (bf16*)next_hi; ex.nx_lo = (bf16*)next_lo; ex.nx_s = next_stride; ex.nx_G = next_grid;

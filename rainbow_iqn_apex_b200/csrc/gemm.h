@@ -58,6 +58,13 @@ struct TcExtra {
   // 16-bit operand formats: 0 = both operand images bf16, 3 = both fp16 (single-pass products only; mixing the two is an
   // illegal instruction), bit 2 = TC_EMBED writes o_hi as fp16(x) and o_lo (optional) as bf16(x) instead of hi / residual
   int fmt = 0;
+  // TC_CONV with TWO weight sets over one stacked batch (the online and the target network's trunks over the same frames
+  // in one launch): m-tiles [0, grp_mt) use B_hi / B_lo / bias, m-tiles [grp_mt, 2*grp_mt) use b2_hi / b2_lo / bias2.
+  // a_wrap != 0: both groups read the SAME A rows (a_rows = rows of the A image; conv1: the pixel block matrix is shared).
+  int grp_mt = 0, a_wrap = 0;
+  long a_rows = 0;
+  const __nv_bfloat16 *b2_hi = nullptr, *b2_lo = nullptr;
+  const float* bias2 = nullptr;
 };
 
 // C (+)= A B^T, A (M,K) / B (N,K) row-major bf16 (K % 8 == 0); *_lo non-null selects the split-bf16 x3 product.

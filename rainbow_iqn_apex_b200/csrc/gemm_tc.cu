@@ -285,6 +285,8 @@ struct alignas(64) TcArgs {
   int mn_major, wg_t, wg_G, wg_kc;                             // MN-major operands / strip weight gradient (gemm.h)
   bf16 *nx_hi, *nx_lo;
   int fmt;               // bit 0: A image is fp16, bit 1: B image is fp16 (else bf16), bit 2: o_hi is written as fp16
+  int grp_mt, a_wrap;    // TC_CONV, two weight sets (gemm.h): group 1's B maps live in mapO[0] / mapO[1]
+  const float* bias2;
 };
 
 template <int NSPLIT, int EPI, int BN>
@@ -311,6 +313,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
   const int total_units = p.m_tiles * p.n_tiles * p.k_splits;
 
   if (warp == 0 && lane == 0) {
+    // descriptor fetch overlaps the barrier / TMEM prologue instead of delaying the first TMA load
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA_hi)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapB_hi)) : "memory");
+    if (NSPLIT == 3) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA_lo)) : "memory");
+    if (NSPLIT >= 2) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapB_lo)) : "memory");
     for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], epi_warps(EPI)); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -368,16 +375,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
             continue;
           }
           int a_col = kb * TBK, a_row = mt * TBM;
+          const CUtensorMap *mb_hi = &mapB_hi, *mb_lo = &mapB_lo;
+          if (EPI == TC_CONV && p.grp_mt && mt >= p.grp_mt) {   // second weight set (and, for a shared A image, its rows again)
+            mb_hi = &p.mapO[0];
+            mb_lo = &p.mapO[1];
+            if (p.a_wrap) a_row = (mt - p.grp_mt) * TBM;
+          }
           if (EPI == TC_CONV) {     // strip convolution: shifted rows of the space-to-depth image
             const int sft = kb / p.strip_kc, dy = sft / p.strip_t;
             a_col = (kb - sft * p.strip_kc) * TBK;
             a_row += dy * p.strip_G + (sft - dy * p.strip_t);
           }
           tma_load_2d(s, &mapA_hi, a_col, a_row, &full[stage]);
-          tma_load_2d(s + Cfg::kOps * Cfg::kABytes, &mapB_hi, kb * TBK, nt * TBN, &full[stage]);
+          tma_load_2d(s + Cfg::kOps * Cfg::kABytes, mb_hi, kb * TBK, nt * TBN, &full[stage]);
           if (NSPLIT == 3) tma_load_2d(s + Cfg::kABytes, &mapA_lo, a_col, a_row, &full[stage]);
           if (NSPLIT >= 2)
-            tma_load_2d(s + Cfg::kAOps * Cfg::kABytes + Cfg::kBBytes, &mapB_lo, kb * TBK, nt * TBN, &full[stage]);
+            tma_load_2d(s + Cfg::kAOps * Cfg::kABytes + Cfg::kBBytes, mb_lo, kb * TBK, nt * TBN, &full[stage]);
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -441,9 +454,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
       for (int j = 0; j < 32; ++j) conv_bias[j] = (chalf * CH0 + j < p.N && chalf * CH0 < TBN) ? p.bias[chalf * CH0 + j] : 0.f;
     }
     int local = 0;
+    bool conv_grp1 = false;
     for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++local) {
       const int t = u % (p.m_tiles * p.n_tiles);
       const int nt = t % p.n_tiles, mt = t / p.n_tiles;
+      if (EPI == TC_CONV && p.grp_mt && (mt >= p.grp_mt) != conv_grp1) {   // a CTA's tiles ascend: this happens at most once
+        conv_grp1 = mt >= p.grp_mt;
+        constexpr int CH1 = TBN >= 64 ? TBN / 2 : TBN;
+        const float* bsrc = conv_grp1 ? p.bias2 : p.bias;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) conv_bias[j] = (chalf * CH1 + j < p.N && chalf * CH1 < TBN) ? bsrc[chalf * CH1 + j] : 0.f;
+      }
       const int as = local & 1;
       const uint32_t aphase = (local >> 1) & 1;
       const int m = mt * TBM + quarter * 32 + lane;
@@ -826,7 +847,7 @@ int gemm_bf16_tc(int M, int N, int K, const bf16* A_hi, const bf16* A_lo, const 
     rc = (ex->mn_major & 2) ? make_map(&mb_hi, B_hi, K, b_cols, 64) : make_map(&mb_hi, B_hi, N, K, bn);
     if (rc) return rc;
   } else {
-    rc = make_map(&ma_hi, A_hi, M, a_k, TBM);
+    rc = make_map(&ma_hi, A_hi, (ex && ex->a_rows) ? ex->a_rows : M, a_k, TBM);
     if (rc) return rc;
     rc = make_map(&mb_hi, B_hi, N, K, bn);
     if (rc) return rc;
@@ -834,7 +855,7 @@ int gemm_bf16_tc(int M, int N, int K, const bf16* A_hi, const bf16* A_lo, const 
   ma_lo = ma_hi;
   mb_lo = mb_hi;
   if (split3) {
-    rc = make_map(&ma_lo, A_lo, M, a_k, TBM);
+    rc = make_map(&ma_lo, A_lo, (ex && ex->a_rows) ? ex->a_rows : M, a_k, TBM);
     if (rc) return rc;
   }
   if (split3 || split2) {
@@ -867,6 +888,14 @@ int gemm_bf16_tc(int M, int N, int K, const bf16* A_hi, const bf16* A_lo, const 
   p.o_hi = ex ? ex->o_hi : nullptr; p.o_lo = ex ? ex->o_lo : nullptr;
   p.o_hiT = ex ? ex->o_hiT : nullptr; p.o_loT = ex ? ex->o_loT : nullptr;
   p.fmt = ex ? ex->fmt : 0;
+  p.grp_mt = ex ? ex->grp_mt : 0; p.a_wrap = ex ? ex->a_wrap : 0; p.bias2 = ex ? ex->bias2 : nullptr;
+  if (p.grp_mt) {
+    if (epi != TC_CONV || !ex->b2_hi || !ex->bias2 || p.m_tiles != 2 * p.grp_mt || (split3 || split2) != (ex->b2_lo != nullptr))
+      return (int)cudaErrorInvalidValue;
+    if ((rc = make_map(&p.mapO[0], ex->b2_hi, N, K, bn))) return rc;
+    p.mapO[1] = p.mapO[0];
+    if (ex->b2_lo && (rc = make_map(&p.mapO[1], ex->b2_lo, N, K, bn))) return rc;
+  }
   if ((p.fmt & 3) && (split3 || split2)) return (int)cudaErrorInvalidValue;      // fp16 images are single-pass operands
   if ((p.fmt & 3) == 1 || (p.fmt & 3) == 2) return (int)cudaErrorInvalidValue;   // mixed fp16 x bf16: illegal instruction
   if ((p.fmt & 4) && epi != TC_EMBED) return (int)cudaErrorInvalidValue;

@@ -515,11 +515,11 @@ class DQN(nn.Module):
             # the fp32 NCHW activations of conv1 / conv2 are only read by the backward (ReLU masks): no-grad passes skip them
             o1, o2 = (ptr(outs[0]), ptr(outs[1])) if keep is not None else (None, None)
             call("riqn_conv_fwd_strip", g1, ptr(a1), None, ptr(ops["conv1"][0]), ptr(ops["conv1"][1]) if x3 else None,
-                 ptr(self.conv1.bias), o1, ptr(a2_hi), ptr(a2_lo), 2, 10)
+                 ptr(self.conv1.bias), o1, ptr(a2_hi), ptr(a2_lo), 2, 10, None, None, None, 0)
             call("riqn_conv_fwd_strip", g2, ptr(a2_hi), ptr(a2_lo), ptr(ops["conv2"][0]), ptr(ops["conv2"][1]) if x3 else None,
-                 ptr(self.conv2.bias), o2, ptr(a3_hi), ptr(a3_lo), 1, 9)
+                 ptr(self.conv2.bias), o2, ptr(a3_hi), ptr(a3_lo), 1, 9, None, None, None, 0)
             call("riqn_conv_fwd_strip", g3, ptr(a3_hi), ptr(a3_lo), ptr(ops["conv3"][0]), ptr(ops["conv3"][1]) if x3 else None,
-                 ptr(self.conv3.bias), ptr(outs[2]), None, None, 0, 0)
+                 ptr(self.conv3.bias), ptr(outs[2]), None, None, 0, 0, None, None, None, 0)
             if keep is not None:                     # operands of the backward products
                 strip_bwd = None
                 if bwd_tc:                           # the strip backward reads the forward's block matrices
@@ -569,6 +569,38 @@ class DQN(nn.Module):
         if keep is not None:
             keep.update(x=x, g=geoms, col=tuple(cols), colT=tuple(colTs), out=outs, bwd_tc=bwd_tc, px_scale=px_scale)
         return outs[2].view(B, FEAT)
+
+    def trunk_pair(self, other, x):
+        """conv1-3 of TWO networks (self = online, other = target) over the same uint8 frames in three launches instead of
+        six (no-grad passes: compute_loss_iqn.py:235,256 both read next_states).  The batch is stacked -- samples [0, B) with
+        self's weights, [B, 2B) with other's -- the pixel block matrix is shared by both halves.  Returns (feat_self,
+        feat_other), each (B, 3136); None when the fast path does not apply (the caller then runs the trunks one by one)."""
+        B = x.shape[0]
+        if (PRECISION["fwd"] == "fp32" or _NO_STRIP or x.dtype != torch.uint8 or x.stride()[1:] != (84 * 84, 84, 1)
+                or x.stride(0) % 16 or x.data_ptr() % 16 or self.history != 4 or other.history != 4 or B % 128):
+            return None
+        for net in (self, other):                      # operand images of the noise-free weights (rebuilt only when dirty)
+            if getattr(net, "_strip_ops", None) is None or getattr(net, "_static_ops_dirty", True):
+                net._refresh_tc_operands(h_done=True)
+        dev = x.device
+        x3 = _small_x3()
+        bf = lambda *sh: torch.empty(*sh, dtype=torch.bfloat16, device=dev)
+        g1 = _geom(B, self.history, 84, 32, 8, 4, 1, in_bstride=x.stride(0))
+        a1 = bf(B * 21 * 21, 16 * self.history)
+        call("riqn_s2d_u8", g1, ptr(x), ptr(a1))
+        g1p, g2p, g3p = _geom(2 * B, self.history, 84, 32, 8, 4, 1), _geom(2 * B, 32, 20, 64, 4, 2, 0), _geom(2 * B, 64, 9, 64, 3, 1, 0)
+        a2_hi, a2_lo = bf(2 * B * 100, 128), (bf(2 * B * 100, 128) if x3 else None)
+        a3_hi, a3_lo = bf(2 * B * 81, 64), (bf(2 * B * 81, 64) if x3 else None)
+        feat = torch.empty(2 * B, FEAT, device=dev)
+        so, oo = self._strip_ops, other._strip_ops
+        lo = lambda t: ptr(t) if x3 else None
+        call("riqn_conv_fwd_strip", g1p, ptr(a1), None, ptr(so["conv1"][0]), lo(so["conv1"][1]), ptr(self.conv1.bias), None,
+             ptr(a2_hi), ptr(a2_lo), 2, 10, ptr(oo["conv1"][0]), lo(oo["conv1"][1]), ptr(other.conv1.bias), 1)
+        call("riqn_conv_fwd_strip", g2p, ptr(a2_hi), ptr(a2_lo), ptr(so["conv2"][0]), lo(so["conv2"][1]), ptr(self.conv2.bias), None,
+             ptr(a3_hi), ptr(a3_lo), 1, 9, ptr(oo["conv2"][0]), lo(oo["conv2"][1]), ptr(other.conv2.bias), 0)
+        call("riqn_conv_fwd_strip", g3p, ptr(a3_hi), ptr(a3_lo), ptr(so["conv3"][0]), lo(so["conv3"][1]), ptr(self.conv3.bias),
+             ptr(feat), None, None, 0, 0, ptr(oo["conv3"][0]), lo(oo["conv3"][1]), ptr(other.conv3.bias), 0)
+        return feat[:B], feat[B:]
 
     def iqn_head(self, feat, num_quantiles, tau, keep=None):
         """Quantile embedding, Hadamard, noisy hidden layers, z-layers, dueling.  model.py:131-157"""
@@ -628,14 +660,16 @@ class DQN(nn.Module):
                         head_bwd_tc=bwd_tc, emb_bwd_tc=emb_tc)
         return q
 
-    def forward(self, x, num_quantiles=None, log=False, tau=None, keep=None, fresh_weights=False, col_cache=None):
-        """model.py:112-157.  Returns (q, quantiles) in IQN mode."""
+    def forward(self, x, num_quantiles=None, log=False, tau=None, keep=None, fresh_weights=False, col_cache=None, feat=None):
+        """model.py:112-157.  Returns (q, quantiles) in IQN mode.  ``feat`` (B, 3136): trunk output computed by the caller
+        (trunk_pair); only valid for no-grad passes."""
         if self.rainbow_only:
             from . import c51
             return c51.forward(self, x, log=log, keep=keep, fresh_weights=fresh_weights)
         if not fresh_weights:
             self.compose_weights()
-        feat = self.trunk(x, keep, col_cache)
+        if feat is None or keep is not None:
+            feat = self.trunk(x, keep, col_cache)
         if tau is None:
             tau = self.draw_quantiles(num_quantiles * x.shape[0])
         else:

@@ -256,3 +256,22 @@ def test_split_bf16_multi_matches_single_calls(cuda_dev):
         assert torch.equal(hi, rh) and torch.equal(lo, rl)
         if hiT is not None:
             assert torch.equal(hiT, rh.t().contiguous())
+
+
+def test_trunk_pair_equals_two_trunks(cuda_dev):
+    """Online + target conv trunks over the same frames as ONE stacked batch (three launches, two weight sets selected by
+    m-tile) == the two trunks run one after the other, bit for bit."""
+    from rainbow_iqn_apex_b200 import DQN
+    B = 128
+    a, b_ = DQN(make_args(cuda_dev), 18).to(cuda_dev), DQN(make_args(cuda_dev), 18).to(cuda_dev)
+    load_params(a, net.make_params(31))
+    load_params(b_, net.make_params(32))
+    x = torch.from_numpy(np.random.RandomState(9).randint(0, 256, (B, 7, 84, 84)).astype(np.uint8)).to(cuda_dev)[:, 3:7]
+    pair = a.trunk_pair(b_, x)
+    assert pair is not None
+    fa, fb = pair
+    assert torch.equal(fa, a.trunk(x)) and torch.equal(fb, b_.trunk(x))
+    assert not torch.equal(fa, fb)
+    ref = net.conv_trunk(net.to_torch(net.make_params(32)), x.cpu().float().div_(255)).numpy()
+    assert rel_err(fb.cpu().numpy(), ref) < 3e-5
+    assert a.trunk_pair(b_, x[:5]) is None                      # rows per network must fill whole 128-row tiles

@@ -194,7 +194,7 @@ def test_strip_convolution_forward_and_backward(cuda_dev, batch):
         out = torch.zeros(batch, cout, gm.OH, gm.OH, device=dev)
         bd = b.to(dev)
         nxt = (ptr(a_hi[i + 1]), ptr(a_lo[i + 1]), geoms[i + 1].stride, grids[i + 1]) if i < 2 else (None, None, 0, 0)
-        call("riqn_conv_fwd_strip", gm, ptr(a_hi[i]), ptr(a_lo[i]), ptr(w_hi), ptr(w_lo), ptr(bd), ptr(out), *nxt)
+        call("riqn_conv_fwd_strip", gm, ptr(a_hi[i]), ptr(a_lo[i]), ptr(w_hi), ptr(w_lo), ptr(bd), ptr(out), *nxt, None, None, None, 0)
         torch.cuda.synchronize()
         outs.append(out)
         assert rel_err(out.cpu().numpy(), outs_ref[i].numpy()) < 2e-5, (i, rel_err(out.cpu().numpy(), outs_ref[i].numpy()))
