@@ -215,9 +215,7 @@ int riqn_quantile_embed_fwd_tc(int batch, int num_quantiles, int embed_dim, int 
                                const float* feat, const void* iqn_w_hi, const void* iqn_w_lo, const float* iqn_b,
                                void* cos_hi, void* cos_lo, void* cos_t_hi, float* x32, void* x_hi, void* x_lo, void* x_hi_t,
                                void* x_lo_t, int x_fp16, void* stream);
-/* x_fp16 != 0: the fp16 arithmetic mode -- cos_hi and iqn_w_hi hold fp16 images and the embedding product is ONE tcgen05 pass
- * (cos_lo, or NULL, then receives the bf16 image of cos that the backward consumes; iqn_w_lo is ignored);
- * x_hi = fp16(x), the operand of the single-pass fp16 head product (same tensor-core rate as bf16, 11-bit
+/* x_fp16 != 0: x_hi = fp16(x), the operand of the single-pass fp16 head product (same tensor-core rate as bf16, 11-bit
  * significand), and x_lo (or NULL) = bf16(x), the operand of the bf16 backward; x_hi_t / x_lo_t must be NULL. */
 /* Backward on bf16 operands (rows % 8 == 0): dx (rows, feat_dim) from the head dgrad, fp32 or (dx_is_bf16 != 0) bf16;
  * x_lo may be NULL (x = x_hi); cos_hi (rows, embed_dim) bf16 row-major (the forward's image); dpre (rows, feat_dim) bf16
@@ -379,7 +377,6 @@ typedef struct riqn_split_job {
   void* hi;
   void* lo;
   void* hi_t;
-  int fp16;             /* != 0: hi receives ONE fp16 image (lo / hi_t ignored) */
 } riqn_split_job;
 int riqn_split_bf16_multi(int n_jobs, const riqn_split_job* jobs, void* stream);
 /* C (+)= A B^T with A (M,K), B (N,K) row-major bf16, K % 8 == 0, fp32 accumulation in TMEM.  a_lo/b_lo non-NULL

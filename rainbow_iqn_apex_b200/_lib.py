@@ -31,7 +31,7 @@ class NoisyLayer(C.Structure):
 class SplitJob(C.Structure):
     """riqn_split_job (include/riqn_b200.h)"""
     _fields_ = [("src", _P), ("perm", _P), ("rows", C.c_int), ("cols", C.c_int), ("div", C.c_float), ("hi", _P),
-                ("lo", _P), ("hi_t", _P), ("fp16", C.c_int)]
+                ("lo", _P), ("hi_t", _P)]
 
 
 # name -> argtypes (everything returns int).  Must list every symbol of include/riqn_b200.h.

@@ -1026,10 +1026,6 @@ __global__ void split_bf16_multi_kernel(SplitJobs t) {
   const int r = idx / J.cols, c = idx - r * J.cols;
   float x = J.src[(long)r * J.cols + (J.perm ? J.perm[c] : c)];
   if (J.div != 1.0f) x = __fdiv_rn(x, J.div);
-  if (J.fp16) {                      // one fp16 image (single-pass fp16 products)
-    reinterpret_cast<__half*>(J.hi)[idx] = __float2half_rn(x);
-    return;
-  }
   const riqn::bf16 h = __float2bfloat16_rn(x);
   reinterpret_cast<riqn::bf16*>(J.hi)[idx] = h;
   if (J.lo) reinterpret_cast<riqn::bf16*>(J.lo)[idx] = __float2bfloat16_rn(x - __bfloat162float(h));

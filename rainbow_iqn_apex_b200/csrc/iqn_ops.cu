@@ -59,7 +59,7 @@ __global__ void cos_embed_kernel(int B, int Nq, int E, const float* __restrict__
 // Same values as bf16 (hi, lo) operand images for the tensor-core embedding product, plus the transposed hi image
 // (E, R) the iqn_fc weight-gradient product consumes.
 __global__ void cos_embed_bf16_kernel(int B, int Nq, int E, const float* __restrict__ tau, __nv_bfloat16* __restrict__ hi,
-                                      __nv_bfloat16* __restrict__ lo, __nv_bfloat16* __restrict__ hiT, int fp16) {
+                                      __nv_bfloat16* __restrict__ lo, __nv_bfloat16* __restrict__ hiT) {
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long R = (long)B * Nq;
   if (idx >= R * E) return;
@@ -68,11 +68,6 @@ __global__ void cos_embed_bf16_kernel(int B, int Nq, int E, const float* __restr
   const int b = (int)(r / Nq), q = (int)(r - (long)b * Nq);
   const float ipi = __fmul_rn((float)i, 3.14159274101257324f);
   const float c = cosf(__fmul_rn(ipi, tau[(long)q * B + b]));
-  if (fp16) {                       // single-pass fp16 embedding product: hi = fp16(c); lo (optional) = bf16(c) for the backward
-    reinterpret_cast<__half*>(hi)[idx] = __float2half_rn(c);
-    if (lo) lo[idx] = __float2bfloat16_rn(c);
-    return;
-  }
   const __nv_bfloat16 h = __float2bfloat16_rn(c);
   hi[idx] = h;
   if (lo) lo[idx] = __float2bfloat16_rn(c - __bfloat162float(h));
@@ -947,21 +942,18 @@ RIQN_API int riqn_quantile_embed_fwd_tc(int batch, int num_quantiles, int embed_
   cudaStream_t s = (cudaStream_t)stream;
   const long R = (long)batch * num_quantiles;
   cos_embed_bf16_kernel<<<riqn_cdiv(R * embed_dim, 256), 256, 0, s>>>(batch, num_quantiles, embed_dim, tau, (__nv_bfloat16*)cos_hi,
-                                                                     (__nv_bfloat16*)cos_lo, (__nv_bfloat16*)cosT_hi, x_fp16 ? 1 : 0);
+                                                                     (__nv_bfloat16*)cos_lo, (__nv_bfloat16*)cosT_hi);
   RIQN_LAUNCH_CHECK();
   TcExtra ex;
   ex.feat = feat;
   ex.batch = num_quantiles;    // rows per sample
   ex.o_hi = (__nv_bfloat16*)x_hi;
   ex.o_lo = (__nv_bfloat16*)x_lo;
-  // x_fp16: the whole embedding runs in the fp16 mode -- cos_hi and iqn_w_hi hold fp16 images (one tcgen05 pass; x is rounded to
-  // fp16 afterwards anyway), cos_lo (optional) is the bf16 image of cos for the backward; x_hi = fp16(x), x_lo (optional) = bf16(x)
-  ex.fmt = x_fp16 ? 7 : 0;
-  if (x_fp16 && cosT_hi != nullptr) return (int)cudaErrorInvalidValue;
+  ex.fmt = x_fp16 ? 4 : 0;       // x_hi = fp16(x) (head forward operand), x_lo (optional) = bf16(x) (backward operand)
   const bool want_t = x_hiT != nullptr || x_loT != nullptr;    // transposed images (cross-check arithmetic modes only)
   if (want_t && (x32 == nullptr || x_fp16)) return (int)cudaErrorInvalidValue;
-  int rc = gemm_bf16_tc((int)R, feat_dim, embed_dim, (const __nv_bfloat16*)cos_hi, x_fp16 ? nullptr : (const __nv_bfloat16*)cos_lo,
-                        (const __nv_bfloat16*)iqn_w_hi, (cos_lo && !x_fp16) ? (const __nv_bfloat16*)iqn_w_lo : nullptr, x32, feat_dim,
+  int rc = gemm_bf16_tc((int)R, feat_dim, embed_dim, (const __nv_bfloat16*)cos_hi, (const __nv_bfloat16*)cos_lo,
+                        (const __nv_bfloat16*)iqn_w_hi, cos_lo ? (const __nv_bfloat16*)iqn_w_lo : nullptr, x32, feat_dim,
                         TC_EMBED, iqn_b, nullptr, nullptr, 1, s, &ex);
   if (rc == 0 && want_t) {
     riqn::note_launches(1);

@@ -426,7 +426,7 @@ class DQN(nn.Module):
             self._split_jobs = None
         # every noise-free weight image in ONE launch (riqn_split_bf16_multi); the job table only holds static addresses
         convs = (("conv1", self.conv1), ("conv2", self.conv2), ("conv3", self.conv3))
-        key = tuple(c.weight.data_ptr() for _, c in convs) + (self._strip_ops["conv1"][0].data_ptr(), PRECISION["fwd"])
+        key = tuple(c.weight.data_ptr() for _, c in convs) + (self._strip_ops["conv1"][0].data_ptr(),)
         if getattr(self, "_split_jobs", None) is None or self._split_jobs[0] != key:
             specs = []
             for name, conv in convs:
@@ -442,9 +442,6 @@ class DQN(nn.Module):
                 j.src, j.perm = src.data_ptr(), perm.data_ptr() if perm is not None else None
                 j.rows, j.cols, j.div = hi.shape[0], hi.shape[1], div
                 j.hi, j.lo, j.hi_t = hi.data_ptr(), lo.data_ptr(), hiT.data_ptr() if hiT is not None else None
-                # fp16 mode: the embedding product is one fp16 pass -> iqn_fc.weight leaves as ONE fp16 image
-                iq = getattr(self, "iqn_fc", None)
-                j.fp16 = 1 if (iq is not None and src is iq.weight and PRECISION["fwd"] == "fp16") else 0
             self._split_jobs = (key, arr, len(specs))
         call("riqn_split_bf16_multi", self._split_jobs[2], self._split_jobs[1])
 
@@ -639,9 +636,7 @@ class DQN(nn.Module):
                       x_lo=bf(R, FEAT) if (head_x3 or (f16 and keep is not None)) else None, f16=f16,
                       x_hiT=bf(FEAT, R) if (bwd_tc and not mn) else None,
                       x_loT=bf(FEAT, R) if (bwd_tc and bwd == "bf16x3") else None,
-                      # fp16 mode: cos_hi = fp16(cos) (forward operand), cos_lo = bf16(cos) for the backward (gradient pass only)
-                      cos_hi=bf(R, E), cos_lo=bf(R, E) if ((x3 and not f16) or (f16 and keep is not None)) else None,
-                      cosT_hi=None, mn=mn)
+                      cos_hi=bf(R, E), cos_lo=bf(R, E) if x3 else None, cosT_hi=None, mn=mn)
             if need_x32:
                 xt = torch.empty(R, FEAT, device=dev)
                 cosv = torch.empty(R, E, device=dev)
@@ -770,7 +765,7 @@ class DQN(nn.Module):
             dpre = torch.empty(R, FEAT, dtype=torch.bfloat16, device=dev)
             # bf16 backward: x = x_hi (the lo image only refines the forward)
             call("riqn_quantile_embed_bwd_tc", B, Nq, E, FEAT, ptr(x_bf), None if (dx_bf16 or f16) else ptr(tc["x_lo"]),
-                 ptr(keep["feat"]), ptr(tc["cos_lo"] if f16 else tc["cos_hi"]), ptr(dx), 1 if dx_bf16 else 0, ptr(dpre), ptr(dfeat),
+                 ptr(keep["feat"]), ptr(tc["cos_hi"]), ptr(dx), 1 if dx_bf16 else 0, ptr(dpre), ptr(dfeat),
                  ptr(gv(self.iqn_fc.weight)), ptr(gv(self.iqn_fc.bias)))
         else:
             call("riqn_quantile_embed_bwd", B, Nq, E, FEAT, ptr(keep["xt"]), ptr(keep["feat"]), ptr(keep["cos"]), ptr(dx),

@@ -76,12 +76,8 @@ def test_forward_injected(cuda_dev, nets):
     def qmajor(t):   # head-internal rows are sample-major (b*Nq + q); the oracle's are quantile-major (q*B + b)
         return t.reshape(B, Nq, -1).transpose(0, 1).reshape(B * Nq, -1)
 
-    if tc["f16"]:     # fp16(cos) for the forward product, bf16(cos) for the backward
-        assert rel_err(qmajor(tc["cos_hi"].view(torch.float16).float()).cpu().numpy(), keep["cos"].numpy()) < 5e-4
-        assert rel_err(qmajor(tc["cos_lo"].float()).cpu().numpy(), keep["cos"].numpy()) < 4e-3
-    else:
-        cos_gpu = qmajor(tc["cos_hi"].float() + tc["cos_lo"].float()).cpu().numpy()    # bf16 hi + lo images
-        assert rel_err(cos_gpu, keep["cos"].numpy()) < 2e-5
+    cos_gpu = qmajor(tc["cos_hi"].float() + tc["cos_lo"].float()).cpu().numpy()    # bf16 hi + lo images
+    assert rel_err(cos_gpu, keep["cos"].numpy()) < 2e-5
     if tc["f16"]:     # default arithmetic: x leaves as fp16(x) (head forward operand) + bf16(x) (backward operand)
         assert tc["x_hi"].dtype == torch.float16
         assert rel_err(qmajor(tc["x_hi"].float()).cpu().numpy(), keep["x"].numpy()) < 5e-4
