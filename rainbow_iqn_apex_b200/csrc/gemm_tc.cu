@@ -93,6 +93,7 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sr
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -681,7 +682,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
               const uint32_t fb = epi_fb + (warp - 2) * 256;
               const bool row_ok = m < p.M;
               const float* frow = p.feat + (long)((row_ok ? m : 0) / p.batch) * p.N + n0;   // per-row feat (several samples per warp)
-              if (lane == 0) tma_store_wait_read();               // the previous tile's stores have read this staging tile
+              // one image: the two 2 KB halves of the staging tile alternate, so only the store of TWO tiles ago must have
+              // read its half (the store of the previous tile stays in flight); two images use both halves every tile
+              const bool one_img = p.o_lo == nullptr;
+              const uint32_t st0 = one_img ? st + (local & 1) * 2048 : st;
+              if (lane == 0) { if (one_img) tma_store_wait_read1(); else tma_store_wait_read(); }
               __syncwarp();
               asm volatile("st.shared.b32 [%0], %1;" ::"r"(fb + lane * 4), "r"(__float_as_uint(ef)) : "memory");
               asm volatile("st.shared.b32 [%0], %1;" ::"r"(fb + 128 + lane * 4), "r"(__float_as_uint(eb)) : "memory");
@@ -709,7 +714,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
                 }
               }
               // 32 rows x 64 bytes per image in the TMA SWIZZLE_64B layout: 16-byte chunk c of row r sits at chunk c ^ ((r >> 1) & 3)
-              const uint32_t srow = st + lane * 64;
+              const uint32_t srow = st0 + lane * 64;
               const int sw = (lane >> 1) & 3;
 #pragma unroll
               for (int c = 0; c < 4; ++c) {
@@ -719,8 +724,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
               fence_proxy_async();                                // generic-proxy writes -> visible to the TMA engine
               __syncwarp();
               if (lane == 0) {
-                if (p.o_hi) tma_store_2d(&p.mapO[0], st, n0, m_base);
-                if (p.o_lo) tma_store_2d(&p.mapO[1], st + 2048, n0, m_base);
+                if (p.o_hi) tma_store_2d(&p.mapO[0], st0, n0, m_base);
+                if (p.o_lo) tma_store_2d(&p.mapO[1], st0 + 2048, n0, m_base);
                 tma_store_commit();
               }
             }
