@@ -8,7 +8,10 @@ import sys
 
 rep = sys.argv[1]
 title = sys.argv[2] if len(sys.argv) > 2 else ""
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True, check=True).stdout
+if rep.endswith(".csv"):          # already exported with `ncu -i x.ncu-rep --page raw --csv` (the reports themselves are large)
+    raw = open(rep).read()
+else:
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True, check=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units, data = rows[0], rows[1], rows[2:]
 col = {k: i for i, k in enumerate(hdr)}
