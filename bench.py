@@ -272,10 +272,10 @@ def run_ours(args):
                   "formula": "2*images*Nq*B*F + 4*Nq*B + 4*B*F + 4*(E*F+F)  (SURVEY 8d, materialised output)"}
     cv_ms = sum(a_.elapsed_time(b_) for a_, b_, _ in timers["riqn_conv_fwd_strip"]) + \
         sum(a_.elapsed_time(b_) for a_, b_, _ in timers["riqn_s2d_u8"])
-    n_trunks = max(1, len(timers["riqn_conv_fwd_strip"]) // 3)
+    n_trunks = 3 * prof_steps              # three network passes per step (the two no-grad trunks share their launches)
     cv_bytes = n_trunks * (B * 4 * 7056 + 4.0 * B * FEAT)                # uint8 frame stack in, fp32 features out
     cv_gbs = cv_bytes / (cv_ms * 1e-3) / 1e9 if cv_ms > 0 else 0.0
-    roof_conv = {"kernel": "conv trunk forward (riqn_s2d_u8 + 3 x riqn_conv_fwd_strip per pass; 3 passes/step)", "bound": "hbm",
+    roof_conv = {"kernel": "conv trunk forward (riqn_s2d_u8 + riqn_conv_fwd_strip: 3 network passes in 6 launches per step)", "bound": "hbm",
                  "achieved": cv_gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": cv_gbs / pk["hbm"], "traffic": None,
                  "algorithmic_bytes_per_step": cv_bytes / prof_steps, "ms_per_step": cv_ms / prof_steps,
                  "formula": "B*4*7056 (uint8 frames) + 4*B*3136 (features) per pass: intermediates are not algorithmic"}
@@ -497,10 +497,12 @@ def run_apex(args):
                 if pool.observe(states, act, rew, done):
                     flushed[0] += pool.flush()
                 states = torch.cat([states[:, 1:], nxt], 1)
+        if not topo.is_learner:
+            # the shard's part of the NEXT batch is drawn before this step's losses arrive (one step of priority staleness;
+            # the reference's sampler queue holds five batches), so the next all-gather never waits for the actors
+            topo.presample(mem)
         topo.route(loss, mem, None if topo.is_learner else batch)
         topo.maybe_publish(agent)
-        if not topo.is_learner:
-            topo.presample(mem)                                # the shard's part of the next batch, drawn after this step's update
 
     def barrier():
         torch.distributed.barrier()

@@ -45,9 +45,10 @@ def sharded_is_weights(pri, shard_of, totals, counts, filled_capacity, beta):
     totals = torch.as_tensor(totals, dtype=torch.float64, device=pri.device)
     counts = torch.as_tensor(counts, dtype=torch.float64, device=pri.device)
     batch = counts.sum()
+    cap = torch.as_tensor(filled_capacity, dtype=torch.float64, device=pri.device)     # may be a device scalar: no host sync
     prob = (counts[shard_of] / batch) * pri / totals[shard_of]
-    prob = torch.where(pri > 0, prob, torch.full_like(prob, 1.0 / float(filled_capacity)))
-    w = (float(filled_capacity) * prob) ** (-float(beta))
+    prob = torch.where(pri > 0, prob, (1.0 / cap).expand_as(prob))
+    w = (cap * prob) ** (-float(beta))
     return w / w.max()
 
 
@@ -291,8 +292,8 @@ class ApexTopology:
             smp, stat = unpack(ticket["out"][s + 1], self.n_max, h, n)
             plist.append(smp)
             stats.append(stat)
-        st = torch.stack(stats).cpu()                      # (S, 2): shard totals and filled capacities, one small D2H
-        return assemble_batch(plist, self.counts, st[:, 0].to(plist[0]["pri"].device), float(st[:, 1].sum()), beta, h, n)
+        st = torch.stack(stats)                            # (S, 2) on the device: shard totals and filled capacities --
+        return assemble_batch(plist, self.counts, st[:, 0], st[:, 1].sum(), beta, h, n)   # the learner's host never waits
 
     def sample(self, mem=None, beta=0.4, device=None, history=4, n_step=3):
         return self.sample_end(self.sample_begin(mem, device, history, n_step), beta)
