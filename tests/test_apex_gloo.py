@@ -151,3 +151,28 @@ def test_shard_counts_and_single_shard_weights():
     pri[5] = 0.0
     w = apex.sharded_is_weights(torch.from_numpy(pri), torch.zeros(40, dtype=torch.int64), [pri.sum()], [40], 5000, 0.4)
     assert w[5] == 1.0 and torch.isfinite(w).all()
+
+
+def test_pack_unpack_roundtrip():
+    """The packed per-shard record (one collective per learner batch) returns every field bit for bit, as views."""
+    from rainbow_iqn_apex_b200 import apex
+    n_max, g = 5, torch.Generator().manual_seed(4)
+    smp = apex.ShardSample.empty(n_max, torch.device("cpu"))
+    smp["tree_idx"].copy_(torch.randint(0, 1 << 40, (n_max,), generator=g))
+    smp["pri"].copy_(torch.rand(n_max, dtype=torch.float64, generator=g))
+    smp["window"].copy_(torch.randint(0, 256, (n_max, 7, 84, 84), dtype=torch.uint8, generator=g))
+    smp["actions"].copy_(torch.randint(0, 18, (n_max,), generator=g))
+    smp["returns"].copy_(torch.randn(n_max, generator=g))
+    smp["nonterminals"].copy_((torch.rand(n_max, generator=g) < 0.9).float())
+    stat = torch.tensor([123.456, 7890.0], dtype=torch.float64)
+    buf = apex.pack(smp, stat, n_max)
+    assert buf.dtype == torch.uint8 and buf.numel() == apex.packed_bytes(n_max)
+    out, st = apex.unpack(buf, n_max)
+    for k in apex.ShardSample.FIELDS:
+        assert out[k].dtype == smp[k].dtype and torch.equal(out[k], smp[k]), k
+    assert torch.equal(st, stat)
+    # the filled capacity may arrive as a device scalar (no host sync on the learner): same weights as with a float
+    pri, sh = torch.rand(8, dtype=torch.float64, generator=g) + 0.01, torch.tensor([0, 0, 0, 1, 1, 1, 1, 0])
+    w1 = apex.sharded_is_weights(pri, sh, [3.0, 5.0], [4, 4], 1000.0, 0.4)
+    w2 = apex.sharded_is_weights(pri, sh, torch.tensor([3.0, 5.0], dtype=torch.float64), [4, 4], torch.tensor(1000.0, dtype=torch.float64), 0.4)
+    assert torch.equal(w1, w2)
