@@ -18,52 +18,54 @@ from .optim import Adam
 
 
 class Agent:
+    # public attribute <- args field (agent.py:13-63; read by the loss code, the actors and the launch scripts)
+    _ARG_FIELDS = (("n", "multi_step"), ("history", "history_length"), ("discount", "discount"), ("device", "device"),
+                   ("batch_size", "batch_size"), ("rainbow_only", "rainbow_only"))
+    _C51_FIELDS = (("atoms", "atoms"), ("Vmin", "V_min"), ("Vmax", "V_max"))
+    _IQN_FIELDS = ("kappa", "num_tau_samples", "num_tau_prime_samples", "num_quantile_samples")
+
     def __init__(self, args, action_space, redis_servor):
         _lib.require_device()
-        self.action_space = action_space
-        self.n = args.multi_step
-        self.history = args.history_length
-        self.discount = args.discount
-        self.redis_servor = redis_servor
-        self.device = args.device
-        self.batch_size = args.batch_size
+        self.action_space, self.redis_servor = action_space, redis_servor
+        for attr, field in self._ARG_FIELDS:
+            setattr(self, attr, getattr(args, field))
         self.length_actor_buffer = getattr(args, "length_actor_buffer", 1000)
 
-        self.online_net = DQN(args, self.action_space).to(device=args.device)
-        checkpoint = None
-        if getattr(args, "model", None):
-            if os.path.isfile(args.model):
-                print("We loaded model ", args.model)
-                checkpoint = torch.load(args.model, map_location="cpu")
-                self.online_net.load_state_dict(checkpoint["model_state_dict"])
-            else:
-                print("We didn't fint the model you gave as input!")
-                raise Exception
-        self.online_net.train()
-
-        self.target_net = DQN(args, self.action_space).to(device=args.device)
+        # online network (+ optional checkpoint, agent.py:26-34), noisy target copy with frozen parameters (:37-41), Adam (:43)
+        checkpoint = self._read_checkpoint(getattr(args, "model", None))
+        self.online_net = DQN(args, action_space).to(device=args.device)
+        if checkpoint is not None:
+            self.online_net.load_state_dict(checkpoint["model_state_dict"])
+        self.target_net = DQN(args, action_space).to(device=args.device)
         self.update_target_net()
-        self.target_net.train()                      # target stays noisy (agent.py:37-41)
-        for param in self.target_net.parameters():
-            param.requires_grad = False
-
+        for net in (self.online_net, self.target_net):
+            net.train()                                  # the target stays in train mode: it is noisy too
+        for p in self.target_net.parameters():
+            p.requires_grad = False
         self.optimiser = Adam(self.online_net.parameters(), lr=args.lr, eps=args.adam_eps)
         if checkpoint is not None:
             self.optimiser.load_state_dict(checkpoint["optimiser_state_dict"])
 
-        self.rainbow_only = args.rainbow_only
-        if self.rainbow_only:
-            self.atoms = args.atoms
-            self.Vmin = args.V_min
-            self.Vmax = args.V_max
-            self.support = torch.linspace(args.V_min, args.V_max, self.atoms).to(device=args.device)
-            self.delta_z = (args.V_max - args.V_min) / (self.atoms - 1)
-        else:
-            self.kappa = args.kappa
-            self.num_tau_samples = args.num_tau_samples
-            self.num_tau_prime_samples = args.num_tau_prime_samples
-            self.num_quantile_samples = args.num_quantile_samples
+        if self.rainbow_only:                            # categorical support (agent.py:49-57)
+            for attr, field in self._C51_FIELDS:
+                setattr(self, attr, getattr(args, field))
+            self.support = torch.linspace(self.Vmin, self.Vmax, self.atoms).to(device=args.device)
+            self.delta_z = (self.Vmax - self.Vmin) / (self.atoms - 1)
+        else:                                            # IQN sampling sizes (agent.py:58-63)
+            for field in self._IQN_FIELDS:
+                setattr(self, field, getattr(args, field))
         self._inject = None  # parity hook: {"noises": (n0, n1, n2), "taus": (t0, t1, t2)}
+
+    @staticmethod
+    def _read_checkpoint(path):
+        """agent.py:26-34: a given but missing checkpoint is an error (bare Exception, like the reference)."""
+        if not path:
+            return None
+        if not os.path.isfile(path):
+            print("We didn't fint the model you gave as input!")
+            raise Exception
+        print("We loaded model ", path)
+        return torch.load(path, map_location="cpu")
 
     def reset_noise(self):
         """agent.py:66-67"""

@@ -250,8 +250,9 @@ class ApexTopology:
 
     def presample(self, mem):
         """Actor ranks: draw this shard's part of the NEXT learner batch now (tree descent + window gather + packing), so that
-        the gather at the start of the next step finds it ready.  Called right after route(): the draw already sees the
-        priorities of the step that just finished."""
+        the collective at the start of the next step finds it ready.  Called before route() (bench.py) the draw is one step
+        stale -- the reference's sampler queue holds five batches, launch_learner.py:24-50 -- and the learner never waits for
+        the shards; called after route() it already sees the priorities of the step that just finished."""
         mine = sample_shard(mem, self.counts[self.shard], self.n_max)
         stat = torch.stack([mem.transitions.tree[0], torch.tensor(float(mem.transitions.get_current_capacity()),
                                                                   dtype=torch.float64, device=mem.device)])
