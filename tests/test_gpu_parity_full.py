@@ -239,7 +239,7 @@ def test_data_parallel_equivalence_one_gpu(cuda_dev):
     full.optimiser.step()
     assert torch.equal(halves[0].online_net._flat, halves[1].online_net._flat)
     dp = (halves[0].online_net._flat - full.online_net._flat).abs().max().item()
-    assert dp < 1.5e-8, dp                                           # <= 2 ulp of a 0.06-sized weight (3e-4 of one Adam step)
+    assert dp < 3e-8, dp                                             # a few ulp of a 0.06-sized weight (6e-4 of one Adam step); observed 1 ulp
     # the native noise path: replicas sharing the Philox seed and counters draw identical epsilons (parallel.py)
     n0, n1 = halves[0].online_net, halves[1].online_net
     n1._rng_seed = n0._rng_seed
