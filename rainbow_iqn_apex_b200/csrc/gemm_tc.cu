@@ -605,20 +605,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
         }
         if (EPI == TC_COL2IM && n0 < p.N) {
           // din[b, c, oh*s + kh, ow*s + kw] += dcol[m, (c, kh, kw)]: lane j decodes column n0 + j once, the offsets are
-          // broadcast by shuffle; lanes = consecutive output pixels, so one red instruction touches a few lines.
-          // Pre-reduction: (lane L, kw) and (lane L + 1, kw - s) of the same (c, kh) hit the SAME input pixel when both
-          // pixels sit in one output row, so a column with kw >= s hands its value to the next lane's column j - s (kw is
-          // the fastest column index) instead of issuing its own atomic; walking j downwards chains the hand-offs
-          // (k = 3, s = 1: three contributions -> one red; k = 4, s = 2: two -> one).  Any partial grouping is valid --
-          // the reds are additive -- so row ends, warp ends and chunk boundaries simply fall back to their own red.
+          // broadcast by shuffle; lanes = consecutive output pixels, so one red instruction touches a few lines
           const int khw = p.ci_kh * p.ci_kw;
           const int kcol = n0 + lane;
-          int coff = -1, ckw = 0;
+          int coff = -1;
           if (kcol < p.N) {
             const int c = kcol / khw, r = kcol - c * khw;
             const int kh = r / p.ci_kw, kw = r - kh * p.ci_kw;
             coff = (c * p.ci_h + kh) * p.ci_w + kw;
-            ckw = kw;
           }
           bool row_ok = m < p.M;
           const int mm = row_ok ? m : 0;
@@ -627,29 +621,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
           const int oh = pp / rw, ow = pp - oh * rw;
           if (p.ci_G) row_ok = row_ok && oh < p.ci_oh && ow < p.ci_ow;   // grid rows beyond the real outputs carry zeros
           float* base = p.C + ((long)b * p.ci_cin * p.ci_h + oh * p.ci_stride) * p.ci_w + ow * p.ci_stride;
-          // lane L + 1 is the next pixel of the same output row, and both are real outputs
-          const int nb_ow = __shfl_down_sync(0xffffffffu, ow, 1), nb_oh = __shfl_down_sync(0xffffffffu, oh, 1);
-          const int nb_b = __shfl_down_sync(0xffffffffu, b, 1), nb_ok = __shfl_down_sync(0xffffffffu, (int)row_ok, 1);
-          const bool next_same = lane < 31 && row_ok && nb_ok && nb_b == b && nb_oh == oh && nb_ow == ow + 1;
-          const bool prev_same = __shfl_up_sync(0xffffffffu, (int)next_same, 1) && lane > 0;
-          const int sstr = p.ci_stride;
 #pragma unroll
-          for (int j = 31; j >= 0; --j) {
+          for (int j = 0; j < 32; ++j) {
             const int off = __shfl_sync(0xffffffffu, coff, j);
-            const int kwj = __shfl_sync(0xffffffffu, ckw, j);
-            const float val = __uint_as_float(v[j]);
-            if (off < 0) continue;                                       // (warp-uniform: column beyond N)
-            if (kwj >= sstr && j - sstr >= 0 && sstr <= 2) {             // hand over to lane + 1, column j - s
-              const float up = __shfl_up_sync(0xffffffffu, val, 1);
-              if (prev_same) {
-                if (sstr == 1) v[j > 0 ? j - 1 : 0] = __float_as_uint(__uint_as_float(v[j > 0 ? j - 1 : 0]) + up);
-                else v[j > 1 ? j - 2 : 0] = __float_as_uint(__uint_as_float(v[j > 1 ? j - 2 : 0]) + up);
-              }
-              if (row_ok && !next_same)
-                asm volatile("red.global.add.f32 [%0], %1;" ::"l"(base + off), "f"(val) : "memory");
-            } else if (row_ok) {
-              asm volatile("red.global.add.f32 [%0], %1;" ::"l"(base + off), "f"(val) : "memory");
-            }
+            if (row_ok && off >= 0)
+              asm volatile("red.global.add.f32 [%0], %1;" ::"l"(base + off), "f"(__uint_as_float(v[j])) : "memory");
           }
         }
         if ((EPI == TC_STORE || EPI == TC_EMBED || (EPI == TC_BIAS_RELU && (p.M & 1) == 0) ||
