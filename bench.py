@@ -9,9 +9,13 @@ device-resident replay shard (sum-tree descent + IS weights + 7-frame window gat
 fused IQN loss, backward, (gradient all-reduce when N > 1), Adam, priority update of the sampled leaves.
 N > 1 is the data-parallel learner of config 5 (512 transitions per GPU, weak scaling).
 
-Timing: W untimed warm-up steps, then K steps bracketed by barrier + torch.cuda.synchronize(), CUDA events on
-the launching stream, max over ranks.  Inputs are larger than L2: every step draws a fresh prioritized
-minibatch from a multi-GB replay shard and streams > 2 GB of activations.
+Timing: W untimed warm-up steps, then `--blocks` regions of EXACTLY K steps each, every one bracketed by barrier +
+torch.cuda.synchronize(), CUDA events on the launching stream, max over ranks; the headline is the median block.  A
+`sustained` leg (>= 3 s of steps, clocks sampled) and the end-to-end leg (pinned host batches, H2D / D2H inside the timed
+region) follow.  Inputs are larger than L2: every step draws a fresh prioritized minibatch from a multi-GB replay shard
+and streams > 1 GB of activations.  Also in the line: rooflines of the hidden products (tensor), the embedding producer,
+the conv trunk and the loss kernel (HBM), the Rainbow-only (C51, configs[2]) leg, and the CPU port timed on the host cores.
+`--topology apex` (N >= 2) runs configs[3] instead: 1 learner rank + N-1 actor GPUs with sharded replay.
 Prints ONE JSON line on rank 0.
 """
 import argparse
