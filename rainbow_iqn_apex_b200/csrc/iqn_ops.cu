@@ -511,6 +511,153 @@ __global__ void __launch_bounds__(256, 2) z_dueling_fwd4_kernel(long R, int B, i
   }
 }
 
+// The same arithmetic (same operation order per output: bit-identical q) with the rows streamed through shared memory.
+// Every warp owns one 4-row stage (4 x 2*HID floats, contiguous in H) filled by a bulk async copy that completes on the
+// warp's mbarrier; as soon as the advantage halves of the current rows sit in registers, lane 0 launches the copy of the
+// warp's next 4 rows, which then runs under the A advantage products (95 % of the arithmetic).  The row registers are no
+// longer the only bytes in flight, so one CTA of 8 warps per SM keeps HBM busy, and with the register cap gone the
+// advantage loop runs two independent product / shuffle chains at a time.
+__device__ __forceinline__ uint32_t zs_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void zs_bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(zs_smem_u32(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   zs_smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(zs_smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void zs_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "ZS_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra ZS_DONE_%=;\n"
+      "bra ZS_WAIT_%=;\n"
+      "ZS_DONE_%=:\n"
+      "}\n" ::"r"(zs_smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+constexpr int ZS_WARPS = 8;
+template <int HID>
+constexpr size_t zs_smem_bytes(int A) {
+  return (size_t)ZS_WARPS * 4 * 2 * HID * sizeof(float) + (size_t)(1 + A) * HID * sizeof(float) + 32 * sizeof(float) +
+         ZS_WARPS * sizeof(uint64_t);
+}
+
+template <int HID>
+__global__ void __launch_bounds__(ZS_WARPS * 32, 1) z_dueling_fwd4s_kernel(long R, int B, int A, const float* __restrict__ H,
+                                                                          const float* __restrict__ Wz,
+                                                                          const float* __restrict__ bz, float* __restrict__ q) {
+  extern __shared__ __align__(1024) unsigned char zs_raw[];
+  constexpr int ROW = 2 * HID;                                  // floats per row of H
+  float* stage_all = reinterpret_cast<float*>(zs_raw);          // ZS_WARPS x (4 rows)
+  float* sW = stage_all + ZS_WARPS * 4 * ROW;                   // (1+A) * HID
+  float* sB = sW + (1 + A) * HID;                               // 32
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + 32);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < (1 + A) * HID / 4; i += blockDim.x)
+    reinterpret_cast<float4*>(sW)[i] = reinterpret_cast<const float4*>(Wz)[i];
+  if (threadIdx.x < 32) sB[threadIdx.x] = threadIdx.x <= A ? bz[threadIdx.x] : 0.f;
+  if (threadIdx.x < ZS_WARPS)
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(zs_smem_u32(bars + threadIdx.x)), "r"(1));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+
+  constexpr int T = HID / 128;
+  const int Nq = (int)(R / B);
+  const int my_rr = ((lane >> 3) & 1) * 2 + ((lane >> 4) & 1), my_j = lane & 7;
+  float* stage = stage_all + warp * 4 * ROW;
+  uint64_t* bar = bars + warp;
+  auto issue = [&](long r) {
+    const long left = R - r;
+    zs_bulk_load(stage, H + r * ROW, (uint32_t)((left < 4 ? left : 4) * ROW * sizeof(float)), bar);
+  };
+  // the transpose-reduce of z_dueling_fwd4_kernel: lane l ends with the sum of row rr(l)
+  auto fold = [&](const float (&p)[4]) -> float {
+    const bool b4 = lane & 16, b3 = lane & 8;
+    const float a01 = (b4 ? p[1] : p[0]) + __shfl_xor_sync(0xffffffffu, b4 ? p[0] : p[1], 16);
+    const float a23 = (b4 ? p[3] : p[2]) + __shfl_xor_sync(0xffffffffu, b4 ? p[2] : p[3], 16);
+    float c = (b3 ? a23 : a01) + __shfl_xor_sync(0xffffffffu, b3 ? a01 : a23, 8);
+    c += __shfl_xor_sync(0xffffffffu, c, 4);
+    c += __shfl_xor_sync(0xffffffffu, c, 2);
+    c += __shfl_xor_sync(0xffffffffu, c, 1);
+    return c;
+  };
+  auto dot4 = [&](const float4 (&hx)[4][T], int k) -> float {
+    const float4* wk = reinterpret_cast<const float4*>(sW + k * HID);
+    float p[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      const float4 w = wk[lane + 32 * t];
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+        const float4 x = hx[rr][t];
+        p[rr] = fmaf(x.x, w.x, p[rr]);
+        p[rr] = fmaf(x.y, w.y, p[rr]);
+        p[rr] = fmaf(x.z, w.z, p[rr]);
+        p[rr] = fmaf(x.w, w.w, p[rr]);
+      }
+    }
+    return fold(p);
+  };
+  const long stride = (long)gridDim.x * ZS_WARPS * 4;
+  long r0 = ((long)blockIdx.x * ZS_WARPS + warp) * 4;
+  if (r0 < R && lane == 0) issue(r0);
+  uint32_t parity = 0;
+  for (; r0 < R; r0 += stride) {
+    zs_wait(bar, parity);
+    parity ^= 1;
+    float4 hx[4][T];
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+      for (int t = 0; t < T; ++t) hx[rr][t] = reinterpret_cast<const float4*>(stage + rr * ROW)[lane + 32 * t];
+    const float v = dot4(hx, 0) + sB[0];
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+      for (int t = 0; t < T; ++t) hx[rr][t] = reinterpret_cast<const float4*>(stage + rr * ROW + HID)[lane + 32 * t];
+    __syncwarp();                                       // every lane has its copy of the rows: the stage is free
+    if (lane == 0 && r0 + stride < R) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      issue(r0 + stride);
+    }
+    float asum = 0.f, mine0 = 0.f, mine1 = 0.f, mine2 = 0.f;
+    auto keep = [&](int a, float c) {                   // A <= 24 on this path
+      if ((a & 7) == my_j) {
+        if (a < 8) mine0 = c; else if (a < 16) mine1 = c; else mine2 = c;
+      }
+    };
+    int k = 1;
+    for (; k + 1 <= A; k += 2) {                        // two independent chains; asum still adds in order k, k+1
+      const float c0 = dot4(hx, k) + sB[k];
+      const float c1 = dot4(hx, k + 1) + sB[k + 1];
+      asum += c0;
+      asum += c1;
+      keep(k - 1, c0);
+      keep(k, c1);
+    }
+    if (k <= A) {
+      const float c = dot4(hx, k) + sB[k];
+      asum += c;
+      keep(k - 1, c);
+    }
+    const long r = r0 + my_rr;
+    if (r < R) {
+      const long b = r / Nq, qi = r - b * Nq;                 // sample-major row -> quantile-major output row
+      float* out = q + (qi * B + b) * A;
+#pragma unroll
+      for (int g = 0; g < 3; ++g) {
+        const int a = my_j + 8 * g;
+        const float mg = g == 0 ? mine0 : (g == 1 ? mine1 : mine2);
+        if (a < A) out[a] = v + mg - asum / (float)A;
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Double-DQN action: a*[b] = argmax_a mean_k q[k*B+b, a]               (compute_loss_iqn.py:238-245)
 // ------------------------------------------------------------------------------------------------
@@ -1096,6 +1243,17 @@ RIQN_API int riqn_dueling_fwd(long rows, int batch, int hidden, int action_space
     if (!attr4_once.done[attr4_dev]) {
       RIQN_CUDA(cudaFuncSetAttribute(z_dueling_fwd4_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
       attr4_once.done[attr4_dev] = true;
+    }
+    if (rows >= 4096 && (reinterpret_cast<uintptr_t>(h) & 15) == 0) {      // streamed variant: one CTA per SM
+      static PerDeviceOnce attrs_once;
+      if (!attrs_once.done[attr4_dev]) {
+        RIQN_CUDA(cudaFuncSetAttribute(z_dueling_fwd4s_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)zs_smem_bytes<512>(24)));
+        attrs_once.done[attr4_dev] = true;
+      }
+      z_dueling_fwd4s_kernel<512><<<148, ZS_WARPS * 32, zs_smem_bytes<512>(action_space), (cudaStream_t)stream>>>(
+          rows, batch, action_space, h, wz, bz, q);
+      return (int)cudaGetLastError();
     }
     z_dueling_fwd4_kernel<512><<<148 * 2, 256, smem, (cudaStream_t)stream>>>(rows, batch, action_space, h, wz, bz, q);
   } else {

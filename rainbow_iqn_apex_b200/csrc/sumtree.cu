@@ -10,6 +10,8 @@
 //               gets `+= diff` sequentially in batch order; index 0 skipped on the way up and the root
 //               finally receives numpy's pairwise np.sum(diffs) (redis_memory.py:94-105,139-151)
 //   * valid-index shift away from actor write heads (redis_memory.py:242-264)
+#include <climits>
+
 #include "common.cuh"
 #include "../../include/riqn_b200.h"
 
@@ -275,8 +277,8 @@ __device__ double np_pairwise_sum_cta(const double* a, int n, int* lo, int* ll, 
 // gridDim.y CTAs per tree depth d >= 1 (blockIdx.x = d - 1) share the batch entries; the last x-row does the root.  For a node X at depth d
 // the reference applies, level by level, first the diffs of batch entries whose leaf is fewer parent steps
 // away (the shallower leaves of a non-power-of-two tree), then the deeper ones, each group in batch order
-// (redis_memory.py:94-105).  The first batch entry that touches X replays exactly that sequence of float64
-// adds, so every node is written by one thread only.
+// (redis_memory.py:94-105).  The warp of the first batch entry that touches X replays exactly that sequence of
+// float64 adds, so every node is written once.
 __global__ void update_propagate_kernel(int n, int max_depth, double* __restrict__ tree,
                                         const int64_t* __restrict__ idx, const double* __restrict__ diff) {
   extern __shared__ unsigned char smem_raw[];
@@ -303,30 +305,56 @@ __global__ void update_propagate_kernel(int n, int max_depth, double* __restrict
     sd[j] = diff[j];
   }
   __syncthreads();
-  // the batch entries of one depth are shared out over gridDim.y CTAs (each still sees all n entries)
-  for (int j = blockIdx.y * blockDim.x + threadIdx.x; j < n; j += gridDim.y * blockDim.x) {
+  // One warp per batch entry j (the entries of one depth are shared out over the warps of gridDim.y CTAs; every CTA
+  // still holds all n entries in shared memory).  The 32 lanes scan the batch 128 entries per step: first occurrence
+  // of j's node and the range of parent-step counts among its hits, reduced with redux.sync.  The owning warp then
+  // replays the float64 adds in the reference's order; the hit masks come from ballots, so every lane walks the
+  // same bits and carries the same accumulator (no divergence, shared-memory reads are broadcasts).
+  constexpr unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  for (int j = blockIdx.y * wpb + warp; j < n; j += gridDim.y * wpb) {
     const int64_t me = node[j];
     if (me <= 0) continue;
-    // branch-free scans (all lanes of a warp walk the same k): first occurrence of my node and the range of steps
-    int first = n, smin = steps[j], smax = steps[j];
-#pragma unroll 4
-    for (int k = 0; k < n; ++k) {
-      const bool hit = node[k] == me;
-      const int st = steps[k];
-      first = min(first, hit ? k : n);
-      smin = hit ? min(smin, st) : smin;
-      smax = hit ? max(smax, st) : smax;
+    int first = n, smin = INT_MAX, smax = INT_MIN;
+    for (int k0 = 0; k0 < n; k0 += 128) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int k = k0 + 32 * u + lane;
+        if (k < n && node[k] == me) {
+          const int st = steps[k];
+          first = min(first, k);
+          smin = min(smin, st);
+          smax = max(smax, st);
+        }
+      }
+      // an earlier entry owns this node: nothing more to learn from the rest of the batch
+      if (__any_sync(FULL, first < j)) break;
     }
-    if (first != j) continue;                       // another (earlier) batch entry owns this node
+    first = __reduce_min_sync(FULL, first);
+    if (first != j) continue;
+    smin = __reduce_min_sync(FULL, smin);
+    smax = __reduce_max_sync(FULL, smax);
     double acc = tree[me];
     for (int s = smin; s <= smax; ++s) {
-#pragma unroll 4
-      for (int k = j; k < n; ++k) {
-        const double dk = sd[k];
-        if (node[k] == me && steps[k] == s) acc += dk;
+      for (int k0 = j & ~127; k0 < n; k0 += 128) {         // no hit below j (j is the first occurrence)
+        unsigned m[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int k = k0 + 32 * u + lane;
+          m[u] = __ballot_sync(FULL, k < n && node[k] == me && steps[k] == s);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          unsigned mm = m[u];
+          while (mm) {
+            const int b = __ffs(mm) - 1;
+            mm &= mm - 1;
+            acc += sd[k0 + 32 * u + b];
+          }
+        }
       }
     }
-    tree[me] = acc;
+    if (lane == 0) tree[me] = acc;
   }
 }
 
@@ -456,8 +484,8 @@ RIQN_API int riqn_sumtree_update(int n, long capacity, double* tree, const long 
     RIQN_CUDA(cudaFuncSetAttribute(update_propagate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     attr_once.done[attr_dev] = true;
   }
-  const int slices = (n + 127) / 128 < 8 ? (n + 127) / 128 : 8;
-  update_propagate_kernel<<<dim3(max_depth + 1, slices), 128, smem, s>>>(n, max_depth, tree, (const int64_t*)tree_idx,
+  const int slices = (n + 63) / 64 < 8 ? (n + 63) / 64 : 8;      // 8 warps per CTA, one batch entry per warp at a time
+  update_propagate_kernel<<<dim3(max_depth + 1, slices), 256, smem, s>>>(n, max_depth, tree, (const int64_t*)tree_idx,
                                                                         diff_scratch);
   return (int)cudaGetLastError();
 }

@@ -275,3 +275,30 @@ def test_trunk_pair_equals_two_trunks(cuda_dev):
     ref = net.conv_trunk(net.to_torch(net.make_params(32)), x.cpu().float().div_(255)).numpy()
     assert rel_err(fb.cpu().numpy(), ref) < 3e-5
     assert a.trunk_pair(b_, x[:5]) is None                      # rows per network must fill whole 128-row tiles
+
+
+@pytest.mark.parametrize("R,B,A", [(8203, 1, 18), (4096, 64, 6), (16384, 512, 18)])
+def test_dueling_fwd_streamed_rows(cuda_dev, R, B, A):
+    """riqn_dueling_fwd takes the shared-memory-streamed kernel from 4096 rows up (model.py:153-156).  Same operation
+    order per output as the register kernel: bit-identical to that kernel run on < 4096-row slices (ragged tail
+    included), and equal to the float64 product within fp32 accumulation error."""
+    call, ptr = _call()
+    g = torch.Generator(device="cpu").manual_seed(R + A)
+    h = torch.randn(R, 1024, generator=g).clamp_(min=0).to(cuda_dev)
+    wz = (torch.randn(1 + A, 512, generator=g) * 0.05).to(cuda_dev)
+    bz = torch.randn(1 + A, generator=g).to(cuda_dev)
+    q = torch.full((R, A), float("nan"), device=cuda_dev)
+    call("riqn_dueling_fwd", R, B, 512, A, ptr(h), ptr(wz), ptr(bz), ptr(q))
+    h64, w64, b64 = h.double().cpu(), wz.double().cpu(), bz.double().cpu()
+    v = h64[:, :512] @ w64[0] + b64[0]
+    adv = h64[:, 512:] @ w64[1:].t() + b64[1:]
+    ref = (v[:, None] + adv - adv.mean(1, keepdim=True)).view(B, R // B, A).transpose(0, 1).reshape(R, A)   # row = q_idx*B + b
+    assert rel_err(q.cpu().numpy(), ref.numpy()) < 5e-6
+    if B == 1:      # identity row map: slices of the input are slices of the output
+        parts = []
+        for lo in range(0, R, 4000):
+            n = min(4000, R - lo)
+            qs = torch.empty(n, A, device=cuda_dev)
+            call("riqn_dueling_fwd", n, 1, 512, A, ptr(h[lo:lo + n]), ptr(wz), ptr(bz), ptr(qs))
+            parts.append(qs)
+        assert torch.equal(q, torch.cat(parts))
