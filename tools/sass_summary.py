@@ -1,6 +1,6 @@
 """SASS evidence for profiles/: per kernel of libriqn_b200.so, how many tcgen05 / TMA / TMEM instructions it contains
 (`cuobjdump -sass`; the PTX names never appear in SASS: tcgen05.mma = UTC*MMA, tcgen05.ld = LDTM, TMA load / store =
-UTMALDG / UTMASTG, tcgen05.commit = UTCBAR, TMEM alloc = UTCATOMSWS).  Usage: python tools/sass_summary.py > profiles/sass_summary.txt"""
+UTMALDG / UTMASTG, cp.async.bulk (non-tensor) = UBLKCP, tcgen05.commit = UTCBAR, TMEM alloc = UTCATOMSWS).  Usage: python tools/sass_summary.py > profiles/sass_summary.txt"""
 import collections
 import os
 import re
@@ -10,7 +10,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 lib = os.path.join(ROOT, "rainbow_iqn_apex_b200", "libriqn_b200.so")
 out = subprocess.run(["cuobjdump", "-sass", lib], stdout=subprocess.PIPE, text=True, check=True).stdout
-MNEM = ("UTCHMMA", "UTMALDG", "UTMASTG", "LDTM", "UTCBAR", "UTCATOMSWS", "HMMA", "REDG", "ATOMG")
+MNEM = ("UTCHMMA", "UTMALDG", "UTMASTG", "UBLKCP", "LDTM", "UTCBAR", "UTCATOMSWS", "HMMA", "REDG", "ATOMG")
 counts, cur = collections.OrderedDict(), None
 for line in out.splitlines():
     m = re.search(r"Function : (\S+)", line)
